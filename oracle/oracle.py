@@ -1,0 +1,268 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end to ``oracle/liboracle.so`` (harness.cpp: our restatement of the
+[EXT] call chain) driving ``oracle/_ref/*.so`` (the reference's own
+CASM-generated Clexulator kernels, compiled unmodified by ``oracle/Makefile``).
+
+May be imported ONLY from ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs.  The product
+package never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REF_DIR = HERE / "_ref"
+LIB_PATH = HERE / "liboracle.so"
+
+# name -> (shared object stem, factory symbol); the factory names are the
+# reference's own (e.g. FCC_binary_vacancy_Clexulator_default.cc:1065-1071).
+CLEXULATORS = {
+    "fcc_default": "FCC_binary_vacancy_Clexulator_default",
+    "zro": "ZrO_Clexulator_formation_energy",
+}
+for _ev in ("A_Va_1NN", "B_Va_1NN"):
+    for _k in range(6):
+        CLEXULATORS[f"fcc_{_ev}_{_k}"] = f"FCC_binary_vacancy_Clexulator_{_ev}_{_k}"
+
+
+def build(ref: bool = True) -> None:
+    """Compile the harness (always) and oracle/_ref (when /root/reference exists)."""
+    targets = ["harness"]
+    if ref and Path("/root/reference").exists():
+        targets.append("ref")
+    subprocess.run(["make", "-s", "-j8", "-C", str(HERE)] + targets, check=True)
+
+
+def available(name: str = "fcc_default") -> bool:
+    return LIB_PATH.exists() and (REF_DIR / (CLEXULATORS[name] + ".so")).exists()
+
+
+_lib = None
+
+
+class OrcStep(C.Structure):
+    _fields_ = [
+        ("l0", C.c_long),
+        ("l1", C.c_long),
+        ("new0", C.c_int),
+        ("new1", C.c_int),
+        ("accepted", C.c_int),
+        ("pad", C.c_int),
+        ("dE", C.c_double),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            build(ref=False)
+        L = C.CDLL(str(LIB_PATH))
+        L.orc_kb.restype = C.c_double
+        L.orc_open.restype = C.c_void_p
+        L.orc_open.argtypes = [C.c_char_p, C.c_char_p, C.c_long]
+        L.orc_close.argtypes = [C.c_void_p]
+        L.orc_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_nlist_cells.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_sublat_indices.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_weight_matrix.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_orbit_site_neighborhood.restype = C.c_long
+        L.orc_orbit_site_neighborhood.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        L.orc_supercell.restype = C.c_void_p
+        L.orc_supercell.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long]
+        L.orc_supercell_free.argtypes = [C.c_void_p]
+        L.orc_delta_corr.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]
+        L.orc_restricted_delta_corr.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_void_p]
+        L.orc_point_corr.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.orc_cell_corr.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.orc_global_corr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_occ_delta_value.restype = C.c_double
+        L.orc_occ_delta_value.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_long, C.c_void_p]
+        L.orc_rng_stream.argtypes = [
+            C.c_uint64, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_void_p]
+        L.orc_metropolis_run.restype = C.c_long
+        L.orc_metropolis_run.argtypes = [
+            C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+            C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long,
+            C.c_double, C.c_uint64, C.c_long, C.c_void_p, C.c_long, C.c_void_p,
+            C.c_void_p, C.c_void_p]
+        L.orc_potential_per_supercell.restype = C.c_double
+        L.orc_potential_per_supercell.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_long, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+KB = 8.6173303e-05
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RefClexulator:
+    """One of the reference's generated Clexulators, loaded from oracle/_ref."""
+
+    def __init__(self, name: str, rmax_override: int = -1):
+        stem = CLEXULATORS[name]
+        so = REF_DIR / (stem + ".so")
+        if not so.exists():
+            raise FileNotFoundError(f"{so} missing: run `make -C oracle ref` where /root/reference exists")
+        self._h = lib().orc_open(str(so).encode(), ("make_" + stem).encode(), rmax_override)
+        if not self._h:
+            raise RuntimeError("orc_open failed")
+        info = np.zeros(8, dtype=np.int64)
+        lib().orc_info(self._h, _p(info))
+        (self.nlist_size, self.corr_size, self.n_point_corr, self.n_sublat,
+         self.n_nlist_sublat, self.n_nlist_cells, self.rmax, self.n_neighborhood) = map(int, info)
+        self.cells = np.zeros((self.n_nlist_cells, 3), dtype=np.int64)
+        lib().orc_nlist_cells(self._h, _p(self.cells))
+        self.sublats = np.zeros(self.n_nlist_sublat, dtype=np.int32)
+        lib().orc_sublat_indices(self._h, _p(self.sublats))
+        self.weight_matrix = np.zeros((3, 3), dtype=np.int64)
+        lib().orc_weight_matrix(self._h, _p(self.weight_matrix))
+
+    def orbit_site_neighborhood(self, corr: int) -> np.ndarray:
+        buf = np.zeros((4096, 4), dtype=np.int64)
+        n = lib().orc_orbit_site_neighborhood(self._h, corr, _p(buf), 4096)
+        return buf[:n].copy()
+
+    def supercell(self, N) -> "RefSupercell":
+        return RefSupercell(self, N)
+
+
+class RefSupercell:
+    def __init__(self, clex: RefClexulator, N):
+        if np.isscalar(N):
+            N = (N, N, N)
+        self.clex = clex
+        self.N = tuple(int(x) for x in N)
+        self.n_cells = self.N[0] * self.N[1] * self.N[2]
+        self.n_sites = self.n_cells * clex.n_sublat
+        self._h = lib().orc_supercell(clex._h, *self.N)
+
+    def __del__(self):
+        try:
+            lib().orc_supercell_free(self._h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _occ(occ):
+        occ = np.ascontiguousarray(occ, dtype=np.int32)
+        return occ
+
+    def delta_corr(self, occ, l: int, new_occ: int) -> np.ndarray:
+        occ = self._occ(occ)
+        out = np.zeros(self.clex.corr_size)
+        lib().orc_delta_corr(self._h, _p(occ), int(l), int(new_occ), _p(out))
+        return out
+
+    def restricted_delta_corr(self, occ, l, new_occ, idx) -> np.ndarray:
+        occ = self._occ(occ)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        out = np.zeros(self.clex.corr_size)
+        lib().orc_restricted_delta_corr(self._h, _p(occ), int(l), int(new_occ), _p(idx), len(idx), _p(out))
+        return out
+
+    def point_corr(self, occ, l: int) -> np.ndarray:
+        occ = self._occ(occ)
+        out = np.zeros(self.clex.corr_size)
+        lib().orc_point_corr(self._h, _p(occ), int(l), _p(out))
+        return out
+
+    def cell_corr(self, occ, cell: int) -> np.ndarray:
+        occ = self._occ(occ)
+        out = np.zeros(self.clex.corr_size)
+        lib().orc_cell_corr(self._h, _p(occ), int(cell), _p(out))
+        return out
+
+    def global_corr(self, occ) -> np.ndarray:
+        """Correlations per supercell (sum over unit cells)."""
+        occ = self._occ(occ)
+        out = np.zeros(self.clex.corr_size)
+        lib().orc_global_corr(self._h, _p(occ), _p(out))
+        return out
+
+    def occ_delta_value(self, occ, l, new_occ, eci_idx, eci_val, return_dcorr=False):
+        occ = self._occ(occ).copy()
+        l = np.ascontiguousarray(np.atleast_1d(l), dtype=np.int64)
+        new_occ = np.ascontiguousarray(np.atleast_1d(new_occ), dtype=np.int32)
+        eci_idx = np.ascontiguousarray(eci_idx, dtype=np.uint32)
+        eci_val = np.ascontiguousarray(eci_val, dtype=np.float64)
+        dcorr = np.zeros(self.clex.corr_size)
+        e = lib().orc_occ_delta_value(self._h, _p(occ), len(l), _p(l), _p(new_occ), _p(eci_idx),
+                                      _p(eci_val), len(eci_idx), _p(dcorr))
+        return (e, dcorr) if return_dcorr else e
+
+    def metropolis_run(self, mode, occ, prim, eci_idx, eci_val, temperature, seed, n_steps,
+                       param_chem_pot=None, log_cap=0):
+        """Sequential loop.  ``prim`` = dict(sublat_to_asym, occ_to_species[n_sublat][max_occ],
+        n_species, Rt[n_param][n_species]).  Returns dict(occ, n_accept, hash, log, seconds)."""
+        occ = self._occ(occ).copy()
+        s2a = np.ascontiguousarray(prim["sublat_to_asym"], dtype=np.int32)
+        o2s = np.ascontiguousarray(prim["occ_to_species"], dtype=np.int32)
+        n_sublat, max_occ = o2s.shape
+        Rt = np.ascontiguousarray(prim.get("Rt", np.zeros((0, prim["n_species"]))), dtype=np.float64)
+        mu = np.ascontiguousarray(param_chem_pot if param_chem_pot is not None else np.zeros(0),
+                                  dtype=np.float64)
+        n_param = len(mu)
+        eci_idx = np.ascontiguousarray(eci_idx, dtype=np.uint32)
+        eci_val = np.ascontiguousarray(eci_val, dtype=np.float64)
+        log = (OrcStep * max(log_cap, 1))()
+        n_acc = C.c_long(0)
+        h = C.c_uint64(0)
+        sec = C.c_double(0)
+        rc = lib().orc_metropolis_run(
+            self._h, int(mode), _p(occ), n_sublat, _p(s2a), _p(o2s), max_occ, int(prim["n_species"]),
+            _p(mu), n_param, _p(Rt), _p(eci_idx), _p(eci_val), len(eci_idx), float(temperature),
+            int(seed), int(n_steps), C.byref(log), int(log_cap), C.byref(n_acc), C.byref(h),
+            C.byref(sec))
+        if rc != n_steps:
+            raise RuntimeError(f"orc_metropolis_run failed rc={rc}")
+        steps = [dict(l0=s.l0, l1=s.l1, new0=s.new0, new1=s.new1, accepted=s.accepted, dE=s.dE)
+                 for s in log[:min(log_cap, n_steps)]]
+        return dict(occ=occ, n_accept=n_acc.value, hash=h.value, log=steps, seconds=sec.value)
+
+    def potential_per_supercell(self, occ, prim, eci_idx, eci_val, param_chem_pot=None):
+        occ = self._occ(occ)
+        s2a = np.ascontiguousarray(prim["sublat_to_asym"], dtype=np.int32)
+        o2s = np.ascontiguousarray(prim["occ_to_species"], dtype=np.int32)
+        n_sublat, max_occ = o2s.shape
+        Rt = np.ascontiguousarray(prim.get("Rt", np.zeros((0, prim["n_species"]))), dtype=np.float64)
+        origin = np.ascontiguousarray(prim.get("origin", np.zeros(prim["n_species"])), dtype=np.float64)
+        mu = np.ascontiguousarray(param_chem_pot if param_chem_pot is not None else np.zeros(0),
+                                  dtype=np.float64)
+        eci_idx = np.ascontiguousarray(eci_idx, dtype=np.uint32)
+        eci_val = np.ascontiguousarray(eci_val, dtype=np.float64)
+        comp = np.zeros(prim["n_species"])
+        e = lib().orc_potential_per_supercell(
+            self._h, _p(occ), n_sublat, _p(s2a), _p(o2s), max_occ, int(prim["n_species"]), _p(mu),
+            len(mu), _p(Rt), _p(origin), _p(eci_idx), _p(eci_val), len(eci_idx), _p(comp))
+        return e, comp
+
+
+def rng_stream(seed: int, kinds, int_max=None, real_max=None):
+    """Replay std::mt19937_64 + libstdc++ distributions (kind 0 raw, 1 int, 2 real)."""
+    kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+    n = len(kinds)
+    int_max = np.ascontiguousarray(int_max if int_max is not None else np.zeros(n), dtype=np.int64)
+    real_max = np.ascontiguousarray(real_max if real_max is not None else np.ones(n), dtype=np.float64)
+    oi = np.zeros(n, dtype=np.int64)
+    orl = np.zeros(n, dtype=np.float64)
+    oraw = np.zeros(n, dtype=np.uint64)
+    lib().orc_rng_stream(int(seed), n, _p(int_max), _p(real_max), _p(kinds), _p(oi), _p(orl), _p(oraw))
+    return oi, orl, oraw
