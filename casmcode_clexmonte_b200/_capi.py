@@ -1,0 +1,341 @@
+"""ctypes binding of the C ABI declared in ``include/cmx_b200.h``.
+
+This is the same binding a reference-side plugin would make;
+everything above it in this package is host bookkeeping.  There is no CPU
+implementation behind these calls: if ``libcmx_b200.so`` is missing or no CUDA
+device is present, they raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .clexulator_tables import ClexulatorTables
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libcmx_b200.so"
+
+CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
+
+# every symbol include/cmx_b200.h declares
+EXPORTED_SYMBOLS = [
+    "cmx_last_error", "cmx_version", "cmx_device_count",
+    "cmx_tables_create", "cmx_tables_destroy",
+    "cmx_state_create", "cmx_state_destroy",
+    "cmx_state_upload_occ", "cmx_state_download_occ",
+    "cmx_state_upload_occ_i8", "cmx_state_download_occ_i8",
+    "cmx_state_randomize", "cmx_state_set_k_offset", "cmx_state_device_ptr",
+    "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
+    "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
+    "cmx_global_corr", "cmx_energy", "cmx_composition",
+    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sweep_info",
+    "cmx_metropolis_sequential", "cmx_rng_stream_test",
+]
+
+
+class CmxError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (the reference throws
+    std::runtime_error at the same places, e.g. CanonicalCalculator.cc:380-391)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[cmx {code}] {message}")
+        self.code = code
+
+
+class TableDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_sublat", "max_occ", "n_func", "corr_size", "n_point_corr", "nlist_len",
+        "n_nlist_sublat", "n_factors", "n_terms", "n_elems", "n_groups")] + [
+        ("nlist_sublat", C.c_void_p), ("n_occ", C.c_void_p), ("phi", C.c_void_p),
+        ("nbr", C.c_void_p), ("factor_f", C.c_void_p), ("factor_n", C.c_void_p),
+        ("term_coef", C.c_void_p), ("term_fbeg", C.c_void_p), ("elem_tbeg", C.c_void_p),
+        ("group_ebeg", C.c_void_p), ("group_dphi", C.c_void_p), ("group_has_sum", C.c_void_p),
+        ("group_div", C.c_void_p), ("global_gbeg", C.c_void_p), ("point_gbeg", C.c_void_p),
+        ("delta_gbeg", C.c_void_p)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("n_attempt", C.c_int64), ("n_accept", C.c_int64), ("dE_sum", C.c_double),
+                ("reserved", C.c_int64)]
+
+
+class StepRecord(C.Structure):
+    _fields_ = [("l0", C.c_int64), ("l1", C.c_int64), ("new0", C.c_int32), ("new1", C.c_int32),
+                ("accepted", C.c_int32), ("pad", C.c_int32), ("dE", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise CmxError(CMX_ERR_CUDA,
+                       f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                       "there is no CPU fallback")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    L.cmx_last_error.restype = C.c_char_p
+    L.cmx_tables_create.argtypes = [C.POINTER(TableDesc), C.c_int, C.POINTER(vp)]
+    L.cmx_tables_destroy.argtypes = [vp]
+    L.cmx_tables_destroy.restype = None
+    L.cmx_state_create.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(vp)]
+    L.cmx_state_destroy.argtypes = [vp]
+    L.cmx_state_destroy.restype = None
+    for f in ("cmx_state_upload_occ", "cmx_state_download_occ", "cmx_state_upload_occ_i8",
+              "cmx_state_download_occ_i8"):
+        getattr(L, f).argtypes = [vp, i32, vp]
+    L.cmx_state_randomize.argtypes = [vp, u64]
+    L.cmx_state_set_k_offset.argtypes = [vp, i32]
+    L.cmx_state_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.cmx_state_set_eci.argtypes = [vp, i32, vp, vp]
+    L.cmx_state_set_conditions.argtypes = [vp, i32, dbl, vp]
+    L.cmx_state_set_occupants.argtypes = [vp, vp, vp, i32]
+    L.cmx_delta_corr.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.cmx_point_corr.argtypes = [vp, i32, i64, vp, vp]
+    L.cmx_cell_corr.argtypes = [vp, i32, i64, vp, vp]
+    L.cmx_delta_e.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp]
+    L.cmx_global_corr.argtypes = [vp, i32, vp]
+    L.cmx_energy.argtypes = [vp, i32, C.POINTER(dbl)]
+    L.cmx_composition.argtypes = [vp, i32, vp]
+    L.cmx_sgc_sweep.argtypes = [vp, i64, u64, i64, vp]
+    L.cmx_sgc_sweep_kgroup.argtypes = [vp, u64, i64, i32, vp]
+    L.cmx_sweep_info.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(dbl), C.POINTER(dbl),
+                                 C.POINTER(i32)]
+    L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
+                                            C.POINTER(u64)]
+    L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != CMX_OK:
+        raise CmxError(rc, lib().cmx_last_error().decode())
+
+
+def device_count() -> int:
+    return int(lib().cmx_device_count())
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Tables:
+    """Device copy of one basis set (``cmx_tables``)."""
+
+    def __init__(self, t: ClexulatorTables, device: int = 0):
+        self.host = t
+        keep = {}
+
+        def arr(name, dtype):
+            a = np.ascontiguousarray(getattr(t, name), dtype=dtype)
+            keep[name] = a
+            return _p(a)
+
+        d = TableDesc()
+        d.n_sublat, d.max_occ, d.n_func = t.n_sublat, t.max_occ, t.n_func
+        d.corr_size, d.n_point_corr = t.corr_size, t.n_point_corr
+        d.nlist_len, d.n_nlist_sublat = t.nlist_len, t.n_nlist_sublat
+        d.n_factors, d.n_terms = len(t.factor_f), len(t.term_coef)
+        d.n_elems, d.n_groups = len(t.elem_tbeg) - 1, len(t.group_div)
+        for name in ("nlist_sublat", "n_occ", "nbr", "factor_f", "factor_n", "term_fbeg",
+                     "elem_tbeg", "group_ebeg", "group_dphi", "group_has_sum", "global_gbeg",
+                     "point_gbeg", "delta_gbeg"):
+            setattr(d, name, arr(name, np.int32))
+        for name in ("phi", "term_coef", "group_div"):
+            setattr(d, name, arr(name, np.float64))
+        self._h = C.c_void_p()
+        check(lib().cmx_tables_create(C.byref(d), device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cmx_tables_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class State:
+    """Device-resident supercell(s) (``cmx_state``)."""
+
+    def __init__(self, tables: Tables, N: Sequence[int], n_replicas: int = 1, halo: int = 0):
+        if np.isscalar(N):
+            N = (N, N, N)
+        self.tables = tables
+        self.N = tuple(int(x) for x in N)
+        self.n_replicas = int(n_replicas)
+        self.halo = int(halo)
+        t = tables.host
+        self.n_cells = self.N[0] * self.N[1] * self.N[2]
+        self.n_sites = self.n_cells * t.n_sublat
+        self._h = C.c_void_p()
+        check(lib().cmx_state_create(tables._h, *self.N, self.n_replicas, self.halo, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cmx_state_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- data movement ------------------------------------------------------
+    def upload_occ(self, occ: np.ndarray, replica: int = 0) -> None:
+        if occ.dtype == np.int8:
+            occ = np.ascontiguousarray(occ)
+            fn = lib().cmx_state_upload_occ_i8
+        else:
+            occ = np.ascontiguousarray(occ, dtype=np.int32)
+            fn = lib().cmx_state_upload_occ
+        if occ.size != self.n_sites:
+            raise CmxError(CMX_ERR_INVALID, f"occupation has {occ.size} sites, expected {self.n_sites}")
+        check(fn(self._h, replica, _p(occ)))
+
+    def download_occ(self, replica: int = 0, dtype=np.int32, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.n_sites, dtype=dtype)
+        fn = lib().cmx_state_download_occ_i8 if out.dtype == np.int8 else lib().cmx_state_download_occ
+        check(fn(self._h, replica, _p(out)))
+        return out
+
+    def randomize(self, seed: int) -> None:
+        check(lib().cmx_state_randomize(self._h, int(seed)))
+
+    def set_k_offset(self, k_offset: int) -> None:
+        check(lib().cmx_state_set_k_offset(self._h, int(k_offset)))
+
+    def device_ptr(self):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        check(lib().cmx_state_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # -- model --------------------------------------------------------------
+    def set_eci(self, index, value) -> None:
+        index = np.ascontiguousarray(index, dtype=np.uint32)
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        if index.shape != value.shape:
+            raise CmxError(CMX_ERR_INVALID, "ECI index/value length mismatch")
+        self.eci_index, self.eci_value = index, value
+        check(lib().cmx_state_set_eci(self._h, len(index), _p(index), _p(value)))
+
+    def set_conditions(self, temperature: float, exch: Optional[np.ndarray] = None, replica: int = 0) -> None:
+        t = self.tables.host
+        if exch is not None:
+            exch = np.ascontiguousarray(exch, dtype=np.float64)
+            if exch.size != t.n_sublat * t.max_occ * t.max_occ:
+                raise CmxError(CMX_ERR_INVALID, "exch must have n_sublat*max_occ*max_occ entries")
+        check(lib().cmx_state_set_conditions(self._h, replica, float(temperature), _p(exch)))
+
+    def set_occupants(self, sublat_to_asym, occ_to_species, n_species: int) -> None:
+        s2a = np.ascontiguousarray(sublat_to_asym, dtype=np.int32)
+        o2s = np.ascontiguousarray(occ_to_species, dtype=np.int32)
+        check(lib().cmx_state_set_occupants(self._h, _p(s2a), _p(o2s), int(n_species)))
+
+    # -- potential / correlations ------------------------------------------
+    def delta_corr(self, l, new_occ, replica: int = 0) -> np.ndarray:
+        l = np.ascontiguousarray(np.atleast_1d(l), dtype=np.int64)
+        new_occ = np.ascontiguousarray(np.atleast_1d(new_occ), dtype=np.int32)
+        out = np.zeros((len(l), self.tables.host.corr_size))
+        check(lib().cmx_delta_corr(self._h, replica, len(l), _p(l), _p(new_occ), _p(out)))
+        return out
+
+    def point_corr(self, l, replica: int = 0) -> np.ndarray:
+        l = np.ascontiguousarray(np.atleast_1d(l), dtype=np.int64)
+        out = np.zeros((len(l), self.tables.host.corr_size))
+        check(lib().cmx_point_corr(self._h, replica, len(l), _p(l), _p(out)))
+        return out
+
+    def cell_corr(self, cells, replica: int = 0) -> np.ndarray:
+        cells = np.ascontiguousarray(np.atleast_1d(cells), dtype=np.int64)
+        out = np.zeros((len(cells), self.tables.host.corr_size))
+        check(lib().cmx_cell_corr(self._h, replica, len(cells), _p(cells), _p(out)))
+        return out
+
+    def delta_e(self, l, new_occ, sites_per_event: int = 1, potential: bool = False,
+                replica: int = 0) -> np.ndarray:
+        l = np.ascontiguousarray(l, dtype=np.int64).reshape(-1)
+        new_occ = np.ascontiguousarray(new_occ, dtype=np.int32).reshape(-1)
+        if len(l) != len(new_occ) or len(l) % sites_per_event:
+            raise CmxError(CMX_ERR_INVALID, "l/new_occ shape mismatch")
+        n = len(l) // sites_per_event
+        out = np.zeros(n)
+        check(lib().cmx_delta_e(self._h, replica, n, sites_per_event, _p(l), _p(new_occ),
+                                1 if potential else 0, _p(out)))
+        return out
+
+    def global_corr(self, replica: int = 0) -> np.ndarray:
+        out = np.zeros(self.tables.host.corr_size)
+        check(lib().cmx_global_corr(self._h, replica, _p(out)))
+        return out
+
+    def energy(self, replica: int = 0) -> float:
+        e = C.c_double()
+        check(lib().cmx_energy(self._h, replica, C.byref(e)))
+        return e.value
+
+    def composition(self, replica: int = 0) -> np.ndarray:
+        t = self.tables.host
+        out = np.zeros((t.n_sublat, t.max_occ), dtype=np.int64)
+        check(lib().cmx_composition(self._h, replica, _p(out)))
+        return out
+
+    # -- drivers --------------------------------------------------------------
+    def sgc_sweep(self, n_sweeps: int, seed: int, first_sweep: int = 0, counters: bool = True):
+        cnt = (Counters * self.n_replicas)() if counters else None
+        check(lib().cmx_sgc_sweep(self._h, int(n_sweeps), int(seed), int(first_sweep),
+                                  C.byref(cnt) if counters else None))
+        return cnt
+
+    def sgc_sweep_kgroup(self, seed: int, sweep: int, kgroup: int, counters: bool = False):
+        cnt = (Counters * self.n_replicas)() if counters else None
+        check(lib().cmx_sgc_sweep_kgroup(self._h, int(seed), int(sweep), int(kgroup),
+                                         C.byref(cnt) if counters else None))
+        return cnt
+
+    def sweep_info(self) -> dict:
+        name = C.create_string_buffer(32)
+        b, f, nc = C.c_double(), C.c_double(), C.c_int32()
+        check(lib().cmx_sweep_info(self._h, name, 32, C.byref(b), C.byref(f), C.byref(nc)))
+        return dict(evaluator=name.value.decode(), bytes_per_step=b.value, flops_per_step=f.value,
+                    n_colours=nc.value)
+
+    def metropolis_sequential(self, mode: int, n_steps: int, seed: int, log_cap: int = 0,
+                              replica: int = 0) -> dict:
+        log = (StepRecord * max(1, log_cap))()
+        n_acc = C.c_int64()
+        h = C.c_uint64()
+        check(lib().cmx_metropolis_sequential(self._h, replica, int(mode), int(n_steps), int(seed),
+                                              C.byref(log), int(log_cap), C.byref(n_acc), C.byref(h)))
+        steps = [dict(l0=s.l0, l1=s.l1, new0=s.new0, new1=s.new1, accepted=s.accepted, dE=s.dE)
+                 for s in log[:min(log_cap, n_steps)]]
+        return dict(n_accept=n_acc.value, hash=h.value, log=steps)
+
+
+def rng_stream_test(seed: int, kinds, int_max=None, real_max=None):
+    kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+    n = len(kinds)
+    int_max = np.ascontiguousarray(int_max if int_max is not None else np.zeros(n), dtype=np.int64)
+    real_max = np.ascontiguousarray(real_max if real_max is not None else np.ones(n), dtype=np.float64)
+    oi = np.zeros(n, dtype=np.int64)
+    orl = np.zeros(n, dtype=np.float64)
+    oraw = np.zeros(n, dtype=np.uint64)
+    check(lib().cmx_rng_stream_test(int(seed), n, _p(int_max), _p(real_max), _p(kinds), _p(oi),
+                                    _p(orl), _p(oraw)))
+    return oi, orl, oraw

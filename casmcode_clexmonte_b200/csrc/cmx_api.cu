@@ -1,0 +1,393 @@
+// C ABI: handles, tables, state, host<->device movement.
+#include <cstring>
+
+#include "cmx_internal.cuh"
+
+static thread_local std::string g_last_error;
+
+void cmx_set_error(const std::string &msg) { g_last_error = msg; }
+
+int cmx_cuda_fail(cudaError_t e, const char *what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return CMX_ERR_CUDA;
+}
+
+static int invalid(const std::string &msg) {
+  cmx_set_error(msg);
+  return CMX_ERR_INVALID;
+}
+
+extern "C" const char *cmx_last_error(void) { return g_last_error.c_str(); }
+extern "C" int cmx_version(void) { return 100; }
+extern "C" int cmx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+template <typename T>
+static int upload(cmx_tables *t, const T *src, size_t n, const T **dst,
+                  std::vector<T> *host) {
+  if (host) host->assign(src, src + n);
+  void *p = nullptr;
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  CMX_CUDA(cudaMalloc(&p, bytes));
+  t->allocs.push_back(p);
+  if (n) CMX_CUDA(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = static_cast<const T *>(p);
+  return CMX_OK;
+}
+
+extern "C" int cmx_tables_create(const cmx_table_desc *d, int device,
+                                 cmx_tables **out) {
+  if (!d || !out) return invalid("cmx_tables_create: null argument");
+  if (d->n_sublat <= 0 || d->max_occ <= 0 || d->n_func <= 0 ||
+      d->corr_size <= 0 || d->nlist_len <= 0 || d->n_point_corr <= 0)
+    return invalid("cmx_tables_create: non-positive size");
+  if (d->max_occ > 8) return invalid("cmx_tables_create: max_occ > 8 unsupported");
+  // structural validation of the CSR
+  for (int i = 0; i < d->n_terms; ++i)
+    if (d->term_fbeg[i] > d->term_fbeg[i + 1])
+      return invalid("cmx_tables_create: term_fbeg not monotone");
+  if (d->term_fbeg[d->n_terms] != d->n_factors ||
+      d->elem_tbeg[d->n_elems] != d->n_terms ||
+      d->group_ebeg[d->n_groups] != d->n_elems)
+    return invalid("cmx_tables_create: CSR sizes inconsistent");
+  for (int i = 0; i < d->n_factors; ++i) {
+    if (d->factor_n[i] < 0 || d->factor_n[i] >= d->nlist_len)
+      return invalid("cmx_tables_create: factor neighbor index out of range");
+    if (d->factor_f[i] < 0 || d->factor_f[i] >= d->n_func)
+      return invalid("cmx_tables_create: factor function index out of range");
+  }
+  for (int i = 0; i < d->nlist_len; ++i) {
+    int b = d->nbr[4 * i + 3];
+    if (b < 0 || b >= d->n_sublat)
+      return invalid("cmx_tables_create: neighbor sublattice out of range");
+  }
+  if (d->global_gbeg[d->corr_size] > d->n_groups ||
+      d->delta_gbeg[d->n_point_corr * d->corr_size] > d->n_groups)
+    return invalid("cmx_tables_create: function table out of range");
+  if (cmx_device_count() == 0) {
+    cmx_set_error("cmx_tables_create: no CUDA device (there is no CPU path)");
+    return CMX_ERR_CUDA;
+  }
+  CMX_CUDA(cudaSetDevice(device));
+  cmx_tables *t = new cmx_tables;
+  t->device = device;
+  DevTables &D = t->d;
+  D.n_sublat = d->n_sublat;
+  D.max_occ = d->max_occ;
+  D.n_func = d->n_func;
+  D.corr_size = d->corr_size;
+  D.n_point_corr = d->n_point_corr;
+  D.nlist_len = d->nlist_len;
+  D.n_nlist_sublat = d->n_nlist_sublat;
+  int rc = CMX_OK;
+  const int32_t *nbr_dev = nullptr;
+#define UP(field, n, host)                                               \
+  if (rc == CMX_OK) rc = upload(t, d->field, (size_t)(n), &D.field, host)
+  UP(nlist_sublat, d->n_nlist_sublat, &t->nlist_sublat);
+  UP(n_occ, d->n_sublat, &t->n_occ);
+  UP(phi, (size_t)d->n_sublat * d->n_func * d->max_occ, &t->phi);
+  if (rc == CMX_OK)
+    rc = upload(t, d->nbr, (size_t)d->nlist_len * 4, &nbr_dev, &t->nbr);
+  D.nbr = reinterpret_cast<const int4 *>(nbr_dev);
+  UP(factor_f, d->n_factors, &t->factor_f);
+  UP(factor_n, d->n_factors, &t->factor_n);
+  UP(term_coef, d->n_terms, &t->term_coef);
+  UP(term_fbeg, d->n_terms + 1, &t->term_fbeg);
+  UP(elem_tbeg, d->n_elems + 1, &t->elem_tbeg);
+  UP(group_ebeg, d->n_groups + 1, &t->group_ebeg);
+  UP(group_dphi, d->n_groups, &t->group_dphi);
+  UP(group_has_sum, d->n_groups, &t->group_has_sum);
+  UP(group_div, d->n_groups, &t->group_div);
+  UP(global_gbeg, d->corr_size + 1, &t->global_gbeg);
+  UP(point_gbeg, d->n_point_corr * d->corr_size + 1, &t->point_gbeg);
+  UP(delta_gbeg, d->n_point_corr * d->corr_size + 1, &t->delta_gbeg);
+#undef UP
+  if (rc != CMX_OK) {
+    cmx_tables_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return CMX_OK;
+}
+
+extern "C" void cmx_tables_destroy(cmx_tables *t) {
+  if (!t) return;
+  for (void *p : t->allocs) cudaFree(p);
+  delete t;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
+                                int32_t N2, int32_t n_replicas, int32_t halo,
+                                cmx_state **out) {
+  if (!t || !out) return invalid("cmx_state_create: null argument");
+  if (N0 <= 0 || N1 <= 0 || N2 <= 0 || n_replicas <= 0 || halo < 0)
+    return invalid("cmx_state_create: non-positive dimension");
+  // the neighbor arithmetic wraps once: every |offset| must be <= N
+  for (int n = 0; n < t->d.nlist_len; ++n) {
+    const int32_t *o = &t->nbr[4 * n];
+    if (std::abs(o[0]) > N0 || std::abs(o[1]) > N1 ||
+        (!halo && std::abs(o[2]) > N2))
+      return invalid("cmx_state_create: supercell smaller than the neighbor list range");
+  }
+  CMX_CUDA(cudaSetDevice(t->device));
+  cmx_state *s = new cmx_state;
+  s->t = t;
+  s->n_replicas = n_replicas;
+  Geom &g = s->g;
+  g.N0 = N0;
+  g.N1 = N1;
+  g.N2 = N2;
+  g.halo = halo;
+  g.layer = (int64_t)N0 * N1;
+  g.n_cells = g.layer * N2;
+  g.sub_stride = g.layer * (N2 + 2 * halo);
+  g.rep_stride = g.sub_stride * t->d.n_sublat;
+  size_t bytes = (size_t)g.rep_stride * n_replicas;
+  cudaError_t e = cudaMalloc(&s->d_occ, bytes);
+  if (e != cudaSuccess) {
+    delete s;
+    return cmx_cuda_fail(e, "cudaMalloc(occupation)");
+  }
+  cudaMemset(s->d_occ, 0, bytes);
+  s->temperature.assign(n_replicas, 0.0);
+  size_t ex = (size_t)t->d.n_sublat * t->d.max_occ * t->d.max_occ;
+  s->exch.assign(ex * n_replicas, 0.0);
+  cudaMalloc(&s->d_beta, sizeof(double) * n_replicas);
+  cudaMalloc(&s->d_exch, sizeof(double) * ex * n_replicas);
+  cudaMemset(s->d_beta, 0, sizeof(double) * n_replicas);
+  cudaMemset(s->d_exch, 0, sizeof(double) * ex * n_replicas);
+  cudaMalloc(&s->d_counters, sizeof(cmx_counters) * n_replicas);
+  cudaMemset(s->d_counters, 0, sizeof(cmx_counters) * n_replicas);
+  cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cmx_state_destroy(s);
+    return cmx_cuda_fail(e, "cmx_state_create");
+  }
+  *out = s;
+  return CMX_OK;
+}
+
+extern "C" void cmx_state_destroy(cmx_state *s) {
+  if (!s) return;
+  cudaSetDevice(s->t->device);
+  cmx_plan_free(s->plan);
+  cudaFree(s->d_occ);
+  cudaFree(s->d_eci_idx);
+  cudaFree(s->d_eci_val);
+  cudaFree(s->d_beta);
+  cudaFree(s->d_exch);
+  cudaFree(s->d_counters);
+  cudaFree(s->d_scratch);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int cmx_scratch(cmx_state *s, size_t bytes) {
+  if (bytes <= s->scratch_bytes) return CMX_OK;
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  cudaFree(s->d_scratch);
+  s->d_scratch = nullptr;
+  s->scratch_bytes = 0;
+  CMX_CUDA(cudaMalloc(&s->d_scratch, bytes));
+  s->scratch_bytes = bytes;
+  return CMX_OK;
+}
+
+// reference layout (no ghost layers, int32 or int8) <-> device layout (int8)
+template <typename SrcT>
+__global__ void k_scatter_occ(const SrcT *__restrict__ src, int8_t *dst, Geom g,
+                              int n_sublat) {
+  int64_t total = g.n_cells * n_sublat;
+  for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < total;
+       l += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
+    dst[b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)src[l];
+  }
+}
+template <typename DstT>
+__global__ void k_gather_occ(const int8_t *__restrict__ src, DstT *dst, Geom g,
+                             int n_sublat) {
+  int64_t total = g.n_cells * n_sublat;
+  for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < total;
+       l += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
+    dst[l] = (DstT)src[b * g.sub_stride + g.halo * g.layer + cell];
+  }
+}
+
+static int check_replica(const cmx_state *s, int32_t r, const char *who) {
+  if (!s) return invalid(std::string(who) + ": null state");
+  if (r < 0 || r >= s->n_replicas)
+    return invalid(std::string(who) + ": replica out of range");
+  return CMX_OK;
+}
+
+template <typename T>
+static int upload_occ(cmx_state *s, int32_t replica, const T *occ) {
+  int rc = check_replica(s, replica, "cmx_state_upload_occ");
+  if (rc) return rc;
+  if (!occ) return invalid("cmx_state_upload_occ: null occupation");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
+  // validate on the host: a bad occupant index would read outside phi
+  for (size_t l = 0; l < n; ++l) {
+    int b = (int)(l / s->g.n_cells);
+    if (occ[l] < 0 || occ[l] >= s->t->n_occ[b])
+      return invalid("cmx_state_upload_occ: occupant index out of range");
+  }
+  rc = cmx_scratch(s, n * sizeof(T));
+  if (rc) return rc;
+  CMX_CUDA(cudaMemcpyAsync(s->d_scratch, occ, n * sizeof(T),
+                           cudaMemcpyHostToDevice, s->stream));
+  int8_t *dst = s->d_occ + (size_t)replica * s->g.rep_stride;
+  k_scatter_occ<T><<<1184, 256, 0, s->stream>>>((const T *)s->d_scratch, dst,
+                                                s->g, s->t->d.n_sublat);
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  return CMX_OK;
+}
+
+template <typename T>
+static int download_occ(const cmx_state *cs, int32_t replica, T *occ) {
+  cmx_state *s = const_cast<cmx_state *>(cs);
+  int rc = check_replica(s, replica, "cmx_state_download_occ");
+  if (rc) return rc;
+  if (!occ) return invalid("cmx_state_download_occ: null occupation");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
+  rc = cmx_scratch(s, n * sizeof(T));
+  if (rc) return rc;
+  const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
+  k_gather_occ<T><<<1184, 256, 0, s->stream>>>(src, (T *)s->d_scratch, s->g,
+                                               s->t->d.n_sublat);
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaMemcpyAsync(occ, s->d_scratch, n * sizeof(T),
+                           cudaMemcpyDeviceToHost, s->stream));
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_upload_occ(cmx_state *s, int32_t r, const int32_t *o) {
+  return upload_occ<int32_t>(s, r, o);
+}
+extern "C" int cmx_state_upload_occ_i8(cmx_state *s, int32_t r, const int8_t *o) {
+  return upload_occ<int8_t>(s, r, o);
+}
+extern "C" int cmx_state_download_occ(const cmx_state *s, int32_t r, int32_t *o) {
+  return download_occ<int32_t>(s, r, o);
+}
+extern "C" int cmx_state_download_occ_i8(const cmx_state *s, int32_t r, int8_t *o) {
+  return download_occ<int8_t>(s, r, o);
+}
+
+// i.i.d. uniform occupation; counter = (site, replica), key = seed
+__global__ void k_randomize(int8_t *occ, Geom g, int n_sublat, int n_replicas,
+                            const int32_t *__restrict__ n_occ, uint32_t k0,
+                            uint32_t k1) {
+  int64_t per = g.n_cells * n_sublat;
+  int64_t total = per * n_replicas;
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < total;
+       x += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = x / per, l = x - r * per;
+    int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
+    int no = n_occ[b];
+    int v = 0;
+    if (no > 1) {
+      Philox p = philox4x32_10((uint32_t)l, (uint32_t)(l >> 32), (uint32_t)r,
+                               0x52414e44u, k0, k1);
+      v = (int)__umulhi(p.c[0], (uint32_t)no);
+    }
+    occ[r * g.rep_stride + b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)v;
+  }
+}
+
+extern "C" int cmx_state_randomize(cmx_state *s, uint64_t seed) {
+  if (!s) return invalid("cmx_state_randomize: null state");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  k_randomize<<<1184, 256, 0, s->stream>>>(s->d_occ, s->g, s->t->d.n_sublat,
+                                           s->n_replicas, s->t->d.n_occ,
+                                           (uint32_t)seed, (uint32_t)(seed >> 32));
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_set_k_offset(cmx_state *s, int32_t k_offset) {
+  if (!s || k_offset < 0) return invalid("cmx_state_set_k_offset: bad argument");
+  s->k_offset = k_offset;
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_device_ptr(cmx_state *s, void **d_ptr, size_t *n_bytes) {
+  if (!s || !d_ptr) return invalid("cmx_state_device_ptr: null argument");
+  *d_ptr = s->d_occ;
+  if (n_bytes) *n_bytes = (size_t)s->g.rep_stride * s->n_replicas;
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_set_eci(cmx_state *s, int32_t n, const uint32_t *index,
+                                 const double *value) {
+  if (!s || n < 0 || (n && (!index || !value)))
+    return invalid("cmx_state_set_eci: bad argument");
+  for (int i = 0; i < n; ++i)
+    if (index[i] >= (uint32_t)s->t->d.corr_size)
+      return invalid("cmx_state_set_eci: coefficient index out of range");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  cudaFree(s->d_eci_idx);
+  cudaFree(s->d_eci_val);
+  s->d_eci_idx = nullptr;
+  s->d_eci_val = nullptr;
+  s->n_eci = n;
+  s->eci_idx.assign(index, index + n);
+  s->eci_val.assign(value, value + n);
+  CMX_CUDA(cudaMalloc(&s->d_eci_idx, sizeof(uint32_t) * (n ? n : 1)));
+  CMX_CUDA(cudaMalloc(&s->d_eci_val, sizeof(double) * (n ? n : 1)));
+  if (n) {
+    CMX_CUDA(cudaMemcpy(s->d_eci_idx, index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    CMX_CUDA(cudaMemcpy(s->d_eci_val, value, sizeof(double) * n, cudaMemcpyHostToDevice));
+  }
+  return cmx_plan_sweep(s);
+}
+
+extern "C" int cmx_state_set_conditions(cmx_state *s, int32_t replica,
+                                        double temperature, const double *exch) {
+  int rc = check_replica(s, replica, "cmx_state_set_conditions");
+  if (rc) return rc;
+  if (!(temperature > 0.0)) return invalid("cmx_state_set_conditions: temperature must be > 0");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  size_t ex = (size_t)s->t->d.n_sublat * s->t->d.max_occ * s->t->d.max_occ;
+  s->temperature[replica] = temperature;
+  double beta = 1.0 / (CMX_KB * temperature);
+  for (size_t i = 0; i < ex; ++i) s->exch[replica * ex + i] = exch ? exch[i] : 0.0;
+  CMX_CUDA(cudaMemcpy(s->d_beta + replica, &beta, sizeof(double), cudaMemcpyHostToDevice));
+  CMX_CUDA(cudaMemcpy(s->d_exch + replica * ex, &s->exch[replica * ex],
+                      sizeof(double) * ex, cudaMemcpyHostToDevice));
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_set_occupants(cmx_state *s, const int32_t *sublat_to_asym,
+                                       const int32_t *occ_to_species,
+                                       int32_t n_species) {
+  if (!s || !sublat_to_asym || !occ_to_species || n_species <= 0)
+    return invalid("cmx_state_set_occupants: bad argument");
+  int nb = s->t->d.n_sublat, mo = s->t->d.max_occ;
+  for (int b = 0; b < nb; ++b) {
+    if (sublat_to_asym[b] < 0 || sublat_to_asym[b] >= nb)
+      return invalid("cmx_state_set_occupants: asym index out of range");
+    for (int o = 0; o < s->t->n_occ[b]; ++o)
+      if (occ_to_species[b * mo + o] < 0 || occ_to_species[b * mo + o] >= n_species)
+        return invalid("cmx_state_set_occupants: species index out of range");
+  }
+  s->sublat_to_asym.assign(sublat_to_asym, sublat_to_asym + nb);
+  s->occ_to_species.assign(occ_to_species, occ_to_species + (size_t)nb * mo);
+  s->n_species = n_species;
+  return CMX_OK;
+}

@@ -1,0 +1,279 @@
+// Internal definitions shared by the sm_100a translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "cmx_b200.h"
+
+// CASM::KB [eV/K] -- the constant behind `beta = 1.0 / (CASM::KB * temperature)`
+// (include/casm/clexmonte/methods/occupation_metropolis.hh:86); value pinned by
+// the documented event state python/libcasm/clexmonte/_MonteCalculator.py:186-199.
+#define CMX_KB 8.6173303e-05
+
+void cmx_set_error(const std::string &msg);
+int cmx_cuda_fail(cudaError_t e, const char *what);
+
+#define CMX_CUDA(call)                                  \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return cmx_cuda_fail(_e, #call); \
+  } while (0)
+
+// Device view of one basis set (all pointers are device pointers).
+struct DevTables {
+  int32_t n_sublat, max_occ, n_func, corr_size, n_point_corr, nlist_len,
+      n_nlist_sublat;
+  const int32_t *nlist_sublat;
+  const int32_t *n_occ;
+  const double *phi;
+  const int4 *nbr;  // (di, dj, dk, b)
+  const int32_t *factor_f, *factor_n;
+  const double *term_coef;
+  const int32_t *term_fbeg, *elem_tbeg, *group_ebeg, *group_dphi,
+      *group_has_sum;
+  const double *group_div;
+  const int32_t *global_gbeg, *point_gbeg, *delta_gbeg;
+};
+
+// Geometry of a (slab of a) supercell.
+struct Geom {
+  int32_t N0, N1, N2;  // local box (N2 = owned layers)
+  int32_t halo;        // ghost layers on each k side (0 = periodic in k)
+  int64_t n_cells;     // N0*N1*N2 (owned)
+  int64_t layer;       // N0*N1
+  int64_t sub_stride;  // bytes between sublattices: N0*N1*(N2+2*halo)
+  int64_t rep_stride;  // bytes between replicas:   n_sublat*sub_stride
+};
+
+struct cmx_tables {
+  int device;
+  DevTables d;               // device pointers
+  std::vector<void *> allocs;  // for cleanup
+  // host copies used when binding ECI / planning sweeps
+  std::vector<int32_t> nlist_sublat, n_occ, nbr, factor_f, factor_n, term_fbeg,
+      elem_tbeg, group_ebeg, group_dphi, group_has_sum, global_gbeg, point_gbeg,
+      delta_gbeg;
+  std::vector<double> phi, term_coef, group_div;
+};
+
+// ---- checkerboard sweep plan (built by cmx_plan_sweep, see cmx_sweep.cu) ----
+struct SweepPlan {
+  bool valid = false;     // sweeps possible (global clexulator + ECI bound)
+  bool pair_lut = false;  // pair-count LUT fast path usable
+  int32_t S[3] = {1, 1, 1};  // colour strides along i, j, k
+  int32_t n_colours = 0;
+  int32_t range_k = 0;  // max |dk| over active neighbors (halo depth needed)
+  std::vector<int32_t> mut_points;  // point positions with > 1 occupant
+  // generic evaluator: ECI-folded, merged delta terms per point position
+  int32_t n_gterms = 0;
+  int32_t *d_gt_beg = nullptr;   // [n_point+1]
+  double *d_gt_w = nullptr;      // [n_gterms][max_occ][max_occ]
+  int32_t *d_gt_fbeg = nullptr;  // [n_gterms+1]
+  int32_t *d_gt_f = nullptr, *d_gt_n = nullptr;
+  // pair LUT: one sublattice, <= 3 occupants, offsets in {-1,0,1}^3,
+  // one class of symmetry-equivalent neighbors
+  int32_t nocc = 0;
+  int32_t z = 0;          // neighbors in the class
+  uint32_t mask = 0;      // bit (dk+1)*9 + (dj+1)*3 + (di+1)
+  int32_t n_lut = 0;      // nocc*(nocc-1)*256 entries
+  double *d_pair_dE = nullptr;       // [n_lut] clex dE per (oi, alt, counts)
+  unsigned long long *d_thr = nullptr;  // [replica][n_lut] acceptance thresholds
+  double *d_dEpot = nullptr;            // [replica][n_lut] dE - exch
+  bool thr_dirty = true;
+  // per-block partial counters of the current call
+  long long *d_part_acc = nullptr;
+  double *d_part_dE = nullptr;
+  int32_t part_blocks = 0;
+  // algorithmic work per attempted step, counted from the tables
+  double bytes_per_step = 0, flops_per_step = 0;
+};
+
+struct cmx_state {
+  const cmx_tables *t;
+  Geom g;
+  int32_t n_replicas;
+  int32_t k_offset = 0;  // global k of local layer 0 (slab decomposition)
+  int8_t *d_occ = nullptr;  // [replica][sublat][k(+halo)][j][i]
+  // ECI
+  int32_t n_eci = 0;
+  uint32_t *d_eci_idx = nullptr;
+  double *d_eci_val = nullptr;
+  std::vector<uint32_t> eci_idx;
+  std::vector<double> eci_val;
+  // conditions
+  std::vector<double> temperature;  // [replica]
+  double *d_beta = nullptr;         // [replica]
+  double *d_exch = nullptr;         // [replica][n_sublat][max_occ][max_occ]
+  std::vector<double> exch;
+  // occupants (sequential mode)
+  std::vector<int32_t> sublat_to_asym, occ_to_species;
+  int32_t n_species = 0;
+  // sweeps
+  SweepPlan plan;
+  cmx_counters *d_counters = nullptr;  // [replica]
+  // scratch
+  void *d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  cudaStream_t stream = nullptr;
+};
+
+int cmx_scratch(cmx_state *s, size_t bytes);
+int cmx_plan_sweep(cmx_state *s);
+void cmx_plan_free(SweepPlan &p);
+
+// ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ int cmx_wrap(int x, int n) {
+  // x in [-n, 2n)
+  x += (x < 0) ? n : 0;
+  x -= (x >= n) ? n : 0;
+  return x;
+}
+
+// byte offset of site (b; i,j,k) inside one replica
+__device__ __forceinline__ int64_t cmx_site_offset(const Geom &g, int b, int i,
+                                                   int j, int k) {
+  return (int64_t)b * g.sub_stride + (int64_t)(k + g.halo) * g.layer +
+         (int64_t)j * g.N0 + i;
+}
+
+// neighbor n of cell (i,j,k): byte offset + linear reference index l
+__device__ __forceinline__ int64_t cmx_nbr_offset(const DevTables &T,
+                                                  const Geom &g, int n, int i,
+                                                  int j, int k, int64_t *l) {
+  int4 o = T.nbr[n];
+  int ii = cmx_wrap(i + o.x, g.N0);
+  int jj = cmx_wrap(j + o.y, g.N1);
+  int kk = g.halo ? (k + o.z) : cmx_wrap(k + o.z, g.N2);
+  if (l) {
+    int kw = cmx_wrap(kk, g.N2);
+    *l = (int64_t)o.w * g.n_cells + ((int64_t)kw * g.N1 + jj) * g.N0 + ii;
+  }
+  return cmx_site_offset(g, o.w, ii, jj, kk);
+}
+
+// Temporary occupant overrides (multi-site events are evaluated sequentially
+// against a configuration in which the earlier sites already changed).
+struct Override {
+  int n;
+  int64_t off[4];
+  int occ[4];
+};
+
+__device__ __forceinline__ int cmx_load_occ(const int8_t *occ, int64_t off,
+                                            const Override &ov) {
+  int v = occ[off];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q < ov.n && ov.off[q] == off) v = ov.occ[q];
+  return v;
+}
+
+// Occupant fetchers for the evaluator below.
+struct LatticeFetch {
+  const DevTables &T;
+  const Geom &g;
+  const int8_t *occ;
+  int i, j, k;
+  const Override &ov;
+  __device__ __forceinline__ int operator()(int n) const {
+    int64_t off = cmx_nbr_offset(T, g, n, i, j, k, nullptr);
+    return cmx_load_occ(occ, off, ov);
+  }
+};
+struct LocalFetch {  // synthetic neighborhood (LUT construction)
+  const int8_t *nbr_occ;
+  __device__ __forceinline__ int operator()(int n) const { return nbr_occ[n]; }
+};
+
+// Faithful evaluation of one generated function (see clexulator_tables.py for
+// the canonical form): same association order as the C++ source, every
+// operation individually rounded (no FMA contraction).
+template <class Fetch>
+__device__ inline double cmx_eval_function_t(const DevTables &T, int gbeg,
+                                             int gend, const Fetch &fetch,
+                                             int pb, int occ_i, int occ_f) {
+  double total = 0.0;
+  bool have_total = false;
+  for (int gi = gbeg; gi < gend; ++gi) {
+    double s = 0.0;
+    bool has_sum = T.group_has_sum[gi] != 0;
+    if (has_sum) {
+      bool have_s = false;
+      for (int e = T.group_ebeg[gi]; e < T.group_ebeg[gi + 1]; ++e) {
+        double ev = 0.0;
+        bool have_e = false;
+        for (int t = T.elem_tbeg[e]; t < T.elem_tbeg[e + 1]; ++t) {
+          double tv = T.term_coef[t];
+          for (int q = T.term_fbeg[t]; q < T.term_fbeg[t + 1]; ++q) {
+            int n = T.factor_n[q];
+            int o = fetch(n);
+            int b = T.nbr[n].w;
+            double ph = T.phi[(b * T.n_func + T.factor_f[q]) * T.max_occ + o];
+            tv = __dmul_rn(tv, ph);
+          }
+          ev = have_e ? __dadd_rn(ev, tv) : tv;
+          have_e = true;
+        }
+        s = have_s ? __dadd_rn(s, ev) : ev;
+        have_s = true;
+      }
+    }
+    double v = s;
+    int fd = T.group_dphi[gi];
+    if (fd >= 0) {
+      const double *ph = T.phi + (pb * T.n_func + fd) * T.max_occ;
+      double d = __dsub_rn(ph[occ_f], ph[occ_i]);
+      v = has_sum ? __dmul_rn(d, s) : d;
+    }
+    double dv = T.group_div[gi];
+    if (dv != 0.0) v = __ddiv_rn(v, dv);
+    total = have_total ? __dadd_rn(total, v) : v;
+    have_total = true;
+  }
+  return total;
+}
+
+__device__ inline double cmx_eval_function(const DevTables &T, const Geom &g,
+                                           const int8_t *occ, int gbeg,
+                                           int gend, int i, int j, int k,
+                                           const Override &ov, int pb,
+                                           int occ_i, int occ_f) {
+  LatticeFetch f{T, g, occ, i, j, k, ov};
+  return cmx_eval_function_t(T, gbeg, gend, f, pb, occ_i, occ_f);
+}
+
+// ---- counter-based RNG: Philox4x32-10 (Salmon et al., SC'11) ---------------
+struct Philox {
+  uint32_t c[4];
+};
+__device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1,
+                                                uint32_t c2, uint32_t c3,
+                                                uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0;
+    uint64_t p1 = (uint64_t)M1 * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += W0;
+    k1 += W1;
+  }
+  Philox o;
+  o.c[0] = c0;
+  o.c[1] = c1;
+  o.c[2] = c2;
+  o.c[3] = c3;
+  return o;
+}

@@ -1,0 +1,241 @@
+/*
+ * cmx_b200.h -- thin C ABI of the B200-native clexmonte hot path.
+ *
+ * This is the boundary a `BaseMonteCalculator` subclass (the reference's
+ * plugin interface, include/casm/clexmonte/monte_calculator/BaseMonteCalculator.hh:47-264,
+ * obtained through `extern "C" make_<Name>()`, e.g.
+ * src/casm/clexmonte/monte_calculator/SemiGrandCanonicalCalculator.cc:517-523)
+ * binds to: opaque handles, plain pointers and sizes, `int` status codes
+ * (0 = ok), `cmx_last_error()` for the message.  No C++ or torch types.
+ * INTEGRATION.md shows the reference-side subclass that calls it.
+ *
+ * All pointer arguments are HOST pointers unless the name starts with `d_`.
+ * Every entry point is implemented by hand-written sm_100a CUDA kernels in
+ * casmcode_clexmonte_b200/csrc/; there is no CPU implementation behind it --
+ * without a CUDA device every compute call fails with CMX_ERR_CUDA.
+ *
+ * Conventions (identical to the reference's):
+ *   linear site index  l = b * n_cells + cell,  cell = i + N0 * (j + N1 * k)
+ *   occupation value   occupant index on the sublattice's allowed list
+ */
+#ifndef CMX_B200_H
+#define CMX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMX_OK 0
+#define CMX_ERR_INVALID 1  /* bad argument / inconsistent tables */
+#define CMX_ERR_CUDA 2     /* CUDA runtime error or no device */
+#define CMX_ERR_UNSUPPORTED 3
+#define CMX_ERR_STATE 4    /* call sequence error (e.g. no ECI bound) */
+
+typedef struct cmx_tables cmx_tables; /* one basis set (one Clexulator) */
+typedef struct cmx_state cmx_state;   /* device-resident supercell(s)   */
+
+/* Message of the last error raised on the calling thread. */
+const char *cmx_last_error(void);
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+int cmx_version(void);
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int cmx_device_count(void);
+
+/* -------------------------------------------------------------------------
+ * Tables: the flat export of one CASM-generated Clexulator.
+ * Replaces the runtime-compiled object behind
+ *   clexulator::BaseClexulator  (generated source, e.g.
+ *   tests/unit/clexmonte/data/FCC_binary_vacancy/basis_sets/bset.default/
+ *   FCC_binary_vacancy_Clexulator_default.cc:306-439 for the data,
+ *   :780-1062 for the expressions).
+ * Layout documented in casmcode_clexmonte_b200/clexulator_tables.py.
+ * ------------------------------------------------------------------------- */
+typedef struct cmx_table_desc {
+  int32_t n_sublat;       /* sublattices in the prim                        */
+  int32_t max_occ;        /* max allowed occupants on any sublattice        */
+  int32_t n_func;         /* max site basis functions per sublattice        */
+  int32_t corr_size;      /* number of correlation (basis) functions        */
+  int32_t n_point_corr;   /* point-corr positions (global: #nlist sublat;   */
+                          /*   local clexulators: nlist_size)               */
+  int32_t nlist_len;      /* neighbor-list sites                            */
+  int32_t n_nlist_sublat; /* sublattices on the neighbor list               */
+  int32_t n_factors, n_terms, n_elems, n_groups;
+  const int32_t *nlist_sublat;  /* [n_nlist_sublat] sorted                   */
+  const int32_t *n_occ;         /* [n_sublat] allowed occupants (1 = fixed)  */
+  const double *phi;            /* [n_sublat][n_func][max_occ]               */
+  const int32_t *nbr;           /* [nlist_len][4] = di, dj, dk, b            */
+  const int32_t *factor_f;      /* [n_factors] site function index           */
+  const int32_t *factor_n;      /* [n_factors] neighbor index                */
+  const double *term_coef;      /* [n_terms]                                 */
+  const int32_t *term_fbeg;     /* [n_terms+1]                               */
+  const int32_t *elem_tbeg;     /* [n_elems+1]                               */
+  const int32_t *group_ebeg;    /* [n_groups+1]                              */
+  const int32_t *group_dphi;    /* [n_groups] f' of the delta factor or -1   */
+  const int32_t *group_has_sum; /* [n_groups]                                */
+  const double *group_div;      /* [n_groups] divisor, 0 = none              */
+  const int32_t *global_gbeg;   /* [corr_size+1]                             */
+  const int32_t *point_gbeg;    /* [n_point_corr*corr_size+1]                */
+  const int32_t *delta_gbeg;    /* [n_point_corr*corr_size+1]                */
+} cmx_table_desc;
+
+int cmx_tables_create(const cmx_table_desc *desc, int device, cmx_tables **out);
+void cmx_tables_destroy(cmx_tables *t);
+
+/* -------------------------------------------------------------------------
+ * State: `n_replicas` independent periodic supercells of N0 x N1 x N2 unit
+ * cells (transformation matrix diag(N0,N1,N2)), occupation stored as int8 on
+ * the device.  Stands in for the (Configuration, SuperNeighborList,
+ * ClusterExpansion, OccLocation) bundle the reference builds in
+ * StateData (src/casm/clexmonte/monte_calculator/StateData.cc:9-79) -- no
+ * neighbor list is materialised; neighbors are (di,dj,dk,b) arithmetic.
+ *
+ * `halo` > 0 creates a slab for domain decomposition along k: the local box
+ * holds N2 layers plus `halo` ghost layers on each side, k is NOT wrapped and
+ * the ghost layers are filled by cmx_state_halo_* (BASELINE config 3).
+ * ------------------------------------------------------------------------- */
+int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1, int32_t N2,
+                     int32_t n_replicas, int32_t halo, cmx_state **out);
+void cmx_state_destroy(cmx_state *s);
+
+/* occupation in the reference's layout (int32, Eigen::VectorXi order
+ * l = b*n_cells + cell); converted to/from int8 on the device. */
+int cmx_state_upload_occ(cmx_state *s, int32_t replica, const int32_t *occ);
+int cmx_state_download_occ(const cmx_state *s, int32_t replica, int32_t *occ);
+/* same, int8 host buffers (1 byte/site over PCIe) */
+int cmx_state_upload_occ_i8(cmx_state *s, int32_t replica, const int8_t *occ);
+int cmx_state_download_occ_i8(const cmx_state *s, int32_t replica, int8_t *occ);
+/* i.i.d. uniform occupation over each sublattice's allowed occupants from the
+ * counter-based generator, keyed by (seed, replica, site). */
+int cmx_state_randomize(cmx_state *s, uint64_t seed);
+/* slab decomposition: global k index of this slab's first owned layer (enters
+ * the RNG counters so that results do not depend on the decomposition). */
+int cmx_state_set_k_offset(cmx_state *s, int32_t k_offset);
+/* raw device pointer to replica 0's int8 occupation including ghost layers,
+ * and its size in bytes (for NCCL halo plumbing by the host). */
+int cmx_state_device_ptr(cmx_state *s, void **d_ptr, size_t *n_bytes);
+
+/* Bind the cluster expansion coefficients: sparse (index, value) pairs as in
+ * the reference's SparseCoefficients; ClexData parsed at
+ * src/casm/clexmonte/system/io/json/System_json_io.cc:491-539. */
+int cmx_state_set_eci(cmx_state *s, int32_t n, const uint32_t *index,
+                      const double *value);
+
+/* Thermodynamic conditions of one replica.
+ *   temperature [K]; beta = 1/(KB*T), KB = 8.6173303e-05 eV/K
+ *     (include/casm/clexmonte/methods/occupation_metropolis.hh:86)
+ *   exch[b][occ_i][occ_f] (n_sublat*max_occ*max_occ doubles, may be NULL = 0):
+ *     the semi-grand term  mu_x . (R^T dN)  of
+ *     SemiGrandCanonicalPotential::occ_delta_per_supercell
+ *     (SemiGrandCanonicalCalculator.cc:201-212) tabulated per occupant change;
+ *     dE_potential = dE_clex - exch[b][occ_i][occ_f]. */
+int cmx_state_set_conditions(cmx_state *s, int32_t replica, double temperature,
+                             const double *exch);
+
+/* -------------------------------------------------------------------------
+ * Potential / correlations (reference rows a1-a8 of SURVEY.md section 8a).
+ * "Faithful" evaluation: the reference's operation order, no FMA contraction,
+ * so results are bit-identical to the generated C++ on x86-64.
+ * ------------------------------------------------------------------------- */
+
+/* Clexulator::calc_delta_point_corr for `n` independent single-site changes
+ * (…default.cc:555-580).  out[n][corr_size]. */
+int cmx_delta_corr(const cmx_state *s, int32_t replica, int64_t n,
+                   const int64_t *l, const int32_t *new_occ, double *out);
+/* Clexulator::calc_point_corr (:500-553).  out[n][corr_size]. */
+int cmx_point_corr(const cmx_state *s, int32_t replica, int64_t n,
+                   const int64_t *l, double *out);
+/* Clexulator::calc_global_corr_contribution for `n` unit cells (:446-470);
+ * for local clexulators this is LocalCorrelations::local.  out[n][corr_size] */
+int cmx_cell_corr(const cmx_state *s, int32_t replica, int64_t n,
+                  const int64_t *cell, double *out);
+/* ClusterExpansion::occ_delta_value for `n` independent events of
+ * `sites_per_event` sites each (1 = semi-grand flip, 2 = canonical swap / KMC
+ * hop): sites are applied sequentially and restored, restricted to the bound
+ * ECI indices (call sites SemiGrandCanonicalCalculator.cc:198-199,
+ * CanonicalCalculator.cc:139).  With `potential` != 0 the replica's exch term
+ * is subtracted (occ_delta_per_supercell, :186-213).  dE[n]. */
+int cmx_delta_e(const cmx_state *s, int32_t replica, int64_t n,
+                int32_t sites_per_event, const int64_t *l,
+                const int32_t *new_occ, int32_t potential, double *dE);
+/* Correlations::per_supercell(): sum over all unit cells of the global
+ * contribution (call sites sampling_functions.cc:131-133).  out[corr_size]. */
+int cmx_global_corr(const cmx_state *s, int32_t replica, double *out);
+/* ClusterExpansion::per_supercell() = sum_i value_i * corr[index_i]. */
+int cmx_energy(const cmx_state *s, int32_t replica, double *E);
+/* occupant counts counts[b][occ] (n_sublat*max_occ int64) -- the input of
+ * CompositionCalculator::mean_num_each_component (sampling_functions.cc:37-54). */
+int cmx_composition(const cmx_state *s, int32_t replica, int64_t *counts);
+
+/* -------------------------------------------------------------------------
+ * Metropolis drivers (reference rows a9/a10).
+ * ------------------------------------------------------------------------- */
+typedef struct cmx_counters {
+  int64_t n_attempt;   /* attempted steps                                    */
+  int64_t n_accept;    /* accepted steps                                     */
+  double dE_sum;       /* sum of accepted delta potential energies           */
+  int64_t reserved;
+} cmx_counters;
+
+/* Semi-grand canonical sublattice-checkerboard sweeps over ALL replicas:
+ * one sweep attempts one single-site change at every mutable site, colour by
+ * colour (non-interacting site sets updated simultaneously), counter-based
+ * RNG keyed by (seed, replica, sweep, site).  Replaces the loop
+ * methods/occupation_metropolis.hh:92-120 with the semi-grand proposal
+ * (SemiGrandCanonicalCalculator.cc:104-120).  counters[n_replicas] (may be
+ * NULL) receive the totals of this call.  `first_sweep` is the index of the
+ * first sweep (the RNG counter), so consecutive calls continue one stream. */
+int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
+                  int64_t first_sweep, cmx_counters *counters);
+/* As above but only the colours with k-parity group `kgroup` of the colour
+ * ordering (0 or 1; -1 = both) -- the unit between two halo exchanges in the
+ * slab-decomposed run. */
+int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
+                         int32_t kgroup, cmx_counters *counters);
+/* Name of the evaluator the sweep uses for the bound ECI ("pair_lut",
+ * "generic"); algorithmic work per attempted step for the roofline
+ * bookkeeping: neighbor bytes read and FP64 flops, counted from the tables. */
+int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
+                   double *bytes_per_step, double *flops_per_step,
+                   int32_t *n_colours);
+
+/* Occupant bookkeeping needed by the reference-order mode:
+ * sublat_to_asym[n_sublat], occ_to_species[n_sublat][max_occ] (-1 padded). */
+int cmx_state_set_occupants(cmx_state *s, const int32_t *sublat_to_asym,
+                            const int32_t *occ_to_species, int32_t n_species);
+
+typedef struct cmx_step_record {
+  int64_t l0, l1;   /* l1 = -1 for semi-grand */
+  int32_t new0, new1;
+  int32_t accepted, pad;
+  double dE;
+} cmx_step_record;
+
+/* Reference-order (sequential) Metropolis on the device, one replica:
+ * std::mt19937_64(seed) stream, libstdc++ uniform_int/uniform_real draws,
+ * OccLocation candidate lists with swap-and-pop, proposals as
+ * propose_semigrand_canonical_event (mode 0) / propose_canonical_event
+ * (mode 1), acceptance as metropolis_acceptance -- the exact sequence of
+ * methods/occupation_metropolis.hh:92-120.  Reproduces the reference
+ * trajectory bit for bit; `hash` is FNV-1a over (l0*2+accepted) per step.
+ * log[log_cap] (may be NULL) receives the first steps. */
+int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t mode,
+                              int64_t n_steps, uint64_t seed,
+                              cmx_step_record *log, int64_t log_cap,
+                              int64_t *n_accept, uint64_t *hash);
+
+/* Test hook: replay `n` draws of the device-side restatement of
+ * std::mt19937_64(seed) + libstdc++ distributions (kind 0 = raw 64-bit,
+ * 1 = uniform_int_distribution<long>(0,int_max), 2 =
+ * uniform_real_distribution<double>(0,real_max)) so the stream can be compared
+ * draw by draw with the host C++ library. */
+int cmx_rng_stream_test(uint64_t seed, int64_t n, const int64_t *int_max,
+                        const double *real_max, const int32_t *kind,
+                        int64_t *out_int, double *out_real, uint64_t *out_raw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMX_B200_H */
