@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- attempted MC steps/s of the semi-grand canonical checkerboard sweep.
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on; it fits
+one B200): FCC ternary (A-B-Va) semi-grand canonical, 512^3 primitive supercell
+(134 217 728 sites), the reference's shipped ECI (points + nearest-neighbour
+pairs), T = 800 K, param_chem_pot = (0, 0), i.i.d. random initial occupation.
+A "step" of this benchmark = `sweeps_per_step` full lattice sweeps (each sweep =
+one attempted Metropolis step at every site).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): the 512^3 box is split into N slabs along k
+with one ghost layer each side, exchanged twice per sweep over NCCL
+(strong scaling).  --impl reference times the reference's own CPU path (the
+generated Clexulator kernels of oracle/_ref inside the restated sequential
+loop), one chain per host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+GOLDEN = ROOT / "tests" / "golden"
+
+METRIC = "attempted MC steps/sec (FCC ternary SGC, 512^3 = 134M sites)"
+UNIT = "steps/s"
+N_BOX = 512
+TEMPERATURE = 800.0
+MU = (0.0, 0.0)
+SWEEPS_PER_STEP = 10
+
+
+def load_system():
+    sysd = json.loads((GOLDEN / "systems.json").read_text())["fcc"]
+    return sysd
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                clk, mxc = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: take every sample
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference CPU path (oracle/_ref), one chain per core
+# ---------------------------------------------------------------------------
+def cpu_reference_rate(seconds_budget: float = 12.0, box: int = 64, threads: int | None = None) -> dict:
+    """Sequential semi-grand Metropolis with the reference's generated kernels
+    (methods/occupation_metropolis.hh:92-120 restated in oracle/harness.cpp), one
+    independent chain per host core, each on a `box`^3 periodic sample of the
+    workload (a 512^3 SuperNeighborList would need 20 GB per chain)."""
+    from oracle import oracle as O
+    kind = "reference"
+    if not O.available("fcc_default"):
+        raise RuntimeError("oracle/_ref not built")
+    sysd = load_system()
+    eci = sysd["eci_sparse"]
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=3, Rt=np.array(sysd["axes"]["Rt"]))
+    cores = threads or len(os.sched_getaffinity(0))
+    clex = O.RefClexulator("fcc_default")
+    scs = [clex.supercell(box) for _ in range(cores)]
+    occs = [np.random.default_rng(c).integers(0, 3, box ** 3).astype(np.int32) for c in range(cores)]
+    # calibrate on one core
+    r = scs[0].metropolis_run(0, occs[0], prim, eci["index"], eci["value"], TEMPERATURE, 1, 200_000,
+                              param_chem_pot=np.array(MU))
+    rate1 = 200_000 / max(r["seconds"], 1e-9)
+    n_steps = int(max(200_000, rate1 * seconds_budget))
+    out = [None] * cores
+
+    def work(c):
+        out[c] = scs[c].metropolis_run(0, occs[c], prim, eci["index"], eci["value"], TEMPERATURE, 100 + c,
+                                       n_steps, param_chem_pot=np.array(MU))
+
+    ths = [threading.Thread(target=work, args=(c,)) for c in range(cores)]
+    t0 = time.time()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.time() - t0
+    total = n_steps * cores
+    return dict(value=total / wall, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{cores} independent chains x {n_steps} sequential steps on a {box}^3-site periodic "
+                       f"box each (same basis/ECI/T/mu; wall {wall:.1f}s)",
+                steps_per_s_per_core=total / wall / cores)
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--box", type=int, default=N_BOX)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"FCC A-B-Va semi-grand canonical, {args.box}^3 primitive supercell, shipped sparse ECI "
+                f"(points+1NN pairs), T={TEMPERATURE:g} K, param_chem_pot={list(MU)}")
+    config = {"workload": workload, "sites": args.box ** 3, "sweeps_per_step": SWEEPS_PER_STEP,
+              "l2_policy": "inputs larger than L2 (134 MB lattice re-streamed every colour pass)",
+              "parallelism": f"slab{world}" if world > 1 else "single"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = cpu_reference_rate(seconds_budget=max(5.0, min(60.0, 4.0 * args.steps)))
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": res,
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    from casmcode_clexmonte_b200 import _capi
+    from casmcode_clexmonte_b200.clexulator_tables import ClexulatorTables
+    from casmcode_clexmonte_b200.potential import semigrand_exchange_table
+
+    if not torch.cuda.is_available() or _capi.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from casmcode_clexmonte_b200.slab import SlabRunner
+    sysd = load_system()
+    eci = sysd["eci_sparse"]
+    tables = _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz"), device=local_rank)
+    ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], MU, 3)
+    N = args.box
+    K, W, S = args.steps, max(3, args.warmup), SWEEPS_PER_STEP
+
+    if world == 1:
+        st = _capi.State(tables, (N, N, N))
+        st.set_eci(eci["index"], eci["value"])
+        st.set_conditions(TEMPERATURE, ex)
+        st.randomize(2026)
+        info = st.sweep_info()
+        stream = torch.cuda.ExternalStream(st.stream())
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # ---- device-resident throughput
+        st.sgc_sweep(W * S, seed=1, first_sweep=0, counters=False)
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        time.sleep(0.3)
+        t0 = time.time()
+        ev0.record(stream)
+        cnt = st.sgc_sweep(K * S, seed=1, first_sweep=W * S)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        ms = ev0.elapsed_time(ev1)
+        clk = clocks.stop(t0, t1)
+        n_sites = N ** 3
+        attempts = K * S * n_sites
+        assert cnt[0].n_attempt == attempts
+        value = attempts / (ms * 1e-3)
+        launches = K * S * info["n_colours"] + 3
+        kernel_ms = ms / (K * S * info["n_colours"])
+        # ---- end to end: host buffers through the C ABI, copies inside the timed region
+        host = torch.empty(n_sites, dtype=torch.int8).pin_memory()
+        harr = host.numpy()
+        st.download_occ(dtype=np.int8, out=harr)
+        for _ in range(2):
+            st.upload_occ(harr)
+            st.sgc_sweep(S, seed=3, first_sweep=0, counters=True)
+            st.download_occ(dtype=np.int8, out=harr)
+        torch.cuda.synchronize()
+        te0 = time.perf_counter()
+        for k in range(K):
+            st.upload_occ(harr)
+            c2 = st.sgc_sweep(S, seed=3, first_sweep=(k + 1) * S, counters=True)
+            st.download_occ(dtype=np.int8, out=harr)
+        torch.cuda.synchronize()
+        te1 = time.perf_counter()
+        e2e = {"value": K * S * n_sites / (te1 - te0), "unit": UNIT,
+               "h2d_bytes_per_step": n_sites, "d2h_bytes_per_step": n_sites + 32,
+               "ms_per_step": (te1 - te0) * 1e3 / K}
+        accept_rate = cnt[0].n_accept / cnt[0].n_attempt
+        st.close()
+    else:
+        runner = SlabRunner(tables, N, eci, TEMPERATURE, ex, rank, world, local_rank, seed_init=2026)
+        info = runner.info()
+        res = runner.bench(K, W, S)
+        ms, clk, e2e, accept_rate = res["ms"], res["clocks"], res["e2e"], res["accept_rate"]
+        n_sites = N ** 3
+        value = K * S * n_sites / (ms * 1e-3)
+        launches = res["launches"]
+        kernel_ms = res["kernel_ms"]
+        if rank != 0:
+            return
+
+    # ---- roofline of the dominant kernel (k_sweep_pair_lut, one colour pass)
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    sites_per_launch = n_sites / world / info["n_colours"]
+    alg_bytes = 2.0 * sites_per_launch           # 2 B per step at the HBM level
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_pair_lut",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_step_hbm": 2.0,
+                "algorithmic_bytes_per_step_l2": info["bytes_per_step"],
+                "note": "the sweep is instruction-issue bound, not HBM bound: see DESIGN.md and profiles/"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "evaluator": info["evaluator"],
+            "accept_rate": accept_rate, "dE_evals_per_s": value}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_reference_rate(seconds_budget=args.cpu_seconds)
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": f"unavailable: {e}"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_create", "cmx_state_destroy",
     "cmx_state_upload_occ", "cmx_state_download_occ",
     "cmx_state_upload_occ_i8", "cmx_state_download_occ_i8",
-    "cmx_state_randomize", "cmx_state_set_k_offset", "cmx_state_device_ptr",
+    "cmx_state_randomize", "cmx_state_set_k_offset", "cmx_state_stream", "cmx_state_device_ptr",
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
@@ -94,6 +94,7 @@ def lib():
     L.cmx_state_randomize.argtypes = [vp, u64]
     L.cmx_state_set_k_offset.argtypes = [vp, i32]
     L.cmx_state_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.cmx_state_stream.argtypes = [vp, C.POINTER(vp)]
     L.cmx_state_set_eci.argtypes = [vp, i32, vp, vp]
     L.cmx_state_set_conditions.argtypes = [vp, i32, dbl, vp]
     L.cmx_state_set_occupants.argtypes = [vp, vp, vp, i32]
@@ -219,6 +220,12 @@ class State:
 
     def set_k_offset(self, k_offset: int) -> None:
         check(lib().cmx_state_set_k_offset(self._h, int(k_offset)))
+
+    def stream(self) -> int:
+        """cudaStream_t the state's kernels run on (for external CUDA events)."""
+        p = C.c_void_p()
+        check(lib().cmx_state_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
 
     def device_ptr(self):
         p = C.c_void_p()

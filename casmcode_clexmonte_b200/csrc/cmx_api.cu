@@ -163,6 +163,7 @@ extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
   cudaMalloc(&s->d_exch, sizeof(double) * ex * n_replicas);
   cudaMemset(s->d_beta, 0, sizeof(double) * n_replicas);
   cudaMemset(s->d_exch, 0, sizeof(double) * ex * n_replicas);
+  cudaMalloc(&s->d_flag, sizeof(int));
   cudaMalloc(&s->d_counters, sizeof(cmx_counters) * n_replicas);
   cudaMemset(s->d_counters, 0, sizeof(cmx_counters) * n_replicas);
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -185,6 +186,7 @@ extern "C" void cmx_state_destroy(cmx_state *s) {
   cudaFree(s->d_beta);
   cudaFree(s->d_exch);
   cudaFree(s->d_counters);
+  cudaFree(s->d_flag);
   cudaFree(s->d_scratch);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -201,16 +203,41 @@ int cmx_scratch(cmx_state *s, size_t bytes) {
   return CMX_OK;
 }
 
-// reference layout (no ghost layers, int32 or int8) <-> device layout (int8)
+// reference layout (no ghost layers, int32 or int8) <-> device layout (int8).
+// Occupant indices are validated on the device (a bad index would read outside
+// the site-function tables): *bad is set when any is out of range.
 template <typename SrcT>
 __global__ void k_scatter_occ(const SrcT *__restrict__ src, int8_t *dst, Geom g,
-                              int n_sublat) {
+                              int n_sublat, const int32_t *__restrict__ n_occ,
+                              int *bad) {
   int64_t total = g.n_cells * n_sublat;
+  int flag = 0;
   for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < total;
        l += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
-    dst[b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)src[l];
+    int v = (int)src[l];
+    flag |= (v < 0 || v >= n_occ[b]);
+    dst[b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)v;
   }
+  if (flag) *bad = 1;
+}
+// in-place validation of an int8 image copied straight into the state (16 sites
+// per thread-iteration; n_cells is a multiple of 16 on this path)
+__global__ void k_validate_occ16(const int4 *__restrict__ occ, int64_t n16,
+                                 int64_t cells16, const int32_t *__restrict__ n_occ,
+                                 int *bad) {
+  int flag = 0;
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n16;
+       x += (int64_t)gridDim.x * blockDim.x) {
+    int no = n_occ[x / cells16];
+    int4 v = occ[x];
+    uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) flag |= (int)((w[q] >> (8 * k)) & 0xffu) >= no;
+  }
+  if (flag) *bad = 1;
 }
 template <typename DstT>
 __global__ void k_gather_occ(const int8_t *__restrict__ src, DstT *dst, Geom g,
@@ -237,21 +264,26 @@ static int upload_occ(cmx_state *s, int32_t replica, const T *occ) {
   if (!occ) return invalid("cmx_state_upload_occ: null occupation");
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
-  // validate on the host: a bad occupant index would read outside phi
-  for (size_t l = 0; l < n; ++l) {
-    int b = (int)(l / s->g.n_cells);
-    if (occ[l] < 0 || occ[l] >= s->t->n_occ[b])
-      return invalid("cmx_state_upload_occ: occupant index out of range");
-  }
-  rc = cmx_scratch(s, n * sizeof(T));
-  if (rc) return rc;
-  CMX_CUDA(cudaMemcpyAsync(s->d_scratch, occ, n * sizeof(T),
-                           cudaMemcpyHostToDevice, s->stream));
   int8_t *dst = s->d_occ + (size_t)replica * s->g.rep_stride;
-  k_scatter_occ<T><<<1184, 256, 0, s->stream>>>((const T *)s->d_scratch, dst,
-                                                s->g, s->t->d.n_sublat);
+  CMX_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
+  if (sizeof(T) == 1 && s->g.halo == 0 && s->g.n_cells % 16 == 0) {
+    // device layout == reference layout: one DMA, validated in place.  On a
+    // bad index the previous occupation is lost -- the caller gets an error.
+    CMX_CUDA(cudaMemcpyAsync(dst, occ, n, cudaMemcpyHostToDevice, s->stream));
+    k_validate_occ16<<<1184, 256, 0, s->stream>>>((const int4 *)dst, (int64_t)(n / 16),
+                                                  s->g.n_cells / 16, s->t->d.n_occ, s->d_flag);
+  } else {
+    rc = cmx_scratch(s, n * sizeof(T));
+    if (rc) return rc;
+    CMX_CUDA(cudaMemcpyAsync(s->d_scratch, occ, n * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    k_scatter_occ<T><<<1184, 256, 0, s->stream>>>((const T *)s->d_scratch, dst, s->g,
+                                                  s->t->d.n_sublat, s->t->d.n_occ, s->d_flag);
+  }
   CMX_CUDA(cudaGetLastError());
+  int bad = 0;
+  CMX_CUDA(cudaMemcpyAsync(&bad, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
+  if (bad) return invalid("cmx_state_upload_occ: occupant index out of range");
   return CMX_OK;
 }
 
@@ -263,9 +295,14 @@ static int download_occ(const cmx_state *cs, int32_t replica, T *occ) {
   if (!occ) return invalid("cmx_state_download_occ: null occupation");
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
+  const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
+  if (sizeof(T) == 1 && s->g.halo == 0) {
+    CMX_CUDA(cudaMemcpyAsync(occ, src, n, cudaMemcpyDeviceToHost, s->stream));
+    CMX_CUDA(cudaStreamSynchronize(s->stream));
+    return CMX_OK;
+  }
   rc = cmx_scratch(s, n * sizeof(T));
   if (rc) return rc;
-  const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
   k_gather_occ<T><<<1184, 256, 0, s->stream>>>(src, (T *)s->d_scratch, s->g,
                                                s->t->d.n_sublat);
   CMX_CUDA(cudaGetLastError());
@@ -323,6 +360,12 @@ extern "C" int cmx_state_randomize(cmx_state *s, uint64_t seed) {
 extern "C" int cmx_state_set_k_offset(cmx_state *s, int32_t k_offset) {
   if (!s || k_offset < 0) return invalid("cmx_state_set_k_offset: bad argument");
   s->k_offset = k_offset;
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_stream(cmx_state *s, void **stream) {
+  if (!s || !stream) return invalid("cmx_state_stream: null argument");
+  *stream = (void *)s->stream;
   return CMX_OK;
 }
 

@@ -115,6 +115,7 @@ struct cmx_state {
   // sweeps
   SweepPlan plan;
   cmx_counters *d_counters = nullptr;  // [replica]
+  int *d_flag = nullptr;               // device-side validation flag
   // scratch
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;

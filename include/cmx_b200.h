@@ -113,6 +113,9 @@ int cmx_state_randomize(cmx_state *s, uint64_t seed);
 /* slab decomposition: global k index of this slab's first owned layer (enters
  * the RNG counters so that results do not depend on the decomposition). */
 int cmx_state_set_k_offset(cmx_state *s, int32_t k_offset);
+/* the CUDA stream (cudaStream_t) every kernel of this state is launched on,
+ * so that callers can bracket the work with their own events. */
+int cmx_state_stream(cmx_state *s, void **stream);
 /* raw device pointer to replica 0's int8 occupation including ghost layers,
  * and its size in bytes (for NCCL halo plumbing by the host). */
 int cmx_state_device_ptr(cmx_state *s, void **d_ptr, size_t *n_bytes);

@@ -1,0 +1,326 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+(1) the committed golden vectors produced by the reference's own generated
+kernels and (2) the live oracle on fresh seeded inputs.
+
+Tolerances: the faithful evaluators (delta corr, point corr, cell corr,
+delta E, sequential trajectories) are required to be BIT-EXACT.  Global sums
+over all unit cells use a different (tree) summation order than the
+reference's ascending loop and are checked to rtol 1e-12 (north_star: 1e-10).
+"""
+import numpy as np
+import pytest
+
+from conftest import CASES
+
+from casmcode_clexmonte_b200 import _capi
+from casmcode_clexmonte_b200.potential import (KB, mol_composition, semigrand_exchange_table,
+                                               semigrand_potential_per_supercell)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev_tables(load_tables):
+    cache = {}
+
+    def _get(name):
+        if name not in cache:
+            cache[name] = _capi.Tables(load_tables(name))
+        return cache[name]
+
+    yield _get
+    for t in cache.values():
+        t.close()
+
+
+def make_state(dev_tables, systems, load_vectors, case, n_replicas=1):
+    sysname, _ = CASES[case]
+    sysd = systems[sysname]
+    v = load_vectors(case)
+    st = _capi.State(dev_tables(sysd["tables"]), tuple(int(x) for x in v["N"]), n_replicas)
+    for r in range(n_replicas):
+        st.upload_occ(v["occ"], r)
+    st.set_eci(v["eci_index"], v["eci_value"])
+    return st, v, sysd
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_faithful_kernels_match_golden(dev_tables, systems, load_vectors, case):
+    st, v, sysd = make_state(dev_tables, systems, load_vectors, case)
+    assert (st.download_occ() == v["occ"]).all()
+    assert (st.download_occ(dtype=np.int8) == v["occ"].astype(np.int8)).all()
+    assert (st.delta_corr(v["l"], v["new_occ"]) == v["delta_corr"]).all()
+    assert (st.point_corr(v["l"]) == v["point_corr"]).all()
+    assert (st.cell_corr(v["cells"]) == v["cell_corr"]).all()
+    assert (st.delta_e(v["l"], v["new_occ"], 1) == v["delta_e_1"]).all()
+    assert (st.delta_e(v["l2"], v["new_occ2"], 2) == v["delta_e_2"]).all()
+    np.testing.assert_allclose(st.global_corr(), v["global_corr"], rtol=1e-12, atol=1e-12)
+    e = st.energy()
+    e_ref = float(np.dot(v["eci_value"], v["global_corr"][v["eci_index"]]))
+    assert e == pytest.approx(e_ref, rel=1e-12, abs=1e-12)
+    # composition + semi-grand potential
+    counts = st.composition()
+    n_cells = int(np.prod(v["N"]))
+    comp = mol_composition(counts, sysd["occ_to_species"], sysd["n_species"], n_cells)
+    np.testing.assert_allclose(comp, v["mol_composition"], rtol=0, atol=1e-15)
+    pot = semigrand_potential_per_supercell(e, comp, sysd["axes"]["origin"], sysd["axes"]["Rt"],
+                                            v["param_chem_pot"], n_cells)
+    assert pot == pytest.approx(float(v["potential_per_supercell"]), rel=1e-12)
+    st.close()
+
+
+def test_local_clexulators_match_golden(dev_tables, load_vectors):
+    """LocalCorrelations::local for the 12 KMC local basis sets."""
+    v = load_vectors("local")
+    for ev in ("A_Va_1NN", "B_Va_1NN"):
+        for k in range(6):
+            name = f"fcc_{ev}_{k}"
+            st = _capi.State(dev_tables(name), tuple(int(x) for x in v["N"]))
+            st.upload_occ(v["occ"])
+            assert (st.cell_corr(v["cells"]) == v[name]).all(), name
+            st.close()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_semigrand_delta_potential(dev_tables, systems, load_vectors, oracle, case):
+    """occ_delta_per_supercell with the exchange term, against the live oracle's
+    single-step log (dE of step 0 of the sequential loop)."""
+    st, v, sysd = make_state(dev_tables, systems, load_vectors, case)
+    ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], v["param_chem_pot"],
+                                  sysd["n_species"])
+    st.set_conditions(float(v["sgc_T"]), ex)
+    l0 = v["sgc_log_l0"][:1]
+    n0 = v["sgc_log_new0"][:1]
+    assert st.delta_e(l0, n0, 1, potential=True)[0] == v["sgc_log_dE"][0]
+    st.close()
+
+
+def test_device_rng_stream_matches_libstdcxx(load_vectors):
+    """mt19937_64 + uniform_int/real on the device == libstdc++ draw by draw."""
+    v = load_vectors("rng")
+    oi, orl, oraw = _capi.rng_stream_test(int(v["seed"]), v["kinds"], v["int_max"], v["real_max"])
+    k = v["kinds"]
+    assert (oraw[k == 0] == v["out_raw"][k == 0]).all()
+    assert (oi[k == 1] == v["out_int"][k == 1]).all()
+    assert (orl[k == 2] == v["out_real"][k == 2]).all()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_sequential_trajectory_matches_golden(dev_tables, systems, load_vectors, case, mode):
+    """Reference-order mode reproduces the oracle's occupation trajectory."""
+    st, v, sysd = make_state(dev_tables, systems, load_vectors, case)
+    ex = None
+    if mode == "sgc":
+        ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], v["param_chem_pot"],
+                                      sysd["n_species"])
+    st.set_conditions(float(v[f"{mode}_T"]), ex)
+    st.set_occupants(sysd["sublat_to_asym"], sysd["occ_to_species"], sysd["n_species"])
+    n_steps = int(v[f"{mode}_steps"])
+    res = st.metropolis_sequential(0 if mode == "sgc" else 1, n_steps, int(v[f"{mode}_seed"]), log_cap=256)
+    log = res["log"]
+    assert [s["l0"] for s in log] == list(v[f"{mode}_log_l0"])
+    assert [s["l1"] for s in log] == list(v[f"{mode}_log_l1"])
+    assert [s["new0"] for s in log] == list(v[f"{mode}_log_new0"])
+    assert [s["accepted"] for s in log] == list(v[f"{mode}_log_acc"])
+    assert [s["dE"] for s in log] == list(v[f"{mode}_log_dE"])
+    assert res["n_accept"] == int(v[f"{mode}_n_accept"])
+    assert res["hash"] == int(v[f"{mode}_hash"])
+    assert (st.download_occ(dtype=np.int8) == v[f"{mode}_final_occ"]).all()
+    st.close()
+
+
+def test_sequential_million_steps_vs_live_oracle(dev_tables, systems, load_vectors, oracle):
+    """north_star (2): 10^6 reference-order steps, bit-exact, on config 1's size
+    (FCC A-B-Va, 4096-site box), canonical and semi-grand."""
+    if oracle is None:
+        pytest.skip("oracle/_ref not built")
+    sysd = systems["fcc"]
+    N = 16
+    rng = np.random.default_rng(42)
+    occ = rng.integers(0, 3, N ** 3).astype(np.int32)
+    eci = sysd["eci_sparse"]
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=3, Rt=np.array(sysd["axes"]["Rt"]))
+    mu = np.array([0.1, -0.4])
+    sc = oracle.RefClexulator("fcc_default").supercell(N)
+    st = _capi.State(dev_tables("fcc_default"), (N, N, N))
+    st.set_eci(eci["index"], eci["value"])
+    st.set_occupants(sysd["sublat_to_asym"], sysd["occ_to_species"], 3)
+    for mode, T in ((0, 1000.0), (1, 600.0)):
+        ref = sc.metropolis_run(mode, occ, prim, eci["index"], eci["value"], T, seed=99, n_steps=10 ** 6,
+                                param_chem_pot=mu if mode == 0 else None)
+        st.upload_occ(occ)
+        ex = semigrand_exchange_table(sysd["occ_to_species"], prim["Rt"], mu, 3) if mode == 0 else None
+        st.set_conditions(T, ex)
+        res = st.metropolis_sequential(mode, 10 ** 6, 99)
+        mism = int((st.download_occ() != ref["occ"]).sum())
+        assert (res["n_accept"], res["hash"], mism) == (ref["n_accept"], ref["hash"], 0), \
+            f"mode {mode}: exact-tie divergence? gpu acc {res['n_accept']} ref {ref['n_accept']} mismatching sites {mism}"
+    st.close()
+
+
+# ---------------------------------------------------------------------------
+# checkerboard sweeps
+# ---------------------------------------------------------------------------
+def _sweep_state(dev_tables, systems, case_sys, eci_key, N, T, mu, n_replicas=1, seed=1):
+    sysd = systems[case_sys]
+    st = _capi.State(dev_tables(sysd["tables"]), N, n_replicas)
+    eci = sysd[eci_key]
+    st.set_eci(eci["index"], eci["value"])
+    ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], mu, sysd["n_species"])
+    for r in range(n_replicas):
+        st.set_conditions(T, ex, r)
+    st.randomize(seed)
+    return st, sysd, ex
+
+
+@pytest.mark.parametrize("case_sys,eci_key,N,expect", [
+    ("fcc", "eci_sparse", (16, 16, 16), "pair_lut"),
+    ("fcc", "eci_full", (16, 16, 16), "generic"),
+    ("fcc", "eci_sparse", (12, 12, 12), "generic"),   # N0 % 8 != 0 -> generic evaluator
+    ("zro", "eci", (8, 8, 8), "generic"),
+])
+def test_sweep_energy_bookkeeping(dev_tables, systems, case_sys, eci_key, N, expect):
+    """Size-independent property: the sum of accepted dE reported by the sweep
+    equals E_potential(after) - E_potential(before) recomputed from scratch by
+    the (faithful) global evaluation; occupants stay in range; counters add up."""
+    mu = [0.2, -0.1][:len(systems[case_sys]["axes"]["end_members"])]
+    st, sysd, ex = _sweep_state(dev_tables, systems, case_sys, eci_key, N, 900.0, mu)
+    info = st.sweep_info()
+    assert info["evaluator"] == expect
+    n_cells = int(np.prod(N))
+
+    def potential():
+        comp = mol_composition(st.composition(), sysd["occ_to_species"], sysd["n_species"], n_cells)
+        return semigrand_potential_per_supercell(st.energy(), comp, sysd["axes"]["origin"],
+                                                 sysd["axes"]["Rt"], mu, n_cells)
+
+    p0 = potential()
+    cnt = st.sgc_sweep(5, seed=77)
+    p1 = potential()
+    n_mut = n_cells * len(sysd["mutable_sublats"])
+    assert cnt[0].n_attempt == 5 * n_mut
+    assert 0 < cnt[0].n_accept < cnt[0].n_attempt
+    assert cnt[0].dE_sum == pytest.approx(p1 - p0, rel=1e-9, abs=1e-7)
+    occ = st.download_occ()
+    nocc = np.array(st.tables.host.n_occ)
+    for b in range(len(nocc)):
+        seg = occ[b * n_cells:(b + 1) * n_cells]
+        assert seg.min() >= 0 and seg.max() < nocc[b]
+    st.close()
+
+
+def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
+    """Counter-based RNG: same seed -> same trajectory; replicas with identical
+    conditions but different replica index diverge; a batched run equals single runs."""
+    N = (16, 16, 16)
+    mu = [0.2, -0.1]
+    a, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=3, seed=5)
+    b, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=3, seed=5)
+    a.sgc_sweep(3, seed=9)
+    b.sgc_sweep(2, seed=9)
+    b.sgc_sweep(1, seed=9, first_sweep=2)   # continuing the stream == one call
+    for r in range(3):
+        assert (a.download_occ(r) == b.download_occ(r)).all()
+    assert (a.download_occ(0) != a.download_occ(1)).any()
+    a.close()
+    b.close()
+
+
+def test_pair_lut_sweep_equals_generic_sweep(dev_tables, systems):
+    """The LUT fast path and the generic evaluator make the same decisions when
+    they see the same random numbers?  They use different RNG counters, so we
+    check the PHYSICS instead: acceptance rate and energy after equilibration
+    agree within statistics (two independent evaluators, same ensemble)."""
+    mu = [0.2, -0.1]
+    T = 1200.0
+    res = {}
+    for N in ((16, 16, 16), (12, 12, 12)):
+        st, sysd, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, T, mu, seed=3)
+        st.sgc_sweep(200, seed=11)
+        acc, e = [], []
+        for k in range(20):
+            cnt = st.sgc_sweep(10, seed=11, first_sweep=200 + 10 * k)
+            acc.append(cnt[0].n_accept / cnt[0].n_attempt)
+            e.append(st.energy() / np.prod(N))
+        res[st.sweep_info()["evaluator"]] = (np.mean(acc), np.std(acc) / np.sqrt(20), np.mean(e),
+                                             np.std(e) / np.sqrt(20))
+        st.close()
+    (a1, sa1, e1, se1), (a2, sa2, e2, se2) = res["pair_lut"], res["generic"]
+    assert abs(a1 - a2) < 5 * np.hypot(sa1, sa2) + 2e-3
+    assert abs(e1 - e2) < 5 * np.hypot(se1, se2) + 2e-3
+
+
+def test_checkerboard_matches_sequential_thermodynamics(dev_tables, systems, oracle):
+    """north_star (3): checkerboard-mode averages agree with the reference's
+    sequential random-site Metropolis within 3 sigma (independent runs)."""
+    if oracle is None:
+        pytest.skip("oracle/_ref not built")
+    sysd = systems["fcc"]
+    eci = sysd["eci_sparse"]
+    N = 8
+    n_cells = N ** 3
+    T = 1500.0
+    mu = np.array([0.3, -0.4])
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=3, Rt=np.array(sysd["axes"]["Rt"]), origin=np.array(sysd["axes"]["origin"]))
+    sc = oracle.RefClexulator("fcc_default").supercell(N)
+    n_runs = 8
+    ref_e, ref_x = [], []
+    for run in range(n_runs):
+        occ = np.random.default_rng(100 + run).integers(0, 3, n_cells).astype(np.int32)
+        out = sc.metropolis_run(0, occ, prim, eci["index"], eci["value"], T, seed=1000 + run,
+                                n_steps=100 * n_cells, param_chem_pot=mu)
+        es, xs = [], []
+        occ = out["occ"]
+        for k in range(40):
+            out = sc.metropolis_run(0, occ, prim, eci["index"], eci["value"], T, seed=5000 + 97 * run + k,
+                                    n_steps=5 * n_cells, param_chem_pot=mu)
+            occ = out["occ"]
+            g = sc.global_corr(occ)
+            es.append(float(np.dot(eci["value"], g[eci["index"]])) / n_cells)
+            xs.append(np.bincount(occ, minlength=3) / n_cells)
+        ref_e.append(np.mean(es))
+        ref_x.append(np.mean(xs, axis=0))
+    st, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", (N, N, N), T, mu, n_replicas=n_runs, seed=8)
+    st.sgc_sweep(100, seed=21)
+    ge = np.zeros((n_runs, 40))
+    gx = np.zeros((n_runs, 40, 3))
+    for k in range(40):
+        st.sgc_sweep(5, seed=21, first_sweep=100 + 5 * k)
+        for r in range(n_runs):
+            ge[r, k] = st.energy(r) / n_cells
+            gx[r, k] = st.composition(r)[0] / n_cells
+    gpu_e = ge.mean(axis=1)
+    gpu_x = gx.mean(axis=1)
+    se = np.hypot(np.std(ref_e, ddof=1), np.std(gpu_e, ddof=1)) / np.sqrt(n_runs)
+    assert abs(np.mean(ref_e) - np.mean(gpu_e)) < 3 * se + 1e-4, (np.mean(ref_e), np.mean(gpu_e), se)
+    for s in range(3):
+        sx = np.hypot(np.std(np.array(ref_x)[:, s], ddof=1), np.std(gpu_x[:, s], ddof=1)) / np.sqrt(n_runs)
+        assert abs(np.mean(np.array(ref_x)[:, s]) - np.mean(gpu_x[:, s])) < 3 * sx + 1e-3
+    st.close()
+
+
+def test_error_paths(dev_tables, load_tables):
+    """Error behaviour mirrors the reference: bad input -> exception, state intact."""
+    st = _capi.State(dev_tables("fcc_default"), (8, 8, 8))
+    with pytest.raises(_capi.CmxError):
+        st.energy()                      # no ECI bound
+    with pytest.raises(_capi.CmxError):
+        st.upload_occ(np.full(512, 7, dtype=np.int32))   # occupant index out of range
+    with pytest.raises(_capi.CmxError):
+        st.upload_occ(np.zeros(5, dtype=np.int32))
+    with pytest.raises(_capi.CmxError):
+        st.delta_corr([10 ** 9], [1])
+    with pytest.raises(_capi.CmxError):
+        st.set_eci([99], [1.0])
+    with pytest.raises(_capi.CmxError):
+        st.set_conditions(-5.0)
+    st.set_eci([1], [0.5])
+    with pytest.raises(_capi.CmxError):
+        st.sgc_sweep(1, seed=1)           # conditions not set
+    assert st.delta_e(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int32)).shape == (0,)
+    with pytest.raises(_capi.CmxError):
+        _capi.State(dev_tables("fcc_default"), (0, 8, 8))
+    st.close()
