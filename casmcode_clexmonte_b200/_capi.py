@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
-    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sweep_info",
+    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info",
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
 ]
 
@@ -106,9 +106,11 @@ def lib():
     L.cmx_energy.argtypes = [vp, i32, C.POINTER(dbl)]
     L.cmx_composition.argtypes = [vp, i32, vp]
     L.cmx_sgc_sweep.argtypes = [vp, i64, u64, i64, vp]
-    L.cmx_sgc_sweep_kgroup.argtypes = [vp, u64, i64, i32, vp]
+    L.cmx_sgc_sweep_kgroup.argtypes = [vp, u64, i64, i32]
+    L.cmx_counters_reset.argtypes = [vp]
+    L.cmx_counters_read.argtypes = [vp, vp]
     L.cmx_sweep_info.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(dbl), C.POINTER(dbl),
-                                 C.POINTER(i32)]
+                                 C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
@@ -310,18 +312,25 @@ class State:
                                   C.byref(cnt) if counters else None))
         return cnt
 
-    def sgc_sweep_kgroup(self, seed: int, sweep: int, kgroup: int, counters: bool = False):
-        cnt = (Counters * self.n_replicas)() if counters else None
-        check(lib().cmx_sgc_sweep_kgroup(self._h, int(seed), int(sweep), int(kgroup),
-                                         C.byref(cnt) if counters else None))
+    def sgc_sweep_kgroup(self, seed: int, sweep: int, kgroup: int) -> None:
+        """Asynchronous: enqueue one k-colour group of one sweep on the state's stream."""
+        check(lib().cmx_sgc_sweep_kgroup(self._h, int(seed), int(sweep), int(kgroup)))
+
+    def counters_reset(self) -> None:
+        check(lib().cmx_counters_reset(self._h))
+
+    def counters_read(self):
+        cnt = (Counters * self.n_replicas)()
+        check(lib().cmx_counters_read(self._h, C.byref(cnt)))
         return cnt
 
     def sweep_info(self) -> dict:
         name = C.create_string_buffer(32)
-        b, f, nc = C.c_double(), C.c_double(), C.c_int32()
-        check(lib().cmx_sweep_info(self._h, name, 32, C.byref(b), C.byref(f), C.byref(nc)))
+        b, f, nc, rk = C.c_double(), C.c_double(), C.c_int32(), C.c_int32()
+        S = (C.c_int32 * 3)()
+        check(lib().cmx_sweep_info(self._h, name, 32, C.byref(b), C.byref(f), C.byref(nc), S, C.byref(rk)))
         return dict(evaluator=name.value.decode(), bytes_per_step=b.value, flops_per_step=f.value,
-                    n_colours=nc.value)
+                    n_colours=nc.value, colour_strides=tuple(S), range_k=rk.value)
 
     def metropolis_sequential(self, mode: int, n_steps: int, seed: int, log_cap: int = 0,
                               replica: int = 0) -> dict:

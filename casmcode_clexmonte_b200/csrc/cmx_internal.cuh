@@ -88,6 +88,7 @@ struct SweepPlan {
   long long *d_part_acc = nullptr;
   double *d_part_dE = nullptr;
   int32_t part_blocks = 0;
+  long long attempts = 0;  // attempted steps per replica since the last reset
   // algorithmic work per attempted step, counted from the tables
   double bytes_per_step = 0, flops_per_step = 0;
 };

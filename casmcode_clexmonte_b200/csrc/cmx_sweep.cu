@@ -774,30 +774,46 @@ static int sweep_prepare(cmx_state *s, const char *who) {
     items = (uint32_t)(s->g.N0 / 8) * (s->g.N1 / 2) * (s->g.N2 / 2);
   else
     items = (uint32_t)(s->g.N0 / P.S[0]) * (s->g.N1 / P.S[1]) * (s->g.N2 / P.S[2]);
-  int rc = ensure_partials(s, sweep_blocks_per_replica(items, s->n_replicas));
-  if (rc) return rc;
-  size_t n = (size_t)P.part_blocks * s->n_replicas;
-  CMX_CUDA(cudaMemsetAsync(P.d_part_acc, 0, sizeof(long long) * n, s->stream));
-  CMX_CUDA(cudaMemsetAsync(P.d_part_dE, 0, sizeof(double) * n, s->stream));
+  int blocks = sweep_blocks_per_replica(items, s->n_replicas);
+  if (P.part_blocks != blocks || !P.d_part_acc) {
+    int rc = ensure_partials(s, blocks);
+    if (rc) return rc;
+    size_t n = (size_t)P.part_blocks * s->n_replicas;
+    CMX_CUDA(cudaMemsetAsync(P.d_part_acc, 0, sizeof(long long) * n, s->stream));
+    CMX_CUDA(cudaMemsetAsync(P.d_part_dE, 0, sizeof(double) * n, s->stream));
+    P.attempts = 0;
+  }
   return CMX_OK;
 }
 
-static int sweep_finish(cmx_state *s, long long attempts, cmx_counters *counters) {
+extern "C" int cmx_counters_reset(cmx_state *s) {
+  int rc = sweep_prepare(s, "cmx_counters_reset");
+  if (rc) return rc;
   SweepPlan &P = s->plan;
-  if (counters) {
-    k_reduce_counters<<<s->n_replicas, 32, 0, s->stream>>>(P.d_part_acc, P.d_part_dE,
-                                                          P.part_blocks, attempts, s->d_counters);
-    CMX_CUDA(cudaGetLastError());
-    CMX_CUDA(cudaMemcpyAsync(counters, s->d_counters, sizeof(cmx_counters) * s->n_replicas,
-                             cudaMemcpyDeviceToHost, s->stream));
-  }
+  size_t n = (size_t)P.part_blocks * s->n_replicas;
+  CMX_CUDA(cudaMemsetAsync(P.d_part_acc, 0, sizeof(long long) * n, s->stream));
+  CMX_CUDA(cudaMemsetAsync(P.d_part_dE, 0, sizeof(double) * n, s->stream));
+  P.attempts = 0;
+  return CMX_OK;
+}
+
+extern "C" int cmx_counters_read(cmx_state *s, cmx_counters *counters) {
+  int rc = sweep_prepare(s, "cmx_counters_read");
+  if (rc) return rc;
+  if (!counters) return invalid("cmx_counters_read: null output");
+  SweepPlan &P = s->plan;
+  k_reduce_counters<<<s->n_replicas, 32, 0, s->stream>>>(P.d_part_acc, P.d_part_dE, P.part_blocks,
+                                                        P.attempts, s->d_counters);
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaMemcpyAsync(counters, s->d_counters, sizeof(cmx_counters) * s->n_replicas,
+                           cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
   return CMX_OK;
 }
 
 extern "C" int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
                              int64_t first_sweep, cmx_counters *counters) {
-  int rc = sweep_prepare(s, "cmx_sgc_sweep");
+  int rc = cmx_counters_reset(s);
   if (rc) return rc;
   if (n_sweeps < 0) return invalid("cmx_sgc_sweep: n_sweeps < 0");
   if (s->g.halo) return invalid("cmx_sgc_sweep: slab states are driven by cmx_sgc_sweep_kgroup");
@@ -805,13 +821,14 @@ extern "C" int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
     rc = sweep_once(s, seed, first_sweep + w, -1, 0);
     if (rc) return rc;
   }
-  long long per = (long long)s->g.n_cells * (long long)s->plan.mut_points.size();
-  return sweep_finish(s, per * n_sweeps, counters);
+  s->plan.attempts += (long long)s->g.n_cells * (long long)s->plan.mut_points.size() * n_sweeps;
+  if (counters) return cmx_counters_read(s, counters);
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  return CMX_OK;
 }
 
-// k_offset rides in `reserved`-free fashion: slab states keep it in the state
 extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
-                                    int32_t kgroup, cmx_counters *counters) {
+                                    int32_t kgroup) {
   int rc = sweep_prepare(s, "cmx_sgc_sweep_kgroup");
   if (rc) return rc;
   if (kgroup < -1 || kgroup >= s->plan.S[2]) return invalid("cmx_sgc_sweep_kgroup: bad kgroup");
@@ -819,12 +836,14 @@ extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
   if (rc) return rc;
   long long per = (long long)s->g.n_cells * (long long)s->plan.mut_points.size();
   if (kgroup >= 0) per /= s->plan.S[2];
-  return sweep_finish(s, per, counters);
+  s->plan.attempts += per;
+  return CMX_OK;  // asynchronous: enqueued on the state's stream
 }
 
 extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
                               double *bytes_per_step, double *flops_per_step,
-                              int32_t *n_colours) {
+                              int32_t *n_colours, int32_t *colour_strides,
+                              int32_t *range_k) {
   if (!s) return invalid("cmx_sweep_info: null state");
   if (!s->plan.valid) {
     cmx_set_error("cmx_sweep_info: no sweep plan");
@@ -838,5 +857,8 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
   if (bytes_per_step) *bytes_per_step = s->plan.bytes_per_step;
   if (flops_per_step) *flops_per_step = s->plan.flops_per_step;
   if (n_colours) *n_colours = s->plan.n_colours;
+  if (colour_strides)
+    for (int a = 0; a < 3; ++a) colour_strides[a] = s->plan.S[a];
+  if (range_k) *range_k = s->plan.range_k;
   return CMX_OK;
 }

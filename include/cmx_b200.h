@@ -192,17 +192,22 @@ typedef struct cmx_counters {
  * first sweep (the RNG counter), so consecutive calls continue one stream. */
 int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
                   int64_t first_sweep, cmx_counters *counters);
-/* As above but only the colours with k-parity group `kgroup` of the colour
- * ordering (0 or 1; -1 = both) -- the unit between two halo exchanges in the
- * slab-decomposed run. */
+/* The unit between two halo exchanges of a slab-decomposed run: one pass over
+ * the colours whose k-colour is `kgroup` (0 .. S_k-1; -1 = all).  ASYNCHRONOUS:
+ * the kernels are enqueued on the state's stream (cmx_state_stream) and the
+ * call returns; counters accumulate until cmx_counters_reset. */
 int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
-                         int32_t kgroup, cmx_counters *counters);
+                         int32_t kgroup);
+int cmx_counters_reset(cmx_state *s);
+/* synchronises the state's stream; counters[n_replicas] */
+int cmx_counters_read(cmx_state *s, cmx_counters *counters);
 /* Name of the evaluator the sweep uses for the bound ECI ("pair_lut",
  * "generic"); algorithmic work per attempted step for the roofline
  * bookkeeping: neighbor bytes read and FP64 flops, counted from the tables. */
 int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
                    double *bytes_per_step, double *flops_per_step,
-                   int32_t *n_colours);
+                   int32_t *n_colours, int32_t *colour_strides /*[3]*/,
+                   int32_t *range_k);
 
 /* Occupant bookkeeping needed by the reference-order mode:
  * sublat_to_asym[n_sublat], occ_to_species[n_sublat][max_occ] (-1 padded). */
