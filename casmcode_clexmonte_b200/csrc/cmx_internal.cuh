@@ -81,7 +81,8 @@ struct SweepPlan {
   uint32_t mask = 0;      // bit (dk+1)*9 + (dj+1)*3 + (di+1)
   int32_t n_lut = 0;      // nocc*(nocc-1)*256 entries
   double *d_pair_dE = nullptr;       // [n_lut] clex dE per (oi, alt, counts)
-  unsigned long long *d_thr = nullptr;  // [replica][n_lut] acceptance thresholds
+  uint32_t *d_thr = nullptr;     // [replica][n_lut] acceptance thresholds, high 31 bits
+  uint32_t *d_thr_lo = nullptr;  // [replica][n_lut] low 22 bits (tie break)
   double *d_dEpot = nullptr;            // [replica][n_lut] dE - exch
   bool thr_dirty = true;
   // per-block partial counters of the current call

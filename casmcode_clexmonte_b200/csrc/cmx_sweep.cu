@@ -36,6 +36,7 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_gt_n);
   cudaFree(p.d_pair_dE);
   cudaFree(p.d_thr);
+  cudaFree(p.d_thr_lo);
   cudaFree(p.d_dEpot);
   cudaFree(p.d_part_acc);
   cudaFree(p.d_part_dE);
@@ -81,11 +82,15 @@ __global__ void k_build_pair_lut(DevTables T, int nocc, int z,
 // thresholds: accept  <=>  r53 < thr,  r53 uniform on [0, 2^53):
 //   dE < 0            -> always            (metropolis_acceptance [EXT])
 //   else u < exp(-dE*beta), u = r53 * 2^-53
+// stored split: thr_hi = thr >> 22 (compared against the 31 random bits every
+// site draws) and thr_lo = thr & (2^22-1) (22 more bits, drawn lazily only when
+// the first 31 tie) -- together exactly the 53-bit comparison.
 __global__ void k_build_thresholds(const double *__restrict__ lut, int n_lut,
                                    int nocc, int max_occ, int b,
                                    const double *__restrict__ beta,
                                    const double *__restrict__ exch, int exch_stride,
-                                   unsigned long long *__restrict__ thr,
+                                   uint32_t *__restrict__ thr_hi,
+                                   uint32_t *__restrict__ thr_lo,
                                    double *__restrict__ dEpot) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   int r = blockIdx.y;
@@ -105,7 +110,8 @@ __global__ void k_build_thresholds(const double *__restrict__ lut, int n_lut,
     double v = ceil(p * two53);
     t = (unsigned long long)v;
   }
-  thr[(size_t)r * n_lut + e] = t;
+  thr_hi[(size_t)r * n_lut + e] = (uint32_t)(t >> 22);
+  thr_lo[(size_t)r * n_lut + e] = (uint32_t)(t & 0x3FFFFFull);
   dEpot[(size_t)r * n_lut + e] = dE;
 }
 
@@ -132,14 +138,16 @@ __device__ __forceinline__ void fastdivmod(uint32_t n, FastDiv f, uint32_t &q,
 }
 
 struct PairSweepArgs {
-  int8_t *occ;  // replica 0 base
+  int8_t *occ;  // replica 0 base (start of the low ghost layers)
   Geom g;
   int cy, cz;          // colour parities along j, k (i parity is a template arg)
   uint32_t mask;       // runtime neighbor mask
   FastDiv divW, divJ;  // chunks per row, rows per layer of this colour
-  uint32_t items;      // per replica
-  const unsigned long long *thr;  // [replica][n_lut]
-  const double *dEpot;            // [replica][n_lut]
+  uint32_t W, J, K;    // item grid of one colour: chunk, row pair, layer pair
+  uint32_t dc, djj, dkk;  // grid stride decomposed on (c, jj, kk)
+  const uint32_t *thr_hi;  // [replica][n_lut]
+  const uint32_t *thr_lo;  // [replica][n_lut]
+  const double *dEpot;     // [replica][n_lut]
   int n_lut;
   long long *part_acc;  // [replica][gridDim.x]
   double *part_dE;
@@ -166,16 +174,27 @@ __device__ __forceinline__ uint32_t extract4(uint32_t lo, uint32_t hi,
   }
 }
 
+// One thread owns 4 same-colour sites of one 8-byte row chunk per iteration.
+//  * occupants of the <= 9 neighbor rows arrive as 8-byte loads (+ one 4-byte
+//    side word where the colour needs the byte just outside the chunk),
+//    32-bit offsets from the replica base;
+//  * the species counts of the 4 sites are accumulated bytewise in one
+//    register (species 1 in the low nibble, species 2 in the high nibble);
+//  * one Philox4x32-10 call yields the 4 x (31-bit uniform + 1 proposal bit);
+//    the acceptance test is one integer compare against the shared-memory
+//    threshold table, the remaining 22 bits of the 53-bit uniform are drawn
+//    only on a tie of the first 31 (probability 2^-31);
+//  * accepted dE (tabulated) is summed in FP64 per thread, reduced per block.
 template <int CX, int NOCC, uint32_t MASK_CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     k_sweep_pair_lut(PairSweepArgs a) {
-  __shared__ unsigned long long sh_thr[NOCC * (NOCC - 1) * 256];
+  __shared__ uint32_t sh_thr[NOCC * (NOCC - 1) * 256];
   __shared__ double sh_dE[NOCC * (NOCC - 1) * 256];
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
   const int r = blockIdx.y;
   {
-    const unsigned long long *gt = a.thr + (size_t)r * a.n_lut;
+    const uint32_t *gt = a.thr_hi + (size_t)r * a.n_lut;
     const double *ge = a.dEpot + (size_t)r * a.n_lut;
     for (int q = threadIdx.x; q < a.n_lut; q += blockDim.x) {
       sh_thr[q] = gt[q];
@@ -185,35 +204,41 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const Geom &g = a.g;
-  int8_t *base = a.occ + (size_t)r * g.rep_stride + (size_t)g.halo * g.layer;
-  const int N0 = g.N0, N1 = g.N1, N2 = g.N2;
-  long long n_acc = 0;
+  int8_t *base = a.occ + (size_t)r * g.rep_stride;  // includes the ghost layers
+  // keep the replica base in a register pair: without this the compiler
+  // re-derives r * rep_stride (a 64-bit multiply-add) for every load
+  asm volatile("" : "+l"(base));
+  const uint32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
+  const uint32_t layer = N0 * N1;
+  const bool halo = g.halo != 0;
+  uint32_t n_acc = 0;  // < 2^32 accepted sites per thread and launch
   double e_sum = 0.0;
 
-  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < a.items;
-       item += gridDim.x * blockDim.x) {
-    uint32_t row, c, kk, jj;
+  uint32_t c, jj, kk;
+  {
+    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x, row;
     fastdivmod(item, a.divW, row, c);
     fastdivmod(row, a.divJ, kk, jj);
-    const int j = 2 * (int)jj + a.cy, k = 2 * (int)kk + a.cz;
-    const int x0 = 8 * (int)c;
-    // neighbor rows
-    int jr[3], kr[3];
-    jr[0] = (j == 0) ? N1 - 1 : j - 1;
-    jr[1] = j;
-    jr[2] = (j == N1 - 1) ? 0 : j + 1;
-    if (g.halo) {
-      kr[0] = k - 1;
-      kr[2] = k + 1;
-    } else {
-      kr[0] = (k == 0) ? N2 - 1 : k - 1;
-      kr[2] = (k == N2 - 1) ? 0 : k + 1;
-    }
-    kr[1] = k;
+  }
+  while (kk < a.K) {
+    const uint32_t j = 2 * jj + a.cy, k = 2 * kk + a.cz;
+    const uint32_t x0 = 8 * c;
+    // 32-bit byte offsets of the neighbor rows relative to the replica base
+    const uint32_t off_c = ((k + g.halo) * N1 + j) * N0 + x0;
+    uint32_t dj[3], dk[3];
+    dj[0] = (j == 0) ? (N1 - 1) * N0 : 0u - N0;
+    dj[1] = 0;
+    dj[2] = (j == N1 - 1) ? 0u - (N1 - 1) * N0 : N0;
+    dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : 0u - layer;
+    dk[1] = 0;
+    dk[2] = (!halo && k == N2 - 1) ? 0u - (N2 - 1) * layer : layer;
     // the side word holds the byte just outside the chunk on the side this
     // colour needs: x0-1 for CX == 0 (dx = -1), x0+8 for CX == 1 (dx = +1)
-    const int xs = (CX == 0) ? ((x0 == 0 ? N0 : x0) - 4) : ((x0 + 8 == N0) ? 0 : x0 + 8);
-    uint32_t acc = 0, self4 = 0;
+    const uint32_t dside = (CX == 0) ? ((x0 == 0) ? N0 - 4 : 0u - 4u)
+                                     : ((x0 + 8 == N0) ? 8u - N0 : 8u);
+    // bytewise sums over the neighbors of the 4 sites: s1 = sum of occupant
+    // codes (n1 + 2 n2 per lane), s2 = sum of (code & 2) (2 n2 per lane)
+    uint32_t s1 = 0, s2 = 0, self4 = 0;
     uint32_t lo_c = 0, hi_c = 0;
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
@@ -222,11 +247,11 @@ __global__ void __launch_bounds__(256)
         const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
         const bool center = (dz == 0 && dy == 0);
         if (m3 == 0 && !center) continue;
-        const int8_t *rp = base + ((int64_t)kr[dz + 1] * N1 + jr[dy + 1]) * N0;
-        const uint2 ch = *reinterpret_cast<const uint2 *>(rp + x0);
+        const uint32_t off = off_c + dk[dz + 1] + dj[dy + 1];
+        const uint2 ch = *reinterpret_cast<const uint2 *>(base + off);
         uint32_t side = 0;
         const bool need_side = (CX == 0) ? (m3 & 1u) : (m3 & 4u);
-        if (need_side) side = *reinterpret_cast<const uint32_t *>(rp + xs);
+        if (need_side) side = *reinterpret_cast<const uint32_t *>(base + (off + dside));
         if (center) {
           lo_c = ch.x;
           hi_c = ch.y;
@@ -236,37 +261,59 @@ __global__ void __launch_bounds__(256)
         for (int dx = -1; dx <= 1; ++dx) {
           if (!(m3 & (1u << (dx + 1)))) continue;
           uint32_t w = extract4<CX>(ch.x, ch.y, side, dx);
-          // occupant codes 0/1/2 -> species-1 count in the low nibble,
-          // species-2 count in the high nibble of each byte lane
-          acc += w + (w & 0x02020202u) * 7u;
+          s1 += w;
+          s2 += w & 0x02020202u;
         }
       }
     }
-    // ---- random numbers: 64 bits per site
-    const uint32_t gid = ((uint32_t)(k + a.k_offset) * (uint32_t)N1 + (uint32_t)j) * a.divW.d + c;
-    Philox pa = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi, a.k0, a.k1);
-    Philox pb = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi | 1u, a.k0, a.k1);
-    uint32_t new4 = self4;
-    int acc_here = 0;
+    // species-1 count in the low nibble, species-2 count in the high nibble of
+    // each byte lane: (s1 - s2) + 8 * s2 = n1 + 16 n2
+    const uint32_t acc = (s1 - s2) + (s2 << 3);
+    // ---- random numbers: one 32-bit word per site
+    const uint32_t gid = ((k + (uint32_t)a.k_offset) * N1 + j) * a.W + c;
+    const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi, a.k0, a.k1);
+    uint32_t new4 = 0;
+    uint32_t ties = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint32_t rlo = (q < 2) ? pa.c[2 * q] : pb.c[2 * (q - 2)];
-      const uint32_t rhi = (q < 2) ? pa.c[2 * q + 1] : pb.c[2 * (q - 2) + 1];
+      const uint32_t w = ph.c[q];
       const uint32_t oi = (self4 >> (8 * q)) & 0xffu;
-      const uint32_t alt = (NOCC == 3) ? (rhi >> 31) : 0u;
-      uint32_t of = oi + 1u + alt;
-      of -= (of >= (uint32_t)NOCC) ? (uint32_t)NOCC : 0u;
+      const uint32_t alt = (NOCC == 3) ? (w & 1u) : 0u;
+      const uint32_t pair = oi * (NOCC - 1) + alt;
+      // of = (oi + 1 + alt) mod NOCC, two bits per pair packed in a constant
+      const uint32_t of = (NOCC == 3) ? ((0x429u >> (2 * pair)) & 3u) : (oi ^ 1u);
       const uint32_t cnt = (acc >> (8 * q)) & 0xffu;
-      const uint32_t idx = ((oi * (NOCC - 1) + alt) << 8) | cnt;
-      const unsigned long long thr = sh_thr[idx];
-      const unsigned long long u53 = ((unsigned long long)(rhi & 0x1FFFFFu) << 32) | rlo;
-      if (u53 < thr) {
-        new4 = (new4 & ~(0xffu << (8 * q))) | (of << (8 * q));
-        e_sum += sh_dE[idx];
-        ++acc_here;
+      const uint32_t idx = (pair << 8) | cnt;
+      const uint32_t thr = sh_thr[idx];
+      const uint32_t u31 = w >> 1;
+      const bool ok = u31 < thr;
+      ties |= (u31 == thr) ? (1u << q) : 0u;
+      double d = 0.0;
+      if (ok) d = sh_dE[idx];
+      e_sum += d;
+      n_acc += ok ? 1u : 0u;
+      new4 |= (ok ? of : oi) << (8 * q);
+    }
+    if (ties) {  // probability 2^-31 per site: draw the low 22 bits of the uniform
+      const Philox p2 = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi | 1u, a.k0, a.k1);
+      const uint32_t *gl = a.thr_lo + (size_t)r * a.n_lut;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!(ties & (1u << q))) continue;
+        const uint32_t w = ph.c[q];
+        const uint32_t oi = (self4 >> (8 * q)) & 0xffu;
+        const uint32_t alt = (NOCC == 3) ? (w & 1u) : 0u;
+        uint32_t of = oi + 1u + alt;
+        of -= (of >= (uint32_t)NOCC) ? (uint32_t)NOCC : 0u;
+        const uint32_t idx = ((oi * (NOCC - 1) + alt) << 8) | ((acc >> (8 * q)) & 0xffu);
+        if ((p2.c[q] & 0x3FFFFFu) < gl[idx]) {
+          new4 = (new4 & ~(0xffu << (8 * q))) | (of << (8 * q));
+          e_sum += sh_dE[idx];
+          n_acc += 1;
+        }
       }
     }
-    if (acc_here) {
+    if (new4 != self4) {
       uint2 out;
       if (CX == 0) {
         out.x = __byte_perm(lo_c, new4, 0x3514);
@@ -275,20 +322,31 @@ __global__ void __launch_bounds__(256)
         out.x = __byte_perm(lo_c, new4, 0x5240);
         out.y = __byte_perm(hi_c, new4, 0x7260);
       }
-      int8_t *rp = base + ((int64_t)k * N1 + j) * N0;
-      *reinterpret_cast<uint2 *>(rp + x0) = out;
-      n_acc += acc_here;
+      *reinterpret_cast<uint2 *>(base + off_c) = out;
     }
+    // ---- next item: grid stride decomposed on (c, jj, kk)
+    c += a.dc;
+    if (c >= a.W) {
+      c -= a.W;
+      jj += 1;
+    }
+    jj += a.djj;
+    if (jj >= a.J) {
+      jj -= a.J;
+      kk += 1;
+    }
+    kk += a.dkk;
   }
   // ---- block reduction of the counters (fixed order -> deterministic)
+  long long n_acc64 = n_acc;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    n_acc += __shfl_down_sync(0xffffffffu, n_acc, o);
+    n_acc64 += __shfl_down_sync(0xffffffffu, n_acc64, o);
     e_sum += __shfl_down_sync(0xffffffffu, e_sum, o);
   }
   const int wid = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
-    sh_acc[wid] = n_acc;
+    sh_acc[wid] = n_acc64;
     sh_sum[wid] = e_sum;
   }
   __syncthreads();
@@ -551,6 +609,7 @@ int cmx_plan_sweep(cmx_state *s) {
   bool ok = (T.n_sublat == 1 && np == 1 && P.mut_points.size() == 1 &&
              t->n_occ[0] >= 2 && t->n_occ[0] <= 3 && T.nlist_len <= 64 &&
              s->g.N0 % 8 == 0 && s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 &&
+             s->g.rep_stride < (int64_t)0xFFFFFFFFll &&
              P.S[0] == 2 && P.S[1] == 2 && P.S[2] == 2);
   std::map<int, std::vector<double>> V;  // neighbor -> V[on][oi][of]
   if (ok) {
@@ -606,7 +665,8 @@ int cmx_plan_sweep(cmx_state *s) {
     CMX_CUDA(cudaGetLastError());
     CMX_CUDA(cudaStreamSynchronize(s->stream));
     cudaFree(d_cls);
-    CMX_CUDA(cudaMalloc((void **)&P.d_thr, sizeof(unsigned long long) * P.n_lut * s->n_replicas));
+    CMX_CUDA(cudaMalloc((void **)&P.d_thr, sizeof(uint32_t) * P.n_lut * s->n_replicas));
+    CMX_CUDA(cudaMalloc((void **)&P.d_thr_lo, sizeof(uint32_t) * P.n_lut * s->n_replicas));
     CMX_CUDA(cudaMalloc((void **)&P.d_dEpot, sizeof(double) * P.n_lut * s->n_replicas));
     P.pair_lut = true;
     // per step: z neighbor bytes + own byte read, 1 byte written; the FP64
@@ -668,7 +728,7 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
       dim3 grid((P.n_lut + 127) / 128, s->n_replicas);
       k_build_thresholds<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.n_lut, P.nocc, T.max_occ, 0,
                                                       s->d_beta, s->d_exch, (int)exs, P.d_thr,
-                                                      P.d_dEpot);
+                                                      P.d_thr_lo, P.d_dEpot);
       CMX_CUDA(cudaGetLastError());
       P.thr_dirty = false;
     }
@@ -679,8 +739,17 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     uint32_t W = g.N0 / 8, J = g.N1 / 2, K = g.N2 / 2;
     a.divW = make_fastdiv(W);
     a.divJ = make_fastdiv(J);
-    a.items = W * J * K;
-    a.thr = P.d_thr;
+    a.W = W;
+    a.J = J;
+    a.K = K;
+    {
+      uint32_t stride = (uint32_t)P.part_blocks * 256u;
+      a.dc = stride % W;
+      a.djj = (stride / W) % J;
+      a.dkk = stride / (W * J);
+    }
+    a.thr_hi = P.d_thr;
+    a.thr_lo = P.d_thr_lo;
     a.dEpot = P.d_dEpot;
     a.n_lut = P.n_lut;
     a.part_acc = P.d_part_acc;
