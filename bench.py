@@ -228,8 +228,8 @@ def main():
         attempts = K * S * n_sites
         assert cnt[0].n_attempt == attempts
         value = attempts / (ms * 1e-3)
-        launches = K * S * info["n_colours"] + 3
-        kernel_ms = ms / (K * S * info["n_colours"])
+        launches = K * S * info["launches_per_sweep"] + 3
+        kernel_ms = ms / (K * S * info["launches_per_sweep"])
         # ---- end to end: host buffers through the C ABI, copies inside the timed region
         host = torch.empty(n_sites, dtype=torch.int8).pin_memory()
         harr = host.numpy()
@@ -269,11 +269,11 @@ def main():
         peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    sites_per_launch = n_sites / world / info["n_colours"]
+    sites_per_launch = n_sites / world / info["launches_per_sweep"]
     alg_bytes = 2.0 * sites_per_launch           # 2 B per step at the HBM level
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_pair_lut",
+                "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_pair16",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_step_hbm": 2.0,
                 "algorithmic_bytes_per_step_l2": info["bytes_per_step"],
                 "note": "the sweep is instruction-issue bound, not HBM bound: see DESIGN.md and profiles/"}

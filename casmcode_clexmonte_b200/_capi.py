@@ -19,6 +19,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libcmx_b200.so"
 
 CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
+CMX_SWEEP_NO_DE_SUM, CMX_SWEEP_FORCE_GENERIC = 1, 2
 
 # every symbol include/cmx_b200.h declares
 EXPORTED_SYMBOLS = [
@@ -31,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
-    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info",
+    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches",
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
 ]
 
@@ -108,9 +109,11 @@ def lib():
     L.cmx_sgc_sweep.argtypes = [vp, i64, u64, i64, vp]
     L.cmx_sgc_sweep_kgroup.argtypes = [vp, u64, i64, i32]
     L.cmx_counters_reset.argtypes = [vp]
+    L.cmx_state_set_sweep_flags.argtypes = [vp, C.c_uint32]
     L.cmx_counters_read.argtypes = [vp, vp]
     L.cmx_sweep_info.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(dbl), C.POINTER(dbl),
                                  C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.cmx_sweep_launches.argtypes = [vp, C.POINTER(i32)]
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
@@ -316,6 +319,9 @@ class State:
         """Asynchronous: enqueue one k-colour group of one sweep on the state's stream."""
         check(lib().cmx_sgc_sweep_kgroup(self._h, int(seed), int(sweep), int(kgroup)))
 
+    def set_sweep_flags(self, flags: int) -> None:
+        check(lib().cmx_state_set_sweep_flags(self._h, int(flags)))
+
     def counters_reset(self) -> None:
         check(lib().cmx_counters_reset(self._h))
 
@@ -329,8 +335,11 @@ class State:
         b, f, nc, rk = C.c_double(), C.c_double(), C.c_int32(), C.c_int32()
         S = (C.c_int32 * 3)()
         check(lib().cmx_sweep_info(self._h, name, 32, C.byref(b), C.byref(f), C.byref(nc), S, C.byref(rk)))
+        nl = C.c_int32()
+        check(lib().cmx_sweep_launches(self._h, C.byref(nl)))
         return dict(evaluator=name.value.decode(), bytes_per_step=b.value, flops_per_step=f.value,
-                    n_colours=nc.value, colour_strides=tuple(S), range_k=rk.value)
+                    n_colours=nc.value, colour_strides=tuple(S), range_k=rk.value,
+                    launches_per_sweep=nl.value)
 
     def metropolis_sequential(self, mode: int, n_steps: int, seed: int, log_cap: int = 0,
                               replica: int = 0) -> dict:

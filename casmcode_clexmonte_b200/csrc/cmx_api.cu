@@ -149,6 +149,7 @@ extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
   g.n_cells = g.layer * N2;
   g.sub_stride = g.layer * (N2 + 2 * halo);
   g.rep_stride = g.sub_stride * t->d.n_sublat;
+  g.coded = (t->d.n_sublat == 1 && t->n_occ[0] == 3) ? 1 : 0;
   size_t bytes = (size_t)g.rep_stride * n_replicas;
   cudaError_t e = cudaMalloc(&s->d_occ, bytes);
   if (e != cudaSuccess) {
@@ -217,14 +218,15 @@ __global__ void k_scatter_occ(const SrcT *__restrict__ src, int8_t *dst, Geom g,
     int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
     int v = (int)src[l];
     flag |= (v < 0 || v >= n_occ[b]);
-    dst[b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)v;
+    dst[b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)cmx_enc(g, v);
   }
   if (flag) *bad = 1;
 }
 // in-place validation of an int8 image copied straight into the state (16 sites
 // per thread-iteration; n_cells is a multiple of 16 on this path)
-__global__ void k_validate_occ16(const int4 *__restrict__ occ, int64_t n16,
-                                 int64_t cells16, const int32_t *__restrict__ n_occ,
+// (and re-coded in place when the state stores occupant 2 as 16, Geom::coded)
+__global__ void k_validate_occ16(int4 *occ, int64_t n16, int64_t cells16,
+                                 const int32_t *__restrict__ n_occ, int coded,
                                  int *bad) {
   int flag = 0;
   for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n16;
@@ -233,9 +235,13 @@ __global__ void k_validate_occ16(const int4 *__restrict__ occ, int64_t n16,
     int4 v = occ[x];
     uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 4; ++q) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) flag |= (int)((w[q] >> (8 * k)) & 0xffu) >= no;
+      // 2 -> 16 per byte lane: move bit 1 to bit 4
+      w[q] = (w[q] & 0x01010101u) | ((w[q] & 0x02020202u) << 3);
+    }
+    if (coded) occ[x] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
   }
   if (flag) *bad = 1;
 }
@@ -246,7 +252,7 @@ __global__ void k_gather_occ(const int8_t *__restrict__ src, DstT *dst, Geom g,
   for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < total;
        l += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
-    dst[l] = (DstT)src[b * g.sub_stride + g.halo * g.layer + cell];
+    dst[l] = (DstT)cmx_dec(src[b * g.sub_stride + g.halo * g.layer + cell]);
   }
 }
 
@@ -270,8 +276,9 @@ static int upload_occ(cmx_state *s, int32_t replica, const T *occ) {
     // device layout == reference layout: one DMA, validated in place.  On a
     // bad index the previous occupation is lost -- the caller gets an error.
     CMX_CUDA(cudaMemcpyAsync(dst, occ, n, cudaMemcpyHostToDevice, s->stream));
-    k_validate_occ16<<<1184, 256, 0, s->stream>>>((const int4 *)dst, (int64_t)(n / 16),
-                                                  s->g.n_cells / 16, s->t->d.n_occ, s->d_flag);
+    k_validate_occ16<<<1184, 256, 0, s->stream>>>((int4 *)dst, (int64_t)(n / 16),
+                                                  s->g.n_cells / 16, s->t->d.n_occ,
+                                                  s->g.coded, s->d_flag);
   } else {
     rc = cmx_scratch(s, n * sizeof(T));
     if (rc) return rc;
@@ -296,7 +303,7 @@ static int download_occ(const cmx_state *cs, int32_t replica, T *occ) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
-  if (sizeof(T) == 1 && s->g.halo == 0) {
+  if (sizeof(T) == 1 && s->g.halo == 0 && !s->g.coded) {
     CMX_CUDA(cudaMemcpyAsync(occ, src, n, cudaMemcpyDeviceToHost, s->stream));
     CMX_CUDA(cudaStreamSynchronize(s->stream));
     return CMX_OK;
@@ -342,7 +349,7 @@ __global__ void k_randomize(int8_t *occ, Geom g, int n_sublat, int n_replicas,
                                0x52414e44u, k0, k1);
       v = (int)__umulhi(p.c[0], (uint32_t)no);
     }
-    occ[r * g.rep_stride + b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)v;
+    occ[r * g.rep_stride + b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)cmx_enc(g, v);
   }
 }
 

@@ -59,7 +59,7 @@ __global__ void k_corr_batch(DevTables T, Geom g, const int8_t *__restrict__ occ
     out[x] = cmx_eval_function(T, g, occ, T.point_gbeg[fi], T.point_gbeg[fi + 1],
                                i, j, k, ov, b, 0, 0);
   } else {
-    int oi = occ[cmx_site_offset(g, b, i, j, k)];
+    int oi = cmx_dec(occ[cmx_site_offset(g, b, i, j, k)]);
     out[x] = cmx_eval_function(T, g, occ, T.delta_gbeg[fi], T.delta_gbeg[fi + 1],
                                i, j, k, ov, b, oi, new_occ[item]);
   }
@@ -193,7 +193,7 @@ __global__ void k_event_energy(Geom g, const int8_t *__restrict__ occ, int64_t n
       int b = (int)(li / g.n_cells);
       int i, j, k;
       cell_ijk(g, li - (int64_t)b * g.n_cells, i, j, k);
-      int oi = occ[cmx_site_offset(g, b, i, j, k)];
+      int oi = cmx_dec(occ[cmx_site_offset(g, b, i, j, k)]);
       double t = exch[(b * max_occ + oi) * max_occ + new_occ[ev * sites_per_event + q]];
       x = (q == 0) ? t : __dadd_rn(x, t);
     }
@@ -360,7 +360,7 @@ __global__ void k_composition(Geom g, int n_sublat, int max_occ,
   for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < total;
        l += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
-    int v = occ[b * g.sub_stride + g.halo * g.layer + cell];
+    int v = cmx_dec(occ[b * g.sub_stride + g.halo * g.layer + cell]);
     atomicAdd(&sh_cnt[b * max_occ + v], 1u);
   }
   __syncthreads();

@@ -47,7 +47,18 @@ struct Geom {
   int64_t layer;       // N0*N1
   int64_t sub_stride;  // bytes between sublattices: N0*N1*(N2+2*halo)
   int64_t rep_stride;  // bytes between replicas:   n_sublat*sub_stride
+  // Storage code of the occupants.  coded == 0: the byte is the occupant index.
+  // coded == 1 (single-sublattice ternary states): occupant 2 is stored as 16, so
+  // that the byte-lane sum over a site's neighbors IS n1 + 16*n2, the index of
+  // the pair-LUT sweep -- no per-neighbor masking.  cmx_dec() reads both codes.
+  int32_t coded;
 };
+
+// occupant index <-> stored byte (see Geom::coded)
+__host__ __device__ __forceinline__ int cmx_dec(int raw) { return (raw & 7) | (raw >> 3); }
+__host__ __device__ __forceinline__ int cmx_enc(const Geom &g, int v) {
+  return (g.coded && v == 2) ? 16 : v;
+}
 
 struct cmx_tables {
   int device;
@@ -64,6 +75,7 @@ struct cmx_tables {
 struct SweepPlan {
   bool valid = false;     // sweeps possible (global clexulator + ECI bound)
   bool pair_lut = false;  // pair-count LUT fast path usable
+  bool rng16 = false;     // generic evaluator draws the pair16 kernel's random bits
   int32_t S[3] = {1, 1, 1};  // colour strides along i, j, k
   int32_t n_colours = 0;
   int32_t range_k = 0;  // max |dk| over active neighbors (halo depth needed)
@@ -81,9 +93,10 @@ struct SweepPlan {
   uint32_t mask = 0;      // bit (dk+1)*9 + (dj+1)*3 + (di+1)
   int32_t n_lut = 0;      // nocc*(nocc-1)*256 entries
   double *d_pair_dE = nullptr;       // [n_lut] clex dE per (oi, alt, counts)
-  uint32_t *d_thr = nullptr;     // [replica][n_lut] acceptance thresholds, high 31 bits
-  uint32_t *d_thr_lo = nullptr;  // [replica][n_lut] low 22 bits (tie break)
-  double *d_dEpot = nullptr;            // [replica][n_lut] dE - exch
+  int32_t n_tab = 0;              // entries of the pair16 acceptance table
+  uint2 *d_tab = nullptr;         // [replica][n_tab] {threshold(15 bit)<<1|1, proposed code}
+  uint32_t *d_thr_lo = nullptr;   // [replica][n_tab] low 32 bits of the threshold (tie break)
+  double *d_dEpot = nullptr;      // [replica][n_tab] dE - exch
   bool thr_dirty = true;
   // per-block partial counters of the current call
   long long *d_part_acc = nullptr;
@@ -116,6 +129,7 @@ struct cmx_state {
   int32_t n_species = 0;
   // sweeps
   SweepPlan plan;
+  uint32_t sweep_flags = 0;            // CMX_SWEEP_* (cmx_state_set_sweep_flags)
   cmx_counters *d_counters = nullptr;  // [replica]
   int *d_flag = nullptr;               // device-side validation flag
   // scratch
@@ -168,7 +182,7 @@ struct Override {
 
 __device__ __forceinline__ int cmx_load_occ(const int8_t *occ, int64_t off,
                                             const Override &ov) {
-  int v = occ[off];
+  int v = cmx_dec(occ[off]);
 #pragma unroll
   for (int q = 0; q < 4; ++q)
     if (q < ov.n && ov.off[q] == off) v = ov.occ[q];

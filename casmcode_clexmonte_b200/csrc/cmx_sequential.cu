@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(32) k_metropolis_sequential(SeqArgs a) {
         int i = (int)(cell % g.N0);
         long long rr = cell / g.N0;
         int j = (int)(rr % g.N1), k = (int)(rr / g.N1);
-        int oi = a.occ[cmx_site_offset(g, b, i, j, k)];
+        int oi = cmx_dec(a.occ[cmx_site_offset(g, b, i, j, k)]);
         dE = __dsub_rn(dE, a.exch[(b * T.max_occ + oi) * T.max_occ + nw[0]]);
       }
       if (dE < 0.0) {
@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(32) k_metropolis_sequential(SeqArgs a) {
           long long rr = cell / g.N0;
           int j = (int)(rr % g.N1), k = (int)(rr / g.N1);
           int asym = a.sublat_to_asym[b];
-          a.occ[cmx_site_offset(g, b, i, j, k)] = (int8_t)a.occ_index[asym * a.n_species + to_sp[q]];
+          a.occ[cmx_site_offset(g, b, i, j, k)] =
+              (int8_t)cmx_enc(g, a.occ_index[asym * a.n_species + to_sp[q]]);
           // remove from the old candidate list: swap with last, pop
           int ci = -1;
           for (int cc = 0; cc < a.n_cand; ++cc)

@@ -11,9 +11,10 @@
 //    models).  dE then depends only on (occ_i, occ_f, neighbor species
 //    counts); it is tabulated ONCE by running the faithful evaluator on a
 //    representative neighborhood per count combination, and the Metropolis
-//    test  u < exp(-beta dE)  becomes a 53-bit integer compare against a
-//    per-replica threshold table staged in shared memory.  Four sites per
-//    thread, occupants gathered as 8-byte row chunks and counted bytewise.
+//    test  u < exp(-beta dE)  becomes an integer compare against a
+//    per-replica threshold table staged in shared memory.  Sixteen sites per
+//    thread (both x colours of a 16-byte row chunk), neighbor species counted
+//    for all 16 byte lanes at once (kernel k_sweep_pair16).
 //  * "generic": any table (multi-sublattice, triplets, quadruplets): ECI-folded
 //    merged term lists, one site per thread, FP64 products, exp().
 #include <algorithm>
@@ -35,7 +36,7 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_gt_f);
   cudaFree(p.d_gt_n);
   cudaFree(p.d_pair_dE);
-  cudaFree(p.d_thr);
+  cudaFree(p.d_tab);
   cudaFree(p.d_thr_lo);
   cudaFree(p.d_dEpot);
   cudaFree(p.d_part_acc);
@@ -79,44 +80,62 @@ __global__ void k_build_pair_lut(DevTables T, int nocc, int z,
   lut[e] = dE;
 }
 
-// thresholds: accept  <=>  r53 < thr,  r53 uniform on [0, 2^53):
-//   dE < 0            -> always            (metropolis_acceptance [EXT])
-//   else u < exp(-dE*beta), u = r53 * 2^-53
-// stored split: thr_hi = thr >> 22 (compared against the 31 random bits every
-// site draws) and thr_lo = thr & (2^22-1) (22 more bits, drawn lazily only when
-// the first 31 tie) -- together exactly the 53-bit comparison.
-__global__ void k_build_thresholds(const double *__restrict__ lut, int n_lut,
-                                   int nocc, int max_occ, int b,
-                                   const double *__restrict__ beta,
-                                   const double *__restrict__ exch, int exch_stride,
-                                   uint32_t *__restrict__ thr_hi,
-                                   uint32_t *__restrict__ thr_lo,
-                                   double *__restrict__ dEpot) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+// ---------------------------------------------------------------------------
+// Acceptance tables of the pair16 kernel.
+//
+// The uniform of one attempted step is a 47-bit integer u47 = (u15 << 32) | w32:
+// u15 comes from the 16-bit field every site draws (bit 0 of the field is the
+// proposal bit `alt`), w32 is drawn lazily only when the first 15 bits tie.
+//   accept  <=>  u47 < t47,   t47 = 2^47                        if dE < 0
+//                              t47 = ceil(exp(-dE*beta) * 2^47)  otherwise
+// (metropolis_acceptance [EXT]: `if (dE < 0) return true; return rng < exp(-dE*beta)`).
+// Table index  idx = cnt | sa << 8,  cnt = n1 + 16*n2 (neighbor species counts),
+// sa = self occupant | alt << 2.  Entry .x = (t47 >> 32) << 1 | 1 -- compared
+// with (field | 1), so neither side needs a shift -- and .y = the storage code of
+// the proposed occupant.
+// ---------------------------------------------------------------------------
+#define CMX_TAB16(NOCC) ((NOCC) == 3 ? 2048 : 512)
+
+__global__ void k_build_tab16(const double *__restrict__ lut, int nocc, int max_occ,
+                              const double *__restrict__ beta,
+                              const double *__restrict__ exch, int exch_stride,
+                              int n_tab, uint2 *__restrict__ tab,
+                              uint32_t *__restrict__ thr_lo,
+                              double *__restrict__ dEpot) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int r = blockIdx.y;
-  if (e >= n_lut) return;
-  int pair = e >> 8;
-  int oi = pair / (nocc - 1), alt = pair - oi * (nocc - 1);
+  if (idx >= n_tab) return;
+  const int cnt = idx & 255, sa = idx >> 8;
+  const int oi = sa & 3, alt = sa >> 2;
+  const int n1 = cnt & 15, n2 = cnt >> 4;
+  size_t o = (size_t)r * n_tab + idx;
+  if (oi >= nocc || alt >= nocc - 1 || (nocc < 3 && n2 > 0)) {
+    tab[o] = make_uint2(1u, 0u);  // never accepted (field | 1 >= 1), tie -> thr_lo 0
+    thr_lo[o] = 0;
+    dEpot[o] = 0.0;
+    return;
+  }
+  (void)n1;
   int of = oi + 1 + alt;
   if (of >= nocc) of -= nocc;
-  double x = exch[(size_t)r * exch_stride + (b * max_occ + oi) * max_occ + of];
-  double dE = __dsub_rn(lut[e], x);
+  const int pair = oi * (nocc - 1) + alt;
+  double x = exch[(size_t)r * exch_stride + (0 * max_occ + oi) * max_occ + of];
+  double dE = __dsub_rn(lut[(pair << 8) | cnt], x);
   unsigned long long t;
-  const double two53 = 9007199254740992.0;
+  const double two47 = 140737488355328.0;
   if (dE < 0.0) {
-    t = 1ull << 53;
+    t = 1ull << 47;
   } else {
     double p = exp(-dE * beta[r]);
-    double v = ceil(p * two53);
-    t = (unsigned long long)v;
+    t = (unsigned long long)ceil(p * two47);
   }
-  thr_hi[(size_t)r * n_lut + e] = (uint32_t)(t >> 22);
-  thr_lo[(size_t)r * n_lut + e] = (uint32_t)(t & 0x3FFFFFull);
-  dEpot[(size_t)r * n_lut + e] = dE;
+  tab[o] = make_uint2((uint32_t)(t >> 32) << 1 | 1u, (uint32_t)((of == 2) ? 16 : of));
+  thr_lo[o] = (uint32_t)(t & 0xFFFFFFFFull);
+  dEpot[o] = dE;
 }
 
 // ---------------------------------------------------------------------------
-// pair-LUT sweep kernel
+// pair16 sweep kernel
 // ---------------------------------------------------------------------------
 struct FastDiv {
   uint32_t d, m;
@@ -137,205 +156,262 @@ __device__ __forceinline__ void fastdivmod(uint32_t n, FastDiv f, uint32_t &q,
   }
 }
 
-struct PairSweepArgs {
+struct Pair16Args {
   int8_t *occ;  // replica 0 base (start of the low ghost layers)
   Geom g;
-  int cy, cz;          // colour parities along j, k (i parity is a template arg)
-  uint32_t mask;       // runtime neighbor mask
-  FastDiv divW, divJ;  // chunks per row, rows per layer of this colour
-  uint32_t W, J, K;    // item grid of one colour: chunk, row pair, layer pair
-  uint32_t dc, djj, dkk;  // grid stride decomposed on (c, jj, kk)
-  const uint32_t *thr_hi;  // [replica][n_lut]
-  const uint32_t *thr_lo;  // [replica][n_lut]
-  const double *dEpot;     // [replica][n_lut]
-  int n_lut;
-  long long *part_acc;  // [replica][gridDim.x]
+  int cy, cz;        // row colour (parities of j and k); both x colours are fused
+  uint32_t mask;     // runtime neighbor mask, bit (dz+1)*9 + (dy+1)*3 + (dx+1)
+  uint32_t W;        // 16-byte chunks per row
+  uint32_t RB;       // whole rows per block and iteration (RB * W <= 256)
+  FastDiv divW, divJ;
+  uint32_t J;        // rows of this colour per layer (N1 / 2)
+  uint32_t n_rows;   // J * (N2 / 2)
+  const uint2 *tab;        // [replica][n_tab]
+  const uint32_t *thr_lo;  // [replica][n_tab]
+  const double *dEpot;     // [replica][n_tab]
+  long long *part_acc;     // [replica][gridDim.x]
   double *part_dE;
   uint32_t k0, k1;       // seed
   uint32_t sweep_lo;     // RNG counter words
-  uint32_t ctr_hi;       // (sweep_hi << 16) | (colour << 8)
+  uint32_t ctr_hi;       // (sweep_hi << 16) | (row colour << 9); bit 8 = x colour, low bits = draw
   int k_offset;          // global k of local layer 0 (slab decomposition)
 };
 
-template <int CX>
-__device__ __forceinline__ uint32_t extract4(uint32_t lo, uint32_t hi,
-                                             uint32_t side, int dx) {
-  // the four neighbor bytes (one per target site) at x-offset dx
-  if (CX == 0) {  // targets at bytes 0,2,4,6
-    if (dx == 0) return __byte_perm(lo, hi, 0x6420);
-    if (dx == 1) return __byte_perm(lo, hi, 0x7531);
-    uint32_t v = __byte_perm(lo, hi, 0x5310);  // [b0,b1,b3,b5]
-    return __byte_perm(v, side, 0x3217);       // [prev.3,b1,b3,b5]
-  } else {  // targets at bytes 1,3,5,7
-    if (dx == 0) return __byte_perm(lo, hi, 0x7531);
-    if (dx == -1) return __byte_perm(lo, hi, 0x6420);
-    uint32_t v = __byte_perm(lo, hi, 0x7642);  // [b2,b4,b6,b7]
-    return __byte_perm(v, side, 0x4210);       // [b2,b4,b6,next.0]
+// The two x colours of one 16-site chunk.
+//  cnt[i]  byte-lane neighbor sums of the chunk (only the lanes of colour CX are used)
+//  C[i]    the chunk (storage codes); accepted sites are replaced in place
+//  SC[i]   occupant indices of the chunk, byte-wise (0,1,2)
+template <int CX, int NOCC, bool ACCUM>
+__device__ __forceinline__ void pair16_update(const uint32_t (&cnt)[4], uint32_t (&C)[4],
+                                              const uint32_t (&SC)[4], const Philox &ph,
+                                              const uint2 *__restrict__ sh_tab,
+                                              const double *__restrict__ sh_dE,
+                                              uint32_t &n_acc, double &e_sum,
+                                              bool &tie) {
+  constexpr uint32_t lanes = CX ? 0xFF00FF00u : 0x00FF00FFu;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t R = ph.c[i];
+    // occupant | alt << 2 in the target lanes, zero elsewhere
+    const uint32_t altw = (NOCC == 3) ? ((R & 0x00010001u) << (CX ? 10 : 2)) : 0u;
+    const uint32_t SA = (SC[i] | altw) & lanes;
+    const uint32_t Rw = R | 0x00010001u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int b = 2 * h + CX;  // byte of the word
+      // idx = cnt byte b | SA byte b << 8  (bytes 2,3 <- a zero byte of SA)
+      const uint32_t sel = (uint32_t)b | ((uint32_t)(4 + b) << 4) | ((uint32_t)(4 + (b ^ 1)) << 8) |
+                           ((uint32_t)(4 + (b ^ 1)) << 12);
+      const uint32_t idx = __byte_perm(cnt[i], SA, sel);
+      const uint2 e = sh_tab[idx];
+      const uint32_t f1 = h ? (Rw >> 16) : (Rw & 0xFFFFu);
+      const bool ok = f1 < e.x;
+      tie |= (f1 == e.x);
+      if (ok) {
+        // byte b of C[i] <- proposed code
+        const uint32_t ins = (b == 0) ? 0x3214u : (b == 1) ? 0x3240u : (b == 2) ? 0x3410u : 0x4210u;
+        C[i] = __byte_perm(C[i], e.y, ins);
+        n_acc += 1;
+        if (ACCUM) e_sum += sh_dE[idx];
+      }
+    }
   }
 }
 
-// One thread owns 4 same-colour sites of one 8-byte row chunk per iteration.
-//  * occupants of the <= 9 neighbor rows arrive as 8-byte loads (+ one 4-byte
-//    side word where the colour needs the byte just outside the chunk),
-//    32-bit offsets from the replica base;
-//  * the species counts of the 4 sites are accumulated bytewise in one
-//    register (species 1 in the low nibble, species 2 in the high nibble);
-//  * one Philox4x32-10 call yields the 4 x (31-bit uniform + 1 proposal bit);
-//    the acceptance test is one integer compare against the shared-memory
-//    threshold table, the remaining 22 bits of the 53-bit uniform are drawn
-//    only on a tie of the first 31 (probability 2^-31);
+// rare path (probability 2^-15 per site): the first 15 bits of the uniform equal
+// the threshold's; draw 32 more bits per site and finish the 47-bit comparison.
+template <int CX, int NOCC, bool ACCUM>
+__device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], uint32_t (&C)[4],
+                                         const uint32_t (&SC)[4], const Philox &ph,
+                                         const uint2 *sh_tab, const double *sh_dE,
+                                         const uint32_t *__restrict__ thr_lo, uint32_t gid,
+                                         uint32_t r, uint32_t sweep_lo, uint32_t ctr, uint32_t k0,
+                                         uint32_t k1, uint32_t &n_acc, double &e_sum) {
+  constexpr uint32_t lanes = CX ? 0xFF00FF00u : 0x00FF00FFu;
+  const Philox lo0 = philox4x32_10(gid, r, sweep_lo, ctr | 1u, k0, k1);
+  const Philox lo1 = philox4x32_10(gid, r, sweep_lo, ctr | 2u, k0, k1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t R = ph.c[i];
+    const uint32_t altw = (NOCC == 3) ? ((R & 0x00010001u) << (CX ? 10 : 2)) : 0u;
+    const uint32_t SA = (SC[i] | altw) & lanes;
+    const uint32_t Rw = R | 0x00010001u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = 2 * h + CX;
+      const uint32_t idx = ((cnt[i] >> (8 * b)) & 0xFFu) | (((SA >> (8 * b)) & 0xFFu) << 8);
+      const uint2 e = sh_tab[idx];
+      const uint32_t f1 = h ? (Rw >> 16) : (Rw & 0xFFFFu);
+      if (f1 != e.x) continue;
+      const int q = 2 * i + h;  // target site of the chunk, 0..7
+      const uint32_t w32 = (q < 4) ? lo0.c[q & 3] : lo1.c[q & 3];
+      if (w32 < thr_lo[idx]) {
+        C[i] = (C[i] & ~(0xFFu << (8 * b))) | (e.y << (8 * b));
+        n_acc += 1;
+        if (ACCUM) e_sum += sh_dE[idx];
+      }
+    }
+  }
+}
+
+// One thread owns one 16-byte chunk (16 consecutive sites) of a row whose (j,k)
+// parities are (cy,cz) and updates BOTH x colours of it:
+//  * the <= 8 neighbor rows arrive as 16-byte loads (+ 4-byte side words for the
+//    bytes just outside the chunk).  Because occupants are stored as 0/1/16, the
+//    plain word-wise sum of the rows is, lane by lane, n1 + 16*n2: the rows are
+//    summed per x-offset class first (A0/Am/Ap), the dx = -1/+1 classes are then
+//    shifted by one byte lane with funnel shifts -- 16 sites at once;
+//  * even lanes are updated first, the changed first byte goes to the left
+//    neighbor chunk through shared memory (a block always owns whole rows), then
+//    the odd lanes are updated against the new even lanes;
+//  * per x colour one Philox4x32-10 call yields the eight 16-bit fields
+//    (1 proposal bit + 15 uniform bits); the Metropolis test is one integer
+//    compare against the shared-memory table, 32 more bits are drawn only on a tie;
 //  * accepted dE (tabulated) is summed in FP64 per thread, reduced per block.
-template <int CX, int NOCC, uint32_t MASK_CT>
-__global__ void __launch_bounds__(256, 4)
-    k_sweep_pair_lut(PairSweepArgs a) {
-  __shared__ uint32_t sh_thr[NOCC * (NOCC - 1) * 256];
-  __shared__ double sh_dE[NOCC * (NOCC - 1) * 256];
+template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+__global__ void __launch_bounds__(256, 3) k_sweep_pair16(Pair16Args a) {
+  constexpr int NTAB = CMX_TAB16(NOCC);
+  __shared__ uint2 sh_tab[NTAB];
+  __shared__ double sh_dE[ACCUM ? NTAB : 1];
+  __shared__ uint8_t sh_x[2][256];
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
-  const int r = blockIdx.y;
+  const uint32_t r = blockIdx.y;
   {
-    const uint32_t *gt = a.thr_hi + (size_t)r * a.n_lut;
-    const double *ge = a.dEpot + (size_t)r * a.n_lut;
-    for (int q = threadIdx.x; q < a.n_lut; q += blockDim.x) {
-      sh_thr[q] = gt[q];
-      sh_dE[q] = ge[q];
+    const uint2 *gt = a.tab + (size_t)r * NTAB;
+    const double *ge = a.dEpot + (size_t)r * NTAB;
+    for (int q = threadIdx.x; q < NTAB; q += blockDim.x) {
+      sh_tab[q] = gt[q];
+      if (ACCUM) sh_dE[q] = ge[q];
     }
   }
   __syncthreads();
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const Geom &g = a.g;
   int8_t *base = a.occ + (size_t)r * g.rep_stride;  // includes the ghost layers
-  // keep the replica base in a register pair: without this the compiler
-  // re-derives r * rep_stride (a 64-bit multiply-add) for every load
-  asm volatile("" : "+l"(base));
+  asm volatile("" : "+l"(base));  // keep the replica base in a register pair
   const uint32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
   const uint32_t layer = N0 * N1;
   const bool halo = g.halo != 0;
   uint32_t n_acc = 0;  // < 2^32 accepted sites per thread and launch
   double e_sum = 0.0;
 
-  uint32_t c, jj, kk;
-  {
-    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x, row;
-    fastdivmod(item, a.divW, row, c);
-    fastdivmod(row, a.divJ, kk, jj);
-  }
-  while (kk < a.K) {
-    const uint32_t j = 2 * jj + a.cy, k = 2 * kk + a.cz;
-    const uint32_t x0 = 8 * c;
-    // 32-bit byte offsets of the neighbor rows relative to the replica base
-    const uint32_t off_c = ((k + g.halo) * N1 + j) * N0 + x0;
-    uint32_t dj[3], dk[3];
-    dj[0] = (j == 0) ? (N1 - 1) * N0 : 0u - N0;
-    dj[1] = 0;
-    dj[2] = (j == N1 - 1) ? 0u - (N1 - 1) * N0 : N0;
-    dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : 0u - layer;
-    dk[1] = 0;
-    dk[2] = (!halo && k == N2 - 1) ? 0u - (N2 - 1) * layer : layer;
-    // the side word holds the byte just outside the chunk on the side this
-    // colour needs: x0-1 for CX == 0 (dx = -1), x0+8 for CX == 1 (dx = +1)
-    const uint32_t dside = (CX == 0) ? ((x0 == 0) ? N0 - 4 : 0u - 4u)
-                                     : ((x0 + 8 == N0) ? 8u - N0 : 8u);
-    // bytewise sums over the neighbors of the 4 sites: s1 = sum of occupant
-    // codes (n1 + 2 n2 per lane), s2 = sum of (code & 2) (2 n2 per lane)
-    uint32_t s1 = 0, s2 = 0, self4 = 0;
-    uint32_t lo_c = 0, hi_c = 0;
+  uint32_t rl, c;
+  fastdivmod(threadIdx.x, a.divW, rl, c);
+  const bool lane_on = rl < a.RB;
+  const uint32_t nxt = (c == a.W - 1) ? threadIdx.x - (a.W - 1) : threadIdx.x + 1;
+  const uint32_t x0 = 16 * c;
+  const uint32_t dl = (x0 == 0) ? N0 - 4 : 0u - 4u;         // word holding byte x0-1
+  const uint32_t dr = (x0 + 16 == N0) ? 16u - N0 : 16u;     // word holding byte x0+16
+  const uint32_t mc = (mask >> 12) & 7u;                     // center row: dx = -1 / +1 bits
+  uint32_t it = 0;
+  for (uint32_t row0 = blockIdx.x * a.RB; row0 < a.n_rows; row0 += gridDim.x * a.RB, ++it) {
+    const uint32_t row = row0 + rl;
+    const bool on = lane_on && row < a.n_rows;
+    uint32_t C[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0}, SC[4];
+    uint32_t cl = 0, off_c = 0, gid = 0;
+    if (on) {
+      uint32_t kk, jj;
+      fastdivmod(row, a.divJ, kk, jj);
+      const uint32_t j = 2 * jj + a.cy, k = 2 * kk + a.cz;
+      off_c = ((k + g.halo) * N1 + j) * N0 + x0;
+      gid = ((k + (uint32_t)a.k_offset) * N1 + j) * a.W + c;
+      uint32_t dj[3], dk[3];
+      dj[0] = (j == 0) ? (N1 - 1) * N0 : 0u - N0;
+      dj[1] = 0;
+      dj[2] = (j == N1 - 1) ? 0u - (N1 - 1) * N0 : N0;
+      dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : 0u - layer;
+      dk[1] = 0;
+      dk[2] = (!halo && k == N2 - 1) ? 0u - (N2 - 1) * layer : layer;
+      uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
+      uint32_t sm = 0, sp = 0;
 #pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
+      for (int dz = -1; dz <= 1; ++dz) {
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
-        const bool center = (dz == 0 && dy == 0);
-        if (m3 == 0 && !center) continue;
-        const uint32_t off = off_c + dk[dz + 1] + dj[dy + 1];
-        const uint2 ch = *reinterpret_cast<const uint2 *>(base + off);
-        uint32_t side = 0;
-        const bool need_side = (CX == 0) ? (m3 & 1u) : (m3 & 4u);
-        if (need_side) side = *reinterpret_cast<const uint32_t *>(base + (off + dside));
-        if (center) {
-          lo_c = ch.x;
-          hi_c = ch.y;
-          self4 = extract4<CX>(ch.x, ch.y, 0, 0);
-        }
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          if (!(m3 & (1u << (dx + 1)))) continue;
-          uint32_t w = extract4<CX>(ch.x, ch.y, side, dx);
-          s1 += w;
-          s2 += w & 0x02020202u;
-        }
-      }
-    }
-    // species-1 count in the low nibble, species-2 count in the high nibble of
-    // each byte lane: (s1 - s2) + 8 * s2 = n1 + 16 n2
-    const uint32_t acc = (s1 - s2) + (s2 << 3);
-    // ---- random numbers: one 32-bit word per site
-    const uint32_t gid = ((k + (uint32_t)a.k_offset) * N1 + j) * a.W + c;
-    const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi, a.k0, a.k1);
-    uint32_t new4 = 0;
-    uint32_t ties = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t w = ph.c[q];
-      const uint32_t oi = (self4 >> (8 * q)) & 0xffu;
-      const uint32_t alt = (NOCC == 3) ? (w & 1u) : 0u;
-      const uint32_t pair = oi * (NOCC - 1) + alt;
-      // of = (oi + 1 + alt) mod NOCC, two bits per pair packed in a constant
-      const uint32_t of = (NOCC == 3) ? ((0x429u >> (2 * pair)) & 3u) : (oi ^ 1u);
-      const uint32_t cnt = (acc >> (8 * q)) & 0xffu;
-      const uint32_t idx = (pair << 8) | cnt;
-      const uint32_t thr = sh_thr[idx];
-      const uint32_t u31 = w >> 1;
-      const bool ok = u31 < thr;
-      ties |= (u31 == thr) ? (1u << q) : 0u;
-      double d = 0.0;
-      if (ok) d = sh_dE[idx];
-      e_sum += d;
-      n_acc += ok ? 1u : 0u;
-      new4 |= (ok ? of : oi) << (8 * q);
-    }
-    if (ties) {  // probability 2^-31 per site: draw the low 22 bits of the uniform
-      const Philox p2 = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi | 1u, a.k0, a.k1);
-      const uint32_t *gl = a.thr_lo + (size_t)r * a.n_lut;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (!(ties & (1u << q))) continue;
-        const uint32_t w = ph.c[q];
-        const uint32_t oi = (self4 >> (8 * q)) & 0xffu;
-        const uint32_t alt = (NOCC == 3) ? (w & 1u) : 0u;
-        uint32_t of = oi + 1u + alt;
-        of -= (of >= (uint32_t)NOCC) ? (uint32_t)NOCC : 0u;
-        const uint32_t idx = ((oi * (NOCC - 1) + alt) << 8) | ((acc >> (8 * q)) & 0xffu);
-        if ((p2.c[q] & 0x3FFFFFu) < gl[idx]) {
-          new4 = (new4 & ~(0xffu << (8 * q))) | (of << (8 * q));
-          e_sum += sh_dE[idx];
-          n_acc += 1;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
+          const bool center = (dz == 0 && dy == 0);
+          if (m3 == 0 && !center) continue;
+          const uint32_t off = off_c + dk[dz + 1] + dj[dy + 1];
+          const uint4 ch = *reinterpret_cast<const uint4 *>(base + off);
+          if (center) {
+            C[0] = ch.x;
+            C[1] = ch.y;
+            C[2] = ch.z;
+            C[3] = ch.w;
+            if (m3 & 1u) cl = *reinterpret_cast<const uint32_t *>(base + (off + dl));
+            continue;
+          }
+          if (m3 & 2u) {
+            A0[0] += ch.x;
+            A0[1] += ch.y;
+            A0[2] += ch.z;
+            A0[3] += ch.w;
+          }
+          if (m3 & 1u) {
+            Am[0] += ch.x;
+            Am[1] += ch.y;
+            Am[2] += ch.z;
+            Am[3] += ch.w;
+            sm += *reinterpret_cast<const uint32_t *>(base + (off + dl));
+          }
+          if (m3 & 4u) {
+            Ap[0] += ch.x;
+            Ap[1] += ch.y;
+            Ap[2] += ch.z;
+            Ap[3] += ch.w;
+            sp += *reinterpret_cast<const uint32_t *>(base + (off + dr));
+          }
         }
       }
-    }
-    if (new4 != self4) {
-      uint2 out;
-      if (CX == 0) {
-        out.x = __byte_perm(lo_c, new4, 0x3514);
-        out.y = __byte_perm(hi_c, new4, 0x3716);
-      } else {
-        out.x = __byte_perm(lo_c, new4, 0x5240);
-        out.y = __byte_perm(hi_c, new4, 0x7260);
+      // T[x] = A0[x] + Am[x-1] + Ap[x+1], byte lanes of the 16-byte chunk
+      T[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
+      T[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
+      T[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
+      T[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        SC[i] = (NOCC == 3) ? ((C[i] & 0x01010101u) | ((C[i] >> 3) & 0x02020202u)) : C[i];
+      // ---- x colour 0: even lanes; same-row neighbors are odd lanes (old values)
+      uint32_t cnt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cnt[i] = T[i];
+        if (mc & 1u) cnt[i] += __funnelshift_l(i ? C[i - 1] : cl, C[i], 8);
+        if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : 0u, 8);
       }
-      *reinterpret_cast<uint2 *>(base + off_c) = out;
+      const uint32_t ctr0 = a.ctr_hi;
+      const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr0, a.k0, a.k1);
+      bool tie = false;
+      pair16_update<0, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, n_acc, e_sum, tie);
+      if (tie)
+        pair16_ties<0, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, a.thr_lo + (size_t)r * NTAB, gid,
+                                    r, a.sweep_lo, ctr0, a.k0, a.k1, n_acc, e_sum);
+      sh_x[it & 1][threadIdx.x] = (uint8_t)(C[0] & 0xFFu);
     }
-    // ---- next item: grid stride decomposed on (c, jj, kk)
-    c += a.dc;
-    if (c >= a.W) {
-      c -= a.W;
-      jj += 1;
+    __syncthreads();
+    if (on) {
+      // ---- x colour 1: odd lanes against the updated even lanes; byte 16 is the
+      // (updated) first byte of the next chunk of the row
+      const uint32_t nb = sh_x[it & 1][nxt];
+      uint32_t cnt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cnt[i] = T[i];
+        if (mc & 1u) cnt[i] += __funnelshift_l(i ? C[i - 1] : 0u, C[i], 8);
+        if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : nb, 8);
+      }
+      const uint32_t ctr1 = a.ctr_hi | 0x100u;
+      const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr1, a.k0, a.k1);
+      bool tie = false;
+      pair16_update<1, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, n_acc, e_sum, tie);
+      if (tie)
+        pair16_ties<1, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, a.thr_lo + (size_t)r * NTAB, gid,
+                                    r, a.sweep_lo, ctr1, a.k0, a.k1, n_acc, e_sum);
+      *reinterpret_cast<uint4 *>(base + off_c) = make_uint4(C[0], C[1], C[2], C[3]);
     }
-    jj += a.djj;
-    if (jj >= a.J) {
-      jj -= a.J;
-      kk += 1;
-    }
-    kk += a.dkk;
   }
   // ---- block reduction of the counters (fixed order -> deterministic)
   long long n_acc64 = n_acc;
@@ -381,6 +457,10 @@ struct GenericSweepArgs {
   double *part_dE;
   uint32_t k0, k1, sweep_lo, ctr_hi;
   int k_offset;
+  // rng16 != 0: draw exactly the random bits the pair16 kernel draws for this
+  // site (same counters, same 47-bit comparison), so that the two evaluators
+  // produce the same trajectory and can be compared bit for bit.
+  int rng16;
 };
 
 __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
@@ -406,12 +486,29 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
     const int i = (int)ii * a.S0 + a.c0, j = (int)jj * a.S1 + a.c1,
               k = (int)kk * a.S2 + a.c2;
     const int64_t off = cmx_site_offset(g, b, i, j, k);
-    const int oi = occ[off];
-    // global site id -> RNG counter
-    const uint32_t gid_lo = (uint32_t)(((uint64_t)(k + a.k_offset) * g.N1 + j) * g.N0 + i);
-    Philox ph = philox4x32_10(gid_lo, (uint32_t)r | ((uint32_t)b << 24), a.sweep_lo,
-                              a.ctr_hi, a.k0, a.k1);
-    const int alt = (int)__umulhi(ph.c[2], (uint32_t)(nocc - 1));
+    const int oi = cmx_dec(occ[off]);
+    int alt;
+    uint32_t u_hi, u_lo;  // rng16: 15 + 32 bit uniform; else 21 + 32 bit
+    if (a.rng16) {
+      const uint32_t gid = (uint32_t)(((uint32_t)(k + a.k_offset) * g.N1 + j) * (g.N0 >> 4) + (i >> 4));
+      const uint32_t x = (uint32_t)i & 15u, q = x >> 1;  // lane of the chunk, target index
+      const uint32_t ctr = a.ctr_hi;
+      const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr, a.k0, a.k1);
+      const uint32_t R = ph.c[x >> 2];
+      const uint32_t field = (x & 2u) ? (R >> 16) : (R & 0xFFFFu);
+      alt = (nocc == 3) ? (int)(field & 1u) : 0;
+      u_hi = field >> 1;
+      const Philox lo = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr | ((q < 4) ? 1u : 2u), a.k0, a.k1);
+      u_lo = lo.c[q & 3];
+    } else {
+      // global site id -> RNG counter
+      const uint32_t gid_lo = (uint32_t)(((uint64_t)(k + a.k_offset) * g.N1 + j) * g.N0 + i);
+      const Philox ph = philox4x32_10(gid_lo, (uint32_t)r | ((uint32_t)b << 24), a.sweep_lo,
+                                      a.ctr_hi, a.k0, a.k1);
+      alt = (int)__umulhi(ph.c[2], (uint32_t)(nocc - 1));
+      u_hi = ph.c[1] & 0x1FFFFFu;
+      u_lo = ph.c[0];
+    }
     int of = oi + 1 + alt;
     if (of >= nocc) of -= nocc;
     double dE = 0.0;
@@ -420,7 +517,7 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
       for (int q = a.gt_fbeg[t]; q < a.gt_fbeg[t + 1]; ++q) {
         const int n = a.gt_n[q];
         const int64_t no = cmx_nbr_offset(T, g, n, i, j, k, nullptr);
-        const int o = occ[no];
+        const int o = cmx_dec(occ[no]);
         v *= T.phi[((size_t)T.nbr[n].w * T.n_func + a.gt_f[q]) * mo + o];
       }
       dE += v;
@@ -428,12 +525,16 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
     dE -= exch[oi * mo + of];
     bool accept = dE < 0.0;
     if (!accept) {
-      const unsigned long long u53 = ((unsigned long long)(ph.c[1] & 0x1FFFFFu) << 32) | ph.c[0];
-      const double u = (double)u53 * (1.0 / 9007199254740992.0);
-      accept = u < exp(-dE * beta);
+      const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
+      if (a.rng16) {
+        // the pair16 kernel's integer test: u47 < ceil(exp(-dE beta) 2^47)
+        accept = u < (unsigned long long)ceil(exp(-dE * beta) * 140737488355328.0);
+      } else {
+        accept = (double)u * (1.0 / 9007199254740992.0) < exp(-dE * beta);
+      }
     }
     if (accept) {
-      occ[off] = (int8_t)of;
+      occ[off] = (int8_t)cmx_enc(g, of);
       ++n_acc;
       e_sum += dE;
     }
@@ -608,7 +709,7 @@ int cmx_plan_sweep(cmx_state *s) {
   // ---- pair-LUT eligibility
   bool ok = (T.n_sublat == 1 && np == 1 && P.mut_points.size() == 1 &&
              t->n_occ[0] >= 2 && t->n_occ[0] <= 3 && T.nlist_len <= 64 &&
-             s->g.N0 % 8 == 0 && s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 &&
+             s->g.N0 % 16 == 0 && s->g.N0 <= 4096 && s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 &&
              s->g.rep_stride < (int64_t)0xFFFFFFFFll &&
              P.S[0] == 2 && P.S[1] == 2 && P.S[2] == 2);
   std::map<int, std::vector<double>> V;  // neighbor -> V[on][oi][of]
@@ -665,10 +766,12 @@ int cmx_plan_sweep(cmx_state *s) {
     CMX_CUDA(cudaGetLastError());
     CMX_CUDA(cudaStreamSynchronize(s->stream));
     cudaFree(d_cls);
-    CMX_CUDA(cudaMalloc((void **)&P.d_thr, sizeof(uint32_t) * P.n_lut * s->n_replicas));
-    CMX_CUDA(cudaMalloc((void **)&P.d_thr_lo, sizeof(uint32_t) * P.n_lut * s->n_replicas));
-    CMX_CUDA(cudaMalloc((void **)&P.d_dEpot, sizeof(double) * P.n_lut * s->n_replicas));
+    P.n_tab = CMX_TAB16(P.nocc);
+    CMX_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(uint2) * P.n_tab * s->n_replicas));
+    CMX_CUDA(cudaMalloc((void **)&P.d_thr_lo, sizeof(uint32_t) * P.n_tab * s->n_replicas));
+    CMX_CUDA(cudaMalloc((void **)&P.d_dEpot, sizeof(double) * P.n_tab * s->n_replicas));
     P.pair_lut = true;
+    P.rng16 = true;  // the generic evaluator on this state mirrors the pair16 random bits
     // per step: z neighbor bytes + own byte read, 1 byte written; the FP64
     // work is the tabulated dE (2 site-function adds per neighbor, the ECI
     // dot, the exp folded into the threshold) -- report the table-free count
@@ -702,17 +805,20 @@ constexpr uint32_t kMaskFcc1NN =
     mbit(0, 0, -1) | mbit(0, 0, 1) | mbit(0, 1, -1) | mbit(0, 1, 0) | mbit(1, -1, 0) |
     mbit(1, 0, -1) | mbit(1, 0, 0);
 
-template <int CX, int NOCC>
-static void launch_pair(const PairSweepArgs &a, dim3 grid, cudaStream_t st, bool fcc) {
-  if (fcc)
-    k_sweep_pair_lut<CX, NOCC, kMaskFcc1NN><<<grid, 256, 0, st>>>(a);
-  else
-    k_sweep_pair_lut<CX, NOCC, 0u><<<grid, 256, 0, st>>>(a);
+template <int NOCC>
+static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum) {
+  if (fcc) {
+    if (accum) k_sweep_pair16<NOCC, kMaskFcc1NN, true><<<grid, 256, 0, st>>>(a);
+    else k_sweep_pair16<NOCC, kMaskFcc1NN, false><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (accum) k_sweep_pair16<NOCC, 0u, true><<<grid, 256, 0, st>>>(a);
+    else k_sweep_pair16<NOCC, 0u, false><<<grid, 256, 0, st>>>(a);
+  }
 }
 
 static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
   int want = (int)((items + 255) / 256);
-  int cap = std::max(1, (148 * 8 + n_replicas - 1) / n_replicas);
+  int cap = std::max(1, (148 * 6 + n_replicas - 1) / n_replicas);
   return std::max(1, std::min(want, cap));
 }
 
@@ -723,35 +829,27 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   const DevTables &T = s->t->d;
   const Geom &g = s->g;
   size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
-  if (P.pair_lut) {
+  if (P.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) {
     if (P.thr_dirty) {
-      dim3 grid((P.n_lut + 127) / 128, s->n_replicas);
-      k_build_thresholds<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.n_lut, P.nocc, T.max_occ, 0,
-                                                      s->d_beta, s->d_exch, (int)exs, P.d_thr,
-                                                      P.d_thr_lo, P.d_dEpot);
+      dim3 grid((P.n_tab + 127) / 128, s->n_replicas);
+      k_build_tab16<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.nocc, T.max_occ, s->d_beta, s->d_exch,
+                                                 (int)exs, P.n_tab, P.d_tab, P.d_thr_lo, P.d_dEpot);
       CMX_CUDA(cudaGetLastError());
       P.thr_dirty = false;
     }
-    PairSweepArgs a;
+    Pair16Args a;
     a.occ = s->d_occ;
     a.g = g;
     a.mask = P.mask;
-    uint32_t W = g.N0 / 8, J = g.N1 / 2, K = g.N2 / 2;
-    a.divW = make_fastdiv(W);
-    a.divJ = make_fastdiv(J);
-    a.W = W;
-    a.J = J;
-    a.K = K;
-    {
-      uint32_t stride = (uint32_t)P.part_blocks * 256u;
-      a.dc = stride % W;
-      a.djj = (stride / W) % J;
-      a.dkk = stride / (W * J);
-    }
-    a.thr_hi = P.d_thr;
+    a.W = g.N0 / 16;
+    a.RB = 256 / a.W;
+    a.divW = make_fastdiv(a.W);
+    a.J = g.N1 / 2;
+    a.divJ = make_fastdiv(a.J);
+    a.n_rows = a.J * (uint32_t)(g.N2 / 2);
+    a.tab = P.d_tab;
     a.thr_lo = P.d_thr_lo;
     a.dEpot = P.d_dEpot;
-    a.n_lut = P.n_lut;
     a.part_acc = P.d_part_acc;
     a.part_dE = P.d_part_dE;
     a.k0 = (uint32_t)seed;
@@ -759,23 +857,17 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     a.sweep_lo = (uint32_t)sweep;
     a.k_offset = k_offset;
     dim3 grid(P.part_blocks, s->n_replicas);
-    bool fcc = (P.mask == kMaskFcc1NN);
+    const bool fcc = (P.mask == kMaskFcc1NN);
+    const bool accum = (s->sweep_flags & CMX_SWEEP_NO_DE_SUM) == 0;
     for (int cz = 0; cz < 2; ++cz) {
       if (kgroup >= 0 && cz != kgroup) continue;
-      for (int cy = 0; cy < 2; ++cy)
-        for (int cx = 0; cx < 2; ++cx) {
-          a.cy = cy;
-          a.cz = cz;
-          uint32_t colour = (cz * 2 + cy) * 2 + cx;
-          a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | (colour << 8);
-          if (P.nocc == 3) {
-            if (cx == 0) launch_pair<0, 3>(a, grid, s->stream, fcc);
-            else launch_pair<1, 3>(a, grid, s->stream, fcc);
-          } else {
-            if (cx == 0) launch_pair<0, 2>(a, grid, s->stream, fcc);
-            else launch_pair<1, 2>(a, grid, s->stream, fcc);
-          }
-        }
+      for (int cy = 0; cy < 2; ++cy) {
+        a.cy = cy;
+        a.cz = cz;
+        a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
+        if (P.nocc == 3) launch_pair16<3>(a, grid, s->stream, fcc, accum);
+        else launch_pair16<2>(a, grid, s->stream, fcc, accum);
+      }
     }
     CMX_CUDA(cudaGetLastError());
     return CMX_OK;
@@ -806,6 +898,7 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   a.k1 = (uint32_t)(seed >> 32);
   a.sweep_lo = (uint32_t)sweep;
   a.k_offset = k_offset;
+  a.rng16 = P.rng16 ? 1 : 0;
   dim3 grid(P.part_blocks, s->n_replicas);
   uint32_t colour = 0;
   for (int c2 = 0; c2 < P.S[2]; ++c2)
@@ -818,7 +911,8 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
           a.c1 = c1;
           a.c2 = c2;
           a.p = p;
-          a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | (col & 0xffffu);
+          a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) |
+                     (a.rng16 ? ((col & 0xffu) << 8) : (col & 0xffffu));
           k_sweep_generic<<<grid, 256, 0, s->stream>>>(a);
         }
   CMX_CUDA(cudaGetLastError());
@@ -839,11 +933,16 @@ static int sweep_prepare(cmx_state *s, const char *who) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   SweepPlan &P = s->plan;
   uint32_t items;
-  if (P.pair_lut)
-    items = (uint32_t)(s->g.N0 / 8) * (s->g.N1 / 2) * (s->g.N2 / 2);
-  else
+  int blocks;
+  if (P.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) {
+    // one block iteration = RB whole rows of one (cy,cz) colour
+    uint32_t W = s->g.N0 / 16, RB = 256 / W;
+    uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
+    items = (n_rows + RB - 1) / RB * 256;
+  } else {
     items = (uint32_t)(s->g.N0 / P.S[0]) * (s->g.N1 / P.S[1]) * (s->g.N2 / P.S[2]);
-  int blocks = sweep_blocks_per_replica(items, s->n_replicas);
+  }
+  blocks = sweep_blocks_per_replica(items, s->n_replicas);
   if (P.part_blocks != blocks || !P.d_part_acc) {
     int rc = ensure_partials(s, blocks);
     if (rc) return rc;
@@ -852,6 +951,15 @@ static int sweep_prepare(cmx_state *s, const char *who) {
     CMX_CUDA(cudaMemsetAsync(P.d_part_dE, 0, sizeof(double) * n, s->stream));
     P.attempts = 0;
   }
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
+  if (!s) return invalid("cmx_state_set_sweep_flags: null state");
+  if (flags & ~(uint32_t)(CMX_SWEEP_NO_DE_SUM | CMX_SWEEP_FORCE_GENERIC))
+    return invalid("cmx_state_set_sweep_flags: unknown flag");
+  s->sweep_flags = flags;
+  s->plan.part_blocks = 0;  // the grid may change with the evaluator
   return CMX_OK;
 }
 
@@ -918,7 +1026,7 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
     cmx_set_error("cmx_sweep_info: no sweep plan");
     return CMX_ERR_STATE;
   }
-  const char *nm = s->plan.pair_lut ? "pair_lut" : "generic";
+  const char *nm = (s->plan.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) ? "pair_lut" : "generic";
   if (name && name_cap) {
     std::strncpy(name, nm, name_cap - 1);
     name[name_cap - 1] = 0;
@@ -929,5 +1037,16 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
   if (colour_strides)
     for (int a = 0; a < 3; ++a) colour_strides[a] = s->plan.S[a];
   if (range_k) *range_k = s->plan.range_k;
+  return CMX_OK;
+}
+
+extern "C" int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep) {
+  if (!s || !per_sweep) return invalid("cmx_sweep_launches: null argument");
+  if (!s->plan.valid) {
+    cmx_set_error("cmx_sweep_launches: no sweep plan");
+    return CMX_ERR_STATE;
+  }
+  const bool pair = s->plan.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC);
+  *per_sweep = pair ? 4 : s->plan.n_colours;
   return CMX_OK;
 }

@@ -235,7 +235,7 @@ class SlabRunner:
         te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=self.mem.device)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         n_sites = self.N[0] * self.N[1] * self.N[2] * self.n_sublat
-        n_col = self._info["n_colours"]
+        n_col = self._info["launches_per_sweep"]
         launches = K * S * n_col
         return dict(ms=float(ms.item()), clocks=clk, accept_rate=float(cnt[1] / max(cnt[0], 1.0)),
                     launches=launches, kernel_ms=float(ms.item()) / (K * S * n_col),

@@ -199,6 +199,16 @@ int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
 int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
                          int32_t kgroup);
 int cmx_counters_reset(cmx_state *s);
+/* Sweep options (default 0).
+ *   CMX_SWEEP_NO_DE_SUM     do not accumulate cmx_counters.dE_sum (the reference
+ *                           loop counts acceptances only,
+ *                           methods/occupation_metropolis.hh:109-116)
+ *   CMX_SWEEP_FORCE_GENERIC use the generic term-list evaluator even where the
+ *                           pair-LUT kernel applies (same random bits, same
+ *                           decisions: a cross-check of the fast path) */
+#define CMX_SWEEP_NO_DE_SUM 1u
+#define CMX_SWEEP_FORCE_GENERIC 2u
+int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* synchronises the state's stream; counters[n_replicas] */
 int cmx_counters_read(cmx_state *s, cmx_counters *counters);
 /* Name of the evaluator the sweep uses for the bound ECI ("pair_lut",
@@ -208,6 +218,10 @@ int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
                    double *bytes_per_step, double *flops_per_step,
                    int32_t *n_colours, int32_t *colour_strides /*[3]*/,
                    int32_t *range_k);
+
+/* Kernel launches one full sweep takes with the current evaluator (the
+ * pair-LUT kernel fuses both x colours of a row: 4 launches for 8 colours). */
+int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep);
 
 /* Occupant bookkeeping needed by the reference-order mode:
  * sublat_to_asym[n_sublat], occ_to_species[n_sublat][max_occ] (-1 padded). */

@@ -178,7 +178,8 @@ def _sweep_state(dev_tables, systems, case_sys, eci_key, N, T, mu, n_replicas=1,
 @pytest.mark.parametrize("case_sys,eci_key,N,expect", [
     ("fcc", "eci_sparse", (16, 16, 16), "pair_lut"),
     ("fcc", "eci_full", (16, 16, 16), "generic"),
-    ("fcc", "eci_sparse", (12, 12, 12), "generic"),   # N0 % 8 != 0 -> generic evaluator
+    ("fcc", "eci_sparse", (12, 12, 12), "generic"),   # N0 % 16 != 0 -> generic evaluator
+    ("fcc", "eci_sparse", (64, 6, 10), "pair_lut"),
     ("zro", "eci", (8, 8, 8), "generic"),
 ])
 def test_sweep_energy_bookkeeping(dev_tables, systems, case_sys, eci_key, N, expect):
@@ -226,6 +227,59 @@ def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
     assert (a.download_occ(0) != a.download_occ(1)).any()
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1)])
+def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas):
+    """The 16-sites-per-thread LUT kernel and the one-site-per-thread generic
+    evaluator (whose delta E is checked against the reference kernels) draw the
+    same random bits and must make the same decisions: identical occupation
+    after several sweeps, identical acceptance counts.  Covers one chunk per row
+    (N0=16), rows that do not fill a block (N0=48), a row spanning a whole warp
+    (N0=512), replicas with different conditions and the int8 transfer path."""
+    mu = [0.2, -0.1]
+    a, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5)
+    b, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5)
+    if n_replicas > 1:
+        ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.4], 3)
+        a.set_conditions(500.0, ex2, replica=1)
+        b.set_conditions(500.0, ex2, replica=1)
+    b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC)
+    assert a.sweep_info()["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
+    for r in range(n_replicas):
+        assert (a.download_occ(r) == b.download_occ(r)).all()
+    ca = a.sgc_sweep(6, seed=9)
+    cb = b.sgc_sweep(6, seed=9)
+    for r in range(n_replicas):
+        oa, ob = a.download_occ(r), b.download_occ(r)
+        assert (oa == ob).all(), f"replica {r}: {(oa != ob).sum()} sites differ"
+        assert (a.download_occ(r, dtype=np.int8) == oa).all()
+        assert ca[r].n_accept == cb[r].n_accept and ca[r].n_attempt == cb[r].n_attempt
+        assert ca[r].dE_sum == pytest.approx(cb[r].dE_sum, rel=1e-9, abs=1e-9)
+    # without the dE accumulation the trajectory is the same
+    a.set_sweep_flags(_capi.CMX_SWEEP_NO_DE_SUM)
+    a.sgc_sweep(2, seed=9, first_sweep=6)
+    b.sgc_sweep(2, seed=9, first_sweep=6)
+    for r in range(n_replicas):
+        assert (a.download_occ(r) == b.download_occ(r)).all()
+    a.close()
+    b.close()
+
+
+def test_int8_round_trip_of_coded_states(dev_tables):
+    """Ternary single-sublattice states store occupant 2 as 16 on the device
+    (Geom::coded); every transfer path must hide that."""
+    st = _capi.State(dev_tables("fcc_default"), (16, 4, 2))
+    occ = np.random.default_rng(3).integers(0, 3, 128).astype(np.int32)
+    st.upload_occ(occ)
+    assert (st.download_occ() == occ).all()
+    assert (st.download_occ(dtype=np.int8) == occ).all()
+    st.upload_occ(occ.astype(np.int8))
+    assert (st.download_occ() == occ).all()
+    assert (st.composition()[0] == np.bincount(occ, minlength=3)).all()
+    with pytest.raises(_capi.CmxError):
+        st.upload_occ(np.full(128, 3, dtype=np.int8))
+    st.close()
 
 
 def test_pair_lut_sweep_equals_generic_sweep(dev_tables, systems):
