@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--box", type=int, default=N_BOX)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = no dE sum)")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,6 +209,7 @@ def main():
         st.set_eci(eci["index"], eci["value"])
         st.set_conditions(TEMPERATURE, ex)
         st.randomize(2026)
+        st.set_sweep_flags(args.sweep_flags)
         info = st.sweep_info()
         stream = torch.cuda.ExternalStream(st.stream())
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,13 +237,13 @@ def main():
         host = torch.empty(n_sites, dtype=torch.int8).pin_memory()
         harr = host.numpy()
         st.download_occ(dtype=np.int8, out=harr)
-        for _ in range(2):
+        for _ in range(0 if args.no_e2e else 2):
             st.upload_occ(harr)
             st.sgc_sweep(S, seed=3, first_sweep=0, counters=True)
             st.download_occ(dtype=np.int8, out=harr)
         torch.cuda.synchronize()
         te0 = time.perf_counter()
-        for k in range(K):
+        for k in range(1 if args.no_e2e else K):
             st.upload_occ(harr)
             c2 = st.sgc_sweep(S, seed=3, first_sweep=(k + 1) * S, counters=True)
             st.download_occ(dtype=np.int8, out=harr)

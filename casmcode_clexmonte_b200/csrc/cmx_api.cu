@@ -224,7 +224,7 @@ __global__ void k_scatter_occ(const SrcT *__restrict__ src, int8_t *dst, Geom g,
 }
 // in-place validation of an int8 image copied straight into the state (16 sites
 // per thread-iteration; n_cells is a multiple of 16 on this path)
-// (and re-coded in place when the state stores occupant 2 as 16, Geom::coded)
+// (and re-coded in place when the state stores occupant 2 as 18, Geom::coded)
 __global__ void k_validate_occ16(int4 *occ, int64_t n16, int64_t cells16,
                                  const int32_t *__restrict__ n_occ, int coded,
                                  int *bad) {
@@ -238,8 +238,8 @@ __global__ void k_validate_occ16(int4 *occ, int64_t n16, int64_t cells16,
     for (int q = 0; q < 4; ++q) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) flag |= (int)((w[q] >> (8 * k)) & 0xffu) >= no;
-      // 2 -> 16 per byte lane: move bit 1 to bit 4
-      w[q] = (w[q] & 0x01010101u) | ((w[q] & 0x02020202u) << 3);
+      // 2 -> 18 per byte lane: copy bit 1 to bit 4
+      w[q] = w[q] | ((w[q] & 0x02020202u) << 3);
     }
     if (coded) occ[x] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
   }

@@ -48,16 +48,17 @@ struct Geom {
   int64_t sub_stride;  // bytes between sublattices: N0*N1*(N2+2*halo)
   int64_t rep_stride;  // bytes between replicas:   n_sublat*sub_stride
   // Storage code of the occupants.  coded == 0: the byte is the occupant index.
-  // coded == 1 (single-sublattice ternary states): occupant 2 is stored as 16, so
-  // that the byte-lane sum over a site's neighbors IS n1 + 16*n2, the index of
-  // the pair-LUT sweep -- no per-neighbor masking.  cmx_dec() reads both codes.
+  // coded == 1 (single-sublattice ternary states): occupant 2 is stored as 18, so
+  // that the byte-lane sum over a site's neighbors IS n1 + 18*n2, the index of
+  // the pair-LUT sweep -- no per-neighbor masking -- and code & 3 is still the
+  // occupant.  cmx_dec() reads both codes.
   int32_t coded;
 };
 
 // occupant index <-> stored byte (see Geom::coded)
 __host__ __device__ __forceinline__ int cmx_dec(int raw) { return (raw & 7) | (raw >> 3); }
 __host__ __device__ __forceinline__ int cmx_enc(const Geom &g, int v) {
-  return (g.coded && v == 2) ? 16 : v;
+  return (g.coded && v == 2) ? 18 : v;
 }
 
 struct cmx_tables {
@@ -94,7 +95,7 @@ struct SweepPlan {
   int32_t n_lut = 0;      // nocc*(nocc-1)*256 entries
   double *d_pair_dE = nullptr;       // [n_lut] clex dE per (oi, alt, counts)
   int32_t n_tab = 0;              // entries of the pair16 acceptance table
-  uint2 *d_tab = nullptr;         // [replica][n_tab] {threshold(15 bit)<<1|1, proposed code}
+  uint32_t *d_tab = nullptr;      // [replica][n_tab] threshold(15 bit)<<9 | 1<<8 | proposed code
   uint32_t *d_thr_lo = nullptr;   // [replica][n_tab] low 32 bits of the threshold (tie break)
   double *d_dEpot = nullptr;      // [replica][n_tab] dE - exch
   bool thr_dirty = true;

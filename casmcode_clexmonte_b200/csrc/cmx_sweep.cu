@@ -89,17 +89,22 @@ __global__ void k_build_pair_lut(DevTables T, int nocc, int z,
 //   accept  <=>  u47 < t47,   t47 = 2^47                        if dE < 0
 //                              t47 = ceil(exp(-dE*beta) * 2^47)  otherwise
 // (metropolis_acceptance [EXT]: `if (dE < 0) return true; return rng < exp(-dE*beta)`).
-// Table index  idx = cnt | sa << 8,  cnt = n1 + 16*n2 (neighbor species counts),
-// sa = self occupant | alt << 2.  Entry .x = (t47 >> 32) << 1 | 1 -- compared
-// with (field | 1), so neither side needs a shift -- and .y = the storage code of
-// the proposed occupant.
+// Table index  idx = cnt | sa << 8:  cnt = n1 + CMX_VA_CODE*n2 is the byte-lane
+// sum of the neighbors' storage codes (n1, n2 = neighbor counts of occupants 1
+// and 2), sa = self occupant | alt << 2.  One 4-byte entry
+//   e = t << 8 | code,  t = (t47 >> 32) << 1 | 1,  code = storage code proposed
+// is compared with (field | 1) << 8 | 0xFF, so one unsigned compare decides
+// u15 < t47 >> 32 and a tie is "the upper 24 bits are equal".  4-byte entries
+// and an even Va code that is not a multiple of 16 spread the physically
+// frequent (n1, n2) over the 32 shared-memory banks.
 // ---------------------------------------------------------------------------
 #define CMX_TAB16(NOCC) ((NOCC) == 3 ? 2048 : 512)
+#define CMX_VA_CODE 18  // must match cmx_enc()
 
-__global__ void k_build_tab16(const double *__restrict__ lut, int nocc, int max_occ,
+__global__ void k_build_tab16(const double *__restrict__ lut, int nocc, int z, int max_occ,
                               const double *__restrict__ beta,
                               const double *__restrict__ exch, int exch_stride,
-                              int n_tab, uint2 *__restrict__ tab,
+                              int n_tab, uint32_t *__restrict__ tab,
                               uint32_t *__restrict__ thr_lo,
                               double *__restrict__ dEpot) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,20 +112,20 @@ __global__ void k_build_tab16(const double *__restrict__ lut, int nocc, int max_
   if (idx >= n_tab) return;
   const int cnt = idx & 255, sa = idx >> 8;
   const int oi = sa & 3, alt = sa >> 2;
-  const int n1 = cnt & 15, n2 = cnt >> 4;
+  const int n2 = (nocc == 3) ? cnt / CMX_VA_CODE : 0;
+  const int n1 = cnt - n2 * CMX_VA_CODE;
   size_t o = (size_t)r * n_tab + idx;
-  if (oi >= nocc || alt >= nocc - 1 || (nocc < 3 && n2 > 0)) {
-    tab[o] = make_uint2(1u, 0u);  // never accepted (field | 1 >= 1), tie -> thr_lo 0
+  if (oi >= nocc || alt >= nocc - 1 || n1 + n2 > z) {
+    tab[o] = 1u << 8;  // never accepted ((field | 1) >= 1); a tie finds thr_lo 0
     thr_lo[o] = 0;
     dEpot[o] = 0.0;
     return;
   }
-  (void)n1;
   int of = oi + 1 + alt;
   if (of >= nocc) of -= nocc;
   const int pair = oi * (nocc - 1) + alt;
   double x = exch[(size_t)r * exch_stride + (0 * max_occ + oi) * max_occ + of];
-  double dE = __dsub_rn(lut[(pair << 8) | cnt], x);
+  double dE = __dsub_rn(lut[(pair << 8) | n1 | (n2 << 4)], x);
   unsigned long long t;
   const double two47 = 140737488355328.0;
   if (dE < 0.0) {
@@ -129,7 +134,8 @@ __global__ void k_build_tab16(const double *__restrict__ lut, int nocc, int max_
     double p = exp(-dE * beta[r]);
     t = (unsigned long long)ceil(p * two47);
   }
-  tab[o] = make_uint2((uint32_t)(t >> 32) << 1 | 1u, (uint32_t)((of == 2) ? 16 : of));
+  const uint32_t t17 = (uint32_t)(t >> 32) << 1 | 1u;
+  tab[o] = (t17 << 8) | (uint32_t)((of == 2) ? CMX_VA_CODE : of);
   thr_lo[o] = (uint32_t)(t & 0xFFFFFFFFull);
   dEpot[o] = dE;
 }
@@ -166,7 +172,7 @@ struct Pair16Args {
   FastDiv divW, divJ;
   uint32_t J;        // rows of this colour per layer (N1 / 2)
   uint32_t n_rows;   // J * (N2 / 2)
-  const uint2 *tab;        // [replica][n_tab]
+  const uint32_t *tab;     // [replica][n_tab]
   const uint32_t *thr_lo;  // [replica][n_tab]
   const double *dEpot;     // [replica][n_tab]
   long long *part_acc;     // [replica][gridDim.x]
@@ -177,44 +183,56 @@ struct Pair16Args {
   int k_offset;          // global k of local layer 0 (slab decomposition)
 };
 
-// The two x colours of one 16-site chunk.
+// shared memory is addressed with explicit 32-bit addresses: the dE table sits at
+// a compile-time offset from the acceptance table, so one address serves both
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64_at(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+
+// One x colour of one 16-site chunk.
 //  cnt[i]  byte-lane neighbor sums of the chunk (only the lanes of colour CX are used)
 //  C[i]    the chunk (storage codes); accepted sites are replaced in place
-//  SC[i]   occupant indices of the chunk, byte-wise (0,1,2)
+//  tab     shared-memory address of the acceptance table, dE table NTAB*4 bytes later
+//          (entry idx at tab + 4*idx resp. tab + NTAB*4 + 8*idx)
 template <int CX, int NOCC, bool ACCUM>
 __device__ __forceinline__ void pair16_update(const uint32_t (&cnt)[4], uint32_t (&C)[4],
-                                              const uint32_t (&SC)[4], const Philox &ph,
-                                              const uint2 *__restrict__ sh_tab,
-                                              const double *__restrict__ sh_dE,
-                                              uint32_t &n_acc, double &e_sum,
-                                              bool &tie) {
-  constexpr uint32_t lanes = CX ? 0xFF00FF00u : 0x00FF00FFu;
+                                              const Philox &ph, uint32_t tab, uint32_t &n_acc,
+                                              double &e_sum, bool &tie) {
+  constexpr int NTAB = CMX_TAB16(NOCC);
+  constexpr uint32_t lanes = CX ? 0x03000300u : 0x00030003u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t R = ph.c[i];
-    // occupant | alt << 2 in the target lanes, zero elsewhere
+    // occupant | alt << 2 in the target lanes, zero elsewhere (code & 3 = occupant)
     const uint32_t altw = (NOCC == 3) ? ((R & 0x00010001u) << (CX ? 10 : 2)) : 0u;
-    const uint32_t SA = (SC[i] | altw) & lanes;
+    const uint32_t SA = (C[i] & lanes) | altw;
     const uint32_t Rw = R | 0x00010001u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      constexpr int dummy = 0;
-      (void)dummy;
       const int b = 2 * h + CX;  // byte of the word
       // idx = cnt byte b | SA byte b << 8  (bytes 2,3 <- a zero byte of SA)
       const uint32_t sel = (uint32_t)b | ((uint32_t)(4 + b) << 4) | ((uint32_t)(4 + (b ^ 1)) << 8) |
                            ((uint32_t)(4 + (b ^ 1)) << 12);
       const uint32_t idx = __byte_perm(cnt[i], SA, sel);
-      const uint2 e = sh_tab[idx];
-      const uint32_t f1 = h ? (Rw >> 16) : (Rw & 0xFFFFu);
-      const bool ok = f1 < e.x;
-      tie |= (f1 == e.x);
+      const uint32_t e = lds_u32(tab + 4u * idx);
+      // (field | 1) << 8 | 0xFF
+      const uint32_t f1s = __byte_perm(Rw, 0xFFu, h ? 0x5324u : 0x5104u);
+      const bool ok = f1s < e;
+      tie |= ((f1s ^ e) < 256u);
       if (ok) {
-        // byte b of C[i] <- proposed code
+        // byte b of C[i] <- proposed code (byte 0 of e)
         const uint32_t ins = (b == 0) ? 0x3214u : (b == 1) ? 0x3240u : (b == 2) ? 0x3410u : 0x4210u;
-        C[i] = __byte_perm(C[i], e.y, ins);
+        C[i] = __byte_perm(C[i], e, ins);
         n_acc += 1;
-        if (ACCUM) e_sum += sh_dE[idx];
+        if (ACCUM) e_sum += lds_f64_at<NTAB * 4>(tab + 4u * idx + 4u * idx);
       }
     }
   }
@@ -222,35 +240,33 @@ __device__ __forceinline__ void pair16_update(const uint32_t (&cnt)[4], uint32_t
 
 // rare path (probability 2^-15 per site): the first 15 bits of the uniform equal
 // the threshold's; draw 32 more bits per site and finish the 47-bit comparison.
+// Re-derives everything from the chunk as it was BEFORE this colour's update.
 template <int CX, int NOCC, bool ACCUM>
-__device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], uint32_t (&C)[4],
-                                         const uint32_t (&SC)[4], const Philox &ph,
-                                         const uint2 *sh_tab, const double *sh_dE,
-                                         const uint32_t *__restrict__ thr_lo, uint32_t gid,
-                                         uint32_t r, uint32_t sweep_lo, uint32_t ctr, uint32_t k0,
-                                         uint32_t k1, uint32_t &n_acc, double &e_sum) {
-  constexpr uint32_t lanes = CX ? 0xFF00FF00u : 0x00FF00FFu;
+__device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], const uint32_t (&C0)[4],
+                                            uint32_t (&C)[4], const Philox &ph, uint32_t tab,
+                                            const uint32_t *__restrict__ thr_lo, uint32_t gid,
+                                            uint32_t r, uint32_t sweep_lo, uint32_t ctr, uint32_t k0,
+                                            uint32_t k1, uint32_t &n_acc, double &e_sum) {
+  constexpr int NTAB = CMX_TAB16(NOCC);
   const Philox lo0 = philox4x32_10(gid, r, sweep_lo, ctr | 1u, k0, k1);
   const Philox lo1 = philox4x32_10(gid, r, sweep_lo, ctr | 2u, k0, k1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t R = ph.c[i];
-    const uint32_t altw = (NOCC == 3) ? ((R & 0x00010001u) << (CX ? 10 : 2)) : 0u;
-    const uint32_t SA = (SC[i] | altw) & lanes;
-    const uint32_t Rw = R | 0x00010001u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int b = 2 * h + CX;
-      const uint32_t idx = ((cnt[i] >> (8 * b)) & 0xFFu) | (((SA >> (8 * b)) & 0xFFu) << 8);
-      const uint2 e = sh_tab[idx];
-      const uint32_t f1 = h ? (Rw >> 16) : (Rw & 0xFFFFu);
-      if (f1 != e.x) continue;
+      const uint32_t field = h ? (R >> 16) : (R & 0xFFFFu);
+      const uint32_t sa = ((C0[i] >> (8 * b)) & 3u) | ((NOCC == 3) ? ((field & 1u) << 2) : 0u);
+      const uint32_t idx = ((cnt[i] >> (8 * b)) & 0xFFu) | (sa << 8);
+      const uint32_t e = lds_u32(tab + 4u * idx);
+      if ((field | 1u) != (e >> 8)) continue;
       const int q = 2 * i + h;  // target site of the chunk, 0..7
       const uint32_t w32 = (q < 4) ? lo0.c[q & 3] : lo1.c[q & 3];
       if (w32 < thr_lo[idx]) {
-        C[i] = (C[i] & ~(0xFFu << (8 * b))) | (e.y << (8 * b));
+        C[i] = (C[i] & ~(0xFFu << (8 * b))) | ((e & 0xFFu) << (8 * b));
         n_acc += 1;
-        if (ACCUM) e_sum += sh_dE[idx];
+        if (ACCUM) e_sum += lds_f64_at<NTAB * 4>(tab + 8u * idx);
       }
     }
   }
@@ -270,28 +286,31 @@ __device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], uint32_t (
 //    (1 proposal bit + 15 uniform bits); the Metropolis test is one integer
 //    compare against the shared-memory table, 32 more bits are drawn only on a tie;
 //  * accepted dE (tabulated) is summed in FP64 per thread, reduced per block.
-template <int NOCC, uint32_t MASK_CT, bool ACCUM>
-__global__ void __launch_bounds__(256, 3) k_sweep_pair16(Pair16Args a) {
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
   constexpr int NTAB = CMX_TAB16(NOCC);
-  __shared__ uint2 sh_tab[NTAB];
-  __shared__ double sh_dE[ACCUM ? NTAB : 1];
+  // [acceptance table: NTAB x 4 B][dE table: NTAB x 8 B]
+  __shared__ __align__(16) unsigned char sh_tables[NTAB * 4 + (ACCUM ? NTAB * 8 : 0)];
   __shared__ uint8_t sh_x[2][256];
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
   const uint32_t r = blockIdx.y;
   {
-    const uint2 *gt = a.tab + (size_t)r * NTAB;
+    const uint32_t *gt = a.tab + (size_t)r * NTAB;
     const double *ge = a.dEpot + (size_t)r * NTAB;
+    uint32_t *st = reinterpret_cast<uint32_t *>(sh_tables);
+    double *se = reinterpret_cast<double *>(sh_tables + NTAB * 4);
     for (int q = threadIdx.x; q < NTAB; q += blockDim.x) {
-      sh_tab[q] = gt[q];
-      if (ACCUM) sh_dE[q] = ge[q];
+      st[q] = gt[q];
+      if (ACCUM) se[q] = ge[q];
     }
   }
+  const uint32_t tab = (uint32_t)__cvta_generic_to_shared(sh_tables);
   __syncthreads();
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const Geom &g = a.g;
   int8_t *base = a.occ + (size_t)r * g.rep_stride;  // includes the ghost layers
-  asm volatile("" : "+l"(base));  // keep the replica base in a register pair
+  // (no asm pinning of base: keep the global address space visible to the compiler)
   const uint32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
   const uint32_t layer = N0 * N1;
   const bool halo = g.halo != 0;
@@ -310,7 +329,7 @@ __global__ void __launch_bounds__(256, 3) k_sweep_pair16(Pair16Args a) {
   for (uint32_t row0 = blockIdx.x * a.RB; row0 < a.n_rows; row0 += gridDim.x * a.RB, ++it) {
     const uint32_t row = row0 + rl;
     const bool on = lane_on && row < a.n_rows;
-    uint32_t C[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0}, SC[4];
+    uint32_t C[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0};
     uint32_t cl = 0, off_c = 0, gid = 0;
     if (on) {
       uint32_t kk, jj;
@@ -371,9 +390,6 @@ __global__ void __launch_bounds__(256, 3) k_sweep_pair16(Pair16Args a) {
       T[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
       T[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
       T[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        SC[i] = (NOCC == 3) ? ((C[i] & 0x01010101u) | ((C[i] >> 3) & 0x02020202u)) : C[i];
       // ---- x colour 0: even lanes; same-row neighbors are odd lanes (old values)
       uint32_t cnt[4];
 #pragma unroll
@@ -385,10 +401,11 @@ __global__ void __launch_bounds__(256, 3) k_sweep_pair16(Pair16Args a) {
       const uint32_t ctr0 = a.ctr_hi;
       const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr0, a.k0, a.k1);
       bool tie = false;
-      pair16_update<0, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, n_acc, e_sum, tie);
+      const uint32_t C0[4] = {C[0], C[1], C[2], C[3]};
+      pair16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, n_acc, e_sum, tie);
       if (tie)
-        pair16_ties<0, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, a.thr_lo + (size_t)r * NTAB, gid,
-                                    r, a.sweep_lo, ctr0, a.k0, a.k1, n_acc, e_sum);
+        pair16_ties<0, NOCC, ACCUM>(cnt, C0, C, ph, tab, a.thr_lo + (size_t)r * NTAB, gid, r,
+                                    a.sweep_lo, ctr0, a.k0, a.k1, n_acc, e_sum);
       sh_x[it & 1][threadIdx.x] = (uint8_t)(C[0] & 0xFFu);
     }
     __syncthreads();
@@ -406,10 +423,11 @@ __global__ void __launch_bounds__(256, 3) k_sweep_pair16(Pair16Args a) {
       const uint32_t ctr1 = a.ctr_hi | 0x100u;
       const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr1, a.k0, a.k1);
       bool tie = false;
-      pair16_update<1, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, n_acc, e_sum, tie);
+      const uint32_t C0[4] = {C[0], C[1], C[2], C[3]};
+      pair16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, n_acc, e_sum, tie);
       if (tie)
-        pair16_ties<1, NOCC, ACCUM>(cnt, C, SC, ph, sh_tab, sh_dE, a.thr_lo + (size_t)r * NTAB, gid,
-                                    r, a.sweep_lo, ctr1, a.k0, a.k1, n_acc, e_sum);
+        pair16_ties<1, NOCC, ACCUM>(cnt, C0, C, ph, tab, a.thr_lo + (size_t)r * NTAB, gid, r,
+                                    a.sweep_lo, ctr1, a.k0, a.k1, n_acc, e_sum);
       *reinterpret_cast<uint4 *>(base + off_c) = make_uint4(C[0], C[1], C[2], C[3]);
     }
   }
@@ -742,7 +760,7 @@ int cmx_plan_sweep(cmx_state *s) {
     for (auto const &kv : V)
       for (size_t x = 0; x < v0.size(); ++x)
         if (std::fabs(kv.second[x] - v0[x]) > 1e-12 * scale) ok = false;
-    if ((int)V.size() > 15) ok = false;  // nibble counters
+    if ((int)V.size() > 14) ok = false;  // byte-lane sums n1 + 18 n2 must stay below 256
     for (auto const &kv : V)
       for (int a = 0; a < 3; ++a)
         if (std::abs(t->nbr[4 * kv.first + a]) > 1) ok = false;
@@ -767,7 +785,7 @@ int cmx_plan_sweep(cmx_state *s) {
     CMX_CUDA(cudaStreamSynchronize(s->stream));
     cudaFree(d_cls);
     P.n_tab = CMX_TAB16(P.nocc);
-    CMX_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(uint2) * P.n_tab * s->n_replicas));
+    CMX_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(uint32_t) * P.n_tab * s->n_replicas));
     CMX_CUDA(cudaMalloc((void **)&P.d_thr_lo, sizeof(uint32_t) * P.n_tab * s->n_replicas));
     CMX_CUDA(cudaMalloc((void **)&P.d_dEpot, sizeof(double) * P.n_tab * s->n_replicas));
     P.pair_lut = true;
@@ -805,20 +823,36 @@ constexpr uint32_t kMaskFcc1NN =
     mbit(0, 0, -1) | mbit(0, 0, 1) | mbit(0, 1, -1) | mbit(0, 1, 0) | mbit(1, -1, 0) |
     mbit(1, 0, -1) | mbit(1, 0, 0);
 
-template <int NOCC>
+template <int NOCC, int MINB>
 static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum) {
   if (fcc) {
-    if (accum) k_sweep_pair16<NOCC, kMaskFcc1NN, true><<<grid, 256, 0, st>>>(a);
-    else k_sweep_pair16<NOCC, kMaskFcc1NN, false><<<grid, 256, 0, st>>>(a);
+    if (accum) k_sweep_pair16<NOCC, kMaskFcc1NN, true, MINB><<<grid, 256, 0, st>>>(a);
+    else k_sweep_pair16<NOCC, kMaskFcc1NN, false, MINB><<<grid, 256, 0, st>>>(a);
   } else {
-    if (accum) k_sweep_pair16<NOCC, 0u, true><<<grid, 256, 0, st>>>(a);
-    else k_sweep_pair16<NOCC, 0u, false><<<grid, 256, 0, st>>>(a);
+    if (accum) k_sweep_pair16<NOCC, 0u, true, MINB><<<grid, 256, 0, st>>>(a);
+    else k_sweep_pair16<NOCC, 0u, false, MINB><<<grid, 256, 0, st>>>(a);
   }
 }
 
+// tuning knobs (environment, read once): resident blocks per SM the pair16 kernel
+// is compiled for, and blocks per SM in the grid
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+static int pair16_minb() {
+  static int v = env_int("CMX_PAIR16_MINB", 3);
+  return v;
+}
+static int sweep_grid_per_sm() {
+  static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 6);
+  return v;
+}
+
+static int sweep_grid_per_sm();
 static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
   int want = (int)((items + 255) / 256);
-  int cap = std::max(1, (148 * 6 + n_replicas - 1) / n_replicas);
+  int cap = std::max(1, (148 * sweep_grid_per_sm() + n_replicas - 1) / n_replicas);
   return std::max(1, std::min(want, cap));
 }
 
@@ -832,7 +866,7 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   if (P.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) {
     if (P.thr_dirty) {
       dim3 grid((P.n_tab + 127) / 128, s->n_replicas);
-      k_build_tab16<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.nocc, T.max_occ, s->d_beta, s->d_exch,
+      k_build_tab16<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.nocc, P.z, T.max_occ, s->d_beta, s->d_exch,
                                                  (int)exs, P.n_tab, P.d_tab, P.d_thr_lo, P.d_dEpot);
       CMX_CUDA(cudaGetLastError());
       P.thr_dirty = false;
@@ -865,8 +899,12 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
         a.cy = cy;
         a.cz = cz;
         a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
-        if (P.nocc == 3) launch_pair16<3>(a, grid, s->stream, fcc, accum);
-        else launch_pair16<2>(a, grid, s->stream, fcc, accum);
+        if (P.nocc == 3) {
+          if (pair16_minb() >= 4) launch_pair16<3, 4>(a, grid, s->stream, fcc, accum);
+          else launch_pair16<3, 3>(a, grid, s->stream, fcc, accum);
+        } else {
+          launch_pair16<2, 3>(a, grid, s->stream, fcc, accum);
+        }
       }
     }
     CMX_CUDA(cudaGetLastError());
