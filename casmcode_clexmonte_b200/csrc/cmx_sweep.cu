@@ -190,6 +190,15 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+// (x, 0xFF) byte permute with the selector as an immediate: `ff` is kept in a
+// register (nvcc would otherwise put the selector in a register and move it
+// from a uniform register before every use)
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt_imm(uint32_t x, uint32_t ff) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(ff), "n"(SEL));
+  return d;
+}
 template <int OFF>
 __device__ __forceinline__ double lds_f64_at(uint32_t addr) {
   double v;
@@ -204,8 +213,8 @@ __device__ __forceinline__ double lds_f64_at(uint32_t addr) {
 //          (entry idx at tab + 4*idx resp. tab + NTAB*4 + 8*idx)
 template <int CX, int NOCC, bool ACCUM>
 __device__ __forceinline__ void pair16_update(const uint32_t (&cnt)[4], uint32_t (&C)[4],
-                                              const Philox &ph, uint32_t tab, uint32_t &n_acc,
-                                              double &e_sum, bool &tie) {
+                                              const Philox &ph, uint32_t tab, uint32_t ff,
+                                              uint32_t &n_acc, double &e_sum, bool &tie) {
   constexpr int NTAB = CMX_TAB16(NOCC);
   constexpr uint32_t lanes = CX ? 0x03000300u : 0x00030003u;
 #pragma unroll
@@ -224,7 +233,7 @@ __device__ __forceinline__ void pair16_update(const uint32_t (&cnt)[4], uint32_t
       const uint32_t idx = __byte_perm(cnt[i], SA, sel);
       const uint32_t e = lds_u32(tab + 4u * idx);
       // (field | 1) << 8 | 0xFF
-      const uint32_t f1s = __byte_perm(Rw, 0xFFu, h ? 0x5324u : 0x5104u);
+      const uint32_t f1s = h ? prmt_imm<0x5324u>(Rw, ff) : prmt_imm<0x5104u>(Rw, ff);
       const bool ok = f1s < e;
       tie |= ((f1s ^ e) < 256u);
       if (ok) {
@@ -306,6 +315,8 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
     }
   }
   const uint32_t tab = (uint32_t)__cvta_generic_to_shared(sh_tables);
+  uint32_t ff;
+  asm volatile("mov.u32 %0, 0xFF;" : "=r"(ff));  // opaque to constant propagation, see prmt_imm
   __syncthreads();
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const Geom &g = a.g;
@@ -354,13 +365,13 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
           const bool center = (dz == 0 && dy == 0);
           if (m3 == 0 && !center) continue;
           const uint32_t off = off_c + dk[dz + 1] + dj[dy + 1];
-          const uint4 ch = *reinterpret_cast<const uint4 *>(base + off);
+          const uint4 ch = *reinterpret_cast<const uint4 *>((base + off));
           if (center) {
             C[0] = ch.x;
             C[1] = ch.y;
             C[2] = ch.z;
             C[3] = ch.w;
-            if (m3 & 1u) cl = *reinterpret_cast<const uint32_t *>(base + (off + dl));
+            if (m3 & 1u) cl = *reinterpret_cast<const uint32_t *>((base + (off + dl)));
             continue;
           }
           if (m3 & 2u) {
@@ -374,14 +385,14 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
             Am[1] += ch.y;
             Am[2] += ch.z;
             Am[3] += ch.w;
-            sm += *reinterpret_cast<const uint32_t *>(base + (off + dl));
+            sm += *reinterpret_cast<const uint32_t *>((base + (off + dl)));
           }
           if (m3 & 4u) {
             Ap[0] += ch.x;
             Ap[1] += ch.y;
             Ap[2] += ch.z;
             Ap[3] += ch.w;
-            sp += *reinterpret_cast<const uint32_t *>(base + (off + dr));
+            sp += *reinterpret_cast<const uint32_t *>((base + (off + dr)));
           }
         }
       }
@@ -402,7 +413,7 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
       const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr0, a.k0, a.k1);
       bool tie = false;
       const uint32_t C0[4] = {C[0], C[1], C[2], C[3]};
-      pair16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, n_acc, e_sum, tie);
+      pair16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
       if (tie)
         pair16_ties<0, NOCC, ACCUM>(cnt, C0, C, ph, tab, a.thr_lo + (size_t)r * NTAB, gid, r,
                                     a.sweep_lo, ctr0, a.k0, a.k1, n_acc, e_sum);
@@ -424,7 +435,7 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
       const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr1, a.k0, a.k1);
       bool tie = false;
       const uint32_t C0[4] = {C[0], C[1], C[2], C[3]};
-      pair16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, n_acc, e_sum, tie);
+      pair16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
       if (tie)
         pair16_ties<1, NOCC, ACCUM>(cnt, C0, C, ph, tab, a.thr_lo + (size_t)r * NTAB, gid, r,
                                     a.sweep_lo, ctr1, a.k0, a.k1, n_acc, e_sum);
@@ -479,6 +490,7 @@ struct GenericSweepArgs {
   // site (same counters, same 47-bit comparison), so that the two evaluators
   // produce the same trajectory and can be compared bit for bit.
   int rng16;
+  int accum;  // CMX_SWEEP_DE_SUM
 };
 
 __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
@@ -554,7 +566,7 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
     if (accept) {
       occ[off] = (int8_t)cmx_enc(g, of);
       ++n_acc;
-      e_sum += dE;
+      if (a.accum) e_sum += dE;
     }
   }
 #pragma unroll
@@ -845,7 +857,7 @@ static int pair16_minb() {
   return v;
 }
 static int sweep_grid_per_sm() {
-  static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 6);
+  static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 3);
   return v;
 }
 
@@ -892,7 +904,7 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     a.k_offset = k_offset;
     dim3 grid(P.part_blocks, s->n_replicas);
     const bool fcc = (P.mask == kMaskFcc1NN);
-    const bool accum = (s->sweep_flags & CMX_SWEEP_NO_DE_SUM) == 0;
+    const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
     for (int cz = 0; cz < 2; ++cz) {
       if (kgroup >= 0 && cz != kgroup) continue;
       for (int cy = 0; cy < 2; ++cy) {
@@ -937,6 +949,7 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   a.sweep_lo = (uint32_t)sweep;
   a.k_offset = k_offset;
   a.rng16 = P.rng16 ? 1 : 0;
+  a.accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) ? 1 : 0;
   dim3 grid(P.part_blocks, s->n_replicas);
   uint32_t colour = 0;
   for (int c2 = 0; c2 < P.S[2]; ++c2)
@@ -994,7 +1007,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
-  if (flags & ~(uint32_t)(CMX_SWEEP_NO_DE_SUM | CMX_SWEEP_FORCE_GENERIC))
+  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;  // the grid may change with the evaluator

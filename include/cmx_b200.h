@@ -179,6 +179,7 @@ typedef struct cmx_counters {
   int64_t n_attempt;   /* attempted steps                                    */
   int64_t n_accept;    /* accepted steps                                     */
   double dE_sum;       /* sum of accepted delta potential energies           */
+                       /*   (only with CMX_SWEEP_DE_SUM, else 0)             */
   int64_t reserved;
 } cmx_counters;
 
@@ -200,13 +201,17 @@ int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
                          int32_t kgroup);
 int cmx_counters_reset(cmx_state *s);
 /* Sweep options (default 0).
- *   CMX_SWEEP_NO_DE_SUM     do not accumulate cmx_counters.dE_sum (the reference
- *                           loop counts acceptances only,
- *                           methods/occupation_metropolis.hh:109-116)
+ *   CMX_SWEEP_DE_SUM        also accumulate cmx_counters.dE_sum, the sum of the
+ *                           accepted delta potential energies (a diagnostic:
+ *                           it must equal E(after) - E(before)).  Off by
+ *                           default -- the reference loop counts acceptances
+ *                           only (methods/occupation_metropolis.hh:109-116)
+ *                           and samples energies from scratch -- and dE_sum
+ *                           then reads 0.
  *   CMX_SWEEP_FORCE_GENERIC use the generic term-list evaluator even where the
  *                           pair-LUT kernel applies (same random bits, same
  *                           decisions: a cross-check of the fast path) */
-#define CMX_SWEEP_NO_DE_SUM 1u
+#define CMX_SWEEP_DE_SUM 1u
 #define CMX_SWEEP_FORCE_GENERIC 2u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* synchronises the state's stream; counters[n_replicas] */

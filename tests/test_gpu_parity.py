@@ -188,6 +188,7 @@ def test_sweep_energy_bookkeeping(dev_tables, systems, case_sys, eci_key, N, exp
     the (faithful) global evaluation; occupants stay in range; counters add up."""
     mu = [0.2, -0.1][:len(systems[case_sys]["axes"]["end_members"])]
     st, sysd, ex = _sweep_state(dev_tables, systems, case_sys, eci_key, N, 900.0, mu)
+    st.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
     info = st.sweep_info()
     assert info["evaluator"] == expect
     n_cells = int(np.prod(N))
@@ -244,7 +245,8 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.4], 3)
         a.set_conditions(500.0, ex2, replica=1)
         b.set_conditions(500.0, ex2, replica=1)
-    b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC)
+    a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
+    b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC | _capi.CMX_SWEEP_DE_SUM)
     assert a.sweep_info()["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
     for r in range(n_replicas):
         assert (a.download_occ(r) == b.download_occ(r)).all()
@@ -256,12 +258,13 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         assert (a.download_occ(r, dtype=np.int8) == oa).all()
         assert ca[r].n_accept == cb[r].n_accept and ca[r].n_attempt == cb[r].n_attempt
         assert ca[r].dE_sum == pytest.approx(cb[r].dE_sum, rel=1e-9, abs=1e-9)
-    # without the dE accumulation the trajectory is the same
-    a.set_sweep_flags(_capi.CMX_SWEEP_NO_DE_SUM)
-    a.sgc_sweep(2, seed=9, first_sweep=6)
-    b.sgc_sweep(2, seed=9, first_sweep=6)
+    # without the dE accumulation (the default) the trajectory is the same
+    a.set_sweep_flags(0)
+    ca = a.sgc_sweep(2, seed=9, first_sweep=6)
+    cb = b.sgc_sweep(2, seed=9, first_sweep=6)
     for r in range(n_replicas):
         assert (a.download_occ(r) == b.download_occ(r)).all()
+        assert ca[r].n_accept == cb[r].n_accept and ca[r].dE_sum == 0.0
     a.close()
     b.close()
 

@@ -28,6 +28,7 @@ def _worker(rank, world, port, N, n_sweeps, out):
     ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [0.1, -0.2], 3)
     init = np.random.default_rng(4).integers(0, 3, N ** 3).astype(np.int8)
     run = SlabRunner(tables, N, sysd["eci_sparse"], 900.0, ex, rank, world, rank, init_occ=init)
+    run.state.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
     run.state.counters_reset()
     run.sweep(n_sweeps, seed=17)
     run.synchronize()
@@ -58,6 +59,7 @@ def test_two_slabs_equal_one_gpu():
     st.set_eci(sysd["eci_sparse"]["index"], sysd["eci_sparse"]["value"])
     st.set_conditions(900.0, semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [0.1, -0.2], 3))
     st.upload_occ(np.random.default_rng(4).integers(0, 3, N ** 3).astype(np.int8))
+    st.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
     cnt = st.sgc_sweep(n_sweeps, seed=17)
     assert (st.download_occ(dtype=np.int8) == out["occ"]).all()
     assert cnt[0].n_accept == int(out["cnt"][1]) and cnt[0].n_attempt == int(out["cnt"][0])
