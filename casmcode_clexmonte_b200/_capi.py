@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "cmx_global_corr", "cmx_energy", "cmx_composition",
     "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches",
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
+    "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
 ]
 
 
@@ -67,6 +68,29 @@ class StepRecord(C.Structure):
     _fields_ = [("l0", C.c_int64), ("l1", C.c_int64), ("new0", C.c_int32), ("new1", C.c_int32),
                 ("accepted", C.c_int32), ("pad", C.c_int32), ("dE", C.c_double)]
 
+
+class PrimEvent(C.Structure):
+    """cmx_prim_event <-> PrimEventData (include/casm/clexmonte/events/event_data.hh:47-72)"""
+    _fields_ = [("n_sites", C.c_int32), ("site", (C.c_int32 * 4) * 4), ("occ_init", C.c_int32 * 4),
+                ("occ_final", C.c_int32 * 4), ("event_type", C.c_int32), ("equivalent_index", C.c_int32)]
+
+
+class EventType(C.Structure):
+    _fields_ = [("n_equivalents", C.c_int32), ("local_tables", C.POINTER(C.c_void_p)),
+                ("n_kra", C.c_int32), ("kra_index", C.c_void_p), ("kra_value", C.c_void_p),
+                ("n_freq", C.c_int32), ("freq_index", C.c_void_p), ("freq_value", C.c_void_p)]
+
+
+class EventState(C.Structure):
+    """cmx_event_state <-> EventState (events/event_data.hh:19-30)"""
+    _fields_ = [("is_allowed", C.c_int32), ("is_normal", C.c_int32), ("dE_final", C.c_double),
+                ("Ekra", C.c_double), ("dE_activated", C.c_double), ("freq", C.c_double),
+                ("rate", C.c_double)]
+
+
+EVENT_STATE_DTYPE = np.dtype([("is_allowed", np.int32), ("is_normal", np.int32), ("dE_final", np.float64),
+                              ("Ekra", np.float64), ("dE_activated", np.float64), ("freq", np.float64),
+                              ("rate", np.float64)])
 
 _lib = None
 
@@ -117,6 +141,11 @@ def lib():
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
+    L.cmx_kmc_create.argtypes = [vp, i32, C.POINTER(EventType), i32, C.POINTER(PrimEvent), C.POINTER(vp)]
+    L.cmx_kmc_destroy.argtypes = [vp]
+    L.cmx_kmc_destroy.restype = None
+    L.cmx_kmc_event_states.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.cmx_kmc_all_rates.argtypes = [vp, vp, vp, C.POINTER(vp)]
     _lib = L
     return L
 
@@ -364,3 +393,73 @@ def rng_stream_test(seed: int, kinds, int_max=None, real_max=None):
     check(lib().cmx_rng_stream_test(int(seed), n, _p(int_max), _p(real_max), _p(kinds), _p(oi),
                                     _p(orl), _p(oraw)))
     return oi, orl, oraw
+
+
+class Kmc:
+    """Device-side event-state calculator of one State (cmx_kmc).
+
+    event_types: list of dicts {local_tables: [Tables per equivalent], kra: (index, value),
+    freq: (index, value)}; prim_events: list of dicts {sites: [(b,i,j,k)], occ_init, occ_final,
+    event_type, equivalent_index} -- see casmcode_clexmonte_b200.kmc for builders."""
+
+    def __init__(self, state: State, event_types, prim_events):
+        self.state = state
+        self._keep = []
+        types = (EventType * len(event_types))()
+        for y, et in enumerate(event_types):
+            hs = (C.c_void_p * len(et["local_tables"]))(*[t._h for t in et["local_tables"]])
+            ki = np.ascontiguousarray(et["kra"][0], dtype=np.uint32)
+            kv = np.ascontiguousarray(et["kra"][1], dtype=np.float64)
+            fi = np.ascontiguousarray(et["freq"][0], dtype=np.uint32)
+            fv = np.ascontiguousarray(et["freq"][1], dtype=np.float64)
+            self._keep += [hs, ki, kv, fi, fv, et["local_tables"]]
+            types[y] = EventType(len(et["local_tables"]), hs, len(ki), _p(ki), _p(kv), len(fi), _p(fi), _p(fv))
+        prim = (PrimEvent * len(prim_events))()
+        for p, ev in enumerate(prim_events):
+            e = prim[p]
+            e.n_sites = len(ev["sites"])
+            if e.n_sites > 4:
+                raise CmxError(CMX_ERR_INVALID, "events with more than 4 sites are not supported")
+            for q, site in enumerate(ev["sites"]):
+                for c in range(4):
+                    e.site[q][c] = int(site[c])
+                e.occ_init[q] = int(ev["occ_init"][q])
+                e.occ_final[q] = int(ev["occ_final"][q])
+            e.event_type = int(ev["event_type"])
+            e.equivalent_index = int(ev["equivalent_index"])
+        self.n_prim = len(prim_events)
+        h = C.c_void_p()
+        check(lib().cmx_kmc_create(state._h, len(event_types), types, len(prim_events), prim, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cmx_kmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def event_states(self, unitcell, prim_event, replica=None) -> np.ndarray:
+        """EventState records (structured array) of the listed events."""
+        uc = np.ascontiguousarray(unitcell, dtype=np.int64)
+        pe = np.ascontiguousarray(prim_event, dtype=np.int32)
+        rp = np.zeros(len(uc), dtype=np.int32) if replica is None else np.ascontiguousarray(replica, dtype=np.int32)
+        if not (len(uc) == len(pe) == len(rp)):
+            raise CmxError(CMX_ERR_INVALID, "event_states: array lengths differ")
+        out = np.zeros(len(uc), dtype=EVENT_STATE_DTYPE)
+        assert out.itemsize == C.sizeof(EventState)
+        check(lib().cmx_kmc_event_states(self._h, len(uc), _p(rp), _p(uc), _p(pe), _p(out)))
+        return out
+
+    def all_rates(self, rates: bool = True):
+        """(rates[replica][unitcell][prim_event] or None, total[replica])"""
+        st = self.state
+        n_cells = int(np.prod(st.N))
+        r = np.zeros((st.n_replicas, n_cells, self.n_prim), dtype=np.float64) if rates else None
+        tot = np.zeros(st.n_replicas, dtype=np.float64)
+        check(lib().cmx_kmc_all_rates(self._h, _p(r) if rates else None, _p(tot), None))
+        return r, tot

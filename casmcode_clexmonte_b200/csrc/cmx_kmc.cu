@@ -1,0 +1,388 @@
+// Kinetic Monte Carlo event states, batched over (trajectory, unit cell, prim
+// event) triples.  One thread evaluates one event exactly as
+//   EventStateCalculator::calculate_event_state       (BaseMonteEventData.cc:87-119)
+//   EventStateCalculator::_default_event_state_calculation (:122-156)
+//   event_is_allowed                                  (events/event_methods.cc:340-351)
+// do: allowed? -> dE_final = ECI . delta_corr(sites applied one after the other)
+// -> local corr of the event's equivalent local clexulator -> E_kra, freq ->
+// dE_activated = dE_final/2 + E_kra, clamped -> rate = freq exp(-beta dE_activated).
+// All correlation arithmetic goes through the faithful evaluator, so dE_final,
+// E_kra and freq are bit-identical to the reference's generated kernels.
+#include <algorithm>
+#include <cstring>
+
+#include "cmx_internal.cuh"
+
+static int invalid(const std::string &msg) {
+  cmx_set_error(msg);
+  return CMX_ERR_INVALID;
+}
+
+struct DevEventType {
+  int32_t n_equivalents;
+  int32_t table0;  // index of equivalent 0 in the DevTables array
+  int32_t kra_beg, kra_end, freq_beg, freq_end;  // into coef_idx / coef_val
+};
+
+struct cmx_kmc {
+  cmx_state *s;
+  int32_t n_types, n_prim;
+  std::vector<cmx_prim_event> prim;
+  std::vector<DevEventType> types;
+  cmx_prim_event *d_prim = nullptr;
+  DevEventType *d_types = nullptr;
+  DevTables *d_tables = nullptr;  // local clexulators, all equivalents of all types
+  uint32_t *d_coef_idx = nullptr;
+  double *d_coef_val = nullptr;
+  double *d_rates = nullptr;  // [replica][cell][prim]
+  double *d_total = nullptr;  // [replica]
+};
+
+struct KmcArgs {
+  DevTables T;  // formation energy basis set
+  Geom g;
+  const int8_t *occ;  // replica 0
+  int n_eci;
+  const uint32_t *eci_idx;
+  const double *eci_val;
+  const double *beta;  // [replica]
+  const cmx_prim_event *prim;
+  const DevEventType *types;
+  const DevTables *local;
+  const uint32_t *coef_idx;
+  const double *coef_val;
+};
+
+__device__ __forceinline__ int kmc_point_index(const DevTables &T, int b) {
+  for (int p = 0; p < T.n_nlist_sublat; ++p)
+    if (T.nlist_sublat[p] == b) return p;
+  return -1;
+}
+
+__device__ void kmc_event_state(const KmcArgs &a, int r, int64_t cell, int pe,
+                                cmx_event_state &out) {
+  const Geom &g = a.g;
+  const DevTables &T = a.T;
+  const int8_t *occ = a.occ + (size_t)r * g.rep_stride;
+  const cmx_prim_event &E = a.prim[pe];
+  int ci = (int)(cell % g.N0);
+  int64_t rest = cell / g.N0;
+  int cj = (int)(rest % g.N1), ck = (int)(rest / g.N1);
+  out.is_allowed = 1;
+  out.is_normal = 0;
+  out.dE_final = out.Ekra = out.dE_activated = out.freq = out.rate = 0.0;
+  int si[CMX_EVENT_MAX_SITES], sj[CMX_EVENT_MAX_SITES], sk[CMX_EVENT_MAX_SITES];
+  // event_is_allowed: every site holds the event's initial occupant
+  for (int q = 0; q < E.n_sites; ++q) {
+    si[q] = cmx_wrap(ci + E.site[q][1], g.N0);
+    sj[q] = cmx_wrap(cj + E.site[q][2], g.N1);
+    sk[q] = cmx_wrap(ck + E.site[q][3], g.N2);
+    int o = cmx_dec(occ[cmx_site_offset(g, E.site[q][0], si[q], sj[q], sk[q])]);
+    if (o != E.occ_init[q]) out.is_allowed = 0;
+  }
+  if (!out.is_allowed) return;
+  // dE_final = coefficients . occ_delta(linear_site_index, occ_final): sites are
+  // changed one after the other (Correlations::occ_delta [EXT])
+  double dE = 0.0;
+  for (int c = 0; c < a.n_eci; ++c) {
+    Override ov;
+    ov.n = 0;
+    double acc = 0.0;
+    for (int q = 0; q < E.n_sites; ++q) {
+      int b = E.site[q][0];
+      int p = kmc_point_index(T, b);
+      double d = 0.0;
+      if (p >= 0) {
+        int fi = p * T.corr_size + (int)a.eci_idx[c];
+        d = cmx_eval_function(T, g, occ, T.delta_gbeg[fi], T.delta_gbeg[fi + 1], si[q], sj[q],
+                              sk[q], ov, b, E.occ_init[q], E.occ_final[q]);
+      }
+      acc = (q == 0) ? d : __dadd_rn(acc, d);
+      ov.off[ov.n] = cmx_site_offset(g, b, si[q], sj[q], sk[q]);
+      ov.occ[ov.n] = E.occ_final[q];
+      ov.n++;
+    }
+    dE = __dadd_rn(dE, __dmul_rn(a.eci_val[c], acc));
+  }
+  out.dE_final = dE;
+  // local correlations of this equivalent about the unit cell, only the
+  // functions that carry a kra or freq coefficient
+  const DevEventType &Y = a.types[E.event_type];
+  const DevTables &L = a.local[Y.table0 + E.equivalent_index];
+  Override none;
+  none.n = 0;
+  double ekra = 0.0, freq = 0.0;
+  for (int q = Y.kra_beg; q < Y.kra_end; ++q) {
+    int c = (int)a.coef_idx[q];
+    double v = cmx_eval_function(L, g, occ, L.global_gbeg[c], L.global_gbeg[c + 1], ci, cj, ck,
+                                 none, 0, 0, 0);
+    ekra = __dadd_rn(ekra, __dmul_rn(a.coef_val[q], v));
+  }
+  for (int q = Y.freq_beg; q < Y.freq_end; ++q) {
+    int c = (int)a.coef_idx[q];
+    double v = cmx_eval_function(L, g, occ, L.global_gbeg[c], L.global_gbeg[c + 1], ci, cj, ck,
+                                 none, 0, 0, 0);
+    freq = __dadd_rn(freq, __dmul_rn(a.coef_val[q], v));
+  }
+  out.Ekra = ekra;
+  out.freq = freq;
+  // BaseMonteEventData.cc:148-155
+  double dEa = __dadd_rn(__dmul_rn(dE, 0.5), ekra);
+  out.is_normal = (dEa > 0.0) && (dEa > dE);
+  if (dEa < dE) dEa = dE;
+  if (dEa < 0.0) dEa = 0.0;
+  out.dE_activated = dEa;
+  out.rate = freq * exp(-a.beta[r] * dEa);
+}
+
+__global__ void k_kmc_event_states(KmcArgs a, int64_t n, const int32_t *__restrict__ replica,
+                                   const int64_t *__restrict__ cell,
+                                   const int32_t *__restrict__ prim,
+                                   cmx_event_state *__restrict__ out) {
+  int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  cmx_event_state st;
+  kmc_event_state(a, replica[x], cell[x], prim[x], st);
+  out[x] = st;
+}
+
+// every event of every replica; thread x = (replica, cell, prim) with prim fastest
+__global__ void k_kmc_all_rates(KmcArgs a, int n_prim, int64_t total,
+                                double *__restrict__ rates) {
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < total;
+       x += (int64_t)gridDim.x * blockDim.x) {
+    int pe = (int)(x % n_prim);
+    int64_t rc = x / n_prim;
+    int64_t cell = rc % a.g.n_cells;
+    int r = (int)(rc / a.g.n_cells);
+    cmx_event_state st;
+    kmc_event_state(a, r, cell, pe, st);
+    rates[x] = st.rate;
+  }
+}
+
+// per-replica total rate: fixed-order two-stage sum (deterministic)
+__global__ void k_kmc_sum(const double *__restrict__ rates, int64_t per_replica,
+                          double *__restrict__ partial) {
+  __shared__ double sh[256];
+  int r = blockIdx.y;
+  const double *p = rates + (size_t)r * per_replica;
+  double acc = 0.0;
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < per_replica;
+       x += (int64_t)gridDim.x * blockDim.x)
+    acc += p[x];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)r * gridDim.x + blockIdx.x] = sh[0];
+}
+__global__ void k_kmc_sum2(const double *__restrict__ partial, int nb, double *__restrict__ total) {
+  int r = blockIdx.x;
+  if (threadIdx.x) return;
+  double a = 0.0;
+  for (int q = 0; q < nb; ++q) a += partial[(size_t)r * nb + q];
+  total[r] = a;
+}
+
+template <typename T>
+static int kmc_to_device(const std::vector<T> &v, T **d) {
+  size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+  CMX_CUDA(cudaMalloc((void **)d, bytes));
+  if (!v.empty())
+    CMX_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return CMX_OK;
+}
+
+extern "C" void cmx_kmc_destroy(cmx_kmc *k) {
+  if (!k) return;
+  cudaSetDevice(k->s->t->device);
+  cudaFree(k->d_prim);
+  cudaFree(k->d_types);
+  cudaFree(k->d_tables);
+  cudaFree(k->d_coef_idx);
+  cudaFree(k->d_coef_val);
+  cudaFree(k->d_rates);
+  cudaFree(k->d_total);
+  delete k;
+}
+
+extern "C" int cmx_kmc_create(cmx_state *s, int32_t n_types, const cmx_event_type *types,
+                              int32_t n_prim, const cmx_prim_event *prim, cmx_kmc **out) {
+  if (!s || !types || !prim || !out || n_types <= 0 || n_prim <= 0)
+    return invalid("cmx_kmc_create: bad argument");
+  if (!s->d_eci_idx) {
+    cmx_set_error("cmx_kmc_create: bind the formation_energy ECI first (cmx_state_set_eci)");
+    return CMX_ERR_STATE;
+  }
+  const DevTables &T = s->t->d;
+  if (T.n_point_corr != T.n_nlist_sublat)
+    return invalid("cmx_kmc_create: the state's basis set must be a global (periodic) clexulator");
+  std::vector<DevTables> tabs;
+  std::vector<DevEventType> dtypes;
+  std::vector<uint32_t> cidx;
+  std::vector<double> cval;
+  for (int y = 0; y < n_types; ++y) {
+    const cmx_event_type &Y = types[y];
+    if (Y.n_equivalents <= 0 || !Y.local_tables || Y.n_kra < 0 || Y.n_freq < 0 ||
+        (Y.n_kra && (!Y.kra_index || !Y.kra_value)) || (Y.n_freq && (!Y.freq_index || !Y.freq_value)))
+      return invalid("cmx_kmc_create: bad event type");
+    DevEventType d;
+    d.n_equivalents = Y.n_equivalents;
+    d.table0 = (int32_t)tabs.size();
+    for (int e = 0; e < Y.n_equivalents; ++e) {
+      const cmx_tables *lt = Y.local_tables[e];
+      if (!lt) return invalid("cmx_kmc_create: null local clexulator");
+      if (lt->device != s->t->device) return invalid("cmx_kmc_create: local clexulator on another device");
+      if (lt->d.n_sublat != T.n_sublat || lt->d.max_occ > 8)
+        return invalid("cmx_kmc_create: local clexulator does not match the prim");
+      for (int n = 0; n < lt->d.nlist_len; ++n) {
+        const int32_t *o = &lt->nbr[4 * n];
+        if (std::abs(o[0]) > s->g.N0 || std::abs(o[1]) > s->g.N1 || std::abs(o[2]) > s->g.N2)
+          return invalid("cmx_kmc_create: supercell smaller than the local neighborhood");
+      }
+      for (int q = 0; q < Y.n_kra; ++q)
+        if (Y.kra_index[q] >= (uint32_t)lt->d.corr_size) return invalid("cmx_kmc_create: kra index out of range");
+      for (int q = 0; q < Y.n_freq; ++q)
+        if (Y.freq_index[q] >= (uint32_t)lt->d.corr_size) return invalid("cmx_kmc_create: freq index out of range");
+      tabs.push_back(lt->d);
+    }
+    d.kra_beg = (int32_t)cidx.size();
+    cidx.insert(cidx.end(), Y.kra_index, Y.kra_index + Y.n_kra);
+    cval.insert(cval.end(), Y.kra_value, Y.kra_value + Y.n_kra);
+    d.kra_end = d.freq_beg = (int32_t)cidx.size();
+    cidx.insert(cidx.end(), Y.freq_index, Y.freq_index + Y.n_freq);
+    cval.insert(cval.end(), Y.freq_value, Y.freq_value + Y.n_freq);
+    d.freq_end = (int32_t)cidx.size();
+    dtypes.push_back(d);
+  }
+  if (s->g.halo) return invalid("cmx_kmc_create: slab states are not supported");
+  for (int p = 0; p < n_prim; ++p) {
+    const cmx_prim_event &E = prim[p];
+    if (E.n_sites < 1 || E.n_sites > CMX_EVENT_MAX_SITES) return invalid("cmx_kmc_create: bad number of event sites");
+    if (E.event_type < 0 || E.event_type >= n_types) return invalid("cmx_kmc_create: event type out of range");
+    if (E.equivalent_index < 0 || E.equivalent_index >= types[E.event_type].n_equivalents)
+      return invalid("cmx_kmc_create: equivalent index out of range");
+    for (int q = 0; q < E.n_sites; ++q) {
+      int b = E.site[q][0];
+      if (b < 0 || b >= T.n_sublat) return invalid("cmx_kmc_create: event sublattice out of range");
+      if (std::abs(E.site[q][1]) > s->g.N0 || std::abs(E.site[q][2]) > s->g.N1 || std::abs(E.site[q][3]) > s->g.N2)
+        return invalid("cmx_kmc_create: supercell smaller than the event");
+      if (E.occ_init[q] < 0 || E.occ_init[q] >= s->t->n_occ[b] || E.occ_final[q] < 0 ||
+          E.occ_final[q] >= s->t->n_occ[b])
+        return invalid("cmx_kmc_create: event occupant index out of range");
+    }
+  }
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  cmx_kmc *k = new cmx_kmc;
+  k->s = s;
+  k->n_types = n_types;
+  k->n_prim = n_prim;
+  k->prim.assign(prim, prim + n_prim);
+  k->types = dtypes;
+  int rc;
+  if ((rc = kmc_to_device(k->prim, &k->d_prim)) || (rc = kmc_to_device(dtypes, &k->d_types)) ||
+      (rc = kmc_to_device(tabs, &k->d_tables)) || (rc = kmc_to_device(cidx, &k->d_coef_idx)) ||
+      (rc = kmc_to_device(cval, &k->d_coef_val))) {
+    cmx_kmc_destroy(k);
+    return rc;
+  }
+  *out = k;
+  return CMX_OK;
+}
+
+static int kmc_args(cmx_kmc *k, KmcArgs &a, const char *who) {
+  cmx_state *s = k->s;
+  for (int r = 0; r < s->n_replicas; ++r)
+    if (!(s->temperature[r] > 0.0)) {
+      cmx_set_error(std::string(who) + ": temperature not set for every replica");
+      return CMX_ERR_STATE;
+    }
+  a.T = s->t->d;
+  a.g = s->g;
+  a.occ = s->d_occ;
+  a.n_eci = s->n_eci;
+  a.eci_idx = s->d_eci_idx;
+  a.eci_val = s->d_eci_val;
+  a.beta = s->d_beta;
+  a.prim = k->d_prim;
+  a.types = k->d_types;
+  a.local = k->d_tables;
+  a.coef_idx = k->d_coef_idx;
+  a.coef_val = k->d_coef_val;
+  return CMX_OK;
+}
+
+extern "C" int cmx_kmc_event_states(cmx_kmc *k, int64_t n, const int32_t *replica,
+                                    const int64_t *unitcell, const int32_t *prim_event,
+                                    cmx_event_state *out) {
+  if (!k) return invalid("cmx_kmc_event_states: null handle");
+  if (n < 0 || (n && (!replica || !unitcell || !prim_event || !out)))
+    return invalid("cmx_kmc_event_states: bad argument");
+  if (n == 0) return CMX_OK;
+  cmx_state *s = k->s;
+  for (int64_t q = 0; q < n; ++q) {
+    if (replica[q] < 0 || replica[q] >= s->n_replicas)
+      return invalid("cmx_kmc_event_states: replica out of range");
+    if (unitcell[q] < 0 || unitcell[q] >= s->g.n_cells)
+      return invalid("cmx_kmc_event_states: unit cell index out of range");
+    if (prim_event[q] < 0 || prim_event[q] >= k->n_prim)
+      return invalid("cmx_kmc_event_states: prim event index out of range");
+  }
+  KmcArgs a;
+  int rc = kmc_args(k, a, "cmx_kmc_event_states");
+  if (rc) return rc;
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  size_t b_r = sizeof(int32_t) * n, b_c = sizeof(int64_t) * n, b_o = sizeof(cmx_event_state) * n;
+  size_t off_c = (b_r + 255) & ~(size_t)255;
+  size_t off_p = (off_c + b_c + 255) & ~(size_t)255;
+  size_t off_o = (off_p + b_r + 255) & ~(size_t)255;
+  rc = cmx_scratch(s, off_o + b_o);
+  if (rc) return rc;
+  char *base = static_cast<char *>(s->d_scratch);
+  CMX_CUDA(cudaMemcpyAsync(base, replica, b_r, cudaMemcpyHostToDevice, s->stream));
+  CMX_CUDA(cudaMemcpyAsync(base + off_c, unitcell, b_c, cudaMemcpyHostToDevice, s->stream));
+  CMX_CUDA(cudaMemcpyAsync(base + off_p, prim_event, b_r, cudaMemcpyHostToDevice, s->stream));
+  k_kmc_event_states<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
+      a, n, (const int32_t *)base, (const int64_t *)(base + off_c), (const int32_t *)(base + off_p),
+      (cmx_event_state *)(base + off_o));
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaMemcpyAsync(out, base + off_o, b_o, cudaMemcpyDeviceToHost, s->stream));
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  return CMX_OK;
+}
+
+extern "C" int cmx_kmc_all_rates(cmx_kmc *k, double *rates, double *total, void **d_rates) {
+  if (!k) return invalid("cmx_kmc_all_rates: null handle");
+  cmx_state *s = k->s;
+  KmcArgs a;
+  int rc = kmc_args(k, a, "cmx_kmc_all_rates");
+  if (rc) return rc;
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  int64_t per = s->g.n_cells * k->n_prim, tot = per * s->n_replicas;
+  if (!k->d_rates) {
+    CMX_CUDA(cudaMalloc((void **)&k->d_rates, sizeof(double) * tot));
+    CMX_CUDA(cudaMalloc((void **)&k->d_total, sizeof(double) * s->n_replicas));
+  }
+  int64_t nb = std::min<int64_t>((tot + 127) / 128, 148 * 16);
+  k_kmc_all_rates<<<(unsigned)nb, 128, 0, s->stream>>>(a, k->n_prim, tot, k->d_rates);
+  CMX_CUDA(cudaGetLastError());
+  if (total) {
+    int nbs = (int)std::min<int64_t>((per + 255) / 256, 64);
+    rc = cmx_scratch(s, sizeof(double) * (size_t)nbs * s->n_replicas);
+    if (rc) return rc;
+    dim3 grid(nbs, s->n_replicas);
+    k_kmc_sum<<<grid, 256, 0, s->stream>>>(k->d_rates, per, (double *)s->d_scratch);
+    k_kmc_sum2<<<s->n_replicas, 32, 0, s->stream>>>((const double *)s->d_scratch, nbs, k->d_total);
+    CMX_CUDA(cudaGetLastError());
+    CMX_CUDA(cudaMemcpyAsync(total, k->d_total, sizeof(double) * s->n_replicas,
+                             cudaMemcpyDeviceToHost, s->stream));
+  }
+  if (rates)
+    CMX_CUDA(cudaMemcpyAsync(rates, k->d_rates, sizeof(double) * tot, cudaMemcpyDeviceToHost, s->stream));
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  if (d_rates) *d_rates = k->d_rates;
+  return CMX_OK;
+}

@@ -1,0 +1,85 @@
+"""Host-side mirror of the reference's KMC event bookkeeping that feeds the device
+event-state kernel (csrc/cmx_kmc.cu).  Names follow the reference:
+
+  PrimEventData / make_prim_event_list   src/casm/clexmonte/events/event_methods.cc:80-133
+  EventState                             include/casm/clexmonte/events/event_data.hh:19-30
+  EventStateCalculator                   src/casm/clexmonte/monte_calculator/BaseMonteEventData.cc:27-156
+
+Only what the rate recompute needs is here; event lists, impact tables and the
+selector stay with the reference's host code.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from .clexulator_tables import read_eci
+
+
+def make_prim_event_list(event_type_data: Sequence[dict]) -> List[dict]:
+    """Linear list of the events associated with the origin unit cell.
+
+    `event_type_data[y]["events"]` lists the equivalent events of type y, each a
+    dict {sites: [(b,i,j,k)...], occ_init: [...], occ_final: [...]}, in the order
+    of the local basis set's equivalents.  As in append_to_prim_event_list
+    (event_methods.cc:80-120) every equivalent contributes its forward event and,
+    when it differs, the reverse event right after it; both share the
+    equivalent_index (the same local clexulator describes the hop in both
+    directions)."""
+    out = []
+    for y, et in enumerate(event_type_data):
+        for eq, ev in enumerate(et["events"]):
+            fwd = dict(event_type=y, event_type_name=et.get("name", str(y)), equivalent_index=eq,
+                       is_forward=True, prim_event_index=len(out), sites=[tuple(s) for s in ev["sites"]],
+                       occ_init=list(ev["occ_init"]), occ_final=list(ev["occ_final"]))
+            out.append(fwd)
+            if list(ev["occ_init"]) != list(ev["occ_final"]):
+                rev = dict(fwd, is_forward=False, prim_event_index=len(out), occ_init=list(ev["occ_final"]),
+                           occ_final=list(ev["occ_init"]))
+                out.append(rev)
+    return out
+
+
+def read_event_type(event_json, equivalents_info_json, kra_eci, freq_eci, name: str = "") -> dict:
+    """Event type data from the reference's input files (system.json "kmc_events"
+    + "local_basis_sets", parsed at system/io/json/System_json_io.cc:88-250,546-602):
+    the prototype event's occupation (event.json "occupation"/"index") placed on
+    the phenomenal cluster of every equivalent (equivalents_info.json
+    "equivalents"[k]/"phenomenal"/"sites", listed in the site order of the
+    transformed event), plus the kra / freq coefficients (dense or sparse form)."""
+    def load(x):
+        return json.loads(Path(x).read_text()) if isinstance(x, (str, Path)) else x
+    ev = load(event_json)
+    info = load(equivalents_info_json)
+    occ_init = [int(x) for x in ev["occupation"]["index"]["initial"]]
+    occ_final = [int(x) for x in ev["occupation"]["index"]["final"]]
+    events = []
+    for eq in info["equivalents"]:
+        sites = [tuple(int(c) for c in s) for s in eq["phenomenal"]["sites"]]
+        if len(sites) != len(occ_init):
+            raise ValueError("event and local basis set have different phenomenal clusters")
+        events.append(dict(sites=sites, occ_init=occ_init, occ_final=occ_final))
+    ki, kv = read_eci(load(kra_eci))
+    fi, fv = read_eci(load(freq_eci))
+    return dict(name=name, events=events, kra=(ki, kv), freq=(fi, fv))
+
+
+def event_linear_site_index(N: Sequence[int], unitcell_index: int, sites: Sequence[Sequence[int]]) -> List[int]:
+    """set_event_linear_site_index (event_methods.cc:141-155) without a
+    SuperNeighborList: l = b*n_cells + cell of (unit cell + site offset), periodic."""
+    N0, N1, N2 = (int(x) for x in N)
+    n_cells = N0 * N1 * N2
+    i, j, k = unitcell_index % N0, (unitcell_index // N0) % N1, unitcell_index // (N0 * N1)
+    return [int(b * n_cells + ((i + di) % N0) + N0 * (((j + dj) % N1) + N1 * ((k + dk) % N2)))
+            for b, di, dj, dk in sites]
+
+
+def complete_event_list(n_cells: int, n_prim_events: int):
+    """(unitcell_index, prim_event_index) of every event, unit cell major -- the
+    order of the CompleteEventList (events/CompleteEventList.cc:10-91)."""
+    uc = np.repeat(np.arange(n_cells, dtype=np.int64), n_prim_events)
+    pe = np.tile(np.arange(n_prim_events, dtype=np.int32), n_cells)
+    return uc, pe

@@ -253,6 +253,72 @@ int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t mode,
                               cmx_step_record *log, int64_t log_cap,
                               int64_t *n_accept, uint64_t *hash);
 
+/* -------------------------------------------------------------------------
+ * Kinetic Monte Carlo: event-state / event-rate evaluation (reference rows
+ * a11/a12).  Replaces EventStateCalculator::calculate_event_state +
+ * _default_event_state_calculation
+ * (src/casm/clexmonte/monte_calculator/BaseMonteEventData.cc:87-156), batched
+ * over (trajectory, unit cell, prim event) triples -- the unit of work of
+ * lotto's update_impacted_event_rates (events/lotto/rejection_free.hpp:322-330)
+ * -- and over many independent trajectories (= replicas of the state).
+ * ------------------------------------------------------------------------- */
+#define CMX_EVENT_MAX_SITES 4
+
+/* PrimEventData (include/casm/clexmonte/events/event_data.hh:47-72): one event
+ * of the origin unit cell.  site[q] = (b, i, j, k) as xtal::UnitCellCoord. */
+typedef struct cmx_prim_event {
+  int32_t n_sites;
+  int32_t site[CMX_EVENT_MAX_SITES][4];
+  int32_t occ_init[CMX_EVENT_MAX_SITES];
+  int32_t occ_final[CMX_EVENT_MAX_SITES];
+  int32_t event_type;       /* index into the event types below              */
+  int32_t equivalent_index; /* which equivalent local clexulator to use      */
+} cmx_prim_event;
+
+/* One event type: its local multi-cluster-expansion (LocalMultiClexData with the
+ * "kra" and "freq" coefficients, BaseMonteEventData.cc:36-61) over one local
+ * clexulator per equivalent (system/io/json/System_json_io.cc:546-602). */
+typedef struct cmx_event_type {
+  int32_t n_equivalents;
+  const cmx_tables *const *local_tables; /* [n_equivalents], same device     */
+  int32_t n_kra;
+  const uint32_t *kra_index;
+  const double *kra_value;
+  int32_t n_freq;
+  const uint32_t *freq_index;
+  const double *freq_value;
+} cmx_event_type;
+
+/* EventState (events/event_data.hh:19-30) without the two pointers. */
+typedef struct cmx_event_state {
+  int32_t is_allowed;
+  int32_t is_normal;
+  double dE_final;
+  double Ekra;
+  double dE_activated;
+  double freq;
+  double rate;
+} cmx_event_state;
+
+typedef struct cmx_kmc cmx_kmc;
+
+/* The state's bound ECI are the "formation_energy" cluster expansion; the
+ * temperature of each replica (cmx_state_set_conditions) gives beta. */
+int cmx_kmc_create(cmx_state *s, int32_t n_event_types, const cmx_event_type *types,
+                   int32_t n_prim_events, const cmx_prim_event *prim_events,
+                   cmx_kmc **out);
+void cmx_kmc_destroy(cmx_kmc *k);
+/* Event states of `n` (replica, unit cell, prim event) triples.  out[n]. */
+int cmx_kmc_event_states(cmx_kmc *k, int64_t n, const int32_t *replica,
+                         const int64_t *unitcell, const int32_t *prim_event,
+                         cmx_event_state *out);
+/* Rates of EVERY event of every replica -- what the event selector computes
+ * once at construction (lotto/rejection_free.hpp:231-234):
+ * rates[replica][unitcell][prim_event] (host, may be NULL) and the per-replica
+ * total rate total[n_replicas] (may be NULL).  The rates stay on the device
+ * (d_rates) for the caller's selector. */
+int cmx_kmc_all_rates(cmx_kmc *k, double *rates, double *total, void **d_rates);
+
 /* Test hook: replay `n` draws of the device-side restatement of
  * std::mt19937_64(seed) + libstdc++ distributions (kind 0 = raw 64-bit,
  * 1 = uniform_int_distribution<long>(0,int_max), 2 =

@@ -266,3 +266,45 @@ def rng_stream(seed: int, kinds, int_max=None, real_max=None):
     oraw = np.zeros(n, dtype=np.uint64)
     lib().orc_rng_stream(int(seed), n, _p(int_max), _p(real_max), _p(kinds), _p(oi), _p(orl), _p(oraw))
     return oi, orl, oraw
+
+
+def event_state(sc_formation: "RefSupercell", sc_local: "RefSupercell", occ, unitcell_index: int,
+                linear_site_index, occ_init, occ_final, eci_idx, eci_val, kra, freq,
+                temperature: float) -> dict:
+    """EventStateCalculator::calculate_event_state + _default_event_state_calculation
+    (src/casm/clexmonte/monte_calculator/BaseMonteEventData.cc:87-156) restated on
+    top of the reference's generated kernels:
+      is_allowed   event_is_allowed (events/event_methods.cc:340-351)
+      dE_final     coefficients . Correlations::occ_delta(sites, occ_final)   :135-139
+      local_corr   LocalCorrelations::local(unitcell_index, equivalent_index) :143-144
+                   = calc_global_corr_contribution of the equivalent's local clexulator
+      Ekra, freq   sparse dot products with the local correlations            :145-149
+      dE_activated dE_final*0.5 + Ekra, is_normal, the two clamps             :152-156
+      rate         freq * exp(-beta * dE_activated), beta = 1/(KB T)          :158
+    `sc_local` is the supercell of the local clexulator of the event's equivalent."""
+    occ = np.ascontiguousarray(occ, dtype=np.int32)
+    st = dict(is_allowed=True, is_normal=False, dE_final=0.0, Ekra=0.0, dE_activated=0.0, freq=0.0, rate=0.0)
+    for l, o in zip(linear_site_index, occ_init):
+        if int(occ[l]) != int(o):
+            st["is_allowed"] = False
+            return st
+    st["dE_final"] = sc_formation.occ_delta_value(occ, list(linear_site_index), list(occ_final), eci_idx, eci_val)
+    local_corr = sc_local.cell_corr(occ, int(unitcell_index))
+    ekra = 0.0
+    for i, v in zip(*kra):
+        ekra = ekra + float(v) * float(local_corr[int(i)])
+    fr = 0.0
+    for i, v in zip(*freq):
+        fr = fr + float(v) * float(local_corr[int(i)])
+    st["Ekra"], st["freq"] = ekra, fr
+    dEa = st["dE_final"] * 0.5 + ekra
+    st["is_normal"] = (dEa > 0.0) and (dEa > st["dE_final"])
+    if dEa < st["dE_final"]:
+        dEa = st["dE_final"]
+    if dEa < 0.0:
+        dEa = 0.0
+    st["dE_activated"] = dEa
+    beta = 1.0 / (KB * temperature)
+    st["rate"] = fr * float(np.exp(-beta * dEa))
+    st["local_corr"] = local_corr
+    return st

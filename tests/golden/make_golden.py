@@ -26,6 +26,7 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 from casmcode_clexmonte_b200.clexulator_tables import parse_clexulator_source, read_eci  # noqa: E402
+from casmcode_clexmonte_b200 import kmc as K  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 REF = Path("/root/reference")
@@ -88,6 +89,130 @@ def systems():
             eci=dict(index=zro_idx.tolist(), value=zro_val.tolist()),
         ),
     }
+
+
+def kmc_system():
+    """The FCC A-B-Va KMC system of the reference's tests (kmc_system.json /
+    KMCTestSystem.cc:17-53): two event types (A-Va and B-Va nearest-neighbour
+    hops), six equivalents each, dense kra/freq coefficients."""
+    F = DATA / "FCC_binary_vacancy"
+    types = []
+    for ev in ("A_Va_1NN", "B_Va_1NN"):
+        et = K.read_event_type(F / f"kmc_events/event.{ev}/event.json",
+                               F / f"basis_sets/bset.{ev}/equivalents_info.json",
+                               F / f"kmc_events/event.{ev}/kra_eci.json",
+                               F / f"kmc_events/event.{ev}/freq_eci.json", name=ev)
+        ski, skv = read_eci(F / f"kmc_events/event.{ev}/kra_sparse_eci.json")
+        sfi, sfv = read_eci(F / f"kmc_events/event.{ev}/freq_sparse_eci.json")
+        types.append(dict(name=ev, local_tables=[f"fcc_{ev}_{k}" for k in range(6)],
+                          events=[dict(sites=[list(x) for x in e["sites"]], occ_init=e["occ_init"],
+                                       occ_final=e["occ_final"]) for e in et["events"]],
+                          kra=dict(index=et["kra"][0].tolist(), value=et["kra"][1].tolist()),
+                          freq=dict(index=et["freq"][0].tolist(), value=et["freq"][1].tolist()),
+                          kra_sparse=dict(index=ski.tolist(), value=skv.tolist()),
+                          freq_sparse=dict(index=sfi.tolist(), value=sfv.tolist())))
+    return dict(event_types=types)
+
+
+def kmc_vectors(S, seed=13):
+    """Event states from the oracle (reference kernels + the restated
+    _default_event_state_calculation): (1) the configuration reproducing the
+    event state documented in python/libcasm/clexmonte/_MonteCalculator.py:186-210,
+    found by enumerating the occupations compatible with the documented
+    local_corr; (2) a random A-B-Va configuration, every prim event at random
+    unit cells."""
+    import itertools
+    sysd = S["fcc"]
+    types = sysd["kmc"]["event_types"]
+    prim = K.make_prim_event_list(types)
+    assert len(prim) == 24
+    out = {}
+    N = 8
+    n = N ** 3
+    form = O.RefClexulator("fcc_default").supercell(N)
+    local = {(y, k): O.RefClexulator(types[y]["local_tables"][k]).supercell(N)
+             for y in range(2) for k in range(6)}
+
+    def site(c):
+        return int(c[0] % N + N * (c[1] % N + N * (c[2] % N)))
+
+    # ---- (1) documented event state: B_Va_1NN, equivalent 2, reverse, prim event 17
+    pe = prim[17]
+    assert (pe["event_type_name"], pe["equivalent_index"], pe["is_forward"]) == ("B_Va_1NN", 2, False)
+    assert pe["occ_init"] == [2, 1] and pe["occ_final"] == [1, 2]
+    X = np.array([3, 3, 3])
+    uc = site(X)
+    ls = K.event_linear_site_index((N, N, N), uc, pe["sites"])
+    eci2 = sysd["eci_2"]
+    g1 = [(0, -1, 1), (0, 2, -2)]
+    g3 = [(-1, 0, 0), (1, 0, 0), (-1, 1, -1), (1, 1, -1)]
+    g5 = [(-1, 1, 0), (0, 0, -1), (0, 1, 0), (1, 0, -1)]
+    g7 = [(-1, 0, 1), (0, -1, 0), (0, 0, 1), (1, -1, 0), (-1, 2, -1), (0, 1, -2), (0, 2, -1), (1, 1, -2)]
+    doc = dict(Ekra=0.7375, dE_activated=1.6666666666666665, dE_final=1.6666666666666665,
+               freq=1e13, rate=1000704.0785393054, is_normal=False,
+               local_corr=[1.0, 0.5, 0.0, 0.5, 0.0, 0.25, 0.0, 0.5, 0.0])
+    kat = None
+    for a, b, c, d in itertools.product(itertools.combinations(g1, 1), itertools.combinations(g3, 2),
+                                        itertools.combinations(g5, 1), itertools.combinations(g7, 4)):
+        occ = np.zeros(n, dtype=np.int32)
+        occ[ls[0]], occ[ls[1]] = 2, 1
+        for s_ in a + b + c + d:
+            occ[site(X + np.array(s_))] = 1
+        st = O.event_state(form, local[(1, 2)], occ, uc, ls, pe["occ_init"], pe["occ_final"],
+                           eci2["index"], eci2["value"],
+                           (types[1]["kra"]["index"], types[1]["kra"]["value"]),
+                           (types[1]["freq"]["index"], types[1]["freq"]["value"]), 1200.0)
+        if all(st[k] == doc[k] for k in ("Ekra", "dE_activated", "dE_final", "freq", "rate", "is_normal")) \
+                and (st["local_corr"] == np.array(doc["local_corr"])).all():
+            kat = occ
+            break
+    assert kat is not None, "no configuration reproduces the documented event state"
+    out["kat_N"] = np.array([N, N, N])
+    out["kat_occ"] = kat.astype(np.int8)
+    out["kat_unitcell"] = np.array(uc)
+    out["kat_prim_event"] = np.array(17)
+    out["kat_T"] = np.array(1200.0)
+    for k in ("Ekra", "dE_activated", "dE_final", "freq", "rate"):
+        out[f"kat_{k}"] = np.array(doc[k])
+    # ---- (2) random configurations (A/B/Va = 60/25/15 %): the dense ECI of the
+    # unit tests, and the larger ECI of formation_energy_eci.2.json, which make
+    # many events "abnormal" (both clamps of BaseMonteEventData.cc:154-155 fire)
+    rng = np.random.default_rng(seed)
+    for key, eci, T in (("rand", sysd["eci_dense"], 900.0), ("rand2", sysd["eci_2"], 1200.0)):
+        occ = rng.choice(3, size=n, p=[0.6, 0.25, 0.15]).astype(np.int32)
+        ucs, pes, rows = [], [], []
+        for p_ in range(24):
+            pe = prim[p_]
+            y, k = pe["event_type"], pe["equivalent_index"]
+            # unit cells where the event is allowed, plus a few where it is not
+            allowed = [c_ for c_ in range(n)
+                       if all(occ[l] == o for l, o in zip(K.event_linear_site_index((N, N, N), c_, pe["sites"]),
+                                                          pe["occ_init"]))]
+            cells = list(rng.choice(allowed, size=min(30, len(allowed)), replace=False)) + \
+                list(rng.integers(0, n, 6))
+            for c_ in cells:
+                ls = K.event_linear_site_index((N, N, N), int(c_), pe["sites"])
+                st = O.event_state(form, local[(y, k)], occ, int(c_), ls, pe["occ_init"], pe["occ_final"],
+                                   eci["index"], eci["value"],
+                                   (types[y]["kra"]["index"], types[y]["kra"]["value"]),
+                                   (types[y]["freq"]["index"], types[y]["freq"]["value"]), T)
+                ucs.append(int(c_))
+                pes.append(p_)
+                rows.append([float(st["is_allowed"]), float(st["is_normal"]), st["dE_final"], st["Ekra"],
+                             st["dE_activated"], st["freq"], st["rate"]])
+        rows = np.array(rows)
+        out[f"{key}_N"] = np.array([N, N, N])
+        out[f"{key}_occ"] = occ.astype(np.int8)
+        out[f"{key}_T"] = np.array(T)
+        out[f"{key}_eci_index"] = np.array(eci["index"], dtype=np.uint32)
+        out[f"{key}_eci_value"] = np.array(eci["value"], dtype=np.float64)
+        out[f"{key}_unitcell"] = np.array(ucs, dtype=np.int64)
+        out[f"{key}_prim_event"] = np.array(pes, dtype=np.int32)
+        out[f"{key}_states"] = rows
+        print("kmc", key, ": allowed", int(rows[:, 0].sum()), "of", len(rows), "normal", int(rows[:, 1].sum()),
+              "clamped to dE_final", int(((rows[:, 4] == rows[:, 2]) & (rows[:, 0] > 0)).sum()),
+              "clamped to 0", int(((rows[:, 4] == 0) & (rows[:, 0] > 0)).sum()))
+    np.savez_compressed(OUT / "vectors_kmc.npz", **out)
 
 
 def random_occ(rng, n_cells, n_sublat, mutable, nocc):
@@ -213,7 +338,9 @@ def main():
         t = parse_clexulator_source(src, name=name)
         t.save(OUT / "tables" / f"{name}.npz")
     S = systems()
+    S["fcc"]["kmc"] = kmc_system()
     (OUT / "systems.json").write_text(json.dumps(S, indent=1))
+    kmc_vectors(S)
     vectors("fcc_sparse", S["fcc"], 6, S["fcc"]["eci_sparse"])
     vectors("fcc_full", S["fcc"], 6, S["fcc"]["eci_full"], seed=8)
     vectors("zro", S["zro"], 8, S["zro"]["eci"], n_events=32, traj_steps=5000, seed=9)
