@@ -693,3 +693,29 @@ def read_eci(data, corr_size: Optional[int] = None) -> Tuple[np.ndarray, np.ndar
     if corr_size is not None and idx and max(idx) >= corr_size:
         raise ValueError(f"ECI index {max(idx)} out of range for corr_size {corr_size}")
     return np.array(idx, dtype=np.uint32), np.array(val, dtype=np.float64)
+
+
+def _main(argv=None) -> int:
+    """python -m casmcode_clexmonte_b200.clexulator_tables <Clexulator.cc> <out.npz> [eci.json]
+
+    Export the flat tables of one CASM-generated Clexulator source (and print
+    the work per single-site delta for the given coefficients)."""
+    import argparse
+    ap = argparse.ArgumentParser(description=_main.__doc__)
+    ap.add_argument("source")
+    ap.add_argument("out")
+    ap.add_argument("eci", nargs="?")
+    a = ap.parse_args(argv)
+    t = parse_clexulator_source(a.source)
+    t.save(a.out)
+    print(f"{a.out}: nlist {t.nlist_len}, corr {t.corr_size}, point corr {t.n_point_corr}, "
+          f"sublattices on the neighbor list {t.n_nlist_sublat}")
+    if a.eci:
+        idx, val = read_eci(a.eci, t.corr_size)
+        for p in range(t.n_nlist_sublat if t.n_point_corr == t.n_nlist_sublat else 0):
+            print(f"  point {p}: {t.delta_work(p, idx)}")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_main())
