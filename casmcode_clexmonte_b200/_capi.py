@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "cmx_global_corr", "cmx_energy", "cmx_composition",
     "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches",
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
+    "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
 ]
 
@@ -141,6 +142,9 @@ def lib():
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
+    L.cmx_canonical_set_swaps.argtypes = [vp, i32, vp]
+    L.cmx_canonical_sweep.argtypes = [vp, i64, u64, i64, vp]
+    L.cmx_canonical_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.cmx_kmc_create.argtypes = [vp, i32, C.POINTER(EventType), i32, C.POINTER(PrimEvent), C.POINTER(vp)]
     L.cmx_kmc_destroy.argtypes = [vp]
     L.cmx_kmc_destroy.restype = None
@@ -347,6 +351,24 @@ class State:
     def sgc_sweep_kgroup(self, seed: int, sweep: int, kgroup: int) -> None:
         """Asynchronous: enqueue one k-colour group of one sweep on the state's stream."""
         check(lib().cmx_sgc_sweep_kgroup(self._h, int(seed), int(sweep), int(kgroup)))
+
+    # -- canonical pair exchanges ----------------------------------------------
+    def canonical_set_swaps(self, swaps) -> list:
+        """swaps: iterable of (b_a, b_b, (t0, t1, t2)).  Returns [(strides, n_colours)] per type."""
+        arr = np.array([[a, b, t[0], t[1], t[2]] for a, b, t in swaps], dtype=np.int32)
+        check(lib().cmx_canonical_set_swaps(self._h, len(arr), _p(arr)))
+        out = []
+        for i in range(len(arr)):
+            S = (C.c_int32 * 3)()
+            nc = C.c_int32()
+            check(lib().cmx_canonical_info(self._h, i, S, C.byref(nc)))
+            out.append((tuple(S), nc.value))
+        return out
+
+    def canonical_sweep(self, n_sweeps: int, seed: int, first_sweep: int = 0):
+        cnt = (Counters * self.n_replicas)()
+        check(lib().cmx_canonical_sweep(self._h, int(n_sweeps), int(seed), int(first_sweep), C.byref(cnt)))
+        return cnt
 
     def set_sweep_flags(self, flags: int) -> None:
         check(lib().cmx_state_set_sweep_flags(self._h, int(flags)))

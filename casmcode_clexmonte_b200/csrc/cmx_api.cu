@@ -180,6 +180,7 @@ extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
 extern "C" void cmx_state_destroy(cmx_state *s) {
   if (!s) return;
   cudaSetDevice(s->t->device);
+  cmx_canonical_free(s);
   cmx_plan_free(s->plan);
   cudaFree(s->d_occ);
   cudaFree(s->d_eci_idx);
@@ -404,6 +405,7 @@ extern "C" int cmx_state_set_eci(cmx_state *s, int32_t n, const uint32_t *index,
     CMX_CUDA(cudaMemcpy(s->d_eci_idx, index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
     CMX_CUDA(cudaMemcpy(s->d_eci_val, value, sizeof(double) * n, cudaMemcpyHostToDevice));
   }
+  cmx_canonical_free(s);  // swap colourings depend on the active neighborhood
   return cmx_plan_sweep(s);
 }
 

@@ -72,6 +72,26 @@ struct cmx_tables {
   std::vector<double> phi, term_coef, group_div;
 };
 
+// exact division of 32-bit indices by a launch-constant divisor
+struct FastDiv {
+  uint32_t d, m;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.m = (d <= 1) ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / d);
+  return f;
+}
+__device__ __forceinline__ void fastdivmod(uint32_t n, FastDiv f, uint32_t &q,
+                                           uint32_t &r) {
+  q = __umulhi(n, f.m);
+  r = n - q * f.d;
+  if (r >= f.d) {
+    r -= f.d;
+    q += 1;
+  }
+}
+
 // ---- checkerboard sweep plan (built by cmx_plan_sweep, see cmx_sweep.cu) ----
 struct SweepPlan {
   bool valid = false;     // sweeps possible (global clexulator + ECI bound)
@@ -81,6 +101,7 @@ struct SweepPlan {
   int32_t n_colours = 0;
   int32_t range_k = 0;  // max |dk| over active neighbors (halo depth needed)
   std::vector<int32_t> mut_points;  // point positions with > 1 occupant
+  std::vector<int32_t> active_nbr;  // neighbor-list sites the bound ECI actually read
   // generic evaluator: ECI-folded, merged delta terms per point position
   int32_t n_gterms = 0;
   int32_t *d_gt_beg = nullptr;   // [n_point+1]
@@ -130,6 +151,7 @@ struct cmx_state {
   int32_t n_species = 0;
   // sweeps
   SweepPlan plan;
+  struct CanonicalPlan *canon = nullptr;  // cmx_canonical_set_swaps
   uint32_t sweep_flags = 0;            // CMX_SWEEP_* (cmx_state_set_sweep_flags)
   cmx_counters *d_counters = nullptr;  // [replica]
   int *d_flag = nullptr;               // device-side validation flag
@@ -141,6 +163,7 @@ struct cmx_state {
 
 int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
+void cmx_canonical_free(cmx_state *s);
 void cmx_plan_free(SweepPlan &p);
 
 // ---- device helpers ---------------------------------------------------------

@@ -143,24 +143,6 @@ __global__ void k_build_tab16(const double *__restrict__ lut, int nocc, int z, i
 // ---------------------------------------------------------------------------
 // pair16 sweep kernel
 // ---------------------------------------------------------------------------
-struct FastDiv {
-  uint32_t d, m;
-};
-static FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  f.d = d;
-  f.m = (d <= 1) ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / d);
-  return f;
-}
-__device__ __forceinline__ void fastdivmod(uint32_t n, FastDiv f, uint32_t &q,
-                                           uint32_t &r) {
-  q = __umulhi(n, f.m);
-  r = n - q * f.d;
-  if (r >= f.d) {
-    r -= f.d;
-    q += 1;
-  }
-}
 
 struct Pair16Args {
   int8_t *occ;  // replica 0 base (start of the low ghost layers)
@@ -700,6 +682,9 @@ int cmx_plan_sweep(cmx_state *s) {
   int R[3] = {0, 0, 0};
   std::vector<char> active(T.nlist_len, 0);
   for (int n : gt_n) active[n] = 1;
+  P.active_nbr.clear();
+  for (int n = 0; n < T.nlist_len; ++n)
+    if (active[n]) P.active_nbr.push_back(n);
   for (int n = 0; n < T.nlist_len; ++n)
     if (active[n])
       for (int a = 0; a < 3; ++a) R[a] = std::max(R[a], std::abs(t->nbr[4 * n + a]));

@@ -92,3 +92,44 @@ def semigrand_potential_per_supercell(e_clex: float, mol_comp, origin, Rt, param
             xp += Rt[p, s] * (mol_comp[s] - origin[s])
         dot += mu[p] * xp
     return e_clex - float(n_cells) * dot
+
+
+def canonical_swap_types(tables, sublat_to_asym, occ_to_species, N, n_shell: int = 12, long_range: bool = True):
+    """Swap types for `State.canonical_set_swaps`, the parallel counterpart of the
+    reference's canonical swap table (make_canonical_swaps [EXT], built at
+    src/casm/clexmonte/system/System.cc:55-58: every pair of candidates with the
+    same species allowed on both asymmetric units).
+
+    For every ordered pair of mutable sublattices on the same asymmetric unit:
+    the `n_shell` shortest translations of the prim neighbor list (one of +t/-t
+    when the sublattices are equal -- both give the same set of pairs), and, with
+    `long_range`, one long translation per pair that moves species across the
+    whole box (t_i = 2 mod 4, so a stride-4 colouring along i is conflict free
+    for any short-ranged basis)."""
+    nbr = np.asarray(tables.nbr).reshape(-1, 4)
+    n_occ = np.asarray(tables.n_occ)
+    mutable = [b for b in range(len(n_occ)) if n_occ[b] > 1]
+    swaps = []
+    for ba in mutable:
+        for bb in mutable:
+            if bb < ba or sublat_to_asym[ba] != sublat_to_asym[bb]:
+                continue
+            if not set(s for s in occ_to_species[ba] if s >= 0) & set(s for s in occ_to_species[bb] if s >= 0):
+                continue
+            seen = set()
+            count = 0
+            for di, dj, dk, b in nbr:
+                t = (int(di), int(dj), int(dk))
+                if b != bb or (t == (0, 0, 0) and ba == bb):
+                    continue
+                if ba == bb and (tuple(-x for x in t) in seen):
+                    continue
+                seen.add(t)
+                swaps.append((ba, bb, t))
+                count += 1
+                if count >= (n_shell // 2 if ba == bb else n_shell):
+                    break
+            if long_range and N[0] >= 8 and N[0] % 4 == 0:
+                t0 = (N[0] // 2) - ((N[0] // 2) % 4) + 2
+                swaps.append((ba, bb, (t0 % N[0], N[1] // 3, N[2] // 2 + 1 if N[2] > 2 else 0)))
+    return swaps

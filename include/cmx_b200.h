@@ -224,6 +224,40 @@ int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
                    int32_t *n_colours, int32_t *colour_strides /*[3]*/,
                    int32_t *range_k);
 
+/* -------------------------------------------------------------------------
+ * Canonical ensemble: parallel pair exchanges.
+ * Replaces the loop of methods/occupation_metropolis.hh:92-120 with the
+ * canonical proposal (CanonicalCalculator.cc:78-88: two unlike-species sites
+ * swap their species) and CanonicalPotential::occ_delta_per_supercell
+ * (CanonicalCalculator.cc:137-140: the two-site, sequentially evaluated
+ * delta E of the formation energy).
+ *
+ * A swap type pairs site (b_a, cell) with site (b_b, cell + t) for every unit
+ * cell.  Per type the cells are coloured so that no site of one pair is within
+ * the interaction range of (or identical to) a site of another pair of the
+ * same colour; the colours are then updated one after the other, all pairs of
+ * a colour simultaneously.  t may be a nearest-neighbour vector (Kawasaki
+ * exchange) or long (global mixing, like the reference's any-two-sites swaps).
+ * Composition is conserved exactly.  Like-species pairs are skipped and not
+ * counted as attempts (the reference never proposes them).
+ * ------------------------------------------------------------------------- */
+typedef struct cmx_swap_type {
+  int32_t b_a, b_b; /* sublattices of the two sites                         */
+  int32_t t[3];     /* unit-cell translation from site a to site b          */
+} cmx_swap_type;
+/* Needs the ECI (cmx_state_set_eci); cross-sublattice swaps need the species
+ * of the occupants (cmx_state_set_occupants).  Fails with CMX_ERR_INVALID when
+ * a type admits no valid colouring of this supercell. */
+int cmx_canonical_set_swaps(cmx_state *s, int32_t n, const cmx_swap_type *swaps);
+/* One sweep = every swap type, every colour, once: n_swap_types * n_cells pairs
+ * visited.  counters[n_replicas]: n_attempt = unlike-species pairs evaluated,
+ * n_accept, dE_sum (always accumulated here). */
+int cmx_canonical_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
+                        int64_t first_sweep, cmx_counters *counters);
+/* colour strides chosen for swap type `i` and its number of colours */
+int cmx_canonical_info(const cmx_state *s, int32_t i, int32_t *strides /*[3]*/,
+                       int32_t *n_colours);
+
 /* Kernel launches one full sweep takes with the current evaluator (the
  * pair-LUT kernel fuses both x colours of a row: 4 launches for 8 colours). */
 int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep);

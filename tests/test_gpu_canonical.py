@@ -1,0 +1,158 @@
+"""GPU tests of the canonical pair-exchange sweeps (csrc/cmx_canonical.cu)."""
+import numpy as np
+import pytest
+
+from casmcode_clexmonte_b200 import _capi
+from casmcode_clexmonte_b200.potential import canonical_swap_types
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev_tables(load_tables):
+    cache = {}
+
+    def _get(name):
+        if name not in cache:
+            cache[name] = _capi.Tables(load_tables(name))
+        return cache[name]
+
+    yield _get
+    for t in cache.values():
+        t.close()
+
+
+def _state(dev_tables, systems, case_sys, eci_key, N, T, occ, n_replicas=1):
+    sysd = systems[case_sys]
+    st = _capi.State(dev_tables(sysd["tables"]), N, n_replicas)
+    eci = sysd[eci_key]
+    st.set_eci(eci["index"], eci["value"])
+    mo = st.tables.host.max_occ
+    o2s = np.full((len(sysd["occ_to_species"]), mo), -1, dtype=np.int32)
+    for b, row in enumerate(sysd["occ_to_species"]):
+        o2s[b, :len(row)] = row
+    st.set_occupants(sysd["sublat_to_asym"], o2s, sysd["n_species"])
+    for r in range(n_replicas):
+        st.set_conditions(T, None, r)
+        st.upload_occ(occ, r)
+    swaps = canonical_swap_types(st.tables.host, sysd["sublat_to_asym"], o2s.tolist(), N)
+    return st, sysd, swaps
+
+
+@pytest.mark.parametrize("case_sys,eci_key,N", [
+    ("fcc", "eci_sparse", (16, 8, 8)),
+    ("fcc", "eci_full", (8, 8, 12)),
+    ("zro", "eci", (8, 8, 8)),
+])
+def test_canonical_sweep_conserves_composition_and_energy(dev_tables, systems, case_sys, eci_key, N):
+    """Size-independent properties: occupant counts per sublattice group are
+    conserved exactly; the accepted delta E sum to E(after) - E(before) computed
+    from scratch by the faithful global evaluation (so the two-site sequential
+    delta E and the conflict-free colourings are right); sites stay in range."""
+    rng = np.random.default_rng(2)
+    sysd = systems[case_sys]
+    n_cells = int(np.prod(N))
+    n_sub = len(sysd["occ_to_species"])
+    occ = np.zeros(n_cells * n_sub, dtype=np.int32)
+    for b in sysd["mutable_sublats"]:
+        nocc = sum(1 for s in sysd["occ_to_species"][b] if s >= 0)
+        occ[b * n_cells:(b + 1) * n_cells] = rng.integers(0, nocc, n_cells)
+    st, sysd, swaps = _state(dev_tables, systems, case_sys, eci_key, N, 1000.0, occ)
+    info = st.canonical_set_swaps(swaps)
+    assert len(info) == len(swaps) and all(nc >= 4 for _, nc in info)
+    e0 = st.energy()
+    c0 = st.composition()
+    cnt = st.canonical_sweep(4, seed=5)
+    e1 = st.energy()
+    c1 = st.composition()
+    # species counts: sum over the sublattices of one asymmetric unit
+    def species_counts(c):
+        out = np.zeros(sysd["n_species"], dtype=np.int64)
+        for b, row in enumerate(sysd["occ_to_species"]):
+            for o, sp in enumerate(row):
+                if sp >= 0:
+                    out[sp] += c[b, o]
+        return out
+    assert (species_counts(c0) == species_counts(c1)).all()
+    assert 0 < cnt[0].n_accept < cnt[0].n_attempt <= 4 * len(swaps) * n_cells
+    assert cnt[0].dE_sum == pytest.approx(e1 - e0, rel=1e-9, abs=1e-7)
+    new = st.download_occ()
+    assert (new != occ).any()
+    for b in range(n_sub):
+        nocc = sum(1 for s in sysd["occ_to_species"][b] if s >= 0)
+        seg = new[b * n_cells:(b + 1) * n_cells]
+        assert seg.min() >= 0 and seg.max() < nocc
+    # deterministic: same seed, same trajectory; continuing the stream == one call
+    st2, _, _ = _state(dev_tables, systems, case_sys, eci_key, N, 1000.0, occ)
+    st2.canonical_set_swaps(swaps)
+    st2.canonical_sweep(3, seed=5)
+    st2.canonical_sweep(1, seed=5, first_sweep=3)
+    assert (st2.download_occ() == new).all()
+    st.close()
+    st2.close()
+
+
+def test_canonical_colourings_are_conflict_free(dev_tables, systems):
+    """A long translation with t_i = 2 mod 4 needs only the stride-4 colouring;
+    nearest-neighbour exchanges need a stride > range + |t| along the hop."""
+    occ = np.zeros(16 * 8 * 8, dtype=np.int32)
+    st, sysd, _ = _state(dev_tables, systems, "fcc", "eci_sparse", (16, 8, 8), 800.0, occ)
+    info = st.canonical_set_swaps([(0, 0, (1, 0, 0)), (0, 0, (10, 3, 5)), (0, 0, (0, 1, -1))])
+    (S0, n0), (S1, n1), (S2, n2) = info
+    assert S0[0] >= 3 and n1 <= 16
+    with pytest.raises(_capi.CmxError):
+        st.canonical_set_swaps([(0, 0, (0, 0, 0))])
+    with pytest.raises(_capi.CmxError):
+        st.canonical_set_swaps([(0, 3, (1, 0, 0))])
+    st.close()
+
+
+def test_canonical_matches_sequential_thermodynamics(dev_tables, systems, oracle):
+    """north_star (3) for the canonical ensemble: averages of the parallel pair
+    exchanges agree with the reference's sequential any-two-sites swaps
+    (oracle: propose_canonical_event restated, reference kernels) within 3 sigma."""
+    if oracle is None:
+        pytest.skip("oracle/_ref not built")
+    sysd = systems["fcc"]
+    eci = sysd["eci_sparse"]
+    N = 8
+    n_cells = N ** 3
+    T = 1200.0
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=3, Rt=np.array(sysd["axes"]["Rt"]), origin=np.array(sysd["axes"]["origin"]))
+    sc = oracle.RefClexulator("fcc_default").supercell(N)
+    n_runs = 8
+    base = np.array([0] * (n_cells // 2) + [1] * (n_cells // 4) + [2] * (n_cells - n_cells // 2 - n_cells // 4),
+                    dtype=np.int32)
+    ref_e = []
+    inits = []
+    for run in range(n_runs):
+        occ = np.random.default_rng(100 + run).permutation(base).astype(np.int32)
+        inits.append(occ.copy())
+        out = sc.metropolis_run(1, occ, prim, eci["index"], eci["value"], T, seed=1000 + run,
+                                n_steps=60 * n_cells)
+        occ = out["occ"]
+        es = []
+        for k in range(30):
+            out = sc.metropolis_run(1, occ, prim, eci["index"], eci["value"], T, seed=5000 + 97 * run + k,
+                                    n_steps=4 * n_cells)
+            occ = out["occ"]
+            g = sc.global_corr(occ)
+            es.append(float(np.dot(eci["value"], g[eci["index"]])) / n_cells)
+        ref_e.append(np.mean(es))
+    st, _, swaps = _state(dev_tables, systems, "fcc", "eci_sparse", (N, N, N), T, inits[0], n_replicas=n_runs)
+    for r in range(n_runs):
+        st.upload_occ(inits[r], r)
+    st.canonical_set_swaps(swaps)
+    st.canonical_sweep(40, seed=21)
+    ge = np.zeros((n_runs, 30))
+    for k in range(30):
+        st.canonical_sweep(3, seed=21, first_sweep=40 + 3 * k)
+        for r in range(n_runs):
+            ge[r, k] = st.energy(r) / n_cells
+    for r in range(n_runs):
+        assert (np.bincount(st.download_occ(r), minlength=3) == np.bincount(base, minlength=3)).all()
+    gpu_e = ge.mean(axis=1)
+    se = np.hypot(np.std(ref_e, ddof=1), np.std(gpu_e, ddof=1)) / np.sqrt(n_runs)
+    assert abs(np.mean(ref_e) - np.mean(gpu_e)) < 3 * se + 1e-4, (np.mean(ref_e), np.mean(gpu_e), se)
+    st.close()
