@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_upload_occ", "cmx_state_download_occ",
     "cmx_state_upload_occ_i8", "cmx_state_download_occ_i8",
     "cmx_state_randomize", "cmx_state_set_k_offset", "cmx_state_stream", "cmx_state_device_ptr",
+    "cmx_state_ipc_export", "cmx_state_ipc_attach", "cmx_state_p2p_active",
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
@@ -122,6 +123,9 @@ def lib():
     L.cmx_state_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.cmx_state_stream.argtypes = [vp, C.POINTER(vp)]
     L.cmx_state_set_eci.argtypes = [vp, i32, vp, vp]
+    L.cmx_state_ipc_export.argtypes = [vp, vp]
+    L.cmx_state_ipc_attach.argtypes = [vp, vp, vp]
+    L.cmx_state_p2p_active.argtypes = [vp, C.POINTER(i32)]
     L.cmx_state_set_conditions.argtypes = [vp, i32, dbl, vp]
     L.cmx_state_set_occupants.argtypes = [vp, vp, vp, i32]
     L.cmx_delta_corr.argtypes = [vp, i32, i64, vp, vp, vp]
@@ -272,6 +276,22 @@ class State:
         return p.value, n.value
 
     # -- model --------------------------------------------------------------
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().cmx_state_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_attach(self, handle_dn: Optional[bytes], handle_up: Optional[bytes]) -> None:
+        """Handles of the lower / upper ring neighbour (None: this state itself)."""
+        dn = C.create_string_buffer(handle_dn, 128) if handle_dn is not None else None
+        up = C.create_string_buffer(handle_up, 128) if handle_up is not None else None
+        check(lib().cmx_state_ipc_attach(self._h, dn, up))
+
+    def p2p_active(self) -> bool:
+        v = C.c_int32()
+        check(lib().cmx_state_p2p_active(self._h, C.byref(v)))
+        return bool(v.value)
+
     def set_eci(self, index, value) -> None:
         index = np.ascontiguousarray(index, dtype=np.uint32)
         value = np.ascontiguousarray(value, dtype=np.float64)

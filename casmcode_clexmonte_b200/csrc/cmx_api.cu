@@ -165,6 +165,8 @@ extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
   cudaMemset(s->d_beta, 0, sizeof(double) * n_replicas);
   cudaMemset(s->d_exch, 0, sizeof(double) * ex * n_replicas);
   cudaMalloc(&s->d_flag, sizeof(int));
+  cudaMalloc((void **)&s->d_sig, sizeof(unsigned long long) * 4);
+  cudaMemset(s->d_sig, 0, sizeof(unsigned long long) * 4);
   cudaMalloc(&s->d_counters, sizeof(cmx_counters) * n_replicas);
   cudaMemset(s->d_counters, 0, sizeof(cmx_counters) * n_replicas);
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -189,6 +191,9 @@ extern "C" void cmx_state_destroy(cmx_state *s) {
   cudaFree(s->d_exch);
   cudaFree(s->d_counters);
   cudaFree(s->d_flag);
+  for (void *m : s->ipc_open)
+    if (m) cudaIpcCloseMemHandle(m);
+  cudaFree(s->d_sig);
   cudaFree(s->d_scratch);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -381,6 +386,69 @@ extern "C" int cmx_state_device_ptr(cmx_state *s, void **d_ptr, size_t *n_bytes)
   if (!s || !d_ptr) return invalid("cmx_state_device_ptr: null argument");
   *d_ptr = s->d_occ;
   if (n_bytes) *n_bytes = (size_t)s->g.rep_stride * s->n_replicas;
+  return CMX_OK;
+}
+
+// ---- NVLink peer memory -------------------------------------------------------
+struct IpcBlob {
+  cudaIpcMemHandle_t occ, sig;
+};
+static_assert(sizeof(IpcBlob) <= CMX_IPC_HANDLE_BYTES, "handle size");
+
+extern "C" int cmx_state_ipc_export(cmx_state *s, void *handle) {
+  if (!s || !handle) return invalid("cmx_state_ipc_export: null argument");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  IpcBlob b;
+  memset(&b, 0, sizeof(b));
+  CMX_CUDA(cudaIpcGetMemHandle(&b.occ, s->d_occ));
+  CMX_CUDA(cudaIpcGetMemHandle(&b.sig, s->d_sig));
+  memset(handle, 0, CMX_IPC_HANDLE_BYTES);
+  memcpy(handle, &b, sizeof(b));
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_ipc_attach(cmx_state *s, const void *handle_dn, const void *handle_up) {
+  if (!s) return invalid("cmx_state_ipc_attach: null state");
+  if (!s->g.halo) return invalid("cmx_state_ipc_attach: not a slab state (halo = 0)");
+  if (s->p2p) return invalid("cmx_state_ipc_attach: already attached");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  auto open_one = [&](const void *h, int slot, int8_t **occ, unsigned long long **sig) -> int {
+    if (!h) {  // the neighbour is this state
+      *occ = s->d_occ;
+      *sig = s->d_sig;
+      return CMX_OK;
+    }
+    IpcBlob b;
+    memcpy(&b, h, sizeof(b));
+    void *po = nullptr, *ps = nullptr;
+    CMX_CUDA(cudaIpcOpenMemHandle(&po, b.occ, cudaIpcMemLazyEnablePeerAccess));
+    s->ipc_open[slot] = po;
+    CMX_CUDA(cudaIpcOpenMemHandle(&ps, b.sig, cudaIpcMemLazyEnablePeerAccess));
+    s->ipc_open[slot + 1] = ps;
+    *occ = (int8_t *)po;
+    *sig = (unsigned long long *)ps;
+    return CMX_OK;
+  };
+  int rc = open_one(handle_dn, 0, &s->peer_occ_dn, &s->peer_sig_dn);
+  if (rc) return rc;
+  if (handle_dn && handle_up && memcmp(handle_dn, handle_up, sizeof(IpcBlob)) == 0) {
+    s->peer_occ_up = s->peer_occ_dn;  // two slabs: both neighbours are the same rank
+    s->peer_sig_up = s->peer_sig_dn;
+  } else {
+    rc = open_one(handle_up, 2, &s->peer_occ_up, &s->peer_sig_up);
+    if (rc) return rc;
+  }
+  CMX_CUDA(cudaMemset(s->d_sig, 0, sizeof(unsigned long long) * 4));
+  s->epoch = 0;
+  s->blocks_done = 0;
+  s->p2p = true;
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_p2p_active(const cmx_state *s, int32_t *active) {
+  if (!s || !active) return invalid("cmx_state_p2p_active: null argument");
+  *active = (s->p2p && s->plan.valid && s->plan.pair_lut &&
+             !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) ? 1 : 0;
   return CMX_OK;
 }
 

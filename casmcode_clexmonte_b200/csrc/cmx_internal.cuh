@@ -155,6 +155,16 @@ struct cmx_state {
   uint32_t sweep_flags = 0;            // CMX_SWEEP_* (cmx_state_set_sweep_flags)
   cmx_counters *d_counters = nullptr;  // [replica]
   int *d_flag = nullptr;               // device-side validation flag
+  // slab decomposition over NVLink peer memory (cmx_state_ipc_attach):
+  // d_sig[0] / [1]: epoch reached by my lower / upper ring neighbour (written by
+  // them), [2]: finished blocks of my own sweep launches, [3]: wait timed out
+  unsigned long long *d_sig = nullptr;
+  bool p2p = false;
+  int8_t *peer_occ_dn = nullptr, *peer_occ_up = nullptr;
+  unsigned long long *peer_sig_dn = nullptr, *peer_sig_up = nullptr;
+  void *ipc_open[4] = {nullptr, nullptr, nullptr, nullptr};  // mappings to close
+  unsigned long long epoch = 0;        // k-group steps completed by this rank
+  unsigned long long blocks_done = 0;  // expected value of d_sig[2]
   // scratch
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;

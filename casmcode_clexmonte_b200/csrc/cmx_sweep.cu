@@ -163,7 +163,24 @@ struct Pair16Args {
   uint32_t sweep_lo;     // RNG counter words
   uint32_t ctr_hi;       // (sweep_hi << 16) | (row colour << 9); bit 8 = x colour, low bits = draw
   int k_offset;          // global k of local layer 0 (slab decomposition)
+  // halo exchange fused into the kernel (cmx_state_ipc_attach): boundary rows are
+  // also stored into the ring neighbours' ghost layers; wait_epoch != 0: do not
+  // read the lattice before both neighbours reached that epoch; signal_epoch != 0:
+  // the last block to finish publishes it to both neighbours
+  int8_t *peer_dn, *peer_up;
+  unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
+  unsigned long long wait_epoch, signal_epoch, blocks_target;
+  int push;
 };
+
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // shared memory is addressed with explicit 32-bit addresses: the dE table sits at
 // a compile-time offset from the acceptance table, so one address serves both
@@ -299,6 +316,17 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
   const uint32_t tab = (uint32_t)__cvta_generic_to_shared(sh_tables);
   uint32_t ff;
   asm volatile("mov.u32 %0, 0xFF;" : "=r"(ff));  // opaque to constant propagation, see prmt_imm
+  if (a.wait_epoch && threadIdx.x == 0) {
+    // acquire: the neighbours' pushes into my ghost layers precede their flag
+    const long long t0 = clock64();
+    while (ld_sys(a.my_sig + 0) < a.wait_epoch || ld_sys(a.my_sig + 1) < a.wait_epoch) {
+      if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour is gone
+        a.my_sig[3] = 1ull;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
   __syncthreads();
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const Geom &g = a.g;
@@ -323,11 +351,12 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
     const uint32_t row = row0 + rl;
     const bool on = lane_on && row < a.n_rows;
     uint32_t C[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0};
-    uint32_t cl = 0, off_c = 0, gid = 0;
+    uint32_t cl = 0, off_c = 0, gid = 0, k_row = 0;
     if (on) {
       uint32_t kk, jj;
       fastdivmod(row, a.divJ, kk, jj);
       const uint32_t j = 2 * jj + a.cy, k = 2 * kk + a.cz;
+      k_row = k;
       off_c = ((k + g.halo) * N1 + j) * N0 + x0;
       gid = ((k + (uint32_t)a.k_offset) * N1 + j) * a.W + c;
       uint32_t dj[3], dk[3];
@@ -421,7 +450,18 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
       if (tie)
         pair16_ties<1, NOCC, ACCUM>(cnt, C0, C, ph, tab, a.thr_lo + (size_t)r * NTAB, gid, r,
                                     a.sweep_lo, ctr1, a.k0, a.k1, n_acc, e_sum);
-      *reinterpret_cast<uint4 *>(base + off_c) = make_uint4(C[0], C[1], C[2], C[3]);
+      const uint4 out = make_uint4(C[0], C[1], C[2], C[3]);
+      *reinterpret_cast<uint4 *>(base + off_c) = out;
+      if (a.push) {
+        // my layer 0 is the lower neighbour's upper ghost, my last layer the
+        // upper neighbour's lower ghost (same slab geometry on every rank)
+        const uint32_t kl = k_row;
+        const size_t rep = (size_t)r * g.rep_stride;
+        if (kl == 0)
+          *reinterpret_cast<uint4 *>(a.peer_dn + rep + off_c + N2 * layer) = out;
+        if (kl == N2 - 1)
+          *reinterpret_cast<uint4 *>(a.peer_up + rep + off_c - N2 * layer) = out;
+      }
     }
   }
   // ---- block reduction of the counters (fixed order -> deterministic)
@@ -447,6 +487,18 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
     size_t slot = (size_t)r * gridDim.x + blockIdx.x;
     a.part_acc[slot] += A;
     a.part_dE[slot] += E;
+    if (a.push) {
+      // release: every store of this block (ordered before this thread by the
+      // barrier above) is visible system-wide before the block counts as done;
+      // the block that completes the step publishes the epoch to both neighbours
+      __threadfence_system();
+      const unsigned long long done = atomicAdd(a.my_sig + 2, 1ull) + 1ull;
+      if (a.signal_epoch && done == a.blocks_target) {
+        __threadfence_system();
+        st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
+        st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
+      }
+    }
   }
 }
 
@@ -890,11 +942,26 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     dim3 grid(P.part_blocks, s->n_replicas);
     const bool fcc = (P.mask == kMaskFcc1NN);
     const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
+    a.push = (s->p2p && g.halo) ? 1 : 0;
+    a.peer_dn = s->peer_occ_dn;
+    a.peer_up = s->peer_occ_up;
+    a.my_sig = s->d_sig;
+    a.peer_sig_dn = s->peer_sig_dn;
+    a.peer_sig_up = s->peer_sig_up;
     for (int cz = 0; cz < 2; ++cz) {
       if (kgroup >= 0 && cz != kgroup) continue;
       for (int cy = 0; cy < 2; ++cy) {
         a.cy = cy;
         a.cz = cz;
+        a.wait_epoch = a.signal_epoch = a.blocks_target = 0;
+        if (a.push) {
+          // one k-colour group = one step of the ring protocol: wait for the
+          // neighbours' previous step before the first launch, publish after the last
+          if (cy == 0) a.wait_epoch = s->epoch;
+          s->blocks_done += (unsigned long long)grid.x * grid.y;
+          a.blocks_target = s->blocks_done;
+          if (cy == 1) a.signal_epoch = ++s->epoch;
+        }
         a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
         if (P.nocc == 3) {
           if (pair16_minb() >= 4) launch_pair16<3, 4>(a, grid, s->stream, fcc, accum);
@@ -1020,7 +1087,14 @@ extern "C" int cmx_counters_read(cmx_state *s, cmx_counters *counters) {
   CMX_CUDA(cudaGetLastError());
   CMX_CUDA(cudaMemcpyAsync(counters, s->d_counters, sizeof(cmx_counters) * s->n_replicas,
                            cudaMemcpyDeviceToHost, s->stream));
+  unsigned long long timed_out = 0;
+  if (s->p2p)
+    CMX_CUDA(cudaMemcpyAsync(&timed_out, s->d_sig + 3, sizeof(timed_out), cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
+  if (timed_out) {
+    cmx_set_error("cmx_counters_read: a ring neighbour did not reach the expected epoch (halo wait timed out)");
+    return CMX_ERR_CUDA;
+  }
   return CMX_OK;
 }
 

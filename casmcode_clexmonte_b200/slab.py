@@ -63,7 +63,7 @@ class _DevMem:
 class SlabRunner:
     def __init__(self, tables: _capi.Tables, N, eci, temperature: float, exch, rank: int, world: int,
                  local_rank: int, seed_init: int = 1, backend_device: Optional[str] = "cuda",
-                 init_occ: Optional[np.ndarray] = None):
+                 init_occ: Optional[np.ndarray] = None, p2p: bool = True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -103,6 +103,27 @@ class SlabRunner:
         if init_occ is None:
             init_occ = np.random.default_rng(seed_init).integers(0, 3, n_cells_g * self.n_sublat).astype(np.int8)
         self.upload_global(init_occ)
+        # halo exchange fused into the sweep kernel: every rank maps its ring
+        # neighbours' slabs (CUDA IPC over NVLink) and the kernel stores the
+        # boundary rows it changes straight into their ghost layers
+        self.p2p = False
+        if p2p:
+            self._attach_peers()
+
+    def _attach_peers(self) -> None:
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            self.state.ipc_attach(None, None)
+        else:
+            mine = torch.frombuffer(bytearray(self.state.ipc_export()), dtype=torch.uint8).to(self.mem.device)
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine)
+            hb = [bytes(h.cpu().numpy().tobytes()) for h in allh]
+            self.stream.synchronize()
+            dist.barrier()
+            self.state.ipc_attach(hb[self.dn], hb[self.up])
+            dist.barrier()  # nobody pushes before everybody has mapped and zeroed its flags
+        self.p2p = self.state.p2p_active()
 
     # -- layout helpers -------------------------------------------------------
     def _layers(self, b: int, k_lo: int, k_hi: int):
@@ -174,7 +195,8 @@ class SlabRunner:
         for w in range(n_sweeps):
             for g in range(self.Sk):
                 self.state.sgc_sweep_kgroup(seed, first_sweep + w, g)
-                self.exchange(g)
+                if not self.p2p:
+                    self.exchange(g)
 
     def synchronize(self):
         self.stream.synchronize()

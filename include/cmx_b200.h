@@ -120,6 +120,23 @@ int cmx_state_stream(cmx_state *s, void **stream);
  * and its size in bytes (for NCCL halo plumbing by the host). */
 int cmx_state_device_ptr(cmx_state *s, void **d_ptr, size_t *n_bytes);
 
+/* Slab decomposition over NVLink peer memory (one process per GPU, one box).
+ * cmx_state_ipc_export writes an opaque handle (CUDA IPC) of a slab state;
+ * the host exchanges the handles of ring neighbours (e.g. an all-gather) and
+ * calls cmx_state_ipc_attach(handle of the lower neighbour, of the upper
+ * neighbour; NULL = the neighbour is this state itself, i.e. one slab).  From
+ * then on the pair-LUT sweep kernel stores every boundary row it changes
+ * straight into the neighbour's ghost layer and the ranks synchronise through
+ * epoch flags in peer memory (release/acquire at system scope): the halo
+ * exchange is fused into the sweep kernel and cmx_sgc_sweep_kgroup needs no
+ * separate exchange between k-colour groups.  Every rank must issue the same
+ * sequence of sweep calls. */
+#define CMX_IPC_HANDLE_BYTES 128
+int cmx_state_ipc_export(cmx_state *s, void *handle);
+int cmx_state_ipc_attach(cmx_state *s, const void *handle_dn, const void *handle_up);
+/* 1 when sweeps of this state push their halos themselves */
+int cmx_state_p2p_active(const cmx_state *s, int32_t *active);
+
 /* Bind the cluster expansion coefficients: sparse (index, value) pairs as in
  * the reference's SparseCoefficients; ClexData parsed at
  * src/casm/clexmonte/system/io/json/System_json_io.cc:491-539. */

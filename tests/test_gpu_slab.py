@@ -12,7 +12,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, N, n_sweeps, out):
+def _worker(rank, world, port, N, n_sweeps, p2p, out):
     import torch
     import torch.distributed as dist
     from casmcode_clexmonte_b200 import _capi
@@ -27,7 +27,8 @@ def _worker(rank, world, port, N, n_sweeps, out):
     tables = _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz"), device=rank)
     ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [0.1, -0.2], 3)
     init = np.random.default_rng(4).integers(0, 3, N ** 3).astype(np.int8)
-    run = SlabRunner(tables, N, sysd["eci_sparse"], 900.0, ex, rank, world, rank, init_occ=init)
+    run = SlabRunner(tables, N, sysd["eci_sparse"], 900.0, ex, rank, world, rank, init_occ=init, p2p=p2p)
+    assert run.p2p == p2p
     run.state.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
     run.state.counters_reset()
     run.sweep(n_sweeps, seed=17)
@@ -40,7 +41,8 @@ def _worker(rank, world, port, N, n_sweeps, out):
     dist.destroy_process_group()
 
 
-def test_two_slabs_equal_one_gpu():
+@pytest.mark.parametrize("p2p", [True, False])
+def test_two_slabs_equal_one_gpu(p2p):
     import torch
     import torch.multiprocessing as mp
     from casmcode_clexmonte_b200 import _capi
@@ -51,8 +53,8 @@ def test_two_slabs_equal_one_gpu():
     N, n_sweeps, world = 32, 6, 2
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29600 + os.getpid() % 1000
-    mp.spawn(_worker, args=(world, port, N, n_sweeps, out), nprocs=world, join=True)
+    port = 29600 + os.getpid() % 1000 + (7 if p2p else 0)
+    mp.spawn(_worker, args=(world, port, N, n_sweeps, p2p, out), nprocs=world, join=True)
     sysd = json.loads((GOLDEN / "systems.json").read_text())["fcc"]
     tables = _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz"))
     st = _capi.State(tables, (N, N, N))
@@ -64,4 +66,39 @@ def test_two_slabs_equal_one_gpu():
     assert (st.download_occ(dtype=np.int8) == out["occ"]).all()
     assert cnt[0].n_accept == int(out["cnt"][1]) and cnt[0].n_attempt == int(out["cnt"][0])
     assert cnt[0].dE_sum == pytest.approx(float(out["cnt"][2]), rel=1e-12)
+    st.close()
+
+
+def test_one_slab_with_fused_halo_equals_periodic_box():
+    """A single slab with ghost layers whose 'neighbours' are itself (the fused
+    peer-memory halo push writing its own ghost layers) reproduces the plain
+    periodic box -- runs on one GPU."""
+    import torch
+    from casmcode_clexmonte_b200 import _capi
+    from casmcode_clexmonte_b200.clexulator_tables import ClexulatorTables
+    from casmcode_clexmonte_b200.potential import semigrand_exchange_table
+    from casmcode_clexmonte_b200.slab import SlabRunner
+    N, n_sweeps = 32, 5
+    sysd = json.loads((GOLDEN / "systems.json").read_text())["fcc"]
+    tables = _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz"))
+    ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [0.1, -0.2], 3)
+    init = np.random.default_rng(4).integers(0, 3, N ** 3).astype(np.int8)
+    res = {}
+    for p2p in (True, False):
+        run = SlabRunner(tables, N, sysd["eci_sparse"], 900.0, ex, 0, 1, 0, init_occ=init, p2p=p2p)
+        assert run.p2p == p2p
+        run.state.counters_reset()
+        run.sweep(n_sweeps, seed=17)
+        run.synchronize()
+        res[p2p] = (run.download_local(), run.state.counters_read()[0].n_accept)
+        run.state.close()
+    st = _capi.State(tables, (N, N, N))
+    st.set_eci(sysd["eci_sparse"]["index"], sysd["eci_sparse"]["value"])
+    st.set_conditions(900.0, ex)
+    st.upload_occ(init)
+    cnt = st.sgc_sweep(n_sweeps, seed=17)
+    ref = st.download_occ(dtype=np.int8)
+    for p2p in (True, False):
+        assert (res[p2p][0] == ref).all(), f"p2p={p2p}"
+        assert res[p2p][1] == cnt[0].n_accept
     st.close()
