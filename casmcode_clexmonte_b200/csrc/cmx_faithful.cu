@@ -5,6 +5,8 @@
 //   _calc_point_corr (:500-553), _calc_global_corr_contribution (:446-498)
 // and of the [EXT] wrappers ClusterExpansion::occ_delta_value / per_supercell
 // (call sites SemiGrandCanonicalCalculator.cc:171-213).
+#include <algorithm>
+
 #include "cmx_internal.cuh"
 
 static int invalid(const std::string &msg) {
@@ -339,6 +341,8 @@ extern "C" int cmx_energy(const cmx_state *cs, int32_t replica, double *E) {
     cmx_set_error("cmx_energy: no ECI bound (call cmx_state_set_eci)");
     return CMX_ERR_STATE;
   }
+  if (replica < 0 || replica >= s->n_replicas) return invalid("cmx_energy: replica out of range");
+  if (s->plan.e_fast && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) return cmx_energy_fast(s, replica, E);
   std::vector<double> corr(s->t->d.corr_size);
   int rc = cmx_global_corr(s, replica, corr.data());
   if (rc) return rc;
@@ -368,6 +372,30 @@ __global__ void k_composition(Geom g, int n_sublat, int max_occ,
     if (sh_cnt[q]) atomicAdd(&counts[q], (unsigned long long)sh_cnt[q]);
 }
 
+// single-sublattice states with <= 3 occupants (storage codes 0 / 1 / 18, or 0 / 1):
+// 16 sites per load, occupants counted with two population counts per word
+__global__ void k_composition_coded(const uint4 *__restrict__ occ, int64_t n16,
+                                    unsigned long long *__restrict__ counts) {
+  unsigned int n1 = 0, n2 = 0;
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n16;
+       x += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = occ[x];
+    n1 += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
+          __popc(v.w & 0x01010101u);
+    n2 += __popc(v.x & 0x10101010u) + __popc(v.y & 0x10101010u) + __popc(v.z & 0x10101010u) +
+          __popc(v.w & 0x10101010u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n1 += __shfl_down_sync(0xffffffffu, n1, o);
+    n2 += __shfl_down_sync(0xffffffffu, n2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n1) atomicAdd(&counts[1], (unsigned long long)n1);
+    if (n2) atomicAdd(&counts[2], (unsigned long long)n2);
+  }
+}
+
 extern "C" int cmx_composition(const cmx_state *cs, int32_t replica, int64_t *counts) {
   cmx_state *s = const_cast<cmx_state *>(cs);
   if (!s || !counts) return invalid("cmx_composition: null argument");
@@ -382,6 +410,22 @@ extern "C" int cmx_composition(const cmx_state *cs, int32_t replica, int64_t *co
   int64_t total = s->g.n_cells * T.n_sublat;
   int nb = (int)((total + 255) / 256);
   if (nb > 1184) nb = 1184;
+  if (T.n_sublat == 1 && T.max_occ <= 3 && s->g.n_cells % 16 == 0 && (s->g.coded || T.max_occ <= 2)) {
+    // owned layers are contiguous (ghost layers sit before and after them)
+    const int8_t *first = s->d_occ + (size_t)replica * s->g.rep_stride + (size_t)s->g.halo * s->g.layer;
+    int64_t n16 = s->g.n_cells / 16;
+    int nbc = (int)std::min<int64_t>((n16 + 255) / 256, 1184);
+    k_composition_coded<<<nbc, 256, 0, s->stream>>>((const uint4 *)first, n16,
+                                                     (unsigned long long *)s->d_scratch);
+    CMX_CUDA(cudaGetLastError());
+    CMX_CUDA(cudaMemcpyAsync(counts, s->d_scratch, sizeof(int64_t) * nbins,
+                             cudaMemcpyDeviceToHost, s->stream));
+    CMX_CUDA(cudaStreamSynchronize(s->stream));
+    int64_t rest = s->g.n_cells;
+    for (int q = 1; q < nbins; ++q) rest -= counts[q];
+    counts[0] = rest;
+    return CMX_OK;
+  }
   k_composition<<<nb, 256, sizeof(unsigned int) * nbins, s->stream>>>(
       s->g, T.n_sublat, T.max_occ, s->d_occ + (size_t)replica * s->g.rep_stride,
       (unsigned long long *)s->d_scratch);

@@ -120,6 +120,12 @@ struct SweepPlan {
   uint32_t *d_thr_lo = nullptr;   // [replica][n_tab] low 32 bits of the threshold (tie break)
   double *d_dEpot = nullptr;      // [replica][n_tab] dE - exch
   bool thr_dirty = true;
+  // fast energy (cmx_energy.cu): per-cell energy as a function of (occupant,
+  // species counts over the cell's "forward" neighbors), same byte-lane counting
+  bool e_fast = false;
+  uint32_t e_mask = 0;   // forward neighbor rows/offsets, bit layout as `mask`
+  int32_t e_z = 0;
+  double *d_e_lut = nullptr;  // [4][256]: index = cnt | occupant << 8
   // per-block partial counters of the current call
   long long *d_part_acc = nullptr;
   double *d_part_dE = nullptr;
@@ -174,6 +180,8 @@ struct cmx_state {
 int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
 void cmx_canonical_free(cmx_state *s);
+int cmx_plan_energy(cmx_state *s);                       // cmx_energy.cu
+int cmx_energy_fast(cmx_state *s, int32_t replica, double *E);  // requires plan.e_fast
 void cmx_plan_free(SweepPlan &p);
 
 // ---- device helpers ---------------------------------------------------------

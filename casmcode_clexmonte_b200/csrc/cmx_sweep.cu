@@ -41,6 +41,7 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_dEpot);
   cudaFree(p.d_part_acc);
   cudaFree(p.d_part_dE);
+  cudaFree(p.d_e_lut);
   p = SweepPlan();
 }
 
@@ -845,6 +846,7 @@ int cmx_plan_sweep(cmx_state *s) {
     P.bytes_per_step = P.z + 2;
   }
   P.thr_dirty = true;
+  if (P.pair_lut) return cmx_plan_energy(s);
   return CMX_OK;
 }
 

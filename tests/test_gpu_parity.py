@@ -269,6 +269,35 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
     b.close()
 
 
+@pytest.mark.parametrize("N", [(16, 6, 4), (48, 10, 8), (512, 4, 2)])
+def test_fast_energy_equals_faithful_global_evaluation(dev_tables, systems, load_vectors, N):
+    """ClusterExpansion::per_supercell through the count-table streaming kernel
+    (cmx_energy.cu) against the sum of faithful per-cell contributions (rtol 1e-12;
+    the reference sums cells in ascending order, both kernels use tree sums)."""
+    sysd = systems["fcc"]
+    for eci_key in ("eci_sparse", "eci_2"):
+        a, _, _ = _sweep_state(dev_tables, systems, "fcc", eci_key, N, 900.0, [0.1, 0.2], n_replicas=2, seed=11)
+        for r in range(2):
+            fast = a.energy(r)
+            a.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC)
+            slow = a.energy(r)
+            a.set_sweep_flags(0)
+            g = a.global_corr(r)
+            eci = sysd[eci_key]
+            ref = float(np.dot(eci["value"], g[eci["index"]]))
+            assert slow == pytest.approx(ref, rel=1e-13)
+            assert fast == pytest.approx(ref, rel=1e-12, abs=1e-9)
+        a.close()
+    # golden configuration of the reference kernels
+    v = load_vectors("fcc_sparse")
+    st = _capi.State(dev_tables("fcc_default"), tuple(int(x) for x in v["N"]))
+    st.upload_occ(v["occ"])
+    st.set_eci(v["eci_index"], v["eci_value"])
+    ref = float(np.dot(v["eci_value"], v["global_corr"][v["eci_index"]]))
+    assert st.energy() == pytest.approx(ref, rel=1e-12)
+    st.close()
+
+
 def test_int8_round_trip_of_coded_states(dev_tables):
     """Ternary single-sublattice states store occupant 2 as 16 on the device
     (Geom::coded); every transfer path must hide that."""
