@@ -336,3 +336,41 @@ __device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1,
   o.c[3] = c3;
   return o;
 }
+
+// Same generator with the round keys (k0 + r*W0, k1 + r*W1) taken from a
+// precomputed schedule: when `rk` lives in the kernel parameter (constant) bank
+// the xors read it directly and the 20 key additions per call disappear.
+struct PhiloxKeys {
+  uint32_t k[20];
+};
+static inline PhiloxKeys philox_key_schedule(uint32_t k0, uint32_t k1) {
+  PhiloxKeys s;
+  for (int r = 0; r < 10; ++r) {
+    s.k[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+    s.k[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+  }
+  return s;
+}
+__device__ __forceinline__ Philox philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                   uint32_t c3, const PhiloxKeys &rk) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0;
+    uint64_t p1 = (uint64_t)M1 * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k[2 * r];
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk.k[2 * r + 1];
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+  }
+  Philox o;
+  o.c[0] = c0;
+  o.c[1] = c1;
+  o.c[2] = c2;
+  o.c[3] = c3;
+  return o;
+}

@@ -158,9 +158,11 @@ struct Pair16Args {
   const uint32_t *tab;     // [replica][n_tab]
   const uint32_t *thr_lo;  // [replica][n_tab]
   const double *dEpot;     // [replica][n_tab]
-  long long *part_acc;     // [replica][gridDim.x]
+  long long *part_acc;     // [replica][part_stride]
+  uint32_t part_stride;
   double *part_dE;
   uint32_t k0, k1;       // seed
+  PhiloxKeys rk;         // its round-key schedule (read from the constant bank)
   uint32_t sweep_lo;     // RNG counter words
   uint32_t ctr_hi;       // (sweep_hi << 16) | (row colour << 9); bit 8 = x colour, low bits = draw
   int k_offset;          // global k of local layer 0 (slab decomposition)
@@ -172,6 +174,15 @@ struct Pair16Args {
   unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
   unsigned long long wait_epoch, signal_epoch, blocks_target;
   int push;
+  // staged variant (k_sweep_pair16s): a tile = RB target rows of one layer; its
+  // source rows are copied into shared memory by bulk async copies, layer block
+  // dz = -1, 0, +1 holds rows [first target row + dy_min[dz], last + dy_max[dz]]
+  uint32_t n_tiles, tiles_per_layer;  // tiles_per_layer = J / RB
+  FastDiv divT;                       // by tiles_per_layer
+  uint32_t blk_rows[3];               // rows of each layer block (0 = layer not needed)
+  uint32_t blk_off[3];                // byte offset of each layer block inside a stage
+  int32_t dy_min[3];
+  uint32_t stage_bytes;
 };
 
 __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p) {
@@ -251,7 +262,7 @@ __device__ __forceinline__ void pair16_update(const uint32_t (&cnt)[4], uint32_t
 // the threshold's; draw 32 more bits per site and finish the 47-bit comparison.
 // Re-derives everything from the chunk as it was BEFORE this colour's update.
 template <int CX, int NOCC, bool ACCUM>
-__device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], const uint32_t (&C0)[4],
+__device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], const uint4 *chunk0,
                                             uint32_t (&C)[4], const Philox &ph, uint32_t tab,
                                             const uint32_t *__restrict__ thr_lo, uint32_t gid,
                                             uint32_t r, uint32_t sweep_lo, uint32_t ctr, uint32_t k0,
@@ -259,6 +270,10 @@ __device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], const uint
   constexpr int NTAB = CMX_TAB16(NOCC);
   const Philox lo0 = philox4x32_10(gid, r, sweep_lo, ctr | 1u, k0, k1);
   const Philox lo1 = philox4x32_10(gid, r, sweep_lo, ctr | 2u, k0, k1);
+  // the chunk as stored in global memory: it is written back only after both
+  // colours, and the occupants of THIS colour's lanes have not changed before
+  const uint4 c0 = *chunk0;
+  const uint32_t C0[4] = {c0.x, c0.y, c0.z, c0.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t R = ph.c[i];
@@ -422,13 +437,13 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
         if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : 0u, 8);
       }
       const uint32_t ctr0 = a.ctr_hi;
-      const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr0, a.k0, a.k1);
+      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr0, a.rk);
       bool tie = false;
-      const uint32_t C0[4] = {C[0], C[1], C[2], C[3]};
       pair16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
       if (tie)
-        pair16_ties<0, NOCC, ACCUM>(cnt, C0, C, ph, tab, a.thr_lo + (size_t)r * NTAB, gid, r,
-                                    a.sweep_lo, ctr0, a.k0, a.k1, n_acc, e_sum);
+        pair16_ties<0, NOCC, ACCUM>(cnt, reinterpret_cast<const uint4 *>(base + off_c), C, ph, tab,
+                                    a.thr_lo + (size_t)r * NTAB, gid, r, a.sweep_lo, ctr0, a.k0, a.k1,
+                                    n_acc, e_sum);
       sh_x[it & 1][threadIdx.x] = (uint8_t)(C[0] & 0xFFu);
     }
     __syncthreads();
@@ -444,13 +459,13 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
         if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : nb, 8);
       }
       const uint32_t ctr1 = a.ctr_hi | 0x100u;
-      const Philox ph = philox4x32_10(gid, r, a.sweep_lo, ctr1, a.k0, a.k1);
+      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr1, a.rk);
       bool tie = false;
-      const uint32_t C0[4] = {C[0], C[1], C[2], C[3]};
       pair16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
       if (tie)
-        pair16_ties<1, NOCC, ACCUM>(cnt, C0, C, ph, tab, a.thr_lo + (size_t)r * NTAB, gid, r,
-                                    a.sweep_lo, ctr1, a.k0, a.k1, n_acc, e_sum);
+        pair16_ties<1, NOCC, ACCUM>(cnt, reinterpret_cast<const uint4 *>(base + off_c), C, ph, tab,
+                                    a.thr_lo + (size_t)r * NTAB, gid, r, a.sweep_lo, ctr1, a.k0, a.k1,
+                                    n_acc, e_sum);
       const uint4 out = make_uint4(C[0], C[1], C[2], C[3]);
       *reinterpret_cast<uint4 *>(base + off_c) = out;
       if (a.push) {
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
       A += sh_acc[w];
       E += sh_sum[w];
     }
-    size_t slot = (size_t)r * gridDim.x + blockIdx.x;
+    size_t slot = (size_t)r * a.part_stride + blockIdx.x;
     a.part_acc[slot] += A;
     a.part_dE[slot] += E;
     if (a.push) {
@@ -498,6 +513,316 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
         __threadfence_system();
         st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
         st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// staged variant: the rows a tile needs are brought into shared memory with bulk
+// asynchronous copies (cp.async.bulk, completion on an mbarrier), double
+// buffered -- tile i+1 is in flight while tile i is computed.  The per-thread
+// global address arithmetic (periodic wraps, 64-bit adds for 12 loads) is gone:
+// every thread reads its 16-byte chunks and side words at loop-invariant
+// shared-memory offsets; the wraps are resolved once per ROW by the thread that
+// issues the row's copy.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32v(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
+// Warp-specialised: warps 0-7 (256 threads) compute, warp 8 is the producer that
+// issues the bulk copies of tile i+STAGES-1 while tile i is computed.
+//   full[s]   producer -> consumers: the stage's bytes have landed (complete_tx)
+//   empty[s]  consumers -> producer: every compute warp has read the stage
+#define CMX_STAGES 2
+template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+__global__ void __launch_bounds__(288, 3) k_sweep_pair16s(Pair16Args a) {
+  constexpr int NTAB = CMX_TAB16(NOCC);
+  constexpr uint32_t TAB_BYTES = NTAB * 4 + (ACCUM ? NTAB * 8 : 0);
+  // dynamic shared memory: [tables][stage 0][stage 1]...
+  extern __shared__ __align__(128) unsigned char sh_dyn[];
+  __shared__ __align__(8) unsigned long long sh_mbar[2 * CMX_STAGES];  // full[], empty[]
+  __shared__ uint8_t sh_x[2][256];
+  __shared__ long long sh_acc[8];
+  __shared__ double sh_sum[8];
+  const uint32_t r = blockIdx.y;
+  if (threadIdx.x < 256) {
+    const uint32_t *gt = a.tab + (size_t)r * NTAB;
+    const double *ge = a.dEpot + (size_t)r * NTAB;
+    uint32_t *st = reinterpret_cast<uint32_t *>(sh_dyn);
+    double *se = reinterpret_cast<double *>(sh_dyn + NTAB * 4);
+    for (int q = threadIdx.x; q < NTAB; q += 256) {
+      st[q] = gt[q];
+      if (ACCUM) se[q] = ge[q];
+    }
+  }
+  const uint32_t tab = (uint32_t)__cvta_generic_to_shared(sh_dyn);
+  const uint32_t stage0 = tab + ((TAB_BYTES + 127u) & ~127u);
+  const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&sh_mbar[0]);
+  const uint32_t empty0 = full0 + 8 * CMX_STAGES;
+  const Geom &g = a.g;
+  int8_t *base = a.occ + (size_t)r * g.rep_stride;
+  const uint32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
+  const uint32_t layer = N0 * N1;
+  const bool halo = g.halo != 0;
+  const uint32_t rows_tot = a.blk_rows[0] + a.blk_rows[1] + a.blk_rows[2];
+  const uint32_t n_issuers = (a.blk_rows[0] ? 1u : 0u) + (a.blk_rows[1] ? 1u : 0u) + (a.blk_rows[2] ? 1u : 0u);
+  (void)rows_tot;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < CMX_STAGES; ++q) {
+      mbar_init(full0 + 8 * q, n_issuers);
+      mbar_init(empty0 + 8 * q, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (threadIdx.x >= 256) {
+    // ------------------------------------------------------------- producer warp
+    const uint32_t lane = threadIdx.x - 256;
+    if (a.wait_epoch && lane == 0) {
+      // acquire: the neighbours' pushes into my ghost layers precede their flag
+      const long long t0 = clock64();
+      while (ld_sys(a.my_sig + 0) < a.wait_epoch || ld_sys(a.my_sig + 1) < a.wait_epoch) {
+        if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour is gone
+          a.my_sig[3] = 1ull;
+          break;
+        }
+        __nanosleep(100);
+      }
+    }
+    __syncwarp();
+    // lane dzi copies layer block dzi: its rows are consecutive rows of one layer,
+    // i.e. ONE contiguous range of global memory -- two when the range wraps
+    // around the periodic j axis (first / last tile of a layer)
+    const uint32_t my_rows = (lane < 3) ? a.blk_rows[lane] : 0u;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t stage = it % CMX_STAGES, use = it / CMX_STAGES;
+      if (use > 0) mbar_wait(empty0 + 8 * stage, (use - 1) & 1u);  // consumers drained the stage
+      if (my_rows == 0) continue;
+      uint32_t kk, tj;
+      fastdivmod(tile, a.divT, kk, tj);
+      const uint32_t k = 2 * kk + a.cz;
+      const uint32_t mbar = full0 + 8 * stage;
+      const uint32_t dst = stage0 + stage * a.stage_bytes + a.blk_off[lane];
+      int kz = (int)k + (int)lane - 1;
+      if (!halo) kz = (kz < 0) ? kz + (int)N2 : ((kz >= (int)N2) ? kz - (int)N2 : kz);
+      const int8_t *lay = base + (size_t)(kz + g.halo) * layer;
+      int jr0 = (int)(2 * tj * a.RB + a.cy) + a.dy_min[lane];  // first row of the block
+      mbar_expect_tx(mbar, my_rows * N0);
+      uint32_t head = 0;  // rows before the wrap
+      if (jr0 < 0) {
+        head = (uint32_t)(-jr0);
+        jr0 += (int)N1;
+      } else if ((uint32_t)jr0 + my_rows > N1) {
+        head = N1 - (uint32_t)jr0;
+      }
+      if (head >= my_rows) head = 0;  // (a range of exactly the remaining rows does not wrap)
+      if (head) {
+        bulk_g2s(dst, lay + (size_t)jr0 * N0, head * N0, mbar);
+        bulk_g2s(dst + head * N0, lay, (my_rows - head) * N0, mbar);
+      } else {
+        if ((uint32_t)jr0 >= N1) jr0 -= (int)N1;
+        bulk_g2s(dst, lay + (size_t)jr0 * N0, my_rows * N0, mbar);
+      }
+    }
+    return;
+  }
+
+  // --------------------------------------------------------------- compute warps
+  uint32_t ff;
+  asm volatile("mov.u32 %0, 0xFF;" : "=r"(ff));
+  const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
+  uint32_t n_acc = 0;
+  double e_sum = 0.0;
+  uint32_t rl, c;
+  fastdivmod(threadIdx.x, a.divW, rl, c);
+  const bool lane_on = rl < a.RB;
+  const uint32_t nxt = (c == a.W - 1) ? threadIdx.x - (a.W - 1) : threadIdx.x + 1;
+  const uint32_t x0 = 16 * c;
+  const uint32_t xl = (x0 == 0) ? N0 - 4 : x0 - 4;     // word holding byte x0-1
+  const uint32_t xr = (x0 + 16 == N0) ? 0u : x0 + 16;  // word holding byte x0+16
+  const uint32_t mc = (mask >> 12) & 7u;
+  // loop-invariant part of this thread's shared-memory addresses
+  const uint32_t row2 = 2 * rl * N0;
+  uint32_t it = 0;
+  for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    const uint32_t stage = it % CMX_STAGES, use = it / CMX_STAGES;
+    mbar_wait(full0 + 8 * stage, use & 1u);
+    const uint32_t sbase = stage0 + stage * a.stage_bytes + row2;
+    uint32_t C[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0};
+    uint32_t cl = 0;
+    uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
+    uint32_t sm = 0, sp = 0;
+    if (lane_on) {
+#pragma unroll
+      for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
+          const bool center = (dz == 0 && dy == 0);
+          if (m3 == 0 && !center) continue;
+          const uint32_t rowa = sbase + a.blk_off[dz + 1] + (uint32_t)(dy - a.dy_min[dz + 1]) * N0;
+          const uint4 ch = lds_u128(rowa + x0);
+          if (center) {
+            C[0] = ch.x;
+            C[1] = ch.y;
+            C[2] = ch.z;
+            C[3] = ch.w;
+            if (m3 & 1u) cl = lds_u32v(rowa + xl);
+            continue;
+          }
+          if (m3 & 2u) {
+            A0[0] += ch.x;
+            A0[1] += ch.y;
+            A0[2] += ch.z;
+            A0[3] += ch.w;
+          }
+          if (m3 & 1u) {
+            Am[0] += ch.x;
+            Am[1] += ch.y;
+            Am[2] += ch.z;
+            Am[3] += ch.w;
+            sm += lds_u32v(rowa + xl);
+          }
+          if (m3 & 4u) {
+            Ap[0] += ch.x;
+            Ap[1] += ch.y;
+            Ap[2] += ch.z;
+            Ap[3] += ch.w;
+            sp += lds_u32v(rowa + xr);
+          }
+        }
+      }
+    }
+    // this warp is done with the stage (mbarrier.arrive releases the loads above)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty0 + 8 * stage);
+    uint32_t off_c = 0, gid = 0, k_row = 0;
+    if (lane_on) {
+      uint32_t kk, tj;
+      fastdivmod(tile, a.divT, kk, tj);
+      const uint32_t jj = tj * a.RB + rl;
+      const uint32_t j = 2 * jj + a.cy, k = 2 * kk + a.cz;
+      k_row = k;
+      off_c = ((k + g.halo) * N1 + j) * N0 + x0;
+      gid = ((k + (uint32_t)a.k_offset) * N1 + j) * a.W + c;
+      T[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
+      T[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
+      T[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
+      T[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
+      uint32_t cnt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cnt[i] = T[i];
+        if (mc & 1u) cnt[i] += __funnelshift_l(i ? C[i - 1] : cl, C[i], 8);
+        if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : 0u, 8);
+      }
+      const uint32_t ctr0 = a.ctr_hi;
+      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr0, a.rk);
+      bool tie = false;
+      pair16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
+      if (tie)
+        pair16_ties<0, NOCC, ACCUM>(cnt, reinterpret_cast<const uint4 *>(base + off_c), C, ph, tab,
+                                    a.thr_lo + (size_t)r * NTAB, gid, r, a.sweep_lo, ctr0, a.k0, a.k1,
+                                    n_acc, e_sum);
+      sh_x[it & 1][threadIdx.x] = (uint8_t)(C[0] & 0xFFu);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // compute warps only
+    if (lane_on) {
+      const uint32_t nb = sh_x[it & 1][nxt];
+      uint32_t cnt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cnt[i] = T[i];
+        if (mc & 1u) cnt[i] += __funnelshift_l(i ? C[i - 1] : 0u, C[i], 8);
+        if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : nb, 8);
+      }
+      const uint32_t ctr1 = a.ctr_hi | 0x100u;
+      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr1, a.rk);
+      bool tie = false;
+      pair16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
+      if (tie)
+        pair16_ties<1, NOCC, ACCUM>(cnt, reinterpret_cast<const uint4 *>(base + off_c), C, ph, tab,
+                                    a.thr_lo + (size_t)r * NTAB, gid, r, a.sweep_lo, ctr1, a.k0, a.k1,
+                                    n_acc, e_sum);
+      const uint4 out = make_uint4(C[0], C[1], C[2], C[3]);
+      *reinterpret_cast<uint4 *>(base + off_c) = out;
+      if (a.push) {
+        const size_t rep = (size_t)r * g.rep_stride;
+        if (k_row == 0) *reinterpret_cast<uint4 *>(a.peer_dn + rep + off_c + N2 * layer) = out;
+        if (k_row == N2 - 1) *reinterpret_cast<uint4 *>(a.peer_up + rep + off_c - N2 * layer) = out;
+      }
+    }
+  }
+  long long n_acc64 = n_acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_acc64 += __shfl_down_sync(0xffffffffu, n_acc64, o);
+    e_sum += __shfl_down_sync(0xffffffffu, e_sum, o);
+  }
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    sh_acc[wid] = n_acc64;
+    sh_sum[wid] = e_sum;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (threadIdx.x == 0) {
+    long long A = 0;
+    double E = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      A += sh_acc[w];
+      E += sh_sum[w];
+    }
+    size_t slot = (size_t)r * a.part_stride + blockIdx.x;
+    a.part_acc[slot] += A;
+    a.part_dE[slot] += E;
+    if (a.push) {
+      __threadfence_system();
+      const unsigned long long done = atomicAdd(a.my_sig + 2, 1ull) + 1ull;
+      if (a.signal_epoch && done == a.blocks_target) {
+        __threadfence_system();
+        st_sys(a.peer_sig_dn + 1, a.signal_epoch);
+        st_sys(a.peer_sig_up + 0, a.signal_epoch);
       }
     }
   }
@@ -885,6 +1210,30 @@ static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool 
   }
 }
 
+template <int NOCC>
+static int launch_pair16s(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum,
+                          size_t dyn_bytes) {
+#define CMX_L16S(M, A)                                                                          \
+  do {                                                                                          \
+    auto kern = k_sweep_pair16s<NOCC, M, A>;                                                    \
+    static bool attr_set = false;                                                               \
+    if (!attr_set) {                                                                            \
+      CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      attr_set = true;                                                                          \
+    }                                                                                           \
+    kern<<<grid, 288, dyn_bytes, st>>>(a);                                                      \
+  } while (0)
+  if (fcc) {
+    if (accum) CMX_L16S(kMaskFcc1NN, true);
+    else CMX_L16S(kMaskFcc1NN, false);
+  } else {
+    if (accum) CMX_L16S(0u, true);
+    else CMX_L16S(0u, false);
+  }
+#undef CMX_L16S
+  return CMX_OK;
+}
+
 // tuning knobs (environment, read once): resident blocks per SM the pair16 kernel
 // is compiled for, and blocks per SM in the grid
 static int env_int(const char *name, int dflt) {
@@ -895,8 +1244,12 @@ static int pair16_minb() {
   static int v = env_int("CMX_PAIR16_MINB", 3);
   return v;
 }
+static int pair16_staged() {
+  static int v = env_int("CMX_PAIR16_STAGED", 0);
+  return v;
+}
 static int sweep_grid_per_sm() {
-  static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 3);
+  static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 4);
   return v;
 }
 
@@ -937,8 +1290,10 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     a.dEpot = P.d_dEpot;
     a.part_acc = P.d_part_acc;
     a.part_dE = P.d_part_dE;
+    a.part_stride = (uint32_t)P.part_blocks;
     a.k0 = (uint32_t)seed;
     a.k1 = (uint32_t)(seed >> 32);
+    a.rk = philox_key_schedule(a.k0, a.k1);
     a.sweep_lo = (uint32_t)sweep;
     a.k_offset = k_offset;
     dim3 grid(P.part_blocks, s->n_replicas);
@@ -950,6 +1305,49 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     a.my_sig = s->d_sig;
     a.peer_sig_dn = s->peer_sig_dn;
     a.peer_sig_up = s->peer_sig_up;
+    // staged variant: tiles of RB whole target rows of one layer
+    bool staged = pair16_staged() && (a.J % a.RB == 0) && !(s->sweep_flags & CMX_SWEEP_NO_STAGING);
+    if (s->sweep_flags & CMX_SWEEP_FORCE_STAGING) {
+      // any box: tiles of the largest number of rows that divides the rows of a layer
+      uint32_t rb = std::min(a.RB, a.J);
+      while (a.J % rb) --rb;
+      a.RB = rb;
+      staged = true;
+    }
+    size_t dyn_bytes = 0;
+    if (staged) {
+      a.tiles_per_layer = a.J / a.RB;
+      a.divT = make_fastdiv(a.tiles_per_layer);
+      a.n_tiles = a.tiles_per_layer * (uint32_t)(g.N2 / 2);
+      uint32_t off = 0;
+      for (int dz = -1; dz <= 1; ++dz) {
+        int lo = 2, hi = -2;
+        for (int dy = -1; dy <= 1; ++dy)
+          if (((P.mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u) || (dz == 0 && dy == 0)) {
+            lo = std::min(lo, dy);
+            hi = std::max(hi, dy);
+          }
+        a.blk_off[dz + 1] = off;
+        if (hi < lo) {
+          a.blk_rows[dz + 1] = 0;
+          a.dy_min[dz + 1] = 0;
+        } else {
+          a.blk_rows[dz + 1] = 2 * (a.RB - 1) + 1 + (uint32_t)(hi - lo);
+          a.dy_min[dz + 1] = lo;
+          off += a.blk_rows[dz + 1] * (uint32_t)g.N0;
+        }
+      }
+      a.stage_bytes = (off + 127u) & ~127u;
+      const size_t tab_bytes = (size_t)P.n_tab * 4 + (accum ? (size_t)P.n_tab * 8 : 0);
+      dyn_bytes = ((tab_bytes + 127) & ~(size_t)127) + CMX_STAGES * (size_t)a.stage_bytes;
+      if (dyn_bytes > 200 * 1024) staged = false;
+    }
+    if (staged) {
+      // persistent blocks: as many as fit, never more than tiles
+      int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (220 * 1024) / (dyn_bytes + 2048)));
+      int want = std::max(1, (148 * per_sm + s->n_replicas - 1) / s->n_replicas);
+      grid.x = (unsigned)std::min<uint32_t>(a.n_tiles, (uint32_t)std::min(want, P.part_blocks));
+    }
     for (int cz = 0; cz < 2; ++cz) {
       if (kgroup >= 0 && cz != kgroup) continue;
       for (int cy = 0; cy < 2; ++cy) {
@@ -965,7 +1363,11 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
           if (cy == 1) a.signal_epoch = ++s->epoch;
         }
         a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
-        if (P.nocc == 3) {
+        if (staged) {
+          int rc = (P.nocc == 3) ? launch_pair16s<3>(a, grid, s->stream, fcc, accum, dyn_bytes)
+                                 : launch_pair16s<2>(a, grid, s->stream, fcc, accum, dyn_bytes);
+          if (rc) return rc;
+        } else if (P.nocc == 3) {
           if (pair16_minb() >= 4) launch_pair16<3, 4>(a, grid, s->stream, fcc, accum);
           else launch_pair16<3, 3>(a, grid, s->stream, fcc, accum);
         } else {
@@ -1061,7 +1463,8 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
-  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC))
+  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_NO_STAGING |
+                         CMX_SWEEP_FORCE_STAGING))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;  // the grid may change with the evaluator

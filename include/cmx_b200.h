@@ -230,6 +230,12 @@ int cmx_counters_reset(cmx_state *s);
  *                           decisions: a cross-check of the fast path) */
 #define CMX_SWEEP_DE_SUM 1u
 #define CMX_SWEEP_FORCE_GENERIC 2u
+/* pair-LUT kernel variants (the trajectory does not depend on the variant):
+ * NO_STAGING reads neighbor rows straight from global memory; FORCE_STAGING uses
+ * the shared-memory staged variant (bulk async copies) even where its tiles do
+ * not fill a block -- by default it is chosen when they do. */
+#define CMX_SWEEP_NO_STAGING 4u
+#define CMX_SWEEP_FORCE_STAGING 8u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* synchronises the state's stream; counters[n_replicas] */
 int cmx_counters_read(cmx_state *s, cmx_counters *counters);

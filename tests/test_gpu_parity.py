@@ -230,8 +230,10 @@ def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
     b.close()
 
 
-@pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1)])
-def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas):
+@pytest.mark.parametrize("staging", ["default", "none", "forced"])
+@pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1),
+                                          ((128, 32, 4), 2)])
+def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas, staging):
     """The 16-sites-per-thread LUT kernel and the one-site-per-thread generic
     evaluator (whose delta E is checked against the reference kernels) draw the
     same random bits and must make the same decisions: identical occupation
@@ -245,7 +247,8 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.4], 3)
         a.set_conditions(500.0, ex2, replica=1)
         b.set_conditions(500.0, ex2, replica=1)
-    a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
+    variant = {"default": 0, "none": _capi.CMX_SWEEP_NO_STAGING, "forced": _capi.CMX_SWEEP_FORCE_STAGING}[staging]
+    a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM | variant)
     b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC | _capi.CMX_SWEEP_DE_SUM)
     assert a.sweep_info()["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
     for r in range(n_replicas):
@@ -259,7 +262,7 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         assert ca[r].n_accept == cb[r].n_accept and ca[r].n_attempt == cb[r].n_attempt
         assert ca[r].dE_sum == pytest.approx(cb[r].dE_sum, rel=1e-9, abs=1e-9)
     # without the dE accumulation (the default) the trajectory is the same
-    a.set_sweep_flags(0)
+    a.set_sweep_flags(variant)
     ca = a.sgc_sweep(2, seed=9, first_sweep=6)
     cb = b.sgc_sweep(2, seed=9, first_sweep=6)
     for r in range(n_replicas):
