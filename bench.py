@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--box", type=int, default=N_BOX)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 4 = no staging, 8 = force staging)")
+    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator, 4 = block kernel, 8 = no fusion)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -231,8 +231,13 @@ def main():
         attempts = K * S * n_sites
         assert cnt[0].n_attempt == attempts
         value = attempts / (ms * 1e-3)
-        launches = K * S * info["launches_per_sweep"] + 3
-        kernel_ms = ms / (K * S * info["launches_per_sweep"])
+        if info["fused"]:
+            # the whole timed call (K steps x S sweeps) is ONE launch of the fused kernel
+            sweep_launches = 1
+        else:
+            sweep_launches = K * S * info["launches_per_sweep"]
+        launches = sweep_launches + 3
+        kernel_ms = ms / sweep_launches
         # ---- end to end: host buffers through the C ABI, copies inside the timed region
         host = torch.empty(n_sites, dtype=torch.int8).pin_memory()
         harr = host.numpy()
@@ -272,11 +277,16 @@ def main():
         peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    sites_per_launch = n_sites / world / info["launches_per_sweep"]
+    if world == 1 and info["fused"]:
+        sites_per_launch = float(n_sites) * K * S
+        kernel_name = "k_sweep_row16_fused"
+    else:
+        sites_per_launch = n_sites / world / info["launches_per_sweep"]
+        kernel_name = "k_sweep_row16"
     alg_bytes = 2.0 * sites_per_launch           # 2 B per step at the HBM level
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_pair16",
+                "traffic": None, "peak_source": peak_src, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_step_hbm": 2.0,
                 "algorithmic_bytes_per_step_l2": info["bytes_per_step"],
                 "note": "the sweep is instruction-issue bound, not HBM bound: see DESIGN.md and profiles/"}

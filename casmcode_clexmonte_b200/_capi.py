@@ -19,7 +19,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libcmx_b200.so"
 
 CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
-CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC, CMX_SWEEP_NO_STAGING, CMX_SWEEP_FORCE_STAGING = 1, 2, 4, 8
+CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC, CMX_SWEEP_BLOCK_KERNEL, CMX_SWEEP_NO_FUSION = 1, 2, 4, 8
 
 # every symbol include/cmx_b200.h declares
 EXPORTED_SYMBOLS = [
@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
-    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches",
+    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_fused_info",
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
     "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
@@ -143,6 +143,7 @@ def lib():
     L.cmx_sweep_info.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(dbl), C.POINTER(dbl),
                                  C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cmx_sweep_launches.argtypes = [vp, C.POINTER(i32)]
+    L.cmx_sweep_fused_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
@@ -408,9 +409,15 @@ class State:
         check(lib().cmx_sweep_info(self._h, name, 32, C.byref(b), C.byref(f), C.byref(nc), S, C.byref(rk)))
         nl = C.c_int32()
         check(lib().cmx_sweep_launches(self._h, C.byref(nl)))
+        fu, ls, fb = C.c_int32(), C.c_int32(), C.c_int32()
+        try:  # needs a device and conditions on every replica
+            check(lib().cmx_sweep_fused_info(self._h, C.byref(fu), C.byref(ls), C.byref(fb)))
+        except CmxError:
+            pass
         return dict(evaluator=name.value.decode(), bytes_per_step=b.value, flops_per_step=f.value,
                     n_colours=nc.value, colour_strides=tuple(S), range_k=rk.value,
-                    launches_per_sweep=nl.value)
+                    launches_per_sweep=nl.value, fused=bool(fu.value), fused_layers_per_slice=ls.value,
+                    fused_blocks=fb.value)
 
     def metropolis_sequential(self, mode: int, n_steps: int, seed: int, log_cap: int = 0,
                               replica: int = 0) -> dict:

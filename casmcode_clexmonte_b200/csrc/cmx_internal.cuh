@@ -76,7 +76,7 @@ struct cmx_tables {
 struct FastDiv {
   uint32_t d, m;
 };
-static inline FastDiv make_fastdiv(uint32_t d) {
+__host__ __device__ static inline FastDiv make_fastdiv(uint32_t d) {
   FastDiv f;
   f.d = d;
   f.m = (d <= 1) ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / d);
@@ -119,6 +119,14 @@ struct SweepPlan {
   uint32_t *d_tab = nullptr;      // [replica][n_tab] threshold(15 bit)<<9 | 1<<8 | proposed code
   uint32_t *d_thr_lo = nullptr;   // [replica][n_tab] low 32 bits of the threshold (tie break)
   double *d_dEpot = nullptr;      // [replica][n_tab] dE - exch
+  bool row16 = false;             // warp-row kernel usable (N0/16 a power of two <= 32)
+  int32_t n_tab24 = 0;            // entries of its acceptance table
+  uint32_t *d_tab24 = nullptr;    // [replica][n_tab24] thr16 | proposed code << 16
+  bool pdl_ok = false;            // tables untouched since the last sweep launch
+  uint32_t *d_stamps = nullptr;   // fused sweep kernel: updates received per row [replica][N2][N1]
+  uint32_t stamp_base = 0;        // value of every stamp between calls
+  unsigned long long *d_fused_timeout = nullptr;
+  int fused_capacity = -1;        // co-resident blocks of the fused kernel (0: unusable)
   bool thr_dirty = true;
   // fast energy (cmx_energy.cu): per-cell energy as a function of (occupant,
   // species counts over the cell's "forward" neighbors), same byte-lane counting

@@ -39,6 +39,9 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_tab);
   cudaFree(p.d_thr_lo);
   cudaFree(p.d_dEpot);
+  cudaFree(p.d_tab24);
+  cudaFree(p.d_stamps);
+  cudaFree(p.d_fused_timeout);
   cudaFree(p.d_part_acc);
   cudaFree(p.d_part_dE);
   cudaFree(p.d_e_lut);
@@ -174,15 +177,10 @@ struct Pair16Args {
   unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
   unsigned long long wait_epoch, signal_epoch, blocks_target;
   int push;
-  // staged variant (k_sweep_pair16s): a tile = RB target rows of one layer; its
-  // source rows are copied into shared memory by bulk async copies, layer block
-  // dz = -1, 0, +1 holds rows [first target row + dy_min[dz], last + dy_max[dz]]
-  uint32_t n_tiles, tiles_per_layer;  // tiles_per_layer = J / RB
-  FastDiv divT;                       // by tiles_per_layer
-  uint32_t blk_rows[3];               // rows of each layer block (0 = layer not needed)
-  uint32_t blk_off[3];                // byte offset of each layer block inside a stage
-  int32_t dy_min[3];
-  uint32_t stage_bytes;
+  // warp-row variant (k_sweep_row16): rows [row_begin, row_begin + n_rows) of the
+  // colour's row sequence (row = kk * J + jj), 32/W rows per warp tile
+  const uint32_t *tab24;  // [replica][CMX_TAB24]
+  uint32_t logW, row_begin, n_tiles;
 };
 
 __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p) {
@@ -232,9 +230,10 @@ __device__ __forceinline__ void pair16_update(const uint32_t (&cnt)[4], uint32_t
   for (int i = 0; i < 4; ++i) {
     const uint32_t R = ph.c[i];
     // occupant | alt << 2 in the target lanes, zero elsewhere (code & 3 = occupant)
-    const uint32_t altw = (NOCC == 3) ? ((R & 0x00010001u) << (CX ? 10 : 2)) : 0u;
+    const uint32_t altw = (NOCC == 3) ? ((R >> (CX ? 5 : 13)) & (CX ? 0x04000400u : 0x00040004u)) : 0u;
     const uint32_t SA = (C[i] & lanes) | altw;
-    const uint32_t Rw = R | 0x00010001u;
+    // (u15 << 1 | 1) in both halves: bit 15 (alt) of the low field lands on the forced bit 16
+    const uint32_t Rw = (R << 1) | 0x00010001u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int b = 2 * h + CX;  // byte of the word
@@ -281,10 +280,10 @@ __device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], const uint
     for (int h = 0; h < 2; ++h) {
       const int b = 2 * h + CX;
       const uint32_t field = h ? (R >> 16) : (R & 0xFFFFu);
-      const uint32_t sa = ((C0[i] >> (8 * b)) & 3u) | ((NOCC == 3) ? ((field & 1u) << 2) : 0u);
+      const uint32_t sa = ((C0[i] >> (8 * b)) & 3u) | ((NOCC == 3) ? ((field >> 15) << 2) : 0u);
       const uint32_t idx = ((cnt[i] >> (8 * b)) & 0xFFu) | (sa << 8);
       const uint32_t e = lds_u32(tab + 4u * idx);
-      if ((field | 1u) != (e >> 8)) continue;
+      if ((((field & 0x7FFFu) << 1) | 1u) != (e >> 8)) continue;
       const int q = 2 * i + h;  // target site of the chunk, 0..7
       const uint32_t w32 = (q < 4) ? lo0.c[q & 3] : lo1.c[q & 3];
       if (w32 < thr_lo[idx]) {
@@ -519,314 +518,7 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
 }
 
 
-// ---------------------------------------------------------------------------
-// staged variant: the rows a tile needs are brought into shared memory with bulk
-// asynchronous copies (cp.async.bulk, completion on an mbarrier), double
-// buffered -- tile i+1 is in flight while tile i is computed.  The per-thread
-// global address arithmetic (periodic wraps, 64-bit adds for 12 loads) is gone:
-// every thread reads its 16-byte chunks and side words at loop-invariant
-// shared-memory offsets; the wraps are resolved once per ROW by the thread that
-// issues the row's copy.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(mbar)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(mbar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u32v(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
-
-// Warp-specialised: warps 0-7 (256 threads) compute, warp 8 is the producer that
-// issues the bulk copies of tile i+STAGES-1 while tile i is computed.
-//   full[s]   producer -> consumers: the stage's bytes have landed (complete_tx)
-//   empty[s]  consumers -> producer: every compute warp has read the stage
-#define CMX_STAGES 2
-template <int NOCC, uint32_t MASK_CT, bool ACCUM>
-__global__ void __launch_bounds__(288, 3) k_sweep_pair16s(Pair16Args a) {
-  constexpr int NTAB = CMX_TAB16(NOCC);
-  constexpr uint32_t TAB_BYTES = NTAB * 4 + (ACCUM ? NTAB * 8 : 0);
-  // dynamic shared memory: [tables][stage 0][stage 1]...
-  extern __shared__ __align__(128) unsigned char sh_dyn[];
-  __shared__ __align__(8) unsigned long long sh_mbar[2 * CMX_STAGES];  // full[], empty[]
-  __shared__ uint8_t sh_x[2][256];
-  __shared__ long long sh_acc[8];
-  __shared__ double sh_sum[8];
-  const uint32_t r = blockIdx.y;
-  if (threadIdx.x < 256) {
-    const uint32_t *gt = a.tab + (size_t)r * NTAB;
-    const double *ge = a.dEpot + (size_t)r * NTAB;
-    uint32_t *st = reinterpret_cast<uint32_t *>(sh_dyn);
-    double *se = reinterpret_cast<double *>(sh_dyn + NTAB * 4);
-    for (int q = threadIdx.x; q < NTAB; q += 256) {
-      st[q] = gt[q];
-      if (ACCUM) se[q] = ge[q];
-    }
-  }
-  const uint32_t tab = (uint32_t)__cvta_generic_to_shared(sh_dyn);
-  const uint32_t stage0 = tab + ((TAB_BYTES + 127u) & ~127u);
-  const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&sh_mbar[0]);
-  const uint32_t empty0 = full0 + 8 * CMX_STAGES;
-  const Geom &g = a.g;
-  int8_t *base = a.occ + (size_t)r * g.rep_stride;
-  const uint32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
-  const uint32_t layer = N0 * N1;
-  const bool halo = g.halo != 0;
-  const uint32_t rows_tot = a.blk_rows[0] + a.blk_rows[1] + a.blk_rows[2];
-  const uint32_t n_issuers = (a.blk_rows[0] ? 1u : 0u) + (a.blk_rows[1] ? 1u : 0u) + (a.blk_rows[2] ? 1u : 0u);
-  (void)rows_tot;
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < CMX_STAGES; ++q) {
-      mbar_init(full0 + 8 * q, n_issuers);
-      mbar_init(empty0 + 8 * q, 8);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (threadIdx.x >= 256) {
-    // ------------------------------------------------------------- producer warp
-    const uint32_t lane = threadIdx.x - 256;
-    if (a.wait_epoch && lane == 0) {
-      // acquire: the neighbours' pushes into my ghost layers precede their flag
-      const long long t0 = clock64();
-      while (ld_sys(a.my_sig + 0) < a.wait_epoch || ld_sys(a.my_sig + 1) < a.wait_epoch) {
-        if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour is gone
-          a.my_sig[3] = 1ull;
-          break;
-        }
-        __nanosleep(100);
-      }
-    }
-    __syncwarp();
-    // lane dzi copies layer block dzi: its rows are consecutive rows of one layer,
-    // i.e. ONE contiguous range of global memory -- two when the range wraps
-    // around the periodic j axis (first / last tile of a layer)
-    const uint32_t my_rows = (lane < 3) ? a.blk_rows[lane] : 0u;
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t stage = it % CMX_STAGES, use = it / CMX_STAGES;
-      if (use > 0) mbar_wait(empty0 + 8 * stage, (use - 1) & 1u);  // consumers drained the stage
-      if (my_rows == 0) continue;
-      uint32_t kk, tj;
-      fastdivmod(tile, a.divT, kk, tj);
-      const uint32_t k = 2 * kk + a.cz;
-      const uint32_t mbar = full0 + 8 * stage;
-      const uint32_t dst = stage0 + stage * a.stage_bytes + a.blk_off[lane];
-      int kz = (int)k + (int)lane - 1;
-      if (!halo) kz = (kz < 0) ? kz + (int)N2 : ((kz >= (int)N2) ? kz - (int)N2 : kz);
-      const int8_t *lay = base + (size_t)(kz + g.halo) * layer;
-      int jr0 = (int)(2 * tj * a.RB + a.cy) + a.dy_min[lane];  // first row of the block
-      mbar_expect_tx(mbar, my_rows * N0);
-      uint32_t head = 0;  // rows before the wrap
-      if (jr0 < 0) {
-        head = (uint32_t)(-jr0);
-        jr0 += (int)N1;
-      } else if ((uint32_t)jr0 + my_rows > N1) {
-        head = N1 - (uint32_t)jr0;
-      }
-      if (head >= my_rows) head = 0;  // (a range of exactly the remaining rows does not wrap)
-      if (head) {
-        bulk_g2s(dst, lay + (size_t)jr0 * N0, head * N0, mbar);
-        bulk_g2s(dst + head * N0, lay, (my_rows - head) * N0, mbar);
-      } else {
-        if ((uint32_t)jr0 >= N1) jr0 -= (int)N1;
-        bulk_g2s(dst, lay + (size_t)jr0 * N0, my_rows * N0, mbar);
-      }
-    }
-    return;
-  }
-
-  // --------------------------------------------------------------- compute warps
-  uint32_t ff;
-  asm volatile("mov.u32 %0, 0xFF;" : "=r"(ff));
-  const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
-  uint32_t n_acc = 0;
-  double e_sum = 0.0;
-  uint32_t rl, c;
-  fastdivmod(threadIdx.x, a.divW, rl, c);
-  const bool lane_on = rl < a.RB;
-  const uint32_t nxt = (c == a.W - 1) ? threadIdx.x - (a.W - 1) : threadIdx.x + 1;
-  const uint32_t x0 = 16 * c;
-  const uint32_t xl = (x0 == 0) ? N0 - 4 : x0 - 4;     // word holding byte x0-1
-  const uint32_t xr = (x0 + 16 == N0) ? 0u : x0 + 16;  // word holding byte x0+16
-  const uint32_t mc = (mask >> 12) & 7u;
-  // loop-invariant part of this thread's shared-memory addresses
-  const uint32_t row2 = 2 * rl * N0;
-  uint32_t it = 0;
-  for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-    const uint32_t stage = it % CMX_STAGES, use = it / CMX_STAGES;
-    mbar_wait(full0 + 8 * stage, use & 1u);
-    const uint32_t sbase = stage0 + stage * a.stage_bytes + row2;
-    uint32_t C[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0};
-    uint32_t cl = 0;
-    uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
-    uint32_t sm = 0, sp = 0;
-    if (lane_on) {
-#pragma unroll
-      for (int dz = -1; dz <= 1; ++dz) {
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-          const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
-          const bool center = (dz == 0 && dy == 0);
-          if (m3 == 0 && !center) continue;
-          const uint32_t rowa = sbase + a.blk_off[dz + 1] + (uint32_t)(dy - a.dy_min[dz + 1]) * N0;
-          const uint4 ch = lds_u128(rowa + x0);
-          if (center) {
-            C[0] = ch.x;
-            C[1] = ch.y;
-            C[2] = ch.z;
-            C[3] = ch.w;
-            if (m3 & 1u) cl = lds_u32v(rowa + xl);
-            continue;
-          }
-          if (m3 & 2u) {
-            A0[0] += ch.x;
-            A0[1] += ch.y;
-            A0[2] += ch.z;
-            A0[3] += ch.w;
-          }
-          if (m3 & 1u) {
-            Am[0] += ch.x;
-            Am[1] += ch.y;
-            Am[2] += ch.z;
-            Am[3] += ch.w;
-            sm += lds_u32v(rowa + xl);
-          }
-          if (m3 & 4u) {
-            Ap[0] += ch.x;
-            Ap[1] += ch.y;
-            Ap[2] += ch.z;
-            Ap[3] += ch.w;
-            sp += lds_u32v(rowa + xr);
-          }
-        }
-      }
-    }
-    // this warp is done with the stage (mbarrier.arrive releases the loads above)
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(empty0 + 8 * stage);
-    uint32_t off_c = 0, gid = 0, k_row = 0;
-    if (lane_on) {
-      uint32_t kk, tj;
-      fastdivmod(tile, a.divT, kk, tj);
-      const uint32_t jj = tj * a.RB + rl;
-      const uint32_t j = 2 * jj + a.cy, k = 2 * kk + a.cz;
-      k_row = k;
-      off_c = ((k + g.halo) * N1 + j) * N0 + x0;
-      gid = ((k + (uint32_t)a.k_offset) * N1 + j) * a.W + c;
-      T[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
-      T[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
-      T[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
-      T[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
-      uint32_t cnt[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        cnt[i] = T[i];
-        if (mc & 1u) cnt[i] += __funnelshift_l(i ? C[i - 1] : cl, C[i], 8);
-        if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : 0u, 8);
-      }
-      const uint32_t ctr0 = a.ctr_hi;
-      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr0, a.rk);
-      bool tie = false;
-      pair16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
-      if (tie)
-        pair16_ties<0, NOCC, ACCUM>(cnt, reinterpret_cast<const uint4 *>(base + off_c), C, ph, tab,
-                                    a.thr_lo + (size_t)r * NTAB, gid, r, a.sweep_lo, ctr0, a.k0, a.k1,
-                                    n_acc, e_sum);
-      sh_x[it & 1][threadIdx.x] = (uint8_t)(C[0] & 0xFFu);
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // compute warps only
-    if (lane_on) {
-      const uint32_t nb = sh_x[it & 1][nxt];
-      uint32_t cnt[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        cnt[i] = T[i];
-        if (mc & 1u) cnt[i] += __funnelshift_l(i ? C[i - 1] : 0u, C[i], 8);
-        if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : nb, 8);
-      }
-      const uint32_t ctr1 = a.ctr_hi | 0x100u;
-      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr1, a.rk);
-      bool tie = false;
-      pair16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
-      if (tie)
-        pair16_ties<1, NOCC, ACCUM>(cnt, reinterpret_cast<const uint4 *>(base + off_c), C, ph, tab,
-                                    a.thr_lo + (size_t)r * NTAB, gid, r, a.sweep_lo, ctr1, a.k0, a.k1,
-                                    n_acc, e_sum);
-      const uint4 out = make_uint4(C[0], C[1], C[2], C[3]);
-      *reinterpret_cast<uint4 *>(base + off_c) = out;
-      if (a.push) {
-        const size_t rep = (size_t)r * g.rep_stride;
-        if (k_row == 0) *reinterpret_cast<uint4 *>(a.peer_dn + rep + off_c + N2 * layer) = out;
-        if (k_row == N2 - 1) *reinterpret_cast<uint4 *>(a.peer_up + rep + off_c - N2 * layer) = out;
-      }
-    }
-  }
-  long long n_acc64 = n_acc;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    n_acc64 += __shfl_down_sync(0xffffffffu, n_acc64, o);
-    e_sum += __shfl_down_sync(0xffffffffu, e_sum, o);
-  }
-  const int wid = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) {
-    sh_acc[wid] = n_acc64;
-    sh_sum[wid] = e_sum;
-  }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (threadIdx.x == 0) {
-    long long A = 0;
-    double E = 0.0;
-    for (int w = 0; w < 8; ++w) {
-      A += sh_acc[w];
-      E += sh_sum[w];
-    }
-    size_t slot = (size_t)r * a.part_stride + blockIdx.x;
-    a.part_acc[slot] += A;
-    a.part_dE[slot] += E;
-    if (a.push) {
-      __threadfence_system();
-      const unsigned long long done = atomicAdd(a.my_sig + 2, 1ull) + 1ull;
-      if (a.signal_epoch && done == a.blocks_target) {
-        __threadfence_system();
-        st_sys(a.peer_sig_dn + 1, a.signal_epoch);
-        st_sys(a.peer_sig_up + 0, a.signal_epoch);
-      }
-    }
-  }
-}
+#include "cmx_sweep_row.cuh"
 
 // ---------------------------------------------------------------------------
 // generic sweep kernel: one site per thread
@@ -886,8 +578,8 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
       const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr, a.k0, a.k1);
       const uint32_t R = ph.c[x >> 2];
       const uint32_t field = (x & 2u) ? (R >> 16) : (R & 0xFFFFu);
-      alt = (nocc == 3) ? (int)(field & 1u) : 0;
-      u_hi = field >> 1;
+      alt = (nocc == 3) ? (int)(field >> 15) : 0;
+      u_hi = field & 0x7FFFu;
       const Philox lo = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr | ((q < 4) ? 1u : 2u), a.k0, a.k1);
       u_lo = lo.c[q & 3];
     } else {
@@ -1163,6 +855,18 @@ int cmx_plan_sweep(cmx_state *s) {
     CMX_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(uint32_t) * P.n_tab * s->n_replicas));
     CMX_CUDA(cudaMalloc((void **)&P.d_thr_lo, sizeof(uint32_t) * P.n_tab * s->n_replicas));
     CMX_CUDA(cudaMalloc((void **)&P.d_dEpot, sizeof(double) * P.n_tab * s->n_replicas));
+    const int W = s->g.N0 / 16;
+    P.row16 = (W <= 32 && (W & (W - 1)) == 0);
+    P.n_tab24 = CMX_TAB24(P.nocc);
+    CMX_CUDA(cudaMalloc((void **)&P.d_tab24, sizeof(uint32_t) * P.n_tab24 * s->n_replicas));
+    if (P.row16 && !s->g.halo) {
+      const size_t n_st = (size_t)s->n_replicas * s->g.N1 * s->g.N2;
+      CMX_CUDA(cudaMalloc((void **)&P.d_stamps, sizeof(uint32_t) * n_st));
+      CMX_CUDA(cudaMemset(P.d_stamps, 0, sizeof(uint32_t) * n_st));
+      CMX_CUDA(cudaMalloc((void **)&P.d_fused_timeout, sizeof(unsigned long long)));
+      CMX_CUDA(cudaMemset(P.d_fused_timeout, 0, sizeof(unsigned long long)));
+      P.stamp_base = 0;
+    }
     P.pair_lut = true;
     P.rng16 = true;  // the generic evaluator on this state mirrors the pair16 random bits
     // per step: z neighbor bytes + own byte read, 1 byte written; the FP64
@@ -1211,53 +915,195 @@ static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool 
 }
 
 template <int NOCC>
-static int launch_pair16s(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum,
-                          size_t dyn_bytes) {
-#define CMX_L16S(M, A)                                                                          \
-  do {                                                                                          \
-    auto kern = k_sweep_pair16s<NOCC, M, A>;                                                    \
-    static bool attr_set = false;                                                               \
-    if (!attr_set) {                                                                            \
-      CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      attr_set = true;                                                                          \
-    }                                                                                           \
-    kern<<<grid, 288, dyn_bytes, st>>>(a);                                                      \
-  } while (0)
+static int launch_row16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if (fcc) {
-    if (accum) CMX_L16S(kMaskFcc1NN, true);
-    else CMX_L16S(kMaskFcc1NN, false);
+    if (accum) CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, kMaskFcc1NN, true>, a));
+    else CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, kMaskFcc1NN, false>, a));
   } else {
-    if (accum) CMX_L16S(0u, true);
-    else CMX_L16S(0u, false);
+    if (accum) CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, 0u, true>, a));
+    else CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, 0u, false>, a));
   }
-#undef CMX_L16S
   return CMX_OK;
 }
 
-// tuning knobs (environment, read once): resident blocks per SM the pair16 kernel
-// is compiled for, and blocks per SM in the grid
+// tuning knobs (environment, read once)
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
-static int pair16_minb() {
+static int pair16_minb() {  // resident blocks per SM k_sweep_pair16 is compiled for
   static int v = env_int("CMX_PAIR16_MINB", 3);
   return v;
 }
-static int pair16_staged() {
-  static int v = env_int("CMX_PAIR16_STAGED", 0);
-  return v;
-}
-static int sweep_grid_per_sm() {
+static int sweep_grid_per_sm() {  // blocks per SM in the grid
   static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 4);
   return v;
 }
+static int sweep_pdl() {  // programmatic dependent launch of consecutive colour passes
+  static int v = env_int("CMX_SWEEP_PDL", 1);
+  return v;
+}
+static int sweep_l2_mb() {  // lattice bytes (MB) a k-slice of the fused sweep kernel may touch
+  static int v = env_int("CMX_SWEEP_L2_MB", 40);
+  return v;
+}
 
-static int sweep_grid_per_sm();
+static bool use_pair(const cmx_state *s) {
+  return s->plan.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC);
+}
+static bool use_row16(const cmx_state *s) {
+  return use_pair(s) && s->plan.row16 && !(s->sweep_flags & CMX_SWEEP_BLOCK_KERNEL);
+}
+
 static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
   int want = (int)((items + 255) / 256);
   int cap = std::max(1, (148 * sweep_grid_per_sm() + n_replicas - 1) / n_replicas);
   return std::max(1, std::min(want, cap));
+}
+
+// acceptance tables (rebuilt when the conditions changed) and the arguments every
+// pair-LUT kernel shares
+static int pair_args(cmx_state *s, uint64_t seed, int64_t sweep, int k_offset, Pair16Args &a) {
+  SweepPlan &P = s->plan;
+  const DevTables &T = s->t->d;
+  const Geom &g = s->g;
+  size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
+  if (P.thr_dirty) {
+    dim3 grid((P.n_tab + 127) / 128, s->n_replicas);
+    k_build_tab16<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.nocc, P.z, T.max_occ, s->d_beta, s->d_exch,
+                                               (int)exs, P.n_tab, P.d_tab, P.d_thr_lo, P.d_dEpot);
+    dim3 grid24((P.n_tab24 + 127) / 128, s->n_replicas);
+    k_build_tab24<<<grid24, 128, 0, s->stream>>>(P.d_tab, P.nocc, P.n_tab, P.n_tab24, P.d_tab24);
+    CMX_CUDA(cudaGetLastError());
+    P.thr_dirty = false;
+    P.pdl_ok = false;
+  }
+  a.occ = s->d_occ;
+  a.g = g;
+  a.mask = P.mask;
+  a.W = g.N0 / 16;
+  a.RB = 256 / a.W;
+  a.divW = make_fastdiv(a.W);
+  a.J = g.N1 / 2;
+  a.divJ = make_fastdiv(a.J);
+  a.n_rows = a.J * (uint32_t)(g.N2 / 2);
+  a.tab = P.d_tab;
+  a.tab24 = P.d_tab24;
+  a.thr_lo = P.d_thr_lo;
+  a.dEpot = P.d_dEpot;
+  a.part_acc = P.d_part_acc;
+  a.part_dE = P.d_part_dE;
+  a.part_stride = (uint32_t)P.part_blocks;
+  a.k0 = (uint32_t)seed;
+  a.k1 = (uint32_t)(seed >> 32);
+  a.rk = philox_key_schedule(a.k0, a.k1);
+  a.sweep_lo = (uint32_t)sweep;
+  a.ctr_hi = 0;
+  a.cy = a.cz = 0;
+  a.k_offset = k_offset;
+  a.logW = 0;
+  while ((1u << a.logW) < a.W) ++a.logW;
+  a.row_begin = 0;
+  a.n_tiles = 0;
+  a.push = (s->p2p && g.halo) ? 1 : 0;
+  a.peer_dn = s->peer_occ_dn;
+  a.peer_up = s->peer_occ_up;
+  a.my_sig = s->d_sig;
+  a.peer_sig_dn = s->peer_sig_dn;
+  a.peer_sig_up = s->peer_sig_up;
+  a.wait_epoch = a.signal_epoch = a.blocks_target = 0;
+  return CMX_OK;
+}
+
+// ---- fused whole-sweep kernel (k_sweep_row16_fused) ------------------------------
+template <int NOCC>
+static const void *fused_kernel(bool fcc, bool accum) {
+  if (fcc) return accum ? (const void *)k_sweep_row16_fused<NOCC, kMaskFcc1NN, true>
+                        : (const void *)k_sweep_row16_fused<NOCC, kMaskFcc1NN, false>;
+  return accum ? (const void *)k_sweep_row16_fused<NOCC, 0u, true>
+               : (const void *)k_sweep_row16_fused<NOCC, 0u, false>;
+}
+
+// grid of the fused kernel: blocks per replica, or 0 if the replicas do not fit a
+// co-resident grid (the stamp protocol needs every warp resident)
+static int fused_blocks(cmx_state *s, const void *kern) {
+  SweepPlan &P = s->plan;
+  if (P.fused_capacity < 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess) per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    P.fused_capacity = coop ? std::min(per_sm, sweep_grid_per_sm()) * sms : 0;
+  }
+  int per = P.fused_capacity / std::max(1, s->n_replicas);
+  return std::min(per, P.part_blocks);
+}
+
+// colour layers per k-slice: a slice spans ~1.5x the tiles in flight (dependencies are
+// then normally satisfied long before they are needed), within the L2 budget
+static uint32_t fused_slice_layers(const cmx_state *s, int gx) {
+  const uint32_t W = (uint32_t)s->g.N0 / 16, rpw = 32u / W, J = (uint32_t)s->g.N1 / 2;
+  const uint32_t tpl = (J + rpw - 1) / rpw, n_kk = (uint32_t)(s->g.N2 / 2);
+  static int slice_env = env_int("CMX_SWEEP_SLICE_LAYERS", 0);
+  if (slice_env > 0) return std::min<uint32_t>((uint32_t)slice_env, n_kk);
+  uint32_t L = (uint32_t)std::ceil(1.5 * 8.0 * gx / tpl);
+  const double per_layer = (double)s->g.layer * s->n_replicas;
+  const uint32_t L_l2 =
+      (uint32_t)std::max(1.0, std::floor((sweep_l2_mb() * 1048576.0 / per_layer - 1.0) / 2.0));
+  return std::max(1u, std::min(std::min(L, L_l2), n_kk));
+}
+
+static bool use_fused(const cmx_state *s) {
+  return use_row16(s) && !s->g.halo && s->plan.d_stamps && !(s->sweep_flags & CMX_SWEEP_NO_FUSION);
+}
+
+// n_sweeps whole sweeps in one cooperative launch; returns -1 if not applicable
+static int sweep_fused(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps) {
+  SweepPlan &P = s->plan;
+  Pair16Args a;
+  int rc = pair_args(s, seed, first_sweep, 0, a);
+  if (rc) return rc;
+  const bool fcc = (P.mask == kMaskFcc1NN);
+  const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
+  const void *kern = (P.nocc == 3) ? fused_kernel<3>(fcc, accum) : fused_kernel<2>(fcc, accum);
+  const int gx = fused_blocks(s, kern);
+  if (gx < 1) return -1;
+  FusedArgs f;
+  f.stamps = P.d_stamps;
+  f.timeout = P.d_fused_timeout;
+  f.n_kk = (uint32_t)(s->g.N2 / 2);
+  const uint32_t rpw = 32u / a.W;
+  f.tpl = (a.J + rpw - 1) / rpw;
+  const uint32_t L = fused_slice_layers(s, gx);
+  f.L = L;
+  const uint32_t n_s = (f.n_kk + L - 1) / L;
+  f.n_slices = n_s + ((f.n_kk % L == 0) ? 1 : 0);  // closing slice: the last odd layer
+  f.n_tiles_sweep = f.n_slices * 4 * L * f.tpl;
+  for (int64_t done = 0; done < n_sweeps;) {
+    // stamps are 32-bit update counts compared with wrap-around arithmetic: bound a launch
+    const int64_t n = std::min<int64_t>(n_sweeps - done, 1 << 20);
+    f.stamp_base = P.stamp_base;
+    f.n_sweeps = (uint32_t)n;
+    f.first_sweep = (uint64_t)(first_sweep + done);
+    void *args[2] = {&a, &f};
+    CMX_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gx, s->n_replicas), dim3(256), args, 0, s->stream));
+    P.stamp_base += (uint32_t)n;
+    done += n;
+  }
+  P.pdl_ok = false;
+  return CMX_OK;
 }
 
 // one pass over the colours whose k-colour equals kgroup (or all if < 0)
@@ -1267,114 +1113,58 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   const DevTables &T = s->t->d;
   const Geom &g = s->g;
   size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
-  if (P.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) {
-    if (P.thr_dirty) {
-      dim3 grid((P.n_tab + 127) / 128, s->n_replicas);
-      k_build_tab16<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.nocc, P.z, T.max_occ, s->d_beta, s->d_exch,
-                                                 (int)exs, P.n_tab, P.d_tab, P.d_thr_lo, P.d_dEpot);
-      CMX_CUDA(cudaGetLastError());
-      P.thr_dirty = false;
-    }
+  if (use_pair(s)) {
     Pair16Args a;
-    a.occ = s->d_occ;
-    a.g = g;
-    a.mask = P.mask;
-    a.W = g.N0 / 16;
-    a.RB = 256 / a.W;
-    a.divW = make_fastdiv(a.W);
-    a.J = g.N1 / 2;
-    a.divJ = make_fastdiv(a.J);
-    a.n_rows = a.J * (uint32_t)(g.N2 / 2);
-    a.tab = P.d_tab;
-    a.thr_lo = P.d_thr_lo;
-    a.dEpot = P.d_dEpot;
-    a.part_acc = P.d_part_acc;
-    a.part_dE = P.d_part_dE;
-    a.part_stride = (uint32_t)P.part_blocks;
-    a.k0 = (uint32_t)seed;
-    a.k1 = (uint32_t)(seed >> 32);
-    a.rk = philox_key_schedule(a.k0, a.k1);
-    a.sweep_lo = (uint32_t)sweep;
-    a.k_offset = k_offset;
+    int rc = pair_args(s, seed, sweep, k_offset, a);
+    if (rc) return rc;
     dim3 grid(P.part_blocks, s->n_replicas);
     const bool fcc = (P.mask == kMaskFcc1NN);
     const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
-    a.push = (s->p2p && g.halo) ? 1 : 0;
-    a.peer_dn = s->peer_occ_dn;
-    a.peer_up = s->peer_occ_up;
-    a.my_sig = s->d_sig;
-    a.peer_sig_dn = s->peer_sig_dn;
-    a.peer_sig_up = s->peer_sig_up;
-    // staged variant: tiles of RB whole target rows of one layer
-    bool staged = pair16_staged() && (a.J % a.RB == 0) && !(s->sweep_flags & CMX_SWEEP_NO_STAGING);
-    if (s->sweep_flags & CMX_SWEEP_FORCE_STAGING) {
-      // any box: tiles of the largest number of rows that divides the rows of a layer
-      uint32_t rb = std::min(a.RB, a.J);
-      while (a.J % rb) --rb;
-      a.RB = rb;
-      staged = true;
-    }
-    size_t dyn_bytes = 0;
-    if (staged) {
-      a.tiles_per_layer = a.J / a.RB;
-      a.divT = make_fastdiv(a.tiles_per_layer);
-      a.n_tiles = a.tiles_per_layer * (uint32_t)(g.N2 / 2);
-      uint32_t off = 0;
-      for (int dz = -1; dz <= 1; ++dz) {
-        int lo = 2, hi = -2;
-        for (int dy = -1; dy <= 1; ++dy)
-          if (((P.mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u) || (dz == 0 && dy == 0)) {
-            lo = std::min(lo, dy);
-            hi = std::max(hi, dy);
-          }
-        a.blk_off[dz + 1] = off;
-        if (hi < lo) {
-          a.blk_rows[dz + 1] = 0;
-          a.dy_min[dz + 1] = 0;
-        } else {
-          a.blk_rows[dz + 1] = 2 * (a.RB - 1) + 1 + (uint32_t)(hi - lo);
-          a.dy_min[dz + 1] = lo;
-          off += a.blk_rows[dz + 1] * (uint32_t)g.N0;
-        }
+    const bool row16 = use_row16(s);
+    // one launch: colour (cy,cz), colour layers [kb, ke); first/last of a k-colour
+    // group carry the ring protocol of the fused halo exchange
+    auto launch = [&](int cy, int cz, uint32_t kb, uint32_t ke, bool group_first, bool group_last) -> int {
+      if (ke <= kb) return CMX_OK;
+      a.cy = cy;
+      a.cz = cz;
+      a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
+      dim3 gl = grid;
+      if (row16) {
+        a.row_begin = kb * a.J;
+        a.n_rows = (ke - kb) * a.J;
+        const uint32_t rpw = 32u / a.W;
+        a.n_tiles = (a.n_rows + rpw - 1) / rpw;
+        gl.x = std::min<uint32_t>((uint32_t)P.part_blocks, (a.n_tiles + 7) / 8);
       }
-      a.stage_bytes = (off + 127u) & ~127u;
-      const size_t tab_bytes = (size_t)P.n_tab * 4 + (accum ? (size_t)P.n_tab * 8 : 0);
-      dyn_bytes = ((tab_bytes + 127) & ~(size_t)127) + CMX_STAGES * (size_t)a.stage_bytes;
-      if (dyn_bytes > 200 * 1024) staged = false;
-    }
-    if (staged) {
-      // persistent blocks: as many as fit, never more than tiles
-      int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (220 * 1024) / (dyn_bytes + 2048)));
-      int want = std::max(1, (148 * per_sm + s->n_replicas - 1) / s->n_replicas);
-      grid.x = (unsigned)std::min<uint32_t>(a.n_tiles, (uint32_t)std::min(want, P.part_blocks));
-    }
-    for (int cz = 0; cz < 2; ++cz) {
+      a.wait_epoch = a.signal_epoch = a.blocks_target = 0;
+      if (a.push) {
+        // one k-colour group = one step of the ring protocol: wait for the
+        // neighbours' previous step before the first launch, publish after the last
+        if (group_first) a.wait_epoch = s->epoch;
+        s->blocks_done += (unsigned long long)gl.x * gl.y;
+        a.blocks_target = s->blocks_done;
+        if (group_last) a.signal_epoch = ++s->epoch;
+      }
+      if (row16) {
+        const bool pdl = sweep_pdl() && P.pdl_ok;
+        int rc = (P.nocc == 3) ? launch_row16<3>(a, gl, s->stream, fcc, accum, pdl)
+                               : launch_row16<2>(a, gl, s->stream, fcc, accum, pdl);
+        if (rc) return rc;
+        P.pdl_ok = true;
+      } else if (P.nocc == 3) {
+        if (pair16_minb() >= 4) launch_pair16<3, 4>(a, grid, s->stream, fcc, accum);
+        else launch_pair16<3, 3>(a, grid, s->stream, fcc, accum);
+      } else {
+        launch_pair16<2, 3>(a, grid, s->stream, fcc, accum);
+      }
+      return CMX_OK;
+    };
+    const uint32_t n_kk = (uint32_t)(g.N2 / 2);
+    for (int cz = 0; cz < 2 && !rc; ++cz) {
       if (kgroup >= 0 && cz != kgroup) continue;
-      for (int cy = 0; cy < 2; ++cy) {
-        a.cy = cy;
-        a.cz = cz;
-        a.wait_epoch = a.signal_epoch = a.blocks_target = 0;
-        if (a.push) {
-          // one k-colour group = one step of the ring protocol: wait for the
-          // neighbours' previous step before the first launch, publish after the last
-          if (cy == 0) a.wait_epoch = s->epoch;
-          s->blocks_done += (unsigned long long)grid.x * grid.y;
-          a.blocks_target = s->blocks_done;
-          if (cy == 1) a.signal_epoch = ++s->epoch;
-        }
-        a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
-        if (staged) {
-          int rc = (P.nocc == 3) ? launch_pair16s<3>(a, grid, s->stream, fcc, accum, dyn_bytes)
-                                 : launch_pair16s<2>(a, grid, s->stream, fcc, accum, dyn_bytes);
-          if (rc) return rc;
-        } else if (P.nocc == 3) {
-          if (pair16_minb() >= 4) launch_pair16<3, 4>(a, grid, s->stream, fcc, accum);
-          else launch_pair16<3, 3>(a, grid, s->stream, fcc, accum);
-        } else {
-          launch_pair16<2, 3>(a, grid, s->stream, fcc, accum);
-        }
-      }
+      for (int cy = 0; cy < 2 && !rc; ++cy) rc = launch(cy, cz, 0, n_kk, cy == 0, cy == 1);
     }
+    if (rc) return rc;
     CMX_CUDA(cudaGetLastError());
     return CMX_OK;
   }
@@ -1441,7 +1231,12 @@ static int sweep_prepare(cmx_state *s, const char *who) {
   SweepPlan &P = s->plan;
   uint32_t items;
   int blocks;
-  if (P.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) {
+  if (use_row16(s)) {
+    // one warp iteration = 32 chunks of whole rows of one (cy,cz) colour
+    uint32_t W = s->g.N0 / 16, rpw = 32 / W;
+    uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
+    items = (n_rows + rpw - 1) / rpw * 32;
+  } else if (use_pair(s)) {
     // one block iteration = RB whole rows of one (cy,cz) colour
     uint32_t W = s->g.N0 / 16, RB = 256 / W;
     uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
@@ -1463,8 +1258,8 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
-  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_NO_STAGING |
-                         CMX_SWEEP_FORCE_STAGING))
+  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_BLOCK_KERNEL |
+                         CMX_SWEEP_NO_FUSION))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;  // the grid may change with the evaluator
@@ -1492,10 +1287,17 @@ extern "C" int cmx_counters_read(cmx_state *s, cmx_counters *counters) {
   CMX_CUDA(cudaGetLastError());
   CMX_CUDA(cudaMemcpyAsync(counters, s->d_counters, sizeof(cmx_counters) * s->n_replicas,
                            cudaMemcpyDeviceToHost, s->stream));
+  unsigned long long fused_to = 0;
+  if (P.d_fused_timeout)
+    CMX_CUDA(cudaMemcpyAsync(&fused_to, P.d_fused_timeout, sizeof(fused_to), cudaMemcpyDeviceToHost, s->stream));
   unsigned long long timed_out = 0;
   if (s->p2p)
     CMX_CUDA(cudaMemcpyAsync(&timed_out, s->d_sig + 3, sizeof(timed_out), cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
+  if (fused_to) {
+    cmx_set_error("cmx_counters_read: the fused sweep kernel timed out waiting for a row stamp (grid not co-resident?)");
+    return CMX_ERR_CUDA;
+  }
   if (timed_out) {
     cmx_set_error("cmx_counters_read: a ring neighbour did not reach the expected epoch (halo wait timed out)");
     return CMX_ERR_CUDA;
@@ -1509,7 +1311,13 @@ extern "C" int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
   if (rc) return rc;
   if (n_sweeps < 0) return invalid("cmx_sgc_sweep: n_sweeps < 0");
   if (s->g.halo) return invalid("cmx_sgc_sweep: slab states are driven by cmx_sgc_sweep_kgroup");
-  for (int64_t w = 0; w < n_sweeps; ++w) {
+  bool fused = false;
+  if (use_fused(s) && n_sweeps > 0) {
+    rc = sweep_fused(s, seed, first_sweep, n_sweeps);
+    if (rc > 0) return rc;
+    fused = (rc == CMX_OK);
+  }
+  for (int64_t w = 0; w < n_sweeps && !fused; ++w) {
     rc = sweep_once(s, seed, first_sweep + w, -1, 0);
     if (rc) return rc;
   }
@@ -1541,7 +1349,7 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
     cmx_set_error("cmx_sweep_info: no sweep plan");
     return CMX_ERR_STATE;
   }
-  const char *nm = (s->plan.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) ? "pair_lut" : "generic";
+  const char *nm = use_pair(s) ? "pair_lut" : "generic";
   if (name && name_cap) {
     std::strncpy(name, nm, name_cap - 1);
     name[name_cap - 1] = 0;
@@ -1555,13 +1363,30 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
   return CMX_OK;
 }
 
+extern "C" int cmx_sweep_fused_info(cmx_state *s, int32_t *fused, int32_t *layers_per_slice,
+                                    int32_t *blocks) {
+  int rc = sweep_prepare(s, "cmx_sweep_fused_info");
+  if (rc) return rc;
+  int gx = 0;
+  if (use_fused(s)) {
+    SweepPlan &P = s->plan;
+    const bool fcc = (P.mask == kMaskFcc1NN);
+    const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
+    gx = fused_blocks(s, (P.nocc == 3) ? fused_kernel<3>(fcc, accum) : fused_kernel<2>(fcc, accum));
+  }
+  if (fused) *fused = gx >= 1;
+  if (layers_per_slice) *layers_per_slice = gx >= 1 ? (int32_t)fused_slice_layers(s, gx) : 0;
+  if (blocks) *blocks = gx;
+  return CMX_OK;
+}
+
 extern "C" int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep) {
   if (!s || !per_sweep) return invalid("cmx_sweep_launches: null argument");
   if (!s->plan.valid) {
     cmx_set_error("cmx_sweep_launches: no sweep plan");
     return CMX_ERR_STATE;
   }
-  const bool pair = s->plan.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC);
-  *per_sweep = pair ? 4 : s->plan.n_colours;
+  // (cmx_sgc_sweep on a fused-eligible state: ONE launch per call, see cmx_sweep_fused_info)
+  *per_sweep = use_pair(s) ? 4 : s->plan.n_colours;
   return CMX_OK;
 }

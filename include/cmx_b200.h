@@ -231,11 +231,13 @@ int cmx_counters_reset(cmx_state *s);
 #define CMX_SWEEP_DE_SUM 1u
 #define CMX_SWEEP_FORCE_GENERIC 2u
 /* pair-LUT kernel variants (the trajectory does not depend on the variant):
- * NO_STAGING reads neighbor rows straight from global memory; FORCE_STAGING uses
- * the shared-memory staged variant (bulk async copies) even where its tiles do
- * not fill a block -- by default it is chosen when they do. */
-#define CMX_SWEEP_NO_STAGING 4u
-#define CMX_SWEEP_FORCE_STAGING 8u
+ * BLOCK_KERNEL forces the block-exchange kernel (k_sweep_pair16: any N0 that is a
+ * multiple of 16) where the warp-row kernel (k_sweep_row16: N0/16 a power of two
+ * <= 32) would be chosen; NO_FUSION makes cmx_sgc_sweep launch one kernel per colour
+ * pass (4 per sweep) instead of the fused whole-call kernel (k_sweep_row16_fused:
+ * periodic warp-row states, row stamps instead of kernel boundaries). */
+#define CMX_SWEEP_BLOCK_KERNEL 4u
+#define CMX_SWEEP_NO_FUSION 8u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* synchronises the state's stream; counters[n_replicas] */
 int cmx_counters_read(cmx_state *s, cmx_counters *counters);
@@ -284,6 +286,10 @@ int cmx_canonical_info(const cmx_state *s, int32_t i, int32_t *strides /*[3]*/,
 /* Kernel launches one full sweep takes with the current evaluator (the
  * pair-LUT kernel fuses both x colours of a row: 4 launches for 8 colours). */
 int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep);
+/* *fused = 1 when cmx_sgc_sweep runs a whole call (all its sweeps) as ONE launch of
+ * the fused kernel on this state (then *layers_per_slice colour layers form a
+ * k-slice of its schedule and *blocks is its co-resident grid per replica). */
+int cmx_sweep_fused_info(cmx_state *s, int32_t *fused, int32_t *layers_per_slice, int32_t *blocks);
 
 /* Occupant bookkeeping needed by the reference-order mode:
  * sublat_to_asym[n_sublat], occ_to_species[n_sublat][max_occ] (-1 padded). */

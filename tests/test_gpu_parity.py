@@ -230,7 +230,7 @@ def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
     b.close()
 
 
-@pytest.mark.parametrize("staging", ["default", "none", "forced"])
+@pytest.mark.parametrize("staging", ["default", "block", "nofusion"])
 @pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1),
                                           ((128, 32, 4), 2)])
 def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas, staging):
@@ -247,7 +247,7 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.4], 3)
         a.set_conditions(500.0, ex2, replica=1)
         b.set_conditions(500.0, ex2, replica=1)
-    variant = {"default": 0, "none": _capi.CMX_SWEEP_NO_STAGING, "forced": _capi.CMX_SWEEP_FORCE_STAGING}[staging]
+    variant = {"default": 0, "block": _capi.CMX_SWEEP_BLOCK_KERNEL, "nofusion": _capi.CMX_SWEEP_NO_FUSION}[staging]
     a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM | variant)
     b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC | _capi.CMX_SWEEP_DE_SUM)
     assert a.sweep_info()["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
@@ -270,6 +270,40 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         assert ca[r].n_accept == cb[r].n_accept and ca[r].dE_sum == 0.0
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("N,n_replicas,n_sweeps", [((512, 512, 512), 1, 6), ((128, 128, 128), 8, 6)])
+def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sweeps):
+    """BASELINE sizes (configs[2]: 512^3; configs[1]: 128^3 replicas with a (mu, T) grid):
+    the fused whole-call kernel, one launch per colour pass, the block-exchange kernel
+    and the generic one-site-per-thread evaluator must leave the SAME occupation and the
+    same acceptance counts.  Only at these sizes are all SMs busy and the row stamps,
+    the overlapped launches and the L2 slices of the fused schedule really exercised."""
+    mu = [0.0, 0.0]
+    variants = {"fused": 0, "nofusion": _capi.CMX_SWEEP_NO_FUSION, "block": _capi.CMX_SWEEP_BLOCK_KERNEL,
+                "generic": _capi.CMX_SWEEP_FORCE_GENERIC}
+    ref_occ, ref_cnt = None, None
+    for name, flags in variants.items():
+        st, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 800.0, mu,
+                                    n_replicas=n_replicas, seed=2026)
+        for r in range(1, n_replicas):
+            exr = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"],
+                                           [-1.0 + 2.0 * r / n_replicas, 0.0], 3)
+            st.set_conditions(400.0 + 200.0 * r, exr, replica=r)
+        st.set_sweep_flags(flags)
+        info = st.sweep_info()
+        assert info["fused"] == (name == "fused")
+        cnt = st.sgc_sweep(n_sweeps - 2, seed=7)
+        cnt2 = st.sgc_sweep(2, seed=7, first_sweep=n_sweeps - 2)   # a second call continues the stamps
+        occ = [st.download_occ(r, dtype=np.int8) for r in range(n_replicas)]
+        acc = [cnt[r].n_accept + cnt2[r].n_accept for r in range(n_replicas)]
+        st.close()
+        if ref_occ is None:
+            ref_occ, ref_cnt = occ, acc
+            continue
+        for r in range(n_replicas):
+            assert (occ[r] == ref_occ[r]).all(), f"{name} vs fused, replica {r}: {(occ[r] != ref_occ[r]).sum()} sites differ"
+        assert acc == ref_cnt, name
 
 
 @pytest.mark.parametrize("N", [(16, 6, 4), (48, 10, 8), (512, 4, 2)])
