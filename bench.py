@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--box", type=int, default=N_BOX)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator, 4 = block kernel, 8 = no fusion)")
+    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator, 4 = block kernel, 8 = fused whole-call kernel)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -914,26 +914,32 @@ static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool 
   }
 }
 
+template <int NOCC, uint32_t MASK, bool ACC>
+static int launch_row16_inst(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
+  auto kern = k_sweep_row16<NOCC, MASK, ACC>;
+  static bool attr_set = false;
+  const size_t bytes = row16_smem_bytes<NOCC>(MASK);
+  if (!attr_set) {
+    CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    attr_set = true;
+  }
+  cfg.dynamicSmemBytes = bytes;
+  CMX_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  return CMX_OK;
+}
 template <int NOCC>
 static int launch_row16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  if (fcc) {
-    if (accum) CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, kMaskFcc1NN, true>, a));
-    else CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, kMaskFcc1NN, false>, a));
-  } else {
-    if (accum) CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, 0u, true>, a));
-    else CMX_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_row16<NOCC, 0u, false>, a));
-  }
-  return CMX_OK;
+  if (fcc) return accum ? launch_row16_inst<NOCC, kMaskFcc1NN, true>(a, cfg) : launch_row16_inst<NOCC, kMaskFcc1NN, false>(a, cfg);
+  return accum ? launch_row16_inst<NOCC, 0u, true>(a, cfg) : launch_row16_inst<NOCC, 0u, false>(a, cfg);
 }
 
 // tuning knobs (environment, read once)
@@ -1066,7 +1072,7 @@ static uint32_t fused_slice_layers(const cmx_state *s, int gx) {
 }
 
 static bool use_fused(const cmx_state *s) {
-  return use_row16(s) && !s->g.halo && s->plan.d_stamps && !(s->sweep_flags & CMX_SWEEP_NO_FUSION);
+  return use_row16(s) && !s->g.halo && s->plan.d_stamps && (s->sweep_flags & CMX_SWEEP_FUSED);
 }
 
 // n_sweeps whole sweeps in one cooperative launch; returns -1 if not applicable
@@ -1259,7 +1265,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
   if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_BLOCK_KERNEL |
-                         CMX_SWEEP_NO_FUSION))
+                         CMX_SWEEP_FUSED))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;  // the grid may change with the evaluator

@@ -183,32 +183,85 @@ __device__ __forceinline__ uint4 row16_load(const int8_t *p) {
 // One tile: every lane updates both x colours of its chunk of row (j, k) and stores
 // it (lanes with on == false redo a valid row without storing).  Returns the
 // chunk's address.
-template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool CG>
-__device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16Lane &L, int32_t j, int32_t k,
-                                              uint32_t sweep_lo, uint32_t ctr_hi, bool on, uint32_t &n_acc,
-                                              double &e_tot) {
-  constexpr int NTAB16 = CMX_TAB16(NOCC);
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+#define CMX_ROW16_SLOT 512u  // bytes between the staged rows of a warp (32 lanes x 16 B)
+
+// address of this lane's chunk of row (j, k) and the byte offsets to the rows around it
+struct Row16Addr {
+  int8_t *pc;
+  int32_t dj[3], dk[3];
+};
+__device__ __forceinline__ Row16Addr row16_addr(const Pair16Args &a, const Row16Lane &L, int32_t j, int32_t k) {
   const Geom &g = a.g;
   const int32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
   const int32_t layer = N0 * N1;
   const bool halo = g.halo != 0;
+  Row16Addr A;
+  A.pc = L.base + ((size_t)((uint32_t)(k + g.halo) * (uint32_t)N1 + (uint32_t)j) * (uint32_t)N0 + 16u * L.c);
+  A.dj[0] = (j == 0) ? (N1 - 1) * N0 : -N0;
+  A.dj[1] = 0;
+  A.dj[2] = (j == N1 - 1) ? -(N1 - 1) * N0 : N0;
+  A.dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : -layer;
+  A.dk[1] = 0;
+  A.dk[2] = (!halo && k == N2 - 1) ? -(N2 - 1) * layer : layer;
+  return A;
+}
+
+// stage the rows tile (j, k) reads into this lane's shared-memory slots (asynchronous
+// 16-byte copies, L2 only): slot n = n-th row of the mask in (dz, dy) order
+template <uint32_t MASK_CT>
+__device__ __forceinline__ void row16_issue(const Pair16Args &a, const Row16Lane &L, int32_t j, int32_t k,
+                                            uint32_t slots) {
+  const uint32_t mask = MASK_CT ? MASK_CT : L.mask;
+  const Row16Addr A = row16_addr(a, L, j, k);
+  uint32_t n = 0;
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
+      if (m3 == 0 && !(dz == 0 && dy == 0)) continue;
+      cp_async16(slots + n * CMX_ROW16_SLOT, A.pc + (ptrdiff_t)(A.dk[dz + 1] + A.dj[dy + 1]));
+      ++n;
+    }
+  }
+}
+
+struct Row16NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// SRC = 0: rows are loaded here (CG: through L2 only); SRC = 1: rows were staged by
+// row16_issue into `slots`; after_loads() runs once this lane has read its slots.
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool CG, int SRC = 0, typename Hook = Row16NoHook>
+__device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16Lane &L, int32_t j, int32_t k,
+                                              uint32_t sweep_lo, uint32_t ctr_hi, bool on, uint32_t &n_acc,
+                                              double &e_tot, uint32_t slots = 0, Hook after_loads = Hook()) {
+  constexpr int NTAB16 = CMX_TAB16(NOCC);
+  const Geom &g = a.g;
+  const int32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
+  const int32_t layer = N0 * N1;
   const uint32_t mask = MASK_CT ? MASK_CT : L.mask;
   const uint32_t mc = (mask >> 12) & 7u;  // center row: dx = -1 / +1 bits
   const uint32_t tab = L.tab, r = L.r;
   const double *dEpot = L.dEpot;
   double e_sum = 0.0;
   const uint32_t gid = ((uint32_t)(k + a.k_offset) * (uint32_t)N1 + (uint32_t)j) * a.W + L.c;
-  int8_t *pc = L.base + ((size_t)((uint32_t)(k + g.halo) * (uint32_t)N1 + (uint32_t)j) * (uint32_t)N0 + 16u * L.c);
-  int32_t dj[3], dk[3];
-  dj[0] = (j == 0) ? (N1 - 1) * N0 : -N0;
-  dj[1] = 0;
-  dj[2] = (j == N1 - 1) ? -(N1 - 1) * N0 : N0;
-  dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : -layer;
-  dk[1] = 0;
-  dk[2] = (!halo && k == N2 - 1) ? -(N2 - 1) * layer : layer;
+  const Row16Addr A = row16_addr(a, L, j, k);
+  int8_t *pc = A.pc;
   uint32_t C[4], T[4];
   {
     uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
+    uint32_t n_slot = 0;
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
 #pragma unroll
@@ -216,7 +269,9 @@ __device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16La
         const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
         const bool center = (dz == 0 && dy == 0);
         if (m3 == 0 && !center) continue;
-        const uint4 ch = row16_load<CG>(pc + (ptrdiff_t)(dk[dz + 1] + dj[dy + 1]));
+        uint4 ch;
+        if (SRC == 1) ch = lds_u128(slots + (n_slot++) * CMX_ROW16_SLOT);
+        else ch = row16_load<CG>(pc + (ptrdiff_t)(A.dk[dz + 1] + A.dj[dy + 1]));
         if (center) {
           C[0] = ch.x;
           C[1] = ch.y;
@@ -244,6 +299,7 @@ __device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16La
         }
       }
     }
+    after_loads();
     // words just outside the chunk: the summed classes of the neighbor chunks
     const uint32_t sm = L.any_m ? __shfl_sync(0xffffffffu, Am[3], L.lane_l) : 0u;
     const uint32_t sp = L.any_p ? __shfl_sync(0xffffffffu, Ap[0], L.lane_r) : 0u;
@@ -355,21 +411,55 @@ __device__ __forceinline__ bool row16_reduce(const Pair16Args &a, uint32_t r, ui
   return true;
 }
 
-// ---- one colour pass (cy,cz) over the colour layers of a k-slice -------------
+// rows a tile reads (center included) for a compile-time mask; 9 when the mask is a runtime value
+__host__ __device__ constexpr uint32_t row16_n_slots(uint32_t mask_ct) {
+  if (mask_ct == 0) return 9;
+  uint32_t n = 0;
+  for (int q = 0; q < 9; ++q) n += (q == 4 || ((mask_ct >> (3 * q)) & 7u)) ? 1u : 0u;
+  return n;
+}
+template <int NOCC>
+__host__ __device__ constexpr size_t row16_smem_bytes(uint32_t mask_ct) {
+  return (size_t)CMX_TAB24(NOCC) * 4 + 8u * row16_n_slots(mask_ct) * CMX_ROW16_SLOT;
+}
+
+// the rows of the acceptance table that exist: (code | alt << 2) in {0,1,18,4,5,22}
+template <int NOCC>
+__device__ __forceinline__ void row16_load_table(uint32_t *sh_tab, const uint32_t *__restrict__ gt) {
+  if (NOCC == 3) {
+    for (int q = threadIdx.x; q < 6 * 256; q += 256) {
+      const int row = q >> 8;
+      const int sab = (row < 3 ? 0 : 4) | ((row % 3) == 2 ? CMX_VA_CODE : (row % 3));
+      sh_tab[(sab << 8) | (q & 255)] = gt[(sab << 8) | (q & 255)];
+    }
+  } else {
+    for (int q = threadIdx.x; q < CMX_TAB24(NOCC); q += 256) sh_tab[q] = gt[q];
+  }
+}
+
+// ---- one colour pass (cy,cz) over the colour layers [row_begin/J, ...) --------------
+// Software pipelined: while a tile is updated, the rows of the warp's NEXT tile are
+// already on their way into the warp's shared-memory slots (cp.async, 16 B per lane
+// and row) -- the global latency is hidden behind ~350 instructions of compute and
+// costs no registers.  A lane only ever reads the slots it filled itself: no
+// barrier, not even a warp one.
 template <int NOCC, uint32_t MASK_CT, bool ACCUM>
 __global__ void __launch_bounds__(256, 4) k_sweep_row16(Pair16Args a) {
   constexpr int NTAB = CMX_TAB24(NOCC);
-  __shared__ __align__(16) uint32_t sh_tab[NTAB];
+  constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
+  // dynamic shared memory: [acceptance table][8 warps x NSLOT row slots x (32 lanes x 16 B)]
+  extern __shared__ __align__(16) unsigned char sh_dyn[];
+  uint32_t *sh_tab = reinterpret_cast<uint32_t *>(sh_dyn);
+  unsigned char *sh_rows = sh_dyn + NTAB * 4;
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  {
-    const uint32_t *gt = a.tab24 + (size_t)blockIdx.y * NTAB;
-    for (int q = threadIdx.x; q < NTAB; q += 256) sh_tab[q] = gt[q];
-  }
+  row16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)blockIdx.y * NTAB);
   const Row16Lane L = row16_lane<NOCC, MASK_CT>(a, sh_tab);
-  const uint32_t rl = (threadIdx.x & 31u) >> a.logW;
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t rl = lane >> a.logW;
   const uint32_t rpw_log = 5u - a.logW;  // log2(rows per warp)
+  const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_ROW16_SLOT) + 16u * lane;
   uint32_t n_acc = 0;
   double e_tot = 0.0;
   // the lattice may only be touched once the previous launch has completed
@@ -386,16 +476,18 @@ __global__ void __launch_bounds__(256, 4) k_sweep_row16(Pair16Args a) {
     }
   }
   __syncthreads();
-  const uint32_t warp0 = blockIdx.x * 8u + (threadIdx.x >> 5), n_warps = gridDim.x * 8u;
+  const uint32_t warp0 = blockIdx.x * 8u + wib, n_warps = gridDim.x * 8u;
   // rows advance by a fixed stride per iteration: decode (kk, jj) once, then step
   uint32_t row = (warp0 << rpw_log) + rl;  // relative to row_begin
   uint32_t kk, jj, kk_last, jj_last, step_k, step_j;
   fastdivmod(min(row, a.n_rows - 1u) + a.row_begin, a.divJ, kk, jj);
   fastdivmod(a.n_rows - 1u + a.row_begin, a.divJ, kk_last, jj_last);
   fastdivmod(n_warps << rpw_log, a.divJ, step_k, step_j);
-  for (uint32_t tile = warp0; tile < a.n_tiles; tile += n_warps) {
-    const bool on = row < a.n_rows;  // a partial last tile: the idle lanes redo the last row, unstored
-    const int32_t j = 2 * (int32_t)(on ? jj : jj_last) + a.cy, k = 2 * (int32_t)(on ? kk : kk_last) + a.cz;
+  // (j, k, on) of the tile at the current position, then advance the position
+  auto take = [&](int32_t &j, int32_t &k, bool &on) {
+    on = row < a.n_rows;  // a partial last tile: the idle lanes redo the last row, unstored
+    j = 2 * (int32_t)(on ? jj : jj_last) + a.cy;
+    k = 2 * (int32_t)(on ? kk : kk_last) + a.cz;
     row += n_warps << rpw_log;
     jj += step_j;
     kk += step_k;
@@ -403,7 +495,25 @@ __global__ void __launch_bounds__(256, 4) k_sweep_row16(Pair16Args a) {
       jj -= a.J;
       kk += 1;
     }
-    row16_tile<NOCC, MASK_CT, ACCUM, true>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot);
+  };
+  int32_t j = 0, k = 0, jn = 0, kn = 0;
+  bool on = false, on_n = false;
+  uint32_t tile = warp0;
+  if (tile < a.n_tiles) {
+    take(j, k, on);
+    row16_issue<MASK_CT>(a, L, j, k, slots);
+  }
+  for (; tile < a.n_tiles; tile += n_warps) {
+    const bool more = tile + n_warps < a.n_tiles;
+    if (more) take(jn, kn, on_n);
+    cp_async_wait_all();
+    auto stage_next = [&]() {
+      if (more) row16_issue<MASK_CT>(a, L, jn, kn, slots);
+    };
+    row16_tile<NOCC, MASK_CT, ACCUM, true, 1>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot, slots, stage_next);
+    j = jn;
+    k = kn;
+    on = on_n;
   }
   if (row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum) && a.push) {
     // release: every store of this block (ordered before this thread by the
@@ -460,10 +570,7 @@ __global__ void __launch_bounds__(256, 4) k_sweep_row16_fused(Pair16Args a, Fuse
   __shared__ __align__(16) uint32_t sh_tab[NTAB];
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
-  {
-    const uint32_t *gt = a.tab24 + (size_t)blockIdx.y * NTAB;
-    for (int q = threadIdx.x; q < NTAB; q += 256) sh_tab[q] = gt[q];
-  }
+  row16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)blockIdx.y * NTAB);
   const Row16Lane L = row16_lane<NOCC, MASK_CT>(a, sh_tab);
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const int32_t N1 = a.g.N1, N2 = a.g.N2;

@@ -233,11 +233,13 @@ int cmx_counters_reset(cmx_state *s);
 /* pair-LUT kernel variants (the trajectory does not depend on the variant):
  * BLOCK_KERNEL forces the block-exchange kernel (k_sweep_pair16: any N0 that is a
  * multiple of 16) where the warp-row kernel (k_sweep_row16: N0/16 a power of two
- * <= 32) would be chosen; NO_FUSION makes cmx_sgc_sweep launch one kernel per colour
- * pass (4 per sweep) instead of the fused whole-call kernel (k_sweep_row16_fused:
- * periodic warp-row states, row stamps instead of kernel boundaries). */
+ * <= 32) would be chosen.  cmx_sgc_sweep launches one kernel per colour pass (4 per
+ * sweep, overlapped with programmatic dependent launch); FUSED selects the
+ * experimental whole-call kernel instead (k_sweep_row16_fused: one cooperative launch,
+ * row stamps instead of kernel boundaries -- measured 2x slower at 512^3 because of
+ * the stamp polling, kept for the bit-exact cross-check and for further work). */
 #define CMX_SWEEP_BLOCK_KERNEL 4u
-#define CMX_SWEEP_NO_FUSION 8u
+#define CMX_SWEEP_FUSED 8u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* synchronises the state's stream; counters[n_replicas] */
 int cmx_counters_read(cmx_state *s, cmx_counters *counters);
