@@ -37,6 +37,8 @@ EXPORTED_SYMBOLS = [
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
     "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
+    "cmx_sampler_create", "cmx_sampler_destroy", "cmx_sampler_set_param_chem_pot", "cmx_sampler_info",
+    "cmx_sampler_reset", "cmx_sampler_sample", "cmx_sampler_read", "cmx_sweep_run",
 ]
 
 
@@ -155,6 +157,14 @@ def lib():
     L.cmx_kmc_destroy.restype = None
     L.cmx_kmc_event_states.argtypes = [vp, i64, vp, vp, vp, vp]
     L.cmx_kmc_all_rates.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.cmx_sampler_create.argtypes = [vp, i32, i32, vp, vp, i32, C.POINTER(vp)]
+    L.cmx_sampler_destroy.argtypes = [vp]
+    L.cmx_sampler_set_param_chem_pot.argtypes = [vp, i32, vp]
+    L.cmx_sampler_info.argtypes = [vp] + [C.POINTER(i32)] * 6
+    L.cmx_sampler_reset.argtypes = [vp]
+    L.cmx_sampler_sample.argtypes = [vp]
+    L.cmx_sampler_read.argtypes = [vp, i32, i32, i32, vp]
+    L.cmx_sweep_run.argtypes = [vp, vp, i32, i64, i64, u64, i64, vp]
     _lib = L
     return L
 
@@ -225,6 +235,7 @@ class State:
         t = tables.host
         self.n_cells = self.N[0] * self.N[1] * self.N[2]
         self.n_sites = self.n_cells * t.n_sublat
+        self._temperature = {}
         self._h = C.c_void_p()
         check(lib().cmx_state_create(tables._h, *self.N, self.n_replicas, self.halo, C.byref(self._h)))
 
@@ -308,6 +319,10 @@ class State:
             if exch.size != t.n_sublat * t.max_occ * t.max_occ:
                 raise CmxError(CMX_ERR_INVALID, "exch must have n_sublat*max_occ*max_occ entries")
         check(lib().cmx_state_set_conditions(self._h, replica, float(temperature), _p(exch)))
+        self._temperature[int(replica)] = float(temperature)
+
+    def temperature(self, replica: int = 0) -> float:
+        return self._temperature[int(replica)]
 
     def set_occupants(self, sublat_to_asym, occ_to_species, n_species: int) -> None:
         s2a = np.ascontiguousarray(sublat_to_asym, dtype=np.int32)
@@ -429,6 +444,102 @@ class State:
         steps = [dict(l0=s.l0, l1=s.l1, new0=s.new0, new1=s.new1, accepted=s.accepted, dE=s.dE)
                  for s in log[:min(log_cap, n_steps)]]
         return dict(n_accept=n_acc.value, hash=h.value, log=steps)
+
+
+KB = 8.6173303e-05  # eV/K, CASM::KB [EXT libcasm-global], pinned by _MonteCalculator.py:186-210
+
+
+class Sampler:
+    """Device-resident sample series of every replica of a State (cmx_sampler_*):
+    the reference's state sampling functions `clex.formation_energy`,
+    `potential_energy`, `mol_composition`, `param_composition`, `corr`
+    (monte_calculator/sampling_functions.cc:37-288, all per unit cell) and, from
+    the series, its analysis functions (monte_calculator/analysis_functions.cc:43-173)."""
+
+    def __init__(self, state: "State", capacity: int, origin=None, Rt=None, with_corr: bool = False):
+        self.state = state
+        Rt = np.zeros((0, 0)) if Rt is None else np.ascontiguousarray(Rt, dtype=np.float64)
+        self.n_param = int(Rt.shape[0])
+        org = None if origin is None else np.ascontiguousarray(origin, dtype=np.float64)
+        self._h = C.c_void_p()
+        check(lib().cmx_sampler_create(state._h, int(capacity), self.n_param, _p(org),
+                                       _p(Rt) if self.n_param else None, int(bool(with_corr)), C.byref(self._h)))
+        v = [C.c_int32() for _ in range(6)]
+        check(lib().cmx_sampler_info(self._h, *[C.byref(x) for x in v]))
+        self.n_quantities, self.n_species, _, self.corr_size, _, self.capacity = [int(x.value) for x in v]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cmx_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_samples(self) -> int:
+        v = C.c_int32()
+        check(lib().cmx_sampler_info(self._h, None, None, None, None, C.byref(v), None))
+        return int(v.value)
+
+    def set_param_chem_pot(self, param_chem_pot, replica: int = 0) -> None:
+        mu = None if param_chem_pot is None else np.ascontiguousarray(param_chem_pot, dtype=np.float64)
+        if mu is not None and mu.size != self.n_param:
+            raise CmxError(CMX_ERR_INVALID, "param_chem_pot has the wrong length")
+        check(lib().cmx_sampler_set_param_chem_pot(self._h, int(replica), _p(mu)))
+
+    def reset(self) -> None:
+        check(lib().cmx_sampler_reset(self._h))
+
+    def sample(self) -> None:
+        """Append one sample of every replica (asynchronous)."""
+        check(lib().cmx_sampler_sample(self._h))
+
+    def run(self, n_samples: int, sweeps_per_sample: int, seed: int, first_sweep: int = 0,
+            ensemble: str = "semigrand_canonical"):
+        """n_samples x (sweeps_per_sample passes, one sample): one stream of launches."""
+        ens = {"semigrand_canonical": 0, "canonical": 1}[ensemble]
+        cnt = (Counters * self.state.n_replicas)()
+        check(lib().cmx_sweep_run(self.state._h, self._h, ens, int(n_samples), int(sweeps_per_sample),
+                                  int(seed), int(first_sweep), cnt))
+        return list(cnt)
+
+    def series(self, replica: int = 0, first: int = 0, n: Optional[int] = None) -> dict:
+        """Sampled series by the reference's sampler names."""
+        n = self.n_samples - first if n is None else n
+        raw = np.empty((n, self.n_quantities), dtype=np.float64)
+        check(lib().cmx_sampler_read(self._h, int(replica), int(first), int(n), _p(raw)))
+        s, p = self.n_species, self.n_param
+        out = {"clex.formation_energy": raw[:, 0], "potential_energy": raw[:, 1],
+               "mol_composition": raw[:, 2:2 + s], "param_composition": raw[:, 2 + s:2 + s + p]}
+        if self.corr_size:
+            out["corr"] = raw[:, 2 + s + p:]
+        return out
+
+    def analysis(self, replica: int = 0, first: int = 0) -> dict:
+        """heat_capacity, mol_susc, param_susc, mol_thermochem_susc, param_thermochem_susc
+        (analysis_functions.cc:43-173): covariances of the sampled series normalised by
+        kB T^2 / n_unitcells resp. kB T / n_unitcells (run/io/convariance_functions.cc:29-143)."""
+        ser = self.series(replica, first)
+        T = self.state.temperature(replica)
+        n_cells = self.state.n_cells
+
+        def cov(a, b):
+            a = a - a.mean(axis=0)
+            b = b - b.mean(axis=0)
+            return a.T @ b / a.shape[0]
+
+        e = ser["potential_energy"][:, None]
+        n, x = ser["mol_composition"], ser["param_composition"]
+        c_heat = KB * T * T / n_cells
+        c_susc = KB * T / n_cells
+        return {"heat_capacity": float(cov(e, e)[0, 0] / c_heat),
+                "mol_susc": cov(n, n) / c_susc, "param_susc": cov(x, x) / c_susc,
+                "mol_thermochem_susc": cov(e, n)[0] / c_susc,
+                "param_thermochem_susc": cov(e, x)[0] / c_susc}
 
 
 def rng_stream_test(seed: int, kinds, int_max=None, real_max=None):

@@ -308,8 +308,8 @@ extern "C" int cmx_canonical_info(const cmx_state *s, int32_t i, int32_t *stride
   return CMX_OK;
 }
 
-extern "C" int cmx_canonical_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
-                                   int64_t first_sweep, cmx_counters *counters) {
+// sweeps enqueued on the state's stream; `reset` zeroes the per-block counters first
+int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep, bool reset) {
   if (!s) return invalid("cmx_canonical_sweep: null state");
   if (!s->canon) {
     cmx_set_error("cmx_canonical_sweep: no swap types (cmx_canonical_set_swaps)");
@@ -340,10 +340,13 @@ extern "C" int cmx_canonical_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed
     CMX_CUDA(cudaMalloc((void **)&P.d_part, sizeof(long long) * 2 * nslots));
     CMX_CUDA(cudaMalloc((void **)&P.d_part_dE, sizeof(double) * nslots));
     P.blocks = blocks;
+    reset = true;
   }
-  size_t nslots = (size_t)P.blocks * s->n_replicas;
-  CMX_CUDA(cudaMemsetAsync(P.d_part, 0, sizeof(long long) * 2 * nslots, s->stream));
-  CMX_CUDA(cudaMemsetAsync(P.d_part_dE, 0, sizeof(double) * nslots, s->stream));
+  if (reset) {
+    size_t nslots = (size_t)P.blocks * s->n_replicas;
+    CMX_CUDA(cudaMemsetAsync(P.d_part, 0, sizeof(long long) * 2 * nslots, s->stream));
+    CMX_CUDA(cudaMemsetAsync(P.d_part_dE, 0, sizeof(double) * nslots, s->stream));
+  }
   CanonArgs a;
   a.occ = s->d_occ;
   a.g = g;
@@ -394,6 +397,12 @@ extern "C" int cmx_canonical_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed
     }
     CMX_CUDA(cudaGetLastError());
   }
+  return CMX_OK;
+}
+
+// counters since the last reset (null: only synchronise)
+int cmx_canonical_counters(cmx_state *s, cmx_counters *counters) {
+  CanonicalPlan &P = *s->canon;
   if (counters) {
     k_canonical_reduce<<<s->n_replicas, 32, 0, s->stream>>>(P.d_part, P.d_part_dE, P.blocks, s->d_counters);
     CMX_CUDA(cudaGetLastError());
@@ -402,4 +411,11 @@ extern "C" int cmx_canonical_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed
   }
   CMX_CUDA(cudaStreamSynchronize(s->stream));
   return CMX_OK;
+}
+
+extern "C" int cmx_canonical_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
+                                   int64_t first_sweep, cmx_counters *counters) {
+  int rc = cmx_canonical_enqueue(s, n_sweeps, seed, first_sweep, true);
+  if (rc) return rc;
+  return cmx_canonical_counters(s, counters);
 }

@@ -14,8 +14,21 @@
 // one streaming pass: 16 sites per thread, forward-neighbor counts for all 16 byte
 // lanes at once (the storage code makes the byte sum n1 + 18 n2), one table
 // lookup and one FP64 add per site, fixed-order block/grid reduction.
+//
+// k_energy_lin16 (the default): with point and pair functions only the per-cell
+// energy is LINEAR in the forward-neighbor counts,
+//   E_cell(o; n1, n2) = c0(o) + n1 d1(o) + n2 d2(o)        (verified on the table),
+// so the supercell energy is a dot product of 9 coefficients with INTEGER bond counts
+//   N_o = #cells with occupant o,  N_o1 = sum_{cells: o} n1,  N_o2 = sum_{cells: o} n2.
+// With <= 7 forward neighbors the byte-lane sum n1 + 18 n2 splits into nibbles
+// (low: n1 + 2 n2 <= 14, high: n2), and four dot-product instructions per 4 sites
+// (occupant indicator lanes x count lanes) accumulate the bond counts: no table
+// gather, no FP64 in the streaming pass, ~6 instructions per site; the FP64 work is
+// 9 multiply-adds per replica in the finishing kernel.  Exact integer counting also
+// makes the sum independent of the grid.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "cmx_internal.cuh"
 
@@ -58,32 +71,27 @@ __global__ void k_build_cell_lut(DevTables T, int nocc, int z, const int32_t *__
 }
 
 struct EnergyArgs {
-  const int8_t *occ;  // replica base
+  const int8_t *occ;  // base of replica blockIdx.y = 0
+  size_t rep_stride;  // bytes between replicas (blockIdx.y)
   Geom g;
   uint32_t mask;
   uint32_t W;       // 16-byte chunks per row
   FastDiv divW, divJ;
   uint32_t n_items;  // W * N1 * N2
   const double *lut;
-  double *partial;  // [gridDim.x]
+  double *partial;  // [gridDim.y][gridDim.x]
+  LinSums *sums;    // k_energy_lin16: [gridDim.y][gridDim.x]
 };
 
-template <int NOCC>
-__global__ void __launch_bounds__(256) k_energy_pair16(EnergyArgs a) {
-  __shared__ double sh_lut[NOCC * 256];
-  __shared__ double sh_red[256];
-  for (int q = threadIdx.x; q < NOCC * 256; q += blockDim.x) sh_lut[q] = a.lut[q];
-  __syncthreads();
+// one 16-site chunk: its codes C[4] and the byte-lane sums cnt[4] = n1 + 18 n2 over the
+// forward neighbors of every site
+__device__ __forceinline__ void energy_chunk(const EnergyArgs &a, const int8_t *base, uint32_t item,
+                                             uint32_t (&C)[4], uint32_t (&cnt)[4]) {
   const Geom &g = a.g;
-  const int8_t *base = a.occ;
   const uint32_t N0 = g.N0, N1 = g.N1, N2 = g.N2;
   const uint32_t layer = N0 * N1;
   const bool halo = g.halo != 0;
   const uint32_t mask = a.mask;
-  const uint32_t mc = (mask >> 12) & 7u;
-  double acc = 0.0;
-  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < a.n_items;
-       item += gridDim.x * blockDim.x) {
     uint32_t row, c, k, j;
     fastdivmod(item, a.divW, row, c);
     fastdivmod(row, a.divJ, k, j);
@@ -98,7 +106,8 @@ __global__ void __launch_bounds__(256) k_energy_pair16(EnergyArgs a) {
     dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : 0u - layer;
     dk[1] = 0;
     dk[2] = (!halo && k == N2 - 1) ? 0u - (N2 - 1) * layer : layer;
-    uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0}, C[4] = {0, 0, 0, 0};
+    uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
+    C[0] = C[1] = C[2] = C[3] = 0;
     uint32_t sm = 0, sp = 0;
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
@@ -137,12 +146,24 @@ __global__ void __launch_bounds__(256) k_energy_pair16(EnergyArgs a) {
         }
       }
     }
-    (void)mc;
-    uint32_t cnt[4];
     cnt[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
     cnt[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
     cnt[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
     cnt[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
+}
+
+template <int NOCC>
+__global__ void __launch_bounds__(256) k_energy_pair16(EnergyArgs a) {
+  __shared__ double sh_lut[NOCC * 256];
+  __shared__ double sh_red[256];
+  for (int q = threadIdx.x; q < NOCC * 256; q += blockDim.x) sh_lut[q] = a.lut[q];
+  __syncthreads();
+  const int8_t *base = a.occ + (size_t)blockIdx.y * a.rep_stride;
+  double acc = 0.0;
+  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < a.n_items;
+       item += gridDim.x * blockDim.x) {
+    uint32_t C[4], cnt[4];
+    energy_chunk(a, base, item, C, cnt);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t S = C[i] & 0x03030303u;
@@ -159,7 +180,72 @@ __global__ void __launch_bounds__(256) k_energy_pair16(EnergyArgs a) {
     if (threadIdx.x < s) sh_red[threadIdx.x] += sh_red[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) a.partial[blockIdx.x] = sh_red[0];
+  if (threadIdx.x == 0) a.partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sh_red[0];
+}
+
+// bond counts by dot-product instructions (see the file comment); NOCC == 2: codes 0 / 1 only
+template <int NOCC>
+__global__ void __launch_bounds__(256) k_energy_lin16(EnergyArgs a) {
+  __shared__ unsigned long long sh_sum[6];
+  if (threadIdx.x < 6) sh_sum[threadIdx.x] = 0;
+  __syncthreads();
+  const int8_t *base = a.occ + (size_t)blockIdx.y * a.rep_stride;
+  unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t acc[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t it = 0;
+  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < a.n_items;
+       item += gridDim.x * blockDim.x) {
+    uint32_t C[4], cnt[4];
+    energy_chunk(a, base, item, C, cnt);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t L = cnt[i] & 0x0F0F0F0Fu;         // n1 + 2 n2 per lane
+      const uint32_t H = (cnt[i] >> 4) & 0x0F0F0F0Fu;  // n2 per lane
+      const uint32_t p1 = C[i] & 0x01010101u;          // occupant 1 lanes (weight 1)
+      acc[0] = __dp4a(p1, 0x01010101u, acc[0]);
+      acc[2] = __dp4a(p1, L, acc[2]);
+      acc[3] = __dp4a(p1, H, acc[3]);
+      if (NOCC == 3) {
+        const uint32_t p2 = C[i] & 0x10101010u;        // occupant 2 lanes (code 18; weight 16)
+        acc[1] += __popc(p2);
+        acc[4] = __dp4a(p2, L, acc[4]);
+        acc[5] = __dp4a(p2, H, acc[5]);
+      }
+    }
+    if ((++it & 1023u) == 0) {  // a chunk adds < 2^12 to a 32-bit accumulator
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        tot[q] += acc[q];
+        acc[q] = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    tot[q] += acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot[q] += __shfl_down_sync(0xffffffffu, tot[q], o);
+    if ((threadIdx.x & 31) == 0 && tot[q]) atomicAdd(&sh_sum[q], tot[q]);  // integers: order-free
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    LinSums r;
+    r.n1 = sh_sum[0];
+    r.n2 = sh_sum[1];
+    r.sl1 = sh_sum[2];
+    r.sh1 = sh_sum[3];
+    r.sl2 = sh_sum[4];
+    r.sh2 = sh_sum[5];
+    a.sums[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = r;
+  }
+}
+
+__global__ void k_energy_lin_final(const LinSums *__restrict__ sums, int nb, long long n_cells, int z,
+                                   const double *__restrict__ lin, double *out) {
+  __shared__ unsigned long long sh[6];
+  unsigned long long v[6];
+  cmx_lin_reduce(sums, nb, sh, v);
+  if (threadIdx.x == 0) *out = cmx_lin_energy(v, n_cells, z, lin, nullptr);
 }
 
 __global__ void k_energy_final(const double *__restrict__ partial, int nb, double *out) {
@@ -229,14 +315,40 @@ int cmx_plan_energy(cmx_state *s) {
   P.e_mask = mask;
   P.e_z = (int32_t)fwd.size();
   P.e_fast = true;
+  // linear in the counts (always true for point + pair functions; checked, not assumed)
+  P.e_lin = false;
+  if (P.e_z <= 7 && (P.nocc == 2 || P.nocc == 3)) {
+    bool ok = true;
+    for (int o = 0; o < 3; ++o) {
+      double c0 = 0.0, d1 = 0.0, d2 = 0.0;
+      if (o < P.nocc) {
+        c0 = l1[o << 8];
+        d1 = (P.e_z >= 1) ? l1[(o << 8) | 1] - c0 : 0.0;
+        d2 = (P.nocc == 3 && P.e_z >= 1) ? l1[(o << 8) | CMX_VA_CODE] - c0 : 0.0;
+        for (int n2 = 0; n2 <= (P.nocc == 3 ? P.e_z : 0); ++n2)
+          for (int n1 = 0; n1 + n2 <= P.e_z; ++n1) {
+            const double want = l1[(o << 8) | (n1 + CMX_VA_CODE * n2)];
+            if (std::fabs(c0 + n1 * d1 + n2 * d2 - want) > 1e-12 * std::max(scale, 1e-300)) ok = false;
+          }
+      }
+      P.e_lin_c[3 * o] = c0;
+      P.e_lin_c[3 * o + 1] = d1;
+      P.e_lin_c[3 * o + 2] = d2;
+    }
+    if (ok) {
+      if (!P.d_e_lin) CMX_CUDA(cudaMalloc((void **)&P.d_e_lin, sizeof(double) * 9));
+      CMX_CUDA(cudaMemcpy(P.d_e_lin, P.e_lin_c, sizeof(double) * 9, cudaMemcpyHostToDevice));
+      P.e_lin = true;
+    }
+  }
   return CMX_OK;
 }
 
-int cmx_energy_fast(cmx_state *s, int32_t replica, double *E) {
-  SweepPlan &P = s->plan;
-  CMX_CUDA(cudaSetDevice(s->t->device));
+static EnergyArgs energy_args(const cmx_state *s, int32_t first_replica) {
+  const SweepPlan &P = s->plan;
   EnergyArgs a;
-  a.occ = s->d_occ + (size_t)replica * s->g.rep_stride;
+  a.occ = s->d_occ + (size_t)first_replica * s->g.rep_stride;
+  a.rep_stride = (size_t)s->g.rep_stride;
   a.g = s->g;
   a.mask = P.e_mask;
   a.W = s->g.N0 / 16;
@@ -244,7 +356,49 @@ int cmx_energy_fast(cmx_state *s, int32_t replica, double *E) {
   a.divJ = make_fastdiv((uint32_t)s->g.N1);
   a.n_items = a.W * (uint32_t)s->g.N1 * (uint32_t)s->g.N2;
   a.lut = P.d_e_lut;
+  a.partial = nullptr;
+  a.sums = nullptr;
+  return a;
+}
+
+int cmx_energy_fast_blocks(const cmx_state *s) {
+  const uint32_t n_items = (uint32_t)(s->g.N0 / 16) * (uint32_t)s->g.N1 * (uint32_t)s->g.N2;
+  const int cap = std::max(148, 148 * 8 / std::max(1, s->n_replicas));
+  return (int)std::min<uint32_t>((n_items + 255) / 256, (uint32_t)cap);
+}
+
+// every replica in one launch (asynchronous, on the state's stream): per-block bond
+// counts d_sums[replica][nb]; requires plan.e_lin
+int cmx_energy_lin_batch(cmx_state *s, int nb, LinSums *d_sums) {
+  EnergyArgs a = energy_args(s, 0);
+  a.sums = d_sums;
+  dim3 grid(nb, s->n_replicas);
+  if (s->plan.nocc == 3) k_energy_lin16<3><<<grid, 256, 0, s->stream>>>(a);
+  else k_energy_lin16<2><<<grid, 256, 0, s->stream>>>(a);
+  CMX_CUDA(cudaGetLastError());
+  return CMX_OK;
+}
+
+int cmx_energy_fast(cmx_state *s, int32_t replica, double *E) {
+  SweepPlan &P = s->plan;
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  EnergyArgs a = energy_args(s, replica);
   int nb = (int)std::min<uint32_t>((a.n_items + 255) / 256, 148 * 8);
+  static const bool force_lut = getenv("CMX_ENERGY_LUT") != nullptr;  // cross-check of the two kernels
+  if (P.e_lin && !force_lut) {
+    int rc = cmx_scratch(s, sizeof(LinSums) * nb + sizeof(double));
+    if (rc) return rc;
+    a.sums = (LinSums *)s->d_scratch;
+    double *d_E = (double *)(a.sums + nb);
+    if (P.nocc == 3) k_energy_lin16<3><<<nb, 256, 0, s->stream>>>(a);
+    else k_energy_lin16<2><<<nb, 256, 0, s->stream>>>(a);
+    CMX_CUDA(cudaGetLastError());
+    k_energy_lin_final<<<1, 256, 0, s->stream>>>(a.sums, nb, (long long)s->g.n_cells, P.e_z, P.d_e_lin, d_E);
+    CMX_CUDA(cudaGetLastError());
+    CMX_CUDA(cudaMemcpyAsync(E, d_E, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CMX_CUDA(cudaStreamSynchronize(s->stream));
+    return CMX_OK;
+  }
   int rc = cmx_scratch(s, sizeof(double) * (nb + 1));
   if (rc) return rc;
   a.partial = (double *)s->d_scratch;

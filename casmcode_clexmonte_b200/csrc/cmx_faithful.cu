@@ -299,7 +299,7 @@ __global__ void k_reduce_partials(const double *__restrict__ partial, int nb,
   out[c] = a;
 }
 
-static int global_corr_device(cmx_state *s, int32_t replica, double **d_out) {
+int cmx_global_corr_device(cmx_state *s, int32_t replica, double **d_out) {
   const DevTables &T = s->t->d;
   int nb = (int)((s->g.n_cells + 255) / 256);
   if (nb > 592) nb = 592;
@@ -326,7 +326,7 @@ extern "C" int cmx_global_corr(const cmx_state *cs, int32_t replica, double *out
     return invalid("cmx_global_corr: replica out of range");
   CMX_CUDA(cudaSetDevice(s->t->device));
   double *d_out = nullptr;
-  int rc = global_corr_device(s, replica, &d_out);
+  int rc = cmx_global_corr_device(s, replica, &d_out);
   if (rc) return rc;
   CMX_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * s->t->d.corr_size,
                            cudaMemcpyDeviceToHost, s->stream));
@@ -396,6 +396,32 @@ __global__ void k_composition_coded(const uint4 *__restrict__ occ, int64_t n16,
   }
 }
 
+// occupant counts of one replica into d_counts[n_sublat * max_occ] (asynchronous, on the
+// state's stream); the coded path leaves bin 0 to the caller (n_cells - the others)
+int cmx_composition_device(cmx_state *s, int32_t replica, unsigned long long *d_counts, bool *bin0_missing) {
+  const DevTables &T = s->t->d;
+  int nbins = T.n_sublat * T.max_occ;
+  CMX_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nbins, s->stream));
+  int64_t total = s->g.n_cells * T.n_sublat;
+  int nb = (int)((total + 255) / 256);
+  if (nb > 1184) nb = 1184;
+  if (T.n_sublat == 1 && T.max_occ <= 3 && s->g.n_cells % 16 == 0 && (s->g.coded || T.max_occ <= 2)) {
+    // owned layers are contiguous (ghost layers sit before and after them)
+    const int8_t *first = s->d_occ + (size_t)replica * s->g.rep_stride + (size_t)s->g.halo * s->g.layer;
+    int64_t n16 = s->g.n_cells / 16;
+    int nbc = (int)std::min<int64_t>((n16 + 255) / 256, 1184);
+    k_composition_coded<<<nbc, 256, 0, s->stream>>>((const uint4 *)first, n16, d_counts);
+    CMX_CUDA(cudaGetLastError());
+    *bin0_missing = true;
+    return CMX_OK;
+  }
+  k_composition<<<nb, 256, sizeof(unsigned int) * nbins, s->stream>>>(
+      s->g, T.n_sublat, T.max_occ, s->d_occ + (size_t)replica * s->g.rep_stride, d_counts);
+  CMX_CUDA(cudaGetLastError());
+  *bin0_missing = false;
+  return CMX_OK;
+}
+
 extern "C" int cmx_composition(const cmx_state *cs, int32_t replica, int64_t *counts) {
   cmx_state *s = const_cast<cmx_state *>(cs);
   if (!s || !counts) return invalid("cmx_composition: null argument");
@@ -406,32 +432,16 @@ extern "C" int cmx_composition(const cmx_state *cs, int32_t replica, int64_t *co
   int nbins = T.n_sublat * T.max_occ;
   int rc = cmx_scratch(s, sizeof(unsigned long long) * nbins);
   if (rc) return rc;
-  CMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(unsigned long long) * nbins, s->stream));
-  int64_t total = s->g.n_cells * T.n_sublat;
-  int nb = (int)((total + 255) / 256);
-  if (nb > 1184) nb = 1184;
-  if (T.n_sublat == 1 && T.max_occ <= 3 && s->g.n_cells % 16 == 0 && (s->g.coded || T.max_occ <= 2)) {
-    // owned layers are contiguous (ghost layers sit before and after them)
-    const int8_t *first = s->d_occ + (size_t)replica * s->g.rep_stride + (size_t)s->g.halo * s->g.layer;
-    int64_t n16 = s->g.n_cells / 16;
-    int nbc = (int)std::min<int64_t>((n16 + 255) / 256, 1184);
-    k_composition_coded<<<nbc, 256, 0, s->stream>>>((const uint4 *)first, n16,
-                                                     (unsigned long long *)s->d_scratch);
-    CMX_CUDA(cudaGetLastError());
-    CMX_CUDA(cudaMemcpyAsync(counts, s->d_scratch, sizeof(int64_t) * nbins,
-                             cudaMemcpyDeviceToHost, s->stream));
-    CMX_CUDA(cudaStreamSynchronize(s->stream));
-    int64_t rest = s->g.n_cells;
-    for (int q = 1; q < nbins; ++q) rest -= counts[q];
-    counts[0] = rest;
-    return CMX_OK;
-  }
-  k_composition<<<nb, 256, sizeof(unsigned int) * nbins, s->stream>>>(
-      s->g, T.n_sublat, T.max_occ, s->d_occ + (size_t)replica * s->g.rep_stride,
-      (unsigned long long *)s->d_scratch);
-  CMX_CUDA(cudaGetLastError());
+  bool bin0_missing = false;
+  rc = cmx_composition_device(s, replica, (unsigned long long *)s->d_scratch, &bin0_missing);
+  if (rc) return rc;
   CMX_CUDA(cudaMemcpyAsync(counts, s->d_scratch, sizeof(int64_t) * nbins,
                            cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
+  if (bin0_missing) {
+    int64_t rest = s->g.n_cells;
+    for (int q = 1; q < nbins; ++q) rest -= counts[q];
+    counts[0] = rest;
+  }
   return CMX_OK;
 }

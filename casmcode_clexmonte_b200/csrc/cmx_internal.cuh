@@ -134,6 +134,9 @@ struct SweepPlan {
   uint32_t e_mask = 0;   // forward neighbor rows/offsets, bit layout as `mask`
   int32_t e_z = 0;
   double *d_e_lut = nullptr;  // [4][256]: index = cnt | occupant << 8
+  bool e_lin = false;         // the table is linear in the counts: integer bond-count kernel
+  double e_lin_c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // [occupant][c0, d1, d2]
+  double *d_e_lin = nullptr;
   // per-block partial counters of the current call
   long long *d_part_acc = nullptr;
   double *d_part_dE = nullptr;
@@ -188,8 +191,71 @@ struct cmx_state {
 int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
 void cmx_canonical_free(cmx_state *s);
+int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep, bool reset);
+int cmx_canonical_counters(cmx_state *s, cmx_counters *counters);
 int cmx_plan_energy(cmx_state *s);                       // cmx_energy.cu
 int cmx_energy_fast(cmx_state *s, int32_t replica, double *E);  // requires plan.e_fast
+// integer bond counts of one block (k_energy_lin16); sl2 / sh2 carry a factor 16
+struct LinSums {
+  unsigned long long n1, n2, sl1, sh1, sl2, sh2;
+};
+
+// E and the occupant counts of one replica from the summed block counts
+// v = (n1, n2, sl1, sh1, sl2, sh2):
+//   N_o1 = sum n1 over cells with occupant o,  N_o2 = sum n2; every site is a forward
+//   neighbor of exactly z cells, which gives the occupant-0 rows
+__host__ __device__ inline double cmx_lin_energy(const unsigned long long *v, long long n_cells, int z,
+                                                 const double *lin /*[3][3]: c0, d1, d2 per occupant*/,
+                                                 unsigned long long *n_occ /*[3] or null*/) {
+  const unsigned long long n1 = v[0], n2 = v[1], sl1 = v[2], sh1 = v[3], sl2 = v[4] >> 4, sh2 = v[5] >> 4;
+  const long long N1 = (long long)n1, N2 = (long long)n2, N0 = n_cells - N1 - N2;
+  const long long N12 = (long long)sh1, N11 = (long long)sl1 - 2 * N12;
+  const long long N22 = (long long)sh2, N21 = (long long)sl2 - 2 * N22;
+  const long long N01 = (long long)z * N1 - N11 - N21, N02 = (long long)z * N2 - N12 - N22;
+  if (n_occ) {
+    n_occ[0] = (unsigned long long)N0;
+    n_occ[1] = n1;
+    n_occ[2] = n2;
+  }
+  double E = (double)N0 * lin[0] + (double)N01 * lin[1] + (double)N02 * lin[2];
+  E += (double)N1 * lin[3] + (double)N11 * lin[4] + (double)N12 * lin[5];
+  E += (double)N2 * lin[6] + (double)N21 * lin[7] + (double)N22 * lin[8];
+  return E;
+}
+
+#ifdef __CUDACC__
+// sum of nb block records by one thread block (integers: any order); the result is
+// valid in every thread after the call.  sh[6] is shared scratch.
+__device__ __forceinline__ void cmx_lin_reduce(const LinSums *__restrict__ sums, int nb,
+                                               unsigned long long *sh, unsigned long long (&v)[6]) {
+  if (threadIdx.x < 6) sh[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long t[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    const LinSums r = sums[b];
+    t[0] += r.n1;
+    t[1] += r.n2;
+    t[2] += r.sl1;
+    t[3] += r.sh1;
+    t[4] += r.sl2;
+    t[5] += r.sh2;
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t[q] += __shfl_down_sync(0xffffffffu, t[q], o);
+    if ((threadIdx.x & 31) == 0 && t[q]) atomicAdd(&sh[q], t[q]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 6; ++q) v[q] = sh[q];
+}
+#endif
+
+int cmx_energy_fast_blocks(const cmx_state *s);
+int cmx_energy_lin_batch(cmx_state *s, int nb, LinSums *d_sums);  // requires plan.e_lin
+int cmx_global_corr_device(cmx_state *s, int32_t replica, double **d_out);  // cmx_faithful.cu; result in scratch
+int cmx_composition_device(cmx_state *s, int32_t replica, unsigned long long *d_counts, bool *bin0_missing);
 void cmx_plan_free(SweepPlan &p);
 
 // ---- device helpers ---------------------------------------------------------

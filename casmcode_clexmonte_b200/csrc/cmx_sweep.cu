@@ -45,6 +45,7 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_part_acc);
   cudaFree(p.d_part_dE);
   cudaFree(p.d_e_lut);
+  cudaFree(p.d_e_lin);
   p = SweepPlan();
 }
 

@@ -319,6 +319,50 @@ int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t mode,
                               int64_t *n_accept, uint64_t *hash);
 
 /* -------------------------------------------------------------------------
+ * Device-side samplers.  Replaces, for every replica
+ * at once and without moving the occupation to the host, the state sampling
+ * functions of src/casm/clexmonte/monte_calculator/sampling_functions.cc:
+ *   "clex.formation_energy" (:141-155)  ClusterExpansion::per_unitcell
+ *   "potential_energy"      (:274-288)  potential().per_unitcell()
+ *                                       = (E - n_cells mu.x) / n_cells
+ *                                       (SemiGrandCanonicalCalculator.cc:171-179;
+ *                                        canonical: mu = 0, CanonicalCalculator.cc:126-133)
+ *   "mol_composition"       (:37-54)    mean_num_each_component
+ *   "param_composition"     (:57-90)    x = R^T (n - origin)
+ *   "corr"                  (:121-139)  Correlations::per_unitcell  (optional)
+ * One series row per replica and sample:
+ *   [formation_energy, potential_energy, mol_composition[n_species],
+ *    param_composition[n_param], corr[corr_size] (with_corr)]
+ * The analysis functions heat_capacity / mol_susc / param_susc / *_thermochem_susc
+ * (monte_calculator/analysis_functions.cc:43-173) are variances and covariances of
+ * these series (host layer: Sampler.analysis()).
+ * Requires bound ECI and cmx_state_set_occupants.  origin[n_species],
+ * Rt[n_param][n_species] as in the composition axes of the system.
+ * ------------------------------------------------------------------------- */
+typedef struct cmx_sampler cmx_sampler;
+int cmx_sampler_create(cmx_state *s, int32_t capacity, int32_t n_param, const double *origin,
+                       const double *Rt, int32_t with_corr, cmx_sampler **out);
+int cmx_sampler_destroy(cmx_sampler *m);
+/* param_chem_pot[n_param] of one replica (NULL: canonical potential, no mu.x term) */
+int cmx_sampler_set_param_chem_pot(cmx_sampler *m, int32_t replica, const double *param_chem_pot);
+int cmx_sampler_info(const cmx_sampler *m, int32_t *n_quantities, int32_t *n_species, int32_t *n_param,
+                     int32_t *corr_size, int32_t *n_samples, int32_t *capacity);
+/* forget the recorded samples */
+int cmx_sampler_reset(cmx_sampler *m);
+/* append one sample of every replica (asynchronous, on the state's stream) */
+int cmx_sampler_sample(cmx_sampler *m);
+/* rows [first, first+n) of one replica: out[n][n_quantities]; synchronises */
+int cmx_sampler_read(cmx_sampler *m, int32_t replica, int32_t first, int32_t n, double *out);
+/* occupation_metropolis_v2 (methods/occupation_metropolis.hh:72-123) with a
+ * sampling period of `sweeps_per_sample` passes: n_samples x (sweeps, sample) as
+ * one stream of launches, one synchronisation at the end.
+ * ensemble 0 = semi-grand canonical sweeps, 1 = canonical pair exchanges.
+ * counters[n_replicas] may be NULL. */
+int cmx_sweep_run(cmx_state *s, cmx_sampler *m, int32_t ensemble, int64_t n_samples,
+                  int64_t sweeps_per_sample, uint64_t seed, int64_t first_sweep,
+                  cmx_counters *counters);
+
+/* -------------------------------------------------------------------------
  * Kinetic Monte Carlo: event-state / event-rate evaluation (reference rows
  * a11/a12).  Replaces EventStateCalculator::calculate_event_state +
  * _default_event_state_calculation
