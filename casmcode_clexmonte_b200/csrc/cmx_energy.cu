@@ -240,6 +240,133 @@ __global__ void __launch_bounds__(256) k_energy_lin16(EnergyArgs a) {
   }
 }
 
+// Warp-row variant of k_energy_lin16 (N0/16 a power of two <= 32, the shapes the
+// warp-row sweep kernel covers): one warp owns 32 / W whole rows per iteration, the
+// bytes just outside a lane's 16-byte window come from the neighbor lane by shuffle
+// (no side-word loads), rows advance with a fixed stride (one division per tile).
+// forward half of the FCC first shell as the generated basis orders it:
+// (0,0,1) (0,1,-1) (0,1,0) (1,-1,0) (1,0,-1) (1,0,0); MASK_CT = 0: mask from the arguments
+constexpr uint32_t kMaskFccFwd = 0x4148a0u;
+template <int NOCC, uint32_t MASK_CT>
+__global__ void __launch_bounds__(256) k_energy_row16(EnergyArgs a, uint32_t logW, uint32_t n_rows, uint32_t n_tiles,
+                                                      uint32_t any_m_rt, uint32_t any_p_rt) {
+  __shared__ unsigned long long sh_sum[6];
+  if (threadIdx.x < 6) sh_sum[threadIdx.x] = 0;
+  __syncthreads();
+  const Geom &g = a.g;
+  const int8_t *base = a.occ + (size_t)blockIdx.y * a.rep_stride;
+  const int32_t N0 = g.N0, N1 = g.N1, N2 = g.N2, layer = N0 * N1;
+  const bool halo = g.halo != 0;
+  const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
+  const bool any_m = MASK_CT ? ((MASK_CT & 0x1249249u) != 0) : (any_m_rt != 0);
+  const bool any_p = MASK_CT ? ((MASK_CT & 0x4924924u) != 0) : (any_p_rt != 0);
+  const uint32_t lane = threadIdx.x & 31u, Wm = a.W - 1u, c = lane & Wm, rl = lane >> logW;
+  const uint32_t lane_l = (lane & ~Wm) | ((c - 1u) & Wm), lane_r = (lane & ~Wm) | ((c + 1u) & Wm);
+  const uint32_t rpw_log = 5u - logW;
+  const uint32_t warp0 = blockIdx.x * 8u + (threadIdx.x >> 5), n_warps = gridDim.x * 8u;
+  unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t acc[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t it = 0;
+  for (uint32_t tile = warp0; tile < n_tiles; tile += n_warps) {
+    const uint32_t row_raw = (tile << rpw_log) + rl;
+    const bool on = row_raw < n_rows;  // a partial last tile: the idle lanes redo the last row, uncounted
+    uint32_t k, j;
+    fastdivmod(on ? row_raw : n_rows - 1u, a.divJ, k, j);
+    const int8_t *pc = base + ((size_t)((k + (uint32_t)g.halo) * (uint32_t)N1 + j) * (uint32_t)N0 + 16u * c);
+    int32_t dj[3], dk[3];
+    dj[0] = (j == 0) ? (N1 - 1) * N0 : -N0;
+    dj[1] = 0;
+    dj[2] = ((int32_t)j == N1 - 1) ? -(N1 - 1) * N0 : N0;
+    dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : -layer;
+    dk[1] = 0;
+    dk[2] = (!halo && (int32_t)k == N2 - 1) ? -(N2 - 1) * layer : layer;
+    uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0}, C[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
+        const bool center = (dz == 0 && dy == 0);
+        if (m3 == 0 && !center) continue;
+        const uint4 ch = *reinterpret_cast<const uint4 *>(pc + (ptrdiff_t)(dk[dz + 1] + dj[dy + 1]));
+        if (center) {
+          C[0] = ch.x;
+          C[1] = ch.y;
+          C[2] = ch.z;
+          C[3] = ch.w;
+        }
+        if ((m3 & 2u) && !center) {
+          A0[0] += ch.x;
+          A0[1] += ch.y;
+          A0[2] += ch.z;
+          A0[3] += ch.w;
+        }
+        if (m3 & 1u) {
+          Am[0] += ch.x;
+          Am[1] += ch.y;
+          Am[2] += ch.z;
+          Am[3] += ch.w;
+        }
+        if (m3 & 4u) {
+          Ap[0] += ch.x;
+          Ap[1] += ch.y;
+          Ap[2] += ch.z;
+          Ap[3] += ch.w;
+        }
+      }
+    }
+    const uint32_t sm = any_m ? __shfl_sync(0xffffffffu, Am[3], lane_l) : 0u;
+    const uint32_t sp = any_p ? __shfl_sync(0xffffffffu, Ap[0], lane_r) : 0u;
+    uint32_t cnt[4];
+    cnt[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
+    cnt[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
+    cnt[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
+    cnt[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t L = cnt[i] & 0x0F0F0F0Fu;
+        const uint32_t H = (cnt[i] >> 4) & 0x0F0F0F0Fu;
+        const uint32_t p1 = C[i] & 0x01010101u;
+        acc[0] += __popc(p1);
+        acc[2] = __dp4a(p1, L, acc[2]);
+        acc[3] = __dp4a(p1, H, acc[3]);
+        if (NOCC == 3) {
+          const uint32_t p2 = C[i] & 0x10101010u;
+          acc[1] += __popc(p2);
+          acc[4] = __dp4a(p2, L, acc[4]);
+          acc[5] = __dp4a(p2, H, acc[5]);
+        }
+      }
+    }
+    if ((++it & 1023u) == 0) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        tot[q] += acc[q];
+        acc[q] = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    tot[q] += acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot[q] += __shfl_down_sync(0xffffffffu, tot[q], o);
+    if ((threadIdx.x & 31) == 0 && tot[q]) atomicAdd(&sh_sum[q], tot[q]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    LinSums r;
+    r.n1 = sh_sum[0];
+    r.n2 = sh_sum[1];
+    r.sl1 = sh_sum[2];
+    r.sh1 = sh_sum[3];
+    r.sl2 = sh_sum[4];
+    r.sh2 = sh_sum[5];
+    a.sums[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = r;
+  }
+}
+
 __global__ void k_energy_lin_final(const LinSums *__restrict__ sums, int nb, long long n_cells, int z,
                                    const double *__restrict__ lin, double *out) {
   __shared__ unsigned long long sh[6];
@@ -361,6 +488,36 @@ static EnergyArgs energy_args(const cmx_state *s, int32_t first_replica) {
   return a;
 }
 
+// launch the bond-count pass over `n_rep` replicas starting at a.occ
+static int launch_energy_lin(const cmx_state *s, EnergyArgs &a, int nb, int n_rep) {
+  const SweepPlan &P = s->plan;
+  dim3 grid(nb, n_rep);
+  static const bool force_block = getenv("CMX_ENERGY_BLOCK") != nullptr;  // cross-check of the two kernels
+  if (P.row16 && !force_block) {
+    uint32_t logW = 0;
+    while ((1u << logW) < a.W) ++logW;
+    const uint32_t n_rows = (uint32_t)s->g.N1 * (uint32_t)s->g.N2, rpw = 32u >> logW;
+    const uint32_t n_tiles = (n_rows + rpw - 1) / rpw;
+    uint32_t any_m = 0, any_p = 0;
+    for (int q = 0; q < 9; ++q) {
+      any_m |= (P.e_mask >> (3 * q)) & 1u;
+      any_p |= (P.e_mask >> (3 * q + 2)) & 1u;
+    }
+    if (P.e_mask == kMaskFccFwd) {
+      if (P.nocc == 3) k_energy_row16<3, kMaskFccFwd><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+      else k_energy_row16<2, kMaskFccFwd><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+    } else {
+      if (P.nocc == 3) k_energy_row16<3, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+      else k_energy_row16<2, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+    }
+  } else {
+    if (P.nocc == 3) k_energy_lin16<3><<<grid, 256, 0, s->stream>>>(a);
+    else k_energy_lin16<2><<<grid, 256, 0, s->stream>>>(a);
+  }
+  CMX_CUDA(cudaGetLastError());
+  return CMX_OK;
+}
+
 int cmx_energy_fast_blocks(const cmx_state *s) {
   const uint32_t n_items = (uint32_t)(s->g.N0 / 16) * (uint32_t)s->g.N1 * (uint32_t)s->g.N2;
   const int cap = std::max(148, 148 * 8 / std::max(1, s->n_replicas));
@@ -372,11 +529,7 @@ int cmx_energy_fast_blocks(const cmx_state *s) {
 int cmx_energy_lin_batch(cmx_state *s, int nb, LinSums *d_sums) {
   EnergyArgs a = energy_args(s, 0);
   a.sums = d_sums;
-  dim3 grid(nb, s->n_replicas);
-  if (s->plan.nocc == 3) k_energy_lin16<3><<<grid, 256, 0, s->stream>>>(a);
-  else k_energy_lin16<2><<<grid, 256, 0, s->stream>>>(a);
-  CMX_CUDA(cudaGetLastError());
-  return CMX_OK;
+  return launch_energy_lin(s, a, nb, s->n_replicas);
 }
 
 int cmx_energy_fast(cmx_state *s, int32_t replica, double *E) {
@@ -390,9 +543,7 @@ int cmx_energy_fast(cmx_state *s, int32_t replica, double *E) {
     if (rc) return rc;
     a.sums = (LinSums *)s->d_scratch;
     double *d_E = (double *)(a.sums + nb);
-    if (P.nocc == 3) k_energy_lin16<3><<<nb, 256, 0, s->stream>>>(a);
-    else k_energy_lin16<2><<<nb, 256, 0, s->stream>>>(a);
-    CMX_CUDA(cudaGetLastError());
+    if ((rc = launch_energy_lin(s, a, nb, 1))) return rc;
     k_energy_lin_final<<<1, 256, 0, s->stream>>>(a.sums, nb, (long long)s->g.n_cells, P.e_z, P.d_e_lin, d_E);
     CMX_CUDA(cudaGetLastError());
     CMX_CUDA(cudaMemcpyAsync(E, d_E, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
