@@ -20,6 +20,7 @@ LIB_PATH = HERE / "libcmx_b200.so"
 
 CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
 CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC, CMX_SWEEP_BLOCK_KERNEL, CMX_SWEEP_FUSED = 1, 2, 4, 8
+CMX_SWEEP_THREAD_GENERIC = 16
 
 # every symbol include/cmx_b200.h declares
 EXPORTED_SYMBOLS = [

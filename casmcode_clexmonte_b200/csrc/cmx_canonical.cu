@@ -14,9 +14,14 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <set>
 
+#include <cooperative_groups.h>
+
 #include "cmx_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 static int invalid(const std::string &msg) {
   cmx_set_error(msg);
@@ -37,6 +42,7 @@ struct CanonicalPlan {
   long long *d_part = nullptr;  // [replica][blocks][2]: attempts, accepts
   double *d_part_dE = nullptr;  // [replica][blocks]
   int32_t blocks = 0;
+  int coop_capacity = -1;  // co-resident blocks of k_canonical_pairs_warp (0: no cooperative launch)
 };
 
 void cmx_canonical_free(cmx_state *s) {
@@ -145,6 +151,83 @@ __global__ void __launch_bounds__(128) k_canonical_pairs(CanonArgs a) {
     long long A = 0, C = 0;
     double E = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      A += sh_att[w];
+      C += sh_acc[w];
+      E += sh_sum[w];
+    }
+    size_t slot = (size_t)r * gridDim.x + blockIdx.x;
+    a.part[2 * slot] += A;
+    a.part[2 * slot + 1] += C;
+    a.part_dE[slot] += E;
+  }
+}
+
+// Warp-cooperative variant: one pair per WARP (cmx_warp_site_delta), and ALL colours of a
+// swap type in one cooperative launch with a grid barrier between colours -- a colour of
+// a wide-orbit model holds a few hundred pairs (the stride must exceed the interaction
+// range plus the translation), so one launch per colour is pure launch latency
+// (ZrO 48^3: 13 800 launches per sweep).  Occupations are read through L2 only: other
+// SMs wrote them before the barrier.  Same proposals, random bits and decision rule as
+// k_canonical_pairs.
+__global__ void __launch_bounds__(256) k_canonical_pairs_warp(CanonArgs a, GenTerms G, int stage_max,
+                                                              int colour_begin, int colour_end, int coop) {
+  extern __shared__ double sh_stage[];  // [8 warps][stage_max]
+  __shared__ long long sh_att[8], sh_acc[8];
+  __shared__ double sh_sum[8];
+  const int r = blockIdx.y;
+  const Geom &g = a.g;
+  int8_t *occ = a.occ + (size_t)r * g.rep_stride;
+  const double beta = a.beta[r];
+  const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  double *sh_val = sh_stage + (size_t)wib * stage_max;
+  long long n_att = 0, n_acc = 0;
+  double e_sum = 0.0;
+  for (int colour = colour_begin; colour < colour_end; ++colour) {
+    const int c0 = colour % a.S0, c1 = (colour / a.S0) % a.S1, c2 = colour / (a.S0 * a.S1);
+    const uint32_t ctr_hi = a.ctr_hi | (uint32_t)colour;
+    for (uint32_t item = blockIdx.x * 8u + wib; item < a.items; item += gridDim.x * 8u) {
+      uint32_t row, ii, kk, jj;
+      fastdivmod(item, a.div0, row, ii);
+      fastdivmod(row, a.div1, kk, jj);
+      const int i = (int)ii * a.S0 + c0, j = (int)jj * a.S1 + c1, k = (int)kk * a.S2 + c2;
+      int i2 = (i + a.t0) % g.N0, j2 = (j + a.t1) % g.N1, k2 = (k + a.t2) % g.N2;
+      i2 += (i2 < 0) ? g.N0 : 0;
+      j2 += (j2 < 0) ? g.N1 : 0;
+      k2 += (k2 < 0) ? g.N2 : 0;
+      const int64_t off_a = cmx_site_offset(g, a.ba, i, j, k);
+      const int64_t off_b = cmx_site_offset(g, a.bb, i2, j2, k2);
+      const int oa = cmx_dec((int)__ldcg(occ + off_a)), ob = cmx_dec((int)__ldcg(occ + off_b));
+      const int na = a.map_ab[ob], nb = a.map_ba[oa];
+      if (na < 0 || nb < 0 || na == oa) continue;  // warp-uniform
+      if (lane == 0) ++n_att;
+      double dE = cmx_warp_site_delta<true>(a.T, g, G, occ, sh_val, a.pa, i, j, k, oa, na, -1, 0, lane);
+      dE += cmx_warp_site_delta<true>(a.T, g, G, occ, sh_val, a.pb, i2, j2, k2, ob, nb, off_a, na, lane);
+      bool accept = dE < 0.0;
+      if (!accept) {
+        const uint32_t gid = (uint32_t)(((uint32_t)k * g.N1 + j) * g.N0 + i);
+        const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr_hi, a.k0, a.k1);
+        const unsigned long long u53 = ((unsigned long long)(ph.c[1] & 0x1FFFFFu) << 32) | ph.c[0];
+        accept = (double)u53 * (1.0 / 9007199254740992.0) < exp(-dE * beta);
+      }
+      if (accept && lane == 0) {
+        occ[off_a] = (int8_t)cmx_enc(g, na);
+        occ[off_b] = (int8_t)cmx_enc(g, nb);
+        ++n_acc;
+        e_sum += dE;
+      }
+    }
+    if (coop && colour + 1 < colour_end) cg::this_grid().sync();
+  }
+  if (lane == 0) {
+    sh_att[wib] = n_att;
+    sh_acc[wib] = n_acc;
+    sh_sum[wib] = e_sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long A = 0, C = 0;
+    double E = 0.0;
+    for (int w = 0; w < 8; ++w) {
       A += sh_att[w];
       C += sh_acc[w];
       E += sh_sum[w];
@@ -329,8 +412,30 @@ int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t
   uint32_t max_items = 1;
   for (auto const &sp : P.swaps)
     max_items = std::max<uint32_t>(max_items, (uint32_t)((g.n_cells) / sp.n_colours));
+  const bool warp = cmx_use_warp_generic(s);
+  const size_t stage_bytes = (size_t)SP.stage_max * 8 * sizeof(double);
   int blocks = (int)std::min<uint32_t>((max_items + 127) / 128,
                                        std::max(1, (148 * 16 + s->n_replicas - 1) / s->n_replicas));
+  bool coop = false;
+  if (warp) {
+    // one pair per warp, 8 warps per block; all blocks co-resident for the grid barrier
+    if (P.coop_capacity < 0) {
+      int per_sm = 0, dev = 0, sms = 0, can = 0;
+      if (stage_bytes > 48 * 1024)
+        CMX_CUDA(cudaFuncSetAttribute(k_canonical_pairs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canonical_pairs_warp, 256, stage_bytes) != cudaSuccess)
+        per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
+      P.coop_capacity = can ? per_sm * sms : 0;
+    }
+    const int want = (int)((max_items + 7) / 8);
+    const int cap = P.coop_capacity / std::max(1, s->n_replicas);
+    static const bool no_coop = getenv("CMX_CANONICAL_NO_COOP") != nullptr;
+    coop = cap >= 1 && !no_coop;
+    blocks = std::max(1, std::min(want, coop ? cap : std::max(1, 148 * 8 / s->n_replicas)));
+  }
   if (blocks != P.blocks || !P.d_part) {
     cudaFree(P.d_part);
     cudaFree(P.d_part_dE);
@@ -383,6 +488,21 @@ int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t
       a.items = n0 * n1 * n2;
       a.map_ab = P.d_map + sp.map_off_ab;
       a.map_ba = P.d_map + sp.map_off_ba;
+      if (warp) {
+        GenTerms G{SP.d_gt_beg, SP.d_gt_fbeg, SP.d_gt_vi, SP.d_act_beg, SP.d_act_n, SP.d_gt_w};
+        int stage_max = SP.stage_max;
+        a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 24) | ((uint32_t)q << 12);
+        if (coop) {
+          int c_begin = 0, c_end = sp.n_colours, one = 1;
+          void *args[6] = {&a, &G, &stage_max, &c_begin, &c_end, &one};
+          CMX_CUDA(cudaLaunchCooperativeKernel((const void *)k_canonical_pairs_warp, grid, dim3(256), args,
+                                               stage_bytes, s->stream));
+        } else {
+          for (int c = 0; c < sp.n_colours; ++c)
+            k_canonical_pairs_warp<<<grid, 256, stage_bytes, s->stream>>>(a, G, stage_max, c, c + 1, 0);
+        }
+        continue;
+      }
       uint32_t colour = 0;
       for (int c2 = 0; c2 < sp.S[2]; ++c2)
         for (int c1 = 0; c1 < sp.S[1]; ++c1)

@@ -108,6 +108,11 @@ struct SweepPlan {
   double *d_gt_w = nullptr;      // [n_gterms][max_occ][max_occ]
   int32_t *d_gt_fbeg = nullptr;  // [n_gterms+1]
   int32_t *d_gt_f = nullptr, *d_gt_n = nullptr;
+  // warp-cooperative evaluation: the neighbors a point position's terms read
+  // (act_n[act_beg[p] .. act_beg[p+1])), and per factor the index of its staged
+  // site-function value, slot * n_func + f
+  int32_t *d_gt_vi = nullptr, *d_act_beg = nullptr, *d_act_n = nullptr;
+  int32_t stage_max = 0;  // max over p of (active neighbors of p) * n_func
   // pair LUT: one sublattice, <= 3 occupants, offsets in {-1,0,1}^3,
   // one class of symmetry-equivalent neighbors
   int32_t nocc = 0;
@@ -190,6 +195,7 @@ struct cmx_state {
 
 int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
+bool cmx_use_warp_generic(const cmx_state *s);  // wide orbit sets: one site per warp
 void cmx_canonical_free(cmx_state *s);
 int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep, bool reset);
 int cmx_canonical_counters(cmx_state *s, cmx_counters *counters);
@@ -321,6 +327,48 @@ struct LocalFetch {  // synthetic neighborhood (LUT construction)
   const int8_t *nbr_occ;
   __device__ __forceinline__ int operator()(int n) const { return nbr_occ[n]; }
 };
+
+// ---- warp-cooperative folded delta E (generic evaluator) -----------------------
+struct GenTerms {
+  const int32_t *gt_beg, *gt_fbeg, *gt_vi, *act_beg, *act_n;
+  const double *gt_w;
+};
+// Single-site delta E of point position p at cell (i,j,k), occupant oi -> of, with one
+// overridden site (byte offset ov_off holds occupant ov_occ), evaluated by ONE WARP:
+//  1. the lanes stage phi_f(occupant) of every neighbor the terms of p read into the
+//     warp's shared array (one gather + wrap arithmetic per neighbor instead of one per
+//     factor: ZrO reads 225 neighbors through ~1400 factors);
+//  2. the terms are dealt to the lanes round robin, each a product of staged values;
+//  3. butterfly sum: every lane returns the same bits, whatever the grid.
+// CG: occupations through L2 only (kernels that synchronise the grid between colours).
+template <bool CG>
+__device__ __forceinline__ double cmx_warp_site_delta(const DevTables &T, const Geom &g, const GenTerms &G,
+                                                      const int8_t *occ, double *sh_val, int p, int i, int j,
+                                                      int k, int oi, int of, int64_t ov_off, int ov_occ,
+                                                      unsigned lane) {
+  const int mo = T.max_occ, nf = T.n_func;
+  const int ab = G.act_beg[p], ae = G.act_beg[p + 1];
+  for (int s = ab + (int)lane; s < ae; s += 32) {
+    const int n = G.act_n[s];
+    const int64_t no = cmx_nbr_offset(T, g, n, i, j, k, nullptr);
+    const int raw = CG ? (int)__ldcg(occ + no) : (int)occ[no];
+    const int o = (no == ov_off) ? ov_occ : cmx_dec(raw);
+    const double *ph = T.phi + ((size_t)T.nbr[n].w * nf) * mo + o;
+    double *dst = sh_val + (size_t)(s - ab) * nf;
+    for (int f = 0; f < nf; ++f) dst[f] = ph[(size_t)f * mo];
+  }
+  __syncwarp();
+  double part = 0.0;
+  for (int t = G.gt_beg[p] + (int)lane; t < G.gt_beg[p + 1]; t += 32) {
+    double v = G.gt_w[((size_t)t * mo + oi) * mo + of];
+    for (int q = G.gt_fbeg[t]; q < G.gt_fbeg[t + 1]; ++q) v *= sh_val[G.gt_vi[q]];
+    part += v;
+  }
+  __syncwarp();  // the staged values may be overwritten by the caller's next evaluation
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  return part;
+}
 
 // Faithful evaluation of one generated function (see clexulator_tables.py for
 // the canonical form): same association order as the C++ source, every

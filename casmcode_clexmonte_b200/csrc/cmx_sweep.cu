@@ -35,6 +35,9 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_gt_fbeg);
   cudaFree(p.d_gt_f);
   cudaFree(p.d_gt_n);
+  cudaFree(p.d_gt_vi);
+  cudaFree(p.d_act_beg);
+  cudaFree(p.d_act_n);
   cudaFree(p.d_pair_dE);
   cudaFree(p.d_tab);
   cudaFree(p.d_thr_lo);
@@ -646,6 +649,92 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// generic sweep kernel, warp-cooperative: one site per WARP (cmx_warp_site_delta).
+// Same random bits and the same decision rule as k_sweep_generic; dE differs from it
+// in the last bits only (summation order).  Wide orbit sets (ZrO: ~700 merged terms,
+// 225 neighbors per site) make the one-thread-per-site kernel latency bound and leave
+// most of the chip idle when a colour holds a few thousand sites.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sweep_generic_warp(GenericSweepArgs a, GenTerms G, int stage_max) {
+  extern __shared__ double sh_stage[];  // [8 warps][stage_max]
+  __shared__ long long sh_acc[8];
+  __shared__ double sh_sum[8];
+  const int r = blockIdx.y;
+  const Geom &g = a.g;
+  const DevTables &T = a.T;
+  int8_t *occ = a.occ + (size_t)r * g.rep_stride;
+  const int b = T.nlist_sublat[a.p];
+  const int nocc = T.n_occ[b];
+  const int mo = T.max_occ;
+  const double beta = a.beta[r];
+  const double *exch = a.exch + (size_t)r * a.exch_stride + (size_t)b * mo * mo;
+  const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  double *sh_val = sh_stage + (size_t)wib * stage_max;
+  long long n_acc = 0;
+  double e_sum = 0.0;
+  for (uint32_t item = blockIdx.x * 8u + wib; item < a.items; item += gridDim.x * 8u) {
+    uint32_t row, ii, kk, jj;
+    fastdivmod(item, a.div0, row, ii);
+    fastdivmod(row, a.div1, kk, jj);
+    const int i = (int)ii * a.S0 + a.c0, j = (int)jj * a.S1 + a.c1, k = (int)kk * a.S2 + a.c2;
+    const int64_t off = cmx_site_offset(g, b, i, j, k);
+    const int oi = cmx_dec(occ[off]);
+    int alt;
+    uint32_t u_hi, u_lo;
+    if (a.rng16) {
+      const uint32_t gid = (uint32_t)(((uint32_t)(k + a.k_offset) * g.N1 + j) * (g.N0 >> 4) + (i >> 4));
+      const uint32_t x = (uint32_t)i & 15u, q = x >> 1;
+      const uint32_t ctr = a.ctr_hi;
+      const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr, a.k0, a.k1);
+      const uint32_t R = ph.c[x >> 2];
+      const uint32_t field = (x & 2u) ? (R >> 16) : (R & 0xFFFFu);
+      alt = (nocc == 3) ? (int)(field >> 15) : 0;
+      u_hi = field & 0x7FFFu;
+      const Philox lo = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr | ((q < 4) ? 1u : 2u), a.k0, a.k1);
+      u_lo = lo.c[q & 3];
+    } else {
+      const uint32_t gid_lo = (uint32_t)(((uint64_t)(k + a.k_offset) * g.N1 + j) * g.N0 + i);
+      const Philox ph = philox4x32_10(gid_lo, (uint32_t)r | ((uint32_t)b << 24), a.sweep_lo,
+                                      a.ctr_hi, a.k0, a.k1);
+      alt = (int)__umulhi(ph.c[2], (uint32_t)(nocc - 1));
+      u_hi = ph.c[1] & 0x1FFFFFu;
+      u_lo = ph.c[0];
+    }
+    int of = oi + 1 + alt;
+    if (of >= nocc) of -= nocc;
+    double dE = cmx_warp_site_delta<false>(T, g, G, occ, sh_val, a.p, i, j, k, oi, of, -1, 0, lane);
+    dE -= exch[oi * mo + of];
+    bool accept = dE < 0.0;
+    if (!accept) {
+      const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
+      if (a.rng16) accept = u < (unsigned long long)ceil(exp(-dE * beta) * 140737488355328.0);
+      else accept = (double)u * (1.0 / 9007199254740992.0) < exp(-dE * beta);
+    }
+    if (accept && lane == 0) {
+      occ[off] = (int8_t)cmx_enc(g, of);
+      ++n_acc;
+      if (a.accum) e_sum += dE;
+    }
+  }
+  if (lane == 0) {
+    sh_acc[wib] = n_acc;
+    sh_sum[wib] = e_sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long A = 0;
+    double E = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      A += sh_acc[w];
+      E += sh_sum[w];
+    }
+    size_t slot = (size_t)r * gridDim.x + blockIdx.x;
+    a.part_acc[slot] += A;
+    a.part_dE[slot] += E;
+  }
+}
+
 __global__ void k_reduce_counters(const long long *__restrict__ part_acc,
                                   const double *__restrict__ part_dE, int nb,
                                   long long attempts, cmx_counters *out) {
@@ -746,6 +835,30 @@ int cmx_plan_sweep(cmx_state *s) {
   if ((rc = to_device(gt_f, &P.d_gt_f))) return rc;
   if ((rc = to_device(gt_n, &P.d_gt_n))) return rc;
   if ((rc = to_device(gt_w, &P.d_gt_w))) return rc;
+  {
+    // warp-cooperative evaluation: per point position the neighbors its terms read,
+    // per factor the index of the staged value
+    std::vector<int32_t> act_beg(1, 0), act_n, gt_vi(gt_n.size(), 0);
+    P.stage_max = 0;
+    for (int p = 0; p < np; ++p) {
+      std::vector<int32_t> slot(T.nlist_len, -1);
+      for (int tt = gt_beg[p]; tt < gt_beg[p + 1]; ++tt)
+        for (int f = gt_fbeg[tt]; f < gt_fbeg[tt + 1]; ++f) slot[gt_n[f]] = 0;
+      int ns = 0;
+      for (int n = 0; n < T.nlist_len; ++n)
+        if (slot[n] == 0) {
+          slot[n] = ns++;
+          act_n.push_back(n);
+        }
+      for (int tt = gt_beg[p]; tt < gt_beg[p + 1]; ++tt)
+        for (int f = gt_fbeg[tt]; f < gt_fbeg[tt + 1]; ++f) gt_vi[f] = slot[gt_n[f]] * T.n_func + gt_f[f];
+      act_beg.push_back((int32_t)act_n.size());
+      P.stage_max = std::max(P.stage_max, ns * T.n_func);
+    }
+    if ((rc = to_device(gt_vi, &P.d_gt_vi))) return rc;
+    if ((rc = to_device(act_beg, &P.d_act_beg))) return rc;
+    if ((rc = to_device(act_n, &P.d_act_n))) return rc;
+  }
 
   // ---- colouring: stride > interaction range along each axis.  Sites on
   // different sublattices of one cell interact through offset (0,0,0), so the
@@ -963,6 +1076,14 @@ static int sweep_pdl() {  // programmatic dependent launch of consecutive colour
 static int sweep_l2_mb() {  // lattice bytes (MB) a k-slice of the fused sweep kernel may touch
   static int v = env_int("CMX_SWEEP_L2_MB", 40);
   return v;
+}
+
+// wide orbit sets: one site per warp (k_sweep_generic_warp)
+bool cmx_use_warp_generic(const cmx_state *s) {
+  const SweepPlan &P = s->plan;
+  if ((s->sweep_flags & CMX_SWEEP_THREAD_GENERIC) || P.stage_max <= 0 || P.mut_points.empty()) return false;
+  if ((size_t)P.stage_max * 8 * sizeof(double) > 96 * 1024) return false;
+  return P.n_gterms / (int)P.mut_points.size() >= 96;
 }
 
 static bool use_pair(const cmx_state *s) {
@@ -1204,6 +1325,16 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   a.rng16 = P.rng16 ? 1 : 0;
   a.accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) ? 1 : 0;
   dim3 grid(P.part_blocks, s->n_replicas);
+  const bool warp = cmx_use_warp_generic(s) && !use_pair(s);
+  const size_t stage_bytes = (size_t)P.stage_max * 8 * sizeof(double);
+  GenTerms G{P.d_gt_beg, P.d_gt_fbeg, P.d_gt_vi, P.d_act_beg, P.d_act_n, P.d_gt_w};
+  if (warp && stage_bytes > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CMX_CUDA(cudaFuncSetAttribute(k_sweep_generic_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+  }
   uint32_t colour = 0;
   for (int c2 = 0; c2 < P.S[2]; ++c2)
     for (int c1 = 0; c1 < P.S[1]; ++c1)
@@ -1217,7 +1348,8 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
           a.p = p;
           a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) |
                      (a.rng16 ? ((col & 0xffu) << 8) : (col & 0xffffu));
-          k_sweep_generic<<<grid, 256, 0, s->stream>>>(a);
+          if (warp) k_sweep_generic_warp<<<grid, 256, stage_bytes, s->stream>>>(a, G, P.stage_max);
+          else k_sweep_generic<<<grid, 256, 0, s->stream>>>(a);
         }
   CMX_CUDA(cudaGetLastError());
   return CMX_OK;
@@ -1250,6 +1382,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
     items = (n_rows + RB - 1) / RB * 256;
   } else {
     items = (uint32_t)(s->g.N0 / P.S[0]) * (s->g.N1 / P.S[1]) * (s->g.N2 / P.S[2]);
+    if (cmx_use_warp_generic(s)) items = (uint32_t)std::min<uint64_t>((uint64_t)items * 32u, 0xFFFFFF00u);  // a warp per site
   }
   blocks = sweep_blocks_per_replica(items, s->n_replicas);
   if (P.part_blocks != blocks || !P.d_part_acc) {
@@ -1266,7 +1399,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
   if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_BLOCK_KERNEL |
-                         CMX_SWEEP_FUSED))
+                         CMX_SWEEP_FUSED | CMX_SWEEP_THREAD_GENERIC))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;  // the grid may change with the evaluator

@@ -240,6 +240,12 @@ int cmx_counters_reset(cmx_state *s);
  * the stamp polling, kept for the bit-exact cross-check and for further work). */
 #define CMX_SWEEP_BLOCK_KERNEL 4u
 #define CMX_SWEEP_FUSED 8u
+/* generic (term-list) evaluator variants: models with wide orbit sets (>= 96 merged
+ * terms per site, e.g. ZrO with triplets and quadruplets) evaluate one site per WARP
+ * (k_sweep_generic_warp, k_canonical_pairs_warp: neighborhood staged once, terms dealt
+ * to the lanes); THREAD_GENERIC forces one site per thread (same random bits and
+ * decisions; dE differs in the last bits through the summation order). */
+#define CMX_SWEEP_THREAD_GENERIC 16u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* synchronises the state's stream; counters[n_replicas] */
 int cmx_counters_read(cmx_state *s, cmx_counters *counters);

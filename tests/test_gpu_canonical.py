@@ -156,3 +156,42 @@ def test_canonical_matches_sequential_thermodynamics(dev_tables, systems, oracle
     se = np.hypot(np.std(ref_e, ddof=1), np.std(gpu_e, ddof=1)) / np.sqrt(n_runs)
     assert abs(np.mean(ref_e) - np.mean(gpu_e)) < 3 * se + 1e-4, (np.mean(ref_e), np.mean(gpu_e), se)
     st.close()
+
+
+@pytest.mark.parametrize("ensemble", ["semigrand", "canonical"])
+def test_warp_evaluator_equals_thread_evaluator(dev_tables, systems, ensemble):
+    """Wide orbit sets (ZrO: ~700 merged terms per site) are evaluated one site per warp
+    (cmx_warp_site_delta; canonical: all colours of a swap type in one cooperative launch
+    with grid barriers).  Same random bits and decision rule as the one-site-per-thread
+    kernels: identical trajectories and counters, dE sums equal to rounding."""
+    from casmcode_clexmonte_b200.potential import semigrand_exchange_table
+    sysd = systems["zro"]
+    N = (12, 8, 8)
+    n_cells = int(np.prod(N))
+    rng = np.random.default_rng(9)
+    occ = np.zeros(n_cells * len(sysd["occ_to_species"]), dtype=np.int32)
+    for b in sysd["mutable_sublats"]:
+        occ[b * n_cells:(b + 1) * n_cells] = rng.random(n_cells) < 0.3
+    out = []
+    for flags in (_capi.CMX_SWEEP_DE_SUM, _capi.CMX_SWEEP_DE_SUM | _capi.CMX_SWEEP_THREAD_GENERIC):
+        st, _, swaps = _state(dev_tables, systems, "zro", "eci", N, 900.0, occ, n_replicas=2)
+        ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [0.3], sysd["n_species"])
+        st.set_conditions(900.0, ex, 0)
+        st.set_conditions(500.0, ex, 1)
+        st.set_sweep_flags(flags)
+        if ensemble == "canonical":
+            st.canonical_set_swaps(swaps)
+            c1 = st.canonical_sweep(2, seed=3)
+            c2 = st.canonical_sweep(1, seed=3, first_sweep=2)
+        else:
+            c1 = st.sgc_sweep(2, seed=3)
+            c2 = st.sgc_sweep(1, seed=3, first_sweep=2)
+        out.append(([st.download_occ(r) for r in range(2)],
+                    [(c1[r].n_attempt + c2[r].n_attempt, c1[r].n_accept + c2[r].n_accept) for r in range(2)],
+                    [c1[r].dE_sum + c2[r].dE_sum for r in range(2)]))
+        st.close()
+    (occ_w, cnt_w, de_w), (occ_t, cnt_t, de_t) = out
+    for r in range(2):
+        assert (occ_w[r] == occ_t[r]).all()
+        assert cnt_w[r] == cnt_t[r] and cnt_w[r][1] > 0
+        assert de_w[r] == pytest.approx(de_t[r], rel=1e-10, abs=1e-9)

@@ -152,21 +152,49 @@ def c4():
         rate = cnt[0].n_attempt / (ms * 1e-3)
         emit(workload=f"c4: ZrO canonical O<->Va pair exchanges, {N}^3 cells (4 sublattices, 2 mutable), quadruplet basis (33 ECI), T=600 K",
              metric="attempted MC steps/s (each a two-site dE)", value=rate, single_site_dcorr_per_s=2 * rate, ms=ms,
-             sweeps=S, swap_types=len(swaps), accept_rate=cnt[0].n_accept / cnt[0].n_attempt, kernel="k_canonical_pairs",
+             sweeps=S, swap_types=len(swaps), accept_rate=cnt[0].n_accept / cnt[0].n_attempt, kernel="k_canonical_pairs_warp (one cooperative launch per swap type)",
              roofline={"bound": "l2 gather (reported against hbm)", "achieved": 2 * 226.0 * rate / 1e9, "peak": HBM,
                        "unit": "GB/s", "frac": 2 * 226.0 * rate / 1e9 / HBM, "algorithmic_bytes_per_single_site_dE": 226.0})
         info = st.sweep_info()
         st.sgc_sweep(1, seed=2)
         ms, cnt = timed(st, lambda: st.sgc_sweep(S, seed=2, first_sweep=1))
         rate = cnt[0].n_attempt / (ms * 1e-3)
-        emit(workload=f"c4b: ZrO semi-grand O/Va flips, {N}^3 cells, generic term-list evaluator ({info['n_colours']} colours)",
-             metric="attempted MC steps/s", value=rate, ms=ms, sweeps=S, kernel="k_sweep_generic",
+        emit(workload=f"c4b: ZrO semi-grand O/Va flips, {N}^3 cells, generic term-list evaluator, one site per warp ({info['n_colours']} colours)",
+             metric="attempted MC steps/s", value=rate, ms=ms, sweeps=S, kernel="k_sweep_generic_warp",
              bytes_per_step=info["bytes_per_step"], flops_per_step=info["flops_per_step"],
              roofline={"bound": "fp64 / l2 gather", "achieved_gflops": info["flops_per_step"] * rate / 1e9,
                        "achieved": info["bytes_per_step"] * rate / 1e9, "peak": HBM, "unit": "GB/s",
                        "frac": info["bytes_per_step"] * rate / 1e9 / HBM})
         st.close()
     t.close()
+
+
+def c4_cpu():
+    """Reference kernels (oracle/_ref ZrO clexulator) in the restated sequential loop, one core."""
+    try:
+        from oracle import oracle as O
+        if not O.available("zro"):
+            raise RuntimeError("oracle/_ref zro not built")
+    except Exception as e:  # noqa: BLE001
+        emit(workload="c4 cpu baseline", unavailable=str(e))
+        return
+    sysd = SYS["zro"]
+    N = 12
+    n_cells = N ** 3
+    rng = np.random.default_rng(1)
+    occ = np.zeros(n_cells * len(sysd["occ_to_species"]), dtype=np.int32)
+    for b in sysd["mutable_sublats"]:
+        occ[b * n_cells:(b + 1) * n_cells] = rng.random(n_cells) < 0.25
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=sysd["n_species"], Rt=np.array(sysd["axes"]["Rt"]), origin=np.array(sysd["axes"]["origin"]))
+    sc = O.RefClexulator("zro").supercell(N)
+    for mode, name in ((1, "canonical"), (0, "semi-grand")):
+        n_steps = 20000
+        r = sc.metropolis_run(mode, occ, prim, sysd["eci"]["index"], sysd["eci"]["value"], 600.0, 7, n_steps,
+                              param_chem_pot=np.array([0.0]) if mode == 0 else None)
+        emit(workload=f"c4 cpu baseline: ZrO {name} sequential Metropolis, reference generated kernels, {N}^3 cells",
+             metric="attempted MC steps/s", value=n_steps / r["seconds"], cores=1, kind="reference",
+             sample=f"{n_steps} steps on one core")
 
 
 def c5():
@@ -216,11 +244,11 @@ def c5():
 
 
 def main():
-    which = sys.argv[1:] or ["c2", "sample", "c4", "c5"]
+    which = sys.argv[1:] or ["c2", "sample", "c4", "c4cpu", "c5"]
     if not torch.cuda.is_available():
         raise SystemExit("bench_workloads.py: no CUDA device")
     for w in which:
-        {"c2": c2, "sample": sample, "c4": c4, "c5": c5}[w]()
+        {"c2": c2, "sample": sample, "c4": c4, "c4cpu": c4_cpu, "c5": c5}[w]()
 
 
 if __name__ == "__main__":
