@@ -348,6 +348,7 @@ __device__ __forceinline__ double cmx_warp_site_delta(const DevTables &T, const 
                                                       unsigned lane) {
   const int mo = T.max_occ, nf = T.n_func;
   const int ab = G.act_beg[p], ae = G.act_beg[p + 1];
+#pragma unroll 4
   for (int s = ab + (int)lane; s < ae; s += 32) {
     const int n = G.act_n[s];
     const int64_t no = cmx_nbr_offset(T, g, n, i, j, k, nullptr);
@@ -359,9 +360,11 @@ __device__ __forceinline__ double cmx_warp_site_delta(const DevTables &T, const 
   }
   __syncwarp();
   double part = 0.0;
+#pragma unroll 4
   for (int t = G.gt_beg[p] + (int)lane; t < G.gt_beg[p + 1]; t += 32) {
     double v = G.gt_w[((size_t)t * mo + oi) * mo + of];
-    for (int q = G.gt_fbeg[t]; q < G.gt_fbeg[t + 1]; ++q) v *= sh_val[G.gt_vi[q]];
+    const int qb = G.gt_fbeg[t], qe = G.gt_fbeg[t + 1];
+    for (int q = qb; q < qe; ++q) v *= sh_val[G.gt_vi[q]];
     part += v;
   }
   __syncwarp();  // the staged values may be overwritten by the caller's next evaluation

@@ -132,7 +132,7 @@ def sample():
 def c4():
     sysd = SYS["zro"]
     t = tables("zro")
-    for N in (24, 48):
+    for N in (24, 48, 96):
         n_cells = N ** 3
         st = _capi.State(t, (N, N, N), 1)
         st.set_eci(sysd["eci"]["index"], sysd["eci"]["value"])
