@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
     "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
+    "cmx_kmc_set_impact_table", "cmx_kmc_run_begin", "cmx_kmc_run", "cmx_kmc_current_rates",
     "cmx_sampler_create", "cmx_sampler_destroy", "cmx_sampler_set_param_chem_pot", "cmx_sampler_info",
     "cmx_sampler_reset", "cmx_sampler_sample", "cmx_sampler_read", "cmx_sweep_run",
 ]
@@ -96,6 +97,9 @@ class EventState(C.Structure):
 EVENT_STATE_DTYPE = np.dtype([("is_allowed", np.int32), ("is_normal", np.int32), ("dE_final", np.float64),
                               ("Ekra", np.float64), ("dE_activated", np.float64), ("freq", np.float64),
                               ("rate", np.float64)])
+
+KMC_STEP_DTYPE = np.dtype([("unitcell", np.int64), ("prim_event", np.int32), ("pad", np.int32),
+                           ("time_increment", np.float64), ("total_rate", np.float64)])
 
 _lib = None
 
@@ -158,6 +162,10 @@ def lib():
     L.cmx_kmc_destroy.restype = None
     L.cmx_kmc_event_states.argtypes = [vp, i64, vp, vp, vp, vp]
     L.cmx_kmc_all_rates.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.cmx_kmc_set_impact_table.argtypes = [vp, i32, vp, vp]
+    L.cmx_kmc_run_begin.argtypes = [vp, vp]
+    L.cmx_kmc_run.argtypes = [vp, i64, vp, i64, vp, vp, vp]
+    L.cmx_kmc_current_rates.argtypes = [vp, vp, vp]
     L.cmx_sampler_create.argtypes = [vp, i32, i32, vp, vp, i32, C.POINTER(vp)]
     L.cmx_sampler_destroy.argtypes = [vp]
     L.cmx_sampler_set_param_chem_pot.argtypes = [vp, i32, vp]
@@ -589,6 +597,7 @@ class Kmc:
             e.event_type = int(ev["event_type"])
             e.equivalent_index = int(ev["equivalent_index"])
         self.n_prim = len(prim_events)
+        self.event_types, self.prim_events = event_types, prim_events
         h = C.c_void_p()
         check(lib().cmx_kmc_create(state._h, len(event_types), types, len(prim_events), prim, C.byref(h)))
         self._h = h
@@ -615,6 +624,52 @@ class Kmc:
         assert out.itemsize == C.sizeof(EventState)
         check(lib().cmx_kmc_event_states(self._h, len(uc), _p(rp), _p(uc), _p(pe), _p(out)))
         return out
+
+    # ---- rejection-free KMC on the device (cmx_kmc_run_*)
+    def impact_table(self):
+        """Relative impact table (events/ImpactTable.cc:150-185) from the exported tables."""
+        from . import kmc as K
+        st = self.state
+        nbh = []
+        for ev in self.prim_events:
+            et = self.event_types[ev["event_type"]]
+            coef = sorted(set(int(x) for x in et["kra"][0]) | set(int(x) for x in et["freq"][0]))
+            nbh.append(K.required_update_neighborhood(st.tables.host, [int(x) for x in st.eci_index],
+                                                      et["local_tables"][ev["equivalent_index"]].host, coef,
+                                                      ev["sites"]))
+        return K.make_relative_impact_table(self.prim_events, nbh)
+
+    def set_impact_table(self, beg, entries) -> None:
+        beg = np.ascontiguousarray(beg, dtype=np.int32)
+        entries = np.ascontiguousarray(entries, dtype=np.int32).reshape(-1, 4)
+        if len(beg) != self.n_prim + 1:
+            raise CmxError(CMX_ERR_INVALID, "impact table: beg must have n_prim + 1 entries")
+        check(lib().cmx_kmc_set_impact_table(self._h, len(entries), _p(beg), _p(entries)))
+        self._impact = (beg, entries)
+
+    def run_begin(self, seeds) -> None:
+        """All rates from the current occupation, sum trees, std::mt19937_64(seeds[r]), time 0."""
+        if getattr(self, "_impact", None) is None:
+            self.set_impact_table(*self.impact_table())
+        seeds = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.state.n_replicas,)))
+        check(lib().cmx_kmc_run_begin(self._h, _p(seeds)))
+
+    def run(self, n_steps: int, log_cap: int = 0) -> dict:
+        """n_steps rejection-free events of every trajectory."""
+        R = self.state.n_replicas
+        log = np.zeros((R, log_cap), dtype=KMC_STEP_DTYPE) if log_cap else None
+        time, total = np.zeros(R), np.zeros(R)
+        done = np.zeros(R, dtype=np.int64)
+        check(lib().cmx_kmc_run(self._h, int(n_steps), _p(log), int(log_cap), _p(time), _p(total), _p(done)))
+        return dict(time=time, total_rate=total, n_steps=done, log=log)
+
+    def current_rates(self):
+        """(rates[replica][unitcell][prim_event], total[replica]) as the selector holds them."""
+        st = self.state
+        r = np.zeros((st.n_replicas, st.n_cells, self.n_prim), dtype=np.float64)
+        tot = np.zeros(st.n_replicas, dtype=np.float64)
+        check(lib().cmx_kmc_current_rates(self._h, _p(r), _p(tot)))
+        return r, tot
 
     def all_rates(self, rates: bool = True):
         """(rates[replica][unitcell][prim_event] or None, total[replica])"""

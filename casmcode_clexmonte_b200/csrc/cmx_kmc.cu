@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "cmx_internal.cuh"
+#include "cmx_mt64.cuh"
 
 static int invalid(const std::string &msg) {
   cmx_set_error(msg);
@@ -36,6 +37,17 @@ struct cmx_kmc {
   double *d_coef_val = nullptr;
   double *d_rates = nullptr;  // [replica][cell][prim]
   double *d_total = nullptr;  // [replica]
+  // rejection-free run (cmx_kmc_run_*)
+  int32_t *d_imp_beg = nullptr;  // [n_prim + 1]
+  int4 *d_imp = nullptr;         // (prim event, dx, dy, dz) relative to the event's unit cell
+  int32_t max_imp = 0;
+  std::vector<int64_t> level_size, level_off;  // sum tree above the leaves (= d_rates)
+  double *d_tree = nullptr;      // [replica][upper nodes]
+  Mt64 *d_mt = nullptr;          // [replica]
+  double *d_time = nullptr;      // [replica]
+  long long *d_pending = nullptr;  // [replica] event whose impact list is not yet applied, or -1
+  long long *d_steps = nullptr;    // [replica] steps done
+  bool run_ready = false;
 };
 
 struct KmcArgs {
@@ -206,6 +218,13 @@ extern "C" void cmx_kmc_destroy(cmx_kmc *k) {
   cudaFree(k->d_coef_val);
   cudaFree(k->d_rates);
   cudaFree(k->d_total);
+  cudaFree(k->d_imp_beg);
+  cudaFree(k->d_imp);
+  cudaFree(k->d_tree);
+  cudaFree(k->d_mt);
+  cudaFree(k->d_time);
+  cudaFree(k->d_pending);
+  cudaFree(k->d_steps);
   delete k;
 }
 
@@ -384,5 +403,371 @@ extern "C" int cmx_kmc_all_rates(cmx_kmc *k, double *rates, double *total, void 
     CMX_CUDA(cudaMemcpyAsync(rates, k->d_rates, sizeof(double) * tot, cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
   if (d_rates) *d_rates = k->d_rates;
+  return CMX_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Rejection-free KMC, whole steps on the device.
+//
+// Reference: kinetic_monte_carlo_v2 (include/casm/clexmonte/methods/kinetic_monte_carlo.hh:
+// 396-507) driving lotto::RejectionFreeEventSelector over the complete event list
+// (CompleteKineticEventData, monte_calculator/kinetic_events.hh:73-133; event ids in the
+// order of make_complete_event_id_list, events/CompleteEventList.cc:76-91: unit cell major):
+//   select_event (submodules/kmc-lotto/include/lotto/rejection_free.hpp:93-111):
+//     update the rates of the events impacted by the previous event (:151-159),
+//     total = root of the sum tree, dt = -log(u1) / total (event_selector.hpp:65-70),
+//     query = total * u2, descend the tree (event_rate_tree_impl.hpp:63-75,135-150:
+//     left if query <= left.rate, else subtract and go right),
+//   time += dt, apply the event (OccLocation::apply), remember its impact list.
+// The tree is lotto's InvertedBinarySumTree (sum_tree_impl.hpp:190-240): leaves joined
+// pairwise level by level, an odd node out is carried up unchanged; here as arrays per
+// level, parent = left + right in that order, so every partial sum has the reference's
+// bits.  u1, u2 come from std::mt19937_64 through lotto's (0, 1] distribution
+// (cmx_mt64.cuh).  One thread block per trajectory: the impact list (708 events for the
+// FCC A-B-Va system) is re-evaluated by the block's threads with the faithful
+// event-state function, then the touched tree paths are re-summed level by level.
+// ---------------------------------------------------------------------------
+#define CMX_KMC_MAX_LEVELS 40
+struct KmcTree {
+  int n_levels;  // levels above the leaves
+  long long size[CMX_KMC_MAX_LEVELS + 1];  // size[0] = leaves
+  long long off[CMX_KMC_MAX_LEVELS + 1];   // offset of level l >= 1 inside a replica's d_tree
+  long long upper;                         // nodes above the leaves per replica
+};
+
+__device__ __forceinline__ double *kmc_level(double *leaves, double *tree, const KmcTree &t, int l) {
+  return l == 0 ? leaves : tree + t.off[l];
+}
+
+// level l (>= 1) of every replica from level l - 1
+__global__ void k_kmc_tree_level(double *rates, double *tree, KmcTree t, int l, long long per) {
+  const int r = blockIdx.y;
+  double *leaves = rates + (size_t)r * per, *up = tree + (size_t)r * t.upper;
+  const double *child = kmc_level(leaves, up, t, l - 1);
+  double *node = kmc_level(leaves, up, t, l);
+  const long long nc = t.size[l - 1];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.size[l];
+       i += (long long)gridDim.x * blockDim.x)
+    node[i] = (2 * i + 1 < nc) ? __dadd_rn(child[2 * i], child[2 * i + 1]) : child[2 * i];
+}
+
+__global__ void k_kmc_seed(Mt64 *mt, const unsigned long long *seeds, double *time, long long *pending,
+                           long long *steps, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  mt_seed(mt[r], seeds[r]);
+  time[r] = 0.0;
+  pending[r] = -1;
+  steps[r] = 0;
+}
+
+struct KmcRunArgs {
+  KmcArgs a;
+  KmcTree t;
+  int n_prim;
+  long long per;  // leaves per replica
+  double *rates, *tree;
+  const int32_t *imp_beg;
+  const int4 *imp;
+  Mt64 *mt;
+  double *time;
+  long long *pending, *steps;
+  cmx_kmc_step *log;
+  long long log_cap;
+  long long n_steps;
+};
+
+// re-evaluate the events impacted by event `ev` and re-sum their tree paths
+__device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, double *leaves, double *up,
+                                 long long *sh_ids) {
+  const Geom &g = A.a.g;
+  const int pe = (int)(ev % A.n_prim);
+  const long long cell = ev / A.n_prim;
+  const int ci = (int)(cell % g.N0);
+  const long long rest = cell / g.N0;
+  const int cj = (int)(rest % g.N1), ck = (int)(rest / g.N1);
+  const int ib = A.imp_beg[pe], n_imp = A.imp_beg[pe + 1] - ib;
+  for (int q = threadIdx.x; q < n_imp; q += blockDim.x) {
+    const int4 e = A.imp[ib + q];
+    const int i2 = cmx_wrap(ci + e.y, g.N0), j2 = cmx_wrap(cj + e.z, g.N1), k2 = cmx_wrap(ck + e.w, g.N2);
+    const long long c2 = ((long long)k2 * g.N1 + j2) * g.N0 + i2;
+    cmx_event_state st;
+    kmc_event_state(A.a, r, c2, e.x, st);
+    const long long id = c2 * A.n_prim + e.x;
+    leaves[id] = st.rate;
+    sh_ids[q] = id;
+  }
+  __syncthreads();
+  for (int l = 1; l <= A.t.n_levels; ++l) {
+    const double *child = kmc_level(leaves, up, A.t, l - 1);
+    double *node = kmc_level(leaves, up, A.t, l);
+    const long long nc = A.t.size[l - 1];
+    for (int q = threadIdx.x; q < n_imp; q += blockDim.x) {
+      const long long i = sh_ids[q] >> l;  // several ids may share a parent: same value written
+      node[i] = (2 * i + 1 < nc) ? __dadd_rn(child[2 * i], child[2 * i + 1]) : child[2 * i];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
+  extern __shared__ long long sh_ids[];
+  __shared__ long long sh_ev;
+  const int r = blockIdx.x;
+  const Geom &g = A.a.g;
+  double *leaves = A.rates + (size_t)r * A.per, *up = A.tree + (size_t)r * A.t.upper;
+  int8_t *occ = const_cast<int8_t *>(A.a.occ) + (size_t)r * g.rep_stride;
+  long long pending = A.pending[r];
+  double time = A.time[r];
+  long long steps = A.steps[r];
+  for (long long step = 0; step < A.n_steps; ++step) {
+    if (pending >= 0) kmc_apply_impact(A, r, pending, leaves, up, sh_ids);
+    if (threadIdx.x == 0) {
+      const double total = *kmc_level(leaves, up, A.t, A.t.n_levels);
+      long long ev = -1;
+      if (total > 0.0) {
+        Mt64 &mt = A.mt[r];
+        const double dt = __ddiv_rn(-log(mt_unit_interval(mt)), total);
+        double q = __dmul_rn(total, mt_unit_interval(mt));
+        long long idx = 0;
+        for (int l = A.t.n_levels; l > 0; --l) {
+          const double *child = kmc_level(leaves, up, A.t, l - 1);
+          const double left = child[2 * idx];
+          if (q <= left || 2 * idx + 1 >= A.t.size[l - 1]) {
+            idx = 2 * idx;
+          } else {
+            q = __dsub_rn(q, left);
+            idx = 2 * idx + 1;
+          }
+        }
+        ev = idx;
+        time = __dadd_rn(time, dt);
+        // OccLocation::apply: every site of the event takes its final occupant
+        const cmx_prim_event &E = A.a.prim[(int)(ev % A.n_prim)];
+        const long long cell = ev / A.n_prim;
+        const int ci = (int)(cell % g.N0);
+        const long long rest = cell / g.N0;
+        const int cj = (int)(rest % g.N1), ck = (int)(rest / g.N1);
+        for (int s = 0; s < E.n_sites; ++s) {
+          const int i2 = cmx_wrap(ci + E.site[s][1], g.N0), j2 = cmx_wrap(cj + E.site[s][2], g.N1),
+                    k2 = cmx_wrap(ck + E.site[s][3], g.N2);
+          occ[cmx_site_offset(g, E.site[s][0], i2, j2, k2)] = (int8_t)cmx_enc(g, E.occ_final[s]);
+        }
+        if (A.log && steps < A.log_cap) {
+          cmx_kmc_step &L = A.log[(size_t)r * A.log_cap + steps];
+          L.unitcell = cell;
+          L.prim_event = (int32_t)(ev % A.n_prim);
+          L.pad = 0;
+          L.time_increment = dt;
+          L.total_rate = total;
+        }
+        ++steps;
+      }
+      sh_ev = ev;
+    }
+    __syncthreads();
+    pending = sh_ev;
+    if (pending < 0) break;  // no event can happen (total rate 0)
+  }
+  // leave rates and tree consistent with the occupation (the reference does this at the
+  // start of the next select_event; the update is idempotent)
+  if (pending >= 0) kmc_apply_impact(A, r, pending, leaves, up, sh_ids);
+  if (threadIdx.x == 0) {
+    A.pending[r] = -1;
+    A.time[r] = time;
+    A.steps[r] = steps;
+  }
+}
+
+extern "C" int cmx_kmc_set_impact_table(cmx_kmc *k, int32_t n_entries, const int32_t *beg,
+                                        const int32_t *entries) {
+  if (!k || !beg || (n_entries && !entries) || n_entries < 0) return invalid("cmx_kmc_set_impact_table: bad argument");
+  if (beg[0] != 0 || beg[k->n_prim] != n_entries) return invalid("cmx_kmc_set_impact_table: inconsistent offsets");
+  const Geom &g = k->s->g;
+  int max_imp = 0;
+  for (int p = 0; p < k->n_prim; ++p) {
+    if (beg[p + 1] < beg[p]) return invalid("cmx_kmc_set_impact_table: offsets not ascending");
+    max_imp = std::max(max_imp, beg[p + 1] - beg[p]);
+  }
+  std::vector<int4> imp(n_entries);
+  for (int q = 0; q < n_entries; ++q) {
+    const int32_t *e = entries + 4 * q;
+    if (e[0] < 0 || e[0] >= k->n_prim) return invalid("cmx_kmc_set_impact_table: prim event out of range");
+    if (std::abs(e[1]) > g.N0 || std::abs(e[2]) > g.N1 || std::abs(e[3]) > g.N2)
+      return invalid("cmx_kmc_set_impact_table: supercell smaller than the impact neighborhood");
+    imp[q] = make_int4(e[0], e[1], e[2], e[3]);
+  }
+  CMX_CUDA(cudaSetDevice(k->s->t->device));
+  cudaFree(k->d_imp_beg);
+  cudaFree(k->d_imp);
+  k->d_imp_beg = nullptr;
+  k->d_imp = nullptr;
+  std::vector<int32_t> b(beg, beg + k->n_prim + 1);
+  int rc;
+  if ((rc = kmc_to_device(b, &k->d_imp_beg)) || (rc = kmc_to_device(imp, &k->d_imp))) return rc;
+  k->max_imp = max_imp;
+  k->run_ready = false;
+  return CMX_OK;
+}
+
+static KmcTree kmc_tree(const cmx_kmc *k) {
+  KmcTree t;
+  t.n_levels = (int)k->level_size.size() - 1;
+  for (size_t l = 0; l < k->level_size.size(); ++l) {
+    t.size[l] = k->level_size[l];
+    t.off[l] = k->level_off[l];
+  }
+  t.upper = k->level_off.back() + k->level_size.back();
+  return t;
+}
+
+// all rates from the current occupation, the sum tree, seeds, time = 0
+extern "C" int cmx_kmc_run_begin(cmx_kmc *k, const uint64_t *seeds) {
+  if (!k || !seeds) return invalid("cmx_kmc_run_begin: null argument");
+  if (!k->d_imp_beg) {
+    cmx_set_error("cmx_kmc_run_begin: no impact table (cmx_kmc_set_impact_table)");
+    return CMX_ERR_STATE;
+  }
+  cmx_state *s = k->s;
+  const int R = s->n_replicas;
+  int rc = cmx_kmc_all_rates(k, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  const long long per = (long long)s->g.n_cells * k->n_prim;
+  k->level_size.assign(1, per);
+  k->level_off.assign(1, 0);
+  long long off = 0;
+  while (k->level_size.back() > 1) {
+    const long long n = (k->level_size.back() + 1) / 2;
+    k->level_off.push_back(off);
+    k->level_size.push_back(n);
+    off += n;
+  }
+  if ((int)k->level_size.size() - 1 > CMX_KMC_MAX_LEVELS) return invalid("cmx_kmc_run_begin: event list too large");
+  if (k->level_size.size() == 1) {  // a single event: the root is the leaf
+    k->level_off.push_back(0);
+    k->level_size.push_back(1);
+    off = 1;
+  }
+  const KmcTree t = kmc_tree(k);
+  cudaFree(k->d_tree);
+  cudaFree(k->d_mt);
+  cudaFree(k->d_time);
+  cudaFree(k->d_pending);
+  cudaFree(k->d_steps);
+  k->d_tree = nullptr;
+  k->d_mt = nullptr;
+  k->d_time = nullptr;
+  k->d_pending = nullptr;
+  k->d_steps = nullptr;
+  CMX_CUDA(cudaMalloc((void **)&k->d_tree, sizeof(double) * (size_t)t.upper * R));
+  CMX_CUDA(cudaMalloc((void **)&k->d_mt, sizeof(Mt64) * R));
+  CMX_CUDA(cudaMalloc((void **)&k->d_time, sizeof(double) * R));
+  CMX_CUDA(cudaMalloc((void **)&k->d_pending, sizeof(long long) * R));
+  CMX_CUDA(cudaMalloc((void **)&k->d_steps, sizeof(long long) * R));
+  for (int l = 1; l <= t.n_levels; ++l) {
+    dim3 grid((unsigned)std::min<long long>((t.size[l] + 255) / 256, 1024), R);
+    k_kmc_tree_level<<<grid, 256, 0, s->stream>>>(k->d_rates, k->d_tree, t, l, per);
+  }
+  CMX_CUDA(cudaGetLastError());
+  rc = cmx_scratch(s, sizeof(unsigned long long) * R);
+  if (rc) return rc;
+  CMX_CUDA(cudaMemcpyAsync(s->d_scratch, seeds, sizeof(unsigned long long) * R, cudaMemcpyHostToDevice, s->stream));
+  k_kmc_seed<<<(R + 63) / 64, 64, 0, s->stream>>>(k->d_mt, (const unsigned long long *)s->d_scratch, k->d_time,
+                                                 k->d_pending, k->d_steps, R);
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  k->run_ready = true;
+  return CMX_OK;
+}
+
+// n_steps events of every trajectory.  log[n_replicas][log_cap] (may be NULL) receives the
+// first log_cap steps since cmx_kmc_run_begin; time / total_rate / n_steps_done [n_replicas]
+// (each may be NULL): simulated time, current total rate, steps done so far.
+extern "C" int cmx_kmc_run(cmx_kmc *k, int64_t n_steps, cmx_kmc_step *log, int64_t log_cap, double *time,
+                           double *total_rate, int64_t *n_steps_done) {
+  if (!k) return invalid("cmx_kmc_run: null handle");
+  if (!k->run_ready) {
+    cmx_set_error("cmx_kmc_run: call cmx_kmc_run_begin first");
+    return CMX_ERR_STATE;
+  }
+  if (n_steps < 0 || log_cap < 0 || (log_cap && !log)) return invalid("cmx_kmc_run: bad argument");
+  cmx_state *s = k->s;
+  const int R = s->n_replicas;
+  KmcRunArgs A;
+  int rc = kmc_args(k, A.a, "cmx_kmc_run");
+  if (rc) return rc;
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  A.t = kmc_tree(k);
+  A.n_prim = k->n_prim;
+  A.per = (long long)s->g.n_cells * k->n_prim;
+  A.rates = k->d_rates;
+  A.tree = k->d_tree;
+  A.imp_beg = k->d_imp_beg;
+  A.imp = k->d_imp;
+  A.mt = k->d_mt;
+  A.time = k->d_time;
+  A.pending = k->d_pending;
+  A.steps = k->d_steps;
+  A.log = nullptr;
+  A.log_cap = log_cap;
+  A.n_steps = n_steps;
+  cmx_kmc_step *d_log = nullptr;
+  if (log_cap) {
+    CMX_CUDA(cudaMalloc((void **)&d_log, sizeof(cmx_kmc_step) * (size_t)R * log_cap));
+    CMX_CUDA(cudaMemcpyAsync(d_log, log, sizeof(cmx_kmc_step) * (size_t)R * log_cap, cudaMemcpyHostToDevice, s->stream));
+    A.log = d_log;
+  }
+  const size_t smem = sizeof(long long) * std::max(1, k->max_imp);
+  if (smem > 48 * 1024) {
+    cudaFree(d_log);
+    return invalid("cmx_kmc_run: impact lists longer than 6144 events are not supported");
+  }
+  k_kmc_run<<<R, 256, smem, s->stream>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(d_log);
+    cmx_set_error(std::string("cmx_kmc_run: ") + cudaGetErrorString(e));
+    return CMX_ERR_CUDA;
+  }
+  if (log_cap)
+    CMX_CUDA(cudaMemcpyAsync(log, d_log, sizeof(cmx_kmc_step) * (size_t)R * log_cap, cudaMemcpyDeviceToHost, s->stream));
+  if (time) CMX_CUDA(cudaMemcpyAsync(time, k->d_time, sizeof(double) * R, cudaMemcpyDeviceToHost, s->stream));
+  if (n_steps_done)
+    CMX_CUDA(cudaMemcpyAsync(n_steps_done, k->d_steps, sizeof(long long) * R, cudaMemcpyDeviceToHost, s->stream));
+  std::vector<double> roots;
+  if (total_rate) {
+    // the root of replica r sits at the end of its block of upper levels
+    const KmcTree &t = A.t;
+    CMX_CUDA(cudaMemcpy2DAsync(total_rate, sizeof(double), k->d_tree + t.off[t.n_levels], sizeof(double) * t.upper,
+                               sizeof(double), R, cudaMemcpyDeviceToHost, s->stream));
+  }
+  e = cudaStreamSynchronize(s->stream);
+  cudaFree(d_log);
+  if (e != cudaSuccess) {
+    cmx_set_error(std::string("cmx_kmc_run: ") + cudaGetErrorString(e));
+    return CMX_ERR_CUDA;
+  }
+  return CMX_OK;
+}
+
+// rates and total rates as the selector currently holds them (no re-evaluation):
+// rates[n_replicas][n_cells][n_prim], total[n_replicas]; either may be NULL
+extern "C" int cmx_kmc_current_rates(cmx_kmc *k, double *rates, double *total) {
+  if (!k) return invalid("cmx_kmc_current_rates: null handle");
+  if (!k->run_ready) {
+    cmx_set_error("cmx_kmc_current_rates: call cmx_kmc_run_begin first");
+    return CMX_ERR_STATE;
+  }
+  cmx_state *s = k->s;
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  const KmcTree t = kmc_tree(k);
+  const size_t per = (size_t)s->g.n_cells * k->n_prim;
+  if (rates)
+    CMX_CUDA(cudaMemcpyAsync(rates, k->d_rates, sizeof(double) * per * s->n_replicas, cudaMemcpyDeviceToHost, s->stream));
+  if (total)
+    CMX_CUDA(cudaMemcpy2DAsync(total, sizeof(double), k->d_tree + t.off[t.n_levels], sizeof(double) * t.upper,
+                               sizeof(double), s->n_replicas, cudaMemcpyDeviceToHost, s->stream));
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
   return CMX_OK;
 }

@@ -83,3 +83,69 @@ def complete_event_list(n_cells: int, n_prim_events: int):
     uc = np.repeat(np.arange(n_cells, dtype=np.int64), n_prim_events)
     pe = np.tile(np.arange(n_prim_events, dtype=np.int32), n_cells)
     return uc, pe
+
+
+# ---------------------------------------------------------------------------
+# impact table (which event rates must be recomputed after an event happened)
+# ---------------------------------------------------------------------------
+def _function_sites(t, gbeg, c) -> set:
+    """Neighbor-list indices read by function `c` of a group table (global_gbeg or
+    delta_gbeg row) of exported Clexulator tables."""
+    used = set()
+    for g in range(int(gbeg[c]), int(gbeg[c + 1])):
+        for el in range(int(t.group_ebeg[g]), int(t.group_ebeg[g + 1])):
+            for tm in range(int(t.elem_tbeg[el]), int(t.elem_tbeg[el + 1])):
+                for f in range(int(t.term_fbeg[tm]), int(t.term_fbeg[tm + 1])):
+                    used.add(int(t.factor_n[f]))
+    return used
+
+
+def required_update_neighborhood(formation_tables, eci_index, local_tables, coef_index, sites) -> set:
+    """Sites (b, i, j, k), relative to the event's unit cell, whose occupation the rate
+    of a prim event depends on -- EventImpactInfo::required_update_neighborhood
+    (src/casm/clexmonte/events/event_methods.cc:157-246 builds it from the
+    formation-energy cluster-expansion neighborhood of the event's sites and the
+    local-cluster-expansion neighborhoods of kra and freq).  Here it is read off the
+    exported tables: the event's own sites (event_is_allowed), for each of them the
+    neighbors its selected delta functions read (dE_final), and the neighbors the
+    selected functions of the equivalent's local clexulator read (E_kra, freq)."""
+    ft = formation_tables
+    nbr = np.asarray(ft.nbr).reshape(-1, 4)
+    nlist_sublat = [int(x) for x in np.asarray(ft.nlist_sublat)]
+    out = set()
+    for b, di, dj, dk in sites:
+        out.add((int(b), int(di), int(dj), int(dk)))
+        if int(b) not in nlist_sublat:
+            continue
+        p = nlist_sublat.index(int(b))
+        for c in eci_index:
+            for n in _function_sites(ft, ft.delta_gbeg, p * int(ft.corr_size) + int(c)):
+                o = nbr[n]
+                out.add((int(o[3]), int(di + o[0]), int(dj + o[1]), int(dk + o[2])))
+    lt = local_tables
+    lnbr = np.asarray(lt.nbr).reshape(-1, 4)
+    for c in coef_index:
+        for n in _function_sites(lt, lt.global_gbeg, int(c)):
+            o = lnbr[n]
+            out.add((int(o[3]), int(o[0]), int(o[1]), int(o[2])))
+    return out
+
+
+def make_relative_impact_table(prim_events: Sequence[dict], neighborhoods: Sequence[set]):
+    """make_relative_impact_table (src/casm/clexmonte/events/ImpactTable.cc:150-185):
+    table[j] = events (i, translation) whose rate must be recomputed after prim event j
+    happened in the origin unit cell: a site event j changes (its phenomenal sites) lies
+    in the required update neighborhood of event i translated by `translation`.
+    Returns (beg[n_prim + 1], entries[n][4] = (i, dx, dy, dz)), entries sorted."""
+    beg, entries = [0], []
+    for ev_j in prim_events:
+        rows = set()
+        for i, nb_i in enumerate(neighborhoods):
+            for (b, x, y, z) in nb_i:
+                for (pb, px, py, pz) in ev_j["sites"]:
+                    if int(pb) == b:
+                        # event i at cell (phenomenal site - neighborhood offset) reads that site
+                        rows.add((i, int(px) - x, int(py) - y, int(pz) - z))
+        entries.extend(sorted(rows))
+        beg.append(len(entries))
+    return np.asarray(beg, dtype=np.int32), np.asarray(entries, dtype=np.int32).reshape(-1, 4)

@@ -434,6 +434,39 @@ int cmx_kmc_event_states(cmx_kmc *k, int64_t n, const int32_t *replica,
  * (d_rates) for the caller's selector. */
 int cmx_kmc_all_rates(cmx_kmc *k, double *rates, double *total, void **d_rates);
 
+/* -------------------------------------------------------------------------
+ * Rejection-free KMC, whole steps on the device: every
+ * replica of the state is an independent trajectory, one thread block each.
+ * Replaces kinetic_monte_carlo_v2 (methods/kinetic_monte_carlo.hh:396-507) with
+ * lotto::RejectionFreeEventSelector over the complete event list
+ * (submodules/kmc-lotto/include/lotto/rejection_free.hpp:50-198; tree:
+ * sum_tree_impl.hpp:190-240, event_rate_tree_impl.hpp:63-75,135-150; random numbers:
+ * std::mt19937_64 + lotto::RandomGeneratorT, random.hpp:35-91): same tree shape, same
+ * summation order, same draws -> the same event sequence as the reference selector
+ * given the same rates and seed.  Event id = unitcell * n_prim_events + prim_event
+ * (make_complete_event_id_list, events/CompleteEventList.cc:76-91).
+ * ------------------------------------------------------------------------- */
+typedef struct cmx_kmc_step {
+  int64_t unitcell;
+  int32_t prim_event, pad;
+  double time_increment; /* -log(u) / total_rate                      */
+  double total_rate;     /* total rate the event was selected from    */
+} cmx_kmc_step;
+/* Relative impact table (make_relative_impact_table, events/ImpactTable.cc:150-185):
+ * entries[beg[j] .. beg[j+1]) = (prim event i, dx, dy, dz): after prim event j happened in
+ * unit cell c the rate of event i in cell c + (dx,dy,dz) must be recomputed.
+ * casmcode_clexmonte_b200.kmc.make_relative_impact_table builds it from the tables. */
+int cmx_kmc_set_impact_table(cmx_kmc *k, int32_t n_entries, const int32_t *beg, const int32_t *entries);
+/* (Re)start: all rates from the current occupation, the sum tree, one seed per
+ * trajectory, time = 0. */
+int cmx_kmc_run_begin(cmx_kmc *k, const uint64_t *seeds);
+/* n_steps events of every trajectory; see csrc/cmx_kmc.cu for the arguments. */
+int cmx_kmc_run(cmx_kmc *k, int64_t n_steps, cmx_kmc_step *log, int64_t log_cap, double *time,
+                double *total_rate, int64_t *n_steps_done);
+/* The selector's current leaves and roots, not re-evaluated:
+ * rates[n_replicas][n_cells][n_prim], total[n_replicas] (either may be NULL). */
+int cmx_kmc_current_rates(cmx_kmc *k, double *rates, double *total);
+
 /* Test hook: replay `n` draws of the device-side restatement of
  * std::mt19937_64(seed) + libstdc++ distributions (kind 0 = raw 64-bit,
  * 1 = uniform_int_distribution<long>(0,int_max), 2 =

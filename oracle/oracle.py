@@ -308,3 +308,59 @@ def event_state(sc_formation: "RefSupercell", sc_local: "RefSupercell", occ, uni
     st["rate"] = fr * float(np.exp(-beta * dEa))
     st["local_corr"] = local_corr
     return st
+
+
+# ---------------------------------------------------------------------------
+# the reference's own KMC event selector (oracle/_ref/libkmc_lotto.so, kmc_lotto.cpp)
+# ---------------------------------------------------------------------------
+LOTTO_PATH = REF_DIR / "libkmc_lotto.so"
+_RATE_CB = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_long)
+_lotto = None
+
+
+def lotto_available() -> bool:
+    return LOTTO_PATH.exists()
+
+
+def _lotto_lib():
+    global _lotto
+    if _lotto is None:
+        L = C.CDLL(str(LOTTO_PATH))
+        L.lotto_create.restype = C.c_void_p
+        L.lotto_create.argtypes = [C.c_long, _RATE_CB, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong]
+        L.lotto_destroy.argtypes = [C.c_void_p]
+        L.lotto_select.restype = C.c_long
+        L.lotto_select.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.lotto_get_rate.restype = C.c_double
+        L.lotto_get_rate.argtypes = [C.c_void_p, C.c_long]
+        _lotto = L
+    return _lotto
+
+
+class LottoSelector:
+    """lotto::RejectionFreeEventSelector<long, ., std::mt19937_64> (the reference's
+    submodules/kmc-lotto, compiled unmodified) over event ids 0..n_events-1.
+    rate_fn(event_id) -> float is called for the initial rates and for every impacted
+    event; impacted[e] lists the event ids to update after event e."""
+
+    def __init__(self, n_events: int, rate_fn, impacted, seed: int):
+        self._cb = _RATE_CB(lambda ctx, e: float(rate_fn(int(e))))
+        beg = np.zeros(n_events + 1, dtype=np.int64)
+        for e in range(n_events):
+            beg[e + 1] = beg[e] + len(impacted[e])
+        imp = (np.concatenate([np.asarray(impacted[e], dtype=np.int64) for e in range(n_events)])
+               if beg[-1] else np.zeros(1, dtype=np.int64))
+        self._h = _lotto_lib().lotto_create(n_events, self._cb, None, _p(beg), _p(np.ascontiguousarray(imp)), int(seed))
+
+    def select(self):
+        dt, tot = C.c_double(), C.c_double()
+        e = _lotto_lib().lotto_select(self._h, C.byref(dt), C.byref(tot))
+        return int(e), dt.value, tot.value
+
+    def rate(self, event_id: int) -> float:
+        return _lotto_lib().lotto_get_rate(self._h, int(event_id))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lotto_lib().lotto_destroy(self._h)
+            self._h = None

@@ -176,3 +176,121 @@ def test_kmc_error_paths(kmc_tables, systems):
         _capi.Kmc(st, dev_types, bad)
     kmc.close()
     st.close()
+
+
+def _impacted_ids(N, n_prim, beg, ent):
+    """Absolute impact lists of the complete event list from the relative table."""
+    N0, N1, N2 = N
+    n_cells = N0 * N1 * N2
+    out = []
+    for c in range(n_cells):
+        i, j, k = c % N0, (c // N0) % N1, c // (N0 * N1)
+        for pe in range(n_prim):
+            rows = ent[beg[pe]:beg[pe + 1]]
+            cells = ((i + rows[:, 1]) % N0) + N0 * (((j + rows[:, 2]) % N1) + N1 * ((k + rows[:, 3]) % N2))
+            out.append(np.unique(cells.astype(np.int64) * n_prim + rows[:, 0]))
+    return out
+
+
+def test_kmc_run_matches_reference_selector(kmc_tables, systems, oracle):
+    """whole KMC steps on the device reproduce the event sequence of the
+    reference's own selector (lotto::RejectionFreeEventSelector, compiled unmodified into
+    oracle/_ref/libkmc_lotto.so, seeded std::mt19937_64) fed with event rates from the
+    reference's generated kernels (oracle.event_state) on the same initial occupation:
+    identical (unit cell, prim event) at every step; time steps and total rates to 1e-12
+    (device exp/log vs glibc)."""
+    if oracle is None or not oracle.lotto_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    N = (6, 6, 6)
+    n = 216
+    R, n_steps = 2, 40
+    occ = rng.choice(3, size=(R, n), p=[0.55, 0.35, 0.10]).astype(np.int32)
+    T = [1200.0, 900.0]
+    seeds = [11, 2026]
+    eci = systems["fcc"]["eci_dense"]
+    st, kmc, prim = _kmc(kmc_tables, systems, N, occ, eci["index"], eci["value"], T, n_replicas=R)
+    kmc.run_begin(seeds)
+    out = kmc.run(n_steps, log_cap=n_steps)
+    assert (out["n_steps"] == n_steps).all()
+    beg, ent = kmc._impact
+    impacted = _impacted_ids(N, len(prim), beg, ent)
+    types = _types(systems)
+    form = oracle.RefClexulator("fcc_default").supercell(N)
+    loc = {name: oracle.RefClexulator(name).supercell(N) for et in types for name in et["local_tables"]}
+    for r in range(R):
+        cur = occ[r].copy()
+
+        def rate(e):
+            cell, pe = divmod(e, len(prim))
+            p = prim[pe]
+            y, k = p["event_type"], p["equivalent_index"]
+            s = oracle.event_state(form, loc[types[y]["local_tables"][k]], cur, cell,
+                                   K.event_linear_site_index(N, cell, p["sites"]), p["occ_init"], p["occ_final"],
+                                   eci["index"], eci["value"], types[y]["kra"], types[y]["freq"], T[r])
+            return s["rate"] if s["is_allowed"] else 0.0
+
+        sel = oracle.LottoSelector(n * len(prim), rate, impacted, seeds[r])
+        t = 0.0
+        for step in range(n_steps):
+            e, dt, tot = sel.select()
+            g = out["log"][r, step]
+            assert (int(g["unitcell"]), int(g["prim_event"])) == divmod(e, len(prim)), f"replica {r} step {step}"
+            assert g["time_increment"] == pytest.approx(dt, rel=1e-12)
+            assert g["total_rate"] == pytest.approx(tot, rel=1e-12)
+            t += dt
+            cell, pe = divmod(e, len(prim))
+            for l, o in zip(K.event_linear_site_index(N, cell, prim[pe]["sites"]), prim[pe]["occ_final"]):
+                cur[l] = o
+        assert out["time"][r] == pytest.approx(t, rel=1e-11)
+        assert (st.download_occ(r) == cur).all()
+    kmc.close()
+    st.close()
+
+
+def test_kmc_run_bookkeeping(kmc_tables, systems):
+    """Size-independent properties of the device KMC: after any number of steps the
+    selector's leaves equal the rates recomputed from scratch for the current occupation
+    (the impact table misses nothing), the roots equal lotto's pairwise tree sums of the
+    leaves bit for bit, species are conserved, time grows, a run continues where the
+    previous call stopped, and a configuration without events stops at once."""
+    rng = np.random.default_rng(8)
+    N = (8, 6, 6)
+    n = int(np.prod(N))
+    R = 6
+    occ = rng.choice(3, size=(R, n), p=[0.7, 0.25, 0.05]).astype(np.int32)
+    occ[R - 1] = rng.choice(2, size=n)          # no vacancy: no allowed event
+    eci = systems["fcc"]["eci_dense"]
+    T = [800.0 + 100.0 * r for r in range(R)]
+    st, kmc, prim = _kmc(kmc_tables, systems, N, occ, eci["index"], eci["value"], T, n_replicas=R)
+    st2, kmc2, _ = _kmc(kmc_tables, systems, N, occ, eci["index"], eci["value"], T, n_replicas=R)
+    seeds = np.arange(R) + 5
+    kmc.run_begin(seeds)
+    kmc2.run_begin(seeds)
+    a = kmc.run(300, log_cap=300)
+    b1 = kmc2.run(120, log_cap=300)
+    b2 = kmc2.run(180, log_cap=300)
+    assert (a["n_steps"][:-1] == 300).all() and a["n_steps"][-1] == 0 and a["time"][-1] == 0.0
+    assert (b2["n_steps"] == a["n_steps"]).all()
+    for name in ("unitcell", "prim_event", "time_increment", "total_rate"):
+        # a call logs only the steps it made: the first call's 120 + the second call's 180
+        assert (a["log"][name][:, :120] == b1["log"][name][:, :120]).all(), name
+        assert (a["log"][name][:, 120:] == b2["log"][name][:, 120:]).all(), name
+    assert (a["time"] == b2["time"]).all() and (a["time"][:-1] > 0).all()
+    cur, tot = kmc.current_rates()
+    fresh, _ = kmc.all_rates()
+    assert (cur == fresh).all()
+    for r in range(R):
+        lvl = cur[r].reshape(-1)
+        while len(lvl) > 1:                       # InvertedBinarySumTree: pairwise, odd one carried up
+            m = len(lvl) // 2
+            nxt = lvl[0:2 * m:2] + lvl[1:2 * m:2]
+            lvl = np.concatenate([nxt, lvl[2 * m:]])
+        assert lvl[0] == tot[r]
+        assert (np.bincount(st.download_occ(r), minlength=3) == np.bincount(occ[r], minlength=3)).all()
+        assert (st.download_occ(r) == st2.download_occ(r)).all()
+    assert (st.download_occ(0) != occ[0]).any()
+    with pytest.raises(_capi.CmxError):
+        _kmc(kmc_tables, systems, N, occ, eci["index"], eci["value"], T, n_replicas=R)[1].run(1)   # no run_begin
+    for x in (kmc, kmc2, st, st2):
+        x.close()

@@ -131,3 +131,67 @@ def test_oracle_reproduces_kmc_golden(oracle, systems):
         row = v["rand2_states"][q]
         assert [float(st["is_allowed"]), float(st["is_normal"]), st["dE_final"], st["Ekra"],
                 st["dE_activated"], st["freq"], st["rate"]] == row.tolist()
+
+
+def test_relative_impact_table_matches_reference_test(systems, load_tables):
+    """tests/unit/clexmonte/events_System_impact_table_test.cpp:43-69: for the FCC A-B-Va
+    system with its shipped formation-energy / kra / freq coefficients there are 24 prim
+    events, every required update neighborhood has 20 sites and every event impacts 708
+    events -- reproduced from the exported tables (kmc.required_update_neighborhood,
+    kmc.make_relative_impact_table)."""
+    from casmcode_clexmonte_b200 import kmc as K
+    sysd = systems["fcc"]
+    ft = load_tables("fcc_default")
+    types = [dict(et, kra=(et["kra"]["index"], et["kra"]["value"]), freq=(et["freq"]["index"], et["freq"]["value"]))
+             for et in sysd["kmc"]["event_types"]]
+    prim = K.make_prim_event_list(types)
+    assert len(prim) == 24
+    nbh = []
+    for p in prim:
+        et = types[p["event_type"]]
+        coef = sorted(set(et["kra"][0]) | set(et["freq"][0]))
+        nbh.append(K.required_update_neighborhood(ft, sysd["eci_dense"]["index"],
+                                                  load_tables(et["local_tables"][p["equivalent_index"]]), coef,
+                                                  p["sites"]))
+    assert [len(x) for x in nbh] == [20] * 24
+    beg, ent = K.make_relative_impact_table(prim, nbh)
+    assert (np.diff(beg) == 708).all() and ent.shape == (24 * 708, 4)
+    # an event always impacts itself and its reverse
+    for j, p in enumerate(prim):
+        rows = {tuple(r) for r in ent[beg[j]:beg[j + 1]]}
+        assert (j, 0, 0, 0) in rows
+
+
+def test_lotto_selector_oracle():
+    """oracle/_ref/libkmc_lotto.so = the reference's lotto::RejectionFreeEventSelector,
+    compiled unmodified: with constant rates the selection frequencies follow the rates,
+    the time steps are exponential with mean 1 / total, and an impacted rate is
+    re-evaluated before the next selection."""
+    from oracle import oracle as O
+    if not O.lotto_available():
+        pytest.skip("oracle/_ref/libkmc_lotto.so not built")
+    rates = [1.0, 2.0, 0.0, 5.0, 2.0]
+    calls = []
+
+    def rate(e):
+        calls.append(e)
+        return rates[e]
+
+    sel = O.LottoSelector(5, rate, [[1], [], [], [0, 4], []], seed=7)
+    assert calls == [0, 1, 2, 3, 4]
+    n = 4000
+    hits, dts = np.zeros(5), []
+    for _ in range(n):
+        before = len(calls)
+        e, dt, tot = sel.select()
+        assert tot == 10.0 and dt > 0
+        hits[e] += 1
+        dts.append(dt)
+        last = e
+    assert hits[2] == 0
+    np.testing.assert_allclose(hits / n, np.array(rates) / 10.0, atol=0.03)
+    assert np.mean(dts) == pytest.approx(0.1, rel=0.06)
+    # the impact list of the last selected event is evaluated at the start of the next select
+    before = len(calls)
+    sel.select()
+    assert calls[before:] == [[1], [], [], [0, 4], []][last]

@@ -237,6 +237,16 @@ def c5():
     emit(workload=f"c5b: impact-list batch, 708 events x {R} trajectories (host lists in, EventState records out: e2e)",
          metric="event-state evaluations/s", value=B / dt, ms=dt * 1e3, allowed=int(s["is_allowed"].sum()),
          kernel="k_kmc_event_states")
+    # whole KMC steps on the device: one block per trajectory (select, apply, 708 impacted rates, tree)
+    kmc.run_begin(np.arange(R) + 1)
+    kmc.run(20)
+    S = 200
+    ms, out = timed(st, lambda: kmc.run(S))
+    hops = float(np.sum(out["n_steps"])) - 20.0 * R
+    emit(workload=f"c5c: rejection-free KMC steps on the device (lotto-order sum tree, mt19937_64), {R} trajectories x {n} cells, 708 impacted events per hop",
+         metric="KMC events (hops)/s", value=hops / (ms * 1e-3), ms=ms, steps_per_trajectory=S,
+         impacted_event_rate_evaluations_per_s=708.0 * hops / (ms * 1e-3), kernel="k_kmc_run",
+         mean_time_per_trajectory_s=float(np.mean(out["time"])))
     kmc.close()
     st.close()
     for x in tb.values():
