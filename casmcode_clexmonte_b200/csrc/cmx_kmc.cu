@@ -71,71 +71,92 @@ __device__ __forceinline__ int kmc_point_index(const DevTables &T, int b) {
   return -1;
 }
 
-__device__ void kmc_event_state(const KmcArgs &a, int r, int64_t cell, int pe,
-                                cmx_event_state &out) {
+// ---- the event state in three pieces, so that a thread block can spread the function
+// evaluations of an allowed event over its threads (k_kmc_run) while a single thread
+// (k_kmc_event_states, k_kmc_all_rates) runs the same pieces one after the other: the
+// arithmetic, and therefore every bit of the result, is the same either way.
+struct KmcEventSites {
+  int ci, cj, ck;
+  int si[CMX_EVENT_MAX_SITES], sj[CMX_EVENT_MAX_SITES], sk[CMX_EVENT_MAX_SITES];
+};
+
+// event_is_allowed (events/event_methods.cc:340-351): every site holds the event's
+// initial occupant
+__device__ __forceinline__ bool kmc_event_sites(const KmcArgs &a, const int8_t *occ, int64_t cell,
+                                                const cmx_prim_event &E, KmcEventSites &S) {
+  const Geom &g = a.g;
+  S.ci = (int)(cell % g.N0);
+  const int64_t rest = cell / g.N0;
+  S.cj = (int)(rest % g.N1);
+  S.ck = (int)(rest / g.N1);
+  bool allowed = true;
+  for (int q = 0; q < E.n_sites; ++q) {
+    S.si[q] = cmx_wrap(S.ci + E.site[q][1], g.N0);
+    S.sj[q] = cmx_wrap(S.cj + E.site[q][2], g.N1);
+    S.sk[q] = cmx_wrap(S.ck + E.site[q][3], g.N2);
+    const int o = cmx_dec(occ[cmx_site_offset(g, E.site[q][0], S.si[q], S.sj[q], S.sk[q])]);
+    if (o != E.occ_init[q]) allowed = false;
+  }
+  return allowed;
+}
+
+// tasks of an event: [0, n_eci * n_sites): delta corr of ECI function c = task / n_sites at
+// site q = task % n_sites, evaluated with sites 0..q-1 already changed
+// (Correlations::occ_delta [EXT]); then the kra functions, then the freq
+// functions of the event's equivalent local clexulator about the unit cell
+__device__ __forceinline__ int kmc_n_tasks(const KmcArgs &a, const cmx_prim_event &E) {
+  const DevEventType &Y = a.types[E.event_type];
+  return a.n_eci * E.n_sites + (Y.kra_end - Y.kra_beg) + (Y.freq_end - Y.freq_beg);
+}
+__device__ double kmc_task_value(const KmcArgs &a, const int8_t *occ, const cmx_prim_event &E,
+                                 const KmcEventSites &S, int task) {
   const Geom &g = a.g;
   const DevTables &T = a.T;
-  const int8_t *occ = a.occ + (size_t)r * g.rep_stride;
-  const cmx_prim_event &E = a.prim[pe];
-  int ci = (int)(cell % g.N0);
-  int64_t rest = cell / g.N0;
-  int cj = (int)(rest % g.N1), ck = (int)(rest / g.N1);
-  out.is_allowed = 1;
-  out.is_normal = 0;
-  out.dE_final = out.Ekra = out.dE_activated = out.freq = out.rate = 0.0;
-  int si[CMX_EVENT_MAX_SITES], sj[CMX_EVENT_MAX_SITES], sk[CMX_EVENT_MAX_SITES];
-  // event_is_allowed: every site holds the event's initial occupant
-  for (int q = 0; q < E.n_sites; ++q) {
-    si[q] = cmx_wrap(ci + E.site[q][1], g.N0);
-    sj[q] = cmx_wrap(cj + E.site[q][2], g.N1);
-    sk[q] = cmx_wrap(ck + E.site[q][3], g.N2);
-    int o = cmx_dec(occ[cmx_site_offset(g, E.site[q][0], si[q], sj[q], sk[q])]);
-    if (o != E.occ_init[q]) out.is_allowed = 0;
-  }
-  if (!out.is_allowed) return;
-  // dE_final = coefficients . occ_delta(linear_site_index, occ_final): sites are
-  // changed one after the other (Correlations::occ_delta [EXT])
-  double dE = 0.0;
-  for (int c = 0; c < a.n_eci; ++c) {
+  const int n_delta = a.n_eci * E.n_sites;
+  if (task < n_delta) {
+    const int c = task / E.n_sites, q = task - c * E.n_sites;
     Override ov;
     ov.n = 0;
-    double acc = 0.0;
-    for (int q = 0; q < E.n_sites; ++q) {
-      int b = E.site[q][0];
-      int p = kmc_point_index(T, b);
-      double d = 0.0;
-      if (p >= 0) {
-        int fi = p * T.corr_size + (int)a.eci_idx[c];
-        d = cmx_eval_function(T, g, occ, T.delta_gbeg[fi], T.delta_gbeg[fi + 1], si[q], sj[q],
-                              sk[q], ov, b, E.occ_init[q], E.occ_final[q]);
-      }
-      acc = (q == 0) ? d : __dadd_rn(acc, d);
-      ov.off[ov.n] = cmx_site_offset(g, b, si[q], sj[q], sk[q]);
-      ov.occ[ov.n] = E.occ_final[q];
+    for (int q2 = 0; q2 < q; ++q2) {
+      ov.off[ov.n] = cmx_site_offset(g, E.site[q2][0], S.si[q2], S.sj[q2], S.sk[q2]);
+      ov.occ[ov.n] = E.occ_final[q2];
       ov.n++;
     }
-    dE = __dadd_rn(dE, __dmul_rn(a.eci_val[c], acc));
+    const int b = E.site[q][0];
+    const int p = kmc_point_index(T, b);
+    if (p < 0) return 0.0;
+    const int fi = p * T.corr_size + (int)a.eci_idx[c];
+    return cmx_eval_function(T, g, occ, T.delta_gbeg[fi], T.delta_gbeg[fi + 1], S.si[q], S.sj[q], S.sk[q], ov, b,
+                             E.occ_init[q], E.occ_final[q]);
   }
-  out.dE_final = dE;
-  // local correlations of this equivalent about the unit cell, only the
-  // functions that carry a kra or freq coefficient
   const DevEventType &Y = a.types[E.event_type];
   const DevTables &L = a.local[Y.table0 + E.equivalent_index];
   Override none;
   none.n = 0;
+  const int c = (int)a.coef_idx[Y.kra_beg + (task - n_delta)];  // kra and freq entries are contiguous
+  return cmx_eval_function(L, g, occ, L.global_gbeg[c], L.global_gbeg[c + 1], S.ci, S.cj, S.ck, none, 0, 0, 0);
+}
+
+// EventStateCalculator::_default_event_state_calculation (BaseMonteEventData.cc:122-156)
+// from the task values v[kmc_n_tasks]
+template <typename V>
+__device__ __forceinline__ void kmc_event_combine(const KmcArgs &a, int r, const cmx_prim_event &E, const V &v,
+                                                  cmx_event_state &out) {
+  double dE = 0.0;
+  for (int c = 0; c < a.n_eci; ++c) {
+    double acc = 0.0;
+    for (int q = 0; q < E.n_sites; ++q) {
+      const double d = v[c * E.n_sites + q];
+      acc = (q == 0) ? d : __dadd_rn(acc, d);
+    }
+    dE = __dadd_rn(dE, __dmul_rn(a.eci_val[c], acc));
+  }
+  out.dE_final = dE;
+  const DevEventType &Y = a.types[E.event_type];
+  int t = a.n_eci * E.n_sites;
   double ekra = 0.0, freq = 0.0;
-  for (int q = Y.kra_beg; q < Y.kra_end; ++q) {
-    int c = (int)a.coef_idx[q];
-    double v = cmx_eval_function(L, g, occ, L.global_gbeg[c], L.global_gbeg[c + 1], ci, cj, ck,
-                                 none, 0, 0, 0);
-    ekra = __dadd_rn(ekra, __dmul_rn(a.coef_val[q], v));
-  }
-  for (int q = Y.freq_beg; q < Y.freq_end; ++q) {
-    int c = (int)a.coef_idx[q];
-    double v = cmx_eval_function(L, g, occ, L.global_gbeg[c], L.global_gbeg[c + 1], ci, cj, ck,
-                                 none, 0, 0, 0);
-    freq = __dadd_rn(freq, __dmul_rn(a.coef_val[q], v));
-  }
+  for (int q = Y.kra_beg; q < Y.kra_end; ++q) ekra = __dadd_rn(ekra, __dmul_rn(a.coef_val[q], v[t++]));
+  for (int q = Y.freq_beg; q < Y.freq_end; ++q) freq = __dadd_rn(freq, __dmul_rn(a.coef_val[q], v[t++]));
   out.Ekra = ekra;
   out.freq = freq;
   // BaseMonteEventData.cc:148-155
@@ -145,6 +166,30 @@ __device__ void kmc_event_state(const KmcArgs &a, int r, int64_t cell, int pe,
   if (dEa < 0.0) dEa = 0.0;
   out.dE_activated = dEa;
   out.rate = freq * exp(-a.beta[r] * dEa);
+}
+
+struct KmcLazyValues {  // single-thread evaluation: a task is computed when it is read
+  const KmcArgs &a;
+  const int8_t *occ;
+  const cmx_prim_event &E;
+  const KmcEventSites &S;
+  __device__ __forceinline__ double operator[](int task) const { return kmc_task_value(a, occ, E, S, task); }
+};
+
+__device__ void kmc_event_state(const KmcArgs &a, int r, int64_t cell, int pe,
+                                cmx_event_state &out) {
+  const int8_t *occ = a.occ + (size_t)r * a.g.rep_stride;
+  const cmx_prim_event &E = a.prim[pe];
+  out.is_allowed = 1;
+  out.is_normal = 0;
+  out.dE_final = out.Ekra = out.dE_activated = out.freq = out.rate = 0.0;
+  KmcEventSites S;
+  if (!kmc_event_sites(a, occ, cell, E, S)) {
+    out.is_allowed = 0;
+    return;
+  }
+  const KmcLazyValues v{a, occ, E, S};
+  kmc_event_combine(a, r, E, v, out);
 }
 
 __global__ void k_kmc_event_states(KmcArgs a, int64_t n, const int32_t *__restrict__ replica,
@@ -476,35 +521,78 @@ struct KmcRunArgs {
   cmx_kmc_step *log;
   long long log_cap;
   long long n_steps;
+  int max_imp, t_max;
+};
+
+#define CMX_KMC_CHUNK 16  // allowed events evaluated per round of the block
+
+// shared scratch of k_kmc_run: ids[max_imp] | allowed[max_imp] | values[CHUNK][t_max]
+struct KmcShared {
+  long long *ids;
+  int *allowed;
+  double *val;
+  int t_max;
 };
 
 // re-evaluate the events impacted by event `ev` and re-sum their tree paths
 __device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, double *leaves, double *up,
-                                 long long *sh_ids) {
+                                 const KmcShared &sh) {
+  __shared__ int sh_n_allowed;
   const Geom &g = A.a.g;
+  const int8_t *occ = A.a.occ + (size_t)r * g.rep_stride;
   const int pe = (int)(ev % A.n_prim);
   const long long cell = ev / A.n_prim;
   const int ci = (int)(cell % g.N0);
   const long long rest = cell / g.N0;
   const int cj = (int)(rest % g.N1), ck = (int)(rest / g.N1);
   const int ib = A.imp_beg[pe], n_imp = A.imp_beg[pe + 1] - ib;
+  if (threadIdx.x == 0) sh_n_allowed = 0;
+  __syncthreads();
+  // 1. events that are not allowed get rate 0 at once; the allowed ones are listed
   for (int q = threadIdx.x; q < n_imp; q += blockDim.x) {
     const int4 e = A.imp[ib + q];
     const int i2 = cmx_wrap(ci + e.y, g.N0), j2 = cmx_wrap(cj + e.z, g.N1), k2 = cmx_wrap(ck + e.w, g.N2);
     const long long c2 = ((long long)k2 * g.N1 + j2) * g.N0 + i2;
-    cmx_event_state st;
-    kmc_event_state(A.a, r, c2, e.x, st);
     const long long id = c2 * A.n_prim + e.x;
-    leaves[id] = st.rate;
-    sh_ids[q] = id;
+    sh.ids[q] = id;
+    KmcEventSites S;
+    if (kmc_event_sites(A.a, occ, c2, A.a.prim[e.x], S)) sh.allowed[atomicAdd(&sh_n_allowed, 1)] = q;
+    else leaves[id] = 0.0;
   }
   __syncthreads();
+  // 2. allowed events, CMX_KMC_CHUNK at a time: their function evaluations (tasks) are
+  // spread over the block, then one thread per event combines them in reference order.
+  // (the order of `allowed` depends on the atomics; every event is evaluated
+  // independently, so the results do not)
+  const int n_allowed = sh_n_allowed;
+  for (int base = 0; base < n_allowed; base += CMX_KMC_CHUNK) {
+    const int n_ev = min(CMX_KMC_CHUNK, n_allowed - base);
+    for (int w = threadIdx.x; w < n_ev * sh.t_max; w += blockDim.x) {
+      const int x = w / sh.t_max, task = w - x * sh.t_max;
+      const long long id = sh.ids[sh.allowed[base + x]];
+      const cmx_prim_event &E = A.a.prim[(int)(id % A.n_prim)];
+      if (task >= kmc_n_tasks(A.a, E)) continue;
+      KmcEventSites S;
+      kmc_event_sites(A.a, occ, id / A.n_prim, E, S);
+      sh.val[w] = kmc_task_value(A.a, occ, E, S, task);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < n_ev; x += blockDim.x) {
+      const long long id = sh.ids[sh.allowed[base + x]];
+      const cmx_prim_event &E = A.a.prim[(int)(id % A.n_prim)];
+      cmx_event_state st;
+      kmc_event_combine(A.a, r, E, sh.val + (size_t)x * sh.t_max, st);
+      leaves[id] = st.rate;
+    }
+    __syncthreads();
+  }
+  // 3. re-sum the touched paths, level by level
   for (int l = 1; l <= A.t.n_levels; ++l) {
     const double *child = kmc_level(leaves, up, A.t, l - 1);
     double *node = kmc_level(leaves, up, A.t, l);
     const long long nc = A.t.size[l - 1];
     for (int q = threadIdx.x; q < n_imp; q += blockDim.x) {
-      const long long i = sh_ids[q] >> l;  // several ids may share a parent: same value written
+      const long long i = sh.ids[q] >> l;  // several ids may share a parent: same value written
       node[i] = (2 * i + 1 < nc) ? __dadd_rn(child[2 * i], child[2 * i + 1]) : child[2 * i];
     }
     __syncthreads();
@@ -512,8 +600,13 @@ __device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, doubl
 }
 
 __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
-  extern __shared__ long long sh_ids[];
+  extern __shared__ long long sh_dyn[];
   __shared__ long long sh_ev;
+  KmcShared sh_ids;
+  sh_ids.ids = sh_dyn;
+  sh_ids.val = reinterpret_cast<double *>(sh_dyn + A.max_imp);
+  sh_ids.allowed = reinterpret_cast<int *>(sh_ids.val + CMX_KMC_CHUNK * A.t_max);
+  sh_ids.t_max = A.t_max;
   const int r = blockIdx.x;
   const Geom &g = A.a.g;
   double *leaves = A.rates + (size_t)r * A.per, *up = A.tree + (size_t)r * A.t.upper;
@@ -718,7 +811,14 @@ extern "C" int cmx_kmc_run(cmx_kmc *k, int64_t n_steps, cmx_kmc_step *log, int64
     CMX_CUDA(cudaMemcpyAsync(d_log, log, sizeof(cmx_kmc_step) * (size_t)R * log_cap, cudaMemcpyHostToDevice, s->stream));
     A.log = d_log;
   }
-  const size_t smem = sizeof(long long) * std::max(1, k->max_imp);
+  int t_max = 1;
+  for (const cmx_prim_event &E : k->prim) {
+    const DevEventType &Y = k->types[E.event_type];
+    t_max = std::max(t_max, s->n_eci * E.n_sites + (Y.kra_end - Y.kra_beg) + (Y.freq_end - Y.freq_beg));
+  }
+  A.max_imp = std::max(1, k->max_imp);
+  A.t_max = t_max;
+  const size_t smem = (sizeof(long long) + sizeof(int)) * A.max_imp + sizeof(double) * CMX_KMC_CHUNK * t_max;
   if (smem > 48 * 1024) {
     cudaFree(d_log);
     return invalid("cmx_kmc_run: impact lists longer than 6144 events are not supported");
