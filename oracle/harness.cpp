@@ -661,3 +661,106 @@ double orc_potential_per_supercell(void *sh, int const *occ, int n_sublat,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// KMC event rates for the reference's own selector (oracle/kmc_lotto.cpp): the C++
+// form of oracle.py::event_state, so that the CPU baseline of the KMC step has no
+// Python in its loop.  EventStateCalculator::calculate_event_state +
+// _default_event_state_calculation (BaseMonteEventData.cc:87-156), event_is_allowed
+// (events/event_methods.cc:340-351); event id = unitcell * n_prim + prim_event
+// (events/CompleteEventList.cc:76-91).
+// ---------------------------------------------------------------------------
+namespace {
+struct KmcPrim {
+  int n_sites;
+  long site[4][4];  // (b, i, j, k)
+  int occ_init[4], occ_final[4];
+  Supercell *local;
+  std::vector<unsigned> kra_idx, freq_idx;
+  std::vector<double> kra_val, freq_val;
+};
+struct KmcCtx {
+  Supercell *form;
+  int *occ;
+  std::vector<KmcPrim> prim;
+  std::vector<unsigned> eci_idx;
+  std::vector<double> eci_val;
+  double beta;
+  std::vector<double> corr;
+};
+inline void kmc_sites(KmcCtx const &c, KmcPrim const &p, long cell, long *l) {
+  Supercell const *s = c.form;
+  long i = cell % s->N[0], j = (cell / s->N[0]) % s->N[1], k = cell / (s->N[0] * s->N[1]);
+  for (int q = 0; q < p.n_sites; ++q)
+    l[q] = p.site[q][0] * s->n_cells + wrap(i + p.site[q][1], s->N[0]) +
+           s->N[0] * (wrap(j + p.site[q][2], s->N[1]) + s->N[1] * wrap(k + p.site[q][3], s->N[2]));
+}
+}  // namespace
+
+extern "C" {
+
+// prim_sites[n_prim][4][4], prim_occ[n_prim][2][4] (init, final), local_sc[n_prim] supercell
+// handles of each prim event's equivalent local clexulator, coefficient lists flattened
+// with offsets kra_beg/freq_beg [n_prim + 1]
+void *orc_kmc_ctx(void *form_sc, int *occ, long n_prim, int const *n_sites, long const *prim_sites,
+                  int const *prim_occ, void *const *local_sc, long const *kra_beg, unsigned const *kra_idx,
+                  double const *kra_val, long const *freq_beg, unsigned const *freq_idx, double const *freq_val,
+                  unsigned const *eci_idx, double const *eci_val, long n_eci, double temperature) {
+  KmcCtx *c = new KmcCtx;
+  c->form = static_cast<Supercell *>(form_sc);
+  c->occ = occ;
+  c->eci_idx.assign(eci_idx, eci_idx + n_eci);
+  c->eci_val.assign(eci_val, eci_val + n_eci);
+  c->beta = 1.0 / (KB * temperature);
+  for (long p = 0; p < n_prim; ++p) {
+    KmcPrim e;
+    e.n_sites = n_sites[p];
+    for (int q = 0; q < 4; ++q) {
+      for (int x = 0; x < 4; ++x) e.site[q][x] = prim_sites[(p * 4 + q) * 4 + x];
+      e.occ_init[q] = prim_occ[(p * 2 + 0) * 4 + q];
+      e.occ_final[q] = prim_occ[(p * 2 + 1) * 4 + q];
+    }
+    e.local = static_cast<Supercell *>(local_sc[p]);
+    e.kra_idx.assign(kra_idx + kra_beg[p], kra_idx + kra_beg[p + 1]);
+    e.kra_val.assign(kra_val + kra_beg[p], kra_val + kra_beg[p + 1]);
+    e.freq_idx.assign(freq_idx + freq_beg[p], freq_idx + freq_beg[p + 1]);
+    e.freq_val.assign(freq_val + freq_beg[p], freq_val + freq_beg[p + 1]);
+    c->prim.push_back(e);
+  }
+  return c;
+}
+
+void orc_kmc_ctx_free(void *p) { delete static_cast<KmcCtx *>(p); }
+
+double orc_kmc_rate(void *ctx, long event_id) {
+  KmcCtx *c = static_cast<KmcCtx *>(ctx);
+  long n_prim = (long)c->prim.size();
+  long cell = event_id / n_prim;
+  KmcPrim const &p = c->prim[event_id % n_prim];
+  long l[4];
+  kmc_sites(*c, p, cell, l);
+  for (int q = 0; q < p.n_sites; ++q)
+    if (c->occ[l[q]] != p.occ_init[q]) return 0.0;
+  double dE = orc_occ_delta_value(c->form, c->occ, p.n_sites, l, p.occ_final, c->eci_idx.data(),
+                                  c->eci_val.data(), (long)c->eci_idx.size(), nullptr);
+  c->corr.resize(p.local->clex->corr_size());
+  orc_cell_corr(p.local, c->occ, cell, c->corr.data());
+  double ekra = 0.0, freq = 0.0;
+  for (size_t i = 0; i < p.kra_idx.size(); ++i) ekra = ekra + p.kra_val[i] * c->corr[p.kra_idx[i]];
+  for (size_t i = 0; i < p.freq_idx.size(); ++i) freq = freq + p.freq_val[i] * c->corr[p.freq_idx[i]];
+  double dEa = dE * 0.5 + ekra;
+  if (dEa < dE) dEa = dE;
+  if (dEa < 0.0) dEa = 0.0;
+  return freq * std::exp(-c->beta * dEa);
+}
+
+// OccLocation::apply for the complete event list: the sites take the final occupants
+void orc_kmc_apply(void *ctx, long event_id) {
+  KmcCtx *c = static_cast<KmcCtx *>(ctx);
+  long n_prim = (long)c->prim.size();
+  KmcPrim const &p = c->prim[event_id % n_prim];
+  long l[4];
+  kmc_sites(*c, p, event_id / n_prim, l);
+  for (int q = 0; q < p.n_sites; ++q) c->occ[l[q]] = p.occ_final[q];
+}
+}

@@ -69,6 +69,22 @@ long lotto_select(void *p, double *dt, double *total) {
   return sel.first;
 }
 
+// n_steps of the loop of kinetic_monte_carlo_v2 (methods/kinetic_monte_carlo.hh:396-507):
+// select, advance the time, apply (callback).  Returns the simulated time; event_log[n_steps]
+// (may be null) receives the selected event ids.
+typedef void (*apply_cb)(void *ctx, long event_id);
+double lotto_run(void *p, long n_steps, apply_cb apply, void *ctx, long *event_log) {
+  Handle *h = static_cast<Handle *>(p);
+  double time = 0.0;
+  for (long s = 0; s < n_steps; ++s) {
+    std::pair<long, double> sel = h->selector->select_event();
+    time += sel.second;
+    apply(ctx, sel.first);
+    if (event_log) event_log[s] = sel.first;
+  }
+  return time;
+}
+
 double lotto_get_rate(void *p, long event_id) {
   return static_cast<Handle *>(p)->selector->get_rate(event_id);
 }

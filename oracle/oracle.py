@@ -364,3 +364,77 @@ class LottoSelector:
         if getattr(self, "_h", None):
             _lotto_lib().lotto_destroy(self._h)
             self._h = None
+
+
+class KmcReference:
+    """The KMC loop of the reference on the CPU with nothing of this repository's product in
+    it: lotto::RejectionFreeEventSelector (compiled unmodified) + event rates from the
+    reference's generated Clexulator kernels (harness.cpp: orc_kmc_rate) + the apply step.
+    prim: list of prim events (kmc.make_prim_event_list); types: event types with
+    local_tables / kra / freq as (index, value); impacted[e]: event ids to update after e."""
+
+    def __init__(self, N, occ, prim, types, eci_idx, eci_val, temperature, impacted, seed):
+        L = lib()
+        L.orc_kmc_ctx.restype = C.c_void_p
+        L.orc_kmc_ctx.argtypes = [C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 12 + [C.c_long, C.c_double]
+        L.orc_kmc_ctx_free.argtypes = [C.c_void_p]
+        K = _lotto_lib()
+        K.lotto_run.restype = C.c_double
+        K.lotto_run.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.N = tuple(int(x) for x in N)
+        self.occ = np.ascontiguousarray(occ, dtype=np.int32).copy()
+        self.n_prim = len(prim)
+        self._form = RefClexulator("fcc_default").supercell(self.N)
+        self._local = {}
+        n_sites = np.array([len(p["sites"]) for p in prim], dtype=np.int32)
+        sites = np.zeros((self.n_prim, 4, 4), dtype=np.int64)
+        pocc = np.zeros((self.n_prim, 2, 4), dtype=np.int32)
+        handles = (C.c_void_p * self.n_prim)()
+        kb, ki, kv, fb, fi, fv = [0], [], [], [0], [], []
+        for q, p in enumerate(prim):
+            for s_, site in enumerate(p["sites"]):
+                sites[q, s_] = site
+            pocc[q, 0, :len(p["occ_init"])] = p["occ_init"]
+            pocc[q, 1, :len(p["occ_final"])] = p["occ_final"]
+            et = types[p["event_type"]]
+            name = et["local_tables"][p["equivalent_index"]]
+            if name not in self._local:
+                self._local[name] = RefClexulator(name).supercell(self.N)
+            handles[q] = self._local[name]._h
+            ki += list(et["kra"][0]); kv += list(et["kra"][1]); kb.append(len(ki))
+            fi += list(et["freq"][0]); fv += list(et["freq"][1]); fb.append(len(fi))
+        arrs = [n_sites, sites, pocc, np.array(kb, dtype=np.int64), np.array(ki, dtype=np.uint32),
+                np.array(kv, dtype=np.float64), np.array(fb, dtype=np.int64), np.array(fi, dtype=np.uint32),
+                np.array(fv, dtype=np.float64), np.ascontiguousarray(eci_idx, dtype=np.uint32),
+                np.ascontiguousarray(eci_val, dtype=np.float64)]
+        self._keep = arrs + [handles]
+        self._ctx = L.orc_kmc_ctx(self._form._h, _p(self.occ), self.n_prim, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]),
+                                  handles, _p(arrs[3]), _p(arrs[4]), _p(arrs[5]), _p(arrs[6]), _p(arrs[7]),
+                                  _p(arrs[8]), _p(arrs[9]), _p(arrs[10]), len(arrs[9]), float(temperature))
+        n_events = int(np.prod(self.N)) * self.n_prim
+        beg = np.zeros(n_events + 1, dtype=np.int64)
+        beg[1:] = np.cumsum([len(x) for x in impacted])
+        imp = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.int64) for x in impacted]))
+        rate = C.cast(L.orc_kmc_rate, C.c_void_p)
+        K.lotto_create.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong]
+        self._sel = K.lotto_create(n_events, rate, self._ctx, _p(beg), _p(imp), int(seed))
+        K.lotto_create.argtypes = [C.c_long, _RATE_CB, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong]
+
+    def run(self, n_steps: int):
+        """(simulated time, selected event ids, wall seconds); self.occ is advanced."""
+        import time as _t
+        ev = np.zeros(n_steps, dtype=np.int64)
+        t0 = _t.perf_counter()
+        t = _lotto_lib().lotto_run(self._sel, int(n_steps), C.cast(lib().orc_kmc_apply, C.c_void_p), self._ctx, _p(ev))
+        return t, ev, _t.perf_counter() - t0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_sel", None):
+                _lotto_lib().lotto_destroy(self._sel)
+                self._sel = None
+            if getattr(self, "_ctx", None):
+                lib().orc_kmc_ctx_free(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass

@@ -196,18 +196,20 @@ def test_kmc_run_matches_reference_selector(kmc_tables, systems, oracle):
     """whole KMC steps on the device reproduce the event sequence of the
     reference's own selector (lotto::RejectionFreeEventSelector, compiled unmodified into
     oracle/_ref/libkmc_lotto.so, seeded std::mt19937_64) fed with event rates from the
-    reference's generated kernels (oracle.event_state) on the same initial occupation:
-    identical (unit cell, prim event) at every step; time steps and total rates to 1e-12
-    (device exp/log vs glibc)."""
+    reference's generated kernels (harness.cpp orc_kmc_rate) on the same initial
+    occupation: identical (unit cell, prim event) at every one of 500 steps of three
+    trajectories, identical final occupation; simulated time to 1e-11 (device exp/log vs
+    glibc in the last bit of individual rates)."""
     if oracle is None or not oracle.lotto_available():
         pytest.skip("oracle/_ref not built")
     rng = np.random.default_rng(3)
     N = (6, 6, 6)
     n = 216
-    R, n_steps = 2, 40
+    R, n_steps = 3, 500
     occ = rng.choice(3, size=(R, n), p=[0.55, 0.35, 0.10]).astype(np.int32)
-    T = [1200.0, 900.0]
-    seeds = [11, 2026]
+    occ[2] = rng.choice(3, size=n, p=[0.88, 0.1, 0.02])
+    T = [1200.0, 900.0, 600.0]
+    seeds = [11, 2026, 5]
     eci = systems["fcc"]["eci_dense"]
     st, kmc, prim = _kmc(kmc_tables, systems, N, occ, eci["index"], eci["value"], T, n_replicas=R)
     kmc.run_begin(seeds)
@@ -216,34 +218,39 @@ def test_kmc_run_matches_reference_selector(kmc_tables, systems, oracle):
     beg, ent = kmc._impact
     impacted = _impacted_ids(N, len(prim), beg, ent)
     types = _types(systems)
+    for r in range(R):
+        ref = oracle.KmcReference(N, occ[r], prim, types, eci["index"], eci["value"], T[r], impacted, seeds[r])
+        t, ev, _ = ref.run(n_steps)
+        gpu_ev = out["log"]["unitcell"][r] * len(prim) + out["log"]["prim_event"][r]
+        mism = np.nonzero(gpu_ev != ev)[0]
+        assert len(mism) == 0, f"replica {r}: first divergence at step {mism[0]}"
+        assert out["time"][r] == pytest.approx(t, rel=1e-11)
+        assert out["log"]["time_increment"][r].sum() == pytest.approx(t, rel=1e-11)
+        assert (st.download_occ(r) == ref.occ).all()
+    # the Python-callback form of the same oracle (oracle.event_state) agrees on a short run
+    cur = occ[0].copy()
     form = oracle.RefClexulator("fcc_default").supercell(N)
     loc = {name: oracle.RefClexulator(name).supercell(N) for et in types for name in et["local_tables"]}
-    for r in range(R):
-        cur = occ[r].copy()
 
-        def rate(e):
-            cell, pe = divmod(e, len(prim))
-            p = prim[pe]
-            y, k = p["event_type"], p["equivalent_index"]
-            s = oracle.event_state(form, loc[types[y]["local_tables"][k]], cur, cell,
-                                   K.event_linear_site_index(N, cell, p["sites"]), p["occ_init"], p["occ_final"],
-                                   eci["index"], eci["value"], types[y]["kra"], types[y]["freq"], T[r])
-            return s["rate"] if s["is_allowed"] else 0.0
+    def rate(e):
+        cell, pe = divmod(e, len(prim))
+        p = prim[pe]
+        y, k = p["event_type"], p["equivalent_index"]
+        s = oracle.event_state(form, loc[types[y]["local_tables"][k]], cur, cell,
+                               K.event_linear_site_index(N, cell, p["sites"]), p["occ_init"], p["occ_final"],
+                               eci["index"], eci["value"], types[y]["kra"], types[y]["freq"], T[0])
+        return s["rate"] if s["is_allowed"] else 0.0
 
-        sel = oracle.LottoSelector(n * len(prim), rate, impacted, seeds[r])
-        t = 0.0
-        for step in range(n_steps):
-            e, dt, tot = sel.select()
-            g = out["log"][r, step]
-            assert (int(g["unitcell"]), int(g["prim_event"])) == divmod(e, len(prim)), f"replica {r} step {step}"
-            assert g["time_increment"] == pytest.approx(dt, rel=1e-12)
-            assert g["total_rate"] == pytest.approx(tot, rel=1e-12)
-            t += dt
-            cell, pe = divmod(e, len(prim))
-            for l, o in zip(K.event_linear_site_index(N, cell, prim[pe]["sites"]), prim[pe]["occ_final"]):
-                cur[l] = o
-        assert out["time"][r] == pytest.approx(t, rel=1e-11)
-        assert (st.download_occ(r) == cur).all()
+    sel = oracle.LottoSelector(n * len(prim), rate, impacted, seeds[0])
+    for step in range(12):
+        e, dt, tot = sel.select()
+        g = out["log"][0, step]
+        assert (int(g["unitcell"]), int(g["prim_event"])) == divmod(e, len(prim))
+        assert g["time_increment"] == pytest.approx(dt, rel=1e-12)
+        assert g["total_rate"] == pytest.approx(tot, rel=1e-12)
+        cell, pe = divmod(e, len(prim))
+        for l, o in zip(K.event_linear_site_index(N, cell, prim[pe]["sites"]), prim[pe]["occ_final"]):
+            cur[l] = o
     kmc.close()
     st.close()
 

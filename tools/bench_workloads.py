@@ -251,6 +251,30 @@ def c5():
     st.close()
     for x in tb.values():
         x.close()
+    # CPU baseline: the reference's own selector + generated kernels, no Python in the loop, one core
+    try:
+        from oracle import oracle as O
+        if not (O.available("fcc_default") and O.lotto_available()):
+            raise RuntimeError("oracle/_ref not built")
+        Nc = (10, 10, 10)
+        beg, ent = kmc._impact
+        N0, N1, N2 = Nc
+        impacted = []
+        for c in range(N0 * N1 * N2):
+            i, j, k_ = c % N0, (c // N0) % N1, c // (N0 * N1)
+            for pe in range(len(prim)):
+                rows = ent[beg[pe]:beg[pe + 1]]
+                cells = ((i + rows[:, 1]) % N0) + N0 * (((j + rows[:, 2]) % N1) + N1 * ((k_ + rows[:, 3]) % N2))
+                impacted.append(np.unique(cells.astype(np.int64) * len(prim) + rows[:, 0]))
+        occ_c = rng.choice(3, size=1000, p=[0.899, 0.1, 0.001]).astype(np.int32)
+        occ_c[:1] = 2
+        ref = O.KmcReference(Nc, occ_c, prim, types, eci["index"], eci["value"], 1200.0, impacted, seed=3)
+        ref.run(2000)
+        _, _, sec = ref.run(20000)
+        emit(workload="c5 cpu baseline: lotto::RejectionFreeEventSelector (reference, unmodified) + reference generated kernels, 10^3 cells, complete event list",
+             metric="KMC events (hops)/s", value=20000 / sec, cores=1, kind="reference", sample="20000 hops of one trajectory on one core")
+    except Exception as e:  # noqa: BLE001
+        emit(workload="c5 cpu baseline", unavailable=str(e))
 
 
 def main():
