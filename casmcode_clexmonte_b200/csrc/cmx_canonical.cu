@@ -169,9 +169,13 @@ __global__ void __launch_bounds__(128) k_canonical_pairs(CanonArgs a) {
 // (ZrO 48^3: 13 800 launches per sweep).  Occupations are read through L2 only: other
 // SMs wrote them before the barrier.  Same proposals, random bits and decision rule as
 // k_canonical_pairs.
+// SH: the term tables of the two point positions are staged in shared memory first
+// (dynamic shared memory: [table a][table b, if another position][8 warps][stage_max + 1]).
+template <bool SH>
 __global__ void __launch_bounds__(256) k_canonical_pairs_warp(CanonArgs a, GenTerms G, int stage_max,
-                                                              int colour_begin, int colour_end, int coop) {
-  extern __shared__ double sh_stage[];  // [8 warps][stage_max]
+                                                              int colour_begin, int colour_end, int coop,
+                                                              int table_bytes) {
+  extern __shared__ __align__(16) unsigned char sh_dyn_c[];
   __shared__ long long sh_att[8], sh_acc[8];
   __shared__ double sh_sum[8];
   const int r = blockIdx.y;
@@ -179,7 +183,18 @@ __global__ void __launch_bounds__(256) k_canonical_pairs_warp(CanonArgs a, GenTe
   int8_t *occ = a.occ + (size_t)r * g.rep_stride;
   const double beta = a.beta[r];
   const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  double *sh_val = sh_stage + (size_t)wib * stage_max;
+  GenShared Sa = {}, Sb = {};
+  int n_tab = 0;
+  if (SH) {
+    cmx_gen_stage_table(a.T, G, a.pa, sh_dyn_c, Sa);
+    Sb = Sa;
+    n_tab = 1;
+    if (a.pb != a.pa) {
+      cmx_gen_stage_table(a.T, G, a.pb, sh_dyn_c + table_bytes, Sb);
+      n_tab = 2;
+    }
+  }
+  double *sh_val = reinterpret_cast<double *>(sh_dyn_c + (size_t)n_tab * table_bytes) + (size_t)wib * (stage_max + 1);
   long long n_att = 0, n_acc = 0;
   double e_sum = 0.0;
   for (int colour = colour_begin; colour < colour_end; ++colour) {
@@ -200,8 +215,16 @@ __global__ void __launch_bounds__(256) k_canonical_pairs_warp(CanonArgs a, GenTe
       const int na = a.map_ab[ob], nb = a.map_ba[oa];
       if (na < 0 || nb < 0 || na == oa) continue;  // warp-uniform
       if (lane == 0) ++n_att;
-      double dE = cmx_warp_site_delta<true>(a.T, g, G, occ, sh_val, a.pa, i, j, k, oa, na, -1, 0, lane);
-      dE += cmx_warp_site_delta<true>(a.T, g, G, occ, sh_val, a.pb, i2, j2, k2, ob, nb, off_a, na, lane);
+      double dE;
+      if (SH) {
+        if (lane == 0) sh_val[Sa.n_act * a.T.n_func] = 1.0;  // the unused-factor slot
+        dE = cmx_warp_site_delta_sh<true>(a.T, g, Sa, occ, sh_val, i, j, k, oa, na, -1, 0, lane);
+        if (lane == 0) sh_val[Sb.n_act * a.T.n_func] = 1.0;
+        dE += cmx_warp_site_delta_sh<true>(a.T, g, Sb, occ, sh_val, i2, j2, k2, ob, nb, off_a, na, lane);
+      } else {
+        dE = cmx_warp_site_delta<true>(a.T, g, G, occ, sh_val, a.pa, i, j, k, oa, na, -1, 0, lane);
+        dE += cmx_warp_site_delta<true>(a.T, g, G, occ, sh_val, a.pb, i2, j2, k2, ob, nb, off_a, na, lane);
+      }
       bool accept = dE < 0.0;
       if (!accept) {
         const uint32_t gid = (uint32_t)(((uint32_t)k * g.N1 + j) * g.N0 + i);
@@ -413,7 +436,10 @@ int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t
   for (auto const &sp : P.swaps)
     max_items = std::max<uint32_t>(max_items, (uint32_t)((g.n_cells) / sp.n_colours));
   const bool warp = cmx_use_warp_generic(s);
-  const size_t stage_bytes = (size_t)SP.stage_max * 8 * sizeof(double);
+  const size_t table_bytes = (cmx_gen_shared_bytes(SP.pk_terms_max, SP.pk_act_max, s->t->d.max_occ) + 15) & ~(size_t)15;
+  const bool staged = warp && SP.d_gt_pk && 2 * table_bytes + (size_t)(SP.stage_max + 1) * 64 <= 200 * 1024;
+  const size_t stage_bytes = (size_t)(SP.stage_max + 1) * 8 * sizeof(double) + (staged ? 2 * table_bytes : 0);
+  const void *kern = staged ? (const void *)k_canonical_pairs_warp<true> : (const void *)k_canonical_pairs_warp<false>;
   int blocks = (int)std::min<uint32_t>((max_items + 127) / 128,
                                        std::max(1, (148 * 16 + s->n_replicas - 1) / s->n_replicas));
   bool coop = false;
@@ -421,9 +447,8 @@ int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t
     // one pair per warp, 8 warps per block; all blocks co-resident for the grid barrier
     if (P.coop_capacity < 0) {
       int per_sm = 0, dev = 0, sms = 0, can = 0;
-      if (stage_bytes > 48 * 1024)
-        CMX_CUDA(cudaFuncSetAttribute(k_canonical_pairs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canonical_pairs_warp, 256, stage_bytes) != cudaSuccess)
+      CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, stage_bytes) != cudaSuccess)
         per_sm = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -489,17 +514,18 @@ int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t
       a.map_ab = P.d_map + sp.map_off_ab;
       a.map_ba = P.d_map + sp.map_off_ba;
       if (warp) {
-        GenTerms G{SP.d_gt_beg, SP.d_gt_fbeg, SP.d_gt_vi, SP.d_act_beg, SP.d_act_n, SP.d_gt_w};
-        int stage_max = SP.stage_max;
+        GenTerms G{SP.d_gt_beg, SP.d_gt_fbeg, SP.d_gt_vi, SP.d_act_beg, SP.d_act_n, SP.d_gt_w, SP.d_gt_pk};
+        int stage_max = SP.stage_max, tb = (int)table_bytes;
         a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 24) | ((uint32_t)q << 12);
         if (coop) {
           int c_begin = 0, c_end = sp.n_colours, one = 1;
-          void *args[6] = {&a, &G, &stage_max, &c_begin, &c_end, &one};
-          CMX_CUDA(cudaLaunchCooperativeKernel((const void *)k_canonical_pairs_warp, grid, dim3(256), args,
-                                               stage_bytes, s->stream));
+          void *args[7] = {&a, &G, &stage_max, &c_begin, &c_end, &one, &tb};
+          CMX_CUDA(cudaLaunchCooperativeKernel(kern, grid, dim3(256), args, stage_bytes, s->stream));
         } else {
-          for (int c = 0; c < sp.n_colours; ++c)
-            k_canonical_pairs_warp<<<grid, 256, stage_bytes, s->stream>>>(a, G, stage_max, c, c + 1, 0);
+          for (int c = 0; c < sp.n_colours; ++c) {
+            if (staged) k_canonical_pairs_warp<true><<<grid, 256, stage_bytes, s->stream>>>(a, G, stage_max, c, c + 1, 0, tb);
+            else k_canonical_pairs_warp<false><<<grid, 256, stage_bytes, s->stream>>>(a, G, stage_max, c, c + 1, 0, tb);
+          }
         }
         continue;
       }

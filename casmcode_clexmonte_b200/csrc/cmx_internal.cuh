@@ -113,6 +113,10 @@ struct SweepPlan {
   // site-function value, slot * n_func + f
   int32_t *d_gt_vi = nullptr, *d_act_beg = nullptr, *d_act_n = nullptr;
   int32_t stage_max = 0;  // max over p of (active neighbors of p) * n_func
+  // packed form for shared-memory staging: 4 x 16-bit value indices per term (unused
+  // factors point at a slot that holds 1.0); 0 when a term has more than 4 factors
+  uint2 *d_gt_pk = nullptr;
+  int32_t pk_terms_max = 0, pk_act_max = 0;  // max over p of terms / active neighbors
   // pair LUT: one sublattice, <= 3 occupants, offsets in {-1,0,1}^3,
   // one class of symmetry-equivalent neighbors
   int32_t nocc = 0;
@@ -332,7 +336,18 @@ struct LocalFetch {  // synthetic neighborhood (LUT construction)
 struct GenTerms {
   const int32_t *gt_beg, *gt_fbeg, *gt_vi, *act_beg, *act_n;
   const double *gt_w;
+  const uint2 *gt_pk;  // packed value indices, or null
 };
+// the tables of ONE point position staged in shared memory (cmx_gen_stage_table)
+struct GenShared {
+  const uint2 *vi;    // [n_terms] 4 x 16-bit indices into the staged values
+  const double *w;    // [n_terms][max_occ][max_occ]
+  const int4 *act;    // [n_act] neighbor offsets (di, dj, dk, sublattice)
+  int n_terms, n_act;
+};
+__host__ __device__ inline size_t cmx_gen_shared_bytes(int n_terms, int n_act, int max_occ) {
+  return (size_t)n_terms * (8 + 8 * max_occ * max_occ) + (size_t)n_act * 16;
+}
 // Single-site delta E of point position p at cell (i,j,k), occupant oi -> of, with one
 // overridden site (byte offset ov_off holds occupant ov_occ), evaluated by ONE WARP:
 //  1. the lanes stage phi_f(occupant) of every neighbor the terms of p read into the
@@ -368,6 +383,68 @@ __device__ __forceinline__ double cmx_warp_site_delta(const DevTables &T, const 
     part += v;
   }
   __syncwarp();  // the staged values may be overwritten by the caller's next evaluation
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  return part;
+}
+
+// Block-wide: copy the packed term table of point position p into shared memory at
+// `smem` (16-byte aligned, cmx_gen_shared_bytes); ends with a barrier.
+__device__ __forceinline__ void cmx_gen_stage_table(const DevTables &T, const GenTerms &G, int p,
+                                                    unsigned char *smem, GenShared &S) {
+  const int mo2 = T.max_occ * T.max_occ;
+  const int tb = G.gt_beg[p], ab = G.act_beg[p];
+  S.n_terms = G.gt_beg[p + 1] - tb;
+  S.n_act = G.act_beg[p + 1] - ab;
+  int4 *act = reinterpret_cast<int4 *>(smem);  // 16-byte entries first: alignment
+  double *w = reinterpret_cast<double *>(act + S.n_act);
+  uint2 *vi = reinterpret_cast<uint2 *>(w + (size_t)S.n_terms * mo2);
+  for (int q = threadIdx.x; q < S.n_terms * mo2; q += blockDim.x) w[q] = G.gt_w[(size_t)tb * mo2 + q];
+  for (int q = threadIdx.x; q < S.n_terms; q += blockDim.x) vi[q] = G.gt_pk[tb + q];
+  for (int q = threadIdx.x; q < S.n_act; q += blockDim.x) act[q] = T.nbr[G.act_n[ab + q]];
+  S.w = w;
+  S.vi = vi;
+  S.act = act;
+  __syncthreads();
+}
+
+// cmx_warp_site_delta with the term table in shared memory: every read of the term loop
+// (indices, weight, staged values) is a shared-memory read, the products of a lane's terms
+// are independent and pipeline; same products in the same order as cmx_warp_site_delta,
+// so the same bits.  sh_val[n_act * n_func] must hold 1.0 (the unused-factor slot).
+template <bool CG>
+__device__ __forceinline__ double cmx_warp_site_delta_sh(const DevTables &T, const Geom &g, const GenShared &S,
+                                                         const int8_t *occ, double *sh_val, int i, int j, int k,
+                                                         int oi, int of, int64_t ov_off, int ov_occ,
+                                                         unsigned lane) {
+  const int mo = T.max_occ, nf = T.n_func;
+#pragma unroll 4
+  for (int s = (int)lane; s < S.n_act; s += 32) {
+    const int4 o = S.act[s];
+    const int ii = cmx_wrap(i + o.x, g.N0), jj = cmx_wrap(j + o.y, g.N1);
+    const int kk = g.halo ? (k + o.z) : cmx_wrap(k + o.z, g.N2);
+    const int64_t no = cmx_site_offset(g, o.w, ii, jj, kk);
+    const int raw = CG ? (int)__ldcg(occ + no) : (int)occ[no];
+    const int oc = (no == ov_off) ? ov_occ : cmx_dec(raw);
+    const double *ph = T.phi + ((size_t)o.w * nf) * mo + oc;
+    double *dst = sh_val + (size_t)s * nf;
+    for (int f = 0; f < nf; ++f) dst[f] = ph[(size_t)f * mo];
+  }
+  __syncwarp();
+  const double *w = S.w + oi * mo + of;
+  const int mo2 = mo * mo;
+  double part = 0.0;
+#pragma unroll 4
+  for (int t = (int)lane; t < S.n_terms; t += 32) {
+    const uint2 pk = S.vi[t];
+    double v = w[(size_t)t * mo2];
+    v *= sh_val[pk.x & 0xFFFFu];
+    v *= sh_val[pk.x >> 16];
+    v *= sh_val[pk.y & 0xFFFFu];
+    v *= sh_val[pk.y >> 16];
+    part += v;
+  }
+  __syncwarp();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   return part;

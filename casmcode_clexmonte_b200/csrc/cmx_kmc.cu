@@ -592,7 +592,10 @@ __device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, doubl
     double *node = kmc_level(leaves, up, A.t, l);
     const long long nc = A.t.size[l - 1];
     for (int q = threadIdx.x; q < n_imp; q += blockDim.x) {
-      const long long i = sh.ids[q] >> l;  // several ids may share a parent: same value written
+      const long long i = sh.ids[q] >> l;
+      // ids mostly ascend (cell-major impact table): the previous entry usually has the
+      // same parent; a repeated parent that slips through writes the same value again
+      if (q > 0 && (sh.ids[q - 1] >> l) == i) continue;
       node[i] = (2 * i + 1 < nc) ? __dadd_rn(child[2 * i], child[2 * i + 1]) : child[2 * i];
     }
     __syncthreads();

@@ -36,6 +36,7 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_gt_f);
   cudaFree(p.d_gt_n);
   cudaFree(p.d_gt_vi);
+  cudaFree(p.d_gt_pk);
   cudaFree(p.d_act_beg);
   cudaFree(p.d_act_n);
   cudaFree(p.d_pair_dE);
@@ -656,13 +657,20 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
 // 225 neighbors per site) make the one-thread-per-site kernel latency bound and leave
 // most of the chip idle when a colour holds a few thousand sites.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sweep_generic_warp(GenericSweepArgs a, GenTerms G, int stage_max) {
-  extern __shared__ double sh_stage[];  // [8 warps][stage_max]
+// SH: the term table of the launch's point position is staged in shared memory first
+// (dynamic shared memory: [table, table_bytes][8 warps][stage_max + 1])
+template <bool SH>
+__global__ void __launch_bounds__(256) k_sweep_generic_warp(GenericSweepArgs a, GenTerms G, int stage_max,
+                                                            int table_bytes) {
+  extern __shared__ __align__(16) unsigned char sh_dyn_g[];
+  double *sh_stage = reinterpret_cast<double *>(sh_dyn_g + (SH ? table_bytes : 0));
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
   const int r = blockIdx.y;
   const Geom &g = a.g;
   const DevTables &T = a.T;
+  GenShared S = {};
+  if (SH) cmx_gen_stage_table(T, G, a.p, sh_dyn_g, S);
   int8_t *occ = a.occ + (size_t)r * g.rep_stride;
   const int b = T.nlist_sublat[a.p];
   const int nocc = T.n_occ[b];
@@ -670,7 +678,9 @@ __global__ void __launch_bounds__(256) k_sweep_generic_warp(GenericSweepArgs a, 
   const double beta = a.beta[r];
   const double *exch = a.exch + (size_t)r * a.exch_stride + (size_t)b * mo * mo;
   const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  double *sh_val = sh_stage + (size_t)wib * stage_max;
+  double *sh_val = sh_stage + (size_t)wib * (stage_max + 1);
+  if (SH && lane == 0) sh_val[S.n_act * T.n_func] = 1.0;  // the unused-factor slot
+  __syncwarp();
   long long n_acc = 0;
   double e_sum = 0.0;
   for (uint32_t item = blockIdx.x * 8u + wib; item < a.items; item += gridDim.x * 8u) {
@@ -703,7 +713,8 @@ __global__ void __launch_bounds__(256) k_sweep_generic_warp(GenericSweepArgs a, 
     }
     int of = oi + 1 + alt;
     if (of >= nocc) of -= nocc;
-    double dE = cmx_warp_site_delta<false>(T, g, G, occ, sh_val, a.p, i, j, k, oi, of, -1, 0, lane);
+    double dE = SH ? cmx_warp_site_delta_sh<false>(T, g, S, occ, sh_val, i, j, k, oi, of, -1, 0, lane)
+                   : cmx_warp_site_delta<false>(T, g, G, occ, sh_val, a.p, i, j, k, oi, of, -1, 0, lane);
     dE -= exch[oi * mo + of];
     bool accept = dE < 0.0;
     if (!accept) {
@@ -858,6 +869,28 @@ int cmx_plan_sweep(cmx_state *s) {
     if ((rc = to_device(gt_vi, &P.d_gt_vi))) return rc;
     if ((rc = to_device(act_beg, &P.d_act_beg))) return rc;
     if ((rc = to_device(act_n, &P.d_act_n))) return rc;
+    // packed form for the shared-memory path: <= 4 factors per term, 16-bit indices
+    std::vector<uint2> pk(gt_fbeg.size() - 1);
+    bool packable = true;
+    P.pk_terms_max = P.pk_act_max = 0;
+    for (int p = 0; p < np && packable; ++p) {
+      const int ns = act_beg[p + 1] - act_beg[p];
+      const uint32_t one = (uint32_t)(ns * T.n_func);  // the slot that holds 1.0
+      if (one > 0xFFFFu) packable = false;
+      P.pk_terms_max = std::max(P.pk_terms_max, gt_beg[p + 1] - gt_beg[p]);
+      P.pk_act_max = std::max(P.pk_act_max, ns);
+      for (int tt = gt_beg[p]; tt < gt_beg[p + 1] && packable; ++tt) {
+        uint32_t v[4] = {one, one, one, one};
+        const int nfac = gt_fbeg[tt + 1] - gt_fbeg[tt];
+        if (nfac > 4) {
+          packable = false;
+          break;
+        }
+        for (int f = 0; f < nfac; ++f) v[f] = (uint32_t)gt_vi[gt_fbeg[tt] + f];
+        pk[tt] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+      }
+    }
+    if (packable && (rc = to_device(pk, &P.d_gt_pk))) return rc;
   }
 
   // ---- colouring: stride > interaction range along each axis.  Sites on
@@ -1082,7 +1115,7 @@ static int sweep_l2_mb() {  // lattice bytes (MB) a k-slice of the fused sweep k
 bool cmx_use_warp_generic(const cmx_state *s) {
   const SweepPlan &P = s->plan;
   if ((s->sweep_flags & CMX_SWEEP_THREAD_GENERIC) || P.stage_max <= 0 || P.mut_points.empty()) return false;
-  if ((size_t)P.stage_max * 8 * sizeof(double) > 96 * 1024) return false;
+  if ((size_t)(P.stage_max + 1) * 8 * sizeof(double) > 96 * 1024) return false;
   return P.n_gterms / (int)P.mut_points.size() >= 96;
 }
 
@@ -1326,12 +1359,15 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   a.accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) ? 1 : 0;
   dim3 grid(P.part_blocks, s->n_replicas);
   const bool warp = cmx_use_warp_generic(s) && !use_pair(s);
-  const size_t stage_bytes = (size_t)P.stage_max * 8 * sizeof(double);
-  GenTerms G{P.d_gt_beg, P.d_gt_fbeg, P.d_gt_vi, P.d_act_beg, P.d_act_n, P.d_gt_w};
-  if (warp && stage_bytes > 48 * 1024) {
+  const size_t stage_bytes = (size_t)(P.stage_max + 1) * 8 * sizeof(double);
+  GenTerms G{P.d_gt_beg, P.d_gt_fbeg, P.d_gt_vi, P.d_act_beg, P.d_act_n, P.d_gt_w, P.d_gt_pk};
+  const size_t table_bytes = (cmx_gen_shared_bytes(P.pk_terms_max, P.pk_act_max, T.max_occ) + 15) & ~(size_t)15;
+  const bool staged = warp && P.d_gt_pk && table_bytes + stage_bytes <= 160 * 1024;
+  if (warp) {
     static bool attr_set = false;
     if (!attr_set) {
-      CMX_CUDA(cudaFuncSetAttribute(k_sweep_generic_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      CMX_CUDA(cudaFuncSetAttribute(k_sweep_generic_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      CMX_CUDA(cudaFuncSetAttribute(k_sweep_generic_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr_set = true;
     }
   }
@@ -1348,8 +1384,12 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
           a.p = p;
           a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) |
                      (a.rng16 ? ((col & 0xffu) << 8) : (col & 0xffffu));
-          if (warp) k_sweep_generic_warp<<<grid, 256, stage_bytes, s->stream>>>(a, G, P.stage_max);
-          else k_sweep_generic<<<grid, 256, 0, s->stream>>>(a);
+          if (staged)
+            k_sweep_generic_warp<true><<<grid, 256, table_bytes + stage_bytes, s->stream>>>(a, G, P.stage_max, (int)table_bytes);
+          else if (warp)
+            k_sweep_generic_warp<false><<<grid, 256, stage_bytes, s->stream>>>(a, G, P.stage_max, 0);
+          else
+            k_sweep_generic<<<grid, 256, 0, s->stream>>>(a);
         }
   CMX_CUDA(cudaGetLastError());
   return CMX_OK;

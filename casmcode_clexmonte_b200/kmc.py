@@ -136,7 +136,7 @@ def make_relative_impact_table(prim_events: Sequence[dict], neighborhoods: Seque
     table[j] = events (i, translation) whose rate must be recomputed after prim event j
     happened in the origin unit cell: a site event j changes (its phenomenal sites) lies
     in the required update neighborhood of event i translated by `translation`.
-    Returns (beg[n_prim + 1], entries[n][4] = (i, dx, dy, dz)), entries sorted."""
+    Returns (beg[n_prim + 1], entries[n][4] = (i, dx, dy, dz))."""
     beg, entries = [0], []
     for ev_j in prim_events:
         rows = set()
@@ -146,6 +146,8 @@ def make_relative_impact_table(prim_events: Sequence[dict], neighborhoods: Seque
                     if int(pb) == b:
                         # event i at cell (phenomenal site - neighborhood offset) reads that site
                         rows.add((i, int(px) - x, int(py) - y, int(pz) - z))
-        entries.extend(sorted(rows))
+        # cell-major order (dz, dy, dx, prim event): the event ids of a list then ascend except
+        # across periodic wraps, which lets the device skip repeated tree parents cheaply
+        entries.extend(sorted(rows, key=lambda e: (e[3], e[2], e[1], e[0])))
         beg.append(len(entries))
     return np.asarray(beg, dtype=np.int32), np.asarray(entries, dtype=np.int32).reshape(-1, 4)
