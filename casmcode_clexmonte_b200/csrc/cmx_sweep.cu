@@ -1099,7 +1099,7 @@ static int pair16_minb() {  // resident blocks per SM k_sweep_pair16 is compiled
   return v;
 }
 static int sweep_grid_per_sm() {  // blocks per SM in the grid
-  static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 4);
+  static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 3);
   return v;
 }
 static int sweep_pdl() {  // programmatic dependent launch of consecutive colour passes
@@ -1128,7 +1128,9 @@ static bool use_row16(const cmx_state *s) {
 
 static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
   int want = (int)((items + 255) / 256);
-  int cap = std::max(1, (148 * sweep_grid_per_sm() + n_replicas - 1) / n_replicas);
+  // one co-resident wave: rounding the per-replica share UP would leave a few blocks of
+  // the last replicas for a second wave
+  int cap = std::max(1, (148 * sweep_grid_per_sm()) / n_replicas);
   return std::max(1, std::min(want, cap));
 }
 

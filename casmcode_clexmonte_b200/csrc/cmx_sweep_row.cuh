@@ -444,7 +444,7 @@ __device__ __forceinline__ void row16_load_table(uint32_t *sh_tab, const uint32_
 // costs no registers.  A lane only ever reads the slots it filled itself: no
 // barrier, not even a warp one.
 template <int NOCC, uint32_t MASK_CT, bool ACCUM>
-__global__ void __launch_bounds__(256, 4) k_sweep_row16(Pair16Args a) {
+__global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   constexpr int NTAB = CMX_TAB24(NOCC);
   constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
   // dynamic shared memory: [acceptance table][8 warps x NSLOT row slots x (32 lanes x 16 B)]
