@@ -258,6 +258,9 @@ __device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16La
   const uint32_t gid = ((uint32_t)(k + a.k_offset) * (uint32_t)N1 + (uint32_t)j) * a.W + L.c;
   const Row16Addr A = row16_addr(a, L, j, k);
   int8_t *pc = A.pc;
+  // both colours' random fields up front: two independent 10-round chains interleave
+  const Philox ph_c0 = philox4x32_10_rk(gid, r, sweep_lo, ctr_hi, a.rk);
+  const Philox ph_c1 = philox4x32_10_rk(gid, r, sweep_lo, ctr_hi | 0x100u, a.rk);
   uint32_t C[4], T[4];
   {
     uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
@@ -320,7 +323,7 @@ __device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16La
   }
   {
     const uint32_t ctr0 = ctr_hi;
-    const Philox ph = philox4x32_10_rk(gid, r, sweep_lo, ctr0, a.rk);
+    const Philox &ph = ph_c0;
     row16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, rej0, tmin, dEpot, e_sum);
     CMX_ROW16_TIES(0, rej0, ctr0);
   }
@@ -335,7 +338,7 @@ __device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16La
   }
   {
     const uint32_t ctr1 = ctr_hi | 0x100u;
-    const Philox ph = philox4x32_10_rk(gid, r, sweep_lo, ctr1, a.rk);
+    const Philox &ph = ph_c1;
     row16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, rej1, tmin, dEpot, e_sum);
     CMX_ROW16_TIES(1, rej1, ctr1);
   }
