@@ -441,6 +441,7 @@ extern "C" int cmx_state_ipc_attach(cmx_state *s, const void *handle_dn, const v
   CMX_CUDA(cudaMemset(s->d_sig, 0, sizeof(unsigned long long) * 4));
   s->epoch = 0;
   s->blocks_done = 0;
+  s->published = 0;
   s->p2p = true;
   return CMX_OK;
 }

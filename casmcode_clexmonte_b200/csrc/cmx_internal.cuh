@@ -191,6 +191,7 @@ struct cmx_state {
   void *ipc_open[4] = {nullptr, nullptr, nullptr, nullptr};  // mappings to close
   unsigned long long epoch = 0;        // k-group steps completed by this rank
   unsigned long long blocks_done = 0;  // expected value of d_sig[2]
+  unsigned long long published = 0;    // last epoch announced to the ring neighbours
   // scratch
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -199,6 +200,7 @@ struct cmx_state {
 
 int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
+int cmx_slab_publish(cmx_state *s);  // announce a completed, unannounced ring step
 bool cmx_use_warp_generic(const cmx_state *s);  // wide orbit sets: one site per warp
 void cmx_canonical_free(cmx_state *s);
 int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep, bool reset);

@@ -1300,13 +1300,27 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
         gl.x = std::min<uint32_t>((uint32_t)P.part_blocks, (a.n_tiles + 7) / 8);
       }
       a.wait_epoch = a.signal_epoch = a.blocks_target = 0;
-      if (a.push) {
-        // one k-colour group = one step of the ring protocol: wait for the
-        // neighbours' previous step before the first launch, publish after the last
+      if (a.push && row16) {
+        // one k-colour group = one step of the ring protocol.  Warp-row kernel: the tiles
+        // next to a ghost layer come last and wait for the neighbours' previous step; the
+        // step this rank completed is published by the first launch that follows it
+        // (cmx_slab_publish at synchronisation points)
+        a.wait_epoch = s->epoch;
+        if (s->epoch > s->published) {
+          a.signal_epoch = s->epoch;
+          s->published = s->epoch;
+        }
+        if (group_last) ++s->epoch;
+      } else if (a.push) {
+        // block kernel: wait for the neighbours' previous step before the first launch,
+        // the last block of the last launch publishes
         if (group_first) a.wait_epoch = s->epoch;
         s->blocks_done += (unsigned long long)gl.x * gl.y;
         a.blocks_target = s->blocks_done;
-        if (group_last) a.signal_epoch = ++s->epoch;
+        if (group_last) {
+          a.signal_epoch = ++s->epoch;
+          s->published = s->epoch;
+        }
       }
       if (row16) {
         const bool pdl = sweep_pdl() && P.pdl_ok;
@@ -1459,10 +1473,27 @@ extern "C" int cmx_counters_reset(cmx_state *s) {
   return CMX_OK;
 }
 
+// slabs: publish the ring epoch this rank has completed but not yet announced (the
+// warp-row kernel announces a step in the prologue of the launch that follows it)
+__global__ void k_slab_publish(unsigned long long *peer_dn, unsigned long long *peer_up, unsigned long long epoch) {
+  __threadfence_system();
+  st_sys(peer_dn + 1, epoch);
+  st_sys(peer_up + 0, epoch);
+}
+int cmx_slab_publish(cmx_state *s) {
+  if (!s->p2p || s->epoch <= s->published) return CMX_OK;
+  k_slab_publish<<<1, 1, 0, s->stream>>>(s->peer_sig_dn, s->peer_sig_up, s->epoch);
+  CMX_CUDA(cudaGetLastError());
+  s->published = s->epoch;
+  s->plan.pdl_ok = false;  // the next sweep launch follows a kernel without a dependent-launch trigger
+  return CMX_OK;
+}
+
 extern "C" int cmx_counters_read(cmx_state *s, cmx_counters *counters) {
   int rc = sweep_prepare(s, "cmx_counters_read");
   if (rc) return rc;
   if (!counters) return invalid("cmx_counters_read: null output");
+  if ((rc = cmx_slab_publish(s))) return rc;
   SweepPlan &P = s->plan;
   k_reduce_counters<<<s->n_replicas, 32, 0, s->stream>>>(P.d_part_acc, P.d_part_dE, P.part_blocks,
                                                         P.attempts, s->d_counters);

@@ -467,16 +467,14 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   double e_tot = 0.0;
   // the lattice may only be touched once the previous launch has completed
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (a.wait_epoch && threadIdx.x == 0) {
-    // acquire: the neighbours' pushes into my ghost layers precede their flag
-    const long long t0 = clock64();
-    while (ld_sys(a.my_sig + 0) < a.wait_epoch || ld_sys(a.my_sig + 1) < a.wait_epoch) {
-      if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour is gone
-        a.my_sig[3] = 1ull;
-        break;
-      }
-      __nanosleep(100);
-    }
+  // Slab ring protocol (see sweep_once).  The previous launches of this rank are complete,
+  // their stores into the neighbours' ghost layers included: publish the epoch they
+  // reached.  Publishing here instead of at the end of the previous launch keeps
+  // system-scope fences and remote round trips out of every launch's tail.
+  if (a.signal_epoch && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
+    st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
   }
   __syncthreads();
   const uint32_t warp0 = blockIdx.x * 8u + wib, n_warps = gridDim.x * 8u;
@@ -486,11 +484,36 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   fastdivmod(min(row, a.n_rows - 1u) + a.row_begin, a.divJ, kk, jj);
   fastdivmod(a.n_rows - 1u + a.row_begin, a.divJ, kk_last, jj_last);
   fastdivmod(n_warps << rpw_log, a.divJ, step_k, step_j);
+  // Only the layer next to a ghost layer (k = 0 for cz = 0, k = N2-1 for cz = 1) reads
+  // the neighbours' data and writes into their ghost layers.  The layers are visited in
+  // rotated order so that this layer comes LAST, and only its tiles wait for the
+  // neighbours' epoch: the interior of the slab is updated while the neighbours finish
+  // their previous step and their flag travels.
+  const int32_t kk_end = (int32_t)((a.row_begin + a.n_rows) / a.J), n_layers = (int32_t)(a.n_rows / a.J);
+  const int32_t rot = (a.push && a.cz == 0) ? 1 : 0;
+  auto wait_neighbours = [&](int32_t k) {
+    const bool need = a.wait_epoch && (k == 0 || k == a.g.N2 - 1);
+    if (!__any_sync(0xffffffffu, need)) return;
+    if (lane == 0) {
+      // acquire: the neighbours' pushes into my ghost layers precede their flag
+      const long long t0 = clock64();
+      while (ld_sys(a.my_sig + 0) < a.wait_epoch || ld_sys(a.my_sig + 1) < a.wait_epoch) {
+        if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour is gone
+          a.my_sig[3] = 1ull;
+          break;
+        }
+        __nanosleep(100);
+      }
+    }
+    __syncwarp();
+  };
   // (j, k, on) of the tile at the current position, then advance the position
   auto take = [&](int32_t &j, int32_t &k, bool &on) {
     on = row < a.n_rows;  // a partial last tile: the idle lanes redo the last row, unstored
     j = 2 * (int32_t)(on ? jj : jj_last) + a.cy;
-    k = 2 * (int32_t)(on ? kk : kk_last) + a.cz;
+    int32_t kq = (int32_t)(on ? kk : kk_last) + rot;
+    if (kq >= kk_end) kq -= n_layers;
+    k = 2 * kq + a.cz;
     row += n_warps << rpw_log;
     jj += step_j;
     kk += step_k;
@@ -504,6 +527,7 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   uint32_t tile = warp0;
   if (tile < a.n_tiles) {
     take(j, k, on);
+    wait_neighbours(k);
     row16_issue<MASK_CT>(a, L, j, k, slots);
   }
   for (; tile < a.n_tiles; tile += n_warps) {
@@ -511,25 +535,17 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
     if (more) take(jn, kn, on_n);
     cp_async_wait_all();
     auto stage_next = [&]() {
-      if (more) row16_issue<MASK_CT>(a, L, jn, kn, slots);
+      if (more) {
+        wait_neighbours(kn);
+        row16_issue<MASK_CT>(a, L, jn, kn, slots);
+      }
     };
     row16_tile<NOCC, MASK_CT, ACCUM, true, 1>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot, slots, stage_next);
     j = jn;
     k = kn;
     on = on_n;
   }
-  if (row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum) && a.push) {
-    // release: every store of this block (ordered before this thread by the
-    // barrier in the reduction) is visible system-wide before the block counts as
-    // done; the block that completes the step publishes the epoch to both neighbours
-    __threadfence_system();
-    const unsigned long long done = atomicAdd(a.my_sig + 2, 1ull) + 1ull;
-    if (a.signal_epoch && done == a.blocks_target) {
-      __threadfence_system();
-      st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
-      st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
-    }
-  }
+  row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum);
 }
 
 // ---- whole sweeps in ONE launch ---------------------------------------------------
