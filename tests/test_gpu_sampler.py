@@ -254,3 +254,66 @@ def test_heat_capacity_and_susceptibility_match_reference_run(dev_tables, system
             (name, ref.mean(axis=0)[q], gpu.mean(axis=0)[q], se[q])
     sm.close()
     st.close()
+
+
+def test_binary_canonical_temperature_path_matches_reference(dev_tables, systems, oracle):
+    """BASELINE configs[0]: FCC A-B canonical Metropolis (vacancy fraction 0) on a
+    4 000-site box along a temperature path.  The conditions of the path are the replicas
+    of ONE state (a run series with independent runs, run/functions.hh:83-166), sampled
+    on the device; <formation energy> and the heat capacity at every temperature agree
+    with the reference's sequential any-two-sites swaps (oracle: propose_canonical_event
+    restated, reference kernels) within 3 sigma over independent runs."""
+    if oracle is None:
+        pytest.skip("oracle/_ref not built")
+    sysd = systems["fcc"]
+    eci = sysd["eci_sparse"]
+    N = (20, 20, 10)                      # 4 000 sites, as the 10^3 conventional FCC box
+    n_cells = int(np.prod(N))
+    temps = [2000.0, 1100.0, 600.0]
+    n_runs, n_samp = 4, 60
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=3, Rt=np.array(sysd["axes"]["Rt"]), origin=np.array(sysd["axes"]["origin"]))
+    sc = oracle.RefClexulator("fcc_default").supercell(N)
+    base = np.array([0] * (n_cells // 2) + [1] * (n_cells - n_cells // 2), dtype=np.int32)
+    inits = [np.random.default_rng(40 + q).permutation(base).astype(np.int32) for q in range(n_runs)]
+    ref = np.zeros((len(temps), n_runs, 2))
+    for ti, T in enumerate(temps):
+        c_heat = _capi.KB * T * T / n_cells
+        for q in range(n_runs):
+            occ = sc.metropolis_run(1, inits[q], prim, eci["index"], eci["value"], T, seed=900 + 17 * ti + q,
+                                    n_steps=40 * n_cells)["occ"]
+            es = np.zeros(n_samp)
+            for k in range(n_samp):
+                occ = sc.metropolis_run(1, occ, prim, eci["index"], eci["value"], T,
+                                        seed=7000 + 1000 * ti + 100 * q + k, n_steps=2 * n_cells)["occ"]
+                g = sc.global_corr(occ)
+                es[k] = float(np.dot(eci["value"], g[eci["index"]])) / n_cells
+            ref[ti, q] = es.mean(), es.var() / c_heat
+    R = len(temps) * n_runs
+    st = _capi.State(dev_tables("fcc_default"), N, R)
+    st.set_eci(eci["index"], eci["value"])
+    o2s = _o2s(sysd, 3)
+    st.set_occupants(sysd["sublat_to_asym"], o2s, 3)
+    for ti, T in enumerate(temps):
+        for q in range(n_runs):
+            st.set_conditions(T, None, ti * n_runs + q)
+            st.upload_occ(inits[q], ti * n_runs + q)
+    st.canonical_set_swaps(canonical_swap_types(st.tables.host, sysd["sublat_to_asym"], o2s.tolist(), N))
+    sm = _capi.Sampler(st, n_samp, sysd["axes"]["origin"], sysd["axes"]["Rt"])
+    st.canonical_sweep(40, seed=77)
+    sm.run(n_samp, 2, seed=77, first_sweep=40, ensemble="canonical")
+    for ti, T in enumerate(temps):
+        gpu = np.zeros((n_runs, 2))
+        for q in range(n_runs):
+            r = ti * n_runs + q
+            ser = sm.series(r)
+            assert (ser["mol_composition"][:, 2] == 0).all()          # no vacancies appear
+            assert (ser["mol_composition"][:, 1] == ser["mol_composition"][0, 1]).all()
+            gpu[q] = ser["clex.formation_energy"].mean(), sm.analysis(r)["heat_capacity"]
+        se = np.hypot(ref[ti].std(axis=0, ddof=1), gpu.std(axis=0, ddof=1)) / np.sqrt(n_runs)
+        diff = np.abs(ref[ti].mean(axis=0) - gpu.mean(axis=0))
+        assert diff[0] < 3 * se[0] + 2e-4, ("energy", T, ref[ti].mean(axis=0), gpu.mean(axis=0), se)
+        assert diff[1] < 3 * se[1] + 0.05 * abs(ref[ti].mean(axis=0)[1]), ("heat capacity", T, ref[ti].mean(axis=0),
+                                                                        gpu.mean(axis=0), se)
+    sm.close()
+    st.close()
