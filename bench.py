@@ -283,10 +283,23 @@ def main():
     else:
         sites_per_launch = n_sites / world / info["launches_per_sweep"]
         kernel_name = "k_sweep_row16"
+    # DRAM traffic of one launch from the committed ncu --set full capture of this kernel at
+    # this workload (512^3, one GPU); null for any other configuration
+    traffic = None
+    prof = ROOT / "profiles" / "r01s_ncu_full_k_sweep_row16.csv"
+    if world == 1 and args.box == N_BOX and kernel_name == "k_sweep_row16" and prof.exists():
+        import csv
+        vals = {}
+        for row in csv.reader(prof.open()):
+            if len(row) == 5 and row[0] == "1" and row[2] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals[row[2]] = float(row[4]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[row[3]]
+        if len(vals) == 2:
+            traffic = sum(vals.values())
     alg_bytes = 2.0 * sites_per_launch           # 2 B per step at the HBM level
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": kernel_name,
+                "traffic": traffic, "traffic_note": "bytes per launch, dram read + write, profiles/r01s_ncu_full_k_sweep_row16.csv",
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_step_hbm": 2.0,
                 "algorithmic_bytes_per_step_l2": info["bytes_per_step"],
                 "note": "the sweep is instruction-issue bound, not HBM bound: see DESIGN.md and profiles/"}

@@ -43,6 +43,7 @@ struct CanonicalPlan {
   double *d_part_dE = nullptr;  // [replica][blocks]
   int32_t blocks = 0;
   int coop_capacity = -1;  // co-resident blocks of k_canonical_pairs_warp (0: no cooperative launch)
+  int lut_capacity = -1;   // co-resident blocks of k_canonical_pairs_lut
 };
 
 void cmx_canonical_free(cmx_state *s) {
@@ -133,6 +134,119 @@ __global__ void __launch_bounds__(128) k_canonical_pairs(CanonArgs a) {
       ++n_acc;
       e_sum += dE;
     }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_att += __shfl_down_sync(0xffffffffu, n_att, o);
+    n_acc += __shfl_down_sync(0xffffffffu, n_acc, o);
+    e_sum += __shfl_down_sync(0xffffffffu, e_sum, o);
+  }
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    sh_att[wid] = n_att;
+    sh_acc[wid] = n_acc;
+    sh_sum[wid] = e_sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long A = 0, C = 0;
+    double E = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      A += sh_att[w];
+      C += sh_acc[w];
+      E += sh_sum[w];
+    }
+    size_t slot = (size_t)r * gridDim.x + blockIdx.x;
+    a.part[2 * slot] += A;
+    a.part[2 * slot + 1] += C;
+    a.part_dE[slot] += E;
+  }
+}
+
+// Pair-LUT variant (the models the pair-LUT sweep covers: one sublattice, <= 3 occupants,
+// point + pair functions of one neighbor shell): the single-site dE of the reference
+// depends only on (occupant change, species counts over the shell) and is tabulated from
+// the faithful evaluator (SweepPlan::d_pair_dE, k_build_pair_lut).  A swap is two
+// lookups: site a on the current configuration, site b with a already changed (the
+// reference's sequential occ_delta_value, CanonicalCalculator.cc:137-140) -- the shell of
+// b is counted with a's new occupant when a belongs to it.  Same proposals and random
+// bits as k_canonical_pairs; dE agrees with it to rounding (the reference sums the two
+// sites' delta correlations before the ECI dot product, here the dot products are summed).
+struct CanonLut {
+  const double *pair_dE;  // [(oi * (nocc - 1) + alt) << 8 | n1 | n2 << 4]
+  int nocc, z;
+  int shell[48];
+};
+
+template <bool CG>
+__device__ __forceinline__ double canon_lut_delta(const CanonArgs &a, const CanonLut &L, const int8_t *occ,
+                                                  int i, int j, int k, int oi, int of, int64_t ov_off,
+                                                  int ov_code) {
+  const Geom &g = a.g;
+  int n1 = 0, n2 = 0;
+#pragma unroll 4
+  for (int q = 0; q < L.z; ++q) {
+    const int ii = cmx_wrap(i + L.shell[3 * q], g.N0), jj = cmx_wrap(j + L.shell[3 * q + 1], g.N1),
+              kk = cmx_wrap(k + L.shell[3 * q + 2], g.N2);
+    const int64_t no = cmx_site_offset(g, 0, ii, jj, kk);
+    const int code = (no == ov_off) ? ov_code : (CG ? (int)__ldcg(occ + no) : (int)occ[no]);
+    n1 += code & 1;   // storage codes 0 / 1 / 18
+    n2 += code >> 4;
+  }
+  int alt = of - oi - 1;
+  if (alt < 0) alt += L.nocc;
+  return L.pair_dE[((oi * (L.nocc - 1) + alt) << 8) | n1 | (n2 << 4)];
+}
+
+// COOP: all colours [colour_begin, colour_end) of the swap type in one cooperative launch,
+// a grid barrier between colours, occupations through L2 only
+template <bool COOP>
+__global__ void __launch_bounds__(128) k_canonical_pairs_lut(CanonArgs a, CanonLut L, int colour_begin,
+                                                             int colour_end) {
+  __shared__ long long sh_att[4], sh_acc[4];
+  __shared__ double sh_sum[4];
+  const int r = blockIdx.y;
+  const Geom &g = a.g;
+  int8_t *occ = a.occ + (size_t)r * g.rep_stride;
+  const double beta = a.beta[r];
+  long long n_att = 0, n_acc = 0;
+  double e_sum = 0.0;
+  for (int colour = colour_begin; colour < colour_end; ++colour) {
+  const int c0 = colour % a.S0, c1 = (colour / a.S0) % a.S1, c2 = colour / (a.S0 * a.S1);
+  const uint32_t ctr_hi = a.ctr_hi | (uint32_t)colour;
+  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < a.items;
+       item += gridDim.x * blockDim.x) {
+    uint32_t row, ii, kk, jj;
+    fastdivmod(item, a.div0, row, ii);
+    fastdivmod(row, a.div1, kk, jj);
+    const int i = (int)ii * a.S0 + c0, j = (int)jj * a.S1 + c1, k = (int)kk * a.S2 + c2;
+    int i2 = (i + a.t0) % g.N0, j2 = (j + a.t1) % g.N1, k2 = (k + a.t2) % g.N2;
+    i2 += (i2 < 0) ? g.N0 : 0;
+    j2 += (j2 < 0) ? g.N1 : 0;
+    k2 += (k2 < 0) ? g.N2 : 0;
+    const int64_t off_a = cmx_site_offset(g, 0, i, j, k);
+    const int64_t off_b = cmx_site_offset(g, 0, i2, j2, k2);
+    const int oa = cmx_dec(COOP ? (int)__ldcg(occ + off_a) : (int)occ[off_a]);
+    const int ob = cmx_dec(COOP ? (int)__ldcg(occ + off_b) : (int)occ[off_b]);
+    if (oa == ob) continue;  // same species: no event
+    ++n_att;
+    double dE = canon_lut_delta<COOP>(a, L, occ, i, j, k, oa, ob, -1, 0);
+    dE += canon_lut_delta<COOP>(a, L, occ, i2, j2, k2, ob, oa, off_a, cmx_enc(g, ob));
+    bool accept = dE < 0.0;
+    if (!accept) {
+      const uint32_t gid = (uint32_t)(((uint32_t)k * g.N1 + j) * g.N0 + i);
+      const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr_hi, a.k0, a.k1);
+      const unsigned long long u53 = ((unsigned long long)(ph.c[1] & 0x1FFFFFu) << 32) | ph.c[0];
+      accept = (double)u53 * (1.0 / 9007199254740992.0) < exp(-dE * beta);
+    }
+    if (accept) {
+      occ[off_a] = (int8_t)cmx_enc(g, ob);
+      occ[off_b] = (int8_t)cmx_enc(g, oa);
+      ++n_acc;
+      e_sum += dE;
+    }
+  }
+  if (COOP && colour + 1 < colour_end) cg::this_grid().sync();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -443,6 +557,22 @@ int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t
   int blocks = (int)std::min<uint32_t>((max_items + 127) / 128,
                                        std::max(1, (148 * 16 + s->n_replicas - 1) / s->n_replicas));
   bool coop = false;
+  const bool lut_path = !warp && SP.pair_lut && SP.z <= 16 && s->g.coded == (SP.nocc == 3) &&
+                        !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC);
+  if (lut_path) {
+    if (P.lut_capacity < 0) {
+      int per_sm = 0, dev = 0, sms = 0, can = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canonical_pairs_lut<true>, 128, 0) != cudaSuccess)
+        per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
+      P.lut_capacity = can ? per_sm * sms : 0;
+    }
+    // a co-resident grid, so that all colours of a swap type run in one cooperative launch
+    if (P.lut_capacity / std::max(1, s->n_replicas) >= 1)
+      blocks = std::max(1, std::min(blocks, P.lut_capacity / s->n_replicas));
+  }
   if (warp) {
     // one pair per warp, 8 warps per block; all blocks co-resident for the grid barrier
     if (P.coop_capacity < 0) {
@@ -526,6 +656,27 @@ int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t
             if (staged) k_canonical_pairs_warp<true><<<grid, 256, stage_bytes, s->stream>>>(a, G, stage_max, c, c + 1, 0, tb);
             else k_canonical_pairs_warp<false><<<grid, 256, stage_bytes, s->stream>>>(a, G, stage_max, c, c + 1, 0, tb);
           }
+        }
+        continue;
+      }
+      const bool lut = lut_path;
+      CanonLut CL;
+      if (lut) {
+        CL.pair_dE = SP.d_pair_dE;
+        CL.nocc = SP.nocc;
+        CL.z = SP.z;
+        for (int x = 0; x < 48; ++x) CL.shell[x] = SP.shell[x];
+      }
+      if (lut) {
+        a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 24) | ((uint32_t)q << 12);
+        static const bool no_coop = getenv("CMX_CANONICAL_NO_COOP") != nullptr;
+        if (!no_coop && (long long)grid.x * grid.y <= P.lut_capacity) {
+          int c_begin = 0, c_end = sp.n_colours;
+          void *args[4] = {&a, &CL, &c_begin, &c_end};
+          CMX_CUDA(cudaLaunchCooperativeKernel((const void *)k_canonical_pairs_lut<true>, grid, dim3(128), args, 0,
+                                               s->stream));
+        } else {
+          for (int c = 0; c < sp.n_colours; ++c) k_canonical_pairs_lut<false><<<grid, 128, 0, s->stream>>>(a, CL, c, c + 1);
         }
         continue;
       }

@@ -121,6 +121,7 @@ struct SweepPlan {
   // one class of symmetry-equivalent neighbors
   int32_t nocc = 0;
   int32_t z = 0;          // neighbors in the class
+  int32_t shell[48] = {0};  // their offsets (di, dj, dk), at most 16
   uint32_t mask = 0;      // bit (dk+1)*9 + (dj+1)*3 + (di+1)
   int32_t n_lut = 0;      // nocc*(nocc-1)*256 entries
   double *d_pair_dE = nullptr;       // [n_lut] clex dE per (oi, alt, counts)

@@ -987,6 +987,11 @@ int cmx_plan_sweep(cmx_state *s) {
     for (auto const &kv : V) {
       const int32_t *o = &t->nbr[4 * kv.first];
       P.mask |= 1u << ((o[2] + 1) * 9 + (o[1] + 1) * 3 + (o[0] + 1));
+      if (cls.size() < 16) {
+        P.shell[3 * cls.size()] = o[0];
+        P.shell[3 * cls.size() + 1] = o[1];
+        P.shell[3 * cls.size() + 2] = o[2];
+      }
       cls.push_back(kv.first);
     }
     P.n_lut = P.nocc * (P.nocc - 1) * 256;

@@ -195,3 +195,31 @@ def test_warp_evaluator_equals_thread_evaluator(dev_tables, systems, ensemble):
         assert (occ_w[r] == occ_t[r]).all()
         assert cnt_w[r] == cnt_t[r] and cnt_w[r][1] > 0
         assert de_w[r] == pytest.approx(de_t[r], rel=1e-10, abs=1e-9)
+
+
+@pytest.mark.parametrize("N,binary", [((32, 16, 16), False), ((16, 8, 8), True), ((64, 4, 6), False)])
+def test_canonical_pair_lut_equals_generic(dev_tables, systems, N, binary):
+    """Pair-LUT canonical kernel (two table lookups per swap, the second with the first
+    site's new occupant) against the generic term-list kernel: same proposals and random
+    bits, dE equal to rounding -> identical trajectories and counters."""
+    rng = np.random.default_rng(12)
+    n_cells = int(np.prod(N))
+    occ = rng.choice(2 if binary else 3, size=n_cells).astype(np.int32)
+    out = []
+    for flags in (0, _capi.CMX_SWEEP_FORCE_GENERIC):
+        st, sysd, swaps = _state(dev_tables, systems, "fcc", "eci_sparse", N, 700.0, occ, n_replicas=2)
+        st.set_conditions(1500.0, None, 1)
+        st.set_sweep_flags(flags)
+        st.canonical_set_swaps(swaps)
+        c1 = st.canonical_sweep(3, seed=4)
+        c2 = st.canonical_sweep(2, seed=4, first_sweep=3)
+        out.append(([st.download_occ(r) for r in range(2)],
+                    [(c1[r].n_attempt + c2[r].n_attempt, c1[r].n_accept + c2[r].n_accept) for r in range(2)],
+                    [c1[r].dE_sum + c2[r].dE_sum for r in range(2)], st.energy(0)))
+        st.close()
+    (occ_l, cnt_l, de_l, e_l), (occ_g, cnt_g, de_g, e_g) = out
+    for r in range(2):
+        assert (occ_l[r] == occ_g[r]).all()
+        assert cnt_l[r] == cnt_g[r] and 0 < cnt_l[r][1] < cnt_l[r][0]
+        assert de_l[r] == pytest.approx(de_g[r], rel=1e-10, abs=1e-9)
+        assert (np.bincount(occ_l[r], minlength=3) == np.bincount(occ, minlength=3)).all()

@@ -98,6 +98,34 @@ def c2():
     t.close()
 
 
+def c1():
+    """FCC A-B canonical pair exchanges (BASELINE configs[0] method) at GPU scale."""
+    sysd = SYS["fcc"]
+    t = tables("fcc_default")
+    for N, R in ((128, 1), (256, 1), (32, 64)):
+        n = N ** 3
+        st = _capi.State(t, (N, N, N), R)
+        st.set_eci(sysd["eci_sparse"]["index"], sysd["eci_sparse"]["value"])
+        m = o2s(sysd, 3)
+        st.set_occupants(sysd["sublat_to_asym"], m, 3)
+        rng = np.random.default_rng(2)
+        occ = (rng.random(n) < 0.5).astype(np.int32)
+        for r in range(R):
+            st.upload_occ(occ, r)
+            st.set_conditions(600.0 + 20.0 * r, None, r)
+        swaps = canonical_swap_types(st.tables.host, sysd["sublat_to_asym"], m.tolist(), (N, N, N))
+        st.canonical_set_swaps(swaps)
+        st.canonical_sweep(1, seed=1)
+        S = 3
+        ms, cnt = timed(st, lambda: st.canonical_sweep(S, seed=1, first_sweep=1))
+        att = float(sum(c.n_attempt for c in cnt))
+        emit(workload=f"c1: FCC A-B canonical pair exchanges, {N}^3 sites x {R} replicas, shipped sparse ECI, {len(swaps)} swap types",
+             metric="attempted MC steps/s (each a two-site dE)", value=att / (ms * 1e-3), ms=ms, sweeps=S,
+             accept_rate=sum(c.n_accept for c in cnt) / att, kernel="k_canonical_pairs")
+        st.close()
+    t.close()
+
+
 def sample():
     sysd = SYS["fcc"]
     t = tables("fcc_default")
@@ -278,11 +306,11 @@ def c5():
 
 
 def main():
-    which = sys.argv[1:] or ["c2", "sample", "c4", "c4cpu", "c5"]
+    which = sys.argv[1:] or ["c1", "c2", "sample", "c4", "c4cpu", "c5"]
     if not torch.cuda.is_available():
         raise SystemExit("bench_workloads.py: no CUDA device")
     for w in which:
-        {"c2": c2, "sample": sample, "c4": c4, "c4cpu": c4_cpu, "c5": c5}[w]()
+        {"c1": c1, "c2": c2, "sample": sample, "c4": c4, "c4cpu": c4_cpu, "c5": c5}[w]()
 
 
 if __name__ == "__main__":
