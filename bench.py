@@ -295,11 +295,28 @@ def main():
                 vals[row[2]] = float(row[4]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[row[3]]
         if len(vals) == 2:
             traffic = sum(vals.values())
+    # the resource ncu identifies as binding (issue slots / ALU pipe), from the same capture
+    binding = None
+    if traffic is not None:
+        import csv
+        m = {}
+        for row in csv.reader(prof.open()):
+            if len(row) == 5 and row[0] == "1":
+                m[row[2]] = row[4]
+        try:
+            binding = {"resource": "instruction issue slots (ALU pipe)", "unit": "% of peak sustained",
+                       "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+                       "alu_pipe_pct": float(m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]),
+                       "dram_pct": float(m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]),
+                       "source": "profiles/r01s_ncu_full_k_sweep_row16.csv (ncu --set full, one launch)"}
+        except (KeyError, ValueError):
+            binding = None
     alg_bytes = 2.0 * sites_per_launch           # 2 B per step at the HBM level
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_note": "bytes per launch, dram read + write, profiles/r01s_ncu_full_k_sweep_row16.csv",
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel": kernel_name,
+                "algorithmic_bytes_per_launch": alg_bytes, "binding_resource": binding, "peak_source": peak_src,
+                "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_step_hbm": 2.0,
                 "algorithmic_bytes_per_step_l2": info["bytes_per_step"],
                 "note": "the sweep is instruction-issue bound, not HBM bound: see DESIGN.md and profiles/"}
