@@ -317,3 +317,30 @@ def test_binary_canonical_temperature_path_matches_reference(dev_tables, systems
                                                                         gpu.mean(axis=0), se)
     sm.close()
     st.close()
+
+
+def test_run_series_batches_the_conditions_path(dev_tables, systems):
+    """run_series with independent runs = the states of an incremental conditions path as
+    replicas of one device state; every state equals the same run done on its own, and a
+    dependent series hands the final configuration to the next state."""
+    from casmcode_clexmonte_b200.run_series import run_series
+    sysd = systems["fcc"]
+    eci = sysd["eci_sparse"]
+    N = (16, 8, 8)
+    occ = np.random.default_rng(2).integers(0, 3, int(np.prod(N))).astype(np.int32)
+    init = {"temperature": 600.0, "param_chem_pot": [-0.5, 0.0]}
+    inc = {"temperature": 300.0, "param_chem_pot": [0.25, 0.0]}
+    kw = dict(n_equilibration_passes=5, n_samples=6, sample_period=2, seed=9)
+    res = run_series(dev_tables("fcc_default"), N, sysd, eci["index"], eci["value"], init, inc, 4, occ, **kw)
+    assert [r["conditions"]["temperature"] for r in res] == [600.0, 900.0, 1200.0, 1500.0]
+    assert all(r["potential_energy"]["n_samples"] == 6 and 0 < r["acceptance_rate"] < 1 for r in res)
+    assert res[0]["acceptance_rate"] < res[-1]["acceptance_rate"]          # hotter: more acceptances
+    # replica 0 of the batch == the one-state series (replica index enters the RNG counter)
+    one = run_series(dev_tables("fcc_default"), N, sysd, eci["index"], eci["value"], init, inc, 1, occ, **kw)
+    assert one[0]["potential_energy"]["mean"] == res[0]["potential_energy"]["mean"]
+    assert (one[0]["final_occupation"] == res[0]["final_occupation"]).all()
+    assert one[0]["heat_capacity"] == res[0]["heat_capacity"]
+    dep = run_series(dev_tables("fcc_default"), N, sysd, eci["index"], eci["value"], init, inc, 2, occ,
+                     dependent_runs=True, **kw)
+    assert (dep[0]["final_occupation"] == res[0]["final_occupation"]).all()
+    assert dep[1]["conditions"]["temperature"] == 900.0 and dep[1]["potential_energy"]["n_samples"] == 6
