@@ -522,6 +522,7 @@ struct KmcRunArgs {
   long long log_cap;
   long long n_steps;
   int max_imp, t_max;
+  int l_sh;  // first tree level kept in shared memory
 };
 
 #define CMX_KMC_CHUNK 16  // allowed events evaluated per round of the block
@@ -532,7 +533,17 @@ struct KmcShared {
   int *allowed;
   double *val;
   int t_max;
+  // the upper levels of the sum tree (from level l_sh on: <= 1024 nodes) live in shared
+  // memory while the kernel runs: re-summing and descending them costs shared-memory
+  // latency instead of an L2 round trip per level
+  double *tree;
+  int l_sh;
 };
+__device__ __forceinline__ double *kmc_level_sh(double *leaves, double *up, const KmcTree &t, const KmcShared &sh,
+                                                int l) {
+  if (l >= sh.l_sh) return sh.tree + (t.off[l] - t.off[sh.l_sh]);
+  return l == 0 ? leaves : up + t.off[l];
+}
 
 // re-evaluate the events impacted by event `ev` and re-sum their tree paths
 __device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, double *leaves, double *up,
@@ -568,13 +579,15 @@ __device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, doubl
   for (int base = 0; base < n_allowed; base += CMX_KMC_CHUNK) {
     const int n_ev = min(CMX_KMC_CHUNK, n_allowed - base);
     for (int w = threadIdx.x; w < n_ev * sh.t_max; w += blockDim.x) {
-      const int x = w / sh.t_max, task = w - x * sh.t_max;
+      // neighbouring threads evaluate the SAME function (task) for different events: the
+      // loops over groups, terms and factors stay convergent within a warp
+      const int task = w / n_ev, x = w - task * n_ev;
       const long long id = sh.ids[sh.allowed[base + x]];
       const cmx_prim_event &E = A.a.prim[(int)(id % A.n_prim)];
       if (task >= kmc_n_tasks(A.a, E)) continue;
       KmcEventSites S;
       kmc_event_sites(A.a, occ, id / A.n_prim, E, S);
-      sh.val[w] = kmc_task_value(A.a, occ, E, S, task);
+      sh.val[x * sh.t_max + task] = kmc_task_value(A.a, occ, E, S, task);
     }
     __syncthreads();
     for (int x = threadIdx.x; x < n_ev; x += blockDim.x) {
@@ -588,8 +601,8 @@ __device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, doubl
   }
   // 3. re-sum the touched paths, level by level
   for (int l = 1; l <= A.t.n_levels; ++l) {
-    const double *child = kmc_level(leaves, up, A.t, l - 1);
-    double *node = kmc_level(leaves, up, A.t, l);
+    const double *child = kmc_level_sh(leaves, up, A.t, sh, l - 1);
+    double *node = kmc_level_sh(leaves, up, A.t, sh, l);
     const long long nc = A.t.size[l - 1];
     for (int q = threadIdx.x; q < n_imp; q += blockDim.x) {
       const long long i = sh.ids[q] >> l;
@@ -610,6 +623,8 @@ __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
   sh_ids.val = reinterpret_cast<double *>(sh_dyn + A.max_imp);
   sh_ids.allowed = reinterpret_cast<int *>(sh_ids.val + CMX_KMC_CHUNK * A.t_max);
   sh_ids.t_max = A.t_max;
+  sh_ids.tree = sh_ids.val + CMX_KMC_CHUNK * A.t_max + (A.max_imp + 1) / 2;  // after `allowed` (ints)
+  sh_ids.l_sh = A.l_sh;
   const int r = blockIdx.x;
   const Geom &g = A.a.g;
   double *leaves = A.rates + (size_t)r * A.per, *up = A.tree + (size_t)r * A.t.upper;
@@ -617,10 +632,13 @@ __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
   long long pending = A.pending[r];
   double time = A.time[r];
   long long steps = A.steps[r];
+  const long long n_sh = A.t.upper - A.t.off[A.l_sh];  // nodes of the shared levels (contiguous at the end)
+  for (long long q = threadIdx.x; q < n_sh; q += blockDim.x) sh_ids.tree[q] = up[A.t.off[A.l_sh] + q];
+  __syncthreads();
   for (long long step = 0; step < A.n_steps; ++step) {
     if (pending >= 0) kmc_apply_impact(A, r, pending, leaves, up, sh_ids);
     if (threadIdx.x == 0) {
-      const double total = *kmc_level(leaves, up, A.t, A.t.n_levels);
+      const double total = *kmc_level_sh(leaves, up, A.t, sh_ids, A.t.n_levels);
       long long ev = -1;
       if (total > 0.0) {
         Mt64 &mt = A.mt[r];
@@ -628,7 +646,7 @@ __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
         double q = __dmul_rn(total, mt_unit_interval(mt));
         long long idx = 0;
         for (int l = A.t.n_levels; l > 0; --l) {
-          const double *child = kmc_level(leaves, up, A.t, l - 1);
+          const double *child = kmc_level_sh(leaves, up, A.t, sh_ids, l - 1);
           const double left = child[2 * idx];
           if (q <= left || 2 * idx + 1 >= A.t.size[l - 1]) {
             idx = 2 * idx;
@@ -669,6 +687,8 @@ __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
   // leave rates and tree consistent with the occupation (the reference does this at the
   // start of the next select_event; the update is idempotent)
   if (pending >= 0) kmc_apply_impact(A, r, pending, leaves, up, sh_ids);
+  __syncthreads();
+  for (long long q = threadIdx.x; q < n_sh; q += blockDim.x) up[A.t.off[A.l_sh] + q] = sh_ids.tree[q];
   if (threadIdx.x == 0) {
     A.pending[r] = -1;
     A.time[r] = time;
@@ -821,7 +841,11 @@ extern "C" int cmx_kmc_run(cmx_kmc *k, int64_t n_steps, cmx_kmc_step *log, int64
   }
   A.max_imp = std::max(1, k->max_imp);
   A.t_max = t_max;
-  const size_t smem = (sizeof(long long) + sizeof(int)) * A.max_imp + sizeof(double) * CMX_KMC_CHUNK * t_max;
+  A.l_sh = A.t.n_levels;
+  while (A.l_sh > 1 && A.t.upper - A.t.off[A.l_sh - 1] <= 2048) --A.l_sh;  // <= 16 KB of upper levels
+  const size_t n_sh = (size_t)(A.t.upper - A.t.off[A.l_sh]);
+  const size_t smem = sizeof(long long) * A.max_imp + sizeof(double) * CMX_KMC_CHUNK * t_max +
+                      sizeof(double) * ((A.max_imp + 1) / 2) + sizeof(double) * n_sh;
   if (smem > 48 * 1024) {
     cudaFree(d_log);
     return invalid("cmx_kmc_run: impact lists longer than 6144 events are not supported");
