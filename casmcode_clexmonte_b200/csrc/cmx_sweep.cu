@@ -1094,6 +1094,39 @@ static int launch_row16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fc
   return accum ? launch_row16_inst<NOCC, 0u, true>(a, cfg) : launch_row16_inst<NOCC, 0u, false>(a, cfg);
 }
 
+template <int NOCC, uint32_t MASK, bool ACC>
+static int launch_row16_flat_inst(const Pair16Args &a, uint32_t n_replicas, cudaLaunchConfig_t &cfg) {
+  auto kern = k_sweep_row16_flat<NOCC, MASK, ACC>;
+  static bool attr_set = false;
+  const size_t bytes = row16_smem_bytes<NOCC>(MASK) + (size_t)CMX_TAB24(NOCC) * 4;
+  if (!attr_set) {
+    CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    attr_set = true;
+  }
+  cfg.dynamicSmemBytes = bytes;
+  CMX_CUDA(cudaLaunchKernelEx(&cfg, kern, a, n_replicas));
+  return CMX_OK;
+}
+// replica grids: the tiles of all replicas as one index space over gx blocks
+template <int NOCC>
+static int launch_row16_flat(const Pair16Args &a, uint32_t gx, uint32_t n_replicas, cudaStream_t st, bool fcc,
+                             bool accum, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (fcc)
+    return accum ? launch_row16_flat_inst<NOCC, kMaskFcc1NN, true>(a, n_replicas, cfg)
+                 : launch_row16_flat_inst<NOCC, kMaskFcc1NN, false>(a, n_replicas, cfg);
+  return accum ? launch_row16_flat_inst<NOCC, 0u, true>(a, n_replicas, cfg)
+               : launch_row16_flat_inst<NOCC, 0u, false>(a, n_replicas, cfg);
+}
+
 // tuning knobs (environment, read once)
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
@@ -1129,6 +1162,22 @@ static bool use_pair(const cmx_state *s) {
 }
 static bool use_row16(const cmx_state *s) {
   return use_pair(s) && s->plan.row16 && !(s->sweep_flags & CMX_SWEEP_BLOCK_KERNEL);
+}
+
+// replica grids on the warp-row kernel: one flat tile space (k_sweep_row16_flat) when a
+// block's share of it stays within two replicas
+static uint32_t row16_tiles_per_replica(const cmx_state *s) {
+  const uint32_t W = s->g.N0 / 16, rpw = 32 / W;
+  const uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
+  return (n_rows + rpw - 1) / rpw;
+}
+static uint32_t row16_flat_blocks(const cmx_state *s) {  // 0: not applicable
+  static int off = env_int("CMX_SWEEP_NO_FLAT", 0);
+  if (off || !use_row16(s) || s->n_replicas < 2 || s->g.halo) return 0;
+  const unsigned long long T = (unsigned long long)row16_tiles_per_replica(s) * s->n_replicas;
+  const uint32_t gx = (uint32_t)std::min<unsigned long long>(148ull * sweep_grid_per_sm(), (T + 7) / 8);
+  if (gx < (uint32_t)s->n_replicas) return 0;  // a block would span more than two replicas
+  return gx;
 }
 
 static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
@@ -1291,6 +1340,7 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     const bool row16 = use_row16(s);
     // one launch: colour (cy,cz), colour layers [kb, ke); first/last of a k-colour
     // group carry the ring protocol of the fused halo exchange
+    const uint32_t n_kk_all = (uint32_t)(g.N2 / 2);
     auto launch = [&](int cy, int cz, uint32_t kb, uint32_t ke, bool group_first, bool group_last) -> int {
       if (ke <= kb) return CMX_OK;
       a.cy = cy;
@@ -1329,8 +1379,14 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
       }
       if (row16) {
         const bool pdl = sweep_pdl() && P.pdl_ok;
-        int rc = (P.nocc == 3) ? launch_row16<3>(a, gl, s->stream, fcc, accum, pdl)
-                               : launch_row16<2>(a, gl, s->stream, fcc, accum, pdl);
+        const uint32_t flat = row16_flat_blocks(s);
+        int rc;
+        if (flat && kb == 0 && ke == n_kk_all)
+          rc = (P.nocc == 3) ? launch_row16_flat<3>(a, flat, (uint32_t)s->n_replicas, s->stream, fcc, accum, pdl)
+                             : launch_row16_flat<2>(a, flat, (uint32_t)s->n_replicas, s->stream, fcc, accum, pdl);
+        else
+          rc = (P.nocc == 3) ? launch_row16<3>(a, gl, s->stream, fcc, accum, pdl)
+                             : launch_row16<2>(a, gl, s->stream, fcc, accum, pdl);
         if (rc) return rc;
         P.pdl_ok = true;
       } else if (P.nocc == 3) {
@@ -1446,6 +1502,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
     if (cmx_use_warp_generic(s)) items = (uint32_t)std::min<uint64_t>((uint64_t)items * 32u, 0xFFFFFF00u);  // a warp per site
   }
   blocks = sweep_blocks_per_replica(items, s->n_replicas);
+  if (const uint32_t gx = row16_flat_blocks(s)) blocks = (int)gx;  // counter slots [replica][block]
   if (P.part_blocks != blocks || !P.d_part_acc) {
     int rc = ensure_partials(s, blocks);
     if (rc) return rc;

@@ -548,6 +548,100 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum);
 }
 
+// ---- replica grids: one flat tile space ---------------------------------------------
+// With one grid row per replica (blockIdx.y) every replica gets the same whole number of
+// blocks: 64 replicas on 444 co-resident blocks use 6 x 64 = 384 of them (86 %).  Here the
+// tiles of all replicas form ONE index space, cut into gridDim.x equal contiguous ranges;
+// a range touches at most two replicas (the host checks), whose acceptance tables both
+// sit in shared memory, and a tile looks up its replica.  Same tiles, same counters (a
+// block adds to the slots of the replicas it touched), same random numbers.
+template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+__global__ void __launch_bounds__(256, 3) k_sweep_row16_flat(Pair16Args a, uint32_t n_replicas) {
+  constexpr int NTAB = CMX_TAB24(NOCC);
+  constexpr int NTAB16 = CMX_TAB16(NOCC);
+  constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
+  // dynamic shared memory: [2 acceptance tables][8 warps x NSLOT row slots x (32 lanes x 16 B)]
+  extern __shared__ __align__(16) unsigned char sh_dyn[];
+  uint32_t *sh_tab = reinterpret_cast<uint32_t *>(sh_dyn);
+  unsigned char *sh_rows = sh_dyn + 2 * NTAB * 4;
+  __shared__ long long sh_acc[8];
+  __shared__ double sh_sum[8];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const unsigned long long T = (unsigned long long)a.n_tiles * n_replicas;
+  const uint32_t tb = (uint32_t)(T * blockIdx.x / gridDim.x), te = (uint32_t)(T * (blockIdx.x + 1) / gridDim.x);
+  const uint32_t r_lo = tb / a.n_tiles, r_hi = (te > tb) ? (te - 1u) / a.n_tiles : r_lo;  // r_hi <= r_lo + 1
+  row16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)r_lo * NTAB);
+  if (r_hi != r_lo) row16_load_table<NOCC>(sh_tab + NTAB, a.tab24 + (size_t)r_hi * NTAB);
+  Row16Lane L = row16_lane<NOCC, MASK_CT>(a, sh_tab);
+  const uint32_t tab0 = L.tab;
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t rl = lane >> a.logW;
+  const uint32_t rpw_log = 5u - a.logW;
+  const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_ROW16_SLOT) + 16u * lane;
+  uint32_t n_acc0 = 0, n_acc1 = 0;
+  double e_tot0 = 0.0, e_tot1 = 0.0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
+  // replica, (j, k) and `on` of tile t
+  auto locate = [&](uint32_t t, uint32_t &rep, int32_t &j, int32_t &k, bool &on) {
+    rep = (r_hi != r_lo && t >= r_hi * a.n_tiles) ? r_hi : r_lo;
+    const uint32_t row = ((t - rep * a.n_tiles) << rpw_log) + rl;
+    on = row < a.n_rows;  // a partial last tile: the idle lanes redo the last row, unstored
+    uint32_t kk, jj;
+    fastdivmod(min(row, a.n_rows - 1u) + a.row_begin, a.divJ, kk, jj);
+    j = 2 * (int32_t)jj + a.cy;
+    k = 2 * (int32_t)kk + a.cz;
+  };
+  auto set_replica = [&](Row16Lane &X, uint32_t rep) {
+    X.r = rep;
+    X.tab = tab0 + ((rep != r_lo) ? (uint32_t)(NTAB * 4) : 0u);
+    X.base = a.occ + (size_t)rep * a.g.rep_stride;
+    X.dEpot = a.dEpot + (size_t)rep * NTAB16;
+    X.thr_lo = a.thr_lo + (size_t)rep * NTAB16;
+  };
+  uint32_t rep = r_lo, rep_n = r_lo;
+  int32_t j = 0, k = 0, jn = 0, kn = 0;
+  bool on = false, on_n = false;
+  uint32_t tile = tb + wib;
+  if (tile < te) {
+    locate(tile, rep, j, k, on);
+    set_replica(L, rep);
+    row16_issue<MASK_CT>(a, L, j, k, slots);
+  }
+  for (; tile < te; tile += 8u) {
+    const bool more = tile + 8u < te;
+    Row16Lane Ln = L;
+    if (more) {
+      locate(tile + 8u, rep_n, jn, kn, on_n);
+      set_replica(Ln, rep_n);
+    }
+    cp_async_wait_all();
+    auto stage_next = [&]() {
+      if (more) row16_issue<MASK_CT>(a, Ln, jn, kn, slots);
+    };
+    uint32_t n_acc = 0;
+    double e_tot = 0.0;
+    row16_tile<NOCC, MASK_CT, ACCUM, true, 1>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot, slots, stage_next);
+    if (rep == r_lo) {
+      n_acc0 += n_acc;
+      e_tot0 += e_tot;
+    } else {
+      n_acc1 += n_acc;
+      e_tot1 += e_tot;
+    }
+    L = Ln;
+    rep = rep_n;
+    j = jn;
+    k = kn;
+    on = on_n;
+  }
+  row16_reduce(a, r_lo, n_acc0, e_tot0, sh_acc, sh_sum);
+  if (r_hi != r_lo) {
+    __syncthreads();
+    row16_reduce(a, r_hi, n_acc1, e_tot1, sh_acc, sh_sum);
+  }
+}
+
 // ---- whole sweeps in ONE launch ---------------------------------------------------
 // Persistent co-resident grid (cooperative launch); n_sweeps sweeps of a periodic
 // (halo-free) lattice.  Tiles are enumerated in the k-sliced colour order
