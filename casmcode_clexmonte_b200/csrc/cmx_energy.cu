@@ -520,7 +520,10 @@ static int launch_energy_lin(const cmx_state *s, EnergyArgs &a, int nb, int n_re
 
 int cmx_energy_fast_blocks(const cmx_state *s) {
   const uint32_t n_items = (uint32_t)(s->g.N0 / 16) * (uint32_t)s->g.N1 * (uint32_t)s->g.N2;
-  const int cap = std::max(148, 148 * 8 / std::max(1, s->n_replicas));
+  // one co-resident wave over all replicas (4 blocks of 256 threads per SM): every warp
+  // works through tens of tiles, the per-block reduction is amortised
+  static const int per_sm = getenv("CMX_ENERGY_BLOCKS_PER_SM") ? atoi(getenv("CMX_ENERGY_BLOCKS_PER_SM")) : 4;
+  const int cap = std::max(1, 148 * per_sm / std::max(1, s->n_replicas));
   return (int)std::min<uint32_t>((n_items + 255) / 256, (uint32_t)cap);
 }
 
