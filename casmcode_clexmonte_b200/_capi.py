@@ -21,6 +21,7 @@ LIB_PATH = HERE / "libcmx_b200.so"
 CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
 CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC, CMX_SWEEP_BLOCK_KERNEL, CMX_SWEEP_FUSED = 1, 2, 4, 8
 CMX_SWEEP_THREAD_GENERIC = 16
+CMX_SWEEP_COOP = 32
 
 # every symbol include/cmx_b200.h declares
 EXPORTED_SYMBOLS = [
@@ -34,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
-    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_fused_info",
+    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sgc_sweep_slab", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_fused_info",
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
     "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
@@ -144,6 +145,7 @@ def lib():
     L.cmx_composition.argtypes = [vp, i32, vp]
     L.cmx_sgc_sweep.argtypes = [vp, i64, u64, i64, vp]
     L.cmx_sgc_sweep_kgroup.argtypes = [vp, u64, i64, i32]
+    L.cmx_sgc_sweep_slab.argtypes = [vp, i64, u64, i64]
     L.cmx_counters_reset.argtypes = [vp]
     L.cmx_state_set_sweep_flags.argtypes = [vp, C.c_uint32]
     L.cmx_counters_read.argtypes = [vp, vp]
@@ -392,6 +394,10 @@ class State:
         check(lib().cmx_sgc_sweep(self._h, int(n_sweeps), int(seed), int(first_sweep),
                                   C.byref(cnt) if counters else None))
         return cnt
+
+    def sgc_sweep_slab(self, n_sweeps: int, seed: int, first_sweep: int = 0) -> None:
+        """Peer-attached slab: whole sweeps in one cooperative launch (asynchronous)."""
+        check(lib().cmx_sgc_sweep_slab(self._h, int(n_sweeps), int(seed), int(first_sweep)))
 
     def sgc_sweep_kgroup(self, seed: int, sweep: int, kgroup: int) -> None:
         """Asynchronous: enqueue one k-colour group of one sweep on the state's stream."""

@@ -1127,6 +1127,37 @@ static int launch_row16_flat(const Pair16Args &a, uint32_t gx, uint32_t n_replic
                : launch_row16_flat_inst<NOCC, 0u, false>(a, n_replicas, cfg);
 }
 
+// whole sweeps in one cooperative launch (k_sweep_row16_coop); *capacity: co-resident blocks
+template <int NOCC, uint32_t MASK, bool ACC>
+static int launch_row16_coop_inst(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, int *capacity) {
+  auto kern = k_sweep_row16_coop<NOCC, MASK, ACC>;
+  static int cap = -1;
+  const size_t bytes = row16_smem_bytes<NOCC>(MASK);
+  if (cap < 0) {
+    CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int per_sm = 0, dev = 0, sms = 0, can = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, bytes) != cudaSuccess) per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
+    cap = can ? per_sm * sms : 0;
+  }
+  *capacity = cap;
+  if ((long long)grid.x * grid.y > cap) return -1;
+  void *args[2] = {&a, &c};
+  CMX_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(256), args, bytes, st));
+  return CMX_OK;
+}
+template <int NOCC>
+static int launch_row16_coop(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, bool fcc, bool accum,
+                             int *capacity) {
+  if (fcc)
+    return accum ? launch_row16_coop_inst<NOCC, kMaskFcc1NN, true>(a, c, grid, st, capacity)
+                 : launch_row16_coop_inst<NOCC, kMaskFcc1NN, false>(a, c, grid, st, capacity);
+  return accum ? launch_row16_coop_inst<NOCC, 0u, true>(a, c, grid, st, capacity)
+               : launch_row16_coop_inst<NOCC, 0u, false>(a, c, grid, st, capacity);
+}
+
 // tuning knobs (environment, read once)
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
@@ -1317,6 +1348,42 @@ static int sweep_fused(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t
     void *args[2] = {&a, &f};
     CMX_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gx, s->n_replicas), dim3(256), args, 0, s->stream));
     P.stamp_base += (uint32_t)n;
+    done += n;
+  }
+  P.pdl_ok = false;
+  return CMX_OK;
+}
+
+// n_sweeps whole sweeps in one cooperative launch; -1 if not applicable (not the warp-row
+// kernel, or the grid is not co-resident)
+static int sweep_coop(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps) {
+  SweepPlan &P = s->plan;
+  if (!use_row16(s) || n_sweeps <= 0) return -1;
+  Pair16Args a;
+  int rc = pair_args(s, seed, first_sweep, s->k_offset, a);
+  if (rc) return rc;
+  const uint32_t n_kk = (uint32_t)(s->g.N2 / 2);
+  a.row_begin = 0;
+  a.n_rows = n_kk * a.J;
+  const uint32_t rpw = 32u / a.W;
+  a.n_tiles = (a.n_rows + rpw - 1) / rpw;
+  dim3 grid(std::min<uint32_t>((uint32_t)P.part_blocks, (a.n_tiles + 7) / 8), s->n_replicas);
+  const bool fcc = (P.mask == kMaskFcc1NN);
+  const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
+  for (int64_t done = 0; done < n_sweeps;) {
+    const int64_t n = std::min<int64_t>(n_sweeps - done, 1 << 20);
+    CoopArgs c;
+    c.n_sweeps = (uint32_t)n;
+    c.first_sweep = (unsigned long long)(first_sweep + done);
+    c.epoch0 = s->epoch;
+    int cap = 0;
+    rc = (P.nocc == 3) ? launch_row16_coop<3>(a, c, grid, s->stream, fcc, accum, &cap)
+                       : launch_row16_coop<2>(a, c, grid, s->stream, fcc, accum, &cap);
+    if (rc) return rc;  // -1: grid not co-resident
+    if (a.push) {
+      s->epoch += 2ull * (unsigned long long)n;
+      s->published = s->epoch;
+    }
     done += n;
   }
   P.pdl_ok = false;
@@ -1517,7 +1584,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
   if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_BLOCK_KERNEL |
-                         CMX_SWEEP_FUSED | CMX_SWEEP_THREAD_GENERIC))
+                         CMX_SWEEP_FUSED | CMX_SWEEP_THREAD_GENERIC | CMX_SWEEP_COOP))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;  // the grid may change with the evaluator
@@ -1591,6 +1658,10 @@ extern "C" int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
     rc = sweep_fused(s, seed, first_sweep, n_sweeps);
     if (rc > 0) return rc;
     fused = (rc == CMX_OK);
+  } else if ((s->sweep_flags & CMX_SWEEP_COOP) && n_sweeps > 0) {
+    rc = sweep_coop(s, seed, first_sweep, n_sweeps);
+    if (rc > 0) return rc;
+    fused = (rc == CMX_OK);
   }
   for (int64_t w = 0; w < n_sweeps && !fused; ++w) {
     rc = sweep_once(s, seed, first_sweep + w, -1, 0);
@@ -1613,6 +1684,29 @@ extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
   if (kgroup >= 0) per /= s->plan.S[2];
   s->plan.attempts += per;
   return CMX_OK;  // asynchronous: enqueued on the state's stream
+}
+
+// Slab states over peer memory: n_sweeps whole sweeps in one cooperative launch (the
+// ring protocol runs inside the kernel).  Asynchronous.  CMX_ERR_UNSUPPORTED when the
+// state is not a peer-attached slab on the warp-row kernel: drive it with
+// cmx_sgc_sweep_kgroup then.
+extern "C" int cmx_sgc_sweep_slab(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep) {
+  int rc = sweep_prepare(s, "cmx_sgc_sweep_slab");
+  if (rc) return rc;
+  if (n_sweeps < 0) return invalid("cmx_sgc_sweep_slab: n_sweeps < 0");
+  if (!s->g.halo || !s->p2p || !use_row16(s)) {
+    cmx_set_error("cmx_sgc_sweep_slab: not a peer-attached slab state on the warp-row kernel");
+    return CMX_ERR_UNSUPPORTED;
+  }
+  if (n_sweeps == 0) return CMX_OK;
+  rc = sweep_coop(s, seed, first_sweep, n_sweeps);
+  if (rc < 0) {
+    cmx_set_error("cmx_sgc_sweep_slab: the grid is not co-resident on this device");
+    return CMX_ERR_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  s->plan.attempts += (long long)s->g.n_cells * (long long)s->plan.mut_points.size() * n_sweeps;
+  return CMX_OK;
 }
 
 extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,

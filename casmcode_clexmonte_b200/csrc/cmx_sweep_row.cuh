@@ -30,6 +30,7 @@
 // serialisation: the table load and the address set-up of launch n+1 overlap the
 // tail of launch n; griddepcontrol.wait orders the lattice accesses.
 #pragma once
+#include <cooperative_groups.h>
 
 #define CMX_TAB24(NOCC) ((NOCC) == 3 ? 23 * 256 : 512)
 
@@ -440,43 +441,12 @@ __device__ __forceinline__ void row16_load_table(uint32_t *sh_tab, const uint32_
   }
 }
 
-// ---- one colour pass (cy,cz) over the colour layers [row_begin/J, ...) --------------
-// Software pipelined: while a tile is updated, the rows of the warp's NEXT tile are
-// already on their way into the warp's shared-memory slots (cp.async, 16 B per lane
-// and row) -- the global latency is hidden behind ~350 instructions of compute and
-// costs no registers.  A lane only ever reads the slots it filled itself: no
-// barrier, not even a warp one.
+// One colour pass (a.cy, a.cz) of this block's share of the rows: the tile loop of
+// k_sweep_row16 (and of every pass of k_sweep_row16_coop).
 template <int NOCC, uint32_t MASK_CT, bool ACCUM>
-__global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
-  constexpr int NTAB = CMX_TAB24(NOCC);
-  constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
-  // dynamic shared memory: [acceptance table][8 warps x NSLOT row slots x (32 lanes x 16 B)]
-  extern __shared__ __align__(16) unsigned char sh_dyn[];
-  uint32_t *sh_tab = reinterpret_cast<uint32_t *>(sh_dyn);
-  unsigned char *sh_rows = sh_dyn + NTAB * 4;
-  __shared__ long long sh_acc[8];
-  __shared__ double sh_sum[8];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  row16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)blockIdx.y * NTAB);
-  const Row16Lane L = row16_lane<NOCC, MASK_CT>(a, sh_tab);
-  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  const uint32_t rl = lane >> a.logW;
-  const uint32_t rpw_log = 5u - a.logW;  // log2(rows per warp)
-  const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_ROW16_SLOT) + 16u * lane;
-  uint32_t n_acc = 0;
-  double e_tot = 0.0;
-  // the lattice may only be touched once the previous launch has completed
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // Slab ring protocol (see sweep_once).  The previous launches of this rank are complete,
-  // their stores into the neighbours' ghost layers included: publish the epoch they
-  // reached.  Publishing here instead of at the end of the previous launch keeps
-  // system-scope fences and remote round trips out of every launch's tail.
-  if (a.signal_epoch && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-    __threadfence_system();
-    st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
-    st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
-  }
-  __syncthreads();
+__device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane &L, uint32_t slots, uint32_t lane,
+                                           uint32_t wib, uint32_t rl, uint32_t rpw_log, uint32_t &n_acc,
+                                           double &e_tot) {
   const uint32_t warp0 = blockIdx.x * 8u + wib, n_warps = gridDim.x * 8u;
   // rows advance by a fixed stride per iteration: decode (kk, jj) once, then step
   uint32_t row = (warp0 << rpw_log) + rl;  // relative to row_begin
@@ -544,6 +514,109 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
     j = jn;
     k = kn;
     on = on_n;
+  }
+}
+
+// ---- one colour pass (cy,cz) over the colour layers [row_begin/J, ...) --------------
+// Software pipelined: while a tile is updated, the rows of the warp's NEXT tile are
+// already on their way into the warp's shared-memory slots (cp.async, 16 B per lane
+// and row) -- the global latency is hidden behind ~350 instructions of compute and
+// costs no registers.  A lane only ever reads the slots it filled itself: no
+// barrier, not even a warp one.
+template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+__global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
+  constexpr int NTAB = CMX_TAB24(NOCC);
+  constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
+  // dynamic shared memory: [acceptance table][8 warps x NSLOT row slots x (32 lanes x 16 B)]
+  extern __shared__ __align__(16) unsigned char sh_dyn[];
+  uint32_t *sh_tab = reinterpret_cast<uint32_t *>(sh_dyn);
+  unsigned char *sh_rows = sh_dyn + NTAB * 4;
+  __shared__ long long sh_acc[8];
+  __shared__ double sh_sum[8];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  row16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)blockIdx.y * NTAB);
+  const Row16Lane L = row16_lane<NOCC, MASK_CT>(a, sh_tab);
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t rl = lane >> a.logW;
+  const uint32_t rpw_log = 5u - a.logW;  // log2(rows per warp)
+  const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_ROW16_SLOT) + 16u * lane;
+  uint32_t n_acc = 0;
+  double e_tot = 0.0;
+  // the lattice may only be touched once the previous launch has completed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Slab ring protocol (see sweep_once).  The previous launches of this rank are complete,
+  // their stores into the neighbours' ghost layers included: publish the epoch they
+  // reached.  Publishing here instead of at the end of the previous launch keeps
+  // system-scope fences and remote round trips out of every launch's tail.
+  if (a.signal_epoch && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
+    st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
+  }
+  __syncthreads();
+  row16_pass<NOCC, MASK_CT, ACCUM>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
+  row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum);
+}
+
+// ---- whole sweeps in one cooperative launch, grid barriers between colour passes ------
+// For launches too short to amortise their fixed cost (slabs of a domain-decomposed
+// supercell: a 64-layer slab is 5 us of work per colour pass against ~5 us of launch,
+// ramp and tail): n_sweeps x 4 passes in ONE launch, cooperative-groups grid barrier
+// between passes.  The slab ring protocol lives inside: a k-colour group waits for the
+// neighbours' epoch in its boundary tiles only (visited last), and the epoch a rank has
+// completed is published by block 0 right after the barrier that ends the group.
+struct CoopArgs {
+  uint32_t n_sweeps;
+  unsigned long long first_sweep;
+  unsigned long long epoch0;  // k-colour groups this rank completed before the launch
+};
+template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+__global__ void __launch_bounds__(256, 3) k_sweep_row16_coop(Pair16Args a, CoopArgs c) {
+  constexpr int NTAB = CMX_TAB24(NOCC);
+  constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
+  extern __shared__ __align__(16) unsigned char sh_dyn[];
+  uint32_t *sh_tab = reinterpret_cast<uint32_t *>(sh_dyn);
+  unsigned char *sh_rows = sh_dyn + NTAB * 4;
+  __shared__ long long sh_acc[8];
+  __shared__ double sh_sum[8];
+  namespace cgr = cooperative_groups;
+  cgr::grid_group grid = cgr::this_grid();
+  row16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)blockIdx.y * NTAB);
+  const Row16Lane L = row16_lane<NOCC, MASK_CT>(a, sh_tab);
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t rl = lane >> a.logW;
+  const uint32_t rpw_log = 5u - a.logW;
+  const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_ROW16_SLOT) + 16u * lane;
+  uint32_t n_acc = 0;
+  double e_tot = 0.0;
+  __syncthreads();
+  unsigned long long epoch = c.epoch0;
+  const bool publisher = a.push && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  if (publisher && epoch) {  // what the previous launches completed (idempotent)
+    __threadfence_system();
+    st_sys(a.peer_sig_dn + 1, epoch);
+    st_sys(a.peer_sig_up + 0, epoch);
+  }
+  for (uint32_t s = 0; s < c.n_sweeps; ++s) {
+    const unsigned long long sweep = c.first_sweep + s;
+    a.sweep_lo = (uint32_t)sweep;
+    for (int cz = 0; cz < 2; ++cz) {
+      for (int cy = 0; cy < 2; ++cy) {
+        a.cy = cy;
+        a.cz = cz;
+        a.ctr_hi = ((uint32_t)(sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
+        a.wait_epoch = a.push ? epoch : 0ull;
+        a.signal_epoch = 0;
+        row16_pass<NOCC, MASK_CT, ACCUM>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
+        grid.sync();  // every store of the pass, the ones into the neighbours' ghost layers included
+      }
+      ++epoch;
+      if (publisher) {
+        __threadfence_system();
+        st_sys(a.peer_sig_dn + 1, epoch);
+        st_sys(a.peer_sig_up + 0, epoch);
+      }
+    }
   }
   row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum);
 }

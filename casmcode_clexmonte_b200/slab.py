@@ -17,6 +17,7 @@ torch is used for what it is here for: NCCL plumbing and stream handles.
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Optional
 
@@ -107,6 +108,8 @@ class SlabRunner:
         # neighbours' slabs (CUDA IPC over NVLink) and the kernel stores the
         # boundary rows it changes straight into their ghost layers
         self.p2p = False
+        # None: try the cooperative whole-sweep kernel; CMX_SLAB_NO_COOP=1 keeps one launch per colour pass
+        self._coop = False if os.environ.get("CMX_SLAB_NO_COOP") else None
         if p2p:
             self._attach_peers()
 
@@ -192,6 +195,16 @@ class SlabRunner:
     # -- driver -----------------------------------------------------------------
     def sweep(self, n_sweeps: int, seed: int, first_sweep: int = 0) -> None:
         """Asynchronous: everything is enqueued on the state's stream."""
+        if self.p2p and self._coop is not False and n_sweeps > 0:
+            # whole sweeps in one cooperative launch, the ring protocol inside the kernel
+            try:
+                self.state.sgc_sweep_slab(n_sweeps, seed, first_sweep)
+                self._coop = True
+                return
+            except _capi.CmxError as e:
+                if e.code != _capi.CMX_ERR_UNSUPPORTED or self._coop:
+                    raise
+                self._coop = False       # e.g. the block kernel: one launch per colour pass
         for w in range(n_sweeps):
             for g in range(self.Sk):
                 self.state.sgc_sweep_kgroup(seed, first_sweep + w, g)

@@ -246,7 +246,16 @@ int cmx_counters_reset(cmx_state *s);
  * to the lanes); THREAD_GENERIC forces one site per thread (same random bits and
  * decisions; dE differs in the last bits through the summation order). */
 #define CMX_SWEEP_THREAD_GENERIC 16u
+/* COOP: cmx_sgc_sweep runs all its sweeps in ONE cooperative launch of the warp-row kernel
+ * with a grid barrier between colour passes (k_sweep_row16_coop) instead of one launch
+ * per pass; pays when a pass is too short to amortise a launch (small boxes, slabs). */
+#define CMX_SWEEP_COOP 32u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
+/* Slab states attached over peer memory (cmx_state_ipc_attach): n_sweeps whole sweeps in
+ * one cooperative launch, the ring protocol of the halo exchange inside the kernel.
+ * Asynchronous (enqueued on the state's stream).  CMX_ERR_UNSUPPORTED when the state is
+ * not such a slab: use cmx_sgc_sweep_kgroup (+ the host-side halo exchange) then. */
+int cmx_sgc_sweep_slab(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep);
 /* synchronises the state's stream; counters[n_replicas] */
 int cmx_counters_read(cmx_state *s, cmx_counters *counters);
 /* Name of the evaluator the sweep uses for the bound ECI ("pair_lut",

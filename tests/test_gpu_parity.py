@@ -230,7 +230,7 @@ def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
     b.close()
 
 
-@pytest.mark.parametrize("staging", ["default", "block", "fused"])
+@pytest.mark.parametrize("staging", ["default", "block", "fused", "coop"])
 @pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1),
                                           ((128, 32, 4), 2)])
 def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas, staging):
@@ -247,7 +247,8 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.4], 3)
         a.set_conditions(500.0, ex2, replica=1)
         b.set_conditions(500.0, ex2, replica=1)
-    variant = {"default": 0, "block": _capi.CMX_SWEEP_BLOCK_KERNEL, "fused": _capi.CMX_SWEEP_FUSED}[staging]
+    variant = {"default": 0, "block": _capi.CMX_SWEEP_BLOCK_KERNEL, "fused": _capi.CMX_SWEEP_FUSED,
+               "coop": _capi.CMX_SWEEP_COOP}[staging]
     a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM | variant)
     b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC | _capi.CMX_SWEEP_DE_SUM)
     assert a.sweep_info()["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
@@ -280,7 +281,8 @@ def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sw
     same acceptance counts.  Only at these sizes are all SMs busy and the row stamps,
     the overlapped launches and the L2 slices of the fused schedule really exercised."""
     mu = [0.0, 0.0]
-    variants = {"row": 0, "fused": _capi.CMX_SWEEP_FUSED, "block": _capi.CMX_SWEEP_BLOCK_KERNEL,
+    variants = {"row": 0, "coop": _capi.CMX_SWEEP_COOP, "fused": _capi.CMX_SWEEP_FUSED,
+                "block": _capi.CMX_SWEEP_BLOCK_KERNEL,
                 "generic": _capi.CMX_SWEEP_FORCE_GENERIC}
     ref_occ, ref_cnt = None, None
     for name, flags in variants.items():
