@@ -232,14 +232,16 @@ def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
 
 @pytest.mark.parametrize("staging", ["default", "block", "fused", "coop"])
 @pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1),
-                                          ((128, 32, 4), 2)])
+                                          ((128, 32, 4), 2), ((128, 24, 20), 3)])
 def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas, staging):
     """The 16-sites-per-thread LUT kernel and the one-site-per-thread generic
     evaluator (whose delta E is checked against the reference kernels) draw the
     same random bits and must make the same decisions: identical occupation
     after several sweeps, identical acceptance counts.  Covers one chunk per row
     (N0=16), rows that do not fill a block (N0=48), a row spanning a whole warp
-    (N0=512), replicas with different conditions and the int8 transfer path."""
+    (N0=512), replicas with different conditions, a replica grid whose flat tile space is
+    cut across replica boundaries ((128, 24, 20) x 3: 30 tiles per replica, 7.5 per block)
+    and the int8 transfer path."""
     mu = [0.2, -0.1]
     a, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5)
     b, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5)
