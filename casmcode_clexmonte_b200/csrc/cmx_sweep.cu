@@ -1390,6 +1390,17 @@ static int sweep_coop(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t 
   return CMX_OK;
 }
 
+// small boxes: a colour pass is a few microseconds of work, less than the per-launch
+// constant; several sweeps in one cooperative launch then win (measured cross-over: a warp
+// has fewer than ~4 tiles per pass)
+static bool coop_pays(const cmx_state *s, int64_t n_sweeps) {
+  static int off = env_int("CMX_SWEEP_NO_AUTO_COOP", 0);
+  if (off || n_sweeps < 2 || !use_row16(s) || s->g.halo || row16_flat_blocks(s)) return false;
+  const uint32_t tiles = row16_tiles_per_replica(s);
+  const uint32_t warps = std::min<uint32_t>((uint32_t)s->plan.part_blocks, (tiles + 7) / 8) * 8u;
+  return tiles < 4u * warps;
+}
+
 // one pass over the colours whose k-colour equals kgroup (or all if < 0)
 static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
                       int k_offset) {
@@ -1658,7 +1669,7 @@ extern "C" int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
     rc = sweep_fused(s, seed, first_sweep, n_sweeps);
     if (rc > 0) return rc;
     fused = (rc == CMX_OK);
-  } else if ((s->sweep_flags & CMX_SWEEP_COOP) && n_sweeps > 0) {
+  } else if (n_sweeps > 0 && ((s->sweep_flags & CMX_SWEEP_COOP) || coop_pays(s, n_sweeps))) {
     rc = sweep_coop(s, seed, first_sweep, n_sweeps);
     if (rc > 0) return rc;
     fused = (rc == CMX_OK);
