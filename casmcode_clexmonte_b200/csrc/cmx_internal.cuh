@@ -201,6 +201,7 @@ struct cmx_state {
 
 int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
+int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps);
 int cmx_slab_publish(cmx_state *s);  // announce a completed, unannounced ring step
 bool cmx_use_warp_generic(const cmx_state *s);  // wide orbit sets: one site per warp
 void cmx_canonical_free(cmx_state *s);

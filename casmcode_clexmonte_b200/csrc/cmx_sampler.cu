@@ -332,8 +332,7 @@ extern "C" int cmx_sweep_run(cmx_state *s, cmx_sampler *m, int32_t ensemble, int
   int64_t sweep = first_sweep;
   for (int64_t k = 0; k < n_samples; ++k) {
     if (ensemble == 0) {
-      for (int64_t w = 0; w < sweeps_per_sample; ++w)
-        if ((rc = cmx_sgc_sweep_kgroup(s, seed, sweep + w, -1))) return rc;
+      if ((rc = cmx_sgc_sweep_enqueue(s, seed, sweep, sweeps_per_sample))) return rc;
     } else {
       if ((rc = cmx_canonical_enqueue(s, sweeps_per_sample, seed, sweep, k == 0))) return rc;
     }

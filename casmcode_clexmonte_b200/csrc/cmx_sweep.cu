@@ -1395,7 +1395,7 @@ static int sweep_coop(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t 
 // has fewer than ~4 tiles per pass)
 static bool coop_pays(const cmx_state *s, int64_t n_sweeps) {
   static int off = env_int("CMX_SWEEP_NO_AUTO_COOP", 0);
-  if (off || n_sweeps < 2 || !use_row16(s) || s->g.halo || row16_flat_blocks(s)) return false;
+  if (off || n_sweeps < 1 || !use_row16(s) || s->g.halo || row16_flat_blocks(s)) return false;
   const uint32_t tiles = row16_tiles_per_replica(s);
   const uint32_t warps = std::min<uint32_t>((uint32_t)s->plan.part_blocks, (tiles + 7) / 8) * 8u;
   return tiles < 4u * warps;
@@ -1664,23 +1664,34 @@ extern "C" int cmx_sgc_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
   if (rc) return rc;
   if (n_sweeps < 0) return invalid("cmx_sgc_sweep: n_sweeps < 0");
   if (s->g.halo) return invalid("cmx_sgc_sweep: slab states are driven by cmx_sgc_sweep_kgroup");
-  bool fused = false;
+  rc = cmx_sgc_sweep_enqueue(s, seed, first_sweep, n_sweeps);
+  if (rc) return rc;
+  if (counters) return cmx_counters_read(s, counters);
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  return CMX_OK;
+}
+
+// n_sweeps whole sweeps enqueued on the state's stream (no reset, no synchronisation):
+// the loop body of cmx_sgc_sweep, shared with cmx_sweep_run
+int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps) {
+  int rc = sweep_prepare(s, "cmx_sgc_sweep");
+  if (rc) return rc;
+  if (s->g.halo) return invalid("cmx_sgc_sweep: slab states are driven by cmx_sgc_sweep_kgroup / cmx_sgc_sweep_slab");
+  bool done = false;
   if (use_fused(s) && n_sweeps > 0) {
     rc = sweep_fused(s, seed, first_sweep, n_sweeps);
     if (rc > 0) return rc;
-    fused = (rc == CMX_OK);
+    done = (rc == CMX_OK);
   } else if (n_sweeps > 0 && ((s->sweep_flags & CMX_SWEEP_COOP) || coop_pays(s, n_sweeps))) {
     rc = sweep_coop(s, seed, first_sweep, n_sweeps);
     if (rc > 0) return rc;
-    fused = (rc == CMX_OK);
+    done = (rc == CMX_OK);
   }
-  for (int64_t w = 0; w < n_sweeps && !fused; ++w) {
+  for (int64_t w = 0; w < n_sweeps && !done; ++w) {
     rc = sweep_once(s, seed, first_sweep + w, -1, 0);
     if (rc) return rc;
   }
   s->plan.attempts += (long long)s->g.n_cells * (long long)s->plan.mut_points.size() * n_sweeps;
-  if (counters) return cmx_counters_read(s, counters);
-  CMX_CUDA(cudaStreamSynchronize(s->stream));
   return CMX_OK;
 }
 
