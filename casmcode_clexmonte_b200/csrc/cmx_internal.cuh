@@ -117,6 +117,7 @@ struct SweepPlan {
   // factors point at a slot that holds 1.0); 0 when a term has more than 4 factors
   uint2 *d_gt_pk = nullptr;
   int32_t pk_terms_max = 0, pk_act_max = 0;  // max over p of terms / active neighbors
+  int generic_coop_capacity = -1;            // co-resident blocks of the cooperative generic kernel
   // pair LUT: one sublattice, <= 3 occupants, offsets in {-1,0,1}^3,
   // one class of symmetry-equivalent neighbors
   int32_t nocc = 0;
