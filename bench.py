@@ -268,6 +268,7 @@ def main():
         value = K * S * n_sites / (ms * 1e-3)
         launches = res["launches"]
         kernel_ms = res["kernel_ms"]
+        slab_coop, slab_sweeps_per_launch = res["coop"], res["sweeps_per_launch"]
         if rank != 0:
             return
 
@@ -280,6 +281,10 @@ def main():
     if world == 1 and info["fused"]:
         sites_per_launch = float(n_sites) * K * S
         kernel_name = "k_sweep_row16_fused"
+    elif world > 1:
+        # cooperative slab sweeps: one launch = all the sweeps of the timed call on this rank's slab
+        sites_per_launch = n_sites / world * slab_sweeps_per_launch
+        kernel_name = "k_sweep_row16_coop" if slab_coop else "k_sweep_row16"
     else:
         sites_per_launch = n_sites / world / info["launches_per_sweep"]
         kernel_name = "k_sweep_row16"

@@ -271,9 +271,11 @@ class SlabRunner:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         n_sites = self.N[0] * self.N[1] * self.N[2] * self.n_sublat
         n_col = self._info["launches_per_sweep"]
-        launches = K * S * n_col
+        coop = self._coop is True          # the timed call was ONE cooperative launch (K * S sweeps)
+        launches = 1 if coop else K * S * n_col
         return dict(ms=float(ms.item()), clocks=clk, accept_rate=float(cnt[1] / max(cnt[0], 1.0)),
-                    launches=launches, kernel_ms=float(ms.item()) / (K * S * n_col),
+                    launches=launches, kernel_ms=float(ms.item()) / launches, coop=coop,
+                    sweeps_per_launch=(K * S if coop else 1.0 / n_col),
                     e2e={"value": K * S * n_sites / float(te.item()), "unit": "steps/s",
                          "h2d_bytes_per_step": n_sites, "d2h_bytes_per_step": n_sites,
                          "ms_per_step": float(te.item()) * 1e3 / K})
