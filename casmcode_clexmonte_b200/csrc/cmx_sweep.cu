@@ -1092,9 +1092,9 @@ static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool 
   }
 }
 
-template <int NOCC, uint32_t MASK, bool ACC>
-static int launch_row16_inst(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
-  auto kern = k_sweep_row16<NOCC, MASK, ACC>;
+template <int NOCC, uint32_t MASK, bool ACC, bool SLAB>
+static int launch_row16_inst2(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
+  auto kern = k_sweep_row16<NOCC, MASK, ACC, SLAB>;
   static bool attr_set = false;
   const size_t bytes = row16_smem_bytes<NOCC>(MASK);
   if (!attr_set) {
@@ -1104,6 +1104,11 @@ static int launch_row16_inst(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
   cfg.dynamicSmemBytes = bytes;
   CMX_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   return CMX_OK;
+}
+template <int NOCC, uint32_t MASK, bool ACC>
+static int launch_row16_inst(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
+  // slabs (a.push): the variant with the ring protocol compiled in
+  return a.push ? launch_row16_inst2<NOCC, MASK, ACC, true>(a, cfg) : launch_row16_inst2<NOCC, MASK, ACC, false>(a, cfg);
 }
 template <int NOCC>
 static int launch_row16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum, bool pdl) {
@@ -1154,9 +1159,9 @@ static int launch_row16_flat(const Pair16Args &a, uint32_t gx, uint32_t n_replic
 }
 
 // whole sweeps in one cooperative launch (k_sweep_row16_coop); *capacity: co-resident blocks
-template <int NOCC, uint32_t MASK, bool ACC>
-static int launch_row16_coop_inst(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, int *capacity) {
-  auto kern = k_sweep_row16_coop<NOCC, MASK, ACC>;
+template <int NOCC, uint32_t MASK, bool ACC, bool SLAB>
+static int launch_row16_coop_inst2(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, int *capacity) {
+  auto kern = k_sweep_row16_coop<NOCC, MASK, ACC, SLAB>;
   static int cap = -1;
   const size_t bytes = row16_smem_bytes<NOCC>(MASK);
   if (cap < 0) {
@@ -1173,6 +1178,11 @@ static int launch_row16_coop_inst(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStr
   void *args[2] = {&a, &c};
   CMX_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(256), args, bytes, st));
   return CMX_OK;
+}
+template <int NOCC, uint32_t MASK, bool ACC>
+static int launch_row16_coop_inst(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, int *capacity) {
+  return a.push ? launch_row16_coop_inst2<NOCC, MASK, ACC, true>(a, c, grid, st, capacity)
+                : launch_row16_coop_inst2<NOCC, MASK, ACC, false>(a, c, grid, st, capacity);
 }
 template <int NOCC>
 static int launch_row16_coop(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, bool fcc, bool accum,

@@ -443,7 +443,7 @@ __device__ __forceinline__ void row16_load_table(uint32_t *sh_tab, const uint32_
 
 // One colour pass (a.cy, a.cz) of this block's share of the rows: the tile loop of
 // k_sweep_row16 (and of every pass of k_sweep_row16_coop).
-template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB>
 __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane &L, uint32_t slots, uint32_t lane,
                                            uint32_t wib, uint32_t rl, uint32_t rpw_log, uint32_t &n_acc,
                                            double &e_tot) {
@@ -460,8 +460,11 @@ __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane 
   // neighbours' epoch: the interior of the slab is updated while the neighbours finish
   // their previous step and their flag travels.
   const int32_t kk_end = (int32_t)((a.row_begin + a.n_rows) / a.J), n_layers = (int32_t)(a.n_rows / a.J);
-  const int32_t rot = (a.push && a.cz == 0) ? 1 : 0;
+  // (SLAB is a compile-time switch: the vote and the rotated order cost the plain
+  // single-GPU kernel 4.6 % when they are merely predicated off)
+  const int32_t rot = (SLAB && a.push && a.cz == 0) ? 1 : 0;
   auto wait_neighbours = [&](int32_t k) {
+    if (!SLAB) return;
     const bool need = a.wait_epoch && (k == 0 || k == a.g.N2 - 1);
     if (!__any_sync(0xffffffffu, need)) return;
     if (lane == 0) {
@@ -523,7 +526,7 @@ __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane 
 // and row) -- the global latency is hidden behind ~350 instructions of compute and
 // costs no registers.  A lane only ever reads the slots it filled itself: no
 // barrier, not even a warp one.
-template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB>
 __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   constexpr int NTAB = CMX_TAB24(NOCC);
   constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
@@ -548,13 +551,13 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   // their stores into the neighbours' ghost layers included: publish the epoch they
   // reached.  Publishing here instead of at the end of the previous launch keeps
   // system-scope fences and remote round trips out of every launch's tail.
-  if (a.signal_epoch && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+  if (SLAB && a.signal_epoch && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     __threadfence_system();
     st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
     st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
   }
   __syncthreads();
-  row16_pass<NOCC, MASK_CT, ACCUM>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
+  row16_pass<NOCC, MASK_CT, ACCUM, SLAB>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
   row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum);
 }
 
@@ -570,7 +573,7 @@ struct CoopArgs {
   unsigned long long first_sweep;
   unsigned long long epoch0;  // k-colour groups this rank completed before the launch
 };
-template <int NOCC, uint32_t MASK_CT, bool ACCUM>
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB>
 __global__ void __launch_bounds__(256, 3) k_sweep_row16_coop(Pair16Args a, CoopArgs c) {
   constexpr int NTAB = CMX_TAB24(NOCC);
   constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16_coop(Pair16Args a, CoopA
   double e_tot = 0.0;
   __syncthreads();
   unsigned long long epoch = c.epoch0;
-  const bool publisher = a.push && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const bool publisher = SLAB && a.push && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
   if (publisher && epoch) {  // what the previous launches completed (idempotent)
     __threadfence_system();
     st_sys(a.peer_sig_dn + 1, epoch);
@@ -605,9 +608,9 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16_coop(Pair16Args a, CoopA
         a.cy = cy;
         a.cz = cz;
         a.ctr_hi = ((uint32_t)(sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
-        a.wait_epoch = a.push ? epoch : 0ull;
+        a.wait_epoch = (SLAB && a.push) ? epoch : 0ull;
         a.signal_epoch = 0;
-        row16_pass<NOCC, MASK_CT, ACCUM>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
+        row16_pass<NOCC, MASK_CT, ACCUM, SLAB>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
         grid.sync();  // every store of the pass, the ones into the neighbours' ghost layers included
       }
       ++epoch;
