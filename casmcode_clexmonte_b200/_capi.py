@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_create", "cmx_state_destroy",
     "cmx_state_upload_occ", "cmx_state_download_occ",
     "cmx_state_upload_occ_i8", "cmx_state_download_occ_i8",
+    "cmx_state_upload_occ_i8_async", "cmx_state_download_occ_i8_async", "cmx_state_synchronize", "cmx_sgc_sweep_async",
     "cmx_state_randomize", "cmx_state_set_k_offset", "cmx_state_stream", "cmx_state_device_ptr",
     "cmx_state_ipc_export", "cmx_state_ipc_attach", "cmx_state_p2p_active",
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
@@ -126,6 +127,10 @@ def lib():
     for f in ("cmx_state_upload_occ", "cmx_state_download_occ", "cmx_state_upload_occ_i8",
               "cmx_state_download_occ_i8"):
         getattr(L, f).argtypes = [vp, i32, vp]
+    L.cmx_state_upload_occ_i8_async.argtypes = [vp, i32, vp]
+    L.cmx_state_download_occ_i8_async.argtypes = [vp, i32, vp]
+    L.cmx_state_synchronize.argtypes = [vp]
+    L.cmx_sgc_sweep_async.argtypes = [vp, i64, u64, i64]
     L.cmx_state_randomize.argtypes = [vp, u64]
     L.cmx_state_set_k_offset.argtypes = [vp, i32]
     L.cmx_state_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -279,6 +284,23 @@ class State:
         fn = lib().cmx_state_download_occ_i8 if out.dtype == np.int8 else lib().cmx_state_download_occ
         check(fn(self._h, replica, _p(out)))
         return out
+
+    # ---- asynchronous forms (pipelines of independent states; pinned int8 host buffers)
+    def upload_occ_async(self, occ: np.ndarray, replica: int = 0) -> None:
+        if occ.dtype != np.int8 or not occ.flags.c_contiguous or occ.size != self.n_sites:
+            raise CmxError(CMX_ERR_INVALID, "upload_occ_async: contiguous int8 array of n_sites entries required")
+        check(lib().cmx_state_upload_occ_i8_async(self._h, int(replica), _p(occ)))
+
+    def download_occ_async(self, out: np.ndarray, replica: int = 0) -> None:
+        if out.dtype != np.int8 or not out.flags.c_contiguous or out.size != self.n_sites:
+            raise CmxError(CMX_ERR_INVALID, "download_occ_async: contiguous int8 array of n_sites entries required")
+        check(lib().cmx_state_download_occ_i8_async(self._h, int(replica), _p(out)))
+
+    def sgc_sweep_async(self, n_sweeps: int, seed: int, first_sweep: int = 0) -> None:
+        check(lib().cmx_sgc_sweep_async(self._h, int(n_sweeps), int(seed), int(first_sweep)))
+
+    def synchronize(self) -> None:
+        check(lib().cmx_state_synchronize(self._h))
 
     def randomize(self, seed: int) -> None:
         check(lib().cmx_state_randomize(self._h, int(seed)))

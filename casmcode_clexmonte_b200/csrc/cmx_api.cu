@@ -325,6 +325,67 @@ static int download_occ(const cmx_state *cs, int32_t replica, T *occ) {
   return CMX_OK;
 }
 
+// ---- asynchronous transfers: a pipeline of independent states (one stream each) overlaps
+// the upload of one job, the sweeps of another and the download of a third.  Nothing here
+// synchronises; cmx_state_synchronize waits and reports what went wrong meanwhile.
+extern "C" int cmx_state_upload_occ_i8_async(cmx_state *s, int32_t replica, const int8_t *occ) {
+  int rc = check_replica(s, replica, "cmx_state_upload_occ_i8_async");
+  if (rc) return rc;
+  if (!occ) return invalid("cmx_state_upload_occ_i8_async: null occupation");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
+  int8_t *dst = s->d_occ + (size_t)replica * s->g.rep_stride;
+  if (s->g.halo == 0 && s->g.n_cells % 16 == 0) {
+    CMX_CUDA(cudaMemcpyAsync(dst, occ, n, cudaMemcpyHostToDevice, s->stream));
+    k_validate_occ16<<<1184, 256, 0, s->stream>>>((int4 *)dst, (int64_t)(n / 16), s->g.n_cells / 16,
+                                                  s->t->d.n_occ, s->g.coded, s->d_flag);
+  } else {
+    rc = cmx_scratch(s, n);
+    if (rc) return rc;
+    CMX_CUDA(cudaMemcpyAsync(s->d_scratch, occ, n, cudaMemcpyHostToDevice, s->stream));
+    k_scatter_occ<int8_t><<<1184, 256, 0, s->stream>>>((const int8_t *)s->d_scratch, dst, s->g, s->t->d.n_sublat,
+                                                       s->t->d.n_occ, s->d_flag);
+  }
+  CMX_CUDA(cudaGetLastError());
+  s->async_upload_pending = true;
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_download_occ_i8_async(cmx_state *s, int32_t replica, int8_t *occ) {
+  int rc = check_replica(s, replica, "cmx_state_download_occ_i8_async");
+  if (rc) return rc;
+  if (!occ) return invalid("cmx_state_download_occ_i8_async: null occupation");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
+  const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
+  if (s->g.halo == 0 && !s->g.coded) {
+    CMX_CUDA(cudaMemcpyAsync(occ, src, n, cudaMemcpyDeviceToHost, s->stream));
+    return CMX_OK;
+  }
+  rc = cmx_scratch(s, n);
+  if (rc) return rc;
+  k_gather_occ<int8_t><<<1184, 256, 0, s->stream>>>(src, (int8_t *)s->d_scratch, s->g, s->t->d.n_sublat);
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaMemcpyAsync(occ, s->d_scratch, n, cudaMemcpyDeviceToHost, s->stream));
+  return CMX_OK;
+}
+
+// wait for everything enqueued on the state's stream; an occupant index out of range in
+// an asynchronous upload since the last call is reported here
+extern "C" int cmx_state_synchronize(cmx_state *s) {
+  if (!s) return invalid("cmx_state_synchronize: null state");
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  int bad = 0;
+  if (s->async_upload_pending) {
+    CMX_CUDA(cudaMemcpyAsync(&bad, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CMX_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
+  }
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  s->async_upload_pending = false;
+  if (bad) return invalid("cmx_state_synchronize: occupant index out of range in an asynchronous upload");
+  return CMX_OK;
+}
+
 extern "C" int cmx_state_upload_occ(cmx_state *s, int32_t r, const int32_t *o) {
   return upload_occ<int32_t>(s, r, o);
 }

@@ -183,6 +183,7 @@ struct cmx_state {
   uint32_t sweep_flags = 0;            // CMX_SWEEP_* (cmx_state_set_sweep_flags)
   cmx_counters *d_counters = nullptr;  // [replica]
   int *d_flag = nullptr;               // device-side validation flag
+  bool async_upload_pending = false;   // an asynchronous upload has not been checked yet
   // slab decomposition over NVLink peer memory (cmx_state_ipc_attach):
   // d_sig[0] / [1]: epoch reached by my lower / upper ring neighbour (written by
   // them), [2]: finished blocks of my own sweep launches, [3]: wait timed out

@@ -1766,6 +1766,15 @@ int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int6
   return CMX_OK;
 }
 
+// cmx_sgc_sweep without the synchronisation: counters are reset, n_sweeps sweeps are
+// enqueued; read the counters (cmx_counters_read) or call cmx_state_synchronize later
+extern "C" int cmx_sgc_sweep_async(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep) {
+  int rc = cmx_counters_reset(s);
+  if (rc) return rc;
+  if (n_sweeps < 0) return invalid("cmx_sgc_sweep_async: n_sweeps < 0");
+  return cmx_sgc_sweep_enqueue(s, seed, first_sweep, n_sweeps);
+}
+
 extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
                                     int32_t kgroup) {
   int rc = sweep_prepare(s, "cmx_sgc_sweep_kgroup");

@@ -251,6 +251,15 @@ int cmx_counters_reset(cmx_state *s);
  * per pass; pays when a pass is too short to amortise a launch (small boxes, slabs). */
 #define CMX_SWEEP_COOP 32u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
+/* Asynchronous forms for pipelines of independent states (each state owns a stream): the
+ * upload of one job overlaps the sweeps of another and the download of a third.  Host
+ * buffers must be pinned for the copies to be asynchronous.  cmx_state_synchronize waits
+ * for the state's stream and reports an occupant index out of range found by an
+ * asynchronous upload; cmx_counters_read (synchronising) returns the sweep counters. */
+int cmx_state_upload_occ_i8_async(cmx_state *s, int32_t replica, const int8_t *occ);
+int cmx_state_download_occ_i8_async(cmx_state *s, int32_t replica, int8_t *occ);
+int cmx_sgc_sweep_async(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep);
+int cmx_state_synchronize(cmx_state *s);
 /* Slab states attached over peer memory (cmx_state_ipc_attach): n_sweeps whole sweeps in
  * one cooperative launch, the ring protocol of the halo exchange inside the kernel.
  * Asynchronous (enqueued on the state's stream).  CMX_ERR_UNSUPPORTED when the state is

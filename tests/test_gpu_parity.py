@@ -451,3 +451,46 @@ def test_error_paths(dev_tables, load_tables):
     with pytest.raises(_capi.CmxError):
         _capi.State(dev_tables("fcc_default"), (0, 8, 8))
     st.close()
+
+
+def test_async_pipeline_equals_synchronous_calls(dev_tables, systems):
+    """Asynchronous upload / sweeps / download on several states (one stream each, pinned
+    host buffers) leave the same occupations and counters as the synchronous calls, and an
+    occupant index out of range in an asynchronous upload surfaces at cmx_state_synchronize."""
+    import torch
+    N = (64, 16, 16)
+    n = int(np.prod(N))
+    rng = np.random.default_rng(3)
+    jobs = [rng.integers(0, 3, n).astype(np.int8) for _ in range(5)]
+    ref, ref_acc = [], []
+    st, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 800.0, [0.1, -0.2], seed=1)
+    for k, occ in enumerate(jobs):
+        st.upload_occ(occ)
+        c = st.sgc_sweep(3, seed=5, first_sweep=3 * k)
+        ref.append(st.download_occ(dtype=np.int8))
+        ref_acc.append(c[0].n_accept)
+    states = [st] + [_sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 800.0, [0.1, -0.2], seed=1)[0]
+                     for _ in range(2)]
+    h_in = [torch.empty(n, dtype=torch.int8).pin_memory().numpy() for _ in range(3)]
+    h_out = [torch.empty(n, dtype=torch.int8).pin_memory().numpy() for _ in range(3)]
+    got, got_acc = {}, {}
+    for k in range(len(jobs) + 3):
+        b = k % 3
+        if k >= 3:
+            got_acc[k - 3] = states[b].counters_read()[0].n_accept
+            got[k - 3] = h_out[b].copy()
+        if k < len(jobs):
+            h_in[b][:] = jobs[k]
+            states[b].upload_occ_async(h_in[b])
+            states[b].sgc_sweep_async(3, seed=5, first_sweep=3 * k)
+            states[b].download_occ_async(h_out[b])
+    for k in range(len(jobs)):
+        assert (got[k] == ref[k]).all() and got_acc[k] == ref_acc[k]
+    h_in[0][:] = 0
+    h_in[0][7] = 5
+    states[0].upload_occ_async(h_in[0])
+    with pytest.raises(_capi.CmxError):
+        states[0].synchronize()
+    states[0].synchronize()            # the error is reported once
+    for s2 in states:
+        s2.close()
