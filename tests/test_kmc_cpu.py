@@ -195,3 +195,23 @@ def test_lotto_selector_oracle():
     before = len(calls)
     sel.select()
     assert calls[before:] == [[1], [], [], [0, 4], []][last]
+
+
+def test_relative_impact_table_point_only(systems, load_tables):
+    """tests/unit/clexmonte/events_System_impact_table_test.cpp:75-128 (Test2): only the
+    A-Va events (12 prim events), point-function formation-energy ECI {0, 1}, constant-only
+    kra / freq coefficients: the required update neighborhood is the 2 event sites and every
+    event impacts 46 events."""
+    from casmcode_clexmonte_b200 import kmc as K
+    sysd = systems["fcc"]
+    ft = load_tables("fcc_default")
+    et = sysd["kmc"]["event_types"][0]
+    assert et["name"] == "A_Va_1NN"
+    types = [dict(et, kra=([0], [0.0]), freq=([0], [0.0]))]
+    prim = K.make_prim_event_list(types)
+    assert len(prim) == 12
+    nbh = [K.required_update_neighborhood(ft, [0, 1], load_tables(et["local_tables"][p["equivalent_index"]]), [0],
+                                          p["sites"]) for p in prim]
+    assert [len(x) for x in nbh] == [2] * 12
+    beg, ent = K.make_relative_impact_table(prim, nbh)
+    assert (np.diff(beg) == 46).all()
