@@ -337,7 +337,7 @@ def main():
     # DRAM traffic of one launch from the committed ncu --set full capture of this kernel at
     # this workload (512^3, one GPU); null for any other configuration
     traffic = None
-    prof = ROOT / "profiles" / "r01s_ncu_full_k_sweep_row16.csv"
+    prof = ROOT / "profiles" / "r01t_ncu_full_k_sweep_row16.csv"
     if world == 1 and args.box == N_BOX and kernel_name == "k_sweep_row16" and prof.exists():
         import csv
         vals = {}
@@ -359,13 +359,13 @@ def main():
                        "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
                        "alu_pipe_pct": float(m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]),
                        "dram_pct": float(m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]),
-                       "source": "profiles/r01s_ncu_full_k_sweep_row16.csv (ncu --set full, one launch)"}
+                       "source": "profiles/r01t_ncu_full_k_sweep_row16.csv (ncu --set full, one launch)"}
         except (KeyError, ValueError):
             binding = None
     alg_bytes = 2.0 * sites_per_launch           # 2 B per step at the HBM level
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_note": "bytes per launch, dram read + write, profiles/r01s_ncu_full_k_sweep_row16.csv",
+                "traffic": traffic, "traffic_note": "bytes per launch, dram read + write, profiles/r01t_ncu_full_k_sweep_row16.csv",
                 "algorithmic_bytes_per_launch": alg_bytes, "binding_resource": binding, "peak_source": peak_src,
                 "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_step_hbm": 2.0,
