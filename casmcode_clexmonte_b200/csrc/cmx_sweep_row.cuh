@@ -484,9 +484,13 @@ __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane 
   auto take = [&](int32_t &j, int32_t &k, bool &on) {
     on = row < a.n_rows;  // a partial last tile: the idle lanes redo the last row, unstored
     j = 2 * (int32_t)(on ? jj : jj_last) + a.cy;
-    int32_t kq = (int32_t)(on ? kk : kk_last) + rot;
-    if (kq >= kk_end) kq -= n_layers;
-    k = 2 * kq + a.cz;
+    if (SLAB) {
+      int32_t kq = (int32_t)(on ? kk : kk_last) + rot;
+      if (kq >= kk_end) kq -= n_layers;
+      k = 2 * kq + a.cz;
+    } else {
+      k = 2 * (int32_t)(on ? kk : kk_last) + a.cz;
+    }
     row += n_warps << rpw_log;
     jj += step_j;
     kk += step_k;
