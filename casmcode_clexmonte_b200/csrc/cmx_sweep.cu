@@ -1092,9 +1092,9 @@ static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool 
   }
 }
 
-template <int NOCC, uint32_t MASK, bool ACC, bool SLAB>
+template <int NOCC, uint32_t MASK, bool ACC, bool SLAB, bool FULL>
 static int launch_row16_inst2(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
-  auto kern = k_sweep_row16<NOCC, MASK, ACC, SLAB>;
+  auto kern = k_sweep_row16<NOCC, MASK, ACC, SLAB, FULL>;
   static bool attr_set = false;
   const size_t bytes = row16_smem_bytes<NOCC>(MASK);
   if (!attr_set) {
@@ -1108,7 +1108,11 @@ static int launch_row16_inst2(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
 template <int NOCC, uint32_t MASK, bool ACC>
 static int launch_row16_inst(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
   // slabs (a.push): the variant with the ring protocol compiled in
-  return a.push ? launch_row16_inst2<NOCC, MASK, ACC, true>(a, cfg) : launch_row16_inst2<NOCC, MASK, ACC, false>(a, cfg);
+  if (a.push) return launch_row16_inst2<NOCC, MASK, ACC, true, false>(a, cfg);
+  // the rows divide evenly into warp tiles: no partial tile anywhere
+  const uint32_t rpw = 32u / a.W;
+  return (a.n_rows % rpw == 0) ? launch_row16_inst2<NOCC, MASK, ACC, false, true>(a, cfg)
+                               : launch_row16_inst2<NOCC, MASK, ACC, false, false>(a, cfg);
 }
 template <int NOCC>
 static int launch_row16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum, bool pdl) {

@@ -443,7 +443,7 @@ __device__ __forceinline__ void row16_load_table(uint32_t *sh_tab, const uint32_
 
 // One colour pass (a.cy, a.cz) of this block's share of the rows: the tile loop of
 // k_sweep_row16 (and of every pass of k_sweep_row16_coop).
-template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB>
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, bool FULL = false>
 __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane &L, uint32_t slots, uint32_t lane,
                                            uint32_t wib, uint32_t rl, uint32_t rpw_log, uint32_t &n_acc,
                                            double &e_tot) {
@@ -482,7 +482,9 @@ __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane 
   };
   // (j, k, on) of the tile at the current position, then advance the position
   auto take = [&](int32_t &j, int32_t &k, bool &on) {
-    on = row < a.n_rows;  // a partial last tile: the idle lanes redo the last row, unstored
+    // a partial last tile: the idle lanes redo the last row, unstored (FULL: the host saw
+    // that the rows divide evenly into tiles -- the predicate and its selects are gone, +1.2 %)
+    on = FULL ? true : (row < a.n_rows);
     j = 2 * (int32_t)(on ? jj : jj_last) + a.cy;
     if (SLAB) {
       int32_t kq = (int32_t)(on ? kk : kk_last) + rot;
@@ -530,7 +532,7 @@ __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane 
 // and row) -- the global latency is hidden behind ~350 instructions of compute and
 // costs no registers.  A lane only ever reads the slots it filled itself: no
 // barrier, not even a warp one.
-template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB>
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, bool FULL>
 __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
   constexpr int NTAB = CMX_TAB24(NOCC);
   constexpr uint32_t NSLOT = row16_n_slots(MASK_CT);
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16(Pair16Args a) {
     st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
   }
   __syncthreads();
-  row16_pass<NOCC, MASK_CT, ACCUM, SLAB>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
+  row16_pass<NOCC, MASK_CT, ACCUM, SLAB, FULL>(a, L, slots, lane, wib, rl, rpw_log, n_acc, e_tot);
   row16_reduce(a, L.r, n_acc, e_tot, sh_acc, sh_sum);
 }
 
