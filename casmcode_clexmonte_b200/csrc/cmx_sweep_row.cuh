@@ -243,7 +243,9 @@ struct Row16NoHook {
 };
 // SRC = 0: rows are loaded here (CG: through L2 only); SRC = 1: rows were staged by
 // row16_issue into `slots`; after_loads() runs once this lane has read its slots.
-template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool CG, int SRC = 0, typename Hook = Row16NoHook>
+// PUSH: slab states also store boundary rows into the ring neighbours' ghost layers
+// (compile-time: the mere branch costs the plain kernel 1.5 %)
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool CG, int SRC = 0, typename Hook = Row16NoHook, bool PUSH = true>
 __device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16Lane &L, int32_t j, int32_t k,
                                               uint32_t sweep_lo, uint32_t ctr_hi, bool on, uint32_t &n_acc,
                                               double &e_tot, uint32_t slots = 0, Hook after_loads = Hook()) {
@@ -350,7 +352,7 @@ __device__ __forceinline__ int8_t *row16_tile(const Pair16Args &a, const Row16La
     const uint32_t A = (~(rej0[0] & rej1[0]) & 0x01010101u) + (~(rej0[1] & rej1[1]) & 0x01010101u) +
                        (~(rej0[2] & rej1[2]) & 0x01010101u) + (~(rej0[3] & rej1[3]) & 0x01010101u);
     n_acc = __dp4a(A, 0x01010101u, n_acc);
-    if (a.push) {
+    if (PUSH && a.push) {
       // my layer 0 is the lower neighbour's upper ghost, my last layer the
       // upper neighbour's lower ghost (same slab geometry on every rank)
       const uint4 out = make_uint4(C[0], C[1], C[2], C[3]);
@@ -519,7 +521,8 @@ __device__ __forceinline__ void row16_pass(const Pair16Args &a, const Row16Lane 
         row16_issue<MASK_CT>(a, L, jn, kn, slots);
       }
     };
-    row16_tile<NOCC, MASK_CT, ACCUM, true, 1>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot, slots, stage_next);
+    row16_tile<NOCC, MASK_CT, ACCUM, true, 1, decltype(stage_next), SLAB>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot,
+                                                                         slots, stage_next);
     j = jn;
     k = kn;
     on = on_n;
@@ -703,7 +706,8 @@ __global__ void __launch_bounds__(256, 3) k_sweep_row16_flat(Pair16Args a, uint3
     };
     uint32_t n_acc = 0;
     double e_tot = 0.0;
-    row16_tile<NOCC, MASK_CT, ACCUM, true, 1>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot, slots, stage_next);
+    row16_tile<NOCC, MASK_CT, ACCUM, true, 1, decltype(stage_next), false>(a, L, j, k, a.sweep_lo, a.ctr_hi, on, n_acc, e_tot,
+                                                                          slots, stage_next);
     if (rep == r_lo) {
       n_acc0 += n_acc;
       e_tot0 += e_tot;
