@@ -11,8 +11,8 @@ one attempted Metropolis step at every site).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N > 1 (torchrun, one rank per GPU): the 512^3 box is split into N slabs along k
-with one ghost layer each side, exchanged twice per sweep over NCCL
-(strong scaling).  --impl reference times the reference's own CPU path (the
+with one ghost layer each side; boundary rows travel over NVLink peer memory inside
+the sweep kernel (strong scaling).  --impl reference times the reference's own CPU path (the
 generated Clexulator kernels of oracle/_ref inside the restated sequential
 loop), one chain per host core.
 """
@@ -21,7 +21,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -46,63 +45,7 @@ def load_system():
     return sysd
 
 
-# ---------------------------------------------------------------------------
-# clocks
-# ---------------------------------------------------------------------------
-class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu: int):
-        self.gpu = gpu
-        self.proc = None
-        self.lines = []
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
-
-    def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, line in self.lines:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                clk, mxc = float(f[1]), float(f[2])
-            except ValueError:
-                continue
-            mx = mxc
-            if t0 - 0.05 <= ts <= t1 + 0.05:
-                sm.append(clk)
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                      "sw_power_cap"), f[4:8]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:  # region shorter than the sampling period: take every sample
-            for ts, line in self.lines:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[1]))
-                except (ValueError, IndexError):
-                    pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+from casmcode_clexmonte_b200.clocks import ClockSampler  # noqa: E402
 
 
 # ---------------------------------------------------------------------------
@@ -151,6 +94,145 @@ def cpu_reference_rate(seconds_budget: float = 12.0, box: int = 64, threads: int
 
 
 # ---------------------------------------------------------------------------
+# end-to-end legs: host buffers through the C ABI, copies inside the timed region
+# ---------------------------------------------------------------------------
+def e2e_single(torch, _capi, st, tables, eci, ex, N, K, S, sweep_flags) -> dict:
+    """The headline e2e is the leg a reference-side plugin would run: ONE state, every step
+    uploads the int32 occupation the previous step downloaded (the reference hands the
+    calculator an Eigen::VectorXi, int32), sweeps, downloads int32 occupation + counters;
+    nothing can overlap.  Reported beside it: the same dependent leg with int8 host buffers
+    (4x fewer PCIe bytes) and a pipeline of independent jobs (three states in flight)."""
+    n_sites = N ** 3
+
+    def dependent(dtype, n_steps):
+        host = torch.empty(n_sites, dtype={np.int8: torch.int8, np.int32: torch.int32}[dtype]).pin_memory()
+        harr = host.numpy()
+        st.download_occ(dtype=dtype, out=harr)
+        for _ in range(1):
+            st.upload_occ(harr)
+            st.sgc_sweep(S, seed=3, first_sweep=0, counters=True)
+            st.download_occ(dtype=dtype, out=harr)
+        torch.cuda.synchronize()
+        te0 = time.perf_counter()
+        for k in range(n_steps):
+            st.upload_occ(harr)
+            st.sgc_sweep(S, seed=3, first_sweep=(k + 1) * S, counters=True)
+            st.download_occ(dtype=dtype, out=harr)
+        torch.cuda.synchronize()
+        te1 = time.perf_counter()
+        b = n_sites * np.dtype(dtype).itemsize
+        return {"value": n_steps * S * n_sites / (te1 - te0), "unit": UNIT, "h2d_bytes_per_step": b,
+                "d2h_bytes_per_step": b + 32, "ms_per_step": (te1 - te0) * 1e3 / n_steps}
+
+    e2e = dependent(np.int32, K)
+    e2e["note"] = ("one state, every step uploads the int32 occupation the previous step downloaded "
+                   "(the reference's Eigen::VectorXi), S sweeps, downloads int32 occupation + counters")
+    e2e["int8_dependent"] = dependent(np.int8, K)
+    # pipelined: every step is an independent job (its own pinned input and output buffers),
+    # three states in flight: the upload of job k+1, the sweeps of job k and the download of
+    # job k-1 overlap (asynchronous C ABI, one stream per state)
+    n_buf = 3
+    states = [st]
+    for _ in range(n_buf - 1):
+        s2 = _capi.State(tables, (N, N, N))
+        s2.set_eci(eci["index"], eci["value"])
+        s2.set_conditions(TEMPERATURE, ex)
+        s2.set_sweep_flags(sweep_flags)
+        states.append(s2)
+    h_in = [torch.empty(n_sites, dtype=torch.int8).pin_memory().numpy() for _ in range(n_buf)]
+    h_out = [torch.empty(n_sites, dtype=torch.int8).pin_memory().numpy() for _ in range(n_buf)]
+    st.download_occ(dtype=np.int8, out=h_in[0])
+    for b in range(1, n_buf):
+        h_in[b][:] = h_in[0]
+
+    def pipeline(n_jobs):
+        acc = 0
+        for k in range(n_jobs + n_buf):
+            b = k % n_buf
+            if k >= n_buf:                      # job k - n_buf: its result is read here
+                acc += states[b].counters_read()[0].n_accept
+            if k < n_jobs:
+                states[b].upload_occ_async(h_in[b])
+                states[b].sgc_sweep_async(S, seed=3, first_sweep=(k + 1) * S)
+                states[b].download_occ_async(h_out[b])
+        return acc
+
+    pipeline(n_buf)
+    torch.cuda.synchronize()
+    tp0 = time.perf_counter()
+    acc = pipeline(K)
+    torch.cuda.synchronize()
+    tp1 = time.perf_counter()
+    assert acc > 0 and (h_out[0] != h_in[0]).any()
+    e2e["int8_pipelined"] = {"value": K * S * n_sites / (tp1 - tp0), "unit": UNIT,
+                             "h2d_bytes_per_step": n_sites, "d2h_bytes_per_step": n_sites + 32,
+                             "ms_per_step": (tp1 - tp0) * 1e3 / K,
+                             "note": "independent jobs, 3 states in flight (upload / sweeps / download overlap)"}
+    for s2 in states[1:]:
+        s2.close()
+    return e2e
+
+
+def bench_slabs(torch, dist, runner, K: int, W: int, S: int, no_e2e: bool = False) -> dict:
+    """N > 1: the box cut into k-slabs, one rank per GPU (casmcode_clexmonte_b200.slab)."""
+    for w in range(W):
+        runner.sweep(S, seed=1, first_sweep=w * S)
+    runner.synchronize()
+    runner.state.counters_reset()
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ev0.record(runner.stream)
+    for k in range(K):
+        runner.sweep(S, seed=1, first_sweep=(W + k) * S)
+    ev1.record(runner.stream)
+    runner.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=runner.mem.device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    cnt = runner.counters()
+    clk = clocks.stop(t0, t1)
+    n_sites = runner.N[0] * runner.N[1] * runner.N[2] * runner.n_sublat
+    stream = bool(runner.p2p and runner.info()["stream"])
+    lps = runner.info()["launches_per_sweep"]
+    launches = K if stream else K * S * max(lps, 1)
+    e2e = None
+    if not no_e2e:
+        # end to end: every rank's int32 host slab in, S sweeps, int32 slab out, every step
+        host = torch.empty(runner.layer * runner.n2 * runner.n_sublat, dtype=torch.int32).pin_memory()
+        harr = host.numpy()
+        runner.state.download_occ(dtype=np.int32, out=harr)
+        dist.barrier()
+        torch.cuda.synchronize()
+        te0 = time.perf_counter()
+        for k in range(K):
+            runner.state.upload_occ(harr)
+            runner.exchange(None)
+            runner.sweep(S, seed=3, first_sweep=k * S)
+            runner.state.download_occ(dtype=np.int32, out=harr)
+        runner.synchronize()
+        dist.barrier()
+        te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=runner.mem.device)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": K * S * n_sites / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 4 * n_sites, "d2h_bytes_per_step": 4 * n_sites,
+               "ms_per_step": float(te.item()) * 1e3 / K,
+               "note": "every rank: int32 host slab uploaded, ghost layers exchanged (NCCL), S sweeps, "
+                       "int32 slab downloaded, every step"}
+    return dict(ms=float(ms.item()), clocks=clk, accept_rate=float(cnt[1] / max(cnt[0], 1.0)),
+                launches=launches, kernel_ms=float(ms.item()) / launches, stream=stream,
+                sweeps_per_launch=(float(S) if stream else 1.0 / max(lps, 1)), e2e=e2e)
+
+
+# ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,7 +242,7 @@ def main():
     ap.add_argument("--box", type=int, default=N_BOX)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator, 4 = block kernel, 8 = fused whole-call kernel)")
+    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -169,7 +251,7 @@ def main():
     workload = (f"FCC A-B-Va semi-grand canonical, {args.box}^3 primitive supercell, shipped sparse ECI "
                 f"(points+1NN pairs), T={TEMPERATURE:g} K, param_chem_pot={list(MU)}")
     config = {"workload": workload, "sites": args.box ** 3, "sweeps_per_step": SWEEPS_PER_STEP,
-              "l2_policy": "inputs larger than L2 (134 MB lattice re-streamed every colour pass)",
+              "l2_policy": "inputs larger than L2 (134 MB lattice, streamed once per sweep and direction)",
               "parallelism": f"slab{world}" if world > 1 else "single"}
 
     if args.impl == "reference":
@@ -204,6 +286,7 @@ def main():
     N = args.box
     K, W, S = args.steps, max(3, args.warmup), SWEEPS_PER_STEP
 
+    n_sites = N ** 3
     if world == 1:
         st = _capi.State(tables, (N, N, N))
         st.set_eci(eci["index"], eci["value"])
@@ -213,169 +296,94 @@ def main():
         info = st.sweep_info()
         stream = torch.cuda.ExternalStream(st.stream())
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # ---- device-resident throughput
-        st.sgc_sweep(W * S, seed=1, first_sweep=0, counters=False)
+        # ---- device-resident throughput: K steps, each one call of S sweeps (the streaming
+        # kernel runs a call as ONE cooperative launch; the other evaluators launch per colour)
+        for w in range(W):   # the same calls as the timed steps (the unit list of a call is cached)
+            st.sgc_sweep(S, seed=1, first_sweep=w * S, counters=False)
         torch.cuda.synchronize()
         clocks = ClockSampler(local_rank)
         clocks.start()
         time.sleep(0.3)
+        st.counters_reset()
         t0 = time.time()
         ev0.record(stream)
-        cnt = st.sgc_sweep(K * S, seed=1, first_sweep=W * S)
+        for k in range(K):
+            st.sgc_sweep_enqueue(S, seed=1, first_sweep=(W + k) * S)
         ev1.record(stream)
         torch.cuda.synchronize()
         t1 = time.time()
+        cnt = st.counters_read()
         ms = ev0.elapsed_time(ev1)
         clk = clocks.stop(t0, t1)
-        n_sites = N ** 3
         attempts = K * S * n_sites
         assert cnt[0].n_attempt == attempts
         value = attempts / (ms * 1e-3)
-        if info["fused"]:
-            # the whole timed call (K steps x S sweeps) is ONE launch of the fused kernel
-            sweep_launches = 1
-        else:
-            sweep_launches = K * S * info["launches_per_sweep"]
-        launches = sweep_launches + 3
+        lps = info["launches_per_sweep"]
+        sweep_launches = K if lps == 0 else K * S * lps
+        sweeps_per_launch = float(S) if lps == 0 else 1.0 / lps
+        launches = sweep_launches + 1          # + the counter reduction
         kernel_ms = ms / sweep_launches
-        # ---- end to end: host buffers through the C ABI, copies inside the timed region
-        host = torch.empty(n_sites, dtype=torch.int8).pin_memory()
-        harr = host.numpy()
-        st.download_occ(dtype=np.int8, out=harr)
-        for _ in range(0 if args.no_e2e else 2):
-            st.upload_occ(harr)
-            st.sgc_sweep(S, seed=3, first_sweep=0, counters=True)
-            st.download_occ(dtype=np.int8, out=harr)
-        torch.cuda.synchronize()
-        te0 = time.perf_counter()
-        for k in range(1 if args.no_e2e else K):
-            st.upload_occ(harr)
-            c2 = st.sgc_sweep(S, seed=3, first_sweep=(k + 1) * S, counters=True)
-            st.download_occ(dtype=np.int8, out=harr)
-        torch.cuda.synchronize()
-        te1 = time.perf_counter()
-        e2e_seq = {"value": K * S * n_sites / (te1 - te0), "unit": UNIT,
-                   "h2d_bytes_per_step": n_sites, "d2h_bytes_per_step": n_sites + 32,
-                   "ms_per_step": (te1 - te0) * 1e3 / K,
-                   "note": "one state, every step uploads what the previous step downloaded (no overlap possible)"}
-        e2e = e2e_seq
-        if not args.no_e2e:
-            # pipelined: every step is an independent job (its own pinned input and output
-            # buffers), three states in flight: the upload of job k+1, the sweeps of job k and
-            # the download of job k-1 overlap (asynchronous C ABI, one stream per state)
-            n_buf = 3
-            states = [st]
-            for _ in range(n_buf - 1):
-                s2 = _capi.State(tables, (N, N, N))
-                s2.set_eci(eci["index"], eci["value"])
-                s2.set_conditions(TEMPERATURE, ex)
-                s2.set_sweep_flags(args.sweep_flags)
-                states.append(s2)
-            h_in = [torch.empty(n_sites, dtype=torch.int8).pin_memory().numpy() for _ in range(n_buf)]
-            h_out = [torch.empty(n_sites, dtype=torch.int8).pin_memory().numpy() for _ in range(n_buf)]
-            for b in range(n_buf):
-                h_in[b][:] = harr
-
-            def pipeline(n_jobs):
-                acc = 0
-                for k in range(n_jobs + n_buf):
-                    b = k % n_buf
-                    if k >= n_buf:                      # job k - n_buf: its result is read here
-                        acc += states[b].counters_read()[0].n_accept
-                    if k < n_jobs:
-                        states[b].upload_occ_async(h_in[b])
-                        states[b].sgc_sweep_async(S, seed=3, first_sweep=(k + 1) * S)
-                        states[b].download_occ_async(h_out[b])
-                return acc
-
-            pipeline(n_buf)
-            torch.cuda.synchronize()
-            tp0 = time.perf_counter()
-            acc = pipeline(K)
-            torch.cuda.synchronize()
-            tp1 = time.perf_counter()
-            assert acc > 0 and (h_out[0] != h_in[0]).any()
-            e2e = {"value": K * S * n_sites / (tp1 - tp0), "unit": UNIT,
-                   "h2d_bytes_per_step": n_sites, "d2h_bytes_per_step": n_sites + 32,
-                   "ms_per_step": (tp1 - tp0) * 1e3 / K,
-                   "note": "independent jobs, 3 states in flight (upload / sweeps / download overlap); "
-                           "every job uploads its own input and downloads occupation + counters",
-                   "sequential": e2e_seq}
-            for s2 in states[1:]:
-                s2.close()
+        kernel_name = "k_sweep_stream16" if info["stream"] else ("k_sweep_pair16" if info["evaluator"] == "pair_lut"
+                                                                 else "k_sweep_generic")
         accept_rate = cnt[0].n_accept / cnt[0].n_attempt
+        e2e = None
+        if not args.no_e2e:
+            e2e = e2e_single(torch, _capi, st, tables, eci, ex, N, K, S, args.sweep_flags)
         st.close()
     else:
+        import torch.distributed as dist
         runner = SlabRunner(tables, N, eci, TEMPERATURE, ex, rank, world, local_rank, seed_init=2026)
         info = runner.info()
-        res = runner.bench(K, W, S)
+        res = bench_slabs(torch, dist, runner, K, W, S, no_e2e=args.no_e2e)
         ms, clk, e2e, accept_rate = res["ms"], res["clocks"], res["e2e"], res["accept_rate"]
-        n_sites = N ** 3
         value = K * S * n_sites / (ms * 1e-3)
-        launches = res["launches"]
-        kernel_ms = res["kernel_ms"]
-        slab_coop, slab_sweeps_per_launch = res["coop"], res["sweeps_per_launch"]
+        launches, kernel_ms, sweeps_per_launch = res["launches"], res["kernel_ms"], res["sweeps_per_launch"]
+        kernel_name = "k_sweep_stream16" if res["stream"] else "k_sweep_pair16"
         if rank != 0:
             return
 
-    # ---- roofline of the dominant kernel (k_sweep_pair_lut, one colour pass)
+    # ---- roofline of the dominant kernel: algorithmic bytes of ONE launch / its duration
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    if world == 1 and info["fused"]:
-        sites_per_launch = float(n_sites) * K * S
-        kernel_name = "k_sweep_row16_fused"
-    elif world > 1:
-        # cooperative slab sweeps: one launch = all the sweeps of the timed call on this rank's slab
-        sites_per_launch = n_sites / world * slab_sweeps_per_launch
-        kernel_name = "k_sweep_row16_coop" if slab_coop else "k_sweep_row16"
-    else:
-        sites_per_launch = n_sites / world / info["launches_per_sweep"]
-        kernel_name = "k_sweep_row16"
-    # DRAM traffic of one launch from the committed ncu --set full capture of this kernel at
-    # this workload (512^3, one GPU); null for any other configuration
-    traffic = None
-    prof = ROOT / "profiles" / "r01t_ncu_full_k_sweep_row16.csv"
-    if world == 1 and args.box == N_BOX and kernel_name == "k_sweep_row16" and prof.exists():
-        import csv
-        vals = {}
-        for row in csv.reader(prof.open()):
-            if len(row) == 5 and row[0] == "1" and row[2] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                vals[row[2]] = float(row[4]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[row[3]]
-        if len(vals) == 2:
-            traffic = sum(vals.values())
-    # the resource ncu identifies as binding (issue slots / ALU pipe), from the same capture
-    binding = None
-    if traffic is not None:
+    sites_per_launch = n_sites / world * sweeps_per_launch   # attempted steps of one launch (one rank)
+    # DRAM traffic of one launch and the binding resource from the committed ncu --set full
+    # capture of this kernel at this workload (512^3, one GPU, S sweeps per launch); null otherwise
+    traffic, binding = None, None
+    prof = ROOT / "profiles" / "r02_ncu_full_k_sweep_stream16.csv"
+    if world == 1 and args.box == N_BOX and kernel_name == "k_sweep_stream16" and prof.exists():
         import csv
         m = {}
         for row in csv.reader(prof.open()):
             if len(row) == 5 and row[0] == "1":
-                m[row[2]] = row[4]
+                m[row[2]] = (row[3], row[4])
         try:
+            unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            traffic = sum(float(m[k][1]) * unit[m[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             binding = {"resource": "instruction issue slots (ALU pipe)", "unit": "% of peak sustained",
-                       "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
-                       "alu_pipe_pct": float(m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]),
-                       "dram_pct": float(m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]),
-                       "source": "profiles/r01t_ncu_full_k_sweep_row16.csv (ncu --set full, one launch)"}
+                       "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][1]),
+                       "alu_pipe_pct": float(m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"][1]),
+                       "dram_pct": float(m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"][1]),
+                       "source": f"profiles/{prof.name} (ncu --set full, one launch = {S} sweeps)"}
         except (KeyError, ValueError):
-            binding = None
+            pass
     alg_bytes = 2.0 * sites_per_launch           # 2 B per step at the HBM level
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_note": "bytes per launch, dram read + write, profiles/r01t_ncu_full_k_sweep_row16.csv",
+                "traffic": traffic, "traffic_note": f"bytes per launch, dram read + write, profiles/{prof.name}",
                 "algorithmic_bytes_per_launch": alg_bytes, "binding_resource": binding, "peak_source": peak_src,
-                "kernel": kernel_name,
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_step_hbm": 2.0,
-                "algorithmic_bytes_per_step_l2": info["bytes_per_step"],
-                "note": "the sweep is instruction-issue bound, not HBM bound: see DESIGN.md and profiles/"}
+                "kernel": kernel_name, "kernel_ms": kernel_ms, "sweeps_per_launch": sweeps_per_launch,
+                "algorithmic_bytes_per_step_hbm": 2.0,
+                "algorithmic_bytes_per_step_l2": info["bytes_per_step"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "evaluator": info["evaluator"],
-            "accept_rate": accept_rate, "dE_evals_per_s": value}
+            "accept_rate": accept_rate, "dE_evals_per_s": value,
+            "schedule": {k: info.get(k) for k in ("stream", "stream_blocks", "stream_group_rowsteps",
+                                                  "stream_gap_units", "launches_per_sweep")}}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_reference_rate(seconds_budget=args.cpu_seconds)

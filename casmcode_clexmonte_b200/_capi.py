@@ -19,24 +19,24 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libcmx_b200.so"
 
 CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
-CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC, CMX_SWEEP_BLOCK_KERNEL, CMX_SWEEP_FUSED = 1, 2, 4, 8
+CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC = 1, 2
 CMX_SWEEP_THREAD_GENERIC = 16
-CMX_SWEEP_COOP = 32
+CMX_STATE_LINEAR_ROWS = 1
 
 # every symbol include/cmx_b200.h declares
 EXPORTED_SYMBOLS = [
     "cmx_last_error", "cmx_version", "cmx_device_count",
     "cmx_tables_create", "cmx_tables_destroy",
-    "cmx_state_create", "cmx_state_destroy",
+    "cmx_state_create", "cmx_state_create_opts", "cmx_state_destroy",
     "cmx_state_upload_occ", "cmx_state_download_occ",
     "cmx_state_upload_occ_i8", "cmx_state_download_occ_i8",
-    "cmx_state_upload_occ_i8_async", "cmx_state_download_occ_i8_async", "cmx_state_synchronize", "cmx_sgc_sweep_async",
+    "cmx_state_upload_occ_i8_async", "cmx_state_download_occ_i8_async", "cmx_state_synchronize", "cmx_sgc_sweep_async", "cmx_sgc_sweep_continue",
     "cmx_state_randomize", "cmx_state_set_k_offset", "cmx_state_stream", "cmx_state_device_ptr",
     "cmx_state_ipc_export", "cmx_state_ipc_attach", "cmx_state_p2p_active",
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
-    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sgc_sweep_slab", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_fused_info",
+    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sgc_sweep_slab", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_stream_info", "cmx_sweep_debug_delta_e",
     "cmx_metropolis_sequential", "cmx_rng_stream_test",
     "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
@@ -131,6 +131,7 @@ def lib():
     L.cmx_state_download_occ_i8_async.argtypes = [vp, i32, vp]
     L.cmx_state_synchronize.argtypes = [vp]
     L.cmx_sgc_sweep_async.argtypes = [vp, i64, u64, i64]
+    L.cmx_sgc_sweep_continue.argtypes = [vp, i64, u64, i64]
     L.cmx_state_randomize.argtypes = [vp, u64]
     L.cmx_state_set_k_offset.argtypes = [vp, i32]
     L.cmx_state_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -157,7 +158,9 @@ def lib():
     L.cmx_sweep_info.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(dbl), C.POINTER(dbl),
                                  C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cmx_sweep_launches.argtypes = [vp, C.POINTER(i32)]
-    L.cmx_sweep_fused_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.cmx_sweep_stream_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.cmx_sweep_debug_delta_e.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.cmx_state_create_opts.argtypes = [vp, i32, i32, i32, i32, i32, C.c_uint32, C.POINTER(vp)]
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
@@ -241,7 +244,8 @@ class Tables:
 class State:
     """Device-resident supercell(s) (``cmx_state``)."""
 
-    def __init__(self, tables: Tables, N: Sequence[int], n_replicas: int = 1, halo: int = 0):
+    def __init__(self, tables: Tables, N: Sequence[int], n_replicas: int = 1, halo: int = 0,
+                 linear_rows: bool = False):
         if np.isscalar(N):
             N = (N, N, N)
         self.tables = tables
@@ -253,7 +257,8 @@ class State:
         self.n_sites = self.n_cells * t.n_sublat
         self._temperature = {}
         self._h = C.c_void_p()
-        check(lib().cmx_state_create(tables._h, *self.N, self.n_replicas, self.halo, C.byref(self._h)))
+        check(lib().cmx_state_create_opts(tables._h, *self.N, self.n_replicas, self.halo,
+                                          CMX_STATE_LINEAR_ROWS if linear_rows else 0, C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -417,6 +422,10 @@ class State:
                                   C.byref(cnt) if counters else None))
         return cnt
 
+    def sgc_sweep_enqueue(self, n_sweeps: int, seed: int, first_sweep: int = 0) -> None:
+        """Asynchronous, counters keep accumulating (cmx_sgc_sweep_continue)."""
+        check(lib().cmx_sgc_sweep_continue(self._h, int(n_sweeps), int(seed), int(first_sweep)))
+
     def sgc_sweep_slab(self, n_sweeps: int, seed: int, first_sweep: int = 0) -> None:
         """Peer-attached slab: whole sweeps in one cooperative launch (asynchronous)."""
         check(lib().cmx_sgc_sweep_slab(self._h, int(n_sweeps), int(seed), int(first_sweep)))
@@ -461,15 +470,24 @@ class State:
         check(lib().cmx_sweep_info(self._h, name, 32, C.byref(b), C.byref(f), C.byref(nc), S, C.byref(rk)))
         nl = C.c_int32()
         check(lib().cmx_sweep_launches(self._h, C.byref(nl)))
-        fu, ls, fb = C.c_int32(), C.c_int32(), C.c_int32()
+        st, sb, gr, gap = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         try:  # needs a device and conditions on every replica
-            check(lib().cmx_sweep_fused_info(self._h, C.byref(fu), C.byref(ls), C.byref(fb)))
+            check(lib().cmx_sweep_stream_info(self._h, C.byref(st), C.byref(sb), C.byref(gr), C.byref(gap)))
         except CmxError:
             pass
         return dict(evaluator=name.value.decode(), bytes_per_step=b.value, flops_per_step=f.value,
                     n_colours=nc.value, colour_strides=tuple(S), range_k=rk.value,
-                    launches_per_sweep=nl.value, fused=bool(fu.value), fused_layers_per_slice=ls.value,
-                    fused_blocks=fb.value)
+                    launches_per_sweep=nl.value, stream=bool(st.value), stream_blocks=sb.value,
+                    stream_group_rowsteps=gr.value, stream_gap_units=gap.value)
+
+    def sweep_debug_delta_e(self, l, new_occ, replica: int = 0) -> np.ndarray:
+        """Delta potential energy of single-site proposals as the SWEEP's evaluator computes it
+        (pair-LUT table entry / folded term lists), for comparison with delta_e()."""
+        l = np.ascontiguousarray(l, dtype=np.int64)
+        new_occ = np.ascontiguousarray(new_occ, dtype=np.int32)
+        out = np.zeros(len(l))
+        check(lib().cmx_sweep_debug_delta_e(self._h, replica, len(l), _p(l), _p(new_occ), _p(out)))
+        return out
 
     def metropolis_sequential(self, mode: int, n_steps: int, seed: int, log_cap: int = 0,
                               replica: int = 0) -> dict:

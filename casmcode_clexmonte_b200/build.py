@@ -14,6 +14,7 @@ LIB = HERE / "libcmx_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-I", str(CSRC)]
+FLAGS += os.environ.get("CMX_NVCC_FLAGS", "").split()  # tuning experiments (e.g. -DCMX_S16_MINB=4)
 
 
 def sources():

@@ -126,7 +126,14 @@ extern "C" void cmx_tables_destroy(cmx_tables *t) {
 extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
                                 int32_t N2, int32_t n_replicas, int32_t halo,
                                 cmx_state **out) {
+  return cmx_state_create_opts(t, N0, N1, N2, n_replicas, halo, 0u, out);
+}
+
+extern "C" int cmx_state_create_opts(const cmx_tables *t, int32_t N0, int32_t N1,
+                                     int32_t N2, int32_t n_replicas, int32_t halo,
+                                     uint32_t options, cmx_state **out) {
   if (!t || !out) return invalid("cmx_state_create: null argument");
+  if (options & ~(uint32_t)CMX_STATE_LINEAR_ROWS) return invalid("cmx_state_create_opts: unknown option");
   if (N0 <= 0 || N1 <= 0 || N2 <= 0 || n_replicas <= 0 || halo < 0)
     return invalid("cmx_state_create: non-positive dimension");
   // the neighbor arithmetic wraps once: every |offset| must be <= N
@@ -150,6 +157,11 @@ extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
   g.sub_stride = g.layer * (N2 + 2 * halo);
   g.rep_stride = g.sub_stride * t->d.n_sublat;
   g.coded = (t->d.n_sublat == 1 && t->n_occ[0] == 3) ? 1 : 0;
+  // x4-interleaved rows (see Geom::xq_log) for the shapes the streaming pair-LUT sweep covers
+  g.xq_log = 0;
+  if (!(options & CMX_STATE_LINEAR_ROWS) && t->d.n_sublat == 1 && t->d.max_occ <= 3 && N0 >= 16 && N0 <= 512 &&
+      (N0 & (N0 - 1)) == 0 && N1 % 2 == 0 && N2 % 2 == 0 && N2 <= 65534)
+    while ((4 << g.xq_log) < N0) ++g.xq_log;
   size_t bytes = (size_t)g.rep_stride * n_replicas;
   cudaError_t e = cudaMalloc(&s->d_occ, bytes);
   if (e != cudaSuccess) {
@@ -164,9 +176,14 @@ extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
   cudaMalloc(&s->d_exch, sizeof(double) * ex * n_replicas);
   cudaMemset(s->d_beta, 0, sizeof(double) * n_replicas);
   cudaMemset(s->d_exch, 0, sizeof(double) * ex * n_replicas);
-  cudaMalloc(&s->d_flag, sizeof(int));
-  cudaMalloc((void **)&s->d_sig, sizeof(unsigned long long) * 4);
-  cudaMemset(s->d_sig, 0, sizeof(unsigned long long) * 4);
+  cudaMalloc(&s->d_flag, 2 * sizeof(int));  // [0]: synchronous uploads, [1]: asynchronous uploads
+  cudaMemset(s->d_flag, 0, 2 * sizeof(int));
+  {
+    const size_t sig_bytes = sizeof(unsigned long long) * 4 + sizeof(uint32_t) * (size_t)n_replicas * (N2 + 2);
+    cudaMalloc((void **)&s->d_sig, sig_bytes);
+    cudaMemset(s->d_sig, 0, sig_bytes);
+    s->d_done = reinterpret_cast<uint32_t *>(s->d_sig + 4);
+  }
   cudaMalloc(&s->d_counters, sizeof(cmx_counters) * n_replicas);
   cudaMemset(s->d_counters, 0, sizeof(cmx_counters) * n_replicas);
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -210,6 +227,63 @@ int cmx_scratch(cmx_state *s, size_t bytes) {
   return CMX_OK;
 }
 
+// byte position of unit cell `cell` (reference order) inside the owned layers of a sublattice
+__device__ __forceinline__ int64_t cmx_cell_pos(const Geom &g, int64_t cell) {
+  if (!g.xq_log) return cell;
+  const int64_t row = cell / g.N0;
+  return row * g.N0 + cmx_xpos(g, (int)(cell - row * g.N0));
+}
+
+// int8 image in reference order <-> x4-interleaved rows, 16 bytes of a row per thread: the
+// four words x = 4c + bQ .. +3 (b = 0..3) of the image are the 4x4 byte transpose of chunk c
+// of the stored row.  TO_DEVICE: validate and encode; else decode.
+__device__ __forceinline__ void cmx_transpose4x4(uint32_t (&w)[4]) {
+  const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140u), t1 = __byte_perm(w[2], w[3], 0x5140u);
+  const uint32_t t2 = __byte_perm(w[0], w[1], 0x7362u), t3 = __byte_perm(w[2], w[3], 0x7362u);
+  w[0] = __byte_perm(t0, t1, 0x5410u);
+  w[1] = __byte_perm(t0, t1, 0x7632u);
+  w[2] = __byte_perm(t2, t3, 0x5410u);
+  w[3] = __byte_perm(t2, t3, 0x7632u);
+}
+template <bool TO_DEVICE>
+__global__ void k_transfer_x4(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int32_t N0, int32_t xq_log,
+                              int64_t n_rows, int n_occ, int coded, int *bad) {
+  const uint32_t W = (uint32_t)N0 >> 4, q4 = (1u << xq_log) >> 2, wpr = (uint32_t)N0 >> 2;  // chunks, Q/4, words per row
+  const int64_t n_chunks = n_rows * W;
+  int flag = 0;
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n_chunks; x += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = x / W;
+    const uint32_t c = (uint32_t)(x - row * W);
+    uint32_t w[4];
+    if (TO_DEVICE) {
+      const uint32_t *sr = src + row * wpr;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) w[b] = sr[c + b * q4];
+      cmx_transpose4x4(w);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) flag |= (int)((w[q] >> (8 * k)) & 0xffu) >= n_occ;
+        if (coded) w[q] = w[q] | ((w[q] & 0x02020202u) << 3);  // 2 -> 18 per byte lane
+      }
+      *reinterpret_cast<uint4 *>(dst + row * wpr + 4 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      const uint4 v = *reinterpret_cast<const uint4 *>(src + row * wpr + 4 * c);
+      w[0] = v.x;
+      w[1] = v.y;
+      w[2] = v.z;
+      w[3] = v.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = (w[q] & 0x07070707u) | ((w[q] >> 3) & 0x03030303u);  // cmx_dec per lane
+      cmx_transpose4x4(w);
+      uint32_t *dr = dst + row * wpr;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dr[c + b * q4] = w[b];
+    }
+  }
+  if (TO_DEVICE && flag) *bad = 1;
+}
+
 // reference layout (no ghost layers, int32 or int8) <-> device layout (int8).
 // Occupant indices are validated on the device (a bad index would read outside
 // the site-function tables): *bad is set when any is out of range.
@@ -224,7 +298,7 @@ __global__ void k_scatter_occ(const SrcT *__restrict__ src, int8_t *dst, Geom g,
     int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
     int v = (int)src[l];
     flag |= (v < 0 || v >= n_occ[b]);
-    dst[b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)cmx_enc(g, v);
+    dst[b * g.sub_stride + g.halo * g.layer + cmx_cell_pos(g, cell)] = (int8_t)cmx_enc(g, v);
   }
   if (flag) *bad = 1;
 }
@@ -258,7 +332,7 @@ __global__ void k_gather_occ(const int8_t *__restrict__ src, DstT *dst, Geom g,
   for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < total;
        l += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = l / g.n_cells, cell = l - b * g.n_cells;
-    dst[l] = (DstT)cmx_dec(src[b * g.sub_stride + g.halo * g.layer + cell]);
+    dst[l] = (DstT)cmx_dec(src[b * g.sub_stride + g.halo * g.layer + cmx_cell_pos(g, cell)]);
   }
 }
 
@@ -278,7 +352,16 @@ static int upload_occ(cmx_state *s, int32_t replica, const T *occ) {
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   int8_t *dst = s->d_occ + (size_t)replica * s->g.rep_stride;
   CMX_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
-  if (sizeof(T) == 1 && s->g.halo == 0 && s->g.n_cells % 16 == 0) {
+  if (sizeof(T) == 1 && s->g.xq_log) {
+    // x4-interleaved rows: the image goes to scratch and is transposed into place
+    rc = cmx_scratch(s, n);
+    if (rc) return rc;
+    CMX_CUDA(cudaMemcpyAsync(s->d_scratch, occ, n, cudaMemcpyHostToDevice, s->stream));
+    k_transfer_x4<true><<<1184, 256, 0, s->stream>>>((const uint32_t *)s->d_scratch,
+                                                     (uint32_t *)(dst + (size_t)s->g.halo * s->g.layer), s->g.N0,
+                                                     s->g.xq_log, (int64_t)s->g.N1 * s->g.N2, s->t->n_occ[0],
+                                                     s->g.coded, s->d_flag);
+  } else if (sizeof(T) == 1 && s->g.halo == 0 && s->g.n_cells % 16 == 0) {
     // device layout == reference layout: one DMA, validated in place.  On a
     // bad index the previous occupation is lost -- the caller gets an error.
     CMX_CUDA(cudaMemcpyAsync(dst, occ, n, cudaMemcpyHostToDevice, s->stream));
@@ -309,15 +392,20 @@ static int download_occ(const cmx_state *cs, int32_t replica, T *occ) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
-  if (sizeof(T) == 1 && s->g.halo == 0 && !s->g.coded) {
+  if (sizeof(T) == 1 && s->g.halo == 0 && !s->g.coded && !s->g.xq_log) {
     CMX_CUDA(cudaMemcpyAsync(occ, src, n, cudaMemcpyDeviceToHost, s->stream));
     CMX_CUDA(cudaStreamSynchronize(s->stream));
     return CMX_OK;
   }
   rc = cmx_scratch(s, n * sizeof(T));
   if (rc) return rc;
-  k_gather_occ<T><<<1184, 256, 0, s->stream>>>(src, (T *)s->d_scratch, s->g,
-                                               s->t->d.n_sublat);
+  if (sizeof(T) == 1 && s->g.xq_log)
+    k_transfer_x4<false><<<1184, 256, 0, s->stream>>>((const uint32_t *)(src + (size_t)s->g.halo * s->g.layer),
+                                                      (uint32_t *)s->d_scratch, s->g.N0, s->g.xq_log,
+                                                      (int64_t)s->g.N1 * s->g.N2, 0, 0, nullptr);
+  else
+    k_gather_occ<T><<<1184, 256, 0, s->stream>>>(src, (T *)s->d_scratch, s->g,
+                                                 s->t->d.n_sublat);
   CMX_CUDA(cudaGetLastError());
   CMX_CUDA(cudaMemcpyAsync(occ, s->d_scratch, n * sizeof(T),
                            cudaMemcpyDeviceToHost, s->stream));
@@ -335,16 +423,24 @@ extern "C" int cmx_state_upload_occ_i8_async(cmx_state *s, int32_t replica, cons
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   int8_t *dst = s->d_occ + (size_t)replica * s->g.rep_stride;
-  if (s->g.halo == 0 && s->g.n_cells % 16 == 0) {
+  if (s->g.xq_log) {
+    rc = cmx_scratch(s, n);
+    if (rc) return rc;
+    CMX_CUDA(cudaMemcpyAsync(s->d_scratch, occ, n, cudaMemcpyHostToDevice, s->stream));
+    k_transfer_x4<true><<<1184, 256, 0, s->stream>>>((const uint32_t *)s->d_scratch,
+                                                     (uint32_t *)(dst + (size_t)s->g.halo * s->g.layer), s->g.N0,
+                                                     s->g.xq_log, (int64_t)s->g.N1 * s->g.N2, s->t->n_occ[0],
+                                                     s->g.coded, s->d_flag + 1);
+  } else if (s->g.halo == 0 && s->g.n_cells % 16 == 0) {
     CMX_CUDA(cudaMemcpyAsync(dst, occ, n, cudaMemcpyHostToDevice, s->stream));
     k_validate_occ16<<<1184, 256, 0, s->stream>>>((int4 *)dst, (int64_t)(n / 16), s->g.n_cells / 16,
-                                                  s->t->d.n_occ, s->g.coded, s->d_flag);
+                                                  s->t->d.n_occ, s->g.coded, s->d_flag + 1);
   } else {
     rc = cmx_scratch(s, n);
     if (rc) return rc;
     CMX_CUDA(cudaMemcpyAsync(s->d_scratch, occ, n, cudaMemcpyHostToDevice, s->stream));
     k_scatter_occ<int8_t><<<1184, 256, 0, s->stream>>>((const int8_t *)s->d_scratch, dst, s->g, s->t->d.n_sublat,
-                                                       s->t->d.n_occ, s->d_flag);
+                                                       s->t->d.n_occ, s->d_flag + 1);
   }
   CMX_CUDA(cudaGetLastError());
   s->async_upload_pending = true;
@@ -358,13 +454,18 @@ extern "C" int cmx_state_download_occ_i8_async(cmx_state *s, int32_t replica, in
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
-  if (s->g.halo == 0 && !s->g.coded) {
+  if (s->g.halo == 0 && !s->g.coded && !s->g.xq_log) {
     CMX_CUDA(cudaMemcpyAsync(occ, src, n, cudaMemcpyDeviceToHost, s->stream));
     return CMX_OK;
   }
   rc = cmx_scratch(s, n);
   if (rc) return rc;
-  k_gather_occ<int8_t><<<1184, 256, 0, s->stream>>>(src, (int8_t *)s->d_scratch, s->g, s->t->d.n_sublat);
+  if (s->g.xq_log)
+    k_transfer_x4<false><<<1184, 256, 0, s->stream>>>((const uint32_t *)(src + (size_t)s->g.halo * s->g.layer),
+                                                      (uint32_t *)s->d_scratch, s->g.N0, s->g.xq_log,
+                                                      (int64_t)s->g.N1 * s->g.N2, 0, 0, nullptr);
+  else
+    k_gather_occ<int8_t><<<1184, 256, 0, s->stream>>>(src, (int8_t *)s->d_scratch, s->g, s->t->d.n_sublat);
   CMX_CUDA(cudaGetLastError());
   CMX_CUDA(cudaMemcpyAsync(occ, s->d_scratch, n, cudaMemcpyDeviceToHost, s->stream));
   return CMX_OK;
@@ -377,8 +478,8 @@ extern "C" int cmx_state_synchronize(cmx_state *s) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   int bad = 0;
   if (s->async_upload_pending) {
-    CMX_CUDA(cudaMemcpyAsync(&bad, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CMX_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
+    CMX_CUDA(cudaMemcpyAsync(&bad, s->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CMX_CUDA(cudaMemsetAsync(s->d_flag + 1, 0, sizeof(int), s->stream));
   }
   CMX_CUDA(cudaStreamSynchronize(s->stream));
   s->async_upload_pending = false;
@@ -416,7 +517,7 @@ __global__ void k_randomize(int8_t *occ, Geom g, int n_sublat, int n_replicas,
                                0x52414e44u, k0, k1);
       v = (int)__umulhi(p.c[0], (uint32_t)no);
     }
-    occ[r * g.rep_stride + b * g.sub_stride + g.halo * g.layer + cell] = (int8_t)cmx_enc(g, v);
+    occ[r * g.rep_stride + b * g.sub_stride + g.halo * g.layer + cmx_cell_pos(g, cell)] = (int8_t)cmx_enc(g, v);
   }
 }
 
@@ -499,17 +600,18 @@ extern "C" int cmx_state_ipc_attach(cmx_state *s, const void *handle_dn, const v
     rc = open_one(handle_up, 2, &s->peer_occ_up, &s->peer_sig_up);
     if (rc) return rc;
   }
-  CMX_CUDA(cudaMemset(s->d_sig, 0, sizeof(unsigned long long) * 4));
-  s->epoch = 0;
-  s->blocks_done = 0;
-  s->published = 0;
+  s->peer_done_dn = reinterpret_cast<uint32_t *>(s->peer_sig_dn + 4);
+  s->peer_done_up = reinterpret_cast<uint32_t *>(s->peer_sig_up + 4);
+  // (the layer counters are NOT reset here: a neighbour that attached first may already
+  // count on them; they are zero from creation and only ever advance in step with
+  // done_even / done_odd)
   s->p2p = true;
   return CMX_OK;
 }
 
 extern "C" int cmx_state_p2p_active(const cmx_state *s, int32_t *active) {
   if (!s || !active) return invalid("cmx_state_p2p_active: null argument");
-  *active = (s->p2p && s->plan.valid && s->plan.pair_lut &&
+  *active = (s->p2p && s->plan.valid && s->plan.pair_lut && s->plan.stream &&
              !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) ? 1 : 0;
   return CMX_OK;
 }
@@ -522,6 +624,7 @@ extern "C" int cmx_state_set_eci(cmx_state *s, int32_t n, const uint32_t *index,
     if (index[i] >= (uint32_t)s->t->d.corr_size)
       return invalid("cmx_state_set_eci: coefficient index out of range");
   CMX_CUDA(cudaSetDevice(s->t->device));
+  CMX_CUDA(cudaStreamSynchronize(s->stream));  // sweeps in flight still read the old coefficients
   cudaFree(s->d_eci_idx);
   cudaFree(s->d_eci_val);
   s->d_eci_idx = nullptr;
@@ -549,9 +652,15 @@ extern "C" int cmx_state_set_conditions(cmx_state *s, int32_t replica,
   s->temperature[replica] = temperature;
   double beta = 1.0 / (CMX_KB * temperature);
   for (size_t i = 0; i < ex; ++i) s->exch[replica * ex + i] = exch ? exch[i] : 0.0;
-  CMX_CUDA(cudaMemcpy(s->d_beta + replica, &beta, sizeof(double), cudaMemcpyHostToDevice));
-  CMX_CUDA(cudaMemcpy(s->d_exch + replica * ex, &s->exch[replica * ex],
-                      sizeof(double) * ex, cudaMemcpyHostToDevice));
+  // s->stream is non-blocking: order the update against sweeps already enqueued on it
+  // (sources are pageable host memory: the copies are staged before they return)
+  CMX_CUDA(cudaMemcpyAsync(s->d_beta + replica, &beta, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CMX_CUDA(cudaMemcpyAsync(s->d_exch + replica * ex, &s->exch[replica * ex],
+                           sizeof(double) * ex, cudaMemcpyHostToDevice, s->stream));
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
+  // the pair-LUT acceptance tables (and the dE - exch table) are functions of (beta, exch)
+  s->plan.thr_dirty = true;
+  s->plan.pdl_ok = false;
   return CMX_OK;
 }
 

@@ -146,6 +146,17 @@ __device__ __forceinline__ void energy_chunk(const EnergyArgs &a, const int8_t *
         }
       }
     }
+    if (g.xq_log) {
+      // x4-interleaved rows: the x neighbors of a word are the words beside it; beyond a
+      // row end lies the row's other end, one byte lane over
+      if (x0 == 0) sm = __funnelshift_l(sm, sm, 8);
+      if (x0 + 16 == N0) sp = __funnelshift_r(sp, sp, 8);
+      cnt[0] = A0[0] + sm + Ap[1];
+      cnt[1] = A0[1] + Am[0] + Ap[2];
+      cnt[2] = A0[2] + Am[1] + Ap[3];
+      cnt[3] = A0[3] + Am[2] + sp;
+      return;
+    }
     cnt[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
     cnt[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
     cnt[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
@@ -315,13 +326,22 @@ __global__ void __launch_bounds__(256) k_energy_row16(EnergyArgs a, uint32_t log
         }
       }
     }
-    const uint32_t sm = any_m ? __shfl_sync(0xffffffffu, Am[3], lane_l) : 0u;
-    const uint32_t sp = any_p ? __shfl_sync(0xffffffffu, Ap[0], lane_r) : 0u;
+    uint32_t sm = any_m ? __shfl_sync(0xffffffffu, Am[3], lane_l) : 0u;
+    uint32_t sp = any_p ? __shfl_sync(0xffffffffu, Ap[0], lane_r) : 0u;
     uint32_t cnt[4];
-    cnt[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
-    cnt[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
-    cnt[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
-    cnt[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
+    if (g.xq_log) {  // x4-interleaved rows, see energy_chunk
+      if (c == 0) sm = __funnelshift_l(sm, sm, 8);
+      if (c == Wm) sp = __funnelshift_r(sp, sp, 8);
+      cnt[0] = A0[0] + sm + Ap[1];
+      cnt[1] = A0[1] + Am[0] + Ap[2];
+      cnt[2] = A0[2] + Am[1] + Ap[3];
+      cnt[3] = A0[3] + Am[2] + sp;
+    } else {
+      cnt[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
+      cnt[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
+      cnt[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
+      cnt[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
+    }
     if (on) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -493,7 +513,8 @@ static int launch_energy_lin(const cmx_state *s, EnergyArgs &a, int nb, int n_re
   const SweepPlan &P = s->plan;
   dim3 grid(nb, n_rep);
   static const bool force_block = getenv("CMX_ENERGY_BLOCK") != nullptr;  // cross-check of the two kernels
-  if (P.row16 && !force_block) {
+  const bool warp_rows = a.W <= 32 && (a.W & (a.W - 1)) == 0;  // a warp owns whole rows
+  if (warp_rows && !force_block) {
     uint32_t logW = 0;
     while ((1u << logW) < a.W) ++logW;
     const uint32_t n_rows = (uint32_t)s->g.N1 * (uint32_t)s->g.N2, rpw = 32u >> logW;

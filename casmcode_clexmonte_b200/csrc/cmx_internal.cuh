@@ -4,7 +4,9 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "cmx_b200.h"
@@ -53,7 +55,19 @@ struct Geom {
   // the pair-LUT sweep -- no per-neighbor masking -- and code & 3 is still the
   // occupant.  cmx_dec() reads both codes.
   int32_t coded;
+  // Row layout.  xq_log == 0: site i of a row is byte i.  xq_log != 0 ("x4-interleaved
+  // rows", N0 = 4 Q, Q = 1 << xq_log): site i is byte 4 (i mod Q) + i div Q, so the 32-bit
+  // word w of a row holds the sites w, w + Q, w + 2Q, w + 3Q.  The x neighbors of a whole
+  // word are then the words left and right of it (no byte shifts), and the sites of a word
+  // share their x colour -- what the streaming pair-LUT sweep (cmx_sweep_stream.cuh) is
+  // built on.  Chosen at creation for single-sublattice states whose N0 is a power of two
+  // in [16, 512]; every kernel addresses sites through cmx_site_offset / cmx_xpos.
+  int32_t xq_log;
 };
+
+__host__ __device__ __forceinline__ int cmx_xpos(const Geom &g, int i) {
+  return g.xq_log ? (((i & ((1 << g.xq_log) - 1)) << 2) | (i >> g.xq_log)) : i;
+}
 
 // occupant index <-> stored byte (see Geom::coded)
 __host__ __device__ __forceinline__ int cmx_dec(int raw) { return (raw & 7) | (raw >> 3); }
@@ -130,14 +144,22 @@ struct SweepPlan {
   uint32_t *d_tab = nullptr;      // [replica][n_tab] threshold(15 bit)<<9 | 1<<8 | proposed code
   uint32_t *d_thr_lo = nullptr;   // [replica][n_tab] low 32 bits of the threshold (tie break)
   double *d_dEpot = nullptr;      // [replica][n_tab] dE - exch
-  bool row16 = false;             // warp-row kernel usable (N0/16 a power of two <= 32)
+  // streaming kernel (cmx_sweep_stream.cuh): x4-interleaved rows
+  bool stream = false;
   int32_t n_tab24 = 0;            // entries of its acceptance table
   uint32_t *d_tab24 = nullptr;    // [replica][n_tab24] thr16 | proposed code << 16
-  bool pdl_ok = false;            // tables untouched since the last sweep launch
-  uint32_t *d_stamps = nullptr;   // fused sweep kernel: updates received per row [replica][N2][N1]
-  uint32_t stamp_base = 0;        // value of every stamp between calls
-  unsigned long long *d_fused_timeout = nullptr;
-  int fused_capacity = -1;        // co-resident blocks of the fused kernel (0: unusable)
+  bool pdl_ok = false;            // (unused by the streaming kernel; kept for set_conditions)
+  struct StreamList {             // the unit order of a call of (n sweeps, kgroup), built once
+    struct StreamUnit *d_units = nullptr;
+    uint32_t n_units = 0;
+    uint32_t min_sep = 0;  // smallest distance (in units) between a unit and one it depends on
+  };
+  std::map<std::pair<int, int>, StreamList> stream_lists;
+  uint32_t *d_ticket = nullptr;   // [replica] group tickets of the streaming kernel (dynamic assignment)
+  int stream_capacity = -1;       // co-resident blocks of the kernel chosen for this state
+  int stream_blocks = 0;          // blocks per replica
+  uint32_t stream_gr = 1;         // row-steps per group
+  uint32_t stream_gap = 0;        // units the host keeps between dependent units
   bool thr_dirty = true;
   // fast energy (cmx_energy.cu): per-cell energy as a function of (occupant,
   // species counts over the cell's "forward" neighbors), same byte-lane counting
@@ -185,16 +207,19 @@ struct cmx_state {
   int *d_flag = nullptr;               // device-side validation flag
   bool async_upload_pending = false;   // an asynchronous upload has not been checked yet
   // slab decomposition over NVLink peer memory (cmx_state_ipc_attach):
-  // d_sig[0] / [1]: epoch reached by my lower / upper ring neighbour (written by
-  // them), [2]: finished blocks of my own sweep launches, [3]: wait timed out
+  // d_sig[3]: a dependency wait timed out ([0..2] unused)
   unsigned long long *d_sig = nullptr;
   bool p2p = false;
   int8_t *peer_occ_dn = nullptr, *peer_occ_up = nullptr;
   unsigned long long *peer_sig_dn = nullptr, *peer_sig_up = nullptr;
   void *ipc_open[4] = {nullptr, nullptr, nullptr, nullptr};  // mappings to close
-  unsigned long long epoch = 0;        // k-group steps completed by this rank
-  unsigned long long blocks_done = 0;  // expected value of d_sig[2]
-  unsigned long long published = 0;    // last epoch announced to the ring neighbours
+  // streaming sweeps: finished row-steps per layer, [replica][N2 + 2] ([0] and [N2+1]: the
+  // ghost layers, counted up by the ring neighbours); lives behind d_sig in one allocation
+  // so that one IPC handle exports both.  done_even / done_odd: the value every even / odd
+  // layer's counter has when no sweep is in flight (all ranks agree: same call sequence)
+  uint32_t *d_done = nullptr;
+  uint32_t *peer_done_dn = nullptr, *peer_done_up = nullptr;
+  uint32_t done_even = 0, done_odd = 0;
   // scratch
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -204,7 +229,6 @@ struct cmx_state {
 int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
 int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps);
-int cmx_slab_publish(cmx_state *s);  // announce a completed, unannounced ring step
 bool cmx_use_warp_generic(const cmx_state *s);  // wide orbit sets: one site per warp
 void cmx_canonical_free(cmx_state *s);
 int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep, bool reset);
@@ -286,7 +310,7 @@ __device__ __forceinline__ int cmx_wrap(int x, int n) {
 __device__ __forceinline__ int64_t cmx_site_offset(const Geom &g, int b, int i,
                                                    int j, int k) {
   return (int64_t)b * g.sub_stride + (int64_t)(k + g.halo) * g.layer +
-         (int64_t)j * g.N0 + i;
+         (int64_t)j * g.N0 + cmx_xpos(g, i);
 }
 
 // neighbor n of cell (i,j,k): byte offset + linear reference index l
@@ -517,13 +541,14 @@ __device__ inline double cmx_eval_function(const DevTables &T, const Geom &g,
 struct Philox {
   uint32_t c[4];
 };
-__device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1,
-                                                uint32_t c2, uint32_t c3,
-                                                uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+__device__ __forceinline__ Philox philox4x32(uint32_t c0, uint32_t c1,
+                                             uint32_t c2, uint32_t c3,
+                                             uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
   const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     uint64_t p0 = (uint64_t)M0 * c0;
     uint64_t p1 = (uint64_t)M1 * c2;
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -545,6 +570,21 @@ __device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1,
   return o;
 }
 
+__device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                uint32_t k0, uint32_t k1) {
+  return philox4x32<10>(c0, c1, c2, c3, k0, k1);
+}
+// The semi-grand checkerboard sweeps draw from Philox4x32-7: seven rounds are the fewest
+// that pass BigCrush ("Crush-resistant", Salmon et al., SC'11, table 2; ten add a safety
+// margin).  The sweep kernels are issue bound and the generator is a third of their
+// instructions; every evaluator of a sweep (streaming, block, generic) uses the same
+// count, so they still agree bit for bit.
+#define CMX_SWEEP_PHILOX_ROUNDS 7
+__device__ __forceinline__ Philox philox_sweep(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+  return philox4x32<CMX_SWEEP_PHILOX_ROUNDS>(c0, c1, c2, c3, k0, k1);
+}
+
 // Same generator with the round keys (k0 + r*W0, k1 + r*W1) taken from a
 // precomputed schedule: when `rk` lives in the kernel parameter (constant) bank
 // the xors read it directly and the 20 key additions per call disappear.
@@ -559,11 +599,12 @@ static inline PhiloxKeys philox_key_schedule(uint32_t k0, uint32_t k1) {
   }
   return s;
 }
-__device__ __forceinline__ Philox philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2,
-                                                   uint32_t c3, const PhiloxKeys &rk) {
+template <int ROUNDS>
+__device__ __forceinline__ Philox philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                uint32_t c3, const PhiloxKeys &rk) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     uint64_t p0 = (uint64_t)M0 * c0;
     uint64_t p1 = (uint64_t)M1 * c2;
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k[2 * r];
@@ -581,4 +622,8 @@ __device__ __forceinline__ Philox philox4x32_10_rk(uint32_t c0, uint32_t c1, uin
   o.c[2] = c2;
   o.c[3] = c3;
   return o;
+}
+__device__ __forceinline__ Philox philox_sweep_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  const PhiloxKeys &rk) {
+  return philox4x32_rk<CMX_SWEEP_PHILOX_ROUNDS>(c0, c1, c2, c3, rk);
 }

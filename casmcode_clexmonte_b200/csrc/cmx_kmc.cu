@@ -655,6 +655,23 @@ __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
             idx = 2 * idx + 1;
           }
         }
+        // Rounding in the residual query can end the descent on a leaf of rate 0 (a
+        // disallowed event; lotto's bifurcate returns the internal node there).  Never
+        // apply such an event: take the nearest leaf that can happen and mark the step
+        // (cmx_kmc_step::pad = 1).
+        int32_t fallback = 0;
+        if (!(leaves[idx] > 0.0)) {
+          fallback = 1;
+          long long lo = idx - 1, hi = idx + 1;
+          const long long n_leaf = A.t.size[0];
+          for (;;) {
+            if (lo >= 0 && leaves[lo] > 0.0) { idx = lo; break; }
+            if (hi < n_leaf && leaves[hi] > 0.0) { idx = hi; break; }
+            --lo;
+            ++hi;
+            if (lo < 0 && hi >= n_leaf) break;  // unreachable: total > 0
+          }
+        }
         ev = idx;
         time = __dadd_rn(time, dt);
         // OccLocation::apply: every site of the event takes its final occupant
@@ -672,7 +689,7 @@ __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
           cmx_kmc_step &L = A.log[(size_t)r * A.log_cap + steps];
           L.unitcell = cell;
           L.prim_event = (int32_t)(ev % A.n_prim);
-          L.pad = 0;
+          L.pad = fallback;
           L.time_increment = dt;
           L.total_rate = total;
         }

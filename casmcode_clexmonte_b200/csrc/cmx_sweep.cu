@@ -46,8 +46,8 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_thr_lo);
   cudaFree(p.d_dEpot);
   cudaFree(p.d_tab24);
-  cudaFree(p.d_stamps);
-  cudaFree(p.d_fused_timeout);
+  for (auto &kv : p.stream_lists) cudaFree(kv.second.d_units);
+  cudaFree(p.d_ticket);
   cudaFree(p.d_part_acc);
   cudaFree(p.d_part_dE);
   cudaFree(p.d_e_lut);
@@ -176,28 +176,7 @@ struct Pair16Args {
   uint32_t sweep_lo;     // RNG counter words
   uint32_t ctr_hi;       // (sweep_hi << 16) | (row colour << 9); bit 8 = x colour, low bits = draw
   int k_offset;          // global k of local layer 0 (slab decomposition)
-  // halo exchange fused into the kernel (cmx_state_ipc_attach): boundary rows are
-  // also stored into the ring neighbours' ghost layers; wait_epoch != 0: do not
-  // read the lattice before both neighbours reached that epoch; signal_epoch != 0:
-  // the last block to finish publishes it to both neighbours
-  int8_t *peer_dn, *peer_up;
-  unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
-  unsigned long long wait_epoch, signal_epoch, blocks_target;
-  int push;
-  // warp-row variant (k_sweep_row16): rows [row_begin, row_begin + n_rows) of the
-  // colour's row sequence (row = kk * J + jj), 32/W rows per warp tile
-  const uint32_t *tab24;  // [replica][CMX_TAB24]
-  uint32_t logW, row_begin, n_tiles;
 };
-
-__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // shared memory is addressed with explicit 32-bit addresses: the dE table sits at
 // a compile-time offset from the acceptance table, so one address serves both
@@ -274,8 +253,8 @@ __device__ __forceinline__ void pair16_ties(const uint32_t (&cnt)[4], const uint
                                             uint32_t r, uint32_t sweep_lo, uint32_t ctr, uint32_t k0,
                                             uint32_t k1, uint32_t &n_acc, double &e_sum) {
   constexpr int NTAB = CMX_TAB16(NOCC);
-  const Philox lo0 = philox4x32_10(gid, r, sweep_lo, ctr | 1u, k0, k1);
-  const Philox lo1 = philox4x32_10(gid, r, sweep_lo, ctr | 2u, k0, k1);
+  const Philox lo0 = philox_sweep(gid, r, sweep_lo, ctr | 1u, k0, k1);
+  const Philox lo1 = philox_sweep(gid, r, sweep_lo, ctr | 2u, k0, k1);
   // the chunk as stored in global memory: it is written back only after both
   // colours, and the occupants of THIS colour's lanes have not changed before
   const uint4 c0 = *chunk0;
@@ -338,17 +317,6 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
   const uint32_t tab = (uint32_t)__cvta_generic_to_shared(sh_tables);
   uint32_t ff;
   asm volatile("mov.u32 %0, 0xFF;" : "=r"(ff));  // opaque to constant propagation, see prmt_imm
-  if (a.wait_epoch && threadIdx.x == 0) {
-    // acquire: the neighbours' pushes into my ghost layers precede their flag
-    const long long t0 = clock64();
-    while (ld_sys(a.my_sig + 0) < a.wait_epoch || ld_sys(a.my_sig + 1) < a.wait_epoch) {
-      if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour is gone
-        a.my_sig[3] = 1ull;
-        break;
-      }
-      __nanosleep(100);
-    }
-  }
   __syncthreads();
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const Geom &g = a.g;
@@ -373,12 +341,11 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
     const uint32_t row = row0 + rl;
     const bool on = lane_on && row < a.n_rows;
     uint32_t C[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0};
-    uint32_t cl = 0, off_c = 0, gid = 0, k_row = 0;
+    uint32_t cl = 0, off_c = 0, gid = 0;
     if (on) {
       uint32_t kk, jj;
       fastdivmod(row, a.divJ, kk, jj);
       const uint32_t j = 2 * jj + a.cy, k = 2 * kk + a.cz;
-      k_row = k;
       off_c = ((k + g.halo) * N1 + j) * N0 + x0;
       gid = ((k + (uint32_t)a.k_offset) * N1 + j) * a.W + c;
       uint32_t dj[3], dk[3];
@@ -443,7 +410,7 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
         if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : 0u, 8);
       }
       const uint32_t ctr0 = a.ctr_hi;
-      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr0, a.rk);
+      const Philox ph = philox_sweep_rk(gid, r, a.sweep_lo, ctr0, a.rk);
       bool tie = false;
       pair16_update<0, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
       if (tie)
@@ -465,7 +432,7 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
         if (mc & 4u) cnt[i] += __funnelshift_r(C[i], (i < 3) ? C[i + 1] : nb, 8);
       }
       const uint32_t ctr1 = a.ctr_hi | 0x100u;
-      const Philox ph = philox4x32_10_rk(gid, r, a.sweep_lo, ctr1, a.rk);
+      const Philox ph = philox_sweep_rk(gid, r, a.sweep_lo, ctr1, a.rk);
       bool tie = false;
       pair16_update<1, NOCC, ACCUM>(cnt, C, ph, tab, ff, n_acc, e_sum, tie);
       if (tie)
@@ -474,16 +441,6 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
                                     n_acc, e_sum);
       const uint4 out = make_uint4(C[0], C[1], C[2], C[3]);
       *reinterpret_cast<uint4 *>(base + off_c) = out;
-      if (a.push) {
-        // my layer 0 is the lower neighbour's upper ghost, my last layer the
-        // upper neighbour's lower ghost (same slab geometry on every rank)
-        const uint32_t kl = k_row;
-        const size_t rep = (size_t)r * g.rep_stride;
-        if (kl == 0)
-          *reinterpret_cast<uint4 *>(a.peer_dn + rep + off_c + N2 * layer) = out;
-        if (kl == N2 - 1)
-          *reinterpret_cast<uint4 *>(a.peer_up + rep + off_c - N2 * layer) = out;
-      }
     }
   }
   // ---- block reduction of the counters (fixed order -> deterministic)
@@ -509,27 +466,46 @@ __global__ void __launch_bounds__(256, MINB) k_sweep_pair16(Pair16Args a) {
     size_t slot = (size_t)r * a.part_stride + blockIdx.x;
     a.part_acc[slot] += A;
     a.part_dE[slot] += E;
-    if (a.push) {
-      // release: every store of this block (ordered before this thread by the
-      // barrier above) is visible system-wide before the block counts as done;
-      // the block that completes the step publishes the epoch to both neighbours
-      __threadfence_system();
-      const unsigned long long done = atomicAdd(a.my_sig + 2, 1ull) + 1ull;
-      if (a.signal_epoch && done == a.blocks_target) {
-        __threadfence_system();
-        st_sys(a.peer_sig_dn + 1, a.signal_epoch);  // I am their upper neighbour
-        st_sys(a.peer_sig_up + 0, a.signal_epoch);  // I am their lower neighbour
-      }
-    }
   }
 }
 
-
-#include "cmx_sweep_row.cuh"
+#include "cmx_sweep_stream.cuh"
 
 // ---------------------------------------------------------------------------
 // generic sweep kernel: one site per thread
 // ---------------------------------------------------------------------------
+// Which random bits the pair-LUT kernels give site i of a row (rng16 mode: the generic
+// evaluator draws the same bits).  One Philox call per (16-byte chunk, x colour) yields
+// four words = eight 16-bit fields [alt:1 | u15:15]; the tie-break words come from the
+// calls with counter | 1 (targets 0..3 of the colour) and | 2 (targets 4..7).
+//   linear rows (k_sweep_pair16):       chunk = i / 16, x = i % 16, target q = x / 2,
+//                                       field = half (x / 2) % 2 of word x / 4
+//   x4-interleaved rows (stream16):     word w = i % Q, byte b = i / Q, chunk = w / 4,
+//                                       h = (w % 4) / 2, target q = 4 h + b,
+//                                       field = half b % 2 of word 2 h + b / 2
+// (the x colour, i % 2 in both layouts, is part of the counter)
+struct Rng16Site {
+  uint32_t chunk, word, half, q;
+};
+__device__ __forceinline__ Rng16Site cmx_rng16_site(const Geom &g, int i) {
+  Rng16Site s;
+  if (g.xq_log) {
+    const uint32_t w = (uint32_t)i & ((1u << g.xq_log) - 1u), b = (uint32_t)i >> g.xq_log;
+    const uint32_t h = (w & 3u) >> 1;
+    s.chunk = w >> 2;
+    s.word = 2u * h + (b >> 1);
+    s.half = b & 1u;
+    s.q = 4u * h + b;
+  } else {
+    const uint32_t x = (uint32_t)i & 15u;
+    s.chunk = (uint32_t)i >> 4;
+    s.word = x >> 2;
+    s.half = (x >> 1) & 1u;
+    s.q = x >> 1;
+  }
+  return s;
+}
+
 struct GenericSweepArgs {
   int8_t *occ;
   Geom g;
@@ -579,15 +555,16 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
     int alt;
     uint32_t u_hi, u_lo;  // rng16: 15 + 32 bit uniform; else 21 + 32 bit
     if (a.rng16) {
-      const uint32_t gid = (uint32_t)(((uint32_t)(k + a.k_offset) * g.N1 + j) * (g.N0 >> 4) + (i >> 4));
-      const uint32_t x = (uint32_t)i & 15u, q = x >> 1;  // lane of the chunk, target index
+      const Rng16Site rs = cmx_rng16_site(g, i);
+      const uint32_t gid = (uint32_t)(((uint32_t)(k + a.k_offset) * g.N1 + j) * (g.N0 >> 4) + rs.chunk);
+      const uint32_t q = rs.q;
       const uint32_t ctr = a.ctr_hi;
-      const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr, a.k0, a.k1);
-      const uint32_t R = ph.c[x >> 2];
-      const uint32_t field = (x & 2u) ? (R >> 16) : (R & 0xFFFFu);
+      const Philox ph = philox_sweep(gid, (uint32_t)r, a.sweep_lo, ctr, a.k0, a.k1);
+      const uint32_t R = ph.c[rs.word];
+      const uint32_t field = rs.half ? (R >> 16) : (R & 0xFFFFu);
       alt = (nocc == 3) ? (int)(field >> 15) : 0;
       u_hi = field & 0x7FFFu;
-      const Philox lo = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr | ((q < 4) ? 1u : 2u), a.k0, a.k1);
+      const Philox lo = philox_sweep(gid, (uint32_t)r, a.sweep_lo, ctr | ((q < 4) ? 1u : 2u), a.k0, a.k1);
       u_lo = lo.c[q & 3];
     } else {
       // global site id -> RNG counter
@@ -719,14 +696,15 @@ __global__ void __launch_bounds__(256) k_sweep_generic_warp(GenericSweepArgs a, 
       int alt;
       uint32_t u_hi, u_lo;
       if (a.rng16) {
-        const uint32_t gid = (uint32_t)(((uint32_t)(k + a.k_offset) * g.N1 + j) * (g.N0 >> 4) + (i >> 4));
-        const uint32_t x = (uint32_t)i & 15u, qq = x >> 1;
-        const Philox ph = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr_hi, a.k0, a.k1);
-        const uint32_t R = ph.c[x >> 2];
-        const uint32_t field = (x & 2u) ? (R >> 16) : (R & 0xFFFFu);
+        const Rng16Site rs = cmx_rng16_site(g, i);
+        const uint32_t gid = (uint32_t)(((uint32_t)(k + a.k_offset) * g.N1 + j) * (g.N0 >> 4) + rs.chunk);
+        const uint32_t qq = rs.q;
+        const Philox ph = philox_sweep(gid, (uint32_t)r, a.sweep_lo, ctr_hi, a.k0, a.k1);
+        const uint32_t R = ph.c[rs.word];
+        const uint32_t field = rs.half ? (R >> 16) : (R & 0xFFFFu);
         alt = (nocc == 3) ? (int)(field >> 15) : 0;
         u_hi = field & 0x7FFFu;
-        const Philox lo = philox4x32_10(gid, (uint32_t)r, a.sweep_lo, ctr_hi | ((qq < 4) ? 1u : 2u), a.k0, a.k1);
+        const Philox lo = philox_sweep(gid, (uint32_t)r, a.sweep_lo, ctr_hi | ((qq < 4) ? 1u : 2u), a.k0, a.k1);
         u_lo = lo.c[qq & 3];
       } else {
         const uint32_t gid_lo = (uint32_t)(((uint64_t)(k + a.k_offset) * g.N1 + j) * g.N0 + i);
@@ -967,8 +945,8 @@ int cmx_plan_sweep(cmx_state *s) {
   // ---- pair-LUT eligibility
   bool ok = (T.n_sublat == 1 && np == 1 && P.mut_points.size() == 1 &&
              t->n_occ[0] >= 2 && t->n_occ[0] <= 3 && T.nlist_len <= 64 &&
-             s->g.N0 % 16 == 0 && s->g.N0 <= 4096 && s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 &&
-             s->g.rep_stride < (int64_t)0xFFFFFFFFll &&
+             s->g.N0 % 16 == 0 && s->g.N0 <= 4096 && s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 && s->g.N2 <= 65534 &&
+             s->g.rep_stride < (int64_t)0x7FFFFFFFll &&
              P.S[0] == 2 && P.S[1] == 2 && P.S[2] == 2);
   std::map<int, std::vector<double>> V;  // neighbor -> V[on][oi][of]
   if (ok) {
@@ -1033,18 +1011,10 @@ int cmx_plan_sweep(cmx_state *s) {
     CMX_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(uint32_t) * P.n_tab * s->n_replicas));
     CMX_CUDA(cudaMalloc((void **)&P.d_thr_lo, sizeof(uint32_t) * P.n_tab * s->n_replicas));
     CMX_CUDA(cudaMalloc((void **)&P.d_dEpot, sizeof(double) * P.n_tab * s->n_replicas));
-    const int W = s->g.N0 / 16;
-    P.row16 = (W <= 32 && (W & (W - 1)) == 0);
+    // x4-interleaved rows: the streaming kernel; linear rows: the block kernel
+    P.stream = s->g.xq_log != 0;
     P.n_tab24 = CMX_TAB24(P.nocc);
     CMX_CUDA(cudaMalloc((void **)&P.d_tab24, sizeof(uint32_t) * P.n_tab24 * s->n_replicas));
-    if (P.row16 && !s->g.halo) {
-      const size_t n_st = (size_t)s->n_replicas * s->g.N1 * s->g.N2;
-      CMX_CUDA(cudaMalloc((void **)&P.d_stamps, sizeof(uint32_t) * n_st));
-      CMX_CUDA(cudaMemset(P.d_stamps, 0, sizeof(uint32_t) * n_st));
-      CMX_CUDA(cudaMalloc((void **)&P.d_fused_timeout, sizeof(unsigned long long)));
-      CMX_CUDA(cudaMemset(P.d_fused_timeout, 0, sizeof(unsigned long long)));
-      P.stamp_base = 0;
-    }
     P.pair_lut = true;
     P.rng16 = true;  // the generic evaluator on this state mirrors the pair16 random bits
     // per step: z neighbor bytes + own byte read, 1 byte written; the FP64
@@ -1092,112 +1062,6 @@ static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool 
   }
 }
 
-template <int NOCC, uint32_t MASK, bool ACC, bool SLAB, bool FULL>
-static int launch_row16_inst2(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
-  auto kern = k_sweep_row16<NOCC, MASK, ACC, SLAB, FULL>;
-  static bool attr_set = false;
-  const size_t bytes = row16_smem_bytes<NOCC>(MASK);
-  if (!attr_set) {
-    CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    attr_set = true;
-  }
-  cfg.dynamicSmemBytes = bytes;
-  CMX_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
-  return CMX_OK;
-}
-template <int NOCC, uint32_t MASK, bool ACC>
-static int launch_row16_inst(const Pair16Args &a, cudaLaunchConfig_t &cfg) {
-  // slabs (a.push): the variant with the ring protocol compiled in
-  if (a.push) return launch_row16_inst2<NOCC, MASK, ACC, true, false>(a, cfg);
-  // the rows divide evenly into warp tiles: no partial tile anywhere
-  const uint32_t rpw = 32u / a.W;
-  return (a.n_rows % rpw == 0) ? launch_row16_inst2<NOCC, MASK, ACC, false, true>(a, cfg)
-                               : launch_row16_inst2<NOCC, MASK, ACC, false, false>(a, cfg);
-}
-template <int NOCC>
-static int launch_row16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum, bool pdl) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(256);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  if (fcc) return accum ? launch_row16_inst<NOCC, kMaskFcc1NN, true>(a, cfg) : launch_row16_inst<NOCC, kMaskFcc1NN, false>(a, cfg);
-  return accum ? launch_row16_inst<NOCC, 0u, true>(a, cfg) : launch_row16_inst<NOCC, 0u, false>(a, cfg);
-}
-
-template <int NOCC, uint32_t MASK, bool ACC>
-static int launch_row16_flat_inst(const Pair16Args &a, uint32_t n_replicas, cudaLaunchConfig_t &cfg) {
-  auto kern = k_sweep_row16_flat<NOCC, MASK, ACC>;
-  static bool attr_set = false;
-  const size_t bytes = row16_smem_bytes<NOCC>(MASK) + (size_t)CMX_TAB24(NOCC) * 4;
-  if (!attr_set) {
-    CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    attr_set = true;
-  }
-  cfg.dynamicSmemBytes = bytes;
-  CMX_CUDA(cudaLaunchKernelEx(&cfg, kern, a, n_replicas));
-  return CMX_OK;
-}
-// replica grids: the tiles of all replicas as one index space over gx blocks
-template <int NOCC>
-static int launch_row16_flat(const Pair16Args &a, uint32_t gx, uint32_t n_replicas, cudaStream_t st, bool fcc,
-                             bool accum, bool pdl) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(gx);
-  cfg.blockDim = dim3(256);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  if (fcc)
-    return accum ? launch_row16_flat_inst<NOCC, kMaskFcc1NN, true>(a, n_replicas, cfg)
-                 : launch_row16_flat_inst<NOCC, kMaskFcc1NN, false>(a, n_replicas, cfg);
-  return accum ? launch_row16_flat_inst<NOCC, 0u, true>(a, n_replicas, cfg)
-               : launch_row16_flat_inst<NOCC, 0u, false>(a, n_replicas, cfg);
-}
-
-// whole sweeps in one cooperative launch (k_sweep_row16_coop); *capacity: co-resident blocks
-template <int NOCC, uint32_t MASK, bool ACC, bool SLAB>
-static int launch_row16_coop_inst2(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, int *capacity) {
-  auto kern = k_sweep_row16_coop<NOCC, MASK, ACC, SLAB>;
-  static int cap = -1;
-  const size_t bytes = row16_smem_bytes<NOCC>(MASK);
-  if (cap < 0) {
-    CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    int per_sm = 0, dev = 0, sms = 0, can = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, bytes) != cudaSuccess) per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
-    cap = can ? per_sm * sms : 0;
-  }
-  *capacity = cap;
-  if ((long long)grid.x * grid.y > cap) return -1;
-  void *args[2] = {&a, &c};
-  CMX_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(256), args, bytes, st));
-  return CMX_OK;
-}
-template <int NOCC, uint32_t MASK, bool ACC>
-static int launch_row16_coop_inst(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, int *capacity) {
-  return a.push ? launch_row16_coop_inst2<NOCC, MASK, ACC, true>(a, c, grid, st, capacity)
-                : launch_row16_coop_inst2<NOCC, MASK, ACC, false>(a, c, grid, st, capacity);
-}
-template <int NOCC>
-static int launch_row16_coop(Pair16Args &a, CoopArgs &c, dim3 grid, cudaStream_t st, bool fcc, bool accum,
-                             int *capacity) {
-  if (fcc)
-    return accum ? launch_row16_coop_inst<NOCC, kMaskFcc1NN, true>(a, c, grid, st, capacity)
-                 : launch_row16_coop_inst<NOCC, kMaskFcc1NN, false>(a, c, grid, st, capacity);
-  return accum ? launch_row16_coop_inst<NOCC, 0u, true>(a, c, grid, st, capacity)
-               : launch_row16_coop_inst<NOCC, 0u, false>(a, c, grid, st, capacity);
-}
-
 // tuning knobs (environment, read once)
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
@@ -1209,14 +1073,6 @@ static int pair16_minb() {  // resident blocks per SM k_sweep_pair16 is compiled
 }
 static int sweep_grid_per_sm() {  // blocks per SM in the grid
   static int v = env_int("CMX_SWEEP_BLOCKS_PER_SM", 3);
-  return v;
-}
-static int sweep_pdl() {  // programmatic dependent launch of consecutive colour passes
-  static int v = env_int("CMX_SWEEP_PDL", 1);
-  return v;
-}
-static int sweep_l2_mb() {  // lattice bytes (MB) a k-slice of the fused sweep kernel may touch
-  static int v = env_int("CMX_SWEEP_L2_MB", 40);
   return v;
 }
 
@@ -1231,25 +1087,7 @@ bool cmx_use_warp_generic(const cmx_state *s) {
 static bool use_pair(const cmx_state *s) {
   return s->plan.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC);
 }
-static bool use_row16(const cmx_state *s) {
-  return use_pair(s) && s->plan.row16 && !(s->sweep_flags & CMX_SWEEP_BLOCK_KERNEL);
-}
-
-// replica grids on the warp-row kernel: one flat tile space (k_sweep_row16_flat) when a
-// block's share of it stays within two replicas
-static uint32_t row16_tiles_per_replica(const cmx_state *s) {
-  const uint32_t W = s->g.N0 / 16, rpw = 32 / W;
-  const uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
-  return (n_rows + rpw - 1) / rpw;
-}
-static uint32_t row16_flat_blocks(const cmx_state *s) {  // 0: not applicable
-  static int off = env_int("CMX_SWEEP_NO_FLAT", 0);
-  if (off || !use_row16(s) || s->n_replicas < 2 || s->g.halo) return 0;
-  const unsigned long long T = (unsigned long long)row16_tiles_per_replica(s) * s->n_replicas;
-  const uint32_t gx = (uint32_t)std::min<unsigned long long>(148ull * sweep_grid_per_sm(), (T + 7) / 8);
-  if (gx < (uint32_t)s->n_replicas) return 0;  // a block would span more than two replicas
-  return gx;
-}
+static bool use_stream(const cmx_state *s) { return use_pair(s) && s->plan.stream; }
 
 static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
   int want = (int)((items + 255) / 256);
@@ -1259,23 +1097,28 @@ static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
   return std::max(1, std::min(want, cap));
 }
 
-// acceptance tables (rebuilt when the conditions changed) and the arguments every
-// pair-LUT kernel shares
-static int pair_args(cmx_state *s, uint64_t seed, int64_t sweep, int k_offset, Pair16Args &a) {
+// acceptance tables of the pair-LUT kernels, rebuilt when ECI or conditions changed
+static int pair_tables(cmx_state *s) {
   SweepPlan &P = s->plan;
   const DevTables &T = s->t->d;
+  if (!P.thr_dirty) return CMX_OK;
+  const size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
+  dim3 grid((P.n_tab + 127) / 128, s->n_replicas);
+  k_build_tab16<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.nocc, P.z, T.max_occ, s->d_beta, s->d_exch,
+                                             (int)exs, P.n_tab, P.d_tab, P.d_thr_lo, P.d_dEpot);
+  dim3 grid24((P.n_tab24 + 127) / 128, s->n_replicas);
+  k_build_tab24<<<grid24, 128, 0, s->stream>>>(P.d_tab, P.nocc, P.n_tab, P.n_tab24, P.d_tab24);
+  CMX_CUDA(cudaGetLastError());
+  P.thr_dirty = false;
+  return CMX_OK;
+}
+
+// arguments of the block kernel
+static int pair_args(cmx_state *s, uint64_t seed, int64_t sweep, int k_offset, Pair16Args &a) {
+  SweepPlan &P = s->plan;
   const Geom &g = s->g;
-  size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
-  if (P.thr_dirty) {
-    dim3 grid((P.n_tab + 127) / 128, s->n_replicas);
-    k_build_tab16<<<grid, 128, 0, s->stream>>>(P.d_pair_dE, P.nocc, P.z, T.max_occ, s->d_beta, s->d_exch,
-                                               (int)exs, P.n_tab, P.d_tab, P.d_thr_lo, P.d_dEpot);
-    dim3 grid24((P.n_tab24 + 127) / 128, s->n_replicas);
-    k_build_tab24<<<grid24, 128, 0, s->stream>>>(P.d_tab, P.nocc, P.n_tab, P.n_tab24, P.d_tab24);
-    CMX_CUDA(cudaGetLastError());
-    P.thr_dirty = false;
-    P.pdl_ok = false;
-  }
+  int rc = pair_tables(s);
+  if (rc) return rc;
   a.occ = s->d_occ;
   a.g = g;
   a.mask = P.mask;
@@ -1286,7 +1129,6 @@ static int pair_args(cmx_state *s, uint64_t seed, int64_t sweep, int k_offset, P
   a.divJ = make_fastdiv(a.J);
   a.n_rows = a.J * (uint32_t)(g.N2 / 2);
   a.tab = P.d_tab;
-  a.tab24 = P.d_tab24;
   a.thr_lo = P.d_thr_lo;
   a.dEpot = P.d_dEpot;
   a.part_acc = P.d_part_acc;
@@ -1299,149 +1141,357 @@ static int pair_args(cmx_state *s, uint64_t seed, int64_t sweep, int k_offset, P
   a.ctr_hi = 0;
   a.cy = a.cz = 0;
   a.k_offset = k_offset;
+  return CMX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// streaming kernel: schedule and launch
+// ---------------------------------------------------------------------------
+typedef void (*StreamKernel)(S16Args);
+template <int NOCC, uint32_t MASK, bool FULL>
+static StreamKernel stream_kernel_nmf(bool accum, bool slab) {
+  if (accum) return slab ? k_sweep_stream16<NOCC, MASK, true, true, FULL> : k_sweep_stream16<NOCC, MASK, true, false, FULL>;
+  return slab ? k_sweep_stream16<NOCC, MASK, false, true, FULL> : k_sweep_stream16<NOCC, MASK, false, false, FULL>;
+}
+template <int NOCC, uint32_t MASK>
+static StreamKernel stream_kernel_nm(bool accum, bool slab, bool full) {
+  return full ? stream_kernel_nmf<NOCC, MASK, true>(accum, slab) : stream_kernel_nmf<NOCC, MASK, false>(accum, slab);
+}
+static StreamKernel stream_kernel(const cmx_state *s, bool accum, bool slab, size_t *smem) {
+  const SweepPlan &P = s->plan;
+  const bool fcc = (P.mask == kMaskFcc1NN);
+  // the rows of one colour of a layer divide evenly into row-steps: no partial row-step
+  const uint32_t rpw = 32u / ((uint32_t)s->g.N0 / 16u);
+  const bool full = ((uint32_t)s->g.N1 / 2u) % rpw == 0;
+  if (P.nocc == 3) {
+    *smem = s16_smem_bytes<3>(fcc ? kMaskFcc1NN : 0u);
+    return fcc ? stream_kernel_nm<3, kMaskFcc1NN>(accum, slab, full) : stream_kernel_nm<3, 0u>(accum, slab, full);
+  }
+  *smem = s16_smem_bytes<2>(fcc ? kMaskFcc1NN : 0u);
+  return fcc ? stream_kernel_nm<2, kMaskFcc1NN>(accum, slab, full) : stream_kernel_nm<2, 0u>(accum, slab, full);
+}
+
+// geometry of the schedule: row-steps per unit, blocks per replica, row-steps per group,
+// and the distance (in units) the list keeps between dependent units
+static int stream_geometry(cmx_state *s) {
+  SweepPlan &P = s->plan;
+  const Geom &g = s->g;
+  const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
+  const bool slab = s->p2p && g.halo;
+  size_t smem = 0;
+  StreamKernel kern = stream_kernel(s, accum, slab, &smem);
+  CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0, dev = 0, sms = 0, can = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess) per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
+  per_sm = std::min(per_sm, std::max(sweep_grid_per_sm(), CMX_S16_MINB));
+  P.stream_capacity = can ? per_sm * sms : 0;
+  if (P.stream_capacity < s->n_replicas) {
+    cmx_set_error("streaming sweep: the replicas do not fit a co-resident grid on this device");
+    return CMX_ERR_UNSUPPORTED;
+  }
+  const uint32_t W = (uint32_t)g.N0 / 16, rpw = 32u / W, J = (uint32_t)g.N1 / 2, H = (uint32_t)g.N2 / 2;
+  const uint32_t tpu = (J + rpw - 1) / rpw;
+  // at least ~4 row-steps per warp and sweep, at most the co-resident share of a replica
+  const uint32_t want = std::max(1u, (4u * H * tpu + 31u) / 32u);
+  P.stream_blocks = (int)std::min<uint32_t>((uint32_t)(P.stream_capacity / s->n_replicas), want);
+  static const int gr_env = env_int("CMX_STREAM_GR", 0);
+  auto gap_for = [&](uint32_t gr) {
+    // units in flight.  The warps advance in rounds (group g, then g + n_warps): a unit is
+    // checked while its warp still works on the previous round, so what it depends on must
+    // lie two rounds back to be complete at that time
+    const uint32_t window = ((uint32_t)P.stream_blocks * 8u * gr + tpu - 1) / tpu + 1u;
+    // (measured, 512^3: 3 windows cost 1.6x the algorithmic DRAM traffic -- the wavefront no
+    // longer fits L2 -- for no gain in time; 2 windows: 1.1x)
+    return 2u * window + 6u;
+  };
+  uint32_t gr = (tpu % 4 == 0 && gap_for(4) <= H) ? 4u : ((tpu % 2 == 0 && gap_for(2) <= H) ? 2u : 1u);
+  if (gr_env > 0 && tpu % (uint32_t)gr_env == 0) gr = (uint32_t)gr_env;
+  P.stream_gr = gr;
+  static const int gap_env = env_int("CMX_STREAM_GAP", 0);
+  P.stream_gap = gap_env > 0 ? (uint32_t)gap_env : gap_for(gr);
+  return CMX_OK;
+}
+
+// Order of the units of a call: n sweeps, k colour group kg (-1: both).  Phases of a
+// sweep: 0/1 = even layers 2t, row colour 0/1; 2/3 = odd layers 2t+1, row colour 0/1.
+// True dependencies (they make the order a topological one; on the device the layer
+// counters enforce them):
+//   (0, t, s) <- (3, t-1, s-1), (3, t, s-1)      (1, t, s) <- (0, t, s)
+//   (2, t, s) <- (1, t, s), (1, t+1, s)          (3, t, s) <- (2, t, s)          (t mod H)
+// List scheduling: units are emitted in the order of a helix key (the wavefront: phase p
+// of layer pair t at step s H + t + p D), but never sooner than `gap` positions after the
+// units they depend on -- then the warps that take a unit find its dependencies complete.
+// Where the key order would violate that (the seam of the periodic box: layer 0 of sweep
+// s+1 follows the last odd layer of sweep s) other ready units fill in.
+struct HostUnit {
+  int s, ph, t;
+};
+static void stream_order(int H, int n_sweeps, int kg, int gap, std::vector<HostUnit> &out, uint32_t *min_sep) {
+  const int nph = 4;
+  const long long total = (long long)n_sweeps * nph * H;
+  auto id_of = [&](int s, int ph, int t) { return ((long long)s * nph + ph) * H + t; };
+  auto present = [&](int ph) { return kg < 0 || (ph >> 1) == kg; };
+  const int D = std::max(1, gap / (kg < 0 ? 4 : 2) + 1);
+  const int lag[4] = {0, D, kg < 0 ? 2 * D + 1 : 0, kg < 0 ? 3 * D + 1 : D};
+  std::vector<int> emit(total, -1), ndep(total, 0);
+  std::vector<long long> ready(total, 0);
+  auto deps = [&](int s, int ph, int t, long long (&d)[2]) -> int {
+    int n = 0;
+    if (ph == 0) {
+      if (s > 0 && present(3)) {
+        d[n++] = id_of(s - 1, 3, (t + H - 1) % H);
+        if (H > 1) d[n++] = id_of(s - 1, 3, t);
+      }
+    } else if (ph == 1) {
+      d[n++] = id_of(s, 0, t);
+    } else if (ph == 2) {
+      if (present(1)) {
+        d[n++] = id_of(s, 1, t);
+        if (H > 1) d[n++] = id_of(s, 1, (t + 1) % H);
+      }
+    } else {
+      d[n++] = id_of(s, 2, t);
+    }
+    return n;
+  };
+  std::vector<long long> cand;
+  long long n_present = 0;
+  for (int s = 0; s < n_sweeps; ++s)
+    for (int ph = 0; ph < nph; ++ph) {
+      if (!present(ph)) continue;
+      for (int t = 0; t < H; ++t) {
+        long long d[2];
+        const long long id = id_of(s, ph, t);
+        ndep[id] = deps(s, ph, t, d);
+        if (ndep[id] == 0) cand.push_back(id);
+        ++n_present;
+      }
+    }
+  std::vector<long long> keys(total);
+  for (int s = 0; s < n_sweeps; ++s)
+    for (int ph = 0; ph < nph; ++ph)
+      for (int t = 0; t < H; ++t) keys[id_of(s, ph, t)] = (long long)s * H + t + lag[ph];
+  auto key_of = [&](long long id) { return keys[id]; };
+  out.clear();
+  out.reserve(n_present);
+  long long sep = n_present + 1;
+  for (long long pos = 0; pos < n_present; ++pos) {
+    // ready units: smallest key; none ready: the one that becomes ready first
+    size_t best = 0;
+    bool best_ready = false;
+    long long best_key = 0, best_when = 0;
+    for (size_t c = 0; c < cand.size(); ++c) {
+      const long long id = cand[c], when = ready[id], key = key_of(id);
+      const bool is_ready = when <= pos;
+      bool better;
+      if (c == 0) better = true;
+      else if (is_ready != best_ready) better = is_ready;
+      else if (is_ready) better = key < best_key || (key == best_key && id < cand[best]);
+      else better = when < best_when || (when == best_when && key < best_key);
+      if (better) {
+        best = c;
+        best_ready = is_ready;
+        best_key = key;
+        best_when = when;
+      }
+    }
+    const long long id = cand[best];
+    cand[best] = cand.back();
+    cand.pop_back();
+    emit[id] = (int)pos;
+    const int t = (int)(id % H), ph = (int)((id / H) % nph), s = (int)(id / ((long long)H * nph));
+    out.push_back({s, ph, t});
+    {
+      long long d[2];
+      const int nd = deps(s, ph, t, d);
+      for (int q = 0; q < nd; ++q) sep = std::min(sep, pos - (long long)emit[d[q]]);
+    }
+    // dependents
+    auto release = [&](int s2, int ph2, int t2) {
+      if (s2 >= n_sweeps || !present(ph2)) return;
+      const long long id2 = id_of(s2, ph2, t2);
+      ready[id2] = std::max(ready[id2], pos + gap);
+      if (--ndep[id2] == 0) cand.push_back(id2);
+    };
+    if (ph == 0) release(s, 1, t);
+    else if (ph == 1) {
+      release(s, 2, t);
+      if (H > 1) release(s, 2, (t + H - 1) % H);
+    } else if (ph == 2) release(s, 3, t);
+    else {
+      release(s + 1, 0, t);
+      if (H > 1) release(s + 1, 0, (t + 1) % H);
+    }
+  }
+  *min_sep = (uint32_t)std::min<long long>(sep, 0x7fffffff);
+}
+
+#define CMX_STREAM_MAX_SWEEPS 32  // sweeps per launch (bounds the cached unit lists)
+
+static int stream_list(cmx_state *s, int n_sweeps, int kg, const SweepPlan::StreamList **out) {
+  SweepPlan &P = s->plan;
+  const Geom &g = s->g;
+  const bool push = s->p2p && g.halo;
+  const std::pair<int, int> key(n_sweeps, (kg + 1) * 2 + (push ? 1 : 0));
+  auto it = P.stream_lists.find(key);
+  if (it != P.stream_lists.end()) {
+    *out = &it->second;
+    return CMX_OK;
+  }
+  const int H = g.N2 / 2;
+  const uint32_t W = (uint32_t)g.N0 / 16, rpw = 32u / W, J = (uint32_t)g.N1 / 2;
+  const uint32_t tpu = (J + rpw - 1) / rpw;
+  std::vector<HostUnit> order;
+  uint32_t min_sep = 0;
+  stream_order(H, n_sweeps, kg, (int)P.stream_gap, order, &min_sep);
+  std::vector<StreamUnit> units(order.size());
+  for (size_t q = 0; q < order.size(); ++q) {
+    const HostUnit &u = order[q];
+    const int cz = u.ph >> 1, cy = u.ph & 1;
+    const int k = 2 * u.t + cz;
+    StreamUnit &d = units[q];
+    uint32_t flags = 0;
+    if (cy == 0) {
+      flags = CMX_S16_DEP_LO | CMX_S16_DEP_HI;
+      // ghost layers nobody counts up (slabs whose halo is exchanged by the host)
+      if (g.halo && !push) {
+        if (k == 0) flags &= ~CMX_S16_DEP_LO;
+        if (k == g.N2 - 1) flags &= ~CMX_S16_DEP_HI;
+      }
+      // the other k colour: all of the previous sweep (even layers) / of this sweep (odd)
+      d.need_rel = (kg < 0) ? (uint32_t)(2 * u.s + 2 * cz) * tpu : 0u;
+      d.base_sel = cz ? 0u : 1u;
+    } else {
+      flags = CMX_S16_DEP_OWN;
+      d.need_rel = (uint32_t)(2 * u.s + 1) * tpu;
+      d.base_sel = cz ? 1u : 0u;
+    }
+    d.kf = (uint32_t)k | flags | ((uint32_t)(cz * 2 + cy) << CMX_S16_COLOUR_SHIFT);
+    d.sweep_rel = (uint32_t)u.s;
+  }
+  SweepPlan::StreamList L;
+  L.n_units = (uint32_t)units.size();
+  L.min_sep = min_sep;
+  CMX_CUDA(cudaMalloc((void **)&L.d_units, sizeof(StreamUnit) * std::max<size_t>(1, units.size())));
+  CMX_CUDA(cudaMemcpy(L.d_units, units.data(), sizeof(StreamUnit) * units.size(), cudaMemcpyHostToDevice));
+  auto ins = P.stream_lists.emplace(key, L);
+  *out = &ins.first->second;
+  return CMX_OK;
+}
+
+// n_sweeps sweeps (k colour group kg, -1 = whole sweeps) as cooperative launches of the
+// streaming kernel on the state's stream
+static int sweep_stream(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps, int kg) {
+  SweepPlan &P = s->plan;
+  const Geom &g = s->g;
+  int rc = pair_tables(s);
+  if (rc) return rc;
+  const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
+  const bool slab = s->p2p && g.halo;
+  size_t smem = 0;
+  StreamKernel kern = stream_kernel(s, accum, slab, &smem);
+  S16Args a;
+  a.occ = s->d_occ;
+  a.g = g;
+  a.mask = P.mask;
+  a.W = (uint32_t)g.N0 / 16;
   a.logW = 0;
   while ((1u << a.logW) < a.W) ++a.logW;
-  a.row_begin = 0;
-  a.n_tiles = 0;
-  a.push = (s->p2p && g.halo) ? 1 : 0;
+  a.J = (uint32_t)g.N1 / 2;
+  const uint32_t rpw = 32u / a.W;
+  a.tpu = (a.J + rpw - 1) / rpw;
+  a.gr = P.stream_gr;
+  const uint32_t gpu = (a.tpu + a.gr - 1) / a.gr;
+  a.div_gpu = make_fastdiv(gpu);
+  a.tab24 = P.d_tab24;
+  a.thr_lo = P.d_thr_lo;
+  a.dEpot = P.d_dEpot;
+  a.part_acc = P.d_part_acc;
+  a.part_dE = P.d_part_dE;
+  a.part_stride = (uint32_t)P.part_blocks;
+  a.k0 = (uint32_t)seed;
+  a.k1 = (uint32_t)(seed >> 32);
+  a.rk = philox_key_schedule(a.k0, a.k1);
+  a.k_offset = s->k_offset;
+  a.wrap_j = (g.N1 - 1) * g.N0;
+  a.layer = g.N0 * g.N1;
+  a.wrap_k = (g.N2 - 1) * a.layer;
+  a.step_pc = (int32_t)(2u * rpw) * g.N0;
+  a.step_j = (int32_t)(2u * rpw);
+  a.step_gid = 2u * rpw * a.W;
+  a.done = s->d_done;
+  a.done_stride = (uint32_t)g.N2 + 2u;
   a.peer_dn = s->peer_occ_dn;
   a.peer_up = s->peer_occ_up;
-  a.my_sig = s->d_sig;
-  a.peer_sig_dn = s->peer_sig_dn;
-  a.peer_sig_up = s->peer_sig_up;
-  a.wait_epoch = a.signal_epoch = a.blocks_target = 0;
-  return CMX_OK;
-}
-
-// ---- fused whole-sweep kernel (k_sweep_row16_fused) ------------------------------
-template <int NOCC>
-static const void *fused_kernel(bool fcc, bool accum) {
-  if (fcc) return accum ? (const void *)k_sweep_row16_fused<NOCC, kMaskFcc1NN, true>
-                        : (const void *)k_sweep_row16_fused<NOCC, kMaskFcc1NN, false>;
-  return accum ? (const void *)k_sweep_row16_fused<NOCC, 0u, true>
-               : (const void *)k_sweep_row16_fused<NOCC, 0u, false>;
-}
-
-// grid of the fused kernel: blocks per replica, or 0 if the replicas do not fit a
-// co-resident grid (the stamp protocol needs every warp resident)
-static int fused_blocks(cmx_state *s, const void *kern) {
-  SweepPlan &P = s->plan;
-  if (P.fused_capacity < 0) {
-    int per_sm = 0, dev = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess) per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int coop = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    P.fused_capacity = coop ? std::min(per_sm, sweep_grid_per_sm()) * sms : 0;
-  }
-  int per = P.fused_capacity / std::max(1, s->n_replicas);
-  return std::min(per, P.part_blocks);
-}
-
-// colour layers per k-slice: a slice spans ~1.5x the tiles in flight (dependencies are
-// then normally satisfied long before they are needed), within the L2 budget
-static uint32_t fused_slice_layers(const cmx_state *s, int gx) {
-  const uint32_t W = (uint32_t)s->g.N0 / 16, rpw = 32u / W, J = (uint32_t)s->g.N1 / 2;
-  const uint32_t tpl = (J + rpw - 1) / rpw, n_kk = (uint32_t)(s->g.N2 / 2);
-  static int slice_env = env_int("CMX_SWEEP_SLICE_LAYERS", 0);
-  if (slice_env > 0) return std::min<uint32_t>((uint32_t)slice_env, n_kk);
-  uint32_t L = (uint32_t)std::ceil(1.5 * 8.0 * gx / tpl);
-  const double per_layer = (double)s->g.layer * s->n_replicas;
-  const uint32_t L_l2 =
-      (uint32_t)std::max(1.0, std::floor((sweep_l2_mb() * 1048576.0 / per_layer - 1.0) / 2.0));
-  return std::max(1u, std::min(std::min(L, L_l2), n_kk));
-}
-
-static bool use_fused(const cmx_state *s) {
-  return use_row16(s) && !s->g.halo && s->plan.d_stamps && (s->sweep_flags & CMX_SWEEP_FUSED);
-}
-
-// n_sweeps whole sweeps in one cooperative launch; returns -1 if not applicable
-static int sweep_fused(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps) {
-  SweepPlan &P = s->plan;
-  Pair16Args a;
-  int rc = pair_args(s, seed, first_sweep, 0, a);
-  if (rc) return rc;
-  const bool fcc = (P.mask == kMaskFcc1NN);
-  const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
-  const void *kern = (P.nocc == 3) ? fused_kernel<3>(fcc, accum) : fused_kernel<2>(fcc, accum);
-  const int gx = fused_blocks(s, kern);
-  if (gx < 1) return -1;
-  FusedArgs f;
-  f.stamps = P.d_stamps;
-  f.timeout = P.d_fused_timeout;
-  f.n_kk = (uint32_t)(s->g.N2 / 2);
-  const uint32_t rpw = 32u / a.W;
-  f.tpl = (a.J + rpw - 1) / rpw;
-  const uint32_t L = fused_slice_layers(s, gx);
-  f.L = L;
-  const uint32_t n_s = (f.n_kk + L - 1) / L;
-  f.n_slices = n_s + ((f.n_kk % L == 0) ? 1 : 0);  // closing slice: the last odd layer
-  f.n_tiles_sweep = f.n_slices * 4 * L * f.tpl;
+  a.peer_done_dn = s->peer_done_dn;
+  a.peer_done_up = s->peer_done_up;
+  a.push = slab ? 1 : 0;
+  a.fail = s->d_sig + 3;
+  static const int dbg_env = env_int("CMX_STREAM_DEBUG", 0);
+  a.dbg = (uint32_t)dbg_env;
+  dim3 grid((unsigned)P.stream_blocks, (unsigned)s->n_replicas);
   for (int64_t done = 0; done < n_sweeps;) {
-    // stamps are 32-bit update counts compared with wrap-around arithmetic: bound a launch
-    const int64_t n = std::min<int64_t>(n_sweeps - done, 1 << 20);
-    f.stamp_base = P.stamp_base;
-    f.n_sweeps = (uint32_t)n;
-    f.first_sweep = (uint64_t)(first_sweep + done);
-    void *args[2] = {&a, &f};
-    CMX_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gx, s->n_replicas), dim3(256), args, 0, s->stream));
-    P.stamp_base += (uint32_t)n;
-    done += n;
-  }
-  P.pdl_ok = false;
-  return CMX_OK;
-}
-
-// n_sweeps whole sweeps in one cooperative launch; -1 if not applicable (not the warp-row
-// kernel, or the grid is not co-resident)
-static int sweep_coop(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps) {
-  SweepPlan &P = s->plan;
-  if (!use_row16(s) || n_sweeps <= 0) return -1;
-  Pair16Args a;
-  int rc = pair_args(s, seed, first_sweep, s->k_offset, a);
-  if (rc) return rc;
-  const uint32_t n_kk = (uint32_t)(s->g.N2 / 2);
-  a.row_begin = 0;
-  a.n_rows = n_kk * a.J;
-  const uint32_t rpw = 32u / a.W;
-  a.n_tiles = (a.n_rows + rpw - 1) / rpw;
-  dim3 grid(std::min<uint32_t>((uint32_t)P.part_blocks, (a.n_tiles + 7) / 8), s->n_replicas);
-  const bool fcc = (P.mask == kMaskFcc1NN);
-  const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
-  for (int64_t done = 0; done < n_sweeps;) {
-    const int64_t n = std::min<int64_t>(n_sweeps - done, 1 << 20);
-    CoopArgs c;
-    c.n_sweeps = (uint32_t)n;
-    c.first_sweep = (unsigned long long)(first_sweep + done);
-    c.epoch0 = s->epoch;
-    int cap = 0;
-    rc = (P.nocc == 3) ? launch_row16_coop<3>(a, c, grid, s->stream, fcc, accum, &cap)
-                       : launch_row16_coop<2>(a, c, grid, s->stream, fcc, accum, &cap);
-    if (rc) return rc;  // -1: grid not co-resident
-    if (a.push) {
-      s->epoch += 2ull * (unsigned long long)n;
-      s->published = s->epoch;
+    const int n = (int)std::min<int64_t>(n_sweeps - done, CMX_STREAM_MAX_SWEEPS);
+    const SweepPlan::StreamList *L = nullptr;
+    if ((rc = stream_list(s, n, kg, &L))) return rc;
+    a.units = L->d_units;
+    a.n_groups = L->n_units * gpu;
+    // block-combined completion counts need dependent groups at least a block-iteration apart
+    a.agg = ((unsigned long long)L->min_sep * gpu >= 8ull && !(a.dbg & 8u)) ? 1u : 0u;
+    // dynamic assignment by default (measured +4 % at 512^3, and robust against SMs of
+    // unequal speed); CMX_STREAM_TICKET=0: static round robin with block-combined counts
+    static const int ticket_env = env_int("CMX_STREAM_TICKET", 1);
+    a.ticket = nullptr;
+    if (ticket_env) {
+      if (!P.d_ticket) CMX_CUDA(cudaMalloc((void **)&P.d_ticket, sizeof(uint32_t) * s->n_replicas));
+      CMX_CUDA(cudaMemsetAsync(P.d_ticket, 0, sizeof(uint32_t) * s->n_replicas, s->stream));
+      a.ticket = P.d_ticket;
+      a.agg = 0;
     }
+    a.first_sweep = (unsigned long long)(first_sweep + done);
+    a.base[0] = s->done_even;
+    a.base[1] = s->done_odd;
+    static const int trace_env = env_int("CMX_STREAM_TRACE", 0);
+    a.trace = nullptr;
+    if (trace_env) {
+      CMX_CUDA(cudaMalloc((void **)&a.trace, sizeof(uint32_t) * 2 * L->n_units));
+      CMX_CUDA(cudaMemsetAsync(a.trace, 0, sizeof(uint32_t) * 2 * L->n_units, s->stream));
+    }
+    void *args[1] = {&a};
+    CMX_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(256), args, smem, s->stream));
+    if (trace_env) {  // diagnostics: which units made their groups wait
+      std::vector<uint32_t> tr(2 * (size_t)L->n_units);
+      std::vector<StreamUnit> un(L->n_units);
+      CMX_CUDA(cudaStreamSynchronize(s->stream));
+      CMX_CUDA(cudaMemcpy(tr.data(), a.trace, sizeof(uint32_t) * tr.size(), cudaMemcpyDeviceToHost));
+      CMX_CUDA(cudaMemcpy(un.data(), L->d_units, sizeof(StreamUnit) * un.size(), cudaMemcpyDeviceToHost));
+      cudaFree(a.trace);
+      unsigned long long blocked = 0, polls = 0, by_ph[4] = {0, 0, 0, 0};
+      for (uint32_t u = 0; u < L->n_units; ++u) {
+        blocked += tr[2 * u];
+        polls += tr[2 * u + 1];
+        by_ph[(un[u].kf >> CMX_S16_COLOUR_SHIFT) & 3u] += tr[2 * u];
+      }
+      fprintf(stderr, "[stream trace] units %u groups/unit %u: blocked groups %llu (of %u), polls %llu; by colour %llu %llu %llu %llu\n",
+              L->n_units, gpu, blocked, a.n_groups, polls, by_ph[0], by_ph[1], by_ph[2], by_ph[3]);
+      if (trace_env > 1)
+        for (uint32_t u = 0; u < L->n_units; ++u)
+          if (tr[2 * u])
+            fprintf(stderr, "  pos %u sweep %u colour %u layer %u: blocked %u polls %u\n", u, un[u].sweep_rel,
+                    (un[u].kf >> CMX_S16_COLOUR_SHIFT) & 3u, un[u].kf & 0xFFFFu, tr[2 * u], tr[2 * u + 1]);
+    }
+    if (kg != 1) s->done_even += 2u * (uint32_t)n * a.tpu;
+    if (kg != 0) s->done_odd += 2u * (uint32_t)n * a.tpu;
     done += n;
   }
-  P.pdl_ok = false;
   return CMX_OK;
 }
 
-// small boxes: a colour pass is a few microseconds of work, less than the per-launch
-// constant; several sweeps in one cooperative launch then win (measured cross-over: a warp
-// has fewer than ~4 tiles per pass)
-static bool coop_pays(const cmx_state *s, int64_t n_sweeps) {
-  static int off = env_int("CMX_SWEEP_NO_AUTO_COOP", 0);
-  if (off || n_sweeps < 1 || !use_row16(s) || s->g.halo || row16_flat_blocks(s)) return false;
-  const uint32_t tiles = row16_tiles_per_replica(s);
-  const uint32_t warps = std::min<uint32_t>((uint32_t)s->plan.part_blocks, (tiles + 7) / 8) * 8u;
-  return tiles < 4u * warps;
-}
-
-// one pass over the colours whose k-colour equals kgroup (or all if < 0)
+// one pass over the colours whose k-colour equals kgroup (or all if < 0): block pair-LUT
+// kernel (states with linear rows) or the generic evaluators
 static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
                       int k_offset) {
   SweepPlan &P = s->plan;
@@ -1455,72 +1505,20 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
     dim3 grid(P.part_blocks, s->n_replicas);
     const bool fcc = (P.mask == kMaskFcc1NN);
     const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
-    const bool row16 = use_row16(s);
-    // one launch: colour (cy,cz), colour layers [kb, ke); first/last of a k-colour
-    // group carry the ring protocol of the fused halo exchange
-    const uint32_t n_kk_all = (uint32_t)(g.N2 / 2);
-    auto launch = [&](int cy, int cz, uint32_t kb, uint32_t ke, bool group_first, bool group_last) -> int {
-      if (ke <= kb) return CMX_OK;
-      a.cy = cy;
-      a.cz = cz;
-      a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
-      dim3 gl = grid;
-      if (row16) {
-        a.row_begin = kb * a.J;
-        a.n_rows = (ke - kb) * a.J;
-        const uint32_t rpw = 32u / a.W;
-        a.n_tiles = (a.n_rows + rpw - 1) / rpw;
-        gl.x = std::min<uint32_t>((uint32_t)P.part_blocks, (a.n_tiles + 7) / 8);
-      }
-      a.wait_epoch = a.signal_epoch = a.blocks_target = 0;
-      if (a.push && row16) {
-        // one k-colour group = one step of the ring protocol.  Warp-row kernel: the tiles
-        // next to a ghost layer come last and wait for the neighbours' previous step; the
-        // step this rank completed is published by the first launch that follows it
-        // (cmx_slab_publish at synchronisation points)
-        a.wait_epoch = s->epoch;
-        if (s->epoch > s->published) {
-          a.signal_epoch = s->epoch;
-          s->published = s->epoch;
-        }
-        if (group_last) ++s->epoch;
-      } else if (a.push) {
-        // block kernel: wait for the neighbours' previous step before the first launch,
-        // the last block of the last launch publishes
-        if (group_first) a.wait_epoch = s->epoch;
-        s->blocks_done += (unsigned long long)gl.x * gl.y;
-        a.blocks_target = s->blocks_done;
-        if (group_last) {
-          a.signal_epoch = ++s->epoch;
-          s->published = s->epoch;
-        }
-      }
-      if (row16) {
-        const bool pdl = sweep_pdl() && P.pdl_ok;
-        const uint32_t flat = row16_flat_blocks(s);
-        int rc;
-        if (flat && kb == 0 && ke == n_kk_all)
-          rc = (P.nocc == 3) ? launch_row16_flat<3>(a, flat, (uint32_t)s->n_replicas, s->stream, fcc, accum, pdl)
-                             : launch_row16_flat<2>(a, flat, (uint32_t)s->n_replicas, s->stream, fcc, accum, pdl);
-        else
-          rc = (P.nocc == 3) ? launch_row16<3>(a, gl, s->stream, fcc, accum, pdl)
-                             : launch_row16<2>(a, gl, s->stream, fcc, accum, pdl);
-        if (rc) return rc;
-        P.pdl_ok = true;
-      } else if (P.nocc == 3) {
-        if (pair16_minb() >= 4) launch_pair16<3, 4>(a, grid, s->stream, fcc, accum);
-        else launch_pair16<3, 3>(a, grid, s->stream, fcc, accum);
-      } else {
-        launch_pair16<2, 3>(a, grid, s->stream, fcc, accum);
-      }
-      return CMX_OK;
-    };
-    const uint32_t n_kk = (uint32_t)(g.N2 / 2);
-    for (int cz = 0; cz < 2 && !rc; ++cz) {
+    for (int cz = 0; cz < 2; ++cz) {
       if (kgroup >= 0 && cz != kgroup) continue;
-      for (int cy = 0; cy < 2 && !rc; ++cy) rc = launch(cy, cz, 0, n_kk, cy == 0, cy == 1);
+      for (int cy = 0; cy < 2; ++cy) {
+        a.cy = cy;
+        a.cz = cz;
+        a.ctr_hi = ((uint32_t)((uint64_t)sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
+        if (P.nocc == 3) {
+          if (pair16_minb() >= 4) launch_pair16<3, 4>(a, grid, s->stream, fcc, accum);
+          else launch_pair16<3, 3>(a, grid, s->stream, fcc, accum);
+        } else {
+          launch_pair16<2, 3>(a, grid, s->stream, fcc, accum);
+        }
+      }
     }
-    if (rc) return rc;
     CMX_CUDA(cudaGetLastError());
     return CMX_OK;
   }
@@ -1638,24 +1636,26 @@ static int sweep_prepare(cmx_state *s, const char *who) {
     }
   CMX_CUDA(cudaSetDevice(s->t->device));
   SweepPlan &P = s->plan;
-  uint32_t items;
   int blocks;
-  if (use_row16(s)) {
-    // one warp iteration = 32 chunks of whole rows of one (cy,cz) colour
-    uint32_t W = s->g.N0 / 16, rpw = 32 / W;
-    uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
-    items = (n_rows + rpw - 1) / rpw * 32;
-  } else if (use_pair(s)) {
-    // one block iteration = RB whole rows of one (cy,cz) colour
-    uint32_t W = s->g.N0 / 16, RB = 256 / W;
-    uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
-    items = (n_rows + RB - 1) / RB * 256;
+  if (use_stream(s)) {
+    if (P.stream_capacity < 0 || P.stream_blocks == 0) {
+      int rc = stream_geometry(s);
+      if (rc) return rc;
+    }
+    blocks = P.stream_blocks;
   } else {
-    items = (uint32_t)(s->g.N0 / P.S[0]) * (s->g.N1 / P.S[1]) * (s->g.N2 / P.S[2]);
-    if (cmx_use_warp_generic(s)) items = (uint32_t)std::min<uint64_t>((uint64_t)items * 32u, 0xFFFFFF00u);  // a warp per site
+    uint32_t items;
+    if (use_pair(s)) {
+      // one block iteration = RB whole rows of one (cy,cz) colour
+      uint32_t W = s->g.N0 / 16, RB = 256 / W;
+      uint32_t n_rows = (uint32_t)(s->g.N1 / 2) * (uint32_t)(s->g.N2 / 2);
+      items = (n_rows + RB - 1) / RB * 256;
+    } else {
+      items = (uint32_t)(s->g.N0 / P.S[0]) * (s->g.N1 / P.S[1]) * (s->g.N2 / P.S[2]);
+      if (cmx_use_warp_generic(s)) items = (uint32_t)std::min<uint64_t>((uint64_t)items * 32u, 0xFFFFFF00u);  // a warp per site
+    }
+    blocks = sweep_blocks_per_replica(items, s->n_replicas);
   }
-  blocks = sweep_blocks_per_replica(items, s->n_replicas);
-  if (const uint32_t gx = row16_flat_blocks(s)) blocks = (int)gx;  // counter slots [replica][block]
   if (P.part_blocks != blocks || !P.d_part_acc) {
     int rc = ensure_partials(s, blocks);
     if (rc) return rc;
@@ -1669,11 +1669,11 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
-  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_BLOCK_KERNEL |
-                         CMX_SWEEP_FUSED | CMX_SWEEP_THREAD_GENERIC | CMX_SWEEP_COOP))
+  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_THREAD_GENERIC))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
-  s->plan.part_blocks = 0;  // the grid may change with the evaluator
+  s->plan.part_blocks = 0;      // the grid may change with the evaluator
+  s->plan.stream_capacity = -1;  // and with the kernel variant
   return CMX_OK;
 }
 
@@ -1688,46 +1688,22 @@ extern "C" int cmx_counters_reset(cmx_state *s) {
   return CMX_OK;
 }
 
-// slabs: publish the ring epoch this rank has completed but not yet announced (the
-// warp-row kernel announces a step in the prologue of the launch that follows it)
-__global__ void k_slab_publish(unsigned long long *peer_dn, unsigned long long *peer_up, unsigned long long epoch) {
-  __threadfence_system();
-  st_sys(peer_dn + 1, epoch);
-  st_sys(peer_up + 0, epoch);
-}
-int cmx_slab_publish(cmx_state *s) {
-  if (!s->p2p || s->epoch <= s->published) return CMX_OK;
-  k_slab_publish<<<1, 1, 0, s->stream>>>(s->peer_sig_dn, s->peer_sig_up, s->epoch);
-  CMX_CUDA(cudaGetLastError());
-  s->published = s->epoch;
-  s->plan.pdl_ok = false;  // the next sweep launch follows a kernel without a dependent-launch trigger
-  return CMX_OK;
-}
-
 extern "C" int cmx_counters_read(cmx_state *s, cmx_counters *counters) {
   int rc = sweep_prepare(s, "cmx_counters_read");
   if (rc) return rc;
   if (!counters) return invalid("cmx_counters_read: null output");
-  if ((rc = cmx_slab_publish(s))) return rc;
   SweepPlan &P = s->plan;
   k_reduce_counters<<<s->n_replicas, 32, 0, s->stream>>>(P.d_part_acc, P.d_part_dE, P.part_blocks,
                                                         P.attempts, s->d_counters);
   CMX_CUDA(cudaGetLastError());
   CMX_CUDA(cudaMemcpyAsync(counters, s->d_counters, sizeof(cmx_counters) * s->n_replicas,
                            cudaMemcpyDeviceToHost, s->stream));
-  unsigned long long fused_to = 0;
-  if (P.d_fused_timeout)
-    CMX_CUDA(cudaMemcpyAsync(&fused_to, P.d_fused_timeout, sizeof(fused_to), cudaMemcpyDeviceToHost, s->stream));
   unsigned long long timed_out = 0;
-  if (s->p2p)
-    CMX_CUDA(cudaMemcpyAsync(&timed_out, s->d_sig + 3, sizeof(timed_out), cudaMemcpyDeviceToHost, s->stream));
+  CMX_CUDA(cudaMemcpyAsync(&timed_out, s->d_sig + 3, sizeof(timed_out), cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
-  if (fused_to) {
-    cmx_set_error("cmx_counters_read: the fused sweep kernel timed out waiting for a row stamp (grid not co-resident?)");
-    return CMX_ERR_CUDA;
-  }
   if (timed_out) {
-    cmx_set_error("cmx_counters_read: a ring neighbour did not reach the expected epoch (halo wait timed out)");
+    cmx_set_error("cmx_counters_read: a streaming sweep timed out waiting for a layer counter "
+                  "(grid not co-resident, or a ring neighbour did not run the same sweeps)");
     return CMX_ERR_CUDA;
   }
   return CMX_OK;
@@ -1752,19 +1728,13 @@ int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int6
   int rc = sweep_prepare(s, "cmx_sgc_sweep");
   if (rc) return rc;
   if (s->g.halo) return invalid("cmx_sgc_sweep: slab states are driven by cmx_sgc_sweep_kgroup / cmx_sgc_sweep_slab");
-  bool done = false;
-  if (use_fused(s) && n_sweeps > 0) {
-    rc = sweep_fused(s, seed, first_sweep, n_sweeps);
-    if (rc > 0) return rc;
-    done = (rc == CMX_OK);
-  } else if (n_sweeps > 0 && ((s->sweep_flags & CMX_SWEEP_COOP) || coop_pays(s, n_sweeps))) {
-    rc = sweep_coop(s, seed, first_sweep, n_sweeps);
-    if (rc > 0) return rc;
-    done = (rc == CMX_OK);
-  }
-  for (int64_t w = 0; w < n_sweeps && !done; ++w) {
-    rc = sweep_once(s, seed, first_sweep + w, -1, 0);
-    if (rc) return rc;
+  if (use_stream(s)) {
+    if (n_sweeps > 0 && (rc = sweep_stream(s, seed, first_sweep, n_sweeps, -1))) return rc;
+  } else {
+    for (int64_t w = 0; w < n_sweeps; ++w) {
+      rc = sweep_once(s, seed, first_sweep + w, -1, 0);
+      if (rc) return rc;
+    }
   }
   s->plan.attempts += (long long)s->g.n_cells * (long long)s->plan.mut_points.size() * n_sweeps;
   return CMX_OK;
@@ -1779,12 +1749,25 @@ extern "C" int cmx_sgc_sweep_async(cmx_state *s, int64_t n_sweeps, uint64_t seed
   return cmx_sgc_sweep_enqueue(s, seed, first_sweep, n_sweeps);
 }
 
+// more sweeps of the same accounting period: no counter reset, no synchronisation
+extern "C" int cmx_sgc_sweep_continue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep) {
+  if (!s) return invalid("cmx_sgc_sweep_continue: null state");
+  if (n_sweeps < 0) return invalid("cmx_sgc_sweep_continue: n_sweeps < 0");
+  return cmx_sgc_sweep_enqueue(s, seed, first_sweep, n_sweeps);
+}
+
 extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
                                     int32_t kgroup) {
   int rc = sweep_prepare(s, "cmx_sgc_sweep_kgroup");
   if (rc) return rc;
   if (kgroup < -1 || kgroup >= s->plan.S[2]) return invalid("cmx_sgc_sweep_kgroup: bad kgroup");
-  rc = sweep_once(s, seed, sweep, kgroup, s->k_offset);
+  if (use_stream(s)) {
+    if (s->p2p && s->g.halo && kgroup >= 0)
+      return invalid("cmx_sgc_sweep_kgroup: peer-attached slabs sweep with cmx_sgc_sweep_slab");
+    rc = sweep_stream(s, seed, sweep, 1, kgroup);
+  } else {
+    rc = sweep_once(s, seed, sweep, kgroup, s->k_offset);
+  }
   if (rc) return rc;
   long long per = (long long)s->g.n_cells * (long long)s->plan.mut_points.size();
   if (kgroup >= 0) per /= s->plan.S[2];
@@ -1792,24 +1775,20 @@ extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
   return CMX_OK;  // asynchronous: enqueued on the state's stream
 }
 
-// Slab states over peer memory: n_sweeps whole sweeps in one cooperative launch (the
-// ring protocol runs inside the kernel).  Asynchronous.  CMX_ERR_UNSUPPORTED when the
-// state is not a peer-attached slab on the warp-row kernel: drive it with
-// cmx_sgc_sweep_kgroup then.
+// Slab states over peer memory: n_sweeps whole sweeps of the streaming kernel; boundary
+// rows go to the ring neighbours' ghost layers and layer counters.  Asynchronous.
+// CMX_ERR_UNSUPPORTED when the state is not a peer-attached slab on the streaming kernel:
+// drive it with cmx_sgc_sweep_kgroup then.
 extern "C" int cmx_sgc_sweep_slab(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep) {
   int rc = sweep_prepare(s, "cmx_sgc_sweep_slab");
   if (rc) return rc;
   if (n_sweeps < 0) return invalid("cmx_sgc_sweep_slab: n_sweeps < 0");
-  if (!s->g.halo || !s->p2p || !use_row16(s)) {
-    cmx_set_error("cmx_sgc_sweep_slab: not a peer-attached slab state on the warp-row kernel");
+  if (!s->g.halo || !s->p2p || !use_stream(s)) {
+    cmx_set_error("cmx_sgc_sweep_slab: not a peer-attached slab state on the streaming kernel");
     return CMX_ERR_UNSUPPORTED;
   }
   if (n_sweeps == 0) return CMX_OK;
-  rc = sweep_coop(s, seed, first_sweep, n_sweeps);
-  if (rc < 0) {
-    cmx_set_error("cmx_sgc_sweep_slab: the grid is not co-resident on this device");
-    return CMX_ERR_UNSUPPORTED;
-  }
+  rc = sweep_stream(s, seed, first_sweep, n_sweeps, -1);
   if (rc) return rc;
   s->plan.attempts += (long long)s->g.n_cells * (long long)s->plan.mut_points.size() * n_sweeps;
   return CMX_OK;
@@ -1838,20 +1817,15 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
   return CMX_OK;
 }
 
-extern "C" int cmx_sweep_fused_info(cmx_state *s, int32_t *fused, int32_t *layers_per_slice,
-                                    int32_t *blocks) {
-  int rc = sweep_prepare(s, "cmx_sweep_fused_info");
+extern "C" int cmx_sweep_stream_info(cmx_state *s, int32_t *stream, int32_t *blocks, int32_t *group_rowsteps,
+                                     int32_t *gap_units) {
+  int rc = sweep_prepare(s, "cmx_sweep_stream_info");
   if (rc) return rc;
-  int gx = 0;
-  if (use_fused(s)) {
-    SweepPlan &P = s->plan;
-    const bool fcc = (P.mask == kMaskFcc1NN);
-    const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
-    gx = fused_blocks(s, (P.nocc == 3) ? fused_kernel<3>(fcc, accum) : fused_kernel<2>(fcc, accum));
-  }
-  if (fused) *fused = gx >= 1;
-  if (layers_per_slice) *layers_per_slice = gx >= 1 ? (int32_t)fused_slice_layers(s, gx) : 0;
-  if (blocks) *blocks = gx;
+  const bool on = use_stream(s);
+  if (stream) *stream = on ? 1 : 0;
+  if (blocks) *blocks = on ? s->plan.stream_blocks : 0;
+  if (group_rowsteps) *group_rowsteps = on ? (int32_t)s->plan.stream_gr : 0;
+  if (gap_units) *gap_units = on ? (int32_t)s->plan.stream_gap : 0;
   return CMX_OK;
 }
 
@@ -1861,7 +1835,161 @@ extern "C" int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep) {
     cmx_set_error("cmx_sweep_launches: no sweep plan");
     return CMX_ERR_STATE;
   }
-  // (cmx_sgc_sweep on a fused-eligible state: ONE launch per call, see cmx_sweep_fused_info)
-  *per_sweep = use_pair(s) ? 4 : s->plan.n_colours;
+  *per_sweep = use_stream(s) ? 0 : (use_pair(s) ? 4 : s->plan.n_colours);
+  return CMX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-proposal dE of the sweep's evaluator (parity/debug entry)
+// ---------------------------------------------------------------------------
+struct DebugDeArgs {
+  const int8_t *occ;  // the replica
+  Geom g;
+  DevTables T;
+  long long n;
+  const long long *l;
+  const int32_t *new_occ;
+  double *out;
+  // pair LUT
+  int nocc, z;
+  int32_t shell[48];
+  const double *dEpot;  // [CMX_TAB16] of the replica
+  // generic
+  const int32_t *gt_beg, *gt_fbeg, *gt_f, *gt_n;
+  const double *gt_w, *exch;
+};
+__device__ __forceinline__ bool debug_site(const DebugDeArgs &a, long long q, int &b, int &i, int &j, int &k) {
+  const Geom &g = a.g;
+  const long long l = a.l[q];
+  if (l < 0 || l >= g.n_cells * a.T.n_sublat) return false;
+  b = (int)(l / g.n_cells);
+  const long long cell = l - (long long)b * g.n_cells;
+  i = (int)(cell % g.N0);
+  const long long rest = cell / g.N0;
+  j = (int)(rest % g.N1);
+  k = (int)(rest / g.N1);
+  return true;
+}
+// mode 0: pair-LUT table entry; 1: folded term lists, one thread per proposal
+__global__ void k_sweep_debug_de(DebugDeArgs a, int mode) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= a.n) return;
+  const Geom &g = a.g;
+  const DevTables &T = a.T;
+  int b, i, j, k;
+  if (!debug_site(a, q, b, i, j, k)) {
+    a.out[q] = nan("");
+    return;
+  }
+  const int oi = cmx_dec(a.occ[cmx_site_offset(g, b, i, j, k)]), of = a.new_occ[q];
+  if (mode == 0) {
+    int cnt = 0;
+    for (int n = 0; n < a.z; ++n) {
+      const int ii = cmx_wrap(i + a.shell[3 * n], g.N0), jj = cmx_wrap(j + a.shell[3 * n + 1], g.N1);
+      const int kk = g.halo ? (k + a.shell[3 * n + 2]) : cmx_wrap(k + a.shell[3 * n + 2], g.N2);
+      cnt += (int)(uint8_t)a.occ[cmx_site_offset(g, 0, ii, jj, kk)];  // storage codes: n1 + 18 n2
+    }
+    int alt = of - oi - 1;
+    if (alt < 0) alt += a.nocc;
+    a.out[q] = (of == oi || alt >= a.nocc - 1) ? nan("") : a.dEpot[cnt | ((oi | (alt << 2)) << 8)];
+    return;
+  }
+  const int mo = T.max_occ;
+  int p = -1;
+  for (int pp = 0; pp < T.n_nlist_sublat; ++pp)
+    if (T.nlist_sublat[pp] == b) p = pp;
+  double dE = 0.0;
+  for (int t = a.gt_beg[p]; t < a.gt_beg[p + 1]; ++t) {
+    double v = a.gt_w[((size_t)t * mo + oi) * mo + of];
+    for (int f = a.gt_fbeg[t]; f < a.gt_fbeg[t + 1]; ++f) {
+      const int n = a.gt_n[f];
+      const int64_t no = cmx_nbr_offset(T, g, n, i, j, k, nullptr);
+      v *= T.phi[((size_t)T.nbr[n].w * T.n_func + a.gt_f[f]) * mo + cmx_dec(a.occ[no])];
+    }
+    dE += v;
+  }
+  a.out[q] = dE - a.exch[((size_t)b * mo + oi) * mo + of];
+}
+// folded term lists, one WARP per proposal (the evaluator of wide orbit sets)
+__global__ void __launch_bounds__(256) k_sweep_debug_de_warp(DebugDeArgs a, GenTerms G, int stage_max) {
+  extern __shared__ __align__(16) unsigned char sh_dbg[];
+  const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  double *sh_val = reinterpret_cast<double *>(sh_dbg) + (size_t)wib * (stage_max + 1);
+  const long long q = blockIdx.x * 8ll + wib;
+  if (q >= a.n) return;
+  const Geom &g = a.g;
+  const DevTables &T = a.T;
+  int b, i, j, k;
+  if (!debug_site(a, q, b, i, j, k)) {
+    if (lane == 0) a.out[q] = nan("");
+    return;
+  }
+  int p = -1;
+  for (int pp = 0; pp < T.n_nlist_sublat; ++pp)
+    if (T.nlist_sublat[pp] == b) p = pp;
+  const int oi = cmx_dec(a.occ[cmx_site_offset(g, b, i, j, k)]), of = a.new_occ[q];
+  const double dE = cmx_warp_site_delta<false>(T, g, G, a.occ, sh_val, p, i, j, k, oi, of, -1, 0, lane);
+  if (lane == 0) a.out[q] = dE - a.exch[((size_t)b * T.max_occ + oi) * T.max_occ + of];
+}
+
+extern "C" int cmx_sweep_debug_delta_e(cmx_state *s, int32_t replica, int64_t n, const int64_t *l,
+                                       const int32_t *new_occ, double *out) {
+  int rc = sweep_prepare(s, "cmx_sweep_debug_delta_e");
+  if (rc) return rc;
+  if (replica < 0 || replica >= s->n_replicas || n < 0 || (n && (!l || !new_occ || !out)))
+    return invalid("cmx_sweep_debug_delta_e: bad argument");
+  if (n == 0) return CMX_OK;
+  SweepPlan &P = s->plan;
+  const DevTables &T = s->t->d;
+  for (int64_t q = 0; q < n; ++q) {
+    if (l[q] < 0 || l[q] >= s->g.n_cells * T.n_sublat) return invalid("cmx_sweep_debug_delta_e: site out of range");
+    const int b = (int)(l[q] / s->g.n_cells);
+    if (new_occ[q] < 0 || new_occ[q] >= s->t->n_occ[b]) return invalid("cmx_sweep_debug_delta_e: occupant out of range");
+  }
+  const size_t bytes = (size_t)n * (sizeof(long long) + sizeof(int32_t) + sizeof(double));
+  if ((rc = cmx_scratch(s, bytes + 64))) return rc;
+  double *d_out = (double *)s->d_scratch;
+  long long *d_l = (long long *)(d_out + n);
+  int32_t *d_new = (int32_t *)(d_l + n);
+  CMX_CUDA(cudaMemcpyAsync(d_l, l, sizeof(long long) * n, cudaMemcpyHostToDevice, s->stream));
+  CMX_CUDA(cudaMemcpyAsync(d_new, new_occ, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s->stream));
+  DebugDeArgs a;
+  a.occ = s->d_occ + (size_t)replica * s->g.rep_stride;
+  a.g = s->g;
+  a.T = T;
+  a.n = n;
+  a.l = d_l;
+  a.new_occ = d_new;
+  a.out = d_out;
+  a.nocc = P.nocc;
+  a.z = std::min(P.z, 16);
+  for (int q = 0; q < 48; ++q) a.shell[q] = P.shell[q];
+  a.dEpot = P.d_dEpot ? P.d_dEpot + (size_t)replica * P.n_tab : nullptr;
+  a.gt_beg = P.d_gt_beg;
+  a.gt_fbeg = P.d_gt_fbeg;
+  a.gt_f = P.d_gt_f;
+  a.gt_n = P.d_gt_n;
+  a.gt_w = P.d_gt_w;
+  const size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
+  a.exch = s->d_exch + (size_t)replica * exs;
+  if (use_pair(s)) {
+    if (P.z > 16) return invalid("cmx_sweep_debug_delta_e: neighbor class larger than 16");
+    if ((rc = pair_tables(s))) return rc;
+    k_sweep_debug_de<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(a, 0);
+  } else if (cmx_use_warp_generic(s)) {
+    GenTerms G{P.d_gt_beg, P.d_gt_fbeg, P.d_gt_vi, P.d_act_beg, P.d_act_n, P.d_gt_w, P.d_gt_pk};
+    const size_t stage_bytes = (size_t)(P.stage_max + 1) * 8 * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CMX_CUDA(cudaFuncSetAttribute(k_sweep_debug_de_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_set = true;
+    }
+    k_sweep_debug_de_warp<<<(unsigned)((n + 7) / 8), 256, stage_bytes, s->stream>>>(a, G, P.stage_max);
+  } else {
+    k_sweep_debug_de<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(a, 1);
+  }
+  CMX_CUDA(cudaGetLastError());
+  CMX_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+  CMX_CUDA(cudaStreamSynchronize(s->stream));
   return CMX_OK;
 }

@@ -3,11 +3,16 @@
 
 One process per GPU.  The N0 x N1 x N2 box is cut into `world` slabs along k;
 each rank owns N2/world layers plus `halo` ghost layers on each side.  A sweep
-is run k-colour group by k-colour group (`cmx_sgc_sweep_kgroup`, asynchronous
-on the state's stream); after group g the boundary layers whose global k is
-congruent to g are the only ones that changed, and exactly those are sent to
-the ring neighbours (NCCL send/recv over NVLink, enqueued on the same stream,
-so no host synchronisation happens inside a sweep).
+runs either
+  * over NVLink peer memory (the default where the ring neighbours can map each other,
+    `cmx_state_ipc_attach`): `cmx_sgc_sweep_slab`, the streaming kernel stores the
+    boundary rows it changes into the neighbours' ghost layers and counts them on the
+    neighbours' layer counters -- no collective in the data path; or
+  * k-colour group by k-colour group (`cmx_sgc_sweep_kgroup`, asynchronous on the
+    state's stream): after group g the boundary layers whose global k is congruent to g
+    are the only ones that changed, and exactly those are sent to the ring neighbours
+    (NCCL send/recv, enqueued on the same stream, no host synchronisation in a sweep).
+The initial fill of the ghost layers after an upload is always the NCCL exchange.
 
 The RNG counters use GLOBAL coordinates (`cmx_state_set_k_offset`), therefore
 the trajectory is bit-identical for every number of slabs -- which the tests
@@ -17,8 +22,6 @@ torch is used for what it is here for: NCCL plumbing and stream handles.
 """
 from __future__ import annotations
 
-import os
-import time
 from typing import Optional
 
 import numpy as np
@@ -108,8 +111,6 @@ class SlabRunner:
         # neighbours' slabs (CUDA IPC over NVLink) and the kernel stores the
         # boundary rows it changes straight into their ghost layers
         self.p2p = False
-        # None: try the cooperative whole-sweep kernel; CMX_SLAB_NO_COOP=1 keeps one launch per colour pass
-        self._coop = False if os.environ.get("CMX_SLAB_NO_COOP") else None
         if p2p:
             self._attach_peers()
 
@@ -195,21 +196,16 @@ class SlabRunner:
     # -- driver -----------------------------------------------------------------
     def sweep(self, n_sweeps: int, seed: int, first_sweep: int = 0) -> None:
         """Asynchronous: everything is enqueued on the state's stream."""
-        if self.p2p and self._coop is not False and n_sweeps > 0:
-            # whole sweeps in one cooperative launch, the ring protocol inside the kernel
-            try:
+        if self.p2p:
+            # streaming kernel over peer memory: boundary rows and their completion counts go
+            # straight into the ring neighbours' ghost layers / layer counters
+            if n_sweeps > 0:
                 self.state.sgc_sweep_slab(n_sweeps, seed, first_sweep)
-                self._coop = True
-                return
-            except _capi.CmxError as e:
-                if e.code != _capi.CMX_ERR_UNSUPPORTED or self._coop:
-                    raise
-                self._coop = False       # e.g. the block kernel: one launch per colour pass
+            return
         for w in range(n_sweeps):
             for g in range(self.Sk):
                 self.state.sgc_sweep_kgroup(seed, first_sweep + w, g)
-                if not self.p2p:
-                    self.exchange(g)
+                self.exchange(g)
 
     def synchronize(self):
         self.stream.synchronize()
@@ -225,57 +221,3 @@ class SlabRunner:
                          device=self.mem.device)
         dist.all_reduce(t)
         return t.cpu().numpy()
-
-    # -- benchmark (bench.py --gpus N) -----------------------------------------------
-    def bench(self, K: int, W: int, S: int) -> dict:
-        torch, dist = self.torch, self.dist
-        from bench import ClockSampler  # the clock sampler lives with the bench contract
-        self.sweep(W * S, seed=1, first_sweep=0)
-        self.synchronize()
-        self.state.counters_reset()
-        dist.barrier()
-        torch.cuda.synchronize()
-        clocks = ClockSampler(torch.cuda.current_device())
-        clocks.start()
-        time.sleep(0.3)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.time()
-        ev0.record(self.stream)
-        self.sweep(K * S, seed=1, first_sweep=W * S)
-        ev1.record(self.stream)
-        self.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t1 = time.time()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=self.mem.device)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        cnt = self.counters()
-        clk = clocks.stop(t0, t1)
-        # end to end: host slabs in, K x (upload, S sweeps, download)
-        host = torch.empty(self.layer * self.n2 * self.n_sublat, dtype=torch.int8).pin_memory()
-        harr = host.numpy()
-        self.state.download_occ(dtype=np.int8, out=harr)
-        dist.barrier()
-        torch.cuda.synchronize()
-        te0 = time.perf_counter()
-        for k in range(K):
-            self.state.upload_occ(harr)
-            self.exchange(None)
-            self.sweep(S, seed=3, first_sweep=k * S)
-            self.state.download_occ(dtype=np.int8, out=harr)
-        self.synchronize()
-        dist.barrier()
-        te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=self.mem.device)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        n_sites = self.N[0] * self.N[1] * self.N[2] * self.n_sublat
-        n_col = self._info["launches_per_sweep"]
-        coop = self._coop is True          # the timed call was ONE cooperative launch (K * S sweeps)
-        launches = 1 if coop else K * S * n_col
-        return dict(ms=float(ms.item()), clocks=clk, accept_rate=float(cnt[1] / max(cnt[0], 1.0)),
-                    launches=launches, kernel_ms=float(ms.item()) / launches, coop=coop,
-                    sweeps_per_launch=(K * S if coop else 1.0 / n_col),
-                    e2e={"value": K * S * n_sites / float(te.item()), "unit": "steps/s",
-                         "h2d_bytes_per_step": n_sites, "d2h_bytes_per_step": n_sites,
-                         "ms_per_step": float(te.item()) * 1e3 / K})

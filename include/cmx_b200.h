@@ -98,6 +98,15 @@ void cmx_tables_destroy(cmx_tables *t);
  * ------------------------------------------------------------------------- */
 int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1, int32_t N2,
                      int32_t n_replicas, int32_t halo, cmx_state **out);
+/* Same with options.  The device layout of a row is private to the library (every
+ * transfer converts): single-sublattice states with <= 3 occupants whose N0 is a power of
+ * two in [16, 512] store "x4-interleaved" rows (word w of a row holds the sites w, w+Q,
+ * w+2Q, w+3Q, Q = N0/4), the layout of the streaming pair-LUT sweep (k_sweep_stream16).
+ * CMX_STATE_LINEAR_ROWS keeps site i at byte i: such states sweep with the block kernel
+ * (k_sweep_pair16) -- a cross-check of the streaming kernel, not a faster path. */
+#define CMX_STATE_LINEAR_ROWS 1u
+int cmx_state_create_opts(const cmx_tables *t, int32_t N0, int32_t N1, int32_t N2,
+                          int32_t n_replicas, int32_t halo, uint32_t options, cmx_state **out);
 void cmx_state_destroy(cmx_state *s);
 
 /* occupation in the reference's layout (int32, Eigen::VectorXi order
@@ -230,26 +239,18 @@ int cmx_counters_reset(cmx_state *s);
  *                           decisions: a cross-check of the fast path) */
 #define CMX_SWEEP_DE_SUM 1u
 #define CMX_SWEEP_FORCE_GENERIC 2u
-/* pair-LUT kernel variants (the trajectory does not depend on the variant):
- * BLOCK_KERNEL forces the block-exchange kernel (k_sweep_pair16: any N0 that is a
- * multiple of 16) where the warp-row kernel (k_sweep_row16: N0/16 a power of two
- * <= 32) would be chosen.  cmx_sgc_sweep launches one kernel per colour pass (4 per
- * sweep, overlapped with programmatic dependent launch); FUSED selects the
- * experimental whole-call kernel instead (k_sweep_row16_fused: one cooperative launch,
- * row stamps instead of kernel boundaries -- measured 2x slower at 512^3 because of
- * the stamp polling, kept for the bit-exact cross-check and for further work). */
-#define CMX_SWEEP_BLOCK_KERNEL 4u
-#define CMX_SWEEP_FUSED 8u
+/* pair-LUT kernels (the trajectory does not depend on the kernel): states with
+ * x4-interleaved rows (cmx_state_create_opts) run a whole cmx_sgc_sweep call -- all its
+ * sweeps, all colours -- as ONE cooperative launch of the streaming kernel
+ * (k_sweep_stream16: per-layer completion counters instead of kernel boundaries or grid
+ * barriers; every lattice byte crosses HBM once per sweep and direction); states with
+ * linear rows launch the block kernel once per colour pass (k_sweep_pair16, 4 per sweep). */
 /* generic (term-list) evaluator variants: models with wide orbit sets (>= 96 merged
  * terms per site, e.g. ZrO with triplets and quadruplets) evaluate one site per WARP
  * (k_sweep_generic_warp, k_canonical_pairs_warp: neighborhood staged once, terms dealt
  * to the lanes); THREAD_GENERIC forces one site per thread (same random bits and
  * decisions; dE differs in the last bits through the summation order). */
 #define CMX_SWEEP_THREAD_GENERIC 16u
-/* COOP: cmx_sgc_sweep runs all its sweeps in ONE cooperative launch of the warp-row kernel
- * with a grid barrier between colour passes (k_sweep_row16_coop) instead of one launch
- * per pass; pays when a pass is too short to amortise a launch (small boxes, slabs). */
-#define CMX_SWEEP_COOP 32u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* Asynchronous forms for pipelines of independent states (each state owns a stream): the
  * upload of one job overlaps the sweeps of another and the download of a third.  Host
@@ -259,9 +260,13 @@ int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 int cmx_state_upload_occ_i8_async(cmx_state *s, int32_t replica, const int8_t *occ);
 int cmx_state_download_occ_i8_async(cmx_state *s, int32_t replica, int8_t *occ);
 int cmx_sgc_sweep_async(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep);
+/* more sweeps of the same accounting period: like cmx_sgc_sweep_async, but the counters
+ * keep accumulating (no reset) */
+int cmx_sgc_sweep_continue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep);
 int cmx_state_synchronize(cmx_state *s);
 /* Slab states attached over peer memory (cmx_state_ipc_attach): n_sweeps whole sweeps in
- * one cooperative launch, the ring protocol of the halo exchange inside the kernel.
+ * one cooperative launch of the streaming kernel; boundary rows are stored into the ring
+ * neighbours' ghost layers and counted on their layer counters (no collective, no barrier).
  * Asynchronous (enqueued on the state's stream).  CMX_ERR_UNSUPPORTED when the state is
  * not such a slab: use cmx_sgc_sweep_kgroup (+ the host-side halo exchange) then. */
 int cmx_sgc_sweep_slab(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep);
@@ -309,13 +314,22 @@ int cmx_canonical_sweep(cmx_state *s, int64_t n_sweeps, uint64_t seed,
 int cmx_canonical_info(const cmx_state *s, int32_t i, int32_t *strides /*[3]*/,
                        int32_t *n_colours);
 
-/* Kernel launches one full sweep takes with the current evaluator (the
- * pair-LUT kernel fuses both x colours of a row: 4 launches for 8 colours). */
+/* Kernel launches one full sweep takes with the current evaluator (block pair-LUT kernel:
+ * 4 launches for 8 colours; generic: one per colour); 0 = the streaming kernel, which runs
+ * a whole cmx_sgc_sweep call as one launch. */
 int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep);
-/* *fused = 1 when cmx_sgc_sweep runs a whole call (all its sweeps) as ONE launch of
- * the fused kernel on this state (then *layers_per_slice colour layers form a
- * k-slice of its schedule and *blocks is its co-resident grid per replica). */
-int cmx_sweep_fused_info(cmx_state *s, int32_t *fused, int32_t *layers_per_slice, int32_t *blocks);
+/* Schedule of the streaming kernel on this state: *stream = 1 when it is the evaluator,
+ * *blocks = co-resident blocks per replica, *group_rowsteps = row-steps a warp takes at a
+ * time, *gap_units = (layer, row colour) units the host keeps between dependent units. */
+int cmx_sweep_stream_info(cmx_state *s, int32_t *stream, int32_t *blocks, int32_t *group_rowsteps,
+                          int32_t *gap_units);
+/* Debug / parity entry: delta potential energy of the proposal (l, new_occ) on the current
+ * occupation of `replica` as the SWEEP's evaluator computes it -- the pair-LUT table entry
+ * (dE - exchange term) or the folded term lists of the generic evaluator (thread or warp
+ * variant, as the sweep would choose) -- to compare with cmx_delta_e (the faithful
+ * evaluator) proposal by proposal.  out[n]. */
+int cmx_sweep_debug_delta_e(cmx_state *s, int32_t replica, int64_t n, const int64_t *l,
+                            const int32_t *new_occ, double *out);
 
 /* Occupant bookkeeping needed by the reference-order mode:
  * sublat_to_asym[n_sublat], occ_to_species[n_sublat][max_occ] (-1 padded). */

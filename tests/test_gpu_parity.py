@@ -163,9 +163,9 @@ def test_sequential_million_steps_vs_live_oracle(dev_tables, systems, load_vecto
 # ---------------------------------------------------------------------------
 # checkerboard sweeps
 # ---------------------------------------------------------------------------
-def _sweep_state(dev_tables, systems, case_sys, eci_key, N, T, mu, n_replicas=1, seed=1):
+def _sweep_state(dev_tables, systems, case_sys, eci_key, N, T, mu, n_replicas=1, seed=1, linear_rows=False):
     sysd = systems[case_sys]
-    st = _capi.State(dev_tables(sysd["tables"]), N, n_replicas)
+    st = _capi.State(dev_tables(sysd["tables"]), N, n_replicas, linear_rows=linear_rows)
     eci = sysd[eci_key]
     st.set_eci(eci["index"], eci["value"])
     ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], mu, sysd["n_species"])
@@ -230,30 +230,37 @@ def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
     b.close()
 
 
-@pytest.mark.parametrize("staging", ["default", "block", "fused", "coop"])
+@pytest.mark.parametrize("kernel", ["stream", "block"])
 @pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1),
-                                          ((128, 32, 4), 2), ((128, 24, 20), 3)])
-def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas, staging):
-    """The 16-sites-per-thread LUT kernel and the one-site-per-thread generic
-    evaluator (whose delta E is checked against the reference kernels) draw the
-    same random bits and must make the same decisions: identical occupation
-    after several sweeps, identical acceptance counts.  Covers one chunk per row
-    (N0=16), rows that do not fill a block (N0=48), a row spanning a whole warp
-    (N0=512), replicas with different conditions, a replica grid whose flat tile space is
-    cut across replica boundaries ((128, 24, 20) x 3: 30 tiles per replica, 7.5 per block)
-    and the int8 transfer path."""
+                                          ((128, 32, 4), 2), ((128, 24, 20), 3), ((64, 2, 2), 1), ((256, 6, 12), 1)])
+def test_pair_lut_kernels_equal_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas, kernel):
+    """The pair-LUT kernels -- the streaming kernel on x4-interleaved rows (one cooperative
+    launch per call, per-layer completion counters) and the block kernel on linear rows --
+    and the one-site-per-thread generic evaluator (whose delta E is checked against the
+    reference kernels) draw the same random bits and must make the same decisions:
+    identical occupation after several sweeps, identical acceptance counts.  Covers one
+    chunk per row (N0=16), rows that do not fill a block (N0=48: block kernel only), a row
+    spanning a whole warp (N0=512), partial row-steps (J not a multiple of the rows per
+    warp), the smallest boxes (two layers, one row per colour), replicas with different
+    conditions and the int8 transfer path.  The generic evaluator runs on the SAME layout
+    as the kernel under test, so the layout-dependent assignment of random fields to sites
+    is covered on both."""
     mu = [0.2, -0.1]
-    a, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5)
-    b, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5)
+    lin = kernel == "block"
+    a, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5,
+                               linear_rows=lin)
+    b, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu, n_replicas=n_replicas, seed=5,
+                           linear_rows=lin)
     if n_replicas > 1:
         ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.4], 3)
         a.set_conditions(500.0, ex2, replica=1)
         b.set_conditions(500.0, ex2, replica=1)
-    variant = {"default": 0, "block": _capi.CMX_SWEEP_BLOCK_KERNEL, "fused": _capi.CMX_SWEEP_FUSED,
-               "coop": _capi.CMX_SWEEP_COOP}[staging]
-    a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM | variant)
+    a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
     b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC | _capi.CMX_SWEEP_DE_SUM)
-    assert a.sweep_info()["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
+    ia = a.sweep_info()
+    assert ia["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
+    pow2 = N[0] <= 512 and (N[0] & (N[0] - 1)) == 0
+    assert ia["stream"] == (kernel == "stream" and pow2)
     for r in range(n_replicas):
         assert (a.download_occ(r) == b.download_occ(r)).all()
     ca = a.sgc_sweep(6, seed=9)
@@ -265,7 +272,7 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
         assert ca[r].n_accept == cb[r].n_accept and ca[r].n_attempt == cb[r].n_attempt
         assert ca[r].dE_sum == pytest.approx(cb[r].dE_sum, rel=1e-9, abs=1e-9)
     # without the dE accumulation (the default) the trajectory is the same
-    a.set_sweep_flags(variant)
+    a.set_sweep_flags(0)
     ca = a.sgc_sweep(2, seed=9, first_sweep=6)
     cb = b.sgc_sweep(2, seed=9, first_sweep=6)
     for r in range(n_replicas):
@@ -275,17 +282,56 @@ def test_pair16_kernel_equals_generic_kernel_bit_for_bit(dev_tables, systems, N,
     b.close()
 
 
+def test_streaming_and_block_kernel_share_their_statistics(dev_tables, systems):
+    """The two pair-LUT kernels assign the random fields to the sites differently (the
+    layouts differ), so their trajectories differ -- but they sample the same ensemble:
+    acceptance rate and composition agree statistically on a 64^3 box."""
+    N, mu = (64, 64, 64), [0.1, -0.2]
+    res = []
+    for lin in (False, True):
+        st, sysd, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 1000.0, mu, seed=3, linear_rows=lin)
+        st.sgc_sweep(30, seed=21)
+        cnt = st.sgc_sweep(60, seed=21, first_sweep=30)
+        comp = st.composition()[0] / float(np.prod(N))
+        res.append((cnt[0].n_accept / cnt[0].n_attempt, comp))
+        st.close()
+    assert res[0][0] == pytest.approx(res[1][0], abs=2e-3)
+    np.testing.assert_allclose(res[0][1], res[1][1], atol=3e-3)
+
+
+def test_conditions_change_after_a_sweep_is_honoured(dev_tables, systems):
+    """the pair-LUT acceptance tables are functions of (T, mu); changing
+    the conditions of a state that has already swept must rebuild them.  sweep ->
+    set_conditions -> sweep equals (bit for bit) a fresh state at the new conditions that
+    starts from the same occupation, and the generic evaluator, which reads beta and the
+    exchange table directly."""
+    N, mu0, mu1 = (32, 16, 8), [0.2, -0.1], [-0.4, 0.3]
+    a, sysd, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, mu0, seed=5)
+    a.sgc_sweep(3, seed=9)
+    occ_mid = a.download_occ()
+    ex1 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], mu1, 3)
+    a.set_conditions(400.0, ex1)
+    ca = a.sgc_sweep(3, seed=9, first_sweep=3)
+    for flags in (0, _capi.CMX_SWEEP_FORCE_GENERIC):
+        b, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 400.0, mu1, seed=5)
+        b.upload_occ(occ_mid)
+        b.set_sweep_flags(flags)
+        cb = b.sgc_sweep(3, seed=9, first_sweep=3)
+        assert (a.download_occ() == b.download_occ()).all(), f"flags {flags}"
+        assert ca[0].n_accept == cb[0].n_accept
+        b.close()
+    a.close()
+
+
 @pytest.mark.parametrize("N,n_replicas,n_sweeps", [((512, 512, 512), 1, 6), ((128, 128, 128), 8, 6)])
 def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sweeps):
     """BASELINE sizes (configs[2]: 512^3; configs[1]: 128^3 replicas with a (mu, T) grid):
-    the fused whole-call kernel, one launch per colour pass, the block-exchange kernel
-    and the generic one-site-per-thread evaluator must leave the SAME occupation and the
-    same acceptance counts.  Only at these sizes are all SMs busy and the row stamps,
-    the overlapped launches and the L2 slices of the fused schedule really exercised."""
+    the streaming kernel and the generic one-site-per-thread evaluator must leave the SAME
+    occupation and the same acceptance counts.  Only at these sizes are all SMs busy and
+    the layer counters, the wavefront order and the seam of the periodic box really
+    exercised (thousands of warps in flight across tens of units)."""
     mu = [0.0, 0.0]
-    variants = {"row": 0, "coop": _capi.CMX_SWEEP_COOP, "fused": _capi.CMX_SWEEP_FUSED,
-                "block": _capi.CMX_SWEEP_BLOCK_KERNEL,
-                "generic": _capi.CMX_SWEEP_FORCE_GENERIC}
+    variants = {"stream": 0, "generic": _capi.CMX_SWEEP_FORCE_GENERIC}
     ref_occ, ref_cnt = None, None
     for name, flags in variants.items():
         st, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 800.0, mu,
@@ -296,9 +342,9 @@ def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sw
             st.set_conditions(400.0 + 200.0 * r, exr, replica=r)
         st.set_sweep_flags(flags)
         info = st.sweep_info()
-        assert info["fused"] == (name == "fused")
+        assert info["stream"] == (name == "stream")
         cnt = st.sgc_sweep(n_sweeps - 2, seed=7)
-        cnt2 = st.sgc_sweep(2, seed=7, first_sweep=n_sweeps - 2)   # a second call continues the stamps
+        cnt2 = st.sgc_sweep(2, seed=7, first_sweep=n_sweeps - 2)   # a second call continues the counters
         occ = [st.download_occ(r, dtype=np.int8) for r in range(n_replicas)]
         acc = [cnt[r].n_accept + cnt2[r].n_accept for r in range(n_replicas)]
         st.close()
@@ -306,8 +352,48 @@ def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sw
             ref_occ, ref_cnt = occ, acc
             continue
         for r in range(n_replicas):
-            assert (occ[r] == ref_occ[r]).all(), f"{name} vs row, replica {r}: {(occ[r] != ref_occ[r]).sum()} sites differ"
+            assert (occ[r] == ref_occ[r]).all(), f"{name} vs stream, replica {r}: {(occ[r] != ref_occ[r]).sum()} sites differ"
         assert acc == ref_cnt, name
+
+
+@pytest.mark.parametrize("case_sys,eci_key,N,flags", [
+    ("fcc", "eci_sparse", (16, 8, 8), 0),                                  # pair-LUT table (streaming kernel)
+    ("fcc", "eci_sparse", (48, 8, 8), 0),                                  # pair-LUT table (block kernel, linear rows)
+    ("fcc", "eci_sparse", (16, 8, 8), _capi.CMX_SWEEP_FORCE_GENERIC),      # folded terms, thread evaluator
+    ("fcc", "eci_full", (8, 8, 8), 0),                                     # 1NN + 2NN pairs: generic
+    ("fcc", "eci_2", (8, 8, 8), 0),
+    ("zro", "eci", (8, 8, 8), 0),                                          # warp evaluator (quadruplets)
+    ("zro", "eci", (8, 8, 8), _capi.CMX_SWEEP_THREAD_GENERIC),
+])
+def test_sweep_evaluators_delta_e_per_proposal(dev_tables, systems, case_sys, eci_key, N, flags):
+    """north_star (1): dE within 1e-10 relative, proposal by proposal, for the evaluators
+    the SWEEPS use: the pair-LUT table entry, the ECI-folded merged
+    term lists (one site per thread) and the warp-staged evaluator -- every mutable site x
+    every alternative occupant of the box -- against cmx_delta_e (the faithful evaluator,
+    bit-exact to the reference's generated kernels, test_faithful_kernels_match_golden)
+    with the semi-grand exchange term of SemiGrandCanonicalCalculator.cc:186-213."""
+    sysd = systems[case_sys]
+    mu = [0.2, -0.1][:len(sysd["axes"]["end_members"])]
+    st, sysd, ex = _sweep_state(dev_tables, systems, case_sys, eci_key, N, 900.0, mu, seed=13)
+    st.set_sweep_flags(flags)
+    n_cells = int(np.prod(N))
+    nocc = np.array(st.tables.host.n_occ)
+    occ = st.download_occ()
+    ls, news = [], []
+    for b in sysd["mutable_sublats"]:
+        for alt in range(1, nocc[b]):
+            l = b * n_cells + np.arange(n_cells)
+            ls.append(l)
+            news.append((occ[l] + alt) % nocc[b])
+    l = np.concatenate(ls)
+    new = np.concatenate(news).astype(np.int32)
+    got = st.sweep_debug_delta_e(l, new)
+    want = st.delta_e(l, new, 1, potential=True)
+    scale = np.abs(want).max()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    assert err <= 1e-10 * scale, f"{st.sweep_info()['evaluator']}: max |dE - dE_ref| = {err:g} (scale {scale:g})"
+    st.close()
 
 
 @pytest.mark.parametrize("N", [(16, 6, 4), (48, 10, 8), (512, 4, 2)])
