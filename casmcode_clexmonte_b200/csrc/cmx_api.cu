@@ -606,6 +606,11 @@ extern "C" int cmx_state_ipc_attach(cmx_state *s, const void *handle_dn, const v
   // count on them; they are zero from creation and only ever advance in step with
   // done_even / done_odd)
   s->p2p = true;
+  // the sweep kernel variant (and with it the co-resident grid) changes: recompute the schedule
+  s->plan.stream_capacity = -1;
+  s->plan.part_blocks = 0;
+  for (auto &kv : s->plan.stream_lists) cudaFree(kv.second.d_units);
+  s->plan.stream_lists.clear();
   return CMX_OK;
 }
 

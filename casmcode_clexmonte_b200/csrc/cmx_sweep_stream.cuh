@@ -600,16 +600,27 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_stream16(S16Args a)
     const uint32_t own = (uint32_t)k + 1u;
     const uint32_t lo = (k == 0) ? (halo ? 0u : (uint32_t)N2) : (uint32_t)k;
     const uint32_t hi = (k == N2 - 1) ? (halo ? (uint32_t)N2 + 1u : 1u) : (uint32_t)k + 2u;
-    i0 = (kf & CMX_S16_DEP_LO) ? lo : own;
-    i1 = (kf & CMX_S16_DEP_HI) ? hi : own;
+    // (a neighbour nobody counts -- a ghost layer filled by the host -- is replaced by the
+    // other one; `own` only for the row colour 1 units, whose threshold is the own layer's)
+    if (kf & CMX_S16_DEP_OWN) {
+      i0 = i1 = own;
+    } else {
+      i0 = (kf & CMX_S16_DEP_LO) ? lo : hi;
+      i1 = (kf & CMX_S16_DEP_HI) ? hi : lo;
+    }
   };
   // dependency test on polled counter values
   auto has_deps = [&](uint32_t kf) { return (kf & (CMX_S16_DEP_LO | CMX_S16_DEP_HI | CMX_S16_DEP_OWN)) && !(a.dbg & 4u); };
+  // (system scope only for the ghost-layer counters, which the ring neighbours write)
+  auto poll1 = [&](uint32_t i) {
+    if (SLAB && (i == 0u || i == (uint32_t)N2 + 1u)) return ld_poll_u32<true>(done + i);
+    return ld_poll_u32<false>(done + i);
+  };
   auto poll = [&](const S16Pos &p, uint32_t &v0, uint32_t &v1) {
     uint32_t i0, i1;
     dep_index(p.kf, i0, i1);
-    v0 = ld_poll_u32<SLAB>(done + i0);
-    v1 = (i1 != i0) ? ld_poll_u32<SLAB>(done + i1) : v0;
+    v0 = poll1(i0);
+    v1 = (i1 != i0) ? poll1(i1) : v0;
   };
   auto reached = [&](const S16Pos &p, uint32_t v0, uint32_t v1) {
     return (int32_t)(v0 - p.need) >= 0 && (int32_t)(v1 - p.need) >= 0;
@@ -663,14 +674,29 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_stream16(S16Args a)
       uint32_t g = pend_g0;
       const uint32_t g_end = pend_g0 + pend_cnt;
       bool first = !(a.dbg & 2u);  // the first count carries the release fence
+      // system scope only when a counted layer was also pushed to a ring neighbour
+      bool sys = false;
+      if (SLAB && a.push) {
+        uint32_t u0, u1, q;
+        fastdivmod(g, a.div_gpu, u0, q);
+        fastdivmod(g_end - 1u, a.div_gpu, u1, q);
+        for (uint32_t u = u0; u <= u1; ++u) {
+          const int32_t k = (int32_t)(__ldg(&a.units[u].kf) & 0xFFFFu);
+          sys |= (k == 0 || k == N2 - 1);
+        }
+      }
       while (g < g_end) {
         uint32_t u, gi0;
         fastdivmod(g, a.div_gpu, u, gi0);
         const uint32_t gi1 = min(gi0 + (g_end - g), gpu_groups);
         const uint32_t n_rs = min(gi1 * a.gr, a.tpu) - gi0 * a.gr;
         const int32_t k = (int32_t)(__ldg(&a.units[u].kf) & 0xFFFFu);
-        if (first) red_release_add_u32<SLAB>(done + k + 1, n_rs);
-        else red_relaxed_add_u32(done + k + 1, n_rs);
+        if (first) {
+          if (sys) red_release_add_u32<true>(done + k + 1, n_rs);
+          else red_release_add_u32<false>(done + k + 1, n_rs);
+        } else {
+          red_relaxed_add_u32(done + k + 1, n_rs);
+        }
         first = false;
         if (SLAB && a.push) {
           if (k == 0) red_relaxed_sys_add_u32(a.peer_done_dn + (size_t)r * a.done_stride + (uint32_t)N2 + 1u, n_rs);
