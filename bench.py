@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--box", type=int, default=N_BOX)
+    ap.add_argument("--layers", type=int, default=0, help="tuning runs: N2 of a (box, box, layers) supercell on one GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator)")
@@ -288,7 +289,9 @@ def main():
 
     n_sites = N ** 3
     if world == 1:
-        st = _capi.State(tables, (N, N, N))
+        if args.layers:
+            n_sites = N * N * args.layers
+        st = _capi.State(tables, (N, N, args.layers or N))
         st.set_eci(eci["index"], eci["value"])
         st.set_conditions(TEMPERATURE, ex)
         st.randomize(2026)
@@ -327,7 +330,7 @@ def main():
                                                                  else "k_sweep_generic")
         accept_rate = cnt[0].n_accept / cnt[0].n_attempt
         e2e = None
-        if not args.no_e2e:
+        if not args.no_e2e and not args.layers:
             e2e = e2e_single(torch, _capi, st, tables, eci, ex, N, K, S, args.sweep_flags)
         st.close()
     else:

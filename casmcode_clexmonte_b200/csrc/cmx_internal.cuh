@@ -207,7 +207,7 @@ struct cmx_state {
   int *d_flag = nullptr;               // device-side validation flag
   bool async_upload_pending = false;   // an asynchronous upload has not been checked yet
   // slab decomposition over NVLink peer memory (cmx_state_ipc_attach):
-  // d_sig[3]: a dependency wait timed out ([0..2] unused)
+  // d_sig[0] / [1]: ring epochs (thin slabs), [3]: a dependency wait timed out
   unsigned long long *d_sig = nullptr;
   bool p2p = false;
   int8_t *peer_occ_dn = nullptr, *peer_occ_up = nullptr;
@@ -220,6 +220,9 @@ struct cmx_state {
   uint32_t *d_done = nullptr;
   uint32_t *peer_done_dn = nullptr, *peer_done_up = nullptr;
   uint32_t done_even = 0, done_odd = 0;
+  // thin slabs (k_sweep_pass16): k-colour groups completed by this rank; d_sig[0] / [1]: the
+  // epoch my lower / upper ring neighbour reached (written by them)
+  unsigned long long epoch = 0;
   // scratch
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;

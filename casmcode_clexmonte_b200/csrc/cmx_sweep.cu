@@ -1171,6 +1171,36 @@ static StreamKernel stream_kernel(const cmx_state *s, bool accum, bool slab, siz
   return fcc ? stream_kernel_nm<2, kMaskFcc1NN>(accum, slab, full) : stream_kernel_nm<2, 0u>(accum, slab, full);
 }
 
+typedef void (*PassKernel)(S16Args, PassArgs);
+template <int NOCC, uint32_t MASK, bool FULL>
+static PassKernel pass_kernel_nmf(bool accum) {
+  return accum ? k_sweep_pass16<NOCC, MASK, true, true, FULL> : k_sweep_pass16<NOCC, MASK, false, true, FULL>;
+}
+static PassKernel pass_kernel(const cmx_state *s, bool accum, size_t *smem) {
+  const SweepPlan &P = s->plan;
+  const bool fcc = (P.mask == kMaskFcc1NN);
+  const uint32_t rpw = 32u / ((uint32_t)s->g.N0 / 16u);
+  const bool full = ((uint32_t)s->g.N1 / 2u) % rpw == 0;
+  if (P.nocc == 3) {
+    *smem = s16_smem_bytes<3>(fcc ? kMaskFcc1NN : 0u);
+    if (fcc) return full ? pass_kernel_nmf<3, kMaskFcc1NN, true>(accum) : pass_kernel_nmf<3, kMaskFcc1NN, false>(accum);
+    return full ? pass_kernel_nmf<3, 0u, true>(accum) : pass_kernel_nmf<3, 0u, false>(accum);
+  }
+  *smem = s16_smem_bytes<2>(fcc ? kMaskFcc1NN : 0u);
+  if (fcc) return full ? pass_kernel_nmf<2, kMaskFcc1NN, true>(accum) : pass_kernel_nmf<2, kMaskFcc1NN, false>(accum);
+  return full ? pass_kernel_nmf<2, 0u, true>(accum) : pass_kernel_nmf<2, 0u, false>(accum);
+}
+
+// Peer-attached slabs too thin for the streaming schedule (see k_sweep_pass16): colour passes
+// with grid barriers.  Decided by the geometry alone, so a state never mixes the two ring
+// protocols (layer counters / epochs).
+static bool use_slab_pass(const cmx_state *s) {
+  static const int force = env_int("CMX_SLAB_PASS", -1);  // 1 / 0: always / never
+  if (!(s->p2p && s->g.halo) || !use_stream(s)) return false;
+  if (force >= 0) return force != 0;
+  return s->g.N2 / 2 < 128;
+}
+
 // geometry of the schedule: row-steps per unit, blocks per replica, row-steps per group,
 // and the distance (in units) the list keeps between dependent units
 static int stream_geometry(cmx_state *s) {
@@ -1179,14 +1209,16 @@ static int stream_geometry(cmx_state *s) {
   const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
   const bool slab = s->p2p && g.halo;
   size_t smem = 0;
-  StreamKernel kern = stream_kernel(s, accum, slab, &smem);
+  const void *kern = use_slab_pass(s) ? (const void *)pass_kernel(s, accum, &smem)
+                                      : (const void *)stream_kernel(s, accum, slab, &smem);
   CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0, dev = 0, sms = 0, can = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess) per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
-  per_sm = std::min(per_sm, std::max(sweep_grid_per_sm(), CMX_S16_MINB));
+  static const int stream_per_sm = env_int("CMX_STREAM_BLOCKS_PER_SM", CMX_S16_MINB);
+  per_sm = std::min(per_sm, stream_per_sm);
   P.stream_capacity = can ? per_sm * sms : 0;
   if (P.stream_capacity < s->n_replicas) {
     cmx_set_error("streaming sweep: the replicas do not fit a co-resident grid on this device");
@@ -1490,6 +1522,64 @@ static int sweep_stream(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_
   return CMX_OK;
 }
 
+// thin peer-attached slabs: n_sweeps whole sweeps as colour passes in cooperative launches
+static int sweep_slab_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps) {
+  SweepPlan &P = s->plan;
+  const Geom &g = s->g;
+  int rc = pair_tables(s);
+  if (rc) return rc;
+  const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
+  size_t smem = 0;
+  PassKernel kern = pass_kernel(s, accum, &smem);
+  S16Args a;
+  memset(&a, 0, sizeof(a));
+  a.occ = s->d_occ;
+  a.g = g;
+  a.mask = P.mask;
+  a.W = (uint32_t)g.N0 / 16;
+  a.logW = 0;
+  while ((1u << a.logW) < a.W) ++a.logW;
+  a.J = (uint32_t)g.N1 / 2;
+  const uint32_t rpw = 32u / a.W;
+  a.tpu = (a.J + rpw - 1) / rpw;
+  a.tab24 = P.d_tab24;
+  a.thr_lo = P.d_thr_lo;
+  a.dEpot = P.d_dEpot;
+  a.part_acc = P.d_part_acc;
+  a.part_dE = P.d_part_dE;
+  a.part_stride = (uint32_t)P.part_blocks;
+  a.k0 = (uint32_t)seed;
+  a.k1 = (uint32_t)(seed >> 32);
+  a.rk = philox_key_schedule(a.k0, a.k1);
+  a.k_offset = s->k_offset;
+  a.wrap_j = (g.N1 - 1) * g.N0;
+  a.layer = g.N0 * g.N1;
+  a.wrap_k = (g.N2 - 1) * a.layer;
+  a.peer_dn = s->peer_occ_dn;
+  a.peer_up = s->peer_occ_up;
+  a.push = 1;
+  a.fail = s->d_sig + 3;
+  PassArgs c;
+  c.div_tpu = make_fastdiv(a.tpu);
+  c.H = (uint32_t)g.N2 / 2;
+  c.my_sig = s->d_sig;
+  c.peer_sig_dn = s->peer_sig_dn;
+  c.peer_sig_up = s->peer_sig_up;
+  const uint32_t n_rs = a.tpu * c.H;
+  dim3 grid(std::min<uint32_t>((uint32_t)P.stream_blocks, (n_rs + 7) / 8), (unsigned)s->n_replicas);
+  for (int64_t done = 0; done < n_sweeps;) {
+    const int64_t n = std::min<int64_t>(n_sweeps - done, 1 << 20);
+    c.n_sweeps = (uint32_t)n;
+    c.first_sweep = (unsigned long long)(first_sweep + done);
+    c.epoch0 = s->epoch;
+    void *args[2] = {&a, &c};
+    CMX_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(256), args, smem, s->stream));
+    s->epoch += 2ull * (unsigned long long)n;
+    done += n;
+  }
+  return CMX_OK;
+}
+
 // one pass over the colours whose k-colour equals kgroup (or all if < 0): block pair-LUT
 // kernel (states with linear rows) or the generic evaluators
 static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
@@ -1788,7 +1878,7 @@ extern "C" int cmx_sgc_sweep_slab(cmx_state *s, int64_t n_sweeps, uint64_t seed,
     return CMX_ERR_UNSUPPORTED;
   }
   if (n_sweeps == 0) return CMX_OK;
-  rc = sweep_stream(s, seed, first_sweep, n_sweeps, -1);
+  rc = use_slab_pass(s) ? sweep_slab_pass(s, seed, first_sweep, n_sweeps) : sweep_stream(s, seed, first_sweep, n_sweeps, -1);
   if (rc) return rc;
   s->plan.attempts += (long long)s->g.n_cells * (long long)s->plan.mut_points.size() * n_sweeps;
   return CMX_OK;

@@ -848,3 +848,183 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_stream16(S16Args a)
     a.part_dE[slot] += E;
   }
 }
+
+// ---- thin slabs: colour passes with grid barriers ----------------------------------------
+// The streaming schedule needs dependent units a few hundred microseconds of work apart;
+// a slab of a few dozen layers (a 512^3 box over 4 or 8 GPUs) is a sweep of ~20-40 us, in
+// which every link of the colour chain (row colour 0 -> 1 -> other k colour ...) has only a
+// quarter of that: the completion latency of a unit (~5 us: row-step, release fence, poll)
+// cannot hide and the dataflow degenerates into waiting.  Such slabs run the same row-step
+// as plain colour passes: n_sweeps x 4 passes in ONE cooperative launch, a grid barrier
+// after every pass, the rows of a pass dealt round robin to the warps.  Halo exchange over
+// peer memory as in the streaming kernel (boundary rows are also stored into the ring
+// neighbour's ghost layer); the ring is ordered by epochs = completed k-colour groups: a
+// pass waits for both neighbours' epoch in its boundary row-steps only, which come LAST
+// (the layers are visited in rotated order), and block 0 publishes the epoch after the
+// barrier that ends a group.
+struct PassArgs {
+  uint32_t n_sweeps;
+  unsigned long long first_sweep;
+  unsigned long long epoch0;   // k-colour groups this rank completed before the launch
+  FastDiv div_tpu;
+  uint32_t H;                  // layers of one k colour
+  unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, bool FULL>
+__global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, PassArgs c) {
+  constexpr int NTAB = CMX_TAB24(NOCC);
+  constexpr int NTAB16 = CMX_TAB16(NOCC);
+  constexpr uint32_t NSLOT = s16_n_slots(MASK_CT);
+  extern __shared__ __align__(16) unsigned char sh_dyn[];
+  uint32_t *sh_tab = reinterpret_cast<uint32_t *>(sh_dyn);
+  unsigned char *sh_rows = sh_dyn + NTAB * 4;
+  __shared__ long long sh_acc[8];
+  __shared__ double sh_sum[8];
+  namespace cgr = cooperative_groups;
+  cgr::grid_group grid = cgr::this_grid();
+  const uint32_t r = blockIdx.y;
+  s16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)r * NTAB);
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  S16Lane L;
+  {
+    L.r = r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(L.tab) : "r"((uint32_t)__cvta_generic_to_shared(sh_tab)));
+    L.dEpot = a.dEpot + (size_t)r * NTAB16;
+    L.thr_lo = a.thr_lo + (size_t)r * NTAB16;
+    L.base = a.occ + (size_t)r * a.g.rep_stride;
+    const uint32_t Wm = a.W - 1u;
+    L.c = lane & Wm;
+    L.lane_l = (lane & ~Wm) | ((L.c - 1u) & Wm);
+    L.lane_r = (lane & ~Wm) | ((L.c + 1u) & Wm);
+    L.rot_l = (L.c == 0) ? 8u : 0u;
+    L.rot_r = (L.c == Wm) ? 8u : 0u;
+  }
+  const uint32_t rl = lane >> a.logW, rpw_log = 5u - a.logW;
+  const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_S16_SLOT) + 16u * lane;
+  const int32_t N2 = a.g.N2;
+  const bool halo = a.g.halo != 0;
+  int32_t n_acc = 0;
+  long long n_acc64 = 0;
+  double e_tot = 0.0;
+  __syncthreads();
+  const uint32_t warp0 = blockIdx.x * 8u + wib, n_warps = gridDim.x * 8u;
+  const uint32_t n_rs = a.tpu * c.H;  // row-steps of one colour pass
+  unsigned long long epoch = c.epoch0;
+  const bool ring = SLAB && a.push;
+  const bool publisher = ring && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  auto publish = [&]() {
+    // every store of the finished groups (the ones into the neighbours' ghost layers
+    // included: the grid barrier ordered them before this thread) precedes the epoch
+    __threadfence_system();
+    st_release_sys_u64(c.peer_sig_dn + 1, epoch);  // I am their upper neighbour
+    st_release_sys_u64(c.peer_sig_up + 0, epoch);  // I am their lower neighbour
+  };
+  if (publisher && epoch) publish();  // what the previous launches completed (idempotent)
+  bool dead = false;
+  uint32_t it = 0;
+  for (uint32_t s = 0; s < c.n_sweeps && !dead; ++s) {
+    const unsigned long long sweep = c.first_sweep + s;
+    const uint32_t sweep_lo = (uint32_t)sweep;
+    for (int cz = 0; cz < 2 && !dead; ++cz) {
+      for (int cy = 0; cy < 2 && !dead; ++cy) {
+        const uint32_t ctr_hi = ((uint32_t)(sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
+        // the layer next to a ghost layer (k = 0 for cz = 0, k = N2-1 for cz = 1) comes last
+        const uint32_t rot = (ring && cz == 0) ? 1u : 0u;
+        struct Pos {
+          int8_t *pc;
+          uint32_t gid;
+          int32_t j, k, dkm, dkp;
+          bool on;
+        };
+        auto locate = [&](uint32_t q, Pos &p) {
+          uint32_t kk, rsu;
+          fastdivmod(q, c.div_tpu, kk, rsu);
+          kk += rot;
+          if (kk >= c.H) kk -= c.H;
+          p.k = 2 * (int32_t)kk + cz;
+          const uint32_t jj = (rsu << rpw_log) + rl;
+          p.on = FULL ? true : (jj < a.J);
+          p.j = 2 * (int32_t)(p.on ? jj : a.J - 1u) + cy;
+          const uint32_t row = (uint32_t)(p.k + a.g.halo) * (uint32_t)a.g.N1 + (uint32_t)p.j;
+          p.pc = L.base + ((size_t)row * (uint32_t)a.g.N0 + 16u * L.c);
+          p.gid = ((uint32_t)(p.k + a.k_offset) * (uint32_t)a.g.N1 + (uint32_t)p.j) * a.W + L.c;
+          p.dkm = (!halo && p.k == 0) ? a.wrap_k : -a.layer;
+          p.dkp = (!halo && p.k == N2 - 1) ? -a.wrap_k : a.layer;
+        };
+        auto wait_neighbours = [&](int32_t k) {
+          if (!ring || !epoch || !(k == 0 || k == N2 - 1)) return;  // (warp-uniform: a row-step lies in one layer)
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(c.my_sig + 0) < epoch || ld_acquire_sys_u64(c.my_sig + 1) < epoch) {
+              if (clock64() - t0 > 20000000000ll) {  // ~10 s: a neighbour is gone
+                *reinterpret_cast<volatile unsigned long long *>(a.fail) = 1ull;
+                break;
+              }
+              __nanosleep(100);
+            }
+          }
+          __syncwarp();
+        };
+        Pos cur, nxt;
+        uint32_t q = warp0;
+        if (q < n_rs) {
+          locate(q, nxt);
+          wait_neighbours(nxt.k);
+          s16_issue<MASK_CT>(a, nxt.pc, nxt.j, nxt.dkm, nxt.dkp, slots);
+        }
+        for (; q < n_rs; q += n_warps) {
+          cur = nxt;
+          const bool more = q + n_warps < n_rs;
+          if (more) locate(q + n_warps, nxt);
+          cp_async_wait_all();
+          auto stage_next = [&]() {
+            if (more) {
+              wait_neighbours(nxt.k);
+              s16_issue<MASK_CT>(a, nxt.pc, nxt.j, nxt.dkm, nxt.dkp, slots);
+            }
+          };
+          s16_rowstep<NOCC, MASK_CT, ACCUM, SLAB>(a, L, cur.pc, cur.gid, cur.k, sweep_lo, ctr_hi, cur.on, n_acc, e_tot, slots,
+                                                  stage_next);
+          if ((++it & 0xFFFFFu) == 0) {
+            n_acc64 += n_acc;
+            n_acc = 0;
+          }
+        }
+        grid.sync();  // every store of the pass, the ones into the neighbours' ghost layers included
+      }
+      ++epoch;
+      if (publisher) publish();
+    }
+  }
+  n_acc64 += n_acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_acc64 += __shfl_down_sync(0xffffffffu, n_acc64, o);
+    e_tot += __shfl_down_sync(0xffffffffu, e_tot, o);
+  }
+  if (lane == 0) {
+    sh_acc[wib] = n_acc64;
+    sh_sum[wib] = e_tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long A = 0;
+    double E = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      A += sh_acc[w];
+      E += sh_sum[w];
+    }
+    const size_t slot = (size_t)r * a.part_stride + blockIdx.x;
+    a.part_acc[slot] += A;
+    a.part_dE[slot] += E;
+  }
+}
