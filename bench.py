@@ -201,7 +201,7 @@ def bench_slabs(torch, dist, runner, K: int, W: int, S: int, no_e2e: bool = Fals
     cnt = runner.counters()
     clk = clocks.stop(t0, t1)
     n_sites = runner.N[0] * runner.N[1] * runner.N[2] * runner.n_sublat
-    stream = bool(runner.p2p and runner.info()["stream"])
+    stream = bool(runner.p2p and runner.info()["one_launch_per_call"])
     lps = runner.info()["launches_per_sweep"]
     launches = K if stream else K * S * max(lps, 1)
     e2e = None
@@ -243,7 +243,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="tuning runs: N2 of a (box, box, layers) supercell on one GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator)")
+    ap.add_argument("--sweep-flags", type=int, default=0, help="CMX_SWEEP_* bits (1 = dE sum, 2 = generic evaluator, 8 = streaming kernel)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -326,8 +326,8 @@ def main():
         sweeps_per_launch = float(S) if lps == 0 else 1.0 / lps
         launches = sweep_launches + 1          # + the counter reduction
         kernel_ms = ms / sweep_launches
-        kernel_name = "k_sweep_stream16" if info["stream"] else ("k_sweep_pair16" if info["evaluator"] == "pair_lut"
-                                                                 else "k_sweep_generic")
+        kernel_name = ("k_sweep_stream16" if info["stream"] else "k_sweep_pass16" if info["one_launch_per_call"]
+                       else "k_sweep_pair16" if info["evaluator"] == "pair_lut" else "k_sweep_generic")
         accept_rate = cnt[0].n_accept / cnt[0].n_attempt
         e2e = None
         if not args.no_e2e and not args.layers:
@@ -341,7 +341,7 @@ def main():
         ms, clk, e2e, accept_rate = res["ms"], res["clocks"], res["e2e"], res["accept_rate"]
         value = K * S * n_sites / (ms * 1e-3)
         launches, kernel_ms, sweeps_per_launch = res["launches"], res["kernel_ms"], res["sweeps_per_launch"]
-        kernel_name = "k_sweep_stream16" if res["stream"] else "k_sweep_pair16"
+        kernel_name = ("k_sweep_stream16" if info["stream"] else "k_sweep_pass16") if res["stream"] else "k_sweep_pair16"
         if rank != 0:
             return
 
@@ -355,8 +355,8 @@ def main():
     # DRAM traffic of one launch and the binding resource from the committed ncu --set full
     # capture of this kernel at this workload (512^3, one GPU, S sweeps per launch); null otherwise
     traffic, binding = None, None
-    prof = ROOT / "profiles" / "r02_ncu_full_k_sweep_stream16.csv"
-    if world == 1 and args.box == N_BOX and kernel_name == "k_sweep_stream16" and prof.exists():
+    prof = ROOT / "profiles" / f"r02_ncu_full_{kernel_name}.csv"
+    if world == 1 and args.box == N_BOX and not args.layers and prof.exists():
         import csv
         m = {}
         for row in csv.reader(prof.open()):

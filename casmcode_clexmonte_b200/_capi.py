@@ -21,6 +21,7 @@ LIB_PATH = HERE / "libcmx_b200.so"
 CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
 CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC = 1, 2
 CMX_SWEEP_THREAD_GENERIC = 16
+CMX_SWEEP_STREAM = 8
 CMX_STATE_LINEAR_ROWS = 1
 
 # every symbol include/cmx_b200.h declares
@@ -477,7 +478,7 @@ class State:
             pass
         return dict(evaluator=name.value.decode(), bytes_per_step=b.value, flops_per_step=f.value,
                     n_colours=nc.value, colour_strides=tuple(S), range_k=rk.value,
-                    launches_per_sweep=nl.value, stream=bool(st.value), stream_blocks=sb.value,
+                    launches_per_sweep=nl.value, one_launch_per_call=(nl.value == 0), stream=bool(st.value), stream_blocks=sb.value,
                     stream_group_rowsteps=gr.value, stream_gap_units=gap.value)
 
     def sweep_debug_delta_e(self, l, new_occ, replica: int = 0) -> np.ndarray:

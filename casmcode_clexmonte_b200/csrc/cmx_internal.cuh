@@ -156,6 +156,7 @@ struct SweepPlan {
   };
   std::map<std::pair<int, int>, StreamList> stream_lists;
   uint32_t *d_ticket = nullptr;   // [replica] group tickets of the streaming kernel (dynamic assignment)
+  bool l2_window_set = false;     // persisting-L2 window of the lattice decided (colour passes on one GPU)
   int stream_capacity = -1;       // co-resident blocks of the kernel chosen for this state
   int stream_blocks = 0;          // blocks per replica
   uint32_t stream_gr = 1;         // row-steps per group

@@ -1191,14 +1191,13 @@ static PassKernel pass_kernel(const cmx_state *s, bool accum, size_t *smem) {
   return full ? pass_kernel_nmf<2, 0u, true>(accum) : pass_kernel_nmf<2, 0u, false>(accum);
 }
 
-// Peer-attached slabs too thin for the streaming schedule (see k_sweep_pass16): colour passes
-// with grid barriers.  Decided by the geometry alone, so a state never mixes the two ring
-// protocols (layer counters / epochs).
-static bool use_slab_pass(const cmx_state *s) {
-  static const int force = env_int("CMX_SLAB_PASS", -1);  // 1 / 0: always / never
-  if (!(s->p2p && s->g.halo) || !use_stream(s)) return false;
-  if (force >= 0) return force != 0;
-  return s->g.N2 / 2 < 128;
+// x4-interleaved rows: colour passes with grid barriers (k_sweep_pass16, the default: measured
+// faster than the streaming kernel on every configuration of this round) unless
+// CMX_SWEEP_STREAM asks for the barrier-free streaming kernel.  Slab states decide once (they
+// must not mix the two ring protocols, layer counters / epochs): the flag as it is when the
+// first sweep runs.
+static bool use_pass(const cmx_state *s) {
+  return use_stream(s) && !(s->sweep_flags & CMX_SWEEP_STREAM);
 }
 
 // geometry of the schedule: row-steps per unit, blocks per replica, row-steps per group,
@@ -1209,7 +1208,7 @@ static int stream_geometry(cmx_state *s) {
   const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
   const bool slab = s->p2p && g.halo;
   size_t smem = 0;
-  const void *kern = use_slab_pass(s) ? (const void *)pass_kernel(s, accum, &smem)
+  const void *kern = use_pass(s) ? (const void *)pass_kernel(s, accum, &smem)
                                       : (const void *)stream_kernel(s, accum, slab, &smem);
   CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0, dev = 0, sms = 0, can = 0;
@@ -1522,8 +1521,43 @@ static int sweep_stream(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_
   return CMX_OK;
 }
 
+// A lattice a little larger than L2 (512^3: 134 MB against 126 MB): pin as much of it as the
+// device allows as PERSISTING L2 lines for the state's stream; those layers then never go
+// back to DRAM between the four colour passes of a sweep, only the remainder streams.
+// (Together with the alternating pass direction: measured DRAM traffic per sweep 2.4x ->
+// see profiles/.)  No effect on lattices that fit L2 anyway, or on slabs.
+static int l2_persist_lattice(cmx_state *s) {
+  SweepPlan &P = s->plan;
+  if (P.l2_window_set) return CMX_OK;
+  P.l2_window_set = true;
+  static const int off = env_int("CMX_NO_L2_PERSIST", 0);
+  const size_t bytes = (size_t)s->g.rep_stride * s->n_replicas;
+  int dev = 0, l2 = 0, max_persist = 0, max_window = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  if (off || max_persist <= 0 || bytes <= (size_t)l2 / 2) return CMX_OK;
+  static const int frac_env = env_int("CMX_L2_PERSIST_PCT", 100);
+  size_t want = std::min<size_t>((size_t)max_persist * (size_t)frac_env / 100, (size_t)max_window);
+  want = std::min(want, bytes);
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+    cudaGetLastError();
+    return CMX_OK;
+  }
+  cudaStreamAttrValue av;
+  memset(&av, 0, sizeof(av));
+  av.accessPolicyWindow.base_ptr = s->d_occ;
+  av.accessPolicyWindow.num_bytes = want;
+  av.accessPolicyWindow.hitRatio = 1.0f;
+  av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+  return CMX_OK;
+}
+
 // thin peer-attached slabs: n_sweeps whole sweeps as colour passes in cooperative launches
-static int sweep_slab_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps) {
+static int sweep_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps, int kgroup) {
   SweepPlan &P = s->plan;
   const Geom &g = s->g;
   int rc = pair_tables(s);
@@ -1557,15 +1591,17 @@ static int sweep_slab_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int
   a.wrap_k = (g.N2 - 1) * a.layer;
   a.peer_dn = s->peer_occ_dn;
   a.peer_up = s->peer_occ_up;
-  a.push = 1;
+  a.push = (s->p2p && g.halo) ? 1 : 0;
   a.fail = s->d_sig + 3;
   PassArgs c;
   c.div_tpu = make_fastdiv(a.tpu);
   c.H = (uint32_t)g.N2 / 2;
+  c.kgroup = kgroup;
   c.my_sig = s->d_sig;
   c.peer_sig_dn = s->peer_sig_dn;
   c.peer_sig_up = s->peer_sig_up;
   const uint32_t n_rs = a.tpu * c.H;
+  if (!g.halo && (rc = l2_persist_lattice(s))) return rc;
   dim3 grid(std::min<uint32_t>((uint32_t)P.stream_blocks, (n_rs + 7) / 8), (unsigned)s->n_replicas);
   for (int64_t done = 0; done < n_sweeps;) {
     const int64_t n = std::min<int64_t>(n_sweeps - done, 1 << 20);
@@ -1574,7 +1610,7 @@ static int sweep_slab_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int
     c.epoch0 = s->epoch;
     void *args[2] = {&a, &c};
     CMX_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(256), args, smem, s->stream));
-    s->epoch += 2ull * (unsigned long long)n;
+    if (a.push) s->epoch += 2ull * (unsigned long long)n;
     done += n;
   }
   return CMX_OK;
@@ -1759,7 +1795,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
-  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_THREAD_GENERIC))
+  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_THREAD_GENERIC | CMX_SWEEP_STREAM))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;      // the grid may change with the evaluator
@@ -1819,7 +1855,10 @@ int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int6
   if (rc) return rc;
   if (s->g.halo) return invalid("cmx_sgc_sweep: slab states are driven by cmx_sgc_sweep_kgroup / cmx_sgc_sweep_slab");
   if (use_stream(s)) {
-    if (n_sweeps > 0 && (rc = sweep_stream(s, seed, first_sweep, n_sweeps, -1))) return rc;
+    if (n_sweeps > 0) {
+      rc = use_pass(s) ? sweep_pass(s, seed, first_sweep, n_sweeps, -1) : sweep_stream(s, seed, first_sweep, n_sweeps, -1);
+      if (rc) return rc;
+    }
   } else {
     for (int64_t w = 0; w < n_sweeps; ++w) {
       rc = sweep_once(s, seed, first_sweep + w, -1, 0);
@@ -1854,7 +1893,7 @@ extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
   if (use_stream(s)) {
     if (s->p2p && s->g.halo && kgroup >= 0)
       return invalid("cmx_sgc_sweep_kgroup: peer-attached slabs sweep with cmx_sgc_sweep_slab");
-    rc = sweep_stream(s, seed, sweep, 1, kgroup);
+    rc = use_pass(s) ? sweep_pass(s, seed, sweep, 1, kgroup) : sweep_stream(s, seed, sweep, 1, kgroup);
   } else {
     rc = sweep_once(s, seed, sweep, kgroup, s->k_offset);
   }
@@ -1878,7 +1917,7 @@ extern "C" int cmx_sgc_sweep_slab(cmx_state *s, int64_t n_sweeps, uint64_t seed,
     return CMX_ERR_UNSUPPORTED;
   }
   if (n_sweeps == 0) return CMX_OK;
-  rc = use_slab_pass(s) ? sweep_slab_pass(s, seed, first_sweep, n_sweeps) : sweep_stream(s, seed, first_sweep, n_sweeps, -1);
+  rc = use_pass(s) ? sweep_pass(s, seed, first_sweep, n_sweeps, -1) : sweep_stream(s, seed, first_sweep, n_sweeps, -1);
   if (rc) return rc;
   s->plan.attempts += (long long)s->g.n_cells * (long long)s->plan.mut_points.size() * n_sweeps;
   return CMX_OK;
@@ -1911,7 +1950,7 @@ extern "C" int cmx_sweep_stream_info(cmx_state *s, int32_t *stream, int32_t *blo
                                      int32_t *gap_units) {
   int rc = sweep_prepare(s, "cmx_sweep_stream_info");
   if (rc) return rc;
-  const bool on = use_stream(s);
+  const bool on = use_stream(s) && !use_pass(s);
   if (stream) *stream = on ? 1 : 0;
   if (blocks) *blocks = on ? s->plan.stream_blocks : 0;
   if (group_rowsteps) *group_rowsteps = on ? (int32_t)s->plan.stream_gr : 0;
@@ -1925,7 +1964,7 @@ extern "C" int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep) {
     cmx_set_error("cmx_sweep_launches: no sweep plan");
     return CMX_ERR_STATE;
   }
-  *per_sweep = use_stream(s) ? 0 : (use_pair(s) ? 4 : s->plan.n_colours);
+  *per_sweep = use_stream(s) ? 0 : (use_pair(s) ? 4 : s->plan.n_colours);  // 0: one launch per call
   return CMX_OK;
 }
 

@@ -750,15 +750,13 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_stream16(S16Args a)
   // group assignment: static round robin, or tickets (a free warp takes the oldest group
   // nobody has started: slow warps then simply take fewer, and the groups in flight stay
   // the oldest n_warps -- with the static deal every warp must keep the pace of the slowest)
-  auto take_ticket = [&]() -> uint32_t {
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(a.ticket + r, 1u);
-    return __shfl_sync(0xffffffffu, t, 0);
-  };
+  // (the ticket stays in lane 0 until it is needed: broadcasting it right away would make
+  // the warp wait for the atomic's round trip)
+  auto take_ticket = [&]() -> uint32_t { return (lane == 0) ? atomicAdd(a.ticket + r, 1u) : 0u; };
   S16Pos nxt;
   uint32_t g_first = warp0, tk_next = 0;
   if (a.ticket) {
-    g_first = take_ticket();
+    g_first = __shfl_sync(0xffffffffu, take_ticket(), 0);
     tk_next = take_ticket();
   }
   bool have = g_first < a.n_groups;
@@ -779,7 +777,7 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_stream16(S16Args a)
     if (!new_group) {
       advance(nxt);
     } else {
-      const uint32_t g2 = a.ticket ? tk_next : nxt.g + n_warps;
+      const uint32_t g2 = a.ticket ? __shfl_sync(0xffffffffu, tk_next, 0) : nxt.g + n_warps;
       more = g2 < a.n_groups;
       if (more) {
         decode(g2, nxt);
@@ -868,6 +866,7 @@ struct PassArgs {
   unsigned long long epoch0;   // k-colour groups this rank completed before the launch
   FastDiv div_tpu;
   uint32_t H;                  // layers of one k colour
+  int32_t kgroup;              // only this k colour (slabs whose halo the host exchanges), -1: both
   unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
 };
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
@@ -930,15 +929,21 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, P
   };
   if (publisher && epoch) publish();  // what the previous launches completed (idempotent)
   bool dead = false;
-  uint32_t it = 0;
+  uint32_t it = 0, pass_no = (uint32_t)(c.first_sweep & 1ull) * 0u;
   for (uint32_t s = 0; s < c.n_sweeps && !dead; ++s) {
     const unsigned long long sweep = c.first_sweep + s;
     const uint32_t sweep_lo = (uint32_t)sweep;
     for (int cz = 0; cz < 2 && !dead; ++cz) {
+      if (c.kgroup >= 0 && cz != c.kgroup) continue;
       for (int cy = 0; cy < 2 && !dead; ++cy) {
         const uint32_t ctr_hi = ((uint32_t)(sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
         // the layer next to a ghost layer (k = 0 for cz = 0, k = N2-1 for cz = 1) comes last
         const uint32_t rot = (ring && cz == 0) ? 1u : 0u;
+        // One box on one GPU: consecutive passes walk the layers in OPPOSITE directions.  A
+        // pass ends with the layers it touched last still in L2 (126 MB against a 134 MB
+        // lattice at 512^3), and that is where the next pass begins: most of its reads hit,
+        // only the far end comes from DRAM again -- no extra synchronisation, just the order.
+        const bool back = ((pass_no++) & 1u) != 0u;
         struct Pos {
           int8_t *pc;
           uint32_t gid;
@@ -948,8 +953,12 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, P
         auto locate = [&](uint32_t q, Pos &p) {
           uint32_t kk, rsu;
           fastdivmod(q, c.div_tpu, kk, rsu);
-          kk += rot;
-          if (kk >= c.H) kk -= c.H;
+          if (ring) {
+            kk += rot;
+            if (kk >= c.H) kk -= c.H;
+          } else if (back) {
+            kk = c.H - 1u - kk;  // see `back`
+          }
           p.k = 2 * (int32_t)kk + cz;
           const uint32_t jj = (rsu << rpw_log) + rl;
           p.on = FULL ? true : (jj < a.J);

@@ -239,12 +239,19 @@ int cmx_counters_reset(cmx_state *s);
  *                           decisions: a cross-check of the fast path) */
 #define CMX_SWEEP_DE_SUM 1u
 #define CMX_SWEEP_FORCE_GENERIC 2u
-/* pair-LUT kernels (the trajectory does not depend on the kernel): states with
+/* pair-LUT kernels (the trajectory does not depend on the kernel).  States with
  * x4-interleaved rows (cmx_state_create_opts) run a whole cmx_sgc_sweep call -- all its
- * sweeps, all colours -- as ONE cooperative launch of the streaming kernel
- * (k_sweep_stream16: per-layer completion counters instead of kernel boundaries or grid
- * barriers; every lattice byte crosses HBM once per sweep and direction); states with
- * linear rows launch the block kernel once per colour pass (k_sweep_pair16, 4 per sweep). */
+ * sweeps, all colours -- as ONE cooperative launch:
+ *   default           colour passes with a grid barrier after each (k_sweep_pass16);
+ *                     consecutive passes walk the layers in opposite directions and a
+ *                     lattice slightly larger than L2 is pinned there as far as the device
+ *                     allows, so a sweep reads most of it from L2
+ *   CMX_SWEEP_STREAM  the barrier-free streaming kernel (k_sweep_stream16): the units of the
+ *                     call in wavefront order, per-layer completion counters instead of
+ *                     barriers; every lattice byte crosses HBM once per sweep and direction
+ *                     whatever the lattice size.
+ * States with linear rows launch the block kernel once per colour pass (k_sweep_pair16). */
+#define CMX_SWEEP_STREAM 8u
 /* generic (term-list) evaluator variants: models with wide orbit sets (>= 96 merged
  * terms per site, e.g. ZrO with triplets and quadruplets) evaluate one site per WARP
  * (k_sweep_generic_warp, k_canonical_pairs_warp: neighborhood staged once, terms dealt
@@ -315,10 +322,11 @@ int cmx_canonical_info(const cmx_state *s, int32_t i, int32_t *strides /*[3]*/,
                        int32_t *n_colours);
 
 /* Kernel launches one full sweep takes with the current evaluator (block pair-LUT kernel:
- * 4 launches for 8 colours; generic: one per colour); 0 = the streaming kernel, which runs
- * a whole cmx_sgc_sweep call as one launch. */
+ * 4 launches for 8 colours; generic: one per colour); 0 = the kernels on x4-interleaved rows,
+ * which run a whole cmx_sgc_sweep call as one launch. */
 int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep);
-/* Schedule of the streaming kernel on this state: *stream = 1 when it is the evaluator,
+/* Schedule of the streaming kernel on this state: *stream = 1 when it is the evaluator
+ * (CMX_SWEEP_STREAM on a state with x4-interleaved rows),
  * *blocks = co-resident blocks per replica, *group_rowsteps = row-steps a warp takes at a
  * time, *gap_units = (layer, row colour) units the host keeps between dependent units. */
 int cmx_sweep_stream_info(cmx_state *s, int32_t *stream, int32_t *blocks, int32_t *group_rowsteps,

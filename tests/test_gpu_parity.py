@@ -230,12 +230,13 @@ def test_sweep_is_deterministic_and_replica_independent(dev_tables, systems):
     b.close()
 
 
-@pytest.mark.parametrize("kernel", ["stream", "block"])
+@pytest.mark.parametrize("kernel", ["pass", "stream", "block"])
 @pytest.mark.parametrize("N,n_replicas", [((16, 16, 16), 2), ((32, 8, 6), 1), ((48, 4, 4), 1), ((512, 2, 2), 1),
                                           ((128, 32, 4), 2), ((128, 24, 20), 3), ((64, 2, 2), 1), ((256, 6, 12), 1)])
 def test_pair_lut_kernels_equal_generic_kernel_bit_for_bit(dev_tables, systems, N, n_replicas, kernel):
-    """The pair-LUT kernels -- the streaming kernel on x4-interleaved rows (one cooperative
-    launch per call, per-layer completion counters) and the block kernel on linear rows --
+    """The pair-LUT kernels -- on x4-interleaved rows the colour-pass kernel (the default: one
+    cooperative launch per call, grid barriers) and the streaming kernel (CMX_SWEEP_STREAM:
+    per-layer completion counters instead of barriers), and the block kernel on linear rows --
     and the one-site-per-thread generic evaluator (whose delta E is checked against the
     reference kernels) draw the same random bits and must make the same decisions:
     identical occupation after several sweeps, identical acceptance counts.  Covers one
@@ -255,12 +256,14 @@ def test_pair_lut_kernels_equal_generic_kernel_bit_for_bit(dev_tables, systems, 
         ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.4], 3)
         a.set_conditions(500.0, ex2, replica=1)
         b.set_conditions(500.0, ex2, replica=1)
-    a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
+    kflag = _capi.CMX_SWEEP_STREAM if kernel == "stream" else 0
+    a.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM | kflag)
     b.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC | _capi.CMX_SWEEP_DE_SUM)
     ia = a.sweep_info()
     assert ia["evaluator"] == "pair_lut" and b.sweep_info()["evaluator"] == "generic"
     pow2 = N[0] <= 512 and (N[0] & (N[0] - 1)) == 0
     assert ia["stream"] == (kernel == "stream" and pow2)
+    assert ia["one_launch_per_call"] == (kernel != "block" and pow2)
     for r in range(n_replicas):
         assert (a.download_occ(r) == b.download_occ(r)).all()
     ca = a.sgc_sweep(6, seed=9)
@@ -272,7 +275,7 @@ def test_pair_lut_kernels_equal_generic_kernel_bit_for_bit(dev_tables, systems, 
         assert ca[r].n_accept == cb[r].n_accept and ca[r].n_attempt == cb[r].n_attempt
         assert ca[r].dE_sum == pytest.approx(cb[r].dE_sum, rel=1e-9, abs=1e-9)
     # without the dE accumulation (the default) the trajectory is the same
-    a.set_sweep_flags(0)
+    a.set_sweep_flags(kflag)
     ca = a.sgc_sweep(2, seed=9, first_sweep=6)
     cb = b.sgc_sweep(2, seed=9, first_sweep=6)
     for r in range(n_replicas):
@@ -326,12 +329,13 @@ def test_conditions_change_after_a_sweep_is_honoured(dev_tables, systems):
 @pytest.mark.parametrize("N,n_replicas,n_sweeps", [((512, 512, 512), 1, 6), ((128, 128, 128), 8, 6)])
 def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sweeps):
     """BASELINE sizes (configs[2]: 512^3; configs[1]: 128^3 replicas with a (mu, T) grid):
-    the streaming kernel and the generic one-site-per-thread evaluator must leave the SAME
-    occupation and the same acceptance counts.  Only at these sizes are all SMs busy and
-    the layer counters, the wavefront order and the seam of the periodic box really
-    exercised (thousands of warps in flight across tens of units)."""
+    the colour-pass kernel (the default), the streaming kernel and the generic
+    one-site-per-thread evaluator must leave the SAME occupation and the same acceptance
+    counts.  Only at these sizes are all SMs busy and the layer counters, the wavefront
+    order and the seam of the periodic box really exercised (thousands of warps in flight
+    across tens of units), and the persisting-L2 window of the pass kernel in effect."""
     mu = [0.0, 0.0]
-    variants = {"stream": 0, "generic": _capi.CMX_SWEEP_FORCE_GENERIC}
+    variants = {"pass": 0, "stream": _capi.CMX_SWEEP_STREAM, "generic": _capi.CMX_SWEEP_FORCE_GENERIC}
     ref_occ, ref_cnt = None, None
     for name, flags in variants.items():
         st, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 800.0, mu,
@@ -352,7 +356,7 @@ def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sw
             ref_occ, ref_cnt = occ, acc
             continue
         for r in range(n_replicas):
-            assert (occ[r] == ref_occ[r]).all(), f"{name} vs stream, replica {r}: {(occ[r] != ref_occ[r]).sum()} sites differ"
+            assert (occ[r] == ref_occ[r]).all(), f"{name} vs pass, replica {r}: {(occ[r] != ref_occ[r]).sum()} sites differ"
         assert acc == ref_cnt, name
 
 

@@ -12,7 +12,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, N, n_sweeps, p2p, out, calls=1):
+def _worker(rank, world, port, N, n_sweeps, p2p, out, calls=1, flags=0):
     import torch
     import torch.distributed as dist
     from casmcode_clexmonte_b200 import _capi
@@ -30,7 +30,7 @@ def _worker(rank, world, port, N, n_sweeps, p2p, out, calls=1):
     init = np.random.default_rng(4).integers(0, 3, int(np.prod(Nt))).astype(np.int8)
     run = SlabRunner(tables, Nt, sysd["eci_sparse"], 900.0, ex, rank, world, rank, init_occ=init, p2p=p2p)
     assert run.p2p == p2p
-    run.state.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
+    run.state.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM | flags)
     run.state.counters_reset()
     for c in range(calls):   # several calls: the layer counters carry over between launches
         run.sweep(n_sweeps, seed=17, first_sweep=c * n_sweeps)
@@ -71,12 +71,14 @@ def test_two_slabs_equal_one_gpu(p2p):
     st.close()
 
 
+@pytest.mark.parametrize("kernel", ["pass", "stream"])
 @pytest.mark.parametrize("world,N,n_sweeps,calls", [(2, (128, 64, 16), 3, 3), (4, (128, 64, 32), 3, 2),
                                                     (8, (128, 64, 64), 3, 2), (2, (512, 512, 128), 2, 2),
                                                     (4, (512, 512, 256), 2, 2), (8, (512, 512, 512), 2, 2)])
-def test_slabs_over_peer_memory_equal_one_gpu(world, N, n_sweeps, calls):
-    """2 / 4 / 8 slabs over NVLink peer memory (streaming kernel: boundary rows stored into
-    the ring neighbours' ghost layers and counted on their layer counters) leave the SAME
+def test_slabs_over_peer_memory_equal_one_gpu(world, N, n_sweeps, calls, kernel):
+    """2 / 4 / 8 slabs over NVLink peer memory (boundary rows are stored into the ring
+    neighbours' ghost layers by the sweep kernel itself; ordered by ring epochs in the
+    colour-pass kernel, by the neighbours' layer counters in the streaming kernel) leave the SAME
     occupation and acceptance counts as one GPU: small boxes whose slabs are a few layers
     thick (every unit touches a ghost layer or waits for one), and 64-layer slabs of
     512 x 512 layers -- the decomposition of BASELINE configs[2] (the 8-GPU case IS the
@@ -90,8 +92,10 @@ def test_slabs_over_peer_memory_equal_one_gpu(world, N, n_sweeps, calls):
         pytest.skip(f"needs {world} GPUs")
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29700 + os.getpid() % 1000 + world
-    mp.spawn(_worker, args=(world, port, N, n_sweeps, True, out, calls), nprocs=world, join=True)
+    port = 29700 + os.getpid() % 1000 + world + (50 if kernel == "stream" else 0)
+    from casmcode_clexmonte_b200 import _capi as _c
+    flags = _c.CMX_SWEEP_STREAM if kernel == "stream" else 0
+    mp.spawn(_worker, args=(world, port, N, n_sweeps, True, out, calls, flags), nprocs=world, join=True)
     sysd = json.loads((GOLDEN / "systems.json").read_text())["fcc"]
     tables = _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz"))
     st = _capi.State(tables, N)
@@ -120,9 +124,10 @@ def test_one_slab_with_fused_halo_equals_periodic_box():
     ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [0.1, -0.2], 3)
     init = np.random.default_rng(4).integers(0, 3, N ** 3).astype(np.int8)
     res = {}
-    for p2p in (True, False):
-        run = SlabRunner(tables, N, sysd["eci_sparse"], 900.0, ex, 0, 1, 0, init_occ=init, p2p=p2p)
-        assert run.p2p == p2p
+    for p2p, flags in ((True, 0), (False, 0), ("stream", _capi.CMX_SWEEP_STREAM), ("stream_host", _capi.CMX_SWEEP_STREAM)):
+        run = SlabRunner(tables, N, sysd["eci_sparse"], 900.0, ex, 0, 1, 0, init_occ=init,
+                         p2p=(p2p is True or p2p == "stream"))
+        run.state.set_sweep_flags(flags)
         run.state.counters_reset()
         run.sweep(n_sweeps, seed=17)
         run.synchronize()
@@ -134,7 +139,7 @@ def test_one_slab_with_fused_halo_equals_periodic_box():
     st.upload_occ(init)
     cnt = st.sgc_sweep(n_sweeps, seed=17)
     ref = st.download_occ(dtype=np.int8)
-    for p2p in (True, False):
+    for p2p in res:
         assert (res[p2p][0] == ref).all(), f"p2p={p2p}"
         assert res[p2p][1] == cnt[0].n_accept
     st.close()
