@@ -233,12 +233,149 @@ def bench_slabs(torch, dist, runner, K: int, W: int, S: int, no_e2e: bool = Fals
 
 
 # ---------------------------------------------------------------------------
+# replica grids / KMC trajectories dealt over the GPUs (BASELINE configs[1], [4])
+# ---------------------------------------------------------------------------
+def bench_replicas(args, torch, _capi, rank, world, local_rank):
+    """Independent replicas: every rank runs its share, ONE NCCL all-reduce of statistics at
+    the end (inside the timed region).  Whole-job rate = all replicas / max-over-ranks time;
+    the total work is fixed (strong scaling)."""
+    from casmcode_clexmonte_b200 import kmc as K
+    from casmcode_clexmonte_b200.clexulator_tables import ClexulatorTables
+    from casmcode_clexmonte_b200.replicas import KmcEnsembleRunner, ReplicaRunner
+    dist = None
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+        dist.all_reduce(torch.zeros(1, dtype=torch.float64, device=device))   # communicator set-up is not the workload
+    sysd = load_system()
+    K_, W_ = args.steps, max(3, args.warmup)
+    tb = lambda n: _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / f"{n}.npz"), device=local_rank)  # noqa: E731
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "c2":
+        N, S = 128, SWEEPS_PER_STEP
+        conds = [{"temperature": float(T), "param_chem_pot": [float(mu), 0.0]}
+                 for mu in np.linspace(-1, 1, 8) for T in np.arange(400.0, 1801.0, 200.0)]
+        run = ReplicaRunner(tb("fcc_default"), (N, N, N), sysd, sysd["eci_sparse"], conds, rank, world,
+                            n_samples=K_ + 1, seed_init=7)
+        run.state.sgc_sweep(W_ * S, seed=1, counters=False)
+        run.sampler.reset()
+        barrier()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        time.sleep(0.3)
+        stream = torch.cuda.ExternalStream(run.state.stream())
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        ev0.record(stream)
+        cnt = run.sampler.run(K_, S, seed=1 + rank, first_sweep=W_ * S)   # K samples, S passes apart
+        res = run.reduce(dist, device)                                     # ONE all-reduce of the moments
+        ev1.record(stream)
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        clk = clocks.stop(t0, t1)
+        n_sites = len(conds) * N ** 3
+        value = K_ * S * n_sites / (ms * 1e-3)
+        info = run.state.sweep_info()
+        metric = "attempted MC steps/sec (FCC ternary SGC, 64 replicas x 128^3)"
+        workload = ("FCC A-B-Va semi-grand canonical, 128^3 primitive supercell x 64 replicas (8 param_chem_pot x 8 T), "
+                    "sampled every 10 passes, statistics all-reduced")
+        extra = {"heat_capacity_first_last": [res[0]["heat_capacity"], res[-1]["heat_capacity"]],
+                 "accept_rate_local_min_max": [min(c.n_accept / c.n_attempt for c in cnt),
+                                               max(c.n_accept / c.n_attempt for c in cnt)],
+                 "samples_per_replica": res[0]["n_samples"]}
+        unit, alg_bytes_per_unit, kernel = UNIT, 2.0, "k_sweep_pass16"
+        launches = K_ * 3
+        run.close()
+    else:
+        names = ["fcc_default"] + [f"fcc_{ev}_{k}" for ev in ("A_Va_1NN", "B_Va_1NN") for k in range(6)]
+        tbs = {n: tb(n) for n in names}
+        types = [dict(et, kra=(et["kra"]["index"], et["kra"]["value"]), freq=(et["freq"]["index"], et["freq"]["value"]))
+                 for et in sysd["kmc"]["event_types"]]
+        prim = K.make_prim_event_list(types)
+        R_, N = 4096, (16, 16, 16)
+        n = int(np.prod(N))
+        base = np.random.default_rng(5).choice(3, size=(64, n), p=[0.899, 0.1, 0.001]).astype(np.int32)
+
+        def factory(st):
+            dev_types = [dict(local_tables=[tbs[x] for x in et["local_tables"]], kra=et["kra"], freq=et["freq"])
+                         for et in types]
+            return _capi.Kmc(st, dev_types, prim)
+
+        run = KmcEnsembleRunner(tbs["fcc_default"], N, sysd["eci_dense"], factory, 1200.0, R_, rank, world, seed0=1,
+                                occ_of=lambda i: base[i % 64])
+        S = 20
+        run.run(W_ * S)
+        barrier()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        time.sleep(0.3)
+        stream = torch.cuda.ExternalStream(run.state.stream())
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        ev0.record(stream)
+        out = run.run(K_ * S)
+        table = run.reduce(out, dist, device)                               # ONE all-reduce of (steps, time, rate)
+        ev1.record(stream)
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        clk = clocks.stop(t0, t1)
+        hops = float(table[:, 0].sum()) - W_ * S * R_
+        value = hops / (ms * 1e-3)
+        metric = "KMC events/sec (FCC A-B-Va, 4096 trajectories x 4096 cells)"
+        workload = ("FCC A-B-Va rejection-free KMC, 16^3 primitive cells per trajectory, x=(0.899, 0.1, 0.001), "
+                    "T=1200 K, 4096 trajectories dealt over the GPUs, (steps, time) all-reduced")
+        extra = {"mean_time_per_trajectory": float(table[:, 1].mean()), "trajectories": R_}
+        unit, alg_bytes_per_unit, kernel = "events/s", 708 * 90.0, "k_kmc_run"
+        launches = 1
+        info = {"evaluator": "kmc"}
+        run.close()
+    if rank != 0:
+        return
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
+    achieved = alg_bytes_per_unit * value / world / 1e9
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K_, "warmup": W_,
+            "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "parallelism": f"replicas over {world} rank(s), round robin",
+                       "collective": "one NCCL all-reduce of statistics (inside the timed region)"},
+            "clocks": clk, "e2e": None, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": kernel,
+                         "note": ("per GPU; the KMC step is latency bound (one block per trajectory, a serial event "
+                                  "chain): the HBM figure is the contract's, not the binding resource")
+                         if args.workload == "c5" else "per GPU, 2 B per attempted step"},
+            "evaluator": info["evaluator"]}
+    line.update(extra)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"],
+                    help="c3 (default, the headline): 512^3 box, slabs over the GPUs; c2: 64-replica (mu, T) grid of "
+                         "128^3 boxes dealt over the GPUs; c5: 4096 KMC trajectories dealt over the GPUs")
     ap.add_argument("--box", type=int, default=N_BOX)
     ap.add_argument("--layers", type=int, default=0, help="tuning runs: N2 of a (box, box, layers) supercell on one GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -276,6 +413,8 @@ def main():
     if not torch.cuda.is_available() or _capi.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    if args.workload != "c3":
+        return bench_replicas(args, torch, _capi, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -27,7 +27,7 @@ CMX_STATE_LINEAR_ROWS = 1
 # every symbol include/cmx_b200.h declares
 EXPORTED_SYMBOLS = [
     "cmx_last_error", "cmx_version", "cmx_device_count",
-    "cmx_tables_create", "cmx_tables_destroy",
+    "cmx_tables_create", "cmx_tables_create_from_file", "cmx_tables_destroy",
     "cmx_state_create", "cmx_state_create_opts", "cmx_state_destroy",
     "cmx_state_upload_occ", "cmx_state_download_occ",
     "cmx_state_upload_occ_i8", "cmx_state_download_occ_i8",
@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
     "cmx_kmc_set_impact_table", "cmx_kmc_run_begin", "cmx_kmc_run", "cmx_kmc_current_rates",
     "cmx_sampler_create", "cmx_sampler_destroy", "cmx_sampler_set_param_chem_pot", "cmx_sampler_info",
-    "cmx_sampler_reset", "cmx_sampler_sample", "cmx_sampler_read", "cmx_sweep_run",
+    "cmx_sampler_reset", "cmx_sampler_sample", "cmx_sampler_read", "cmx_sweep_run", "cmx_sampler_moments",
 ]
 
 
@@ -185,6 +185,7 @@ def lib():
     L.cmx_sampler_sample.argtypes = [vp]
     L.cmx_sampler_read.argtypes = [vp, i32, i32, i32, vp]
     L.cmx_sweep_run.argtypes = [vp, vp, i32, i64, i64, u64, i64, vp]
+    L.cmx_sampler_moments.argtypes = [vp, i32, vp, i32]
     _lib = L
     return L
 
@@ -562,6 +563,22 @@ class Sampler:
         check(lib().cmx_sweep_run(self.state._h, self._h, ens, int(n_samples), int(sweeps_per_sample),
                                   int(seed), int(first_sweep), cnt))
         return list(cnt)
+
+    @property
+    def n_scalar_quantities(self) -> int:
+        return 2 + self.n_species + self.n_param
+
+    def moments(self, first: int = 0, device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        """{n, sum q, sum q q^T} of every replica over the samples [first, n_samples)
+        (cmx_sampler_moments).  device_ptr: write to that device address instead (asynchronous
+        on the state's stream; the caller hands the buffer to NCCL)."""
+        Q = self.n_scalar_quantities
+        if device_ptr is not None:
+            check(lib().cmx_sampler_moments(self._h, int(first), C.c_void_p(int(device_ptr)), 1))
+            return None
+        out = np.zeros((self.state.n_replicas, 1 + Q + Q * Q))
+        check(lib().cmx_sampler_moments(self._h, int(first), _p(out), 0))
+        return out
 
     def series(self, replica: int = 0, first: int = 0, n: Optional[int] = None) -> dict:
         """Sampled series by the reference's sampler names."""

@@ -360,6 +360,29 @@ class ClexulatorTables:
                "delta_gbeg orbit_nbhd_beg orbit_nbhd corr_orbit corr_func").split()
     _SCALARS = "name nlist_size corr_size n_point_corr n_sublat max_occ n_func is_local".split()
 
+    def save_flat(self, path) -> None:
+        """The tables as one flat little-endian file, the form `cmx_tables_create_from_file`
+        reads (a C++ plugin has no numpy): magic "CMXT1\0\0\0", the eleven int32 sizes of
+        `cmx_table_desc` (n_sublat, max_occ, n_func, corr_size, n_point_corr, nlist_len,
+        n_nlist_sublat, n_factors, n_terms, n_elems, n_groups), then its sixteen arrays in
+        declaration order, each 8-byte aligned."""
+        import struct
+        sizes = [self.n_sublat, self.max_occ, self.n_func, self.corr_size, self.n_point_corr, self.nlist_len,
+                 self.n_nlist_sublat, len(self.factor_f), len(self.term_coef), len(self.elem_tbeg) - 1,
+                 len(self.group_div)]
+        order = [("nlist_sublat", np.int32), ("n_occ", np.int32), ("phi", np.float64), ("nbr", np.int32),
+                 ("factor_f", np.int32), ("factor_n", np.int32), ("term_coef", np.float64), ("term_fbeg", np.int32),
+                 ("elem_tbeg", np.int32), ("group_ebeg", np.int32), ("group_dphi", np.int32),
+                 ("group_has_sum", np.int32), ("group_div", np.float64), ("global_gbeg", np.int32),
+                 ("point_gbeg", np.int32), ("delta_gbeg", np.int32)]
+        with open(path, "wb") as f:
+            f.write(b"CMXT1\0\0\0")
+            f.write(struct.pack("<11i", *[int(x) for x in sizes]))
+            f.write(b"\0" * 4)
+            for name, dt in order:
+                b = np.ascontiguousarray(getattr(self, name), dtype=dt).tobytes()
+                f.write(b + b"\0" * (-len(b) % 8))
+
     def save(self, path) -> None:
         d = {k: getattr(self, k) for k in self._ARRAYS}
         for k in self._SCALARS:
@@ -696,18 +719,22 @@ def read_eci(data, corr_size: Optional[int] = None) -> Tuple[np.ndarray, np.ndar
 
 
 def _main(argv=None) -> int:
-    """python -m casmcode_clexmonte_b200.clexulator_tables <Clexulator.cc> <out.npz> [eci.json]
+    """python -m casmcode_clexmonte_b200.clexulator_tables <Clexulator.cc> <out.npz> [eci.json] [--flat out.cmxt]
 
     Export the flat tables of one CASM-generated Clexulator source (and print
-    the work per single-site delta for the given coefficients)."""
+    the work per single-site delta for the given coefficients).  --flat: also the
+    single-file form cmx_tables_create_from_file reads (what a C++ plugin loads)."""
     import argparse
     ap = argparse.ArgumentParser(description=_main.__doc__)
     ap.add_argument("source")
     ap.add_argument("out")
     ap.add_argument("eci", nargs="?")
+    ap.add_argument("--flat")
     a = ap.parse_args(argv)
     t = parse_clexulator_source(a.source)
     t.save(a.out)
+    if a.flat:
+        t.save_flat(a.flat)
     print(f"{a.out}: nlist {t.nlist_len}, corr {t.corr_size}, point corr {t.n_point_corr}, "
           f"sublattices on the neighbor list {t.n_nlist_sublat}")
     if a.eci:

@@ -116,6 +116,71 @@ extern "C" int cmx_tables_create(const cmx_table_desc *d, int device,
   return CMX_OK;
 }
 
+// the flat file ClexulatorTables.save_flat writes (clexulator_tables.py): a plugin written in
+// C++ loads the export of a basis set without numpy
+extern "C" int cmx_tables_create_from_file(const char *path, int device, cmx_tables **out) {
+  if (!path || !out) return invalid("cmx_tables_create_from_file: null argument");
+  FILE *f = fopen(path, "rb");
+  if (!f) return invalid(std::string("cmx_tables_create_from_file: cannot open ") + path);
+  std::vector<unsigned char> buf;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  buf.resize(n > 0 ? (size_t)n : 0);
+  const size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+  fclose(f);
+  if (got != buf.size() || buf.size() < 8 + 48 || memcmp(buf.data(), "CMXT1\0\0\0", 8) != 0)
+    return invalid(std::string("cmx_tables_create_from_file: not a flat tables file: ") + path);
+  int32_t sz[11];
+  memcpy(sz, buf.data() + 8, sizeof(sz));
+  for (int q = 0; q < 11; ++q)
+    if (sz[q] < 0) return invalid("cmx_tables_create_from_file: negative size");
+  cmx_table_desc d;
+  memset(&d, 0, sizeof(d));
+  d.n_sublat = sz[0];
+  d.max_occ = sz[1];
+  d.n_func = sz[2];
+  d.corr_size = sz[3];
+  d.n_point_corr = sz[4];
+  d.nlist_len = sz[5];
+  d.n_nlist_sublat = sz[6];
+  d.n_factors = sz[7];
+  d.n_terms = sz[8];
+  d.n_elems = sz[9];
+  d.n_groups = sz[10];
+  size_t off = 8 + 48;
+  bool ok = true;
+  auto take = [&](size_t count, size_t elem) -> const void * {
+    const size_t bytes = count * elem;
+    if (off + bytes > buf.size()) {
+      ok = false;
+      return nullptr;
+    }
+    const void *p = buf.data() + off;
+    off += bytes + ((8 - bytes % 8) % 8);
+    return p;
+  };
+  const size_t pc = (size_t)d.n_point_corr * d.corr_size + 1;
+  d.nlist_sublat = (const int32_t *)take(d.n_nlist_sublat, 4);
+  d.n_occ = (const int32_t *)take(d.n_sublat, 4);
+  d.phi = (const double *)take((size_t)d.n_sublat * d.n_func * d.max_occ, 8);
+  d.nbr = (const int32_t *)take((size_t)d.nlist_len * 4, 4);
+  d.factor_f = (const int32_t *)take(d.n_factors, 4);
+  d.factor_n = (const int32_t *)take(d.n_factors, 4);
+  d.term_coef = (const double *)take(d.n_terms, 8);
+  d.term_fbeg = (const int32_t *)take((size_t)d.n_terms + 1, 4);
+  d.elem_tbeg = (const int32_t *)take((size_t)d.n_elems + 1, 4);
+  d.group_ebeg = (const int32_t *)take((size_t)d.n_groups + 1, 4);
+  d.group_dphi = (const int32_t *)take(d.n_groups, 4);
+  d.group_has_sum = (const int32_t *)take(d.n_groups, 4);
+  d.group_div = (const double *)take(d.n_groups, 8);
+  d.global_gbeg = (const int32_t *)take((size_t)d.corr_size + 1, 4);
+  d.point_gbeg = (const int32_t *)take(pc, 4);
+  d.delta_gbeg = (const int32_t *)take(pc, 4);
+  if (!ok) return invalid(std::string("cmx_tables_create_from_file: truncated file: ") + path);
+  return cmx_tables_create(&d, device, out);
+}
+
 extern "C" void cmx_tables_destroy(cmx_tables *t) {
   if (!t) return;
   for (void *p : t->allocs) cudaFree(p);

@@ -351,3 +351,51 @@ extern "C" int cmx_sweep_run(cmx_state *s, cmx_sampler *m, int32_t ensemble, int
   }
   return cmx_canonical_counters(s, counters);
 }
+
+// ---- moments of the sampled series (replica grids: statistics are reduced, not series) ----
+// Per replica, over the samples [first, n_samples) and the Q = 2 + n_species + n_param scalar
+// quantities q = (clex.formation_energy, potential_energy, mol_composition, param_composition):
+//   out[replica] = { n, sum_a q_a (Q), sum q_a q_b (Q x Q) }          M = 1 + Q + Q^2 doubles
+// -- everything heat_capacity, mol_susc, param_susc and the thermochemical susceptibilities
+// (analysis_functions.cc:43-173, covariances per run/io/convariance_functions.cc:29-143) need,
+// and ADDITIVE over disjoint sets of samples, so that ranks holding different replicas (or
+// different sample ranges of one replica) combine them with one all-reduce.  One thread per
+// entry sums its samples in ascending order: deterministic.
+__global__ void k_sampler_moments(const double *__restrict__ series, int capacity, int nq, int Q, int first, int n_samples,
+                                  double *__restrict__ out) {
+  const int r = blockIdx.x, M = 1 + Q + Q * Q;
+  const double *ser = series + (size_t)r * capacity * nq;
+  for (int e = threadIdx.x; e < M; e += blockDim.x) {
+    double acc = 0.0;
+    if (e == 0) {
+      acc = (double)(n_samples - first);
+    } else if (e <= Q) {
+      for (int t = first; t < n_samples; ++t) acc += ser[(size_t)t * nq + (e - 1)];
+    } else {
+      const int a = (e - 1 - Q) / Q, b = (e - 1 - Q) % Q;
+      for (int t = first; t < n_samples; ++t) acc += ser[(size_t)t * nq + a] * ser[(size_t)t * nq + b];
+    }
+    out[(size_t)r * M + e] = acc;
+  }
+}
+
+extern "C" int cmx_sampler_moments(cmx_sampler *m, int32_t first, double *out, int32_t out_on_device) {
+  if (!m || !out) return invalid("cmx_sampler_moments: null argument");
+  if (first < 0 || first > m->n_samples) return invalid("cmx_sampler_moments: first sample out of range");
+  cmx_state *s = m->s;
+  CMX_CUDA(cudaSetDevice(s->t->device));
+  const int Q = 2 + m->n_species + m->n_param, M = 1 + Q + Q * Q, R = s->n_replicas;
+  double *d_out = out;
+  if (!out_on_device) {
+    int rc = cmx_scratch(s, sizeof(double) * (size_t)R * M);
+    if (rc) return rc;
+    d_out = (double *)s->d_scratch;
+  }
+  k_sampler_moments<<<R, 128, 0, s->stream>>>(m->d_series, m->capacity, m->nq, Q, first, m->n_samples, d_out);
+  CMX_CUDA(cudaGetLastError());
+  if (!out_on_device) {
+    CMX_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)R * M, cudaMemcpyDeviceToHost, s->stream));
+    CMX_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  return CMX_OK;  // out_on_device: asynchronous on the state's stream
+}

@@ -82,6 +82,10 @@ typedef struct cmx_table_desc {
 } cmx_table_desc;
 
 int cmx_tables_create(const cmx_table_desc *desc, int device, cmx_tables **out);
+/* The same from the flat file `ClexulatorTables.save_flat(path)` writes
+ * (casmcode_clexmonte_b200/clexulator_tables.py: the export of one generated Clexulator
+ * source): what a C++ plugin loads in its _reset(). */
+int cmx_tables_create_from_file(const char *path, int device, cmx_tables **out);
 void cmx_tables_destroy(cmx_tables *t);
 
 /* -------------------------------------------------------------------------
@@ -407,6 +411,15 @@ int cmx_sampler_read(cmx_sampler *m, int32_t replica, int32_t first, int32_t n, 
 int cmx_sweep_run(cmx_state *s, cmx_sampler *m, int32_t ensemble, int64_t n_samples,
                   int64_t sweeps_per_sample, uint64_t seed, int64_t first_sweep,
                   cmx_counters *counters);
+/* Moments of the sampled series of every replica over the samples [first, n_samples):
+ * out[replica][M], M = 1 + Q + Q*Q, Q = 2 + n_species + n_param scalar quantities
+ * q = (clex.formation_energy, potential_energy, mol_composition..., param_composition...):
+ * { n, sum q_a, sum q_a q_b }.  Additive over disjoint samples / replicas: ranks that hold
+ * different replicas of a (mu, T) grid combine them with ONE all-reduce, and the analysis
+ * functions (heat_capacity, *_susc: analysis_functions.cc:43-173) follow from the sums.
+ * out_on_device != 0: `out` is a device pointer (e.g. a torch tensor handed to NCCL) and the
+ * call is asynchronous on the state's stream. */
+int cmx_sampler_moments(cmx_sampler *m, int32_t first, double *out, int32_t out_on_device);
 
 /* -------------------------------------------------------------------------
  * Kinetic Monte Carlo: event-state / event-rate evaluation (reference rows

@@ -344,3 +344,33 @@ def test_run_series_batches_the_conditions_path(dev_tables, systems):
                      dependent_runs=True, **kw)
     assert (dep[0]["final_occupation"] == res[0]["final_occupation"]).all()
     assert dep[1]["conditions"]["temperature"] == 900.0 and dep[1]["potential_energy"]["n_samples"] == 6
+
+
+def test_device_moments_equal_the_series_moments(dev_tables, systems):
+    """cmx_sampler_moments ({n, sum q, sum q q^T} per replica, accumulated on the device: what
+    ranks all-reduce for a replica grid) against the same sums of the downloaded series, and
+    the analysis functions computed from them against Sampler.analysis."""
+    from casmcode_clexmonte_b200 import replicas as R
+    sysd = systems["fcc"]
+    st = _capi.State(dev_tables(sysd["tables"]), (16, 16, 16), 3)
+    st.set_eci(sysd["eci_sparse"]["index"], sysd["eci_sparse"]["value"])
+    o2s = np.array(sysd["occ_to_species"], dtype=np.int32)
+    st.set_occupants(sysd["sublat_to_asym"], o2s, sysd["n_species"])
+    sm = _capi.Sampler(st, 40, sysd["axes"]["origin"], sysd["axes"]["Rt"])
+    for r, (T, mu) in enumerate(((700.0, [0.1, 0.0]), (1000.0, [-0.2, 0.1]), (1500.0, [0.0, 0.3]))):
+        st.set_conditions(T, semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], mu, 3), r)
+        sm.set_param_chem_pot(mu, r)
+    st.randomize(3)
+    sm.run(40, 2, seed=5)
+    got = sm.moments(first=4)
+    for r in range(3):
+        ser = sm.series(r, first=4)
+        q = np.column_stack([ser["clex.formation_energy"], ser["potential_energy"], ser["mol_composition"],
+                             ser["param_composition"]])
+        np.testing.assert_allclose(got[r], R.moments_from_series(q), rtol=1e-12, atol=1e-12)
+        a = R.analysis_from_moments(got[r], st.temperature(r), st.n_cells, sm.n_species, sm.n_param)
+        b = sm.analysis(r, first=4)
+        assert a["heat_capacity"] == pytest.approx(b["heat_capacity"], rel=1e-6, abs=1e-9)
+        np.testing.assert_allclose(a["param_susc"], b["param_susc"], rtol=1e-6, atol=1e-8)
+    sm.close()
+    st.close()

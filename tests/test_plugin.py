@@ -1,0 +1,57 @@
+"""The reference-side plugin (plugin/B200SemiGrandCanonicalCalculator.cc): C++ host code against
+the reference's plugin interface, calling the CUDA library through the C ABI only.  It is
+compiled with g++ against the stand-in headers of plugin/shim (libcasm is not in this image)
+and driven by plugin/test_plugin.cc the way MonteCalculator drives a plugin: dlopen,
+make_B200SemiGrandCanonicalCalculator(), reset(params, system), run(state, occ_location,
+run_manager)."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from conftest import GOLDEN
+
+ROOT = Path(__file__).resolve().parents[1]
+PLUGIN = ROOT / "plugin"
+
+
+@pytest.fixture(scope="module")
+def built(tmp_path_factory):
+    from casmcode_clexmonte_b200 import build
+    from casmcode_clexmonte_b200.clexulator_tables import ClexulatorTables
+    build.build()
+    r = subprocess.run(["make", "-C", str(PLUGIN)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    flat = tmp_path_factory.mktemp("plugin") / "fcc_default.cmxt"
+    ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz").save_flat(flat)
+    return flat
+
+
+def test_plugin_builds_and_exports_the_factory(built):
+    """CPU: the plugin source compiles, exports the C-linkage factory the reference looks up
+    ("make_" + name, MonteCalculator.cc:163-166), and the calculator it returns declares its
+    requirements and rejects params without the tables (no GPU needed)."""
+    so = PLUGIN / "_build" / "libB200SemiGrandCanonicalCalculator.so"
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True).stdout
+    assert " T make_B200SemiGrandCanonicalCalculator" in nm
+    # the only undefined symbols that are not libc / libstdc++ are the C ABI's
+    und = subprocess.run(["nm", "-D", "--undefined-only", str(so)], capture_output=True, text=True).stdout
+    cmx = sorted({line.split()[-1] for line in und.splitlines() if " cmx_" in line})
+    assert "cmx_sgc_sweep" in cmx and "cmx_delta_e" in cmx and "cmx_tables_create_from_file" in cmx
+    r = subprocess.run([str(PLUGIN / "_build" / "test_plugin"), str(so), str(built), "--no-gpu"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "plugin ok" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["", "_bulk"])
+def test_plugin_run_equals_the_c_abi(built, variant):
+    """GPU: one run() through the plugin (sampling fixture every 2 passes, counters through the
+    RunManager calls of occupation_metropolis.hh:109-116 -- one by one, or with the proposed
+    bulk call) leaves the occupation, the acceptance count and the potential the C ABI gives
+    for the same seed; the potential's occ_delta / per_supercell are served by the device."""
+    so = PLUGIN / "_build" / f"libB200SemiGrandCanonicalCalculator{variant}.so"
+    r = subprocess.run([str(PLUGIN / "_build" / "test_plugin"), str(so), str(built)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "plugin ok: 10 passes" in r.stdout
