@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
     "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sgc_sweep_slab", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_stream_info", "cmx_sweep_debug_delta_e",
-    "cmx_metropolis_sequential", "cmx_rng_stream_test",
+    "cmx_metropolis_sequential", "cmx_metropolis_sequential_ties", "cmx_rng_stream_test",
     "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
     "cmx_kmc_set_impact_table", "cmx_kmc_run_begin", "cmx_kmc_run", "cmx_kmc_current_rates",
@@ -164,6 +164,7 @@ def lib():
     L.cmx_state_create_opts.argtypes = [vp, i32, i32, i32, i32, i32, C.c_uint32, C.POINTER(vp)]
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
+    L.cmx_metropolis_sequential_ties.argtypes = [vp, C.POINTER(i64), vp, i32]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
     L.cmx_canonical_set_swaps.argtypes = [vp, i32, vp]
     L.cmx_canonical_sweep.argtypes = [vp, i64, u64, i64, vp]
@@ -500,7 +501,11 @@ class State:
                                               C.byref(log), int(log_cap), C.byref(n_acc), C.byref(h)))
         steps = [dict(l0=s.l0, l1=s.l1, new0=s.new0, new1=s.new1, accepted=s.accepted, dE=s.dE)
                  for s in log[:min(log_cap, n_steps)]]
-        return dict(n_accept=n_acc.value, hash=h.value, log=steps)
+        nt = C.c_int64()
+        ts = (C.c_int64 * 16)()
+        check(lib().cmx_metropolis_sequential_ties(self._h, C.byref(nt), ts, 16))
+        return dict(n_accept=n_acc.value, hash=h.value, log=steps, n_near_ties=nt.value,
+                    tie_steps=[int(x) for x in ts if x >= 0])
 
 
 KB = 8.6173303e-05  # eV/K, CASM::KB [EXT libcasm-global], pinned by _MonteCalculator.py:186-210

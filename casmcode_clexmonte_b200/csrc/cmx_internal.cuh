@@ -224,6 +224,7 @@ struct cmx_state {
   // thin slabs (k_sweep_pass16): k-colour groups completed by this rank; d_sig[0] / [1]: the
   // epoch my lower / upper ring neighbour reached (written by them)
   unsigned long long epoch = 0;
+  long long seq_ties[17] = {0};  // tie report of the last cmx_metropolis_sequential call
   // scratch
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;

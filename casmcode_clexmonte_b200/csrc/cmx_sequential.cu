@@ -98,7 +98,10 @@ struct SeqArgs {
   long long *n_accept;
   unsigned long long *hash;
   int *status;
+  // tie report: [0] = number of near ties, [1 + q] = step of the q-th (q < CMX_TIE_CAP)
+  long long *ties;
 };
+#define CMX_TIE_CAP 16
 
 __device__ __forceinline__ unsigned long long fnv_step(unsigned long long h, unsigned long long x) {
 #pragma unroll
@@ -224,7 +227,15 @@ __global__ void __launch_bounds__(32) k_metropolis_sequential(SeqArgs a) {
         accept = 1;
       } else {
         double u = mt_real(rng, 1.0);
-        accept = u < exp(__dmul_rn(-dE, a.beta));
+        const double p = exp(__dmul_rn(-dE, a.beta));
+        accept = u < p;
+        // near tie: the decision would flip if exp() were one ulp off (CUDA's and glibc's
+        // exp may differ in the last place) -- the only way this mode can leave the
+        // reference's trajectory; counted and reported, never hidden
+        if (u == p || u == nextafter(p, 0.0) || u == nextafter(p, 2.0)) {
+          const long long q = a.ties[0]++;
+          if (q < CMX_TIE_CAP) a.ties[1 + q] = step;
+        }
       }
       if (step < a.log_cap) {
         cmx_step_record &rec = a.log[step];
@@ -419,6 +430,9 @@ extern "C" int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t 
   DC(z1, d_nacc);
   std::vector<unsigned long long> z2(1, 0);
   DC(z2, d_hash);
+  std::vector<long long> z3(1 + CMX_TIE_CAP, 0);
+  long long *d_ties;
+  DC(z3, d_ties);
 #undef DC
   if (a.log_cap > 0) {
     cudaError_t e = cudaMalloc((void **)&d_log, sizeof(cmx_step_record) * a.log_cap);
@@ -443,6 +457,7 @@ extern "C" int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t 
   a.n_accept = d_nacc;
   a.hash = d_hash;
   a.status = d_status;
+  a.ties = d_ties;
   k_metropolis_sequential<<<1, 32, 0, s->stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
@@ -453,6 +468,7 @@ extern "C" int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t 
     cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost);
     cudaMemcpy(&nacc, d_nacc, sizeof(long long), cudaMemcpyDeviceToHost);
     cudaMemcpy(&hh, d_hash, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(s->seq_ties, d_ties, sizeof(long long) * (1 + CMX_TIE_CAP), cudaMemcpyDeviceToHost);
     if (a.log_cap > 0 && log)
       cudaMemcpy(log, d_log, sizeof(cmx_step_record) * a.log_cap, cudaMemcpyDeviceToHost);
   }
@@ -464,5 +480,16 @@ extern "C" int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t 
   }
   if (n_accept) *n_accept = nacc;
   if (hash) *hash = hh;
+  return CMX_OK;
+}
+
+// Tie report of the last cmx_metropolis_sequential call on this state: the number of steps
+// whose uniform draw was within one ulp of exp(-beta dE) -- the only steps at which the
+// device (CUDA exp) and the reference (glibc exp) could decide differently -- and the first
+// `cap` (<= 16) of their step indices.
+extern "C" int cmx_metropolis_sequential_ties(const cmx_state *s, int64_t *n_near_ties, int64_t *steps, int32_t cap) {
+  if (!s || !n_near_ties) return invalid("cmx_metropolis_sequential_ties: null argument");
+  *n_near_ties = s->seq_ties[0];
+  for (int q = 0; q < cap && q < CMX_TIE_CAP && steps; ++q) steps[q] = (q < s->seq_ties[0]) ? s->seq_ties[1 + q] : -1;
   return CMX_OK;
 }

@@ -367,6 +367,13 @@ int cmx_metropolis_sequential(cmx_state *s, int32_t replica, int32_t mode,
                               int64_t n_steps, uint64_t seed,
                               cmx_step_record *log, int64_t log_cap,
                               int64_t *n_accept, uint64_t *hash);
+/* Tie report of the last cmx_metropolis_sequential call on this state.  The one operation of
+ * that mode not under our control is exp(): CUDA's and glibc's results may differ in the last
+ * place, which flips an accept/reject decision only if the uniform draw lies within one ulp of
+ * exp(-beta dE).  Such steps are counted (*n_near_ties) and the first `cap` (<= 16) step
+ * indices returned (steps[cap], -1 padded): a trajectory that leaves the reference's can be
+ * traced to them, and a report of 0 near ties means none could have. */
+int cmx_metropolis_sequential_ties(const cmx_state *s, int64_t *n_near_ties, int64_t *steps, int32_t cap);
 
 /* -------------------------------------------------------------------------
  * Device-side samplers.  Replaces, for every replica

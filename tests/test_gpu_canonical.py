@@ -158,6 +158,71 @@ def test_canonical_matches_sequential_thermodynamics(dev_tables, systems, oracle
     st.close()
 
 
+def test_zro_canonical_matches_sequential_thermodynamics(dev_tables, systems, oracle):
+    """BASELINE configs[3] (HCP Zr-O, O/Va on two interstitial sublattices, pairs + triplets +
+    quadruplets): the parallel pair exchanges -- swap types restricted to a set of
+    translations, coloured conflict-free -- sample the same canonical ensemble as the
+    reference's sequential any-two-sites swaps (oracle: propose_canonical_event restated
+    around the reference's compiled ZrO kernels): <formation energy> per cell and its
+    variance (the heat capacity) within 3 sigma over independent runs, 12^3 cells."""
+    if oracle is None:
+        pytest.skip("oracle/_ref not built")
+    sysd = systems["zro"]
+    eci = sysd["eci"]
+    N = (12, 12, 12)
+    n_cells = int(np.prod(N))
+    n_sub = len(sysd["occ_to_species"])
+    T = 900.0
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=sysd["n_species"], Rt=np.array(sysd["axes"]["Rt"]), origin=np.array(sysd["axes"]["origin"]))
+    sc = oracle.RefClexulator(sysd["tables"]).supercell(N)
+    n_runs, n_eq, n_smp, period = 4, 30, 40, 2
+    n_mut = n_cells * len(sysd["mutable_sublats"])
+    inits = []
+    for run in range(n_runs):
+        rng = np.random.default_rng(300 + run)
+        occ = np.zeros(n_cells * n_sub, dtype=np.int32)
+        flat = np.zeros(n_mut, dtype=np.int32)
+        flat[rng.permutation(n_mut)[:n_mut // 4]] = 1          # x_O = 0.25 over the interstitial sites
+        for q, b in enumerate(sysd["mutable_sublats"]):
+            occ[b * n_cells:(b + 1) * n_cells] = flat[q * n_cells:(q + 1) * n_cells]
+        inits.append(occ)
+    ref = []
+    for run in range(n_runs):
+        occ = sc.metropolis_run(1, inits[run], prim, eci["index"], eci["value"], T, seed=1000 + run,
+                                n_steps=n_eq * n_mut)["occ"]
+        es = []
+        for k in range(n_smp):
+            occ = sc.metropolis_run(1, occ, prim, eci["index"], eci["value"], T, seed=5000 + 97 * run + k,
+                                    n_steps=period * n_mut)["occ"]
+            g = sc.global_corr(occ)
+            es.append(float(np.dot(eci["value"], g[eci["index"]])) / n_cells)
+        ref.append([np.mean(es), np.var(es)])
+    st, _, swaps = _state(dev_tables, systems, "zro", "eci", N, T, inits[0], n_replicas=n_runs)
+    for r in range(n_runs):
+        st.upload_occ(inits[r], r)
+    st.canonical_set_swaps(swaps)
+    # one device sweep visits n_swap_types * n_cells pairs: match the reference's attempts per pass
+    per_sweep = len(swaps) * n_cells
+    eq = max(1, round(n_eq * n_mut / per_sweep))
+    per = max(1, round(period * n_mut / per_sweep))
+    st.canonical_sweep(eq, seed=21)
+    ge = np.zeros((n_runs, n_smp))
+    for k in range(n_smp):
+        st.canonical_sweep(per, seed=21, first_sweep=eq + per * k)
+        for r in range(n_runs):
+            ge[r, k] = st.energy(r) / n_cells
+    for r in range(n_runs):
+        assert np.bincount(st.download_occ(r)).tolist() == np.bincount(inits[r]).tolist()
+    st.close()
+    gpu = np.array([[ge[r].mean(), ge[r].var()] for r in range(n_runs)])
+    ref = np.array(ref)
+    for q, (name, floor) in enumerate((("formation energy per cell", 2e-4), ("variance of the energy", 0.0))):
+        se = np.hypot(ref[:, q].std(ddof=1), gpu[:, q].std(ddof=1)) / np.sqrt(n_runs)
+        d = abs(ref[:, q].mean() - gpu[:, q].mean())
+        assert d <= 3 * se + floor, f"{name}: reference {ref[:, q].mean():.6g} gpu {gpu[:, q].mean():.6g} (3 sigma {3 * se:.3g})"
+
+
 @pytest.mark.parametrize("ensemble", ["semigrand", "canonical"])
 def test_warp_evaluator_equals_thread_evaluator(dev_tables, systems, ensemble):
     """Wide orbit sets (ZrO: ~700 merged terms per site) are evaluated one site per warp

@@ -270,7 +270,7 @@ def test_binary_canonical_temperature_path_matches_reference(dev_tables, systems
     N = (20, 20, 10)                      # 4 000 sites, as the 10^3 conventional FCC box
     n_cells = int(np.prod(N))
     temps = [2000.0, 1100.0, 600.0]
-    n_runs, n_samp = 4, 60
+    n_runs, n_samp = 8, 100
     prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
                 n_species=3, Rt=np.array(sysd["axes"]["Rt"]), origin=np.array(sysd["axes"]["origin"]))
     sc = oracle.RefClexulator("fcc_default").supercell(N)
@@ -313,8 +313,7 @@ def test_binary_canonical_temperature_path_matches_reference(dev_tables, systems
         se = np.hypot(ref[ti].std(axis=0, ddof=1), gpu.std(axis=0, ddof=1)) / np.sqrt(n_runs)
         diff = np.abs(ref[ti].mean(axis=0) - gpu.mean(axis=0))
         assert diff[0] < 3 * se[0] + 2e-4, ("energy", T, ref[ti].mean(axis=0), gpu.mean(axis=0), se)
-        assert diff[1] < 3 * se[1] + 0.05 * abs(ref[ti].mean(axis=0)[1]), ("heat capacity", T, ref[ti].mean(axis=0),
-                                                                        gpu.mean(axis=0), se)
+        assert diff[1] < 3 * se[1], ("heat capacity", T, ref[ti].mean(axis=0), gpu.mean(axis=0), se)
     sm.close()
     st.close()
 
