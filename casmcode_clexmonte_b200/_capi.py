@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 from pathlib import Path
-from typing import Optional, Sequence
+from typing import Tuple, Optional, Sequence
 
 import numpy as np
 
@@ -28,7 +28,8 @@ CMX_STATE_LINEAR_ROWS = 1
 EXPORTED_SYMBOLS = [
     "cmx_last_error", "cmx_version", "cmx_device_count",
     "cmx_tables_create", "cmx_tables_create_from_file", "cmx_tables_destroy",
-    "cmx_state_create", "cmx_state_create_opts", "cmx_state_destroy",
+    "cmx_state_create", "cmx_state_create_opts", "cmx_state_create_general", "cmx_state_box", "cmx_supercell_box",
+    "cmx_state_cell_index", "cmx_state_set_site_order", "cmx_state_destroy",
     "cmx_state_upload_occ", "cmx_state_download_occ",
     "cmx_state_upload_occ_i8", "cmx_state_download_occ_i8",
     "cmx_state_upload_occ_i8_async", "cmx_state_download_occ_i8_async", "cmx_state_synchronize", "cmx_sgc_sweep_async", "cmx_sgc_sweep_continue",
@@ -162,6 +163,11 @@ def lib():
     L.cmx_sweep_stream_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cmx_sweep_debug_delta_e.argtypes = [vp, i32, i64, vp, vp, vp]
     L.cmx_state_create_opts.argtypes = [vp, i32, i32, i32, i32, i32, C.c_uint32, C.POINTER(vp)]
+    L.cmx_state_create_general.argtypes = [vp, vp, i32, C.c_uint32, C.POINTER(vp)]
+    L.cmx_state_box.argtypes = [vp, vp]
+    L.cmx_supercell_box.argtypes = [vp, vp]
+    L.cmx_state_cell_index.argtypes = [vp, i64, vp, vp]
+    L.cmx_state_set_site_order.argtypes = [vp, vp]
     L.cmx_metropolis_sequential.argtypes = [vp, i32, i32, i64, u64, vp, i64, C.POINTER(i64),
                                             C.POINTER(u64)]
     L.cmx_metropolis_sequential_ties.argtypes = [vp, C.POINTER(i64), vp, i32]
@@ -244,24 +250,67 @@ class Tables:
             pass
 
 
+def supercell_box(transformation_matrix) -> Tuple[int, ...]:
+    """(N0, N1, N2, s10, s20, s21): the Hermite-normal-form box of a transformation matrix
+    (host arithmetic only)."""
+    T = np.ascontiguousarray(np.asarray(transformation_matrix).reshape(3, 3), dtype=np.int32)
+    box = np.zeros(6, dtype=np.int32)
+    check(lib().cmx_supercell_box(_p(T), _p(box)))
+    return tuple(int(x) for x in box)
+
+
 class State:
     """Device-resident supercell(s) (``cmx_state``)."""
 
     def __init__(self, tables: Tables, N: Sequence[int], n_replicas: int = 1, halo: int = 0,
-                 linear_rows: bool = False):
-        if np.isscalar(N):
-            N = (N, N, N)
+                 linear_rows: bool = False, transformation_matrix=None):
+        """N: the diag(N0, N1, N2) supercell, or (``transformation_matrix`` 3x3 integers,
+        columns = supercell lattice vectors in prim coordinates, as the reference's
+        ``transformation_matrix_to_super``) a general supercell -- N is then ignored and
+        ``self.N`` / ``self.skew`` report the Hermite-normal-form box."""
         self.tables = tables
-        self.N = tuple(int(x) for x in N)
         self.n_replicas = int(n_replicas)
         self.halo = int(halo)
         t = tables.host
-        self.n_cells = self.N[0] * self.N[1] * self.N[2]
-        self.n_sites = self.n_cells * t.n_sublat
         self._temperature = {}
         self._h = C.c_void_p()
-        check(lib().cmx_state_create_opts(tables._h, *self.N, self.n_replicas, self.halo,
-                                          CMX_STATE_LINEAR_ROWS if linear_rows else 0, C.byref(self._h)))
+        opts = CMX_STATE_LINEAR_ROWS if linear_rows else 0
+        if transformation_matrix is not None:
+            T = np.ascontiguousarray(np.asarray(transformation_matrix).reshape(3, 3), dtype=np.int32)
+            if halo:
+                raise CmxError(CMX_ERR_INVALID, "slabs of a general supercell are not supported")
+            check(lib().cmx_state_create_general(tables._h, _p(T), self.n_replicas, opts, C.byref(self._h)))
+            box = np.zeros(6, dtype=np.int32)
+            check(lib().cmx_state_box(self._h, _p(box)))
+            self.N = tuple(int(x) for x in box[:3])
+            self.skew = tuple(int(x) for x in box[3:])
+        else:
+            if np.isscalar(N):
+                N = (N, N, N)
+            self.N = tuple(int(x) for x in N)
+            self.skew = (0, 0, 0)
+            check(lib().cmx_state_create_opts(tables._h, *self.N, self.n_replicas, self.halo, opts,
+                                              C.byref(self._h)))
+        self.n_cells = self.N[0] * self.N[1] * self.N[2]
+        self.n_sites = self.n_cells * t.n_sublat
+
+    def cell_index(self, ijk) -> np.ndarray:
+        """Unit cells by prim-lattice coordinates (any integers, [n][3]) -> cell index."""
+        ijk = np.ascontiguousarray(np.asarray(ijk).reshape(-1, 3), dtype=np.int32)
+        out = np.empty(ijk.shape[0], dtype=np.int64)
+        check(lib().cmx_state_cell_index(self._h, ijk.shape[0], _p(ijk), _p(out)))
+        return out
+
+    def set_site_order(self, order) -> None:
+        """order[l_caller] = l of this library (b * n_cells + cell); None: identity.  Applies
+        to the synchronous upload_occ / download_occ."""
+        if order is None:
+            check(lib().cmx_state_set_site_order(self._h, None))
+            return
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        if order.size != self.n_sites:
+            raise CmxError(CMX_ERR_INVALID, "site order must list every site")
+        check(lib().cmx_state_set_site_order(self._h, _p(order)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -194,15 +194,131 @@ extern "C" int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1,
   return cmx_state_create_opts(t, N0, N1, N2, n_replicas, halo, 0u, out);
 }
 
+// Hermite normal form of a transformation matrix T (columns = supercell lattice vectors in
+// prim coordinates): the same lattice with the basis (h00, h10, h20), (0, h11, h21),
+// (0, 0, h22), 0 <= h10 < h11, 0 <= h20, h21 < h22.  Integer column operations only.
+static bool hermite_normal_form(const int32_t *T9, long long (&H)[3][3]) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) H[r][c] = T9[3 * r + c];
+  for (int r = 0; r < 3; ++r) {
+    for (;;) {  // Euclid on row r over the columns r..2
+      int n_nz = 0, c0 = -1;
+      for (int c = r; c < 3; ++c)
+        if (H[r][c] != 0) {
+          ++n_nz;
+          if (c0 < 0 || std::llabs(H[r][c]) < std::llabs(H[r][c0])) c0 = c;
+        }
+      if (n_nz == 0) return false;  // singular
+      if (n_nz == 1) {
+        if (c0 != r)
+          for (int q = 0; q < 3; ++q) std::swap(H[q][r], H[q][c0]);
+        break;
+      }
+      for (int c = r; c < 3; ++c)
+        if (c != c0 && H[r][c] != 0) {
+          const long long f = H[r][c] / H[r][c0];
+          for (int q = 0; q < 3; ++q) H[q][c] -= f * H[q][c0];
+        }
+    }
+    if (H[r][r] < 0)
+      for (int q = 0; q < 3; ++q) H[q][r] = -H[q][r];
+    for (int c = 0; c < r; ++c) {  // reduce the entries left of the diagonal into [0, h_rr)
+      long long f = H[r][c] / H[r][r];
+      if (H[r][c] - f * H[r][r] < 0) --f;
+      for (int q = 0; q < 3; ++q) H[q][c] -= f * H[q][r];
+    }
+  }
+  return true;
+}
+
+// host only: the box a transformation matrix gets (no device needed)
+extern "C" int cmx_supercell_box(const int32_t *T9, int32_t *box6) {
+  if (!T9 || !box6) return invalid("cmx_supercell_box: null argument");
+  long long H[3][3];
+  if (!hermite_normal_form(T9, H)) return invalid("cmx_supercell_box: singular transformation matrix");
+  const long long v[6] = {H[0][0], H[1][1], H[2][2], H[1][0], H[2][0], H[2][1]};
+  for (int q = 0; q < 6; ++q) {
+    if (v[q] > 0x7fffffffll) return invalid("cmx_supercell_box: supercell too large");
+    box6[q] = (int32_t)v[q];
+  }
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_create_general(const cmx_tables *t, const int32_t *T9, int32_t n_replicas, uint32_t options,
+                                        cmx_state **out) {
+  if (!t || !T9 || !out) return invalid("cmx_state_create_general: null argument");
+  long long H[3][3];
+  if (!hermite_normal_form(T9, H)) return invalid("cmx_state_create_general: singular transformation matrix");
+  for (int a = 0; a < 3; ++a)
+    if (H[a][a] <= 0 || H[a][a] > 0x7fffffffll) return invalid("cmx_state_create_general: supercell too large");
+  const bool skew = H[1][0] != 0 || H[2][0] != 0 || H[2][1] != 0;
+  int rc = cmx_state_create_opts(t, (int32_t)H[0][0], (int32_t)H[1][1], (int32_t)H[2][2], n_replicas, 0,
+                                 options | (skew ? CMX_STATE_LINEAR_ROWS | 0x80000000u : 0u), out);
+  if (rc) return rc;
+  (*out)->g.s10 = (int32_t)H[1][0];
+  (*out)->g.s20 = (int32_t)H[2][0];
+  (*out)->g.s21 = (int32_t)H[2][1];
+  return CMX_OK;
+}
+
+// unit cells given by prim-lattice coordinates (any integers) -> cell index inside the box
+extern "C" int cmx_state_cell_index(const cmx_state *s, int64_t n, const int32_t *ijk, int64_t *cell) {
+  if (!s || n < 0 || (n && (!ijk || !cell))) return invalid("cmx_state_cell_index: bad argument");
+  Geom g = s->g;
+  g.halo = 0;
+  for (int64_t q = 0; q < n; ++q) {
+    int i = ijk[3 * q], j = ijk[3 * q + 1], k = ijk[3 * q + 2];
+    if (!(g.s10 | g.s20 | g.s21)) {  // (the diag shortcut of cmx_wrap_cell wraps once only)
+      i -= cmx_floor_div(i, g.N0) * g.N0;
+      j -= cmx_floor_div(j, g.N1) * g.N1;
+      k -= cmx_floor_div(k, g.N2) * g.N2;
+    } else {
+      cmx_wrap_cell(g, i, j, k);
+    }
+    cell[q] = (int64_t)i + (int64_t)g.N0 * ((int64_t)j + (int64_t)g.N1 * (int64_t)k);
+  }
+  return CMX_OK;
+}
+
+extern "C" int cmx_state_box(const cmx_state *s, int32_t *box6) {
+  if (!s || !box6) return invalid("cmx_state_box: null argument");
+  box6[0] = s->g.N0;
+  box6[1] = s->g.N1;
+  box6[2] = s->g.N2;
+  box6[3] = s->g.s10;
+  box6[4] = s->g.s20;
+  box6[5] = s->g.s21;
+  return CMX_OK;
+}
+
+// Site order of the caller (upload / download only): order[l_caller] = l of this library
+// (l = b * n_cells + cell).  NULL restores the identity.
+extern "C" int cmx_state_set_site_order(cmx_state *s, const int64_t *order) {
+  if (!s) return invalid("cmx_state_set_site_order: null state");
+  const int64_t n = s->g.n_cells * s->t->d.n_sublat;
+  s->site_order.clear();
+  if (!order) return CMX_OK;
+  std::vector<char> seen((size_t)n, 0);
+  for (int64_t l = 0; l < n; ++l) {
+    if (order[l] < 0 || order[l] >= n || seen[(size_t)order[l]])
+      return invalid("cmx_state_set_site_order: not a permutation of the sites");
+    seen[(size_t)order[l]] = 1;
+  }
+  s->site_order.assign(order, order + n);
+  return CMX_OK;
+}
+
 extern "C" int cmx_state_create_opts(const cmx_tables *t, int32_t N0, int32_t N1,
                                      int32_t N2, int32_t n_replicas, int32_t halo,
                                      uint32_t options, cmx_state **out) {
   if (!t || !out) return invalid("cmx_state_create: null argument");
+  const bool general = (options & 0x80000000u) != 0;  // internal: a skewed box follows (no range check)
+  options &= ~0x80000000u;
   if (options & ~(uint32_t)CMX_STATE_LINEAR_ROWS) return invalid("cmx_state_create_opts: unknown option");
   if (N0 <= 0 || N1 <= 0 || N2 <= 0 || n_replicas <= 0 || halo < 0)
     return invalid("cmx_state_create: non-positive dimension");
   // the neighbor arithmetic wraps once: every |offset| must be <= N
-  for (int n = 0; n < t->d.nlist_len; ++n) {
+  for (int n = 0; n < t->d.nlist_len && !general; ++n) {
     const int32_t *o = &t->nbr[4 * n];
     if (std::abs(o[0]) > N0 || std::abs(o[1]) > N1 ||
         (!halo && std::abs(o[2]) > N2))
@@ -223,6 +339,7 @@ extern "C" int cmx_state_create_opts(const cmx_tables *t, int32_t N0, int32_t N1
   g.rep_stride = g.sub_stride * t->d.n_sublat;
   g.coded = (t->d.n_sublat == 1 && t->n_occ[0] == 3) ? 1 : 0;
   // x4-interleaved rows (see Geom::xq_log) for the shapes the streaming pair-LUT sweep covers
+  g.s10 = g.s20 = g.s21 = 0;
   g.xq_log = 0;
   if (!(options & CMX_STATE_LINEAR_ROWS) && t->d.n_sublat == 1 && t->d.max_occ <= 3 && N0 >= 16 && N0 <= 512 &&
       (N0 & (N0 - 1)) == 0 && N1 % 2 == 0 && N2 % 2 == 0 && N2 <= 65534)
@@ -416,6 +533,12 @@ static int upload_occ(cmx_state *s, int32_t replica, const T *occ) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   int8_t *dst = s->d_occ + (size_t)replica * s->g.rep_stride;
+  std::vector<T> permuted;
+  if (!s->site_order.empty()) {  // the caller's site order -> ours
+    permuted.resize(n);
+    for (size_t l = 0; l < n; ++l) permuted[(size_t)s->site_order[l]] = occ[l];
+    occ = permuted.data();
+  }
   CMX_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
   if (sizeof(T) == 1 && s->g.xq_log) {
     // x4-interleaved rows: the image goes to scratch and is transposed into place
@@ -457,7 +580,7 @@ static int download_occ(const cmx_state *cs, int32_t replica, T *occ) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;
-  if (sizeof(T) == 1 && s->g.halo == 0 && !s->g.coded && !s->g.xq_log) {
+  if (sizeof(T) == 1 && s->g.halo == 0 && !s->g.coded && !s->g.xq_log && s->site_order.empty()) {
     CMX_CUDA(cudaMemcpyAsync(occ, src, n, cudaMemcpyDeviceToHost, s->stream));
     CMX_CUDA(cudaStreamSynchronize(s->stream));
     return CMX_OK;
@@ -475,6 +598,10 @@ static int download_occ(const cmx_state *cs, int32_t replica, T *occ) {
   CMX_CUDA(cudaMemcpyAsync(occ, s->d_scratch, n * sizeof(T),
                            cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
+  if (!s->site_order.empty()) {  // ours -> the caller's site order
+    std::vector<T> tmp(occ, occ + n);
+    for (size_t l = 0; l < n; ++l) occ[l] = tmp[(size_t)s->site_order[l]];
+  }
   return CMX_OK;
 }
 
@@ -485,6 +612,10 @@ extern "C" int cmx_state_upload_occ_i8_async(cmx_state *s, int32_t replica, cons
   int rc = check_replica(s, replica, "cmx_state_upload_occ_i8_async");
   if (rc) return rc;
   if (!occ) return invalid("cmx_state_upload_occ_i8_async: null occupation");
+  if (!s->site_order.empty()) {
+    cmx_set_error("cmx_state_upload_occ_i8_async: a caller site order is set (use the synchronous transfer)");
+    return CMX_ERR_UNSUPPORTED;
+  }
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   int8_t *dst = s->d_occ + (size_t)replica * s->g.rep_stride;
@@ -516,6 +647,10 @@ extern "C" int cmx_state_download_occ_i8_async(cmx_state *s, int32_t replica, in
   int rc = check_replica(s, replica, "cmx_state_download_occ_i8_async");
   if (rc) return rc;
   if (!occ) return invalid("cmx_state_download_occ_i8_async: null occupation");
+  if (!s->site_order.empty()) {
+    cmx_set_error("cmx_state_download_occ_i8_async: a caller site order is set (use the synchronous transfer)");
+    return CMX_ERR_UNSUPPORTED;
+  }
   CMX_CUDA(cudaSetDevice(s->t->device));
   size_t n = (size_t)s->g.n_cells * s->t->d.n_sublat;
   const int8_t *src = s->d_occ + (size_t)replica * s->g.rep_stride;

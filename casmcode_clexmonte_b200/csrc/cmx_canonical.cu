@@ -186,8 +186,8 @@ __device__ __forceinline__ double canon_lut_delta(const CanonArgs &a, const Cano
   int n1 = 0, n2 = 0;
 #pragma unroll 4
   for (int q = 0; q < L.z; ++q) {
-    const int ii = cmx_wrap(i + L.shell[3 * q], g.N0), jj = cmx_wrap(j + L.shell[3 * q + 1], g.N1),
-              kk = cmx_wrap(k + L.shell[3 * q + 2], g.N2);
+    int ii = i + L.shell[3 * q], jj = j + L.shell[3 * q + 1], kk = k + L.shell[3 * q + 2];
+    cmx_wrap_cell(g, ii, jj, kk);
     const int64_t no = cmx_site_offset(g, 0, ii, jj, kk);
     const int code = (no == ov_off) ? ov_code : (CG ? (int)__ldcg(occ + no) : (int)occ[no]);
     n1 += code & 1;   // storage codes 0 / 1 / 18
@@ -430,6 +430,11 @@ extern "C" int cmx_canonical_set_swaps(cmx_state *s, int32_t n, const cmx_swap_t
     return CMX_ERR_STATE;
   }
   if (s->g.halo) return invalid("cmx_canonical_set_swaps: slab states are not supported");
+  if (s->g.s10 | s->g.s20 | s->g.s21) {
+    cmx_set_error("cmx_canonical_set_swaps: pair-exchange colourings need a diag(N0, N1, N2) supercell "
+                  "(general supercells: semi-grand sweeps, the reference-order mode and KMC)");
+    return CMX_ERR_UNSUPPORTED;
+  }
   const cmx_tables *t = s->t;
   const DevTables &T = t->d;
   const int mo = T.max_occ;

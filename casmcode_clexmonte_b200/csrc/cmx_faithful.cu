@@ -301,6 +301,12 @@ __global__ void k_reduce_partials(const double *__restrict__ partial, int nb,
 
 int cmx_global_corr_device(cmx_state *s, int32_t replica, double **d_out) {
   const DevTables &T = s->t->d;
+  // point + pair bases on one sublattice: integer bond counts per forward-neighbor set
+  if (!(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC)) {
+    int rc = cmx_plan_corr_lin(s);
+    if (rc) return rc;
+    if (s->plan.corr_lin_state == 1) return cmx_global_corr_lin_device(s, replica, d_out);
+  }
   int nb = (int)((s->g.n_cells + 255) / 256);
   if (nb > 592) nb = 592;
   size_t b_part = sizeof(double) * (size_t)nb * T.corr_size;

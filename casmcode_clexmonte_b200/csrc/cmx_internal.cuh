@@ -63,6 +63,11 @@ struct Geom {
   // built on.  Chosen at creation for single-sublattice states whose N0 is a power of two
   // in [16, 512]; every kernel addresses sites through cmx_site_offset / cmx_xpos.
   int32_t xq_log;
+  // General supercells (cmx_state_create_general): the supercell lattice in Hermite normal
+  // form has the basis (N0, s10, s20), (0, N1, s21), (0, 0, N2) in prim coordinates, so the
+  // unit cells are still the box 0 <= i < N0, 0 <= j < N1, 0 <= k < N2, but leaving it along
+  // i also shifts j and k, leaving it along j shifts k (cmx_wrap_cell).  All zero: diag(N).
+  int32_t s10, s20, s21;
 };
 
 __host__ __device__ __forceinline__ int cmx_xpos(const Geom &g, int i) {
@@ -171,6 +176,13 @@ struct SweepPlan {
   bool e_lin = false;         // the table is linear in the counts: integer bond-count kernel
   double e_lin_c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // [occupant][c0, d1, d2]
   double *d_e_lin = nullptr;
+  // streaming global correlations (cmx_energy.cu): functions grouped by forward-neighbor set
+  int corr_lin_state = 0;  // 0: not planned yet, 1: usable, -1: not applicable
+  int corr_n_masks = 0, corr_nocc = 0;
+  uint32_t corr_mask[4] = {0, 0, 0, 0};
+  int32_t corr_z[4] = {0, 0, 0, 0};
+  int32_t *d_corr_func_mask = nullptr;  // [corr_size] index into corr_mask
+  double *d_corr_lin = nullptr;         // [corr_size][9]: c0, d1, d2 per occupant
   // per-block partial counters of the current call
   long long *d_part_acc = nullptr;
   double *d_part_dE = nullptr;
@@ -224,6 +236,7 @@ struct cmx_state {
   // thin slabs (k_sweep_pass16): k-colour groups completed by this rank; d_sig[0] / [1]: the
   // epoch my lower / upper ring neighbour reached (written by them)
   unsigned long long epoch = 0;
+  std::vector<int64_t> site_order;  // caller's l -> ours (upload / download), empty: identity
   long long seq_ties[17] = {0};  // tie report of the last cmx_metropolis_sequential call
   // scratch
   void *d_scratch = nullptr;
@@ -300,6 +313,8 @@ __device__ __forceinline__ void cmx_lin_reduce(const LinSums *__restrict__ sums,
 int cmx_energy_fast_blocks(const cmx_state *s);
 int cmx_energy_lin_batch(cmx_state *s, int nb, LinSums *d_sums);  // requires plan.e_lin
 int cmx_global_corr_device(cmx_state *s, int32_t replica, double **d_out);  // cmx_faithful.cu; result in scratch
+int cmx_plan_corr_lin(cmx_state *s);                                          // cmx_energy.cu
+int cmx_global_corr_lin_device(cmx_state *s, int32_t replica, double **d_out);
 int cmx_composition_device(cmx_state *s, int32_t replica, unsigned long long *d_counts, bool *bin0_missing);
 void cmx_plan_free(SweepPlan &p);
 
@@ -309,6 +324,34 @@ __device__ __forceinline__ int cmx_wrap(int x, int n) {
   x += (x < 0) ? n : 0;
   x -= (x >= n) ? n : 0;
   return x;
+}
+
+__host__ __device__ __forceinline__ int cmx_floor_div(int x, int n) {
+  return (x >= 0) ? x / n : -((-x + n - 1) / n);
+}
+// unit cell (i, j, k) (any integers) -> its representative inside the box.  Slab states
+// (halo) leave k alone.  diag(N) boxes take the single-wrap shortcut (|offset| <= N, checked
+// at creation); skewed boxes reduce along i, then j, then k with the lattice basis above.
+__host__ __device__ __forceinline__ void cmx_wrap_cell(const Geom &g, int &i, int &j, int &k) {
+  if (g.s10 | g.s20 | g.s21) {
+    const int q0 = cmx_floor_div(i, g.N0);
+    i -= q0 * g.N0;
+    j -= q0 * g.s10;
+    k -= q0 * g.s20;
+    const int q1 = cmx_floor_div(j, g.N1);
+    j -= q1 * g.N1;
+    k -= q1 * g.s21;
+    k -= cmx_floor_div(k, g.N2) * g.N2;
+    return;
+  }
+  i += (i < 0) ? g.N0 : 0;
+  i -= (i >= g.N0) ? g.N0 : 0;
+  j += (j < 0) ? g.N1 : 0;
+  j -= (j >= g.N1) ? g.N1 : 0;
+  if (!g.halo) {
+    k += (k < 0) ? g.N2 : 0;
+    k -= (k >= g.N2) ? g.N2 : 0;
+  }
 }
 
 // byte offset of site (b; i,j,k) inside one replica
@@ -323,9 +366,8 @@ __device__ __forceinline__ int64_t cmx_nbr_offset(const DevTables &T,
                                                   const Geom &g, int n, int i,
                                                   int j, int k, int64_t *l) {
   int4 o = T.nbr[n];
-  int ii = cmx_wrap(i + o.x, g.N0);
-  int jj = cmx_wrap(j + o.y, g.N1);
-  int kk = g.halo ? (k + o.z) : cmx_wrap(k + o.z, g.N2);
+  int ii = i + o.x, jj = j + o.y, kk = k + o.z;
+  cmx_wrap_cell(g, ii, jj, kk);
   if (l) {
     int kw = cmx_wrap(kk, g.N2);
     *l = (int64_t)o.w * g.n_cells + ((int64_t)kw * g.N1 + jj) * g.N0 + ii;
@@ -456,8 +498,8 @@ __device__ __forceinline__ double cmx_warp_site_delta_sh(const DevTables &T, con
 #pragma unroll 4
   for (int s = (int)lane; s < S.n_act; s += 32) {
     const int4 o = S.act[s];
-    const int ii = cmx_wrap(i + o.x, g.N0), jj = cmx_wrap(j + o.y, g.N1);
-    const int kk = g.halo ? (k + o.z) : cmx_wrap(k + o.z, g.N2);
+    int ii = i + o.x, jj = j + o.y, kk = k + o.z;
+    cmx_wrap_cell(g, ii, jj, kk);
     const int64_t no = cmx_site_offset(g, o.w, ii, jj, kk);
     const int raw = CG ? (int)__ldcg(occ + no) : (int)occ[no];
     const int oc = (no == ov_off) ? ov_occ : cmx_dec(raw);

@@ -91,9 +91,10 @@ __device__ __forceinline__ bool kmc_event_sites(const KmcArgs &a, const int8_t *
   S.ck = (int)(rest / g.N1);
   bool allowed = true;
   for (int q = 0; q < E.n_sites; ++q) {
-    S.si[q] = cmx_wrap(S.ci + E.site[q][1], g.N0);
-    S.sj[q] = cmx_wrap(S.cj + E.site[q][2], g.N1);
-    S.sk[q] = cmx_wrap(S.ck + E.site[q][3], g.N2);
+    S.si[q] = S.ci + E.site[q][1];
+    S.sj[q] = S.cj + E.site[q][2];
+    S.sk[q] = S.ck + E.site[q][3];
+    cmx_wrap_cell(g, S.si[q], S.sj[q], S.sk[q]);
     const int o = cmx_dec(occ[cmx_site_offset(g, E.site[q][0], S.si[q], S.sj[q], S.sk[q])]);
     if (o != E.occ_init[q]) allowed = false;
   }
@@ -562,7 +563,8 @@ __device__ void kmc_apply_impact(const KmcRunArgs &A, int r, long long ev, doubl
   // 1. events that are not allowed get rate 0 at once; the allowed ones are listed
   for (int q = threadIdx.x; q < n_imp; q += blockDim.x) {
     const int4 e = A.imp[ib + q];
-    const int i2 = cmx_wrap(ci + e.y, g.N0), j2 = cmx_wrap(cj + e.z, g.N1), k2 = cmx_wrap(ck + e.w, g.N2);
+    int i2 = ci + e.y, j2 = cj + e.z, k2 = ck + e.w;
+    cmx_wrap_cell(g, i2, j2, k2);
     const long long c2 = ((long long)k2 * g.N1 + j2) * g.N0 + i2;
     const long long id = c2 * A.n_prim + e.x;
     sh.ids[q] = id;
@@ -681,8 +683,8 @@ __global__ void __launch_bounds__(256) k_kmc_run(KmcRunArgs A) {
         const long long rest = cell / g.N0;
         const int cj = (int)(rest % g.N1), ck = (int)(rest / g.N1);
         for (int s = 0; s < E.n_sites; ++s) {
-          const int i2 = cmx_wrap(ci + E.site[s][1], g.N0), j2 = cmx_wrap(cj + E.site[s][2], g.N1),
-                    k2 = cmx_wrap(ck + E.site[s][3], g.N2);
+          int i2 = ci + E.site[s][1], j2 = cj + E.site[s][2], k2 = ck + E.site[s][3];
+          cmx_wrap_cell(g, i2, j2, k2);
           occ[cmx_site_offset(g, E.site[s][0], i2, j2, k2)] = (int8_t)cmx_enc(g, E.occ_final[s]);
         }
         if (A.log && steps < A.log_cap) {

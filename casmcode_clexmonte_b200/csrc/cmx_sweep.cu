@@ -52,6 +52,8 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_part_dE);
   cudaFree(p.d_e_lut);
   cudaFree(p.d_e_lin);
+  cudaFree(p.d_corr_func_mask);
+  cudaFree(p.d_corr_lin);
   p = SweepPlan();
 }
 
@@ -911,6 +913,21 @@ int cmx_plan_sweep(cmx_state *s) {
       for (int a = 0; a < 3; ++a) R[a] = std::max(R[a], std::abs(t->nbr[4 * n + a]));
   int N[3] = {s->g.N0, s->g.N1, s->g.N2};
   for (int a = 0; a < 3; ++a) P.S[a] = smallest_divisor_above(N[a], R[a]);
+  // skewed boxes: leaving the box along i shifts j by s10 and k by s20, along j shifts k by
+  // s21 -- the colour (i mod S0, j mod S1, k mod S2) survives the wrap only if the strides
+  // divide the shifts
+  const bool skewed = (s->g.s10 | s->g.s20 | s->g.s21) != 0;
+  bool colour_ok = true;
+  if (skewed) {
+    auto pick = [&](int n, int r, int d1, int d2) {
+      for (int q = r + 1; q <= n; ++q)
+        if (n % q == 0 && d1 % q == 0 && d2 % q == 0) return q;
+      return 0;
+    };
+    P.S[1] = pick(N[1], R[1], s->g.s10, 0);
+    P.S[2] = pick(N[2], R[2], s->g.s20, s->g.s21);
+    colour_ok = P.S[1] > 0 && P.S[2] > 0;
+  }
   P.range_k = R[2];
   P.n_colours = P.S[0] * P.S[1] * P.S[2] * (int)P.mut_points.size();
   if (s->g.halo && s->g.halo < R[2])
@@ -940,10 +957,11 @@ int cmx_plan_sweep(cmx_state *s) {
     P.bytes_per_step = bytes / nm;
     P.flops_per_step = flops / nm;
   }
-  P.valid = true;
+  P.valid = colour_ok;  // (no colouring of this skewed box: no checkerboard sweeps; everything else works)
+  if (!colour_ok) return CMX_OK;
 
   // ---- pair-LUT eligibility
-  bool ok = (T.n_sublat == 1 && np == 1 && P.mut_points.size() == 1 &&
+  bool ok = (!skewed && T.n_sublat == 1 && np == 1 && P.mut_points.size() == 1 &&
              t->n_occ[0] >= 2 && t->n_occ[0] <= 3 && T.nlist_len <= 64 &&
              s->g.N0 % 16 == 0 && s->g.N0 <= 4096 && s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 && s->g.N2 <= 65534 &&
              s->g.rep_stride < (int64_t)0x7FFFFFFFll &&
@@ -2014,8 +2032,8 @@ __global__ void k_sweep_debug_de(DebugDeArgs a, int mode) {
   if (mode == 0) {
     int cnt = 0;
     for (int n = 0; n < a.z; ++n) {
-      const int ii = cmx_wrap(i + a.shell[3 * n], g.N0), jj = cmx_wrap(j + a.shell[3 * n + 1], g.N1);
-      const int kk = g.halo ? (k + a.shell[3 * n + 2]) : cmx_wrap(k + a.shell[3 * n + 2], g.N2);
+      int ii = i + a.shell[3 * n], jj = j + a.shell[3 * n + 1], kk = k + a.shell[3 * n + 2];
+      cmx_wrap_cell(g, ii, jj, kk);
       cnt += (int)(uint8_t)a.occ[cmx_site_offset(g, 0, ii, jj, kk)];  // storage codes: n1 + 18 n2
     }
     int alt = of - oi - 1;

@@ -14,8 +14,13 @@
  * casmcode_clexmonte_b200/csrc/; there is no CPU implementation behind it --
  * without a CUDA device every compute call fails with CMX_ERR_CUDA.
  *
- * Conventions (identical to the reference's):
- *   linear site index  l = b * n_cells + cell,  cell = i + N0 * (j + N1 * k)
+ * Conventions:
+ *   linear site index  l = b * n_cells + cell  (sublattice-major, as the reference's, SURVEY.md
+ *                      Appendix B), cell = i + N0 * (j + N1 * k) over the unit cells of the
+ *                      supercell box.  The reference's unit-cell ORDER (UnitCellIndexConverter,
+ *                      [EXT] libcasm-crystallography) is not reproduced: a caller that needs
+ *                      its own numbering binds through cmx_state_cell_index /
+ *                      cmx_state_set_site_order.
  *   occupation value   occupant index on the sublattice's allowed list
  */
 #ifndef CMX_B200_H
@@ -111,6 +116,23 @@ int cmx_state_create(const cmx_tables *t, int32_t N0, int32_t N1, int32_t N2,
 #define CMX_STATE_LINEAR_ROWS 1u
 int cmx_state_create_opts(const cmx_tables *t, int32_t N0, int32_t N1, int32_t N2,
                           int32_t n_replicas, int32_t halo, uint32_t options, cmx_state **out);
+/* General supercells: T[9] (row major) is the transformation matrix to the supercell, columns
+ * = supercell lattice vectors in prim coordinates (StateData::transformation_matrix_to_super,
+ * e.g. 10 * fcc_conventional, tests/unit/teststructures.hh:12-16).  The library brings it to
+ * Hermite normal form: the unit cells are the box 0 <= i < box[0], j < box[1], k < box[2]
+ * of prim-lattice coordinates, periodic with the skewed images (box[3..5] = s10, s20, s21:
+ * leaving the box along i shifts j and k, along j shifts k).  cell = i + box[0] (j + box[1] k),
+ * l = b * n_cells + cell.  The reference numbers unit cells differently (its
+ * UnitCellIndexConverter walks the Smith normal form); cmx_state_cell_index converts unit-cell
+ * coordinates, and cmx_state_set_site_order makes upload / download speak the caller's order.
+ * Skewed boxes run the faithful evaluators, the reference-order mode, KMC and the generic
+ * checkerboard sweeps; the pair-LUT kernels and pair exchanges need diag(N0, N1, N2). */
+int cmx_state_create_general(const cmx_tables *t, const int32_t *T, int32_t n_replicas, uint32_t options,
+                             cmx_state **out);
+int cmx_state_box(const cmx_state *s, int32_t *box /*[6]*/);
+int cmx_supercell_box(const int32_t *T, int32_t *box /*[6]*/); /* host only: the box of T */
+int cmx_state_cell_index(const cmx_state *s, int64_t n, const int32_t *ijk /*[n][3]*/, int64_t *cell /*[n]*/);
+int cmx_state_set_site_order(cmx_state *s, const int64_t *order /*[n_sites] caller l -> library l, or NULL*/);
 void cmx_state_destroy(cmx_state *s);
 
 /* occupation in the reference's layout (int32, Eigen::VectorXi order

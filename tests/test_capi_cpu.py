@@ -4,6 +4,7 @@ import ctypes
 import re
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 from casmcode_clexmonte_b200 import _capi
@@ -52,3 +53,29 @@ def test_product_does_not_import_oracle():
             list((ROOT / "include").glob("*.h")):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+def test_supercell_box_is_the_same_lattice():
+    """Hermite normal form of transformation matrices (host arithmetic): lower triangular,
+    reduced, and T^-1 H unimodular -- H spans the lattice T spans.  10 * fcc_conventional
+    (tests/unit/teststructures.hh:12-16 times 10) is the box of the reference's KMC tests."""
+    from casmcode_clexmonte_b200 import _capi
+    conv = np.array([[-1, 1, 1], [1, -1, 1], [1, 1, -1]])
+    assert _capi.supercell_box(conv * 10) == (10, 20, 20, 10, 10, 0)
+    assert _capi.supercell_box(np.diag([4, 6, 8])) == (4, 6, 8, 0, 0, 0)
+    rng = np.random.default_rng(5)
+    n = 0
+    while n < 200:
+        T = rng.integers(-6, 7, (3, 3))
+        det = int(round(np.linalg.det(T)))
+        if det == 0:
+            with pytest.raises(_capi.CmxError):
+                _capi.supercell_box(T)
+            continue
+        n += 1
+        N0, N1, N2, s10, s20, s21 = _capi.supercell_box(T)
+        assert N0 * N1 * N2 == abs(det)
+        assert 0 <= s10 < N1 and 0 <= s20 < N2 and 0 <= s21 < N2
+        H = np.array([[N0, 0, 0], [s10, N1, 0], [s20, s21, N2]], dtype=float)
+        U = np.linalg.solve(T.astype(float), H)
+        assert np.allclose(U, np.round(U), atol=1e-9) and abs(abs(np.linalg.det(U)) - 1) < 1e-9

@@ -536,6 +536,26 @@ def test_checkerboard_matches_sequential_thermodynamics(dev_tables, systems, ora
         assert d <= 3 * se + floors[q], f"{name} at T={T}, mu={mu}: reference {ref[:, q].mean():.6g} gpu {gpu[:, q].mean():.6g} (3 sigma = {3 * se:.3g})"
 
 
+@pytest.mark.parametrize("N,linear", [((16, 6, 4), False), ((48, 10, 8), True), ((512, 4, 2), False), ((64, 64, 64), False)])
+def test_streaming_global_corr_equals_faithful_sum(dev_tables, systems, N, linear):
+    """Correlations::per_supercell (the `corr.<bset>` sampler) through the streaming bond-count
+    passes (cmx_energy.cu: every function of a point + pair basis is linear in the species
+    counts over its orbit's forward neighbors; one integer pass per forward-neighbor set)
+    against the faithful term-by-term sum over all cells: ALL nine functions of the FCC basis
+    (constant, points, 1NN and 2NN pairs), both row layouts, rtol 1e-12."""
+    st, sysd, _ = _sweep_state(dev_tables, systems, "fcc", "eci_sparse", N, 900.0, [0.1, 0.2], n_replicas=2, seed=11,
+                               linear_rows=linear)
+    for r in range(2):
+        fast = st.global_corr(r)
+        st.set_sweep_flags(_capi.CMX_SWEEP_FORCE_GENERIC)
+        slow = st.global_corr(r)
+        st.set_sweep_flags(0)
+        assert np.abs(slow).min() > 0      # every function is exercised
+        np.testing.assert_allclose(fast, slow, rtol=1e-12, atol=1e-9)
+    # not applicable (triplets / several sublattices): the faithful kernel serves the call
+    st.close()
+
+
 def test_error_paths(dev_tables, load_tables):
     """Error behaviour mirrors the reference: bad input -> exception, state intact."""
     st = _capi.State(dev_tables("fcc_default"), (8, 8, 8))
