@@ -81,6 +81,7 @@ struct EnergyArgs {
   const double *lut;
   double *partial;  // [gridDim.y][gridDim.x]
   LinSums *sums;    // k_energy_lin16: [gridDim.y][gridDim.x]
+  LinSums *sums2;   // second mask of the fused FCC pass
 };
 
 // one 16-site chunk: its codes C[4] and the byte-lane sums cnt[4] = n1 + 18 n2 over the
@@ -258,25 +259,37 @@ __global__ void __launch_bounds__(256) k_energy_lin16(EnergyArgs a) {
 // forward half of the FCC first shell as the generated basis orders it:
 // (0,0,1) (0,1,-1) (0,1,0) (1,-1,0) (1,0,-1) (1,0,0); MASK_CT = 0: mask from the arguments
 constexpr uint32_t kMaskFccFwd = 0x4148a0u;
-template <int NOCC, uint32_t MASK_CT>
+// forward half of the FCC second shell: (1,-1,-1) (1,-1,1) (1,1,-1)
+constexpr uint32_t kMaskFcc2nnFwd = 0x100104u;
+// MASK2_CT != 0: the bond counts of a SECOND forward-neighbor set in the same pass (the
+// global correlations of both FCC pair shells read the lattice once), into a.sums2
+template <int NOCC, uint32_t MASK_CT, uint32_t MASK2_CT>
 __global__ void __launch_bounds__(256) k_energy_row16(EnergyArgs a, uint32_t logW, uint32_t n_rows, uint32_t n_tiles,
                                                       uint32_t any_m_rt, uint32_t any_p_rt) {
-  __shared__ unsigned long long sh_sum[6];
-  if (threadIdx.x < 6) sh_sum[threadIdx.x] = 0;
+  constexpr int NM = MASK2_CT ? 2 : 1;
+  __shared__ unsigned long long sh_sum[NM][6];
+  if (threadIdx.x < 6 * NM) (&sh_sum[0][0])[threadIdx.x] = 0;
   __syncthreads();
   const Geom &g = a.g;
   const int8_t *base = a.occ + (size_t)blockIdx.y * a.rep_stride;
   const int32_t N0 = g.N0, N1 = g.N1, N2 = g.N2, layer = N0 * N1;
   const bool halo = g.halo != 0;
-  const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
-  const bool any_m = MASK_CT ? ((MASK_CT & 0x1249249u) != 0) : (any_m_rt != 0);
-  const bool any_p = MASK_CT ? ((MASK_CT & 0x4924924u) != 0) : (any_p_rt != 0);
+  const uint32_t mask[2] = {MASK_CT ? MASK_CT : a.mask, MASK2_CT};
+  const bool any_m[2] = {MASK_CT ? ((MASK_CT & 0x1249249u) != 0) : (any_m_rt != 0), (MASK2_CT & 0x1249249u) != 0};
+  const bool any_p[2] = {MASK_CT ? ((MASK_CT & 0x4924924u) != 0) : (any_p_rt != 0), (MASK2_CT & 0x4924924u) != 0};
   const uint32_t lane = threadIdx.x & 31u, Wm = a.W - 1u, c = lane & Wm, rl = lane >> logW;
   const uint32_t lane_l = (lane & ~Wm) | ((c - 1u) & Wm), lane_r = (lane & ~Wm) | ((c + 1u) & Wm);
   const uint32_t rpw_log = 5u - logW;
   const uint32_t warp0 = blockIdx.x * 8u + (threadIdx.x >> 5), n_warps = gridDim.x * 8u;
-  unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
-  uint32_t acc[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long tot[NM][6];
+  uint32_t acc[NM][6];
+#pragma unroll
+  for (int m = 0; m < NM; ++m)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      tot[m][q] = 0;
+      acc[m][q] = 0;
+    }
   uint32_t it = 0;
   for (uint32_t tile = warp0; tile < n_tiles; tile += n_warps) {
     const uint32_t row_raw = (tile << rpw_log) + rl;
@@ -291,14 +304,19 @@ __global__ void __launch_bounds__(256) k_energy_row16(EnergyArgs a, uint32_t log
     dk[0] = (!halo && k == 0) ? (N2 - 1) * layer : -layer;
     dk[1] = 0;
     dk[2] = (!halo && (int32_t)k == N2 - 1) ? -(N2 - 1) * layer : layer;
-    uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0}, C[4] = {0, 0, 0, 0};
+    uint32_t A0[NM][4], Am[NM][4], Ap[NM][4], C[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) A0[m][i] = Am[m][i] = Ap[m][i] = 0;
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy) {
-        const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
+        const int sh = (dz + 1) * 9 + (dy + 1) * 3;
+        const uint32_t m3[2] = {(mask[0] >> sh) & 7u, (mask[1] >> sh) & 7u};
         const bool center = (dz == 0 && dy == 0);
-        if (m3 == 0 && !center) continue;
+        if (m3[0] == 0 && m3[NM - 1] == 0 && !center) continue;
         const uint4 ch = *reinterpret_cast<const uint4 *>(pc + (ptrdiff_t)(dk[dz + 1] + dj[dy + 1]));
         if (center) {
           C[0] = ch.x;
@@ -306,84 +324,95 @@ __global__ void __launch_bounds__(256) k_energy_row16(EnergyArgs a, uint32_t log
           C[2] = ch.z;
           C[3] = ch.w;
         }
-        if ((m3 & 2u) && !center) {
-          A0[0] += ch.x;
-          A0[1] += ch.y;
-          A0[2] += ch.z;
-          A0[3] += ch.w;
-        }
-        if (m3 & 1u) {
-          Am[0] += ch.x;
-          Am[1] += ch.y;
-          Am[2] += ch.z;
-          Am[3] += ch.w;
-        }
-        if (m3 & 4u) {
-          Ap[0] += ch.x;
-          Ap[1] += ch.y;
-          Ap[2] += ch.z;
-          Ap[3] += ch.w;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          if ((m3[m] & 2u) && !center) {
+            A0[m][0] += ch.x;
+            A0[m][1] += ch.y;
+            A0[m][2] += ch.z;
+            A0[m][3] += ch.w;
+          }
+          if (m3[m] & 1u) {
+            Am[m][0] += ch.x;
+            Am[m][1] += ch.y;
+            Am[m][2] += ch.z;
+            Am[m][3] += ch.w;
+          }
+          if (m3[m] & 4u) {
+            Ap[m][0] += ch.x;
+            Ap[m][1] += ch.y;
+            Ap[m][2] += ch.z;
+            Ap[m][3] += ch.w;
+          }
         }
       }
     }
-    uint32_t sm = any_m ? __shfl_sync(0xffffffffu, Am[3], lane_l) : 0u;
-    uint32_t sp = any_p ? __shfl_sync(0xffffffffu, Ap[0], lane_r) : 0u;
-    uint32_t cnt[4];
-    if (g.xq_log) {  // x4-interleaved rows, see energy_chunk
-      if (c == 0) sm = __funnelshift_l(sm, sm, 8);
-      if (c == Wm) sp = __funnelshift_r(sp, sp, 8);
-      cnt[0] = A0[0] + sm + Ap[1];
-      cnt[1] = A0[1] + Am[0] + Ap[2];
-      cnt[2] = A0[2] + Am[1] + Ap[3];
-      cnt[3] = A0[3] + Am[2] + sp;
-    } else {
-      cnt[0] = A0[0] + __funnelshift_l(sm, Am[0], 8) + __funnelshift_r(Ap[0], Ap[1], 8);
-      cnt[1] = A0[1] + __funnelshift_l(Am[0], Am[1], 8) + __funnelshift_r(Ap[1], Ap[2], 8);
-      cnt[2] = A0[2] + __funnelshift_l(Am[1], Am[2], 8) + __funnelshift_r(Ap[2], Ap[3], 8);
-      cnt[3] = A0[3] + __funnelshift_l(Am[2], Am[3], 8) + __funnelshift_r(Ap[3], sp, 8);
-    }
-    if (on) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t L = cnt[i] & 0x0F0F0F0Fu;
-        const uint32_t H = (cnt[i] >> 4) & 0x0F0F0F0Fu;
-        const uint32_t p1 = C[i] & 0x01010101u;
-        acc[0] += __popc(p1);
-        acc[2] = __dp4a(p1, L, acc[2]);
-        acc[3] = __dp4a(p1, H, acc[3]);
-        if (NOCC == 3) {
-          const uint32_t p2 = C[i] & 0x10101010u;
-          acc[1] += __popc(p2);
-          acc[4] = __dp4a(p2, L, acc[4]);
-          acc[5] = __dp4a(p2, H, acc[5]);
+    for (int m = 0; m < NM; ++m) {
+      uint32_t sm = any_m[m] ? __shfl_sync(0xffffffffu, Am[m][3], lane_l) : 0u;
+      uint32_t sp = any_p[m] ? __shfl_sync(0xffffffffu, Ap[m][0], lane_r) : 0u;
+      uint32_t cnt[4];
+      if (g.xq_log) {  // x4-interleaved rows, see energy_chunk
+        if (c == 0) sm = __funnelshift_l(sm, sm, 8);
+        if (c == Wm) sp = __funnelshift_r(sp, sp, 8);
+        cnt[0] = A0[m][0] + sm + Ap[m][1];
+        cnt[1] = A0[m][1] + Am[m][0] + Ap[m][2];
+        cnt[2] = A0[m][2] + Am[m][1] + Ap[m][3];
+        cnt[3] = A0[m][3] + Am[m][2] + sp;
+      } else {
+        cnt[0] = A0[m][0] + __funnelshift_l(sm, Am[m][0], 8) + __funnelshift_r(Ap[m][0], Ap[m][1], 8);
+        cnt[1] = A0[m][1] + __funnelshift_l(Am[m][0], Am[m][1], 8) + __funnelshift_r(Ap[m][1], Ap[m][2], 8);
+        cnt[2] = A0[m][2] + __funnelshift_l(Am[m][1], Am[m][2], 8) + __funnelshift_r(Ap[m][2], Ap[m][3], 8);
+        cnt[3] = A0[m][3] + __funnelshift_l(Am[m][2], Am[m][3], 8) + __funnelshift_r(Ap[m][3], sp, 8);
+      }
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t L = cnt[i] & 0x0F0F0F0Fu;
+          const uint32_t H = (cnt[i] >> 4) & 0x0F0F0F0Fu;
+          const uint32_t p1 = C[i] & 0x01010101u;
+          acc[m][0] += __popc(p1);
+          acc[m][2] = __dp4a(p1, L, acc[m][2]);
+          acc[m][3] = __dp4a(p1, H, acc[m][3]);
+          if (NOCC == 3) {
+            const uint32_t p2 = C[i] & 0x10101010u;
+            acc[m][1] += __popc(p2);
+            acc[m][4] = __dp4a(p2, L, acc[m][4]);
+            acc[m][5] = __dp4a(p2, H, acc[m][5]);
+          }
         }
       }
     }
     if ((++it & 1023u) == 0) {
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        tot[q] += acc[q];
-        acc[q] = 0;
-      }
+      for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          tot[m][q] += acc[m][q];
+          acc[m][q] = 0;
+        }
     }
   }
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    tot[q] += acc[q];
+  for (int m = 0; m < NM; ++m)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot[q] += __shfl_down_sync(0xffffffffu, tot[q], o);
-    if ((threadIdx.x & 31) == 0 && tot[q]) atomicAdd(&sh_sum[q], tot[q]);
-  }
+    for (int q = 0; q < 6; ++q) {
+      tot[m][q] += acc[m][q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot[m][q] += __shfl_down_sync(0xffffffffu, tot[m][q], o);
+      if ((threadIdx.x & 31) == 0 && tot[m][q]) atomicAdd(&sh_sum[m][q], tot[m][q]);
+    }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < NM) {
+    const int m = threadIdx.x;
     LinSums r;
-    r.n1 = sh_sum[0];
-    r.n2 = sh_sum[1];
-    r.sl1 = sh_sum[2];
-    r.sh1 = sh_sum[3];
-    r.sl2 = sh_sum[4];
-    r.sh2 = sh_sum[5];
-    a.sums[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = r;
+    r.n1 = sh_sum[m][0];
+    r.n2 = sh_sum[m][1];
+    r.sl1 = sh_sum[m][2];
+    r.sh1 = sh_sum[m][3];
+    r.sl2 = sh_sum[m][4];
+    r.sh2 = sh_sum[m][5];
+    (m ? a.sums2 : a.sums)[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = r;
   }
 }
 
@@ -506,16 +535,20 @@ static EnergyArgs energy_args(const cmx_state *s, int32_t first_replica) {
   a.lut = P.d_e_lut;
   a.partial = nullptr;
   a.sums = nullptr;
+  a.sums2 = nullptr;
   return a;
 }
 
 // launch the bond-count pass over `n_rep` replicas starting at a.occ
-static int launch_energy_lin(const cmx_state *s, EnergyArgs &a, int nb, int n_rep, int nocc_override = 0) {
+static bool energy_warp_rows(const EnergyArgs &a) {
+  static const bool force_block = getenv("CMX_ENERGY_BLOCK") != nullptr;  // cross-check of the two kernels
+  return a.W <= 32 && (a.W & (a.W - 1)) == 0 && !force_block;  // a warp owns whole rows
+}
+static int launch_energy_lin(const cmx_state *s, EnergyArgs &a, int nb, int n_rep, int nocc_override = 0,
+                             uint32_t mask2 = 0) {
   const int nocc = nocc_override ? nocc_override : s->plan.nocc;
   dim3 grid(nb, n_rep);
-  static const bool force_block = getenv("CMX_ENERGY_BLOCK") != nullptr;  // cross-check of the two kernels
-  const bool warp_rows = a.W <= 32 && (a.W & (a.W - 1)) == 0;  // a warp owns whole rows
-  if (warp_rows && !force_block) {
+  if (energy_warp_rows(a)) {
     uint32_t logW = 0;
     while ((1u << logW) < a.W) ++logW;
     const uint32_t n_rows = (uint32_t)s->g.N1 * (uint32_t)s->g.N2, rpw = 32u >> logW;
@@ -525,14 +558,20 @@ static int launch_energy_lin(const cmx_state *s, EnergyArgs &a, int nb, int n_re
       any_m |= (a.mask >> (3 * q)) & 1u;
       any_p |= (a.mask >> (3 * q + 2)) & 1u;
     }
-    if (a.mask == kMaskFccFwd) {
-      if (nocc == 3) k_energy_row16<3, kMaskFccFwd><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
-      else k_energy_row16<2, kMaskFccFwd><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+    if (a.mask == kMaskFccFwd && mask2 == kMaskFcc2nnFwd) {
+      if (nocc == 3) k_energy_row16<3, kMaskFccFwd, kMaskFcc2nnFwd><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+      else k_energy_row16<2, kMaskFccFwd, kMaskFcc2nnFwd><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+    } else if (mask2) {
+      return CMX_ERR_UNSUPPORTED;  // (callers ask cmx_energy_lin_fusable first)
+    } else if (a.mask == kMaskFccFwd) {
+      if (nocc == 3) k_energy_row16<3, kMaskFccFwd, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+      else k_energy_row16<2, kMaskFccFwd, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
     } else {
-      if (nocc == 3) k_energy_row16<3, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
-      else k_energy_row16<2, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+      if (nocc == 3) k_energy_row16<3, 0u, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
+      else k_energy_row16<2, 0u, 0u><<<grid, 256, 0, s->stream>>>(a, logW, n_rows, n_tiles, any_m, any_p);
     }
   } else {
+    if (mask2) return CMX_ERR_UNSUPPORTED;
     if (nocc == 3) k_energy_lin16<3><<<grid, 256, 0, s->stream>>>(a);
     else k_energy_lin16<2><<<grid, 256, 0, s->stream>>>(a);
   }
@@ -606,28 +645,43 @@ int cmx_energy_fast(cmx_state *s, int32_t replica, double *E) {
 // ---------------------------------------------------------------------------
 struct CorrLinFinalArgs {
   const LinSums *sums;  // [n_masks][nb]
-  int nb, n_masks, corr_size;
+  int nb, n_masks, corr_size, mask0_from;
   long long n_cells;
   int z[4];
   const int32_t *func_mask;  // [corr_size]
   const double *lin;         // [corr_size][9]
   double *out;               // [corr_size]
 };
-__global__ void k_corr_lin_final(CorrLinFinalArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.corr_size) return;
-  const int m = a.func_mask[c];
-  const LinSums *sm = a.sums + (size_t)m * a.nb;
-  unsigned long long v[6] = {0, 0, 0, 0, 0, 0};
-  for (int b = 0; b < a.nb; ++b) {  // integers: any order
-    v[0] += sm[b].n1;
-    v[1] += sm[b].n2;
-    v[2] += sm[b].sl1;
-    v[3] += sm[b].sh1;
-    v[4] += sm[b].sl2;
-    v[5] += sm[b].sh2;
+__global__ void __launch_bounds__(256) k_corr_lin_final(CorrLinFinalArgs a) {  // one block
+  __shared__ unsigned long long sh[4][6];
+  if (threadIdx.x < 24) (&sh[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+  for (int m = 0; m < a.n_masks; ++m) {
+    const LinSums *sm = a.sums + (size_t)(m ? m : a.mask0_from) * a.nb;
+    unsigned long long v[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < a.nb; b += blockDim.x) {  // integers: any order
+      v[0] += sm[b].n1;
+      v[1] += sm[b].n2;
+      v[2] += sm[b].sl1;
+      v[3] += sm[b].sh1;
+      v[4] += sm[b].sl2;
+      v[5] += sm[b].sh2;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+      if ((threadIdx.x & 31) == 0 && v[q]) atomicAdd(&sh[m][q], v[q]);
+    }
   }
-  a.out[c] = cmx_lin_energy(v, a.n_cells, a.z[m], a.lin + 9 * c, nullptr);
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.corr_size; c += blockDim.x) {
+    const int m = a.func_mask[c];
+    unsigned long long v[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) v[q] = sh[m][q];
+    a.out[c] = cmx_lin_energy(v, a.n_cells, a.z[m], a.lin + 9 * c, nullptr);
+  }
 }
 
 int cmx_plan_corr_lin(cmx_state *s) {
@@ -754,10 +808,18 @@ int cmx_global_corr_lin_device(cmx_state *s, int32_t replica, double **d_out) {
   char *base = static_cast<char *>(s->d_scratch);
   // masks[0] (no neighbors) needs the occupant counts only: they are part of every pass, so
   // it shares the pass of masks[1] when there is one
-  for (int m = (M > 1 ? 1 : 0); m < M; ++m) {
-    a.mask = P.corr_mask[m];
-    a.sums = reinterpret_cast<LinSums *>(base) + (size_t)m * nb;
-    if ((rc = launch_energy_lin(s, a, nb, 1, P.corr_nocc))) return rc;
+  if (M == 3 && P.corr_mask[1] == kMaskFccFwd && P.corr_mask[2] == kMaskFcc2nnFwd && energy_warp_rows(a)) {
+    // both FCC pair shells in one pass over the lattice
+    a.mask = kMaskFccFwd;
+    a.sums = reinterpret_cast<LinSums *>(base) + (size_t)nb;
+    a.sums2 = reinterpret_cast<LinSums *>(base) + (size_t)2 * nb;
+    if ((rc = launch_energy_lin(s, a, nb, 1, P.corr_nocc, kMaskFcc2nnFwd))) return rc;
+  } else {
+    for (int m = (M > 1 ? 1 : 0); m < M; ++m) {
+      a.mask = P.corr_mask[m];
+      a.sums = reinterpret_cast<LinSums *>(base) + (size_t)m * nb;
+      if ((rc = launch_energy_lin(s, a, nb, 1, P.corr_nocc))) return rc;
+    }
   }
   CorrLinFinalArgs f;
   f.sums = reinterpret_cast<const LinSums *>(base);
@@ -769,13 +831,10 @@ int cmx_global_corr_lin_device(cmx_state *s, int32_t replica, double **d_out) {
   f.func_mask = P.d_corr_func_mask;
   f.lin = P.d_corr_lin;
   f.out = reinterpret_cast<double *>(base + off_out);
-  if (M > 1) {
-    // functions without neighbors read the counts of pass 1
-    // (their d1 = d2 = 0: only N_o enters, which every pass counts)
-    CMX_CUDA(cudaMemcpyAsync(base, base + sizeof(LinSums) * (size_t)nb, sizeof(LinSums) * (size_t)nb,
-                             cudaMemcpyDeviceToDevice, s->stream));
-  }
-  k_corr_lin_final<<<(nc + 63) / 64, 64, 0, s->stream>>>(f);
+  // functions without neighbors (mask 0) read the counts of pass 1: their d1 = d2 = 0, only
+  // N_o enters, which every pass counts
+  f.mask0_from = (M > 1) ? 1 : 0;
+  k_corr_lin_final<<<1, 256, 0, s->stream>>>(f);
   CMX_CUDA(cudaGetLastError());
   *d_out = f.out;
   return CMX_OK;
