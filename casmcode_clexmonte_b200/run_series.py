@@ -14,9 +14,11 @@ replicas of ONE device state: one equilibration call and one sampled run (Sample
 advance the whole path.  dependent_runs == true is inherently sequential (state k starts
 from the final configuration of state k-1) and is run one state at a time on replica 0.
 
-Results are returned per state with the reference's sampler / analysis function names;
-writing summary.json / completed_runs.json stays with the reference's results I/O
-([EXT] libcasm-monte jsonResultsIO), which is not present in this repository's toolchain.
+Results are returned per state with the reference's sampler / analysis function names and,
+when an output directory is given, written as the reference writes them: one column per run
+appended to summary.json, RunData appended to completed_runs.json (results_io.py); a series
+started again with the same output directory reads completed_runs.json and continues after
+the last completed state (run/IncrementalConditionsStateGenerator.hh:100-196).
 """
 from __future__ import annotations
 
@@ -24,8 +26,11 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
+import time
+
 from . import _capi
 from .potential import semigrand_exchange_table
+from .results_io import CompletedRuns, RunDataOutputParams, SummaryWriter, state_to_json
 
 
 def make_incremented_values(initial: Dict, increment: Dict, k: int) -> Dict:
@@ -51,13 +56,37 @@ def conditions_path(initial: Dict, increment: Dict, n_states: int) -> List[Dict]
 def run_series(tables: "_capi.Tables", N: Sequence[int], system: Dict, eci_index, eci_value,
                initial_conditions: Dict, conditions_increment: Dict, n_states: int, occupation: np.ndarray,
                n_equilibration_passes: int, n_samples: int, sample_period: int = 1, seed: int = 0,
-               dependent_runs: bool = False, with_corr: bool = False) -> List[Dict]:
+               dependent_runs: bool = False, with_corr: bool = False,
+               output_params: Optional[RunDataOutputParams] = None, summary_dir=None) -> List[Dict]:
     """Semi-grand canonical run series.  `system`: occ_to_species, sublat_to_asym, n_species,
     axes {origin, Rt}.  Conditions: {"temperature": T, "param_chem_pot": [...]}.
-    Returns one dict per state: conditions, means of the sampled quantities, the analysis
-    functions, acceptance rate, final occupation."""
+    Returns one dict per state RUN BY THIS CALL: conditions, means of the sampled quantities,
+    the analysis functions, acceptance rate, final occupation.  output_params.output_dir:
+    completed_runs.json (read first: completed states are not run again); summary_dir
+    (default: the same directory): summary.json."""
     path = conditions_path(initial_conditions, conditions_increment, n_states)
     axes = system["axes"]
+    completed = CompletedRuns(output_params or RunDataOutputParams())
+    n_done = min(completed.read(), len(path))
+    if summary_dir is None:
+        summary_dir = completed.params.output_dir
+    species = system.get("species") or [str(i) for i in range(system["n_species"])]
+    param_names = ["abcdefghijklmnopqrstuvwxyz"[q] for q in range(len(axes["Rt"]))]
+    summary = SummaryWriter(summary_dir, species, param_names) if summary_dir else None
+    T_super = np.diag([int(x) for x in (N if not np.isscalar(N) else (N, N, N))])
+
+    def record(res: Dict, cond: Dict, occ_initial, series, n_attempt, seconds) -> None:
+        jc = {k: np.asarray(v).tolist() for k, v in cond.items()}
+        completed.append({"initial_state": state_to_json(occ_initial, T_super, jc),
+                          "final_state": state_to_json(res["final_occupation"], T_super, jc),
+                          "conditions": jc, "transformation_matrix_to_supercell": T_super.tolist(),
+                          "n_unitcells": int(np.prod(np.diag(T_super)))})
+        completed.write()
+        if summary is not None:
+            analysis = {k: res[k] for k in ("heat_capacity", "mol_susc", "param_susc", "mol_thermochem_susc",
+                                            "param_thermochem_susc") if k in res}
+            summary.append(jc, analysis, series, int(n_samples), res["acceptance_rate"], int(n_attempt), seconds)
+
     max_occ = tables.host.max_occ
     o2s = np.full((len(system["occ_to_species"]), max_occ), -1, dtype=np.int32)
     for b, row in enumerate(system["occ_to_species"]):
@@ -75,8 +104,13 @@ def run_series(tables: "_capi.Tables", N: Sequence[int], system: Dict, eci_index
             sm.set_param_chem_pot(mu, r)
         return st, sm
 
-    def collect(st, sm, r, cond, counters) -> Dict:
+    def collect(st, sm, r, cond, counters, occ_initial=None, seconds=0.0) -> Dict:
         ser = sm.series(r)
+        out = _collect(st, sm, r, cond, counters, ser)
+        record(out, cond, occupation if occ_initial is None else occ_initial, ser, counters[r].n_attempt, seconds)
+        return out
+
+    def _collect(st, sm, r, cond, counters, ser) -> Dict:
         out = {"conditions": {k: np.asarray(v).tolist() for k, v in cond.items()},
                "acceptance_rate": counters[r].n_accept / max(1, counters[r].n_attempt),
                "final_occupation": st.download_occ(r, dtype=np.int8)}
@@ -86,23 +120,36 @@ def run_series(tables: "_capi.Tables", N: Sequence[int], system: Dict, eci_index
         return out
 
     results = []
+    todo = path[n_done:]
+    if not todo:
+        return results
     if not dependent_runs:
-        st, sm = make_state(path)
-        for r in range(len(path)):
+        t0 = time.perf_counter()
+        st, sm = make_state(todo)
+        for r in range(len(todo)):
             st.upload_occ(occupation, r)
         st.sgc_sweep(int(n_equilibration_passes), seed=seed, counters=False)
         cnt = sm.run(int(n_samples), int(sample_period), seed=seed, first_sweep=int(n_equilibration_passes))
-        results = [collect(st, sm, r, path[r], cnt) for r in range(len(path))]
+        st.synchronize()
+        dt = (time.perf_counter() - t0) / len(todo)
+        results = [collect(st, sm, r, todo[r], cnt, seconds=dt) for r in range(len(todo))]
         sm.close()
         st.close()
         return results
     occ = np.asarray(occupation)
-    for k, cond in enumerate(path):
+    if n_done:
+        occ = completed.last_final_occupation()
+        if occ is None:
+            raise ValueError("run_series: when dependent_runs == true the final state of the last completed run "
+                             "must have been saved (save_last_final_state / write_final_states)")
+    for k, cond in enumerate(todo, start=n_done):
+        t0 = time.perf_counter()
         st, sm = make_state([cond])
         st.upload_occ(occ)
         st.sgc_sweep(int(n_equilibration_passes), seed=seed + k, counters=False)
         cnt = sm.run(int(n_samples), int(sample_period), seed=seed + k, first_sweep=int(n_equilibration_passes))
-        res = collect(st, sm, 0, cond, cnt)
+        st.synchronize()
+        res = collect(st, sm, 0, cond, cnt, occ_initial=occ, seconds=time.perf_counter() - t0)
         occ = res["final_occupation"]
         results.append(res)
         sm.close()

@@ -345,6 +345,52 @@ def test_run_series_batches_the_conditions_path(dev_tables, systems):
     assert dep[1]["conditions"]["temperature"] == 900.0 and dep[1]["potential_energy"]["n_samples"] == 6
 
 
+def test_run_series_writes_the_reference_result_files_and_restarts(dev_tables, systems, tmp_path):
+    """summary.json in the layout python/tests/conftest.py:180-240 (validate_summary_file) of
+    the reference checks, completed_runs.json per RunData_json_io.hh, and the restart of
+    python/tests/run_management/test_run_series.py: a series started again on the same output
+    directory continues after the completed states -- dependent runs from the saved final
+    state -- and ends with the files an uninterrupted series writes."""
+    import json
+    from test_run_series_cpu import validate_summary_file
+    from casmcode_clexmonte_b200.results_io import RunDataOutputParams
+    from casmcode_clexmonte_b200.run_series import run_series
+    sysd = systems["zro"]
+    eci = sysd["eci"]
+    N = (6, 6, 4)
+    n_cells = int(np.prod(N))
+    occ = np.zeros(4 * n_cells, dtype=np.int32)
+    init = {"temperature": 300.0, "param_chem_pot": [-4.0]}
+    inc = {"temperature": 0.0, "param_chem_pot": [0.5]}
+    kw = dict(n_equilibration_passes=4, n_samples=8, sample_period=1, seed=3, dependent_runs=True)
+
+    def series(out, n_states):
+        p = RunDataOutputParams(do_save_all_initial_states=True, do_save_all_final_states=True,
+                                write_initial_states=True, write_final_states=True, output_dir=str(out))
+        return run_series(dev_tables(sysd["tables"]), N, sysd, eci["index"], eci["value"], init, inc, n_states, occ,
+                          output_params=p, **kw)
+
+    full = series(tmp_path / "full", 5)
+    assert len(full) == 5
+    first = series(tmp_path / "parts", 2)
+    rest = series(tmp_path / "parts", 5)          # reads completed_runs.json: runs states 2, 3, 4 only
+    assert len(first) == 2 and len(rest) == 3
+    assert [r["conditions"]["param_chem_pot"] for r in rest] == [[-3.0], [-2.5], [-2.0]]
+    assert series(tmp_path / "parts", 5) == []    # complete: nothing left to run
+    a = validate_summary_file(tmp_path / "full" / "summary.json", 5)
+    b = validate_summary_file(tmp_path / "parts" / "summary.json", 5)
+    for sec in ("analysis", "conditions", "statistics"):
+        assert a[sec] == b[sec], sec
+    assert a["completion_check_results"]["count"] == b["completion_check_results"]["count"] == [8 * 2 * n_cells] * 5
+    assert a["conditions"]["param_chem_pot"]["a"] == [-4.0, -3.5, -3.0, -2.5, -2.0]
+    ra = json.loads((tmp_path / "full" / "completed_runs.json").read_text())
+    rb = json.loads((tmp_path / "parts" / "completed_runs.json").read_text())
+    assert ra == rb and len(ra) == 5
+    assert ra[3]["initial_state"]["configuration"]["dof"]["occ"] == ra[2]["final_state"]["configuration"]["dof"]["occ"]
+    assert ra[0]["n_unitcells"] == n_cells and ra[0]["transformation_matrix_to_supercell"] == np.diag(N).tolist()
+    assert (np.array(ra[4]["final_state"]["configuration"]["dof"]["occ"]) == full[4]["final_occupation"]).all()
+
+
 def test_device_moments_equal_the_series_moments(dev_tables, systems):
     """cmx_sampler_moments ({n, sum q, sum q q^T} per replica, accumulated on the device: what
     ranks all-reduce for a replica grid) against the same sums of the downloaded series, and
