@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import json
 from pathlib import Path
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -151,3 +151,55 @@ def make_relative_impact_table(prim_events: Sequence[dict], neighborhoods: Seque
         entries.extend(sorted(rows, key=lambda e: (e[3], e[2], e[1], e[0])))
         beg.append(len(entries))
     return np.asarray(beg, dtype=np.int32), np.asarray(entries, dtype=np.int32).reshape(-1, 4)
+
+
+# ---------------------------------------------------------------------------
+# calculator parameters (accepted as the reference accepts them)
+# ---------------------------------------------------------------------------
+KINETIC_PARAMS = {
+    # key: (default, allowed values or None)
+    "verbosity": ("standard", None),
+    "print_event_data_summary": (False, (True, False)),
+    "mol_composition_tol": (1e-10, None),
+    "event_data_type": ("default", ("high_memory", "default", "low_memory")),
+    "event_selector_type": ("vector_sum_tree", ("vector_sum_tree", "sum_tree", "direct_sum")),
+    "abnormal_event_handling": (None, None),
+    "impact_table_type": ("neighborlist", ("neighborlist", "relative")),
+    "assign_allowed_events_only": (True, (True, False)),
+    "selected_event_data": (None, None),
+}
+
+
+def parse_kinetic_params(params: Optional[dict]) -> dict:
+    """The "params" of the kinetic calculator as KineticCalculator::_reset reads them
+    (src/casm/clexmonte/monte_calculator/KineticCalculator.cc:78-100 lists the keys,
+    :707-830 the values): unknown keys and invalid values are errors with the reference's
+    wording; the accepted values are returned with defaults filled in.
+
+    On the device these choose nothing: the selector is always the block-local sum tree over
+    the COMPLETE event list with the relative impact table (cmx_kmc.cu), whose selections equal
+    the reference's for every event_data_type / event_selector_type / impact_table_type --
+    those only trade memory for speed on the host and do not change which event a random
+    number picks.  ``device_equivalent`` in the result names what runs."""
+    params = dict(params or {})
+    unknown = sorted(set(params) - set(KINETIC_PARAMS))
+    if unknown:
+        raise ValueError(f"Error in KineticCalculator: unrecognized params: {unknown}")
+    out = {}
+    for key, (default, allowed) in KINETIC_PARAMS.items():
+        v = params.get(key, default)
+        if allowed is not None and v not in allowed:
+            raise ValueError(f"Invalid {key}: {v!r} (allowed: {list(allowed)})")
+        out[key] = v
+    out["device_equivalent"] = dict(event_data_type="high_memory", event_selector_type="vector_sum_tree",
+                                    impact_table_type="relative")
+    return out
+
+
+def allowed_event_list(is_allowed: np.ndarray, n_prim_events: int):
+    """The allowed-event list of AllowedEventList (src/casm/clexmonte/events/AllowedEventList.cc:70-98):
+    the (unitcell_index, prim_event_index) of every event whose is_allowed flag is set, in
+    complete-list order.  `is_allowed`: flags of the complete event list (unit cell major),
+    e.g. ``Kmc.event_states(*complete_event_list(...))["is_allowed"]``."""
+    idx = np.flatnonzero(np.asarray(is_allowed).reshape(-1))
+    return idx // int(n_prim_events), (idx % int(n_prim_events)).astype(np.int32)

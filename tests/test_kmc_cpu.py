@@ -215,3 +215,31 @@ def test_relative_impact_table_point_only(systems, load_tables):
     assert [len(x) for x in nbh] == [2] * 12
     beg, ent = K.make_relative_impact_table(prim, nbh)
     assert (np.diff(beg) == 46).all()
+
+
+def test_kinetic_params_are_accepted_like_the_reference():
+    """KineticCalculator.cc:78-100 (keys), :707-830 (values and defaults)."""
+    p = K.parse_kinetic_params(None)
+    assert (p["event_data_type"], p["event_selector_type"], p["impact_table_type"]) == \
+        ("default", "vector_sum_tree", "neighborlist")
+    assert p["assign_allowed_events_only"] is True
+    for sel in ("vector_sum_tree", "sum_tree", "direct_sum"):
+        for imp in ("neighborlist", "relative"):
+            for dat in ("high_memory", "default", "low_memory"):
+                q = K.parse_kinetic_params({"event_selector_type": sel, "impact_table_type": imp,
+                                            "event_data_type": dat})
+                assert q["device_equivalent"]["impact_table_type"] == "relative"
+    with pytest.raises(ValueError, match="event_selector_type"):
+        K.parse_kinetic_params({"event_selector_type": "heap"})
+    with pytest.raises(ValueError, match="impact_table_type"):
+        K.parse_kinetic_params({"impact_table_type": "absolute"})
+    with pytest.raises(ValueError, match="unrecognized"):
+        K.parse_kinetic_params({"event_selector": "sum_tree"})
+
+
+def test_allowed_event_list_order():
+    """AllowedEventList.cc:70-98: allowed events in complete-list (unit cell major) order."""
+    flags = np.zeros((5, 4), dtype=np.int32)
+    flags[0, 3] = flags[2, 1] = flags[2, 2] = flags[4, 0] = 1
+    uc, pe = K.allowed_event_list(flags, 4)
+    assert uc.tolist() == [0, 2, 2, 4] and pe.tolist() == [3, 1, 2, 0]
