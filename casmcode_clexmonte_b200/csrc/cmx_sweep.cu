@@ -48,6 +48,7 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_tab24);
   for (auto &kv : p.stream_lists) cudaFree(kv.second.d_units);
   cudaFree(p.d_ticket);
+  cudaFree(p.d_gridbar);
   cudaFree(p.d_part_acc);
   cudaFree(p.d_part_dE);
   cudaFree(p.d_e_lut);
@@ -1191,22 +1192,25 @@ static StreamKernel stream_kernel(const cmx_state *s, bool accum, bool slab, siz
 
 typedef void (*PassKernel)(S16Args, PassArgs);
 template <int NOCC, uint32_t MASK, bool FULL>
-static PassKernel pass_kernel_nmf(bool accum) {
-  return accum ? k_sweep_pass16<NOCC, MASK, true, true, FULL> : k_sweep_pass16<NOCC, MASK, false, true, FULL>;
+static PassKernel pass_kernel_nmf(bool accum, bool slab) {
+  if (slab) return accum ? k_sweep_pass16<NOCC, MASK, true, true, FULL> : k_sweep_pass16<NOCC, MASK, false, true, FULL>;
+  return accum ? k_sweep_pass16<NOCC, MASK, true, false, FULL> : k_sweep_pass16<NOCC, MASK, false, false, FULL>;
 }
+// (slab: the instantiation that carries the ring protocol and the peer stores)
 static PassKernel pass_kernel(const cmx_state *s, bool accum, size_t *smem) {
   const SweepPlan &P = s->plan;
   const bool fcc = (P.mask == kMaskFcc1NN);
+  const bool slab = s->p2p && s->g.halo;
   const uint32_t rpw = 32u / ((uint32_t)s->g.N0 / 16u);
   const bool full = ((uint32_t)s->g.N1 / 2u) % rpw == 0;
   if (P.nocc == 3) {
     *smem = s16_smem_bytes<3>(fcc ? kMaskFcc1NN : 0u);
-    if (fcc) return full ? pass_kernel_nmf<3, kMaskFcc1NN, true>(accum) : pass_kernel_nmf<3, kMaskFcc1NN, false>(accum);
-    return full ? pass_kernel_nmf<3, 0u, true>(accum) : pass_kernel_nmf<3, 0u, false>(accum);
+    if (fcc) return full ? pass_kernel_nmf<3, kMaskFcc1NN, true>(accum, slab) : pass_kernel_nmf<3, kMaskFcc1NN, false>(accum, slab);
+    return full ? pass_kernel_nmf<3, 0u, true>(accum, slab) : pass_kernel_nmf<3, 0u, false>(accum, slab);
   }
   *smem = s16_smem_bytes<2>(fcc ? kMaskFcc1NN : 0u);
-  if (fcc) return full ? pass_kernel_nmf<2, kMaskFcc1NN, true>(accum) : pass_kernel_nmf<2, kMaskFcc1NN, false>(accum);
-  return full ? pass_kernel_nmf<2, 0u, true>(accum) : pass_kernel_nmf<2, 0u, false>(accum);
+  if (fcc) return full ? pass_kernel_nmf<2, kMaskFcc1NN, true>(accum, slab) : pass_kernel_nmf<2, kMaskFcc1NN, false>(accum, slab);
+  return full ? pass_kernel_nmf<2, 0u, true>(accum, slab) : pass_kernel_nmf<2, 0u, false>(accum, slab);
 }
 
 // x4-interleaved rows: colour passes with grid barriers (k_sweep_pass16, the default: measured
@@ -1621,11 +1625,35 @@ static int sweep_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t 
   const uint32_t n_rs = a.tpu * c.H;
   if (!g.halo && (rc = l2_persist_lattice(s))) return rc;
   dim3 grid(std::min<uint32_t>((uint32_t)P.stream_blocks, (n_rs + 7) / 8), (unsigned)s->n_replicas);
+  c.dq_k = (grid.x * 8u) / a.tpu;
+  c.dq_r = (grid.x * 8u) % a.tpu;
+  c.ch_row = a.W;
+  c.ch_layer = (uint32_t)g.N1 * a.W;
+  c.ch_pair = 2u * c.ch_layer;
+  c.ch_wrap_j = (int32_t)(((uint32_t)g.N1 - 1u) * a.W);
+  c.ch_wrap_k = (int32_t)(((uint32_t)g.N2 - 1u) * c.ch_layer);
+  c.gid_off = ((uint32_t)s->k_offset - (uint32_t)g.halo) * c.ch_layer;
+  if (((uint64_t)g.rep_stride >> 4) >= (1ull << 32)) {
+    cmx_set_error("colour-pass sweep: a replica exceeds 2^32 16-byte chunks");
+    return CMX_ERR_UNSUPPORTED;
+  }
+  if (!P.d_gridbar) {
+    CMX_CUDA(cudaMalloc((void **)&P.d_gridbar, sizeof(uint32_t)));
+    CMX_CUDA(cudaMemsetAsync(P.d_gridbar, 0, sizeof(uint32_t), s->stream));
+    P.gridbar_count = 0;
+  }
+  c.bar = P.d_gridbar;
+  c.n_blocks = grid.x * grid.y;
+  const uint32_t passes_per_sweep = kgroup < 0 ? 4u : 2u;
+  // (the barrier counter is compared modulo 2^32: a launch adds less than 2^30 arrivals)
+  const int64_t max_sweeps = std::max<int64_t>(1, (int64_t)((1u << 30) / (passes_per_sweep * c.n_blocks)));
   for (int64_t done = 0; done < n_sweeps;) {
-    const int64_t n = std::min<int64_t>(n_sweeps - done, 1 << 20);
+    const int64_t n = std::min<int64_t>(n_sweeps - done, std::min<int64_t>(1 << 20, max_sweeps));
     c.n_sweeps = (uint32_t)n;
     c.first_sweep = (unsigned long long)(first_sweep + done);
     c.epoch0 = s->epoch;
+    c.bar_base = P.gridbar_count;
+    P.gridbar_count += (uint32_t)n * passes_per_sweep * c.n_blocks;
     void *args[2] = {&a, &c};
     CMX_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(256), args, smem, s->stream));
     if (a.push) s->epoch += 2ull * (unsigned long long)n;

@@ -30,6 +30,7 @@
 // exchange -- no collective, no barrier, no host round trip.
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #define CMX_TAB24(NOCC) ((NOCC) == 3 ? 23 * 256 : 512)
 
@@ -281,10 +282,17 @@ __device__ __forceinline__ void s16_issue(const S16Args &a, const int8_t *pc, in
 // One row-step: every lane updates both x colours of its chunk of row (j, k) and stores it
 // (lanes with on == false redo a valid row without storing).  The rows were staged by
 // s16_issue into `slots`; after_loads() runs once this lane has read its slots.
+// base + 16 t: one multiply-add (the chunk index t is what the callers carry)
+__device__ __forceinline__ int8_t *s16_chunk_ptr(const int8_t *base, uint32_t t) {
+  unsigned long long p;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(p) : "r"(t), "l"((unsigned long long)base));
+  return reinterpret_cast<int8_t *>(p);
+}
+
 template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, typename Hook>
-__device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, int8_t *pc, uint32_t gid, int32_t k,
-                                            uint32_t sweep_lo, uint32_t ctr_hi, bool on, int32_t &n_acc,
-                                            double &e_tot, uint32_t slots, Hook after_loads) {
+__device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, const int8_t *pbase, uint32_t pt,
+                                            uint32_t gid, int32_t k, uint32_t sweep_lo, uint32_t ctr_hi, bool on,
+                                            int32_t &n_acc, double &e_tot, uint32_t slots, Hook after_loads) {
   const Geom &g = a.g;
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const uint32_t mc = (mask >> 12) & 7u;  // center row: dx = -1 / +1 bits
@@ -445,7 +453,8 @@ __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, 
   if (on) {
     if (ACCUM) e_tot += e_sum;
     const uint4 out = make_uint4(C[0], C[1], C[2], C[3]);
-    *reinterpret_cast<uint4 *>(pc) = out;
+    int8_t *const pc = s16_chunk_ptr(pbase, pt);
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pc), "r"(out.x), "r"(out.y), "r"(out.z), "r"(out.w) : "memory");
     // rejected lanes hold 0xFF = -1: four signed dot products count them
     n_acc = __dp4a((int)rj[0], 0x01010101, n_acc);
     n_acc = __dp4a((int)rj[1], 0x01010101, n_acc);
@@ -801,7 +810,7 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_stream16(S16Args a)
         issued = true;
       }
     };
-    s16_rowstep<NOCC, MASK_CT, ACCUM, SLAB>(a, L, pc, gid, k, sweep_lo, ctr_hi, on, n_acc, e_tot, slots, stage_next);
+    s16_rowstep<NOCC, MASK_CT, ACCUM, SLAB>(a, L, pc, 0u, gid, k, sweep_lo, ctr_hi, on, n_acc, e_tot, slots, stage_next);
     if (new_group) {
       arr_pending = true;
       arr_n = itg++;
@@ -866,9 +875,39 @@ struct PassArgs {
   unsigned long long epoch0;   // k-colour groups this rank completed before the launch
   FastDiv div_tpu;
   uint32_t H;                  // layers of one k colour
+  uint32_t dq_k, dq_r;         // (layers, row-steps) a warp moves on between its row-steps: divmod(warps, tpu)
+  // the lattice in 16-byte chunks (kernel parameters are constant-bank operands: no registers)
+  uint32_t ch_row, ch_layer, ch_pair;  // chunks per row (W), per layer, per two layers
+  int32_t ch_wrap_j, ch_wrap_k;        // (N1 - 1) rows, (N2 - 1) layers
+  uint32_t gid_off;                    // global chunk id (RNG counter) minus local chunk index
   int32_t kgroup;              // only this k colour (slabs whose halo the host exchanges), -1: both
   unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
+  uint32_t *bar;               // grid barrier: arrivals so far (monotonic, modulo 2^32)
+  uint32_t bar_base, n_blocks; // its value when the launch starts; blocks of the grid
 };
+
+// Grid barrier of the colour-pass kernel (cooperative launch: all blocks are co-resident).
+// Every block adds one arrival (release at GPU scope: the block's stores of the pass,
+// ordered before it by the block barrier, are visible to whoever sees the count), and waits
+// until the count has reached `target`.  WARP 0 polls as a whole: cooperative_groups'
+// grid.sync() polls with thread 0 alone, and that thread did not rejoin its warp afterwards
+// (measured: warp 0 of every block ran the next pass split 1 + 31 lanes, every instruction
+// twice and every shuffle through the divergent path, and the grid waited for it at the
+// next barrier).  The poll is a relaxed load: what the barrier guards is read through L2
+// only (cp.async.cg), control dependent on the polled value -- no L1 invalidation per poll.
+__device__ __forceinline__ void s16_grid_barrier(uint32_t *bar, uint32_t target) {
+  __syncthreads();
+  if (threadIdx.x < 32u) {
+    // (fence by the whole warp, the arrival predicated on lane 0: no divergent branch at all)
+    asm volatile(
+        "{ .reg .pred p; setp.eq.u32 p, %1, 0; fence.acq_rel.gpu; @p red.relaxed.gpu.global.add.u32 [%0], 1; }" ::"l"(bar),
+        "r"(threadIdx.x)
+        : "memory");
+    while ((int32_t)(ld_poll_u32<false>(bar) - target) < 0) {
+    }
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -876,6 +915,29 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 }
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// stage the rows of a row-step, addressed by CHUNK INDEX: t = this lane's chunk of the
+// target row counted from the replica base (16-byte units; a replica of an x4-interleaved
+// state is < 2^32 chunks), djm / djp / dkm / dkp = chunks to the rows below / above in j and
+// k (periodic wrap folded in by the caller).  One add and one multiply-add per row.
+template <uint32_t MASK_CT>
+__device__ __forceinline__ void s16_issue_t(const S16Args &a, const int8_t *base, uint32_t t, int32_t djm, int32_t djp,
+                                            int32_t dkm, int32_t dkp, uint32_t slots) {
+  const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
+  const int32_t dj[3] = {djm, 0, djp};
+  const int32_t dk[3] = {dkm, 0, dkp};
+  uint32_t n = 0;
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
+      if (m3 == 0 && !(dz == 0 && dy == 0)) continue;
+      cp_async16(slots + n * CMX_S16_SLOT, s16_chunk_ptr(base, t + (uint32_t)(dk[dz + 1] + dj[dy + 1])));
+      ++n;
+    }
+  }
 }
 
 template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, bool FULL>
@@ -888,8 +950,6 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, P
   unsigned char *sh_rows = sh_dyn + NTAB * 4;
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
-  namespace cgr = cooperative_groups;
-  cgr::grid_group grid = cgr::this_grid();
   const uint32_t r = blockIdx.y;
   s16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)r * NTAB);
   const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
@@ -907,16 +967,21 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, P
     L.rot_l = (L.c == 0) ? 8u : 0u;
     L.rot_r = (L.c == Wm) ? 8u : 0u;
   }
+  uint32_t bar_target = c.bar_base;
   const uint32_t rl = lane >> a.logW, rpw_log = 5u - a.logW;
   const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_S16_SLOT) + 16u * lane;
   const int32_t N2 = a.g.N2;
-  const bool halo = a.g.halo != 0;
+  const uint32_t halo = (uint32_t)a.g.halo;
   int32_t n_acc = 0;
   long long n_acc64 = 0;
   double e_tot = 0.0;
   __syncthreads();
   const uint32_t warp0 = blockIdx.x * 8u + wib, n_warps = gridDim.x * 8u;
   const uint32_t n_rs = a.tpu * c.H;  // row-steps of one colour pass
+  // Everything is addressed in 16-byte chunks from the replica base: row (k, j) starts at
+  // chunk ((k + halo) N1 + j) W, a row-step is 64 chunks (2 rpw rows x W) after the previous
+  // one of its layer, a layer pair 2 N1 W chunks.  The global chunk id (RNG counter) is the
+  // local one plus a constant.
   unsigned long long epoch = c.epoch0;
   const bool ring = SLAB && a.push;
   const bool publisher = ring && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
@@ -928,93 +993,141 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, P
     st_release_sys_u64(c.peer_sig_up + 0, epoch);  // I am their lower neighbour
   };
   if (publisher && epoch) publish();  // what the previous launches completed (idempotent)
-  bool dead = false;
-  uint32_t it = 0, pass_no = (uint32_t)(c.first_sweep & 1ull) * 0u;
-  for (uint32_t s = 0; s < c.n_sweeps && !dead; ++s) {
-    const unsigned long long sweep = c.first_sweep + s;
-    const uint32_t sweep_lo = (uint32_t)sweep;
-    for (int cz = 0; cz < 2 && !dead; ++cz) {
-      if (c.kgroup >= 0 && cz != c.kgroup) continue;
-      for (int cy = 0; cy < 2 && !dead; ++cy) {
-        const uint32_t ctr_hi = ((uint32_t)(sweep >> 32) << 16) | ((uint32_t)(cz * 2 + cy) << 9);
-        // the layer next to a ghost layer (k = 0 for cz = 0, k = N2-1 for cz = 1) comes last
-        const uint32_t rot = (ring && cz == 0) ? 1u : 0u;
-        // One box on one GPU: consecutive passes walk the layers in OPPOSITE directions.  A
-        // pass ends with the layers it touched last still in L2 (126 MB against a 134 MB
-        // lattice at 512^3), and that is where the next pass begins: most of its reads hit,
-        // only the far end comes from DRAM again -- no extra synchronisation, just the order.
-        const bool back = ((pass_no++) & 1u) != 0u;
-        struct Pos {
-          int8_t *pc;
-          uint32_t gid;
-          int32_t j, k, dkm, dkp;
-          bool on;
-        };
-        auto locate = [&](uint32_t q, Pos &p) {
-          uint32_t kk, rsu;
-          fastdivmod(q, c.div_tpu, kk, rsu);
-          if (ring) {
-            kk += rot;
-            if (kk >= c.H) kk -= c.H;
-          } else if (back) {
-            kk = c.H - 1u - kk;  // see `back`
-          }
-          p.k = 2 * (int32_t)kk + cz;
-          const uint32_t jj = (rsu << rpw_log) + rl;
-          p.on = FULL ? true : (jj < a.J);
-          p.j = 2 * (int32_t)(p.on ? jj : a.J - 1u) + cy;
-          const uint32_t row = (uint32_t)(p.k + a.g.halo) * (uint32_t)a.g.N1 + (uint32_t)p.j;
-          p.pc = L.base + ((size_t)row * (uint32_t)a.g.N0 + 16u * L.c);
-          p.gid = ((uint32_t)(p.k + a.k_offset) * (uint32_t)a.g.N1 + (uint32_t)p.j) * a.W + L.c;
-          p.dkm = (!halo && p.k == 0) ? a.wrap_k : -a.layer;
-          p.dkp = (!halo && p.k == N2 - 1) ? -a.wrap_k : a.layer;
-        };
-        auto wait_neighbours = [&](int32_t k) {
-          if (!ring || !epoch || !(k == 0 || k == N2 - 1)) return;  // (warp-uniform: a row-step lies in one layer)
-          if (lane == 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_sys_u64(c.my_sig + 0) < epoch || ld_acquire_sys_u64(c.my_sig + 1) < epoch) {
-              if (clock64() - t0 > 20000000000ll) {  // ~10 s: a neighbour is gone
-                *reinterpret_cast<volatile unsigned long long *>(a.fail) = 1ull;
-                break;
-              }
-              __nanosleep(100);
-            }
-          }
-          __syncwarp();
-        };
-        Pos cur, nxt;
-        uint32_t q = warp0;
-        if (q < n_rs) {
-          locate(q, nxt);
-          wait_neighbours(nxt.k);
-          s16_issue<MASK_CT>(a, nxt.pc, nxt.j, nxt.dkm, nxt.dkp, slots);
-        }
-        for (; q < n_rs; q += n_warps) {
-          cur = nxt;
-          const bool more = q + n_warps < n_rs;
-          if (more) locate(q + n_warps, nxt);
-          cp_async_wait_all();
-          auto stage_next = [&]() {
-            if (more) {
-              wait_neighbours(nxt.k);
-              s16_issue<MASK_CT>(a, nxt.pc, nxt.j, nxt.dkm, nxt.dkp, slots);
-            }
-          };
-          s16_rowstep<NOCC, MASK_CT, ACCUM, SLAB>(a, L, cur.pc, cur.gid, cur.k, sweep_lo, ctr_hi, cur.on, n_acc, e_tot, slots,
-                                                  stage_next);
-          if ((++it & 0xFFFFFu) == 0) {
-            n_acc64 += n_acc;
-            n_acc = 0;
-          }
-        }
-        grid.sync();  // every store of the pass, the ones into the neighbours' ghost layers included
+  // this warp's first row-step of a pass: (layer of the colour, row-step of the layer)
+  uint32_t kk0, rs0;
+  fastdivmod(warp0, c.div_tpu, kk0, rs0);
+  // the row-step in which this lane meets the periodic seam in j: row 0 (row colour 0, the
+  // row below wraps) / row N1-1 (row colour 1, the row above wraps); none: never
+  const uint32_t jl = a.J - 1u;
+  const uint32_t rs_edge0 = (rl == 0u) ? 0u : 0xFFFFFFFFu;
+  const uint32_t rs_edge1 = ((jl & ((1u << rpw_log) - 1u)) == rl) ? (jl >> rpw_log) : 0xFFFFFFFFu;
+  const int8_t *const base = L.base;
+
+  // One colour pass (cy, cz compile-time: the seam tests and the constant row offsets fold)
+  auto pass = [&](auto cy_tag, auto cz_tag, uint32_t sweep_lo, uint32_t sweep_hi) {
+    constexpr int CY = decltype(cy_tag)::value, CZ = decltype(cz_tag)::value;
+    const uint32_t ctr_hi = (sweep_hi << 16) | ((uint32_t)(CZ * 2 + CY) << 9);
+    // the layer next to a ghost layer (k = 0 for cz = 0, k = N2-1 for cz = 1) comes last
+    const uint32_t rot = (ring && CZ == 0) ? 1u : 0u;
+    // One box on one GPU: consecutive passes walk the layers in OPPOSITE directions (row
+    // colour 1 backwards).  A pass ends with the layers it touched last still in L2 (126 MB
+    // against a 134 MB lattice at 512^3), and that is where the next pass begins: most of
+    // its reads hit, only the far end comes from DRAM again -- no extra synchronisation,
+    // just the order.
+    const bool back = !ring && CY != 0;
+    // chunk of this lane in row-step 0 of layer pair 0 of the pass's colour
+    const uint32_t t00 = (((uint32_t)CZ + halo) * (uint32_t)a.g.N1 + 2u * rl + (uint32_t)CY) * c.ch_row + L.c;
+    const uint32_t rs_edge = CY ? rs_edge1 : rs_edge0;
+    const uint32_t kk_edge = CZ ? c.H - 1u : 0u;
+    // row offsets towards the seam side, inside the box / across the seam (slabs do not
+    // wrap in k: ghost layers)
+    const int32_t dj_in = CY ? (int32_t)c.ch_row : -(int32_t)c.ch_row, dj_wrap = CY ? -c.ch_wrap_j : c.ch_wrap_j;
+    const int32_t dk_in = CZ ? (int32_t)c.ch_layer : -(int32_t)c.ch_layer;
+    const int32_t dk_wrap = halo ? dk_in : (CZ ? -c.ch_wrap_k : c.ch_wrap_k);
+    struct Pos {
+      uint32_t t;   // this lane's chunk of its target row
+      uint32_t kk;  // layer of the colour (after rotation / reversal): k = 2 kk + cz
+      bool on;
+    };
+    // position of row-step (kq, rs) and the offsets of its seam-side rows
+    auto locate = [&](uint32_t kq, uint32_t rs, Pos &p, int32_t &dj_e, int32_t &dk_e) {
+      uint32_t kk = kq;
+      if (ring) {
+        kk += rot;
+        if (kk >= c.H) kk -= c.H;
+      } else if (back) {
+        kk = c.H - 1u - kk;
       }
+      p.kk = kk;
+      p.on = true;
+      uint32_t tr = rs * 64u;
+      if (!FULL) {
+        const uint32_t jj = (rs << rpw_log) + rl;
+        if (jj >= a.J) {  // partial last row-step of a layer: redo the last row, unstored
+          p.on = false;
+          tr = 2u * (jl - rl) * c.ch_row;
+        }
+      }
+      p.t = kk * c.ch_pair + tr + t00;
+      bool edge = (rs == rs_edge);
+      if (!FULL && !p.on) edge = CY ? true : (jl == 0u);  // (the redone row is the last one of its colour)
+      dj_e = edge ? dj_wrap : dj_in;
+      dk_e = (kk == kk_edge) ? dk_wrap : dk_in;
+    };
+    auto issue = [&](const Pos &p, int32_t dj_e, int32_t dk_e) {
+      // (cy = 0: the row below may wrap, the row above never does; cy = 1 the other way)
+      const int32_t djm = CY ? -(int32_t)c.ch_row : dj_e, djp = CY ? dj_e : (int32_t)c.ch_row;
+      const int32_t dkm = CZ ? -(int32_t)c.ch_layer : dk_e, dkp = CZ ? dk_e : (int32_t)c.ch_layer;
+      s16_issue_t<MASK_CT>(a, base, p.t, djm, djp, dkm, dkp, slots);
+    };
+    auto wait_neighbours = [&](uint32_t kk) {
+      if (!ring || !epoch || kk != kk_edge) return;  // (warp-uniform: a row-step lies in one layer)
+      if (lane == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(c.my_sig + 0) < epoch || ld_acquire_sys_u64(c.my_sig + 1) < epoch) {
+          if (clock64() - t0 > 20000000000ll) {  // ~10 s: a neighbour is gone
+            *reinterpret_cast<volatile unsigned long long *>(a.fail) = 1ull;
+            break;
+          }
+          __nanosleep(100);
+        }
+      }
+      __syncwarp();
+    };
+    Pos cur, nxt;
+    uint32_t q = warp0, kq = kk0, rs = rs0;
+    if (q < n_rs) {
+      int32_t dj_e, dk_e;
+      locate(kq, rs, nxt, dj_e, dk_e);
+      wait_neighbours(nxt.kk);
+      issue(nxt, dj_e, dk_e);
+    }
+    for (; q < n_rs; q += n_warps) {
+      cur = nxt;
+      const bool more = q + n_warps < n_rs;
+      // the warp's next row-step: n_warps further = (dq_k layers, dq_r row-steps) with carry
+      rs += c.dq_r;
+      kq += c.dq_k;
+      if (rs >= a.tpu) {
+        rs -= a.tpu;
+        kq += 1u;
+      }
+      int32_t dj_e = 0, dk_e = 0;
+      if (more) locate(kq, rs, nxt, dj_e, dk_e);
+      cp_async_wait_all();
+      auto stage_next = [&]() {
+        if (more) {
+          wait_neighbours(nxt.kk);
+          issue(nxt, dj_e, dk_e);
+        }
+      };
+      s16_rowstep<NOCC, MASK_CT, ACCUM, SLAB>(a, L, base, cur.t, cur.t + c.gid_off, 2 * (int32_t)cur.kk + CZ, sweep_lo,
+                                              ctr_hi, FULL ? true : cur.on, n_acc, e_tot, slots, stage_next);
+    }
+    n_acc64 += n_acc;  // (a pass adds at most 16 per row-step to the 32-bit count)
+    n_acc = 0;
+    // every store of the pass, the ones into the neighbours' ghost layers included
+    bar_target += c.n_blocks;
+    s16_grid_barrier(c.bar, bar_target);
+  };
+  using T0 = std::integral_constant<int, 0>;
+  using T1 = std::integral_constant<int, 1>;
+  for (uint32_t s = 0; s < c.n_sweeps; ++s) {
+    const unsigned long long sweep = c.first_sweep + s;
+    const uint32_t sweep_lo = (uint32_t)sweep, sweep_hi = (uint32_t)(sweep >> 32);
+    if (c.kgroup != 1) {
+      pass(T0{}, T0{}, sweep_lo, sweep_hi);
+      pass(T1{}, T0{}, sweep_lo, sweep_hi);
+      ++epoch;
+      if (publisher) publish();
+    }
+    if (c.kgroup != 0) {
+      pass(T0{}, T1{}, sweep_lo, sweep_hi);
+      pass(T1{}, T1{}, sweep_lo, sweep_hi);
       ++epoch;
       if (publisher) publish();
     }
   }
-  n_acc64 += n_acc;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     n_acc64 += __shfl_down_sync(0xffffffffu, n_acc64, o);
