@@ -258,12 +258,14 @@ def bench_replicas(args, torch, _capi, rank, world, local_rank):
         torch.cuda.synchronize()
 
     if args.workload == "c2":
-        N, S = 128, SWEEPS_PER_STEP
+        N, S = 128, 10 * SWEEPS_PER_STEP   # a sample every 100 passes: the (mu, T) grid is a long run per point
         conds = [{"temperature": float(T), "param_chem_pot": [float(mu), 0.0]}
                  for mu in np.linspace(-1, 1, 8) for T in np.arange(400.0, 1801.0, 200.0)]
         run = ReplicaRunner(tb("fcc_default"), (N, N, N), sysd, sysd["eci_sparse"], conds, rank, world,
                             n_samples=K_ + 1, seed_init=7)
-        run.state.sgc_sweep(W_ * S, seed=1, counters=False)
+        run.state.sgc_sweep(W_ * SWEEPS_PER_STEP, seed=1, counters=False)
+        run.sampler.run(1, 1, seed=1 + rank, first_sweep=W_ * SWEEPS_PER_STEP)
+        run.reduce(dist, device)            # warm-up of the collective at its real size
         run.sampler.reset()
         barrier()
         clocks = ClockSampler(local_rank)
@@ -289,7 +291,7 @@ def bench_replicas(args, torch, _capi, rank, world, local_rank):
         info = run.state.sweep_info()
         metric = "attempted MC steps/sec (FCC ternary SGC, 64 replicas x 128^3)"
         workload = ("FCC A-B-Va semi-grand canonical, 128^3 primitive supercell x 64 replicas (8 param_chem_pot x 8 T), "
-                    "sampled every 10 passes, statistics all-reduced")
+                    "sampled every 100 passes, statistics all-reduced")
         extra = {"heat_capacity_first_last": [res[0]["heat_capacity"], res[-1]["heat_capacity"]],
                  "accept_rate_local_min_max": [min(c.n_accept / c.n_attempt for c in cnt),
                                                max(c.n_accept / c.n_attempt for c in cnt)],
@@ -314,8 +316,8 @@ def bench_replicas(args, torch, _capi, rank, world, local_rank):
 
         run = KmcEnsembleRunner(tbs["fcc_default"], N, sysd["eci_dense"], factory, 1200.0, R_, rank, world, seed0=1,
                                 occ_of=lambda i: base[i % 64])
-        S = 20
-        run.run(W_ * S)
+        S = 100
+        run.reduce(run.run(W_ * S), dist, device)   # warm-up, the collective at its real size included
         barrier()
         clocks = ClockSampler(local_rank)
         clocks.start()

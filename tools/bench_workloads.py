@@ -83,7 +83,7 @@ def c2():
     steps = S * R * N ** 3
     rate = steps / (ms * 1e-3)
     emit(workload="c2: FCC A-B-Va SGC, 128^3 x 64 replicas (8 mu x 8 T), shipped sparse ECI", metric="attempted MC steps/s",
-         value=rate, ms=ms, sweeps=S, launches=S * 4, kernel="k_sweep_row16",
+         value=rate, ms=ms, sweeps=S, launches=1, kernel="k_sweep_pass16",
          roofline={"bound": "hbm", "achieved": 2.0 * rate / 1e9, "peak": HBM, "unit": "GB/s", "frac": 2.0 * rate / 1e9 / HBM},
          accept_min=min(c.n_accept / c.n_attempt for c in cnt), accept_max=max(c.n_accept / c.n_attempt for c in cnt))
     # the same run sampled every pass (device-side samplers, one sync at the end)
@@ -95,6 +95,33 @@ def c2():
          sampling_overhead=ms2 / ms - 1.0, heat_capacity_replica0=sm.analysis(0)["heat_capacity"])
     sm.close()
     st.close()
+    t.close()
+
+
+def c3full():
+    """BASELINE configs[2] with ALL nine functions of the FCC basis selected (constant, points,
+    1NN and 2NN pairs -- the 19-site neighbourhood SURVEY section 8d quotes; coefficient values
+    of the golden fixture `eci_full`): two neighbour classes, so outside the pair-LUT fast path
+    -- the generic folded-term evaluator runs (one site per thread)."""
+    sysd = SYS["fcc"]
+    t = tables("fcc_default")
+    for N in (256, 512):
+        st = _capi.State(t, (N, N, N), 1)
+        st.set_eci(sysd["eci_full"]["index"], sysd["eci_full"]["value"])
+        st.set_conditions(800.0, semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], (0.0, 0.0), 3))
+        st.randomize(7)
+        st.sgc_sweep(2, seed=1)
+        S = 5
+        ms, cnt = timed(st, lambda: st.sgc_sweep(S, seed=1, first_sweep=2))
+        rate = S * N ** 3 / (ms * 1e-3)
+        info = st.sweep_info()
+        emit(workload=f"c3 all functions: FCC A-B-Va SGC, {N}^3, points + 1NN + 2NN pairs (19-site neighbourhood)",
+             metric="attempted MC steps/s", value=rate, ms=ms, sweeps=S, evaluator=info.get("evaluator"),
+             bytes_per_step_l2=info.get("bytes_per_step"), flops_per_step=info.get("flops_per_step"),
+             roofline={"bound": "hbm", "achieved": 2.0 * rate / 1e9, "peak": HBM, "unit": "GB/s", "frac": 2.0 * rate / 1e9 / HBM,
+                       "note": "2 B per step at HBM; the evaluator is gather / FP64-issue bound (20 B per step through L1/L2)"},
+             accept_rate=cnt[0].n_accept / cnt[0].n_attempt)
+        st.close()
     t.close()
 
 
@@ -306,11 +333,11 @@ def c5():
 
 
 def main():
-    which = sys.argv[1:] or ["c1", "c2", "sample", "c4", "c4cpu", "c5"]
+    which = sys.argv[1:] or ["c1", "c2", "c3full", "sample", "c4", "c4cpu", "c5"]
     if not torch.cuda.is_available():
         raise SystemExit("bench_workloads.py: no CUDA device")
     for w in which:
-        {"c1": c1, "c2": c2, "sample": sample, "c4": c4, "c4cpu": c4_cpu, "c5": c5}[w]()
+        {"c1": c1, "c2": c2, "c3full": c3full, "sample": sample, "c4": c4, "c4cpu": c4_cpu, "c5": c5}[w]()
 
 
 if __name__ == "__main__":
