@@ -500,8 +500,8 @@ def main():
     if world == 1 and args.box == N_BOX and not args.layers and prof.exists():
         import csv
         m = {}
-        for row in csv.reader(prof.open()):
-            if len(row) == 5 and row[0] == "1":
+        for row in csv.reader(prof.open()):   # (the last launch of the capture wins)
+            if len(row) == 5 and row[0].isdigit():
                 m[row[2]] = (row[3], row[4])
         try:
             unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}

@@ -137,6 +137,13 @@ struct SweepPlan {
   uint2 *d_gt_pk = nullptr;
   int32_t pk_terms_max = 0, pk_act_max = 0;  // max over p of terms / active neighbors
   int generic_coop_capacity = -1;            // co-resident blocks of the cooperative generic kernel
+  // pair-sum evaluator (k_sweep_pairsum): every folded term has at most one factor (point
+  // and pair functions, any number of shells and sublattices), so dE is a sum of
+  // per-neighbor tables V[slot][oi][of][neighbor occupant] (slots = act_n order) plus the
+  // factor-free part P0[p][oi][of]
+  bool pair_sum = false;
+  double *d_ps_V = nullptr, *d_ps_P0 = nullptr;
+  int32_t ps_range[3] = {0, 0, 0};  // max |offset| per axis over the active neighbors
   // pair LUT: one sublattice, <= 3 occupants, offsets in {-1,0,1}^3,
   // one class of symmetry-equivalent neighbors
   int32_t nocc = 0;
@@ -250,6 +257,7 @@ int cmx_scratch(cmx_state *s, size_t bytes);
 int cmx_plan_sweep(cmx_state *s);
 int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps);
 bool cmx_use_warp_generic(const cmx_state *s);  // wide orbit sets: one site per warp
+bool cmx_use_pair_sum(const cmx_state *s);      // point + pair bases outside the pair-LUT path
 void cmx_canonical_free(cmx_state *s);
 int cmx_canonical_enqueue(cmx_state *s, int64_t n_sweeps, uint64_t seed, int64_t first_sweep, bool reset);
 int cmx_canonical_counters(cmx_state *s, cmx_counters *counters);

@@ -41,6 +41,8 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_gt_pk);
   cudaFree(p.d_act_beg);
   cudaFree(p.d_act_n);
+  cudaFree(p.d_ps_V);
+  cudaFree(p.d_ps_P0);
   cudaFree(p.d_pair_dE);
   cudaFree(p.d_tab);
   cudaFree(p.d_thr_lo);
@@ -633,6 +635,169 @@ __global__ void __launch_bounds__(256) k_sweep_generic(GenericSweepArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// pair-sum sweep kernel: one site per thread, dE from per-neighbor tables
+// ---------------------------------------------------------------------------
+// Bases of point and pair functions only (every folded term has at most one factor):
+//   dE(oi -> of) = P0[oi][of] + sum over the active neighbors s of V[s][oi][of][occupant_s]
+// with V folded from the same term lists the generic evaluator walks (cmx_plan_sweep).  The
+// tables of the colour's point position sit in shared memory; a site whose neighborhood does
+// not cross a periodic seam (all but a thin shell of the box) reaches its neighbors by adding
+// precomputed byte offsets.  Same random bits and the same decision rule as k_sweep_generic;
+// dE differs from it in the last bits only (summation order), checked per proposal by
+// cmx_sweep_debug_delta_e.  This is the evaluator of the reference's dense FCC ECI (points +
+// 1NN + 2NN pairs, the 19-site neighbourhood of SURVEY 8d), of multi-sublattice pair models
+// and of pair models on boxes the pair-LUT kernels do not take.
+struct PairSumArgs {
+  const double *V;    // [act slot][oi][of][on]
+  const double *P0;   // [point position][oi][of]
+  const int32_t *act_beg, *act_n;
+  int32_t R[3];       // interaction range per axis
+  int32_t fast;       // byte offsets of a replica fit 32 bits
+};
+
+__device__ __forceinline__ double pairsum_delta(const Geom &g, const int8_t *occ, const double *shV, const int4 *shN,
+                                                const int32_t *shD, int n_act, int mo, const int32_t (&R)[3], int fast,
+                                                double p0, int i, int j, int k, int64_t off, int oi, int of) {
+  const int mo3 = mo * mo * mo;
+  const double *Vrow = shV + (oi * mo + of) * mo;
+  double dE = p0;
+  const int w = g.xq_log ? (i & ((1 << g.xq_log) - 1)) : i;
+  const int wmax = g.xq_log ? (1 << g.xq_log) : g.N0;
+  const bool inside = fast && w >= R[0] && w < wmax - R[0] && j >= R[1] && j < g.N1 - R[1] &&
+                      (g.halo || (k >= R[2] && k < g.N2 - R[2]));
+  if (inside) {
+#pragma unroll 6
+    for (int s = 0; s < n_act; ++s) dE += Vrow[s * mo3 + cmx_dec(occ[off + shD[s]])];
+  } else {
+    for (int s = 0; s < n_act; ++s) {
+      const int4 o = shN[s];
+      int ii = i + o.x, jj = j + o.y, kk = k + o.z;
+      cmx_wrap_cell(g, ii, jj, kk);
+      dE += Vrow[s * mo3 + cmx_dec(occ[cmx_site_offset(g, o.w, ii, jj, kk)])];
+    }
+  }
+  return dE;
+}
+// the tables of point position p into shared memory: [V][neighbor offsets][byte offsets]
+__device__ __forceinline__ void pairsum_stage(const DevTables &T, const Geom &g, const PairSumArgs &ps, int p,
+                                              unsigned char *smem, double *&shV, int4 *&shN, int32_t *&shD, int &n_act) {
+  const int mo3 = T.max_occ * T.max_occ * T.max_occ;
+  const int ab = ps.act_beg[p];
+  n_act = ps.act_beg[p + 1] - ab;
+  const int b = T.nlist_sublat[p];
+  shN = reinterpret_cast<int4 *>(smem);  // 16-byte entries first: alignment
+  shV = reinterpret_cast<double *>(shN + n_act);
+  shD = reinterpret_cast<int32_t *>(shV + (size_t)n_act * mo3);
+  for (int q = threadIdx.x; q < n_act * mo3; q += blockDim.x) shV[q] = ps.V[(size_t)ab * mo3 + q];
+  for (int q = threadIdx.x; q < n_act; q += blockDim.x) {
+    const int4 o = T.nbr[ps.act_n[ab + q]];
+    shN[q] = o;
+    shD[q] = (int32_t)((int64_t)(o.w - b) * g.sub_stride + (int64_t)o.z * g.layer + (int64_t)o.y * g.N0 +
+                       (int64_t)o.x * (g.xq_log ? 4 : 1));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_sweep_pairsum(GenericSweepArgs a, PairSumArgs ps) {
+  extern __shared__ __align__(16) unsigned char sh_ps[];
+  __shared__ long long sh_acc[8];
+  __shared__ double sh_sum[8];
+  const int r = blockIdx.y;
+  const Geom &g = a.g;
+  const DevTables &T = a.T;
+  int8_t *occ = a.occ + (size_t)r * g.rep_stride;
+  const int b = T.nlist_sublat[a.p];
+  const int nocc = T.n_occ[b];
+  const int mo = T.max_occ;
+  const double beta = a.beta[r];
+  const double *exch = a.exch + (size_t)r * a.exch_stride + (size_t)b * mo * mo;
+  double *shV;
+  int4 *shN;
+  int32_t *shD;
+  int n_act;
+  pairsum_stage(T, g, ps, a.p, sh_ps, shV, shN, shD, n_act);
+  const double *P0 = ps.P0 + (size_t)a.p * mo * mo;
+  long long n_acc = 0;
+  double e_sum = 0.0;
+  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < a.items; item += gridDim.x * blockDim.x) {
+    uint32_t row, ii, kk, jj;
+    fastdivmod(item, a.div0, row, ii);
+    fastdivmod(row, a.div1, kk, jj);
+    const int i = (int)ii * a.S0 + a.c0, j = (int)jj * a.S1 + a.c1, k = (int)kk * a.S2 + a.c2;
+    const int64_t off = cmx_site_offset(g, b, i, j, k);
+    const int oi = cmx_dec(occ[off]);
+    int alt;
+    uint32_t u_hi, u_lo;
+    Rng16Site rs;
+    uint32_t gid = 0;
+    if (a.rng16) {
+      rs = cmx_rng16_site(g, i);
+      gid = (uint32_t)(((uint32_t)(k + a.k_offset) * g.N1 + j) * (g.N0 >> 4) + rs.chunk);
+      const Philox ph = philox_sweep(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi, a.k0, a.k1);
+      const uint32_t R = ph.c[rs.word];
+      const uint32_t field = rs.half ? (R >> 16) : (R & 0xFFFFu);
+      alt = (nocc == 3) ? (int)(field >> 15) : 0;
+      u_hi = field & 0x7FFFu;
+      u_lo = 0;
+    } else {
+      const uint32_t gid_lo = (uint32_t)(((uint64_t)(k + a.k_offset) * g.N1 + j) * g.N0 + i);
+      const Philox ph = philox4x32_10(gid_lo, (uint32_t)r | ((uint32_t)b << 24), a.sweep_lo, a.ctr_hi, a.k0, a.k1);
+      alt = (int)__umulhi(ph.c[2], (uint32_t)(nocc - 1));
+      u_hi = ph.c[1] & 0x1FFFFFu;
+      u_lo = ph.c[0];
+    }
+    int of = oi + 1 + alt;
+    if (of >= nocc) of -= nocc;
+    double dE = pairsum_delta(g, occ, shV, shN, shD, n_act, mo, ps.R, ps.fast, P0[oi * mo + of], i, j, k, off, oi, of);
+    dE -= exch[oi * mo + of];
+    bool accept = dE < 0.0;
+    if (!accept) {
+      if (a.rng16) {
+        // the pair16 kernel's integer test, u47 < ceil(exp(-dE beta) 2^47); the low 32 bits
+        // only decide when the high 15 tie
+        const unsigned long long thr = (unsigned long long)ceil(exp(-dE * beta) * 140737488355328.0);
+        const uint32_t t_hi = (uint32_t)(thr >> 32);
+        accept = u_hi < t_hi;
+        if (u_hi == t_hi) {
+          const Philox lo = philox_sweep(gid, (uint32_t)r, a.sweep_lo, a.ctr_hi | ((rs.q < 4) ? 1u : 2u), a.k0, a.k1);
+          accept = lo.c[rs.q & 3] < (uint32_t)thr;
+        }
+      } else {
+        const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
+        accept = (double)u * (1.0 / 9007199254740992.0) < exp(-dE * beta);
+      }
+    }
+    if (accept) {
+      occ[off] = (int8_t)cmx_enc(g, of);
+      ++n_acc;
+      if (a.accum) e_sum += dE;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_acc += __shfl_down_sync(0xffffffffu, n_acc, o);
+    e_sum += __shfl_down_sync(0xffffffffu, e_sum, o);
+  }
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    sh_acc[wid] = n_acc;
+    sh_sum[wid] = e_sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long A = 0;
+    double E = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      A += sh_acc[w];
+      E += sh_sum[w];
+    }
+    size_t slot = (size_t)r * gridDim.x + blockIdx.x;
+    a.part_acc[slot] += A;
+    a.part_dE[slot] += E;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // generic sweep kernel, warp-cooperative: one site per WARP (cmx_warp_site_delta).
 // Same random bits and the same decision rule as k_sweep_generic; dE differs from it
 // in the last bits only (summation order).  Wide orbit sets (ZrO: ~700 merged terms,
@@ -898,6 +1063,35 @@ int cmx_plan_sweep(cmx_state *s) {
       }
     }
     if (packable && (rc = to_device(pk, &P.d_gt_pk))) return rc;
+    // pair-sum tables: V[slot][oi][of][on] = sum over the one-factor terms (slot, f) of
+    // w[oi][of] phi_f(on), P0[p][oi][of] = the factor-free terms; both in term order
+    bool single = mo <= 4 && !P.mut_points.empty();
+    for (int tt = 0; tt + 1 < (int)gt_fbeg.size() && single; ++tt) single = gt_fbeg[tt + 1] - gt_fbeg[tt] <= 1;
+    const int mo3 = mo * mo * mo;
+    for (int p = 0; p < np && single; ++p)
+      single = (size_t)(act_beg[p + 1] - act_beg[p]) * (mo3 * 8 + 20) <= 44 * 1024;
+    if (single) {
+      std::vector<double> V((size_t)act_n.size() * mo3, 0.0), P0((size_t)np * mo * mo, 0.0);
+      for (int p = 0; p < np; ++p)
+        for (int tt = gt_beg[p]; tt < gt_beg[p + 1]; ++tt) {
+          const double *w = &gt_w[(size_t)tt * mo * mo];
+          if (gt_fbeg[tt + 1] == gt_fbeg[tt]) {
+            for (int x = 0; x < mo * mo; ++x) P0[(size_t)p * mo * mo + x] += w[x];
+            continue;
+          }
+          const int f = gt_fbeg[tt], n = gt_n[f];
+          const int slot = act_beg[p] + gt_vi[f] / T.n_func;
+          const double *ph = &t->phi[((size_t)t->nbr[4 * n + 3] * T.n_func + gt_f[f]) * mo];
+          for (int x = 0; x < mo * mo; ++x)
+            for (int on = 0; on < mo; ++on) V[((size_t)slot * mo * mo + x) * mo + on] += w[x] * ph[on];
+        }
+      for (int a = 0; a < 3; ++a) P.ps_range[a] = 0;
+      for (int n : act_n)
+        for (int a = 0; a < 3; ++a) P.ps_range[a] = std::max(P.ps_range[a], std::abs(t->nbr[4 * n + a]));
+      if ((rc = to_device(V, &P.d_ps_V))) return rc;
+      if ((rc = to_device(P0, &P.d_ps_P0))) return rc;
+      P.pair_sum = true;
+    }
   }
 
   // ---- colouring: stride > interaction range along each axis.  Sites on
@@ -1105,6 +1299,13 @@ bool cmx_use_warp_generic(const cmx_state *s) {
 
 static bool use_pair(const cmx_state *s) {
   return s->plan.pair_lut && !(s->sweep_flags & CMX_SWEEP_FORCE_GENERIC);
+}
+// point + pair bases the pair-LUT path does not take (several neighbor classes, several
+// sublattices, box shapes): per-neighbor tables, one site per thread.  Either generic flag
+// selects the term-list evaluators instead (the cross-check of this one).
+bool cmx_use_pair_sum(const cmx_state *s) {
+  return s->plan.pair_sum && !use_pair(s) &&
+         !(s->sweep_flags & (CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_THREAD_GENERIC));
 }
 static bool use_stream(const cmx_state *s) { return use_pair(s) && s->plan.stream; }
 
@@ -1723,8 +1924,17 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   a.rng16 = P.rng16 ? 1 : 0;
   a.accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) ? 1 : 0;
   dim3 grid(P.part_blocks, s->n_replicas);
-  const bool warp = cmx_use_warp_generic(s) && !use_pair(s);
+  const bool pair_sum = cmx_use_pair_sum(s);
+  const bool warp = cmx_use_warp_generic(s) && !use_pair(s) && !pair_sum;
   const size_t stage_bytes = (size_t)(P.stage_max + 1) * 8 * sizeof(double);
+  PairSumArgs ps;
+  ps.V = P.d_ps_V;
+  ps.P0 = P.d_ps_P0;
+  ps.act_beg = P.d_act_beg;
+  ps.act_n = P.d_act_n;
+  for (int q = 0; q < 3; ++q) ps.R[q] = P.ps_range[q];
+  ps.fast = (g.rep_stride < (int64_t)0x7FFFFFFFll) ? 1 : 0;
+  const size_t ps_bytes = (size_t)P.pk_act_max * (T.max_occ * T.max_occ * T.max_occ * 8 + 20) + 16;
   GenTerms G{P.d_gt_beg, P.d_gt_fbeg, P.d_gt_vi, P.d_act_beg, P.d_act_n, P.d_gt_w, P.d_gt_pk};
   const size_t table_bytes = (cmx_gen_shared_bytes(P.pk_terms_max, P.pk_act_max, T.max_occ) + 15) & ~(size_t)15;
   const bool staged = warp && P.d_gt_pk && table_bytes + stage_bytes <= 160 * 1024;
@@ -1784,7 +1994,9 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
           a.ctr_hi = C.ctr_base | (a.rng16 ? ((col & 0xffu) << 8) : (col & 0xffffu));
           C.col_begin = (int)col;
           C.col_end = (int)col + 1;
-          if (staged)
+          if (pair_sum)
+            k_sweep_pairsum<<<grid, 256, ps_bytes, s->stream>>>(a, ps);
+          else if (staged)
             k_sweep_generic_warp<true, false><<<grid, 256, table_bytes + stage_bytes, s->stream>>>(a, G, P.stage_max, (int)table_bytes, C);
           else if (warp)
             k_sweep_generic_warp<false, false><<<grid, 256, stage_bytes, s->stream>>>(a, G, P.stage_max, 0, C);
@@ -1824,7 +2036,8 @@ static int sweep_prepare(cmx_state *s, const char *who) {
       items = (n_rows + RB - 1) / RB * 256;
     } else {
       items = (uint32_t)(s->g.N0 / P.S[0]) * (s->g.N1 / P.S[1]) * (s->g.N2 / P.S[2]);
-      if (cmx_use_warp_generic(s)) items = (uint32_t)std::min<uint64_t>((uint64_t)items * 32u, 0xFFFFFF00u);  // a warp per site
+      if (cmx_use_warp_generic(s) && !cmx_use_pair_sum(s))
+        items = (uint32_t)std::min<uint64_t>((uint64_t)items * 32u, 0xFFFFFF00u);  // a warp per site
     }
     blocks = sweep_blocks_per_replica(items, s->n_replicas);
   }
@@ -1978,7 +2191,7 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
     cmx_set_error("cmx_sweep_info: no sweep plan");
     return CMX_ERR_STATE;
   }
-  const char *nm = use_pair(s) ? "pair_lut" : "generic";
+  const char *nm = use_pair(s) ? "pair_lut" : cmx_use_pair_sum(s) ? "pair_sum" : "generic";
   if (name && name_cap) {
     std::strncpy(name, nm, name_cap - 1);
     name[name_cap - 1] = 0;
@@ -2032,6 +2245,9 @@ struct DebugDeArgs {
   // generic
   const int32_t *gt_beg, *gt_fbeg, *gt_f, *gt_n;
   const double *gt_w, *exch;
+  // pair sum
+  const double *ps_V, *ps_P0;
+  const int32_t *act_beg, *act_n;
 };
 __device__ __forceinline__ bool debug_site(const DebugDeArgs &a, long long q, int &b, int &i, int &j, int &k) {
   const Geom &g = a.g;
@@ -2045,7 +2261,7 @@ __device__ __forceinline__ bool debug_site(const DebugDeArgs &a, long long q, in
   k = (int)(rest / g.N1);
   return true;
 }
-// mode 0: pair-LUT table entry; 1: folded term lists, one thread per proposal
+// mode 0: pair-LUT table entry; 1: folded term lists, one thread per proposal; 2: pair-sum tables
 __global__ void k_sweep_debug_de(DebugDeArgs a, int mode) {
   const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= a.n) return;
@@ -2074,6 +2290,16 @@ __global__ void k_sweep_debug_de(DebugDeArgs a, int mode) {
   for (int pp = 0; pp < T.n_nlist_sublat; ++pp)
     if (T.nlist_sublat[pp] == b) p = pp;
   double dE = 0.0;
+  if (mode == 2) {  // per-neighbor tables of the pair-sum evaluator, in its summation order
+    const int ab = a.act_beg[p], ae = a.act_beg[p + 1];
+    dE = a.ps_P0[((size_t)p * mo + oi) * mo + of];
+    for (int s = ab; s < ae; ++s) {
+      const int64_t no = cmx_nbr_offset(T, g, a.act_n[s], i, j, k, nullptr);
+      dE += a.ps_V[(((size_t)s * mo + oi) * mo + of) * mo + cmx_dec(a.occ[no])];
+    }
+    a.out[q] = dE - a.exch[((size_t)b * mo + oi) * mo + of];
+    return;
+  }
   for (int t = a.gt_beg[p]; t < a.gt_beg[p + 1]; ++t) {
     double v = a.gt_w[((size_t)t * mo + oi) * mo + of];
     for (int f = a.gt_fbeg[t]; f < a.gt_fbeg[t + 1]; ++f) {
@@ -2147,7 +2373,13 @@ extern "C" int cmx_sweep_debug_delta_e(cmx_state *s, int32_t replica, int64_t n,
   a.gt_w = P.d_gt_w;
   const size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
   a.exch = s->d_exch + (size_t)replica * exs;
-  if (use_pair(s)) {
+  a.ps_V = P.d_ps_V;
+  a.ps_P0 = P.d_ps_P0;
+  a.act_beg = P.d_act_beg;
+  a.act_n = P.d_act_n;
+  if (cmx_use_pair_sum(s)) {
+    k_sweep_debug_de<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(a, 2);
+  } else if (use_pair(s)) {
     if (P.z > 16) return invalid("cmx_sweep_debug_delta_e: neighbor class larger than 16");
     if ((rc = pair_tables(s))) return rc;
     k_sweep_debug_de<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(a, 0);

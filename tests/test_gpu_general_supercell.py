@@ -128,7 +128,7 @@ def test_sweep_on_skewed_box_keeps_the_energy_book(dev_tables, systems, case_sys
     st.randomize(9)
     st.set_sweep_flags(_capi.CMX_SWEEP_DE_SUM)
     info = st.sweep_info()
-    assert info["evaluator"] == "generic"
+    assert info["evaluator"] == ("generic" if case_sys == "zro" else "pair_sum")   # (no pair LUT on skewed boxes)
     S = info["colour_strides"]
     assert st.skew[0] % S[1] == 0 and st.skew[1] % S[2] == 0 and st.skew[2] % S[2] == 0
 

@@ -183,8 +183,8 @@ def _sweep_state(dev_tables, systems, case_sys, eci_key, N, T, mu, n_replicas=1,
 
 @pytest.mark.parametrize("case_sys,eci_key,N,expect", [
     ("fcc", "eci_sparse", (16, 16, 16), "pair_lut"),
-    ("fcc", "eci_full", (16, 16, 16), "generic"),
-    ("fcc", "eci_sparse", (12, 12, 12), "generic"),   # N0 % 16 != 0 -> generic evaluator
+    ("fcc", "eci_full", (16, 16, 16), "pair_sum"),    # two neighbor classes: per-neighbor tables
+    ("fcc", "eci_sparse", (12, 12, 12), "pair_sum"),  # N0 % 16 != 0: outside the pair-LUT path
     ("fcc", "eci_sparse", (64, 6, 10), "pair_lut"),
     ("zro", "eci", (8, 8, 8), "generic"),
 ])
@@ -370,7 +370,9 @@ def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sw
     ("fcc", "eci_sparse", (16, 8, 8), 0),                                  # pair-LUT table (streaming kernel)
     ("fcc", "eci_sparse", (48, 8, 8), 0),                                  # pair-LUT table (block kernel, linear rows)
     ("fcc", "eci_sparse", (16, 8, 8), _capi.CMX_SWEEP_FORCE_GENERIC),      # folded terms, thread evaluator
-    ("fcc", "eci_full", (8, 8, 8), 0),                                     # 1NN + 2NN pairs: generic
+    ("fcc", "eci_full", (8, 8, 8), 0),                                     # 1NN + 2NN pairs: pair-sum tables
+    ("fcc", "eci_full", (8, 8, 8), _capi.CMX_SWEEP_THREAD_GENERIC),        # the same through the term lists
+    ("fcc", "eci_full", (12, 6, 10), 0),                                   # linear rows
     ("fcc", "eci_2", (8, 8, 8), 0),
     ("zro", "eci", (8, 8, 8), 0),                                          # warp evaluator (quadruplets)
     ("zro", "eci", (8, 8, 8), _capi.CMX_SWEEP_THREAD_GENERIC),
@@ -452,8 +454,8 @@ def test_int8_round_trip_of_coded_states(dev_tables):
 
 
 def test_pair_lut_sweep_equals_generic_sweep(dev_tables, systems):
-    """The LUT fast path and the generic evaluator make the same decisions when
-    they see the same random numbers?  They use different RNG counters, so we
+    """The LUT fast path and the pair-sum evaluator (a box outside the LUT path) make the same
+    decisions when they see the same random numbers?  They use different RNG counters, so we
     check the PHYSICS instead: acceptance rate and energy after equilibration
     agree within statistics (two independent evaluators, same ensemble)."""
     mu = [0.2, -0.1]
@@ -470,9 +472,48 @@ def test_pair_lut_sweep_equals_generic_sweep(dev_tables, systems):
         res[st.sweep_info()["evaluator"]] = (np.mean(acc), np.std(acc) / np.sqrt(20), np.mean(e),
                                              np.std(e) / np.sqrt(20))
         st.close()
-    (a1, sa1, e1, se1), (a2, sa2, e2, se2) = res["pair_lut"], res["generic"]
+    (a1, sa1, e1, se1), (a2, sa2, e2, se2) = res["pair_lut"], res["pair_sum"]
     assert abs(a1 - a2) < 5 * np.hypot(sa1, sa2) + 2e-3
     assert abs(e1 - e2) < 5 * np.hypot(se1, se2) + 2e-3
+
+
+@pytest.mark.parametrize("case_sys,eci_key,N,linear_rows,n_replicas", [
+    ("fcc", "eci_full", (16, 8, 8), False, 1),     # x4-interleaved rows
+    ("fcc", "eci_full", (64, 6, 4), False, 3),     # several replicas with different conditions
+    ("fcc", "eci_full", (12, 10, 6), False, 1),    # linear rows (N0 not a power of two)
+    ("fcc", "eci_sparse", (12, 12, 12), False, 2),
+    ("fcc", "eci_2", (24, 8, 8), False, 1),
+    ("fcc", "eci_full", (4, 4, 4), False, 1),      # every site on a periodic seam
+])
+def test_pair_sum_kernel_equals_term_list_kernel(dev_tables, systems, case_sys, eci_key, N, linear_rows, n_replicas):
+    """The pair-sum evaluator (per-neighbor tables folded from the term lists; the evaluator
+    of the reference's dense FCC ECI -- points, 1NN and 2NN pairs, SURVEY 8d's 19-site
+    neighbourhood) draws the same random bits as the one-site-per-thread term-list kernel
+    and must leave the SAME occupation and counters: its dE differs only in the summation
+    order (checked per proposal in test_sweep_evaluators_delta_e_per_proposal), which moves
+    a 47/53-bit acceptance threshold with probability ~1e-15 per step.  Boxes with the
+    seam-free fast path and the wrapped path, both row layouts, replicas, several calls."""
+    mu = [0.2, -0.1]
+    sts = []
+    for flags in (0, _capi.CMX_SWEEP_THREAD_GENERIC):
+        st, sysd, ex = _sweep_state(dev_tables, systems, case_sys, eci_key, N, 900.0, mu, n_replicas=n_replicas,
+                                    seed=5, linear_rows=linear_rows)
+        for r in range(n_replicas):
+            st.set_conditions(700.0 + 250.0 * r, ex, r)
+        st.set_sweep_flags(flags | _capi.CMX_SWEEP_DE_SUM)
+        sts.append(st)
+    a, b = sts
+    assert a.sweep_info()["evaluator"] == "pair_sum" and b.sweep_info()["evaluator"] == "generic"
+    for call in range(3):
+        ca = a.sgc_sweep(4, seed=21, first_sweep=4 * call)
+        cb = b.sgc_sweep(4, seed=21, first_sweep=4 * call)
+        for r in range(n_replicas):
+            assert (a.download_occ(r) == b.download_occ(r)).all(), f"call {call}, replica {r}"
+            assert (ca[r].n_attempt, ca[r].n_accept) == (cb[r].n_attempt, cb[r].n_accept)
+            assert 0 < ca[r].n_accept < ca[r].n_attempt
+            assert ca[r].dE_sum == pytest.approx(cb[r].dE_sum, rel=1e-9, abs=1e-9)
+    a.close()
+    b.close()
 
 
 @pytest.mark.parametrize("T", [500.0, 900.0, 1500.0])
