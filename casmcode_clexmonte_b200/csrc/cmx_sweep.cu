@@ -661,13 +661,26 @@ __device__ __forceinline__ double pairsum_delta(const Geom &g, const int8_t *occ
   const int mo3 = mo * mo * mo;
   const double *Vrow = shV + (oi * mo + of) * mo;
   double dE = p0;
-  const int w = g.xq_log ? (i & ((1 << g.xq_log) - 1)) : i;
-  const int wmax = g.xq_log ? (1 << g.xq_log) : g.N0;
-  const bool inside = fast && w >= R[0] && w < wmax - R[0] && j >= R[1] && j < g.N1 - R[1] &&
-                      (g.halo || (k >= R[2] && k < g.N2 - R[2]));
-  if (inside) {
+  const bool skewed = (g.s10 | g.s20 | g.s21) != 0;
+  const bool in_jk = fast && j >= R[1] && j < g.N1 - R[1] && (g.halo || (k >= R[2] && k < g.N2 - R[2]));
+  if (in_jk && R[0] <= 1 && (!skewed || (i >= 1 && i < g.N0 - 1))) {
+    // Range 1 along i (every first-shell model): the x neighbors' byte offsets are computed per
+    // site -- with x4-interleaved rows EVERY warp holds a site next to a word-lane seam, and
+    // sending that one lane through the wrapped path would cost the warp the whole path
+    const int im = (i == 0) ? g.N0 - 1 : i - 1, ip = (i == g.N0 - 1) ? 0 : i + 1;
+    const int x0 = cmx_xpos(g, i);
+    const int xm = cmx_xpos(g, im) - x0, xp = cmx_xpos(g, ip) - x0;
 #pragma unroll 6
-    for (int s = 0; s < n_act; ++s) dE += Vrow[s * mo3 + cmx_dec(occ[off + shD[s]])];
+    for (int s = 0; s < n_act; ++s) {
+      const int dx = shN[s].x;
+      const int32_t d = shD[s] + (dx < 0 ? xm : (dx > 0 ? xp : 0));
+      dE += Vrow[s * mo3 + cmx_dec(occ[off + d])];
+    }
+  } else if (in_jk && (g.xq_log ? ((i & ((1 << g.xq_log) - 1)) >= R[0] && (i & ((1 << g.xq_log) - 1)) < (1 << g.xq_log) - R[0])
+                                : (i >= R[0] && i < g.N0 - R[0]))) {
+    const int xs = g.xq_log ? 4 : 1;
+#pragma unroll 6
+    for (int s = 0; s < n_act; ++s) dE += Vrow[s * mo3 + cmx_dec(occ[off + shD[s] + shN[s].x * xs])];
   } else {
     for (int s = 0; s < n_act; ++s) {
       const int4 o = shN[s];
@@ -678,7 +691,7 @@ __device__ __forceinline__ double pairsum_delta(const Geom &g, const int8_t *occ
   }
   return dE;
 }
-// the tables of point position p into shared memory: [V][neighbor offsets][byte offsets]
+// the tables of point position p into shared memory: [neighbor offsets][V][byte offsets of the (dj, dk, sublattice) part]
 __device__ __forceinline__ void pairsum_stage(const DevTables &T, const Geom &g, const PairSumArgs &ps, int p,
                                               unsigned char *smem, double *&shV, int4 *&shN, int32_t *&shD, int &n_act) {
   const int mo3 = T.max_occ * T.max_occ * T.max_occ;
@@ -692,8 +705,7 @@ __device__ __forceinline__ void pairsum_stage(const DevTables &T, const Geom &g,
   for (int q = threadIdx.x; q < n_act; q += blockDim.x) {
     const int4 o = T.nbr[ps.act_n[ab + q]];
     shN[q] = o;
-    shD[q] = (int32_t)((int64_t)(o.w - b) * g.sub_stride + (int64_t)o.z * g.layer + (int64_t)o.y * g.N0 +
-                       (int64_t)o.x * (g.xq_log ? 4 : 1));
+    shD[q] = (int32_t)((int64_t)(o.w - b) * g.sub_stride + (int64_t)o.z * g.layer + (int64_t)o.y * g.N0);  // (x apart)
   }
   __syncthreads();
 }
