@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "cmx_state_set_eci", "cmx_state_set_conditions", "cmx_state_set_occupants",
     "cmx_delta_corr", "cmx_point_corr", "cmx_cell_corr", "cmx_delta_e",
     "cmx_global_corr", "cmx_energy", "cmx_composition",
-    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sgc_sweep_slab", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_stream_info", "cmx_sweep_debug_delta_e",
+    "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sgc_sweep_slab", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_term_counts", "cmx_sweep_stream_info", "cmx_sweep_debug_delta_e",
     "cmx_metropolis_sequential", "cmx_metropolis_sequential_ties", "cmx_rng_stream_test",
     "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
@@ -160,6 +160,7 @@ def lib():
     L.cmx_sweep_info.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(dbl), C.POINTER(dbl),
                                  C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cmx_sweep_launches.argtypes = [vp, C.POINTER(i32)]
+    L.cmx_sweep_term_counts.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
     L.cmx_sweep_stream_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cmx_sweep_debug_delta_e.argtypes = [vp, i32, i64, vp, vp, vp]
     L.cmx_state_create_opts.argtypes = [vp, i32, i32, i32, i32, i32, C.c_uint32, C.POINTER(vp)]
@@ -527,7 +528,10 @@ class State:
             check(lib().cmx_sweep_stream_info(self._h, C.byref(st), C.byref(sb), C.byref(gr), C.byref(gap)))
         except CmxError:
             pass
+        nt, nn = C.c_double(), C.c_double()
+        check(lib().cmx_sweep_term_counts(self._h, C.byref(nt), C.byref(nn)))
         return dict(evaluator=name.value.decode(), bytes_per_step=b.value, flops_per_step=f.value,
+                    terms_per_step=nt.value, neighbors_per_step=nn.value,
                     n_colours=nc.value, colour_strides=tuple(S), range_k=rk.value,
                     launches_per_sweep=nl.value, one_launch_per_call=(nl.value == 0), stream=bool(st.value), stream_blocks=sb.value,
                     stream_group_rowsteps=gr.value, stream_gap_units=gap.value)

@@ -2239,6 +2239,18 @@ extern "C" int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep) {
   return CMX_OK;
 }
 
+extern "C" int cmx_sweep_term_counts(const cmx_state *s, double *terms_per_step, double *neighbors_per_step) {
+  if (!s) return invalid("cmx_sweep_term_counts: null state");
+  if (!s->plan.valid || s->plan.mut_points.empty()) {
+    cmx_set_error("cmx_sweep_term_counts: no sweep plan");
+    return CMX_ERR_STATE;
+  }
+  const double nm = (double)s->plan.mut_points.size();
+  if (terms_per_step) *terms_per_step = s->plan.n_gterms / nm;
+  if (neighbors_per_step) *neighbors_per_step = s->plan.bytes_per_step - 2.0;  // (bytes = neighbors + own + write)
+  return CMX_OK;
+}
+
 // ---------------------------------------------------------------------------
 // per-proposal dE of the sweep's evaluator (parity/debug entry)
 // ---------------------------------------------------------------------------

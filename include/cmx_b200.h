@@ -351,6 +351,10 @@ int cmx_canonical_info(const cmx_state *s, int32_t i, int32_t *strides /*[3]*/,
  * 4 launches for 8 colours; generic: one per colour); 0 = the kernels on x4-interleaved rows,
  * which run a whole cmx_sgc_sweep call as one launch. */
 int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep);
+/* Size of the ECI-folded term lists the term-list evaluators walk, averaged over the mutable
+ * point positions: merged terms per attempted step and distinct neighbor sites they read
+ * (for the shared-memory / FP64 roofline bookkeeping of wide orbit sets). */
+int cmx_sweep_term_counts(const cmx_state *s, double *terms_per_step, double *neighbors_per_step);
 /* Schedule of the streaming kernel on this state: *stream = 1 when it is the evaluator
  * (CMX_SWEEP_STREAM on a state with x4-interleaved rows),
  * *blocks = co-resident blocks per replica, *group_rowsteps = row-steps a warp takes at a

@@ -102,7 +102,7 @@ def c3full():
     """BASELINE configs[2] with ALL nine functions of the FCC basis selected (constant, points,
     1NN and 2NN pairs -- the 19-site neighbourhood SURVEY section 8d quotes; coefficient values
     of the golden fixture `eci_full`): two neighbour classes, so outside the pair-LUT fast path
-    -- the generic folded-term evaluator runs (one site per thread)."""
+    -- the pair-sum evaluator runs (per-neighbor tables, one site per thread)."""
     sysd = SYS["fcc"]
     t = tables("fcc_default")
     for N in (256, 512):
@@ -118,8 +118,9 @@ def c3full():
         emit(workload=f"c3 all functions: FCC A-B-Va SGC, {N}^3, points + 1NN + 2NN pairs (19-site neighbourhood)",
              metric="attempted MC steps/s", value=rate, ms=ms, sweeps=S, evaluator=info.get("evaluator"),
              bytes_per_step_l2=info.get("bytes_per_step"), flops_per_step=info.get("flops_per_step"),
-             roofline={"bound": "hbm", "achieved": 2.0 * rate / 1e9, "peak": HBM, "unit": "GB/s", "frac": 2.0 * rate / 1e9 / HBM,
-                       "note": "2 B per step at HBM; the evaluator is gather / FP64-issue bound (20 B per step through L1/L2)"},
+             roofline={"bound": "issue (L1 gather + FP64 adds)", "achieved": info.get("bytes_per_step") * rate / 1e9,
+                       "unit": "GB/s of neighborhood gather through L1", "hbm_frac_at_2B_per_step": 2.0 * rate / 1e9 / HBM,
+                       "note": "2 B per step at HBM; the pair-sum evaluator is issue bound (20 B per step through L1/L2, ~550 instructions)"},
              accept_rate=cnt[0].n_accept / cnt[0].n_attempt)
         st.close()
     t.close()
@@ -208,8 +209,7 @@ def c4():
         emit(workload=f"c4: ZrO canonical O<->Va pair exchanges, {N}^3 cells (4 sublattices, 2 mutable), quadruplet basis (33 ECI), T=600 K",
              metric="attempted MC steps/s (each a two-site dE)", value=rate, single_site_dcorr_per_s=2 * rate, ms=ms,
              sweeps=S, swap_types=len(swaps), accept_rate=cnt[0].n_accept / cnt[0].n_attempt, kernel="k_canonical_pairs_warp (one cooperative launch per swap type)",
-             roofline={"bound": "l2 gather (reported against hbm)", "achieved": 2 * 226.0 * rate / 1e9, "peak": HBM,
-                       "unit": "GB/s", "frac": 2 * 226.0 * rate / 1e9 / HBM, "algorithmic_bytes_per_single_site_dE": 226.0})
+             roofline=wide_roofline(st.sweep_info(), rate, evals_per_step=2))
         info = st.sweep_info()
         st.sgc_sweep(1, seed=2)
         ms, cnt = timed(st, lambda: st.sgc_sweep(S, seed=2, first_sweep=1))
@@ -217,11 +217,25 @@ def c4():
         emit(workload=f"c4b: ZrO semi-grand O/Va flips, {N}^3 cells, generic term-list evaluator, one site per warp ({info['n_colours']} colours)",
              metric="attempted MC steps/s", value=rate, ms=ms, sweeps=S, kernel="k_sweep_generic_warp",
              bytes_per_step=info["bytes_per_step"], flops_per_step=info["flops_per_step"],
-             roofline={"bound": "fp64 / l2 gather", "achieved_gflops": info["flops_per_step"] * rate / 1e9,
-                       "achieved": info["bytes_per_step"] * rate / 1e9, "peak": HBM, "unit": "GB/s",
-                       "frac": info["bytes_per_step"] * rate / 1e9 / HBM})
+             roofline=wide_roofline(info, rate, evals_per_step=1))
         st.close()
     t.close()
+
+
+def wide_roofline(info, rate, evals_per_step):
+    """Wide orbit sets (one site per warp, term tables and staged site-function values in shared
+    memory): the binding resource is shared-memory bandwidth -- per merged term one packed index
+    word, one weight and four staged values (6 x 8 B), per neighbor the staged values written once
+    -- and, behind it, the FP64 pipe.  Peaks: 148 SMs x 128 B/clk x 1.965 GHz of shared-memory
+    bandwidth (B300_MICROARCH.md: 128 B/clk/SM), 37 TFLOP/s nominal FP64 (datasheet, not measured)."""
+    smem_peak = 148 * 128 * 1.965  # GB/s
+    smem_bytes = evals_per_step * (info["terms_per_step"] * 48.0 + info["neighbors_per_step"] * 16.0)
+    flops = evals_per_step * (info["terms_per_step"] * 5.0) + 25.0
+    return {"bound": "shared-memory bandwidth", "achieved": smem_bytes * rate / 1e9, "peak": smem_peak, "unit": "GB/s",
+            "frac": smem_bytes * rate / 1e9 / smem_peak, "shared_bytes_per_step": smem_bytes,
+            "terms_per_single_site_dE": info["terms_per_step"], "neighbors_per_single_site_dE": info["neighbors_per_step"],
+            "fp64": {"achieved_tflops": flops * rate / 1e12, "peak_tflops_nominal": 37.0, "frac": flops * rate / 1e12 / 37.0,
+                     "flops_per_step": flops}}
 
 
 def c4_cpu():
