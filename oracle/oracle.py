@@ -27,6 +27,8 @@ CLEXULATORS = {
     "fcc_default": "FCC_binary_vacancy_Clexulator_default",
     "zro": "ZrO_Clexulator_formation_energy",
 }
+# the synthetic FCC binary pair + triplet basis (tests/golden/make_synthetic_clexulator.py, SURVEY 8c "Gap")
+CLEXULATORS["fcc_synthetic"] = "FCC_binary_Clexulator_synthetic"
 for _ev in ("A_Va_1NN", "B_Va_1NN"):
     for _k in range(6):
         CLEXULATORS[f"fcc_{_ev}_{_k}"] = f"FCC_binary_vacancy_Clexulator_{_ev}_{_k}"
@@ -37,6 +39,7 @@ def build(ref: bool = True) -> None:
     targets = ["harness"]
     if ref and Path("/root/reference").exists():
         targets.append("ref")
+        targets.append("synthetic")
     subprocess.run(["make", "-s", "-j8", "-C", str(HERE)] + targets, check=True)
 
 

@@ -75,4 +75,6 @@ CASES = {
     "fcc_sparse": ("fcc", "eci_sparse"),
     "fcc_full": ("fcc", "eci_full"),
     "zro": ("zro", "eci"),
+    # the synthetic FCC binary pair + triplet basis (tests/golden/make_synthetic_clexulator.py)
+    "fcc_synthetic": ("fcc_syn", "eci"),
 }

@@ -13,6 +13,10 @@
    sequential Metropolis trajectories (std::mt19937_64).
 3. tests/golden/systems.json    the small prim / ECI / composition-axes facts the
    tests need (values read from the reference's JSON fixtures).
+4. the same for the SYNTHETIC FCC binary pair + triplet basis ("fcc_synthetic" / "fcc_syn"):
+   source emitted by tests/golden/make_synthetic_clexulator.py in the generated-source
+   grammar, compiled into oracle/_ref like the reference's own (`... make_golden.py synthetic`
+   regenerates only these).
 """
 from __future__ import annotations
 
@@ -331,7 +335,33 @@ def rng_vectors():
                         int_max=int_max, real_max=real_max, out_int=oi, out_real=orl, out_raw=oraw)
 
 
+def synthetic_system():
+    """The synthetic FCC binary A-B pair + triplet basis (make_synthetic_clexulator.py, SURVEY 8c
+    "Gap" / BASELINE configs[0]): composition axis from pure A to pure B, test coefficients on
+    every function."""
+    origin, ends = [1.0, 0.0], [[0.0, 1.0]]
+    return dict(tables="fcc_synthetic", n_species=2, species=["A", "B"], sublat_to_asym=[0],
+                occ_to_species=[[0, 1]], mutable_sublats=[0],
+                axes=dict(components=["A", "B"], origin=origin, end_members=ends, Rt=rt_matrix(origin, ends).tolist()),
+                eci=dict(index=[0, 1, 2, 3, 4], value=[-0.02, 0.01, 0.035, -0.012, 0.008]))
+
+
+def synthetic():
+    """Only the synthetic-basis fixtures (the reference-derived ones stay untouched):
+    python tests/golden/make_golden.py synthetic"""
+    O.build()
+    from make_synthetic_clexulator import NAME
+    t = parse_clexulator_source(ROOT / "oracle/_ref" / f"{NAME}.cc", name="fcc_synthetic")
+    t.save(OUT / "tables" / "fcc_synthetic.npz")
+    S = json.loads((OUT / "systems.json").read_text())
+    S["fcc_syn"] = synthetic_system()
+    (OUT / "systems.json").write_text(json.dumps(S, indent=1))
+    vectors("fcc_synthetic", S["fcc_syn"], 6, S["fcc_syn"]["eci"], seed=10)
+
+
 def main():
+    if sys.argv[1:] == ["synthetic"]:
+        return synthetic()
     O.build()
     (OUT / "tables").mkdir(exist_ok=True)
     for name, src in SOURCES.items():
@@ -344,6 +374,7 @@ def main():
     vectors("fcc_sparse", S["fcc"], 6, S["fcc"]["eci_sparse"])
     vectors("fcc_full", S["fcc"], 6, S["fcc"]["eci_full"], seed=8)
     vectors("zro", S["zro"], 8, S["zro"]["eci"], n_events=32, traj_steps=5000, seed=9)
+    synthetic()
     local_vectors()
     rng_vectors()
 

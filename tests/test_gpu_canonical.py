@@ -158,6 +158,66 @@ def test_canonical_matches_sequential_thermodynamics(dev_tables, systems, oracle
     st.close()
 
 
+def test_config0_binary_pair_triplet_canonical_temperature_path(dev_tables, systems, oracle):
+    """BASELINE configs[0]: FCC binary A-B canonical Metropolis on a pair + triplet basis along a
+    cooling path.  The reference ships no such clexulator (SURVEY 8c "Gap"): the basis is the
+    synthetic one emitted in the generated-source grammar (make_synthetic_clexulator.py) and
+    compiled into oracle/_ref like the reference's own.  x_B = 0.5, every temperature starts
+    from the final state of the one before (dependent runs); mean formation energy of the
+    parallel pair exchanges against the restated sequential any-two-sites loop driving the
+    compiled kernels, 3 sigma over independent runs at every temperature."""
+    if oracle is None or not oracle.available("fcc_synthetic"):
+        pytest.skip("oracle/_ref has no synthetic clexulator")
+    sysd = systems["fcc_syn"]
+    eci = sysd["eci"]
+    N = 8
+    n_cells = N ** 3
+    temps = [1500.0, 700.0, 300.0]
+    prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
+                n_species=2, Rt=np.array(sysd["axes"]["Rt"]), origin=np.array(sysd["axes"]["origin"]))
+    sc = oracle.RefClexulator("fcc_synthetic").supercell(N)
+    n_runs = 8
+    base = np.array([0] * (n_cells // 2) + [1] * (n_cells - n_cells // 2), dtype=np.int32)
+    inits = [np.random.default_rng(300 + r).permutation(base).astype(np.int32) for r in range(n_runs)]
+    ref_e = np.zeros((len(temps), n_runs))
+    for run in range(n_runs):
+        occ = inits[run].copy()
+        for ti, T in enumerate(temps):
+            occ = sc.metropolis_run(1, occ, prim, eci["index"], eci["value"], T, seed=7000 + 31 * run + ti,
+                                    n_steps=60 * n_cells)["occ"]
+            es = []
+            for k in range(24):
+                occ = sc.metropolis_run(1, occ, prim, eci["index"], eci["value"], T,
+                                        seed=9000 + 977 * run + 37 * ti + k, n_steps=4 * n_cells)["occ"]
+                g = sc.global_corr(occ)
+                es.append(float(np.dot(eci["value"], g[eci["index"]])) / n_cells)
+            ref_e[ti, run] = np.mean(es)
+    st, _, swaps = _state(dev_tables, systems, "fcc_syn", "eci", (N, N, N), temps[0], inits[0], n_replicas=n_runs)
+    for r in range(n_runs):
+        st.upload_occ(inits[r], r)
+    st.canonical_set_swaps(swaps)
+    sweep = 0
+    for ti, T in enumerate(temps):
+        for r in range(n_runs):
+            st.set_conditions(T, None, r)
+        st.canonical_sweep(40, seed=33, first_sweep=sweep)
+        sweep += 40
+        ge = np.zeros((n_runs, 24))
+        for k in range(24):
+            st.canonical_sweep(3, seed=33, first_sweep=sweep)
+            sweep += 3
+            for r in range(n_runs):
+                ge[r, k] = st.energy(r) / n_cells
+        gpu_e = ge.mean(axis=1)
+        se = np.hypot(np.std(ref_e[ti], ddof=1), np.std(gpu_e, ddof=1)) / np.sqrt(n_runs)
+        assert abs(np.mean(ref_e[ti]) - np.mean(gpu_e)) < 3 * se + 1e-4, (T, np.mean(ref_e[ti]), np.mean(gpu_e), se)
+    for r in range(n_runs):
+        assert (np.bincount(st.download_occ(r), minlength=2) == np.bincount(base, minlength=2)).all()
+    # the path really cools: the mean energy drops from the first to the last temperature
+    assert np.mean(ref_e[-1]) < np.mean(ref_e[0])
+    st.close()
+
+
 def test_zro_canonical_matches_sequential_thermodynamics(dev_tables, systems, oracle):
     """BASELINE configs[3] (HCP Zr-O, O/Va on two interstitial sublattices, pairs + triplets +
     quadruplets): the parallel pair exchanges -- swap types restricted to a set of

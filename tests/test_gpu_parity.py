@@ -187,6 +187,7 @@ def _sweep_state(dev_tables, systems, case_sys, eci_key, N, T, mu, n_replicas=1,
     ("fcc", "eci_sparse", (12, 12, 12), "pair_sum"),  # N0 % 16 != 0: outside the pair-LUT path
     ("fcc", "eci_sparse", (64, 6, 10), "pair_lut"),
     ("zro", "eci", (8, 8, 8), "generic"),
+    ("fcc_syn", "eci", (16, 8, 8), "generic"),        # synthetic FCC binary pair + triplet basis
 ])
 def test_sweep_energy_bookkeeping(dev_tables, systems, case_sys, eci_key, N, expect):
     """Size-independent property: the sum of accepted dE reported by the sweep
@@ -376,6 +377,7 @@ def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sw
     ("fcc", "eci_2", (8, 8, 8), 0),
     ("zro", "eci", (8, 8, 8), 0),                                          # warp evaluator (quadruplets)
     ("zro", "eci", (8, 8, 8), _capi.CMX_SWEEP_THREAD_GENERIC),
+    ("fcc_syn", "eci", (8, 8, 8), 0),                                      # FCC triplets: term lists per thread
 ])
 def test_sweep_evaluators_delta_e_per_proposal(dev_tables, systems, case_sys, eci_key, N, flags):
     """north_star (1): dE within 1e-10 relative, proposal by proposal, for the evaluators

@@ -68,7 +68,10 @@ def test_delta_equals_difference_of_global(oracle):
     global contribution after - before == delta point corr."""
     if oracle is None:
         pytest.skip("oracle/_ref not built")
-    for name, N, mut, nocc, tol in (("fcc_default", 6, [0], 3, 5e-14), ("zro", 8, [2, 3], 2, 5e-13)):
+    for name, N, mut, nocc, tol in (("fcc_default", 6, [0], 3, 5e-14), ("zro", 8, [2, 3], 2, 5e-13),
+                                    ("fcc_synthetic", 6, [0], 2, 5e-14)):
+        if not oracle.available(name):
+            pytest.skip(f"oracle/_ref has no {name}")
         sc = oracle.RefClexulator(name).supercell(N)
         rng = np.random.default_rng(5)
         occ = np.zeros(sc.n_sites, dtype=np.int32)
@@ -90,6 +93,8 @@ def test_oracle_reproduces_golden(oracle, systems, load_vectors, case):
     if oracle is None:
         pytest.skip("oracle/_ref not built")
     sysname, _ = CASES[case]
+    if not oracle.available(systems[sysname]["tables"]):
+        pytest.skip(f"oracle/_ref has no {systems[sysname]['tables']}")
     v = load_vectors(case)
     sc = oracle.RefClexulator(systems[sysname]["tables"]).supercell(tuple(v["N"]))
     occ = v["occ"]
@@ -161,6 +166,29 @@ def test_exporter_matches_committed_tables(load_tables):
         for k in CT.ClexulatorTables._ARRAYS:
             assert np.array_equal(getattr(fresh, k), getattr(old, k)), (name, k)
         assert fresh.nlist_size == old.nlist_size and fresh.corr_size == old.corr_size
+
+
+def test_synthetic_source_exports_to_committed_tables(load_tables, tmp_path):
+    """The synthetic FCC binary pair + triplet basis (SURVEY 8c "Gap", BASELINE configs[0]):
+    the emitter writes the generated-source grammar, the exporter reads it back into exactly
+    the committed tables -- 1 + 12 + 6 pair and 24 triplet clusters around a site, divisors
+    6 / 3 / 8.  Runs anywhere (no reference, no oracle build needed)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_synthetic_clexulator", GOLDEN / "make_synthetic_clexulator.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    src = tmp_path / f"{mod.NAME}.cc"
+    src.write_text(mod.emit())
+    fresh = CT.parse_clexulator_source(src, name="fcc_synthetic")
+    old = load_tables("fcc_synthetic")
+    for k in CT.ClexulatorTables._ARRAYS:
+        assert np.array_equal(getattr(fresh, k), getattr(old, k)), k
+    assert (fresh.nlist_size, fresh.corr_size, fresh.n_point_corr) == (19, 5, 1)
+    # delta function of the triplet orbit: 24 two-factor terms under one divisor
+    g = fresh.delta_gbeg[4]
+    assert fresh.group_div[g] == 8.0
+    terms = range(fresh.elem_tbeg[fresh.group_ebeg[g]], fresh.elem_tbeg[fresh.group_ebeg[g + 1]])
+    assert len(terms) == 24 and all(fresh.term_fbeg[t + 1] - fresh.term_fbeg[t] == 2 for t in terms)
 
 
 def test_table_shapes(load_tables):
