@@ -281,15 +281,38 @@ __global__ void __launch_bounds__(256) k_energy_row16(EnergyArgs a, uint32_t log
   const uint32_t lane_l = (lane & ~Wm) | ((c - 1u) & Wm), lane_r = (lane & ~Wm) | ((c + 1u) & Wm);
   const uint32_t rpw_log = 5u - logW;
   const uint32_t warp0 = blockIdx.x * 8u + (threadIdx.x >> 5), n_warps = gridDim.x * 8u;
-  unsigned long long tot[NM][6];
+  // 32-bit partial sums per lane, handed to the block's 64-bit shared sums every 1024 tiles and at
+  // the end (no 64-bit totals in registers).  Scaled: [1] = 16 n2; [2] = sum over occupant-1 cells
+  // of the whole count byte L + 16 H instead of L, [4] the same over occupant-2 cells (x 16 like
+  // [5]) -- one dot product with the byte sums as they are, undone in `flush`.  The occupant
+  // counts do not depend on the neighbor set: only set 0 counts them.
   uint32_t acc[NM][6];
 #pragma unroll
   for (int m = 0; m < NM; ++m)
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      tot[m][q] = 0;
-      acc[m][q] = 0;
+    for (int q = 0; q < 6; ++q) acc[m][q] = 0;
+  auto flush = [&]() {
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      unsigned long long t[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) t[q] = acc[m][q];
+      t[0] = acc[0][0];
+      t[1] = acc[0][1] >> 4;
+      t[2] -= 16ull * t[3];
+      t[4] -= 16ull * t[5];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[q] += __shfl_down_sync(0xffffffffu, t[q], o);
+        if ((threadIdx.x & 31) == 0 && t[q]) atomicAdd(&sh_sum[m][q], t[q]);  // integers: order-free
+      }
     }
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[m][q] = 0;
+  };
   uint32_t it = 0;
   for (uint32_t tile = warp0; tile < n_tiles; tile += n_warps) {
     const uint32_t row_raw = (tile << rpw_log) + rl;
@@ -368,40 +391,23 @@ __global__ void __launch_bounds__(256) k_energy_row16(EnergyArgs a, uint32_t log
       if (on) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t L = cnt[i] & 0x0F0F0F0Fu;
           const uint32_t H = (cnt[i] >> 4) & 0x0F0F0F0Fu;
           const uint32_t p1 = C[i] & 0x01010101u;
-          acc[m][0] += __popc(p1);
-          acc[m][2] = __dp4a(p1, L, acc[m][2]);
+          if (m == 0) acc[0][0] = __dp4a(p1, 0x01010101u, acc[0][0]);
+          acc[m][2] = __dp4a(p1, cnt[i], acc[m][2]);
           acc[m][3] = __dp4a(p1, H, acc[m][3]);
           if (NOCC == 3) {
             const uint32_t p2 = C[i] & 0x10101010u;
-            acc[m][1] += __popc(p2);
-            acc[m][4] = __dp4a(p2, L, acc[m][4]);
+            if (m == 0) acc[0][1] = __dp4a(p2, 0x01010101u, acc[0][1]);
+            acc[m][4] = __dp4a(p2, cnt[i], acc[m][4]);
             acc[m][5] = __dp4a(p2, H, acc[m][5]);
           }
         }
       }
     }
-    if ((++it & 1023u) == 0) {
-#pragma unroll
-      for (int m = 0; m < NM; ++m)
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          tot[m][q] += acc[m][q];
-          acc[m][q] = 0;
-        }
-    }
+    if ((++it & 1023u) == 0) flush();  // a tile adds < 2^15 to a 32-bit sum
   }
-#pragma unroll
-  for (int m = 0; m < NM; ++m)
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      tot[m][q] += acc[m][q];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot[m][q] += __shfl_down_sync(0xffffffffu, tot[m][q], o);
-      if ((threadIdx.x & 31) == 0 && tot[m][q]) atomicAdd(&sh_sum[m][q], tot[m][q]);
-    }
+  flush();
   __syncthreads();
   if (threadIdx.x < NM) {
     const int m = threadIdx.x;
