@@ -681,9 +681,18 @@ extern "C" int cmx_state_synchronize(cmx_state *s) {
     CMX_CUDA(cudaMemcpyAsync(&bad, s->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CMX_CUDA(cudaMemsetAsync(s->d_flag + 1, 0, sizeof(int), s->stream));
   }
+  // (a sweep that gave up waiting for a ring neighbour or a layer counter set this word and
+  // went on: callers that never read the counters learn it here)
+  unsigned long long timed_out = 0;
+  CMX_CUDA(cudaMemcpyAsync(&timed_out, s->d_sig + 3, sizeof(timed_out), cudaMemcpyDeviceToHost, s->stream));
   CMX_CUDA(cudaStreamSynchronize(s->stream));
   s->async_upload_pending = false;
   if (bad) return invalid("cmx_state_synchronize: occupant index out of range in an asynchronous upload");
+  if (timed_out) {
+    cmx_set_error("cmx_state_synchronize: a sweep timed out waiting for a ring neighbour's epoch or a layer counter "
+                  "(grid not co-resident, or a neighbour did not run the same sweeps); the occupation is not valid");
+    return CMX_ERR_CUDA;
+  }
   return CMX_OK;
 }
 
