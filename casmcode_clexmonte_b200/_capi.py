@@ -21,6 +21,7 @@ LIB_PATH = HERE / "libcmx_b200.so"
 CMX_OK, CMX_ERR_INVALID, CMX_ERR_CUDA, CMX_ERR_UNSUPPORTED, CMX_ERR_STATE = range(5)
 CMX_SWEEP_DE_SUM, CMX_SWEEP_FORCE_GENERIC = 1, 2
 CMX_SWEEP_THREAD_GENERIC = 16
+CMX_SWEEP_PAIR_SUM = 32
 CMX_SWEEP_STREAM = 8
 CMX_STATE_LINEAR_ROWS = 1
 

@@ -156,6 +156,20 @@ struct SweepPlan {
   uint32_t *d_tab = nullptr;      // [replica][n_tab] threshold(15 bit)<<9 | 1<<8 | proposed code
   uint32_t *d_thr_lo = nullptr;   // [replica][n_tab] low 32 bits of the threshold (tie break)
   double *d_dEpot = nullptr;      // [replica][n_tab] dE - exch
+  // two-class count table (k_sweep_pass16 with a second mask): point + pair bases whose active
+  // neighbors form TWO classes (the reference's dense FCC ECI: 1NN + 2NN pairs) on
+  // x4-interleaved rows.  Compact index: row(oi, alt) n1 n2 + i1 n2 + i2, i_c = index of the
+  // class's (n_B, n_Va) among the combinations with n_B + n_Va <= z_c
+  bool pair2 = false;
+  uint32_t mask2 = 0;              // offsets of the second class (bit layout as `mask`)
+  int32_t z2 = 0;
+  int32_t shell2[48] = {0};
+  int32_t n_tab2 = 0;              // 2 nocc x n1 x n2 entries
+  double *d_pair2_dE = nullptr;    // [n_tab2] clex dE, summed in the pair-sum evaluator's order
+  uint16_t *d_maps2 = nullptr;     // [544] index maps (S16Args::maps2)
+  uint32_t *d_tab2 = nullptr;      // [replica][n_tab2] thr16 | proposed code << 16
+  uint32_t *d_thr_lo2 = nullptr;   // [replica][n_tab2]
+  double *d_dEpot2 = nullptr;      // [replica][n_tab2] dE - exch
   // streaming kernel (cmx_sweep_stream.cuh): x4-interleaved rows
   bool stream = false;
   int32_t n_tab24 = 0;            // entries of its acceptance table

@@ -48,6 +48,11 @@ void cmx_plan_free(SweepPlan &p) {
   cudaFree(p.d_thr_lo);
   cudaFree(p.d_dEpot);
   cudaFree(p.d_tab24);
+  cudaFree(p.d_pair2_dE);
+  cudaFree(p.d_maps2);
+  cudaFree(p.d_tab2);
+  cudaFree(p.d_thr_lo2);
+  cudaFree(p.d_dEpot2);
   for (auto &kv : p.stream_lists) cudaFree(kv.second.d_units);
   cudaFree(p.d_ticket);
   cudaFree(p.d_gridbar);
@@ -154,6 +159,34 @@ __global__ void k_build_tab16(const double *__restrict__ lut, int nocc, int z, i
   tab[o] = (t17 << 8) | (uint32_t)((of == 2) ? CMX_VA_CODE : of);
   thr_lo[o] = (uint32_t)(t & 0xFFFFFFFFull);
   dEpot[o] = dE;
+}
+
+// Acceptance tables of the two-class kernel (compact index, SweepPlan::pair2): the same
+// threshold arithmetic, entry = thr16 | proposed code << 16 (the colour-pass kernel's format).
+__global__ void k_build_tab2(const double *__restrict__ lut2, int n_tab2, int per_row, int nocc, int max_occ,
+                             const double *__restrict__ beta, const double *__restrict__ exch, int exch_stride,
+                             uint32_t *__restrict__ tab2, uint32_t *__restrict__ thr_lo2, double *__restrict__ dEpot2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (idx >= n_tab2) return;
+  const int row = idx / per_row;
+  const int oi = row / (nocc - 1), alt = row - oi * (nocc - 1);
+  int of = oi + 1 + alt;
+  if (of >= nocc) of -= nocc;
+  const double x = exch[(size_t)r * exch_stride + (0 * max_occ + oi) * max_occ + of];
+  const double dE = __dsub_rn(lut2[idx], x);
+  unsigned long long t;
+  const double two47 = 140737488355328.0;
+  if (dE < 0.0) {
+    t = 1ull << 47;
+  } else {
+    const double p = exp(-dE * beta[r]);
+    t = (unsigned long long)ceil(p * two47);
+  }
+  const size_t o = (size_t)r * n_tab2 + idx;
+  tab2[o] = (uint32_t)(t >> 32) | ((uint32_t)((of == 2) ? CMX_VA_CODE : of) << 16);
+  thr_lo2[o] = (uint32_t)(t & 0xFFFFFFFFull);
+  dEpot2[o] = dE;
 }
 
 // ---------------------------------------------------------------------------
@@ -965,6 +998,21 @@ static int smallest_divisor_above(int N, int R) {
   return N;
 }
 
+// FCC nearest-neighbor shell in CASM's standard primitive cell
+// (offsets of m_orbit_site_neighborhood[3], FCC default clexulator :404-414)
+constexpr uint32_t mbit(int dx, int dy, int dz) {
+  return 1u << ((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
+}
+constexpr uint32_t kMaskFcc1NN =
+    mbit(-1, 0, 0) | mbit(-1, 0, 1) | mbit(-1, 1, 0) | mbit(0, -1, 0) | mbit(0, -1, 1) |
+    mbit(0, 0, -1) | mbit(0, 0, 1) | mbit(0, 1, -1) | mbit(0, 1, 0) | mbit(1, -1, 0) |
+    mbit(1, 0, -1) | mbit(1, 0, 0);
+
+// ... and the second shell (neighbor-list sites 13-18 of the same clexulator): every offset has
+// dx = +-1 and none lies in the site's own row
+constexpr uint32_t kMaskFcc2NN =
+    mbit(-1, -1, 1) | mbit(-1, 1, -1) | mbit(-1, 1, 1) | mbit(1, -1, -1) | mbit(1, -1, 1) | mbit(1, 1, -1);
+
 int cmx_plan_sweep(cmx_state *s) {
   cmx_plan_free(s->plan);
   SweepPlan &P = s->plan;
@@ -1030,6 +1078,8 @@ int cmx_plan_sweep(cmx_state *s) {
   if ((rc = to_device(gt_f, &P.d_gt_f))) return rc;
   if ((rc = to_device(gt_n, &P.d_gt_n))) return rc;
   if ((rc = to_device(gt_w, &P.d_gt_w))) return rc;
+  std::vector<double> psV, psP0;   // host copies of the pair-sum tables (two-class count table below)
+  std::vector<int32_t> ps_act_n;
   {
     // warp-cooperative evaluation: per point position the neighbors its terms read,
     // per factor the index of the staged value
@@ -1103,6 +1153,9 @@ int cmx_plan_sweep(cmx_state *s) {
       if ((rc = to_device(V, &P.d_ps_V))) return rc;
       if ((rc = to_device(P0, &P.d_ps_P0))) return rc;
       P.pair_sum = true;
+      psV = V;
+      psP0 = P0;
+      ps_act_n = act_n;
     }
   }
 
@@ -1247,6 +1300,110 @@ int cmx_plan_sweep(cmx_state *s) {
     // dot, the exp folded into the threshold) -- report the table-free count
     P.bytes_per_step = P.z + 2;
   }
+  // ---- two-class count table: a point + pair basis on one ternary sublattice whose active
+  // neighbors are exactly the FCC 1NN and 2NN shells with one table per shell, on
+  // x4-interleaved rows of one GPU's box.  dE per (oi, alt, class-1 counts, class-2 counts) is
+  // summed HERE in the pair-sum evaluator's order (P0, then the neighbors in slot order) on a
+  // representative arrangement, so the table holds values k_sweep_pairsum itself produces.
+  if (!P.pair_lut && P.pair_sum && !skewed && T.n_sublat == 1 && np == 1 && P.mut_points.size() == 1 &&
+      t->n_occ[0] == 3 && mo == 3 && s->g.coded && s->g.xq_log != 0 && s->g.halo == 0 && s->g.N0 % 16 == 0 &&
+      s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 && s->g.N2 <= 65534 && ((uint64_t)s->g.rep_stride >> 4) < (1ull << 32) &&
+      P.S[0] == 2 && P.S[1] == 2 && P.S[2] == 2 && !ps_act_n.empty() && ps_act_n.size() <= 32) {
+    const int n_act = (int)ps_act_n.size(), mo3 = mo * mo * mo;
+    double scale = 0;
+    for (double x : psV) scale = std::max(scale, std::fabs(x));
+    auto same = [&](int a, int b) {
+      for (int x = 0; x < mo3; ++x)
+        if (std::fabs(psV[(size_t)a * mo3 + x] - psV[(size_t)b * mo3 + x]) > 1e-12 * scale) return false;
+      return true;
+    };
+    std::vector<int> cls(n_act, -1);
+    int rep[2] = {0, 0}, n_cls = 0;
+    bool two = true;
+    for (int a = 0; a < n_act && two; ++a) {
+      for (int c = 0; c < n_cls; ++c)
+        if (same(a, rep[c])) cls[a] = c;
+      if (cls[a] < 0) {
+        if (n_cls == 2) two = false;
+        else {
+          rep[n_cls] = a;
+          cls[a] = n_cls++;
+        }
+      }
+    }
+    uint32_t m[2] = {0, 0};
+    int zc[2] = {0, 0};
+    if (two && n_cls == 2)
+      for (int a = 0; a < n_act; ++a) {
+        const int32_t *o = &t->nbr[4 * ps_act_n[a]];
+        if (std::abs(o[0]) > 1 || std::abs(o[1]) > 1 || std::abs(o[2]) > 1 || (o[0] == 0 && o[1] == 0 && o[2] == 0)) two = false;
+        else m[cls[a]] |= mbit(o[0], o[1], o[2]);
+        ++zc[cls[a]];
+      }
+    int c1 = -1;
+    if (two && n_cls == 2) {
+      if (m[0] == kMaskFcc1NN && m[1] == kMaskFcc2NN) c1 = 0;
+      else if (m[1] == kMaskFcc1NN && m[0] == kMaskFcc2NN) c1 = 1;
+    }
+    if (c1 >= 0 && zc[c1] == 12 && zc[1 - c1] == 6) {
+      const int z1 = 12, z2 = 6, nocc = 3;
+      const int n1 = (z1 + 1) * (z1 + 2) / 2, n2 = (z2 + 1) * (z2 + 2) / 2, per_row = n1 * n2;
+      const int n_tab2 = nocc * (nocc - 1) * per_row;
+      auto tri = [](int z, int nB, int nV) { return nV * (z + 1) - nV * (nV - 1) / 2 + nB; };
+      std::vector<uint16_t> maps(CMX_S16_MAPS, 0);
+      for (int nV = 0; nV <= z1; ++nV)
+        for (int nB = 0; nB + nV <= z1; ++nB) maps[nB + CMX_VA_CODE * nV] = (uint16_t)(tri(z1, nB, nV) * n2);
+      for (int nV = 0; nV <= z2; ++nV)
+        for (int nB = 0; nB + nV <= z2; ++nB) maps[256 + nB + CMX_VA_CODE * nV] = (uint16_t)tri(z2, nB, nV);
+      for (int oi = 0; oi < nocc; ++oi)
+        for (int alt = 0; alt < nocc - 1; ++alt)
+          maps[512 + ((oi == 2 ? CMX_VA_CODE : oi) | (alt << 2))] = (uint16_t)((oi * (nocc - 1) + alt) * per_row);
+      std::vector<double> lut2((size_t)n_tab2, 0.0);
+      std::vector<int> occ_n(n_act);
+      for (int oi = 0; oi < nocc; ++oi)
+        for (int alt = 0; alt < nocc - 1; ++alt) {
+          int of = oi + 1 + alt;
+          if (of >= nocc) of -= nocc;
+          const size_t row = (size_t)(oi * (nocc - 1) + alt) * per_row;
+          for (int nV1 = 0; nV1 <= z1; ++nV1)
+            for (int nB1 = 0; nB1 + nV1 <= z1; ++nB1)
+              for (int nV2 = 0; nV2 <= z2; ++nV2)
+                for (int nB2 = 0; nB2 + nV2 <= z2; ++nB2) {
+                  int seen[2] = {0, 0};
+                  for (int a = 0; a < n_act; ++a) {
+                    const bool first = (cls[a] == c1);
+                    const int nB = first ? nB1 : nB2, nV = first ? nV1 : nV2;
+                    const int q = seen[first ? 0 : 1]++;
+                    occ_n[a] = (q < nB) ? 1 : ((q < nB + nV) ? 2 : 0);
+                  }
+                  volatile double dE = psP0[(size_t)oi * mo + of];
+                  for (int a = 0; a < n_act; ++a) dE = dE + psV[(((size_t)a * mo + oi) * mo + of) * mo + occ_n[a]];
+                  lut2[row + (size_t)tri(z1, nB1, nV1) * n2 + tri(z2, nB2, nV2)] = dE;
+                }
+        }
+      if ((rc = to_device(lut2, &P.d_pair2_dE))) return rc;
+      if ((rc = to_device(maps, &P.d_maps2))) return rc;
+      CMX_CUDA(cudaMalloc((void **)&P.d_tab2, sizeof(uint32_t) * n_tab2 * s->n_replicas));
+      CMX_CUDA(cudaMalloc((void **)&P.d_thr_lo2, sizeof(uint32_t) * n_tab2 * s->n_replicas));
+      CMX_CUDA(cudaMalloc((void **)&P.d_dEpot2, sizeof(double) * n_tab2 * s->n_replicas));
+      P.nocc = nocc;
+      P.z = z1;
+      P.z2 = z2;
+      P.mask = kMaskFcc1NN;
+      P.mask2 = kMaskFcc2NN;
+      int q1 = 0, q2 = 0;
+      for (int a = 0; a < n_act; ++a) {
+        const int32_t *o = &t->nbr[4 * ps_act_n[a]];
+        int32_t *dst = (cls[a] == c1) ? &P.shell[3 * q1++] : &P.shell2[3 * q2++];
+        dst[0] = o[0];
+        dst[1] = o[1];
+        dst[2] = o[2];
+      }
+      P.n_tab2 = n_tab2;
+      P.pair2 = true;
+      P.rng16 = true;  // the pair-sum and term-list evaluators of this state mirror the kernel's random bits
+    }
+  }
   P.thr_dirty = true;
   if (P.pair_lut) return cmx_plan_energy(s);
   return CMX_OK;
@@ -1265,16 +1422,6 @@ static int ensure_partials(cmx_state *s, int blocks) {
   P.part_blocks = blocks;
   return CMX_OK;
 }
-
-// FCC nearest-neighbor shell in CASM's standard primitive cell
-// (offsets of m_orbit_site_neighborhood[3], FCC default clexulator :404-414)
-constexpr uint32_t mbit(int dx, int dy, int dz) {
-  return 1u << ((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
-}
-constexpr uint32_t kMaskFcc1NN =
-    mbit(-1, 0, 0) | mbit(-1, 0, 1) | mbit(-1, 1, 0) | mbit(0, -1, 0) | mbit(0, -1, 1) |
-    mbit(0, 0, -1) | mbit(0, 0, 1) | mbit(0, 1, -1) | mbit(0, 1, 0) | mbit(1, -1, 0) |
-    mbit(1, 0, -1) | mbit(1, 0, 0);
 
 template <int NOCC, int MINB>
 static void launch_pair16(const Pair16Args &a, dim3 grid, cudaStream_t st, bool fcc, bool accum) {
@@ -1315,10 +1462,16 @@ static bool use_pair(const cmx_state *s) {
 // point + pair bases the pair-LUT path does not take (several neighbor classes, several
 // sublattices, box shapes): per-neighbor tables, one site per thread.  Either generic flag
 // selects the term-list evaluators instead (the cross-check of this one).
-bool cmx_use_pair_sum(const cmx_state *s) {
+static bool pair_sum_allowed(const cmx_state *s) {
   return s->plan.pair_sum && !use_pair(s) &&
          !(s->sweep_flags & (CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_THREAD_GENERIC));
 }
+// two neighbor classes on x4-interleaved rows: the colour-pass kernel with the two-class count
+// table, unless a flag asks for one of the evaluators it is cross-checked against
+static bool use_pair2(const cmx_state *s) {
+  return s->plan.pair2 && pair_sum_allowed(s) && !(s->sweep_flags & CMX_SWEEP_PAIR_SUM);
+}
+bool cmx_use_pair_sum(const cmx_state *s) { return pair_sum_allowed(s) && !use_pair2(s); }
 static bool use_stream(const cmx_state *s) { return use_pair(s) && s->plan.stream; }
 
 static int sweep_blocks_per_replica(uint32_t items, int n_replicas) {
@@ -1340,6 +1493,19 @@ static int pair_tables(cmx_state *s) {
                                              (int)exs, P.n_tab, P.d_tab, P.d_thr_lo, P.d_dEpot);
   dim3 grid24((P.n_tab24 + 127) / 128, s->n_replicas);
   k_build_tab24<<<grid24, 128, 0, s->stream>>>(P.d_tab, P.nocc, P.n_tab, P.n_tab24, P.d_tab24);
+  CMX_CUDA(cudaGetLastError());
+  P.thr_dirty = false;
+  return CMX_OK;
+}
+
+static int pair2_tables(cmx_state *s) {
+  SweepPlan &P = s->plan;
+  const DevTables &T = s->t->d;
+  if (!P.thr_dirty) return CMX_OK;
+  const size_t exs = (size_t)T.n_sublat * T.max_occ * T.max_occ;
+  dim3 grid((P.n_tab2 + 127) / 128, s->n_replicas);
+  k_build_tab2<<<grid, 128, 0, s->stream>>>(P.d_pair2_dE, P.n_tab2, P.n_tab2 / (P.nocc * (P.nocc - 1)), P.nocc, T.max_occ,
+                                            s->d_beta, s->d_exch, (int)exs, P.d_tab2, P.d_thr_lo2, P.d_dEpot2);
   CMX_CUDA(cudaGetLastError());
   P.thr_dirty = false;
   return CMX_OK;
@@ -1426,6 +1592,18 @@ static PassKernel pass_kernel(const cmx_state *s, bool accum, size_t *smem) {
   return full ? pass_kernel_nmf<2, 0u, true>(accum, slab) : pass_kernel_nmf<2, 0u, false>(accum, slab);
 }
 
+// two neighbor classes (FCC 1NN + 2NN, ternary)
+static PassKernel pass2_kernel(const cmx_state *s, bool accum, size_t *smem) {
+  const uint32_t rpw = 32u / ((uint32_t)s->g.N0 / 16u);
+  const bool full = ((uint32_t)s->g.N1 / 2u) % rpw == 0;
+  *smem = (size_t)s16_tab2_bytes((uint32_t)s->plan.n_tab2) + 8u * s16_n_slots(kMaskFcc1NN | kMaskFcc2NN) * CMX_S16_SLOT;
+  if (full)
+    return accum ? k_sweep_pass16<3, kMaskFcc1NN, true, false, true, kMaskFcc2NN>
+                 : k_sweep_pass16<3, kMaskFcc1NN, false, false, true, kMaskFcc2NN>;
+  return accum ? k_sweep_pass16<3, kMaskFcc1NN, true, false, false, kMaskFcc2NN>
+               : k_sweep_pass16<3, kMaskFcc1NN, false, false, false, kMaskFcc2NN>;
+}
+
 // x4-interleaved rows: colour passes with grid barriers (k_sweep_pass16, the default: measured
 // faster than the streaming kernel on every configuration of this round) unless
 // CMX_SWEEP_STREAM asks for the barrier-free streaming kernel.  Slab states decide once (they
@@ -1443,8 +1621,9 @@ static int stream_geometry(cmx_state *s) {
   const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
   const bool slab = s->p2p && g.halo;
   size_t smem = 0;
-  const void *kern = use_pass(s) ? (const void *)pass_kernel(s, accum, &smem)
-                                      : (const void *)stream_kernel(s, accum, slab, &smem);
+  const void *kern = use_pair2(s)  ? (const void *)pass2_kernel(s, accum, &smem)
+                     : use_pass(s) ? (const void *)pass_kernel(s, accum, &smem)
+                                   : (const void *)stream_kernel(s, accum, slab, &smem);
   CMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0, dev = 0, sms = 0, can = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess) per_sm = 0;
@@ -1696,6 +1875,8 @@ static int sweep_stream(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_
   a.peer_done_up = s->peer_done_up;
   a.push = slab ? 1 : 0;
   a.fail = s->d_sig + 3;
+  a.n_tab2 = 0;
+  a.maps2 = nullptr;
   static const int dbg_env = env_int("CMX_STREAM_DEBUG", 0);
   a.dbg = (uint32_t)dbg_env;
   dim3 grid((unsigned)P.stream_blocks, (unsigned)s->n_replicas);
@@ -1795,11 +1976,12 @@ static int l2_persist_lattice(cmx_state *s) {
 static int sweep_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t n_sweeps, int kgroup) {
   SweepPlan &P = s->plan;
   const Geom &g = s->g;
-  int rc = pair_tables(s);
+  const bool two = use_pair2(s);
+  int rc = two ? pair2_tables(s) : pair_tables(s);
   if (rc) return rc;
   const bool accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) != 0;
   size_t smem = 0;
-  PassKernel kern = pass_kernel(s, accum, &smem);
+  PassKernel kern = two ? pass2_kernel(s, accum, &smem) : pass_kernel(s, accum, &smem);
   S16Args a;
   memset(&a, 0, sizeof(a));
   a.occ = s->d_occ;
@@ -1811,9 +1993,11 @@ static int sweep_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t 
   a.J = (uint32_t)g.N1 / 2;
   const uint32_t rpw = 32u / a.W;
   a.tpu = (a.J + rpw - 1) / rpw;
-  a.tab24 = P.d_tab24;
-  a.thr_lo = P.d_thr_lo;
-  a.dEpot = P.d_dEpot;
+  a.tab24 = two ? P.d_tab2 : P.d_tab24;
+  a.thr_lo = two ? P.d_thr_lo2 : P.d_thr_lo;
+  a.dEpot = two ? P.d_dEpot2 : P.d_dEpot;
+  a.n_tab2 = two ? (uint32_t)P.n_tab2 : 0u;
+  a.maps2 = two ? P.d_maps2 : nullptr;
   a.part_acc = P.d_part_acc;
   a.part_dE = P.d_part_dE;
   a.part_stride = (uint32_t)P.part_blocks;
@@ -1936,7 +2120,7 @@ static int sweep_once(cmx_state *s, uint64_t seed, int64_t sweep, int kgroup,
   a.rng16 = P.rng16 ? 1 : 0;
   a.accum = (s->sweep_flags & CMX_SWEEP_DE_SUM) ? 1 : 0;
   dim3 grid(P.part_blocks, s->n_replicas);
-  const bool pair_sum = cmx_use_pair_sum(s);
+  const bool pair_sum = pair_sum_allowed(s);  // (a two-class state reaches this function through cmx_sgc_sweep_kgroup only)
   const bool warp = cmx_use_warp_generic(s) && !use_pair(s) && !pair_sum;
   const size_t stage_bytes = (size_t)(P.stage_max + 1) * 8 * sizeof(double);
   PairSumArgs ps;
@@ -2033,7 +2217,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   SweepPlan &P = s->plan;
   int blocks;
-  if (use_stream(s)) {
+  if (use_stream(s) || use_pair2(s)) {
     if (P.stream_capacity < 0 || P.stream_blocks == 0) {
       int rc = stream_geometry(s);
       if (rc) return rc;
@@ -2048,7 +2232,7 @@ static int sweep_prepare(cmx_state *s, const char *who) {
       items = (n_rows + RB - 1) / RB * 256;
     } else {
       items = (uint32_t)(s->g.N0 / P.S[0]) * (s->g.N1 / P.S[1]) * (s->g.N2 / P.S[2]);
-      if (cmx_use_warp_generic(s) && !cmx_use_pair_sum(s))
+      if (cmx_use_warp_generic(s) && !pair_sum_allowed(s))
         items = (uint32_t)std::min<uint64_t>((uint64_t)items * 32u, 0xFFFFFF00u);  // a warp per site
     }
     blocks = sweep_blocks_per_replica(items, s->n_replicas);
@@ -2066,7 +2250,8 @@ static int sweep_prepare(cmx_state *s, const char *who) {
 
 extern "C" int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags) {
   if (!s) return invalid("cmx_state_set_sweep_flags: null state");
-  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_THREAD_GENERIC | CMX_SWEEP_STREAM))
+  if (flags & ~(uint32_t)(CMX_SWEEP_DE_SUM | CMX_SWEEP_FORCE_GENERIC | CMX_SWEEP_THREAD_GENERIC | CMX_SWEEP_STREAM |
+                          CMX_SWEEP_PAIR_SUM))
     return invalid("cmx_state_set_sweep_flags: unknown flag");
   s->sweep_flags = flags;
   s->plan.part_blocks = 0;      // the grid may change with the evaluator
@@ -2125,7 +2310,9 @@ int cmx_sgc_sweep_enqueue(cmx_state *s, uint64_t seed, int64_t first_sweep, int6
   int rc = sweep_prepare(s, "cmx_sgc_sweep");
   if (rc) return rc;
   if (s->g.halo) return invalid("cmx_sgc_sweep: slab states are driven by cmx_sgc_sweep_kgroup / cmx_sgc_sweep_slab");
-  if (use_stream(s)) {
+  if (use_pair2(s)) {
+    if (n_sweeps > 0 && (rc = sweep_pass(s, seed, first_sweep, n_sweeps, -1))) return rc;
+  } else if (use_stream(s)) {
     if (n_sweeps > 0) {
       rc = use_pass(s) ? sweep_pass(s, seed, first_sweep, n_sweeps, -1) : sweep_stream(s, seed, first_sweep, n_sweeps, -1);
       if (rc) return rc;
@@ -2161,7 +2348,9 @@ extern "C" int cmx_sgc_sweep_kgroup(cmx_state *s, uint64_t seed, int64_t sweep,
   int rc = sweep_prepare(s, "cmx_sgc_sweep_kgroup");
   if (rc) return rc;
   if (kgroup < -1 || kgroup >= s->plan.S[2]) return invalid("cmx_sgc_sweep_kgroup: bad kgroup");
-  if (use_stream(s)) {
+  if (use_pair2(s)) {
+    rc = sweep_pass(s, seed, sweep, 1, kgroup);
+  } else if (use_stream(s)) {
     if (s->p2p && s->g.halo && kgroup >= 0)
       return invalid("cmx_sgc_sweep_kgroup: peer-attached slabs sweep with cmx_sgc_sweep_slab");
     rc = use_pass(s) ? sweep_pass(s, seed, sweep, 1, kgroup) : sweep_stream(s, seed, sweep, 1, kgroup);
@@ -2203,7 +2392,7 @@ extern "C" int cmx_sweep_info(const cmx_state *s, char *name, size_t name_cap,
     cmx_set_error("cmx_sweep_info: no sweep plan");
     return CMX_ERR_STATE;
   }
-  const char *nm = use_pair(s) ? "pair_lut" : cmx_use_pair_sum(s) ? "pair_sum" : "generic";
+  const char *nm = use_pair(s) ? "pair_lut" : use_pair2(s) ? "pair_lut2" : cmx_use_pair_sum(s) ? "pair_sum" : "generic";
   if (name && name_cap) {
     std::strncpy(name, nm, name_cap - 1);
     name[name_cap - 1] = 0;
@@ -2235,7 +2424,7 @@ extern "C" int cmx_sweep_launches(const cmx_state *s, int32_t *per_sweep) {
     cmx_set_error("cmx_sweep_launches: no sweep plan");
     return CMX_ERR_STATE;
   }
-  *per_sweep = use_stream(s) ? 0 : (use_pair(s) ? 4 : s->plan.n_colours);  // 0: one launch per call
+  *per_sweep = (use_stream(s) || use_pair2(s)) ? 0 : (use_pair(s) ? 4 : s->plan.n_colours);  // 0: one launch per call
   return CMX_OK;
 }
 
@@ -2272,6 +2461,10 @@ struct DebugDeArgs {
   // pair sum
   const double *ps_V, *ps_P0;
   const int32_t *act_beg, *act_n;
+  // two-class count table
+  int z2;
+  int32_t shell2[48];
+  const uint16_t *maps2;
 };
 __device__ __forceinline__ bool debug_site(const DebugDeArgs &a, long long q, int &b, int &i, int &j, int &k) {
   const Geom &g = a.g;
@@ -2285,7 +2478,8 @@ __device__ __forceinline__ bool debug_site(const DebugDeArgs &a, long long q, in
   k = (int)(rest / g.N1);
   return true;
 }
-// mode 0: pair-LUT table entry; 1: folded term lists, one thread per proposal; 2: pair-sum tables
+// mode 0: pair-LUT table entry; 1: folded term lists, one thread per proposal; 2: pair-sum tables;
+// 3: entry of the two-class count table (a.dEpot = the replica's dEpot2)
 __global__ void k_sweep_debug_de(DebugDeArgs a, int mode) {
   const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= a.n) return;
@@ -2307,6 +2501,24 @@ __global__ void k_sweep_debug_de(DebugDeArgs a, int mode) {
     int alt = of - oi - 1;
     if (alt < 0) alt += a.nocc;
     a.out[q] = (of == oi || alt >= a.nocc - 1) ? nan("") : a.dEpot[cnt | ((oi | (alt << 2)) << 8)];
+    return;
+  }
+  if (mode == 3) {
+    int cnt1 = 0, cnt2 = 0;
+    for (int n = 0; n < a.z + a.z2; ++n) {
+      const int32_t *o = (n < a.z) ? &a.shell[3 * n] : &a.shell2[3 * (n - a.z)];
+      int ii = i + o[0], jj = j + o[1], kk = k + o[2];
+      cmx_wrap_cell(g, ii, jj, kk);
+      const int code = (int)(uint8_t)a.occ[cmx_site_offset(g, 0, ii, jj, kk)];
+      if (n < a.z) cnt1 += code;
+      else cnt2 += code;
+    }
+    int alt = of - oi - 1;
+    if (alt < 0) alt += a.nocc;
+    const uint32_t sab = (uint32_t)((oi == 2 ? CMX_VA_CODE : oi) | (alt << 2));
+    a.out[q] = (of == oi || alt >= a.nocc - 1)
+                   ? nan("")
+                   : a.dEpot[(uint32_t)a.maps2[cnt1] + (uint32_t)a.maps2[256 + cnt2] + (uint32_t)a.maps2[512 + sab]];
     return;
   }
   const int mo = T.max_occ;
@@ -2401,7 +2613,14 @@ extern "C" int cmx_sweep_debug_delta_e(cmx_state *s, int32_t replica, int64_t n,
   a.ps_P0 = P.d_ps_P0;
   a.act_beg = P.d_act_beg;
   a.act_n = P.d_act_n;
-  if (cmx_use_pair_sum(s)) {
+  a.z2 = P.z2;
+  for (int q = 0; q < 48; ++q) a.shell2[q] = P.shell2[q];
+  a.maps2 = P.d_maps2;
+  if (use_pair2(s)) {
+    if ((rc = pair2_tables(s))) return rc;
+    a.dEpot = P.d_dEpot2 + (size_t)replica * P.n_tab2;
+    k_sweep_debug_de<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(a, 3);
+  } else if (cmx_use_pair_sum(s)) {
     k_sweep_debug_de<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(a, 2);
   } else if (use_pair(s)) {
     if (P.z > 16) return invalid("cmx_sweep_debug_delta_e: neighbor class larger than 16");

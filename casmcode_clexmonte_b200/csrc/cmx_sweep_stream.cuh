@@ -174,11 +174,17 @@ struct S16Args {
   uint32_t *ticket;  // [replica] next group to hand out (dynamic assignment), or null: warp w takes w, w + n_warps, ...
   unsigned long long *fail;  // set when a dependency never arrives
   uint32_t dbg;  // CMX_STREAM_DEBUG (diagnostics only): 2 no release fence (WRONG), 4 no dependency checks (WRONG)
+  // two neighbor classes (k_sweep_pass16 with MASK2_CT): tab24 / thr_lo / dEpot then hold n_tab2
+  // entries per replica in the COMPACT index of s16_update_word2, maps2 = its three index maps
+  uint32_t n_tab2;
+  const uint16_t *maps2;  // [256] class-1 sum -> i1 * n2 | [256] class-2 sum -> i2 | [32] code | alt << 2 -> row offset
 };
+#define CMX_S16_MAPS 544u  // uint16 entries of the index maps
 
 // per-thread constants
 struct S16Lane {
   uint32_t tab;  // shared-memory address of the acceptance table
+  uint32_t maps; // shared-memory address of the index maps (two neighbor classes)
   const double *dEpot;
   const uint32_t *thr_lo;
   int8_t *base;  // replica base (includes the ghost layers)
@@ -255,6 +261,78 @@ __device__ __noinline__ void s16_ties(S16Tie *t, uint32_t tab, const uint32_t *_
   }
 }
 
+// ---- two neighbor classes (the reference's dense FCC ECI: 1NN + 2NN pairs) -------------------
+// dE depends on (occupant, proposal, class-1 species counts, class-2 species counts).  The two
+// byte-lane sums cnt1, cnt2 (n_B + 18 n_Va each) go through small index maps to the compact
+// entry  idx = row(code, alt) + i1(cnt1) n2 + i2(cnt2)  of a table of 6 x n1 x n2 entries
+// (FCC: 6 x 91 x 28 = 15 288, 61 KB of shared memory); entry, compare and merge are the
+// one-class path's.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int NOCC>
+__device__ __forceinline__ void s16_update_word2(uint32_t cnt1, uint32_t cnt2, uint32_t &C, uint32_t R0, uint32_t R1,
+                                                 uint32_t tab, uint32_t maps, uint32_t &rj, uint32_t &tmin,
+                                                 uint32_t (&idx)[4]) {
+  uint32_t SA = C;
+  if (NOCC == 3) {
+    const uint32_t am = prmt_s<0xFDB9u>(R0, R1);
+    SA = C | (am & 0x04040404u);
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const uint32_t o1 = (b == 0) ? ((cnt1 << 1) & 0x1FEu) : ((cnt1 >> (8 * b - 1)) & 0x1FEu);
+    const uint32_t o2 = (b == 0) ? ((cnt2 << 1) & 0x1FEu) : ((cnt2 >> (8 * b - 1)) & 0x1FEu);
+    const uint32_t os = (b == 0) ? ((SA << 1) & 0x3Eu) : ((SA >> (8 * b - 1)) & 0x3Eu);
+    idx[b] = lds_u16(maps + o1) + lds_u16(maps + 512u + o2) + lds_u16(maps + 1024u + os);
+  }
+  const uint32_t e0 = lds_u32(tab + 4u * idx[0]);
+  const uint32_t e1 = lds_u32(tab + 4u * idx[1]);
+  const uint32_t e2 = lds_u32(tab + 4u * idx[2]);
+  const uint32_t e3 = lds_u32(tab + 4u * idx[3]);
+  const uint32_t T01 = __byte_perm(e0, e1, 0x5410u);
+  const uint32_t T23 = __byte_perm(e2, e3, 0x5410u);
+  const uint32_t D0 = (R0 | 0x80008000u) - T01;
+  const uint32_t D1 = (R1 | 0x80008000u) - T23;
+  tmin = min_s16x2(tmin, min_s16x2(D0, D1));
+  rj = prmt_s<0xFDB9u>(D0, D1);  // bit 15 of a half: u15 >= thr
+  const uint32_t P = __byte_perm(__byte_perm(e0, e1, 0x0062u), __byte_perm(e2, e3, 0x0062u), 0x5410u);
+  C = (C & rj) | (P & ~rj);
+}
+struct S16Tie2 {
+  uint32_t cnt1[2], cnt2[2], C[2], rj[2], R[4];
+  double e_sum;
+};
+template <int NOCC, bool ACCUM>
+__device__ __noinline__ void s16_ties2(S16Tie2 *t, uint32_t tab, const uint16_t *__restrict__ maps,
+                                       const uint32_t *__restrict__ thr_lo, const double *__restrict__ dEpot,
+                                       uint32_t gid, uint32_t r, uint32_t sweep_lo, uint32_t ctr, uint32_t k0,
+                                       uint32_t k1) {
+  const Philox lo0 = philox_sweep(gid, r, sweep_lo, ctr | 1u, k0, k1);
+  const Philox lo1 = philox_sweep(gid, r, sweep_lo, ctr | 2u, k0, k1);
+  for (int h = 0; h < 2; ++h) {
+    for (int b = 0; b < 4; ++b) {
+      if (!((t->rj[h] >> (8 * b)) & 1u)) continue;  // accepted by the main path: the lane holds the NEW code
+      const uint32_t R = t->R[2 * h + (b >> 1)];
+      const uint32_t field = (b & 1) ? (R >> 16) : (R & 0xFFFFu);
+      const uint32_t sab = ((t->C[h] >> (8 * b)) & 0xFFu) | ((NOCC == 3) ? ((field >> 15) << 2) : 0u);
+      const uint32_t idx = (uint32_t)maps[(t->cnt1[h] >> (8 * b)) & 0xFFu] +
+                           (uint32_t)maps[256u + ((t->cnt2[h] >> (8 * b)) & 0xFFu)] + (uint32_t)maps[512u + (sab & 31u)];
+      const uint32_t e = lds_u32(tab + 4u * idx);
+      if ((field & 0x7FFFu) != (e & 0xFFFFu)) continue;
+      const int q = 4 * h + b;  // target site of the chunk's colour, 0..7
+      const uint32_t w32 = (q < 4) ? lo0.c[q & 3] : lo1.c[q & 3];
+      if (w32 < thr_lo[idx]) {
+        t->C[h] = (t->C[h] & ~(0xFFu << (8 * b))) | (((e >> 16) & 0xFFu) << (8 * b));
+        t->rj[h] &= ~(0xFFu << (8 * b));
+        if (ACCUM) t->e_sum += dEpot[idx];
+      }
+    }
+  }
+}
+
 // stage the rows a row-step reads into this lane's shared-memory slots (asynchronous
 // 16-byte copies, L2 only): slot n = n-th row of the mask in (dz, dy) order.  pc = this
 // lane's chunk of the target row j; dkm / dkp = byte offsets to the layers below / above
@@ -289,10 +367,14 @@ __device__ __forceinline__ int8_t *s16_chunk_ptr(const int8_t *base, uint32_t t)
   return reinterpret_cast<int8_t *>(p);
 }
 
-template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, typename Hook>
+// MASK2_CT != 0: a second neighbor class (compile-time offsets, none in the site's own row)
+// summed separately; the table index is then s16_update_word2's.
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, uint32_t MASK2_CT = 0u, typename Hook>
 __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, const int8_t *pbase, uint32_t pt,
                                             uint32_t gid, int32_t k, uint32_t sweep_lo, uint32_t ctr_hi, bool on,
                                             int32_t &n_acc, double &e_tot, uint32_t slots, Hook after_loads) {
+  constexpr bool TWO = MASK2_CT != 0u;
+  static_assert(!TWO || (MASK_CT != 0u && ((MASK2_CT >> 12) & 7u) == 0u), "second class: compile-time masks, no same-row neighbors");
   const Geom &g = a.g;
   const uint32_t mask = MASK_CT ? MASK_CT : a.mask;
   const uint32_t mc = (mask >> 12) & 7u;  // center row: dx = -1 / +1 bits
@@ -300,9 +382,10 @@ __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, 
   // both colours' random fields up front: two independent chains interleave
   const Philox ph0 = philox_sweep_rk(gid, r, sweep_lo, ctr_hi, a.rk);
   const Philox ph1 = philox_sweep_rk(gid, r, sweep_lo, ctr_hi | 0x100u, a.rk);
-  uint32_t C[4], T[4];
+  uint32_t C[4], T[4], T2[4] = {0, 0, 0, 0};
   {
     uint32_t A0[4] = {0, 0, 0, 0}, Am[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
+    uint32_t B0[4] = {0, 0, 0, 0}, Bm[4] = {0, 0, 0, 0}, Bp[4] = {0, 0, 0, 0};
     bool any_m = false, any_p = false;
     uint32_t n_slot = 0;
 #pragma unroll
@@ -310,8 +393,9 @@ __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, 
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy) {
         const uint32_t m3 = (mask >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
+        const uint32_t m3b = (MASK2_CT >> ((dz + 1) * 9 + (dy + 1) * 3)) & 7u;
         const bool center = (dz == 0 && dy == 0);
-        if (m3 == 0 && !center) continue;
+        if ((m3 | m3b) == 0 && !center) continue;
         const uint4 ch = lds_u128(slots + (n_slot++) * CMX_S16_SLOT);
         if (center) {
           C[0] = ch.x;
@@ -340,6 +424,26 @@ __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, 
           Ap[2] += ch.z;
           Ap[3] += ch.w;
         }
+        if (TWO) {
+          if (m3b & 2u) {
+            B0[0] += ch.x;
+            B0[1] += ch.y;
+            B0[2] += ch.z;
+            B0[3] += ch.w;
+          }
+          if (m3b & 1u) {
+            Bm[0] += ch.x;
+            Bm[1] += ch.y;
+            Bm[2] += ch.z;
+            Bm[3] += ch.w;
+          }
+          if (m3b & 4u) {
+            Bp[0] += ch.x;
+            Bp[1] += ch.y;
+            Bp[2] += ch.z;
+            Bp[3] += ch.w;
+          }
+        }
       }
     }
     after_loads();
@@ -359,13 +463,67 @@ __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, 
     T[1] = A0[1] + Am[0] + Ap[2];
     T[2] = A0[2] + Am[1] + Ap[3];
     T[3] = A0[3] + Am[2] + sp;
+    if (TWO) {
+      uint32_t sm2 = __shfl_sync(0xffffffffu, Bm[3], L.lane_l);
+      sm2 = __funnelshift_l(sm2, sm2, L.rot_l);
+      uint32_t sp2 = __shfl_sync(0xffffffffu, Bp[0], L.lane_r);
+      sp2 = __funnelshift_r(sp2, sp2, L.rot_r);
+      T2[0] = B0[0] + sm2 + Bp[1];
+      T2[1] = B0[1] + Bm[0] + Bp[2];
+      T2[2] = B0[2] + Bm[1] + Bp[3];
+      T2[3] = B0[3] + Bm[2] + sp2;
+    }
   }
   uint32_t rj[4], tmin, idx[4];
   double e_sum = 0.0;
   auto accum = [&](uint32_t rjw, const uint32_t (&ix)[4]) {
 #pragma unroll
     for (int b = 0; b < 4; ++b)
-      if (!((rjw >> (8 * b)) & 1u)) e_sum += L.dEpot[cmx_tab24_to_16(ix[b])];
+      if (!((rjw >> (8 * b)) & 1u)) e_sum += L.dEpot[TWO ? ix[b] : cmx_tab24_to_16(ix[b])];
+  };
+  // Metropolis test of one word / the rare tie path of a colour (words wa, wb), either table
+  auto update = [&](uint32_t cnt, uint32_t cnt2, uint32_t &Cw, uint32_t R0, uint32_t R1, uint32_t &rjw) {
+    if (TWO) s16_update_word2<NOCC>(cnt, cnt2, Cw, R0, R1, tab, L.maps, rjw, tmin, idx);
+    else s16_update_word<NOCC>(cnt, Cw, R0, R1, tab, rjw, tmin, idx);
+  };
+  auto ties = [&](uint32_t ca, uint32_t cb, int wa, int wb, const Philox &ph, uint32_t ctr) {
+    if (TWO) {
+      S16Tie2 t;
+      t.cnt1[0] = ca;
+      t.cnt1[1] = cb;
+      t.cnt2[0] = T2[wa];
+      t.cnt2[1] = T2[wb];
+      t.C[0] = C[wa];
+      t.C[1] = C[wb];
+      t.rj[0] = rj[wa];
+      t.rj[1] = rj[wb];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) t.R[i] = ph.c[i];
+      t.e_sum = 0.0;
+      s16_ties2<NOCC, ACCUM>(&t, tab, a.maps2, L.thr_lo, L.dEpot, gid, r, sweep_lo, ctr, a.k0, a.k1);
+      C[wa] = t.C[0];
+      C[wb] = t.C[1];
+      rj[wa] = t.rj[0];
+      rj[wb] = t.rj[1];
+      if (ACCUM) e_sum += t.e_sum;
+    } else {
+      S16Tie t;
+      t.cnt[0] = ca;
+      t.cnt[1] = cb;
+      t.C[0] = C[wa];
+      t.C[1] = C[wb];
+      t.rj[0] = rj[wa];
+      t.rj[1] = rj[wb];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) t.R[i] = ph.c[i];
+      t.e_sum = 0.0;
+      s16_ties<NOCC, ACCUM>(&t, tab, L.thr_lo, L.dEpot, gid, r, sweep_lo, ctr, a.k0, a.k1);
+      C[wa] = t.C[0];
+      C[wb] = t.C[1];
+      rj[wa] = t.rj[0];
+      rj[wb] = t.rj[1];
+      if (ACCUM) e_sum += t.e_sum;
+    }
   };
   // ---- x colour 0: words 0 and 2; their same-row neighbors are the odd words (old values)
   {
@@ -384,29 +542,12 @@ __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, 
       c2 += C[3];
     }
     tmin = 0x7FFF7FFFu;
-    s16_update_word<NOCC>(c0, C[0], ph0.c[0], ph0.c[1], tab, rj[0], tmin, idx);
+    update(c0, T2[0], C[0], ph0.c[0], ph0.c[1], rj[0]);
     if (ACCUM) accum(rj[0], idx);
-    s16_update_word<NOCC>(c2, C[2], ph0.c[2], ph0.c[3], tab, rj[2], tmin, idx);
+    update(c2, T2[2], C[2], ph0.c[2], ph0.c[3], rj[2]);
     if (ACCUM) accum(rj[2], idx);
     const uint32_t tz = tmin ^ 0x80008000u;
-    if ((tz - 0x00010001u) & ~tz & 0x80008000u) {
-      S16Tie t;
-      t.cnt[0] = c0;
-      t.cnt[1] = c2;
-      t.C[0] = C[0];
-      t.C[1] = C[2];
-      t.rj[0] = rj[0];
-      t.rj[1] = rj[2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) t.R[i] = ph0.c[i];
-      t.e_sum = 0.0;
-      s16_ties<NOCC, ACCUM>(&t, tab, L.thr_lo, L.dEpot, gid, r, sweep_lo, ctr_hi, a.k0, a.k1);
-      C[0] = t.C[0];
-      C[2] = t.C[1];
-      rj[0] = t.rj[0];
-      rj[2] = t.rj[1];
-      if (ACCUM) e_sum += t.e_sum;
-    }
+    if ((tz - 0x00010001u) & ~tz & 0x80008000u) ties(c0, c2, 0, 2, ph0, ctr_hi);
   }
   // ---- x colour 1: words 1 and 3 against the updated even words; word 4 is the (updated)
   // first word of the next chunk of the row
@@ -426,29 +567,12 @@ __device__ __forceinline__ void s16_rowstep(const S16Args &a, const S16Lane &L, 
       c3 += nb;
     }
     tmin = 0x7FFF7FFFu;
-    s16_update_word<NOCC>(c1, C[1], ph1.c[0], ph1.c[1], tab, rj[1], tmin, idx);
+    update(c1, T2[1], C[1], ph1.c[0], ph1.c[1], rj[1]);
     if (ACCUM) accum(rj[1], idx);
-    s16_update_word<NOCC>(c3, C[3], ph1.c[2], ph1.c[3], tab, rj[3], tmin, idx);
+    update(c3, T2[3], C[3], ph1.c[2], ph1.c[3], rj[3]);
     if (ACCUM) accum(rj[3], idx);
     const uint32_t tz = tmin ^ 0x80008000u;
-    if ((tz - 0x00010001u) & ~tz & 0x80008000u) {
-      S16Tie t;
-      t.cnt[0] = c1;
-      t.cnt[1] = c3;
-      t.C[0] = C[1];
-      t.C[1] = C[3];
-      t.rj[0] = rj[1];
-      t.rj[1] = rj[3];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) t.R[i] = ph1.c[i];
-      t.e_sum = 0.0;
-      s16_ties<NOCC, ACCUM>(&t, tab, L.thr_lo, L.dEpot, gid, r, sweep_lo, ctr_hi | 0x100u, a.k0, a.k1);
-      C[1] = t.C[0];
-      C[3] = t.C[1];
-      rj[1] = t.rj[0];
-      rj[3] = t.rj[1];
-      if (ACCUM) e_sum += t.e_sum;
-    }
+    if ((tz - 0x00010001u) & ~tz & 0x80008000u) ties(c1, c3, 1, 3, ph1, ctr_hi | 0x100u);
   }
   if (on) {
     if (ACCUM) e_tot += e_sum;
@@ -539,6 +663,7 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_stream16(S16Args a)
     L.r = r;
     // (opaque: the compiler would otherwise rematerialise the shared-window address at every use)
     asm volatile("mov.u32 %0, %1;" : "=r"(L.tab) : "r"((uint32_t)__cvta_generic_to_shared(sh_tab)));
+    L.maps = 0u;
     L.dEpot = a.dEpot + (size_t)r * NTAB16;
     L.thr_lo = a.thr_lo + (size_t)r * NTAB16;
     L.base = a.occ + (size_t)r * a.g.rep_stride;
@@ -940,25 +1065,41 @@ __device__ __forceinline__ void s16_issue_t(const S16Args &a, const int8_t *base
   }
 }
 
-template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, bool FULL>
-__global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, PassArgs c) {
+// dynamic shared memory of the two-class instantiation: [table n_tab2 x 4 B][index maps][row slots]
+__host__ __device__ constexpr uint32_t s16_tab2_bytes(uint32_t n_tab2) {
+  return (n_tab2 * 4u + CMX_S16_MAPS * 2u + 15u) & ~15u;
+}
+// MASK2_CT != 0: two neighbor classes (s16_update_word2; 2 blocks per SM: the second set of
+// byte-lane sums does not fit the 80-register budget of 3 blocks)
+template <int NOCC, uint32_t MASK_CT, bool ACCUM, bool SLAB, bool FULL, uint32_t MASK2_CT = 0u>
+__global__ void __launch_bounds__(256, MASK2_CT ? 2 : CMX_S16_MINB) k_sweep_pass16(S16Args a, PassArgs c) {
+  constexpr bool TWO = MASK2_CT != 0u;
+  static_assert(!TWO || !SLAB, "two neighbor classes: single-GPU boxes only");
   constexpr int NTAB = CMX_TAB24(NOCC);
   constexpr int NTAB16 = CMX_TAB16(NOCC);
-  constexpr uint32_t NSLOT = s16_n_slots(MASK_CT);
+  constexpr uint32_t NSLOT = s16_n_slots(MASK_CT | MASK2_CT);
   extern __shared__ __align__(16) unsigned char sh_dyn[];
   uint32_t *sh_tab = reinterpret_cast<uint32_t *>(sh_dyn);
-  unsigned char *sh_rows = sh_dyn + NTAB * 4;
+  unsigned char *sh_rows = sh_dyn + (TWO ? s16_tab2_bytes(a.n_tab2) : (uint32_t)NTAB * 4u);
   __shared__ long long sh_acc[8];
   __shared__ double sh_sum[8];
   const uint32_t r = blockIdx.y;
-  s16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)r * NTAB);
+  if (TWO) {
+    const uint32_t *gt = a.tab24 + (size_t)r * a.n_tab2;
+    for (uint32_t q = threadIdx.x; q < a.n_tab2; q += 256u) sh_tab[q] = gt[q];
+    uint16_t *sh_maps = reinterpret_cast<uint16_t *>(sh_tab + a.n_tab2);
+    for (uint32_t q = threadIdx.x; q < CMX_S16_MAPS; q += 256u) sh_maps[q] = a.maps2[q];
+  } else {
+    s16_load_table<NOCC>(sh_tab, a.tab24 + (size_t)r * NTAB);
+  }
   const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   S16Lane L;
   {
     L.r = r;
     asm volatile("mov.u32 %0, %1;" : "=r"(L.tab) : "r"((uint32_t)__cvta_generic_to_shared(sh_tab)));
-    L.dEpot = a.dEpot + (size_t)r * NTAB16;
-    L.thr_lo = a.thr_lo + (size_t)r * NTAB16;
+    L.maps = TWO ? L.tab + 4u * a.n_tab2 : 0u;
+    L.dEpot = a.dEpot + (size_t)r * (TWO ? a.n_tab2 : (uint32_t)NTAB16);
+    L.thr_lo = a.thr_lo + (size_t)r * (TWO ? a.n_tab2 : (uint32_t)NTAB16);
     L.base = a.occ + (size_t)r * a.g.rep_stride;
     const uint32_t Wm = a.W - 1u;
     L.c = lane & Wm;
@@ -1058,7 +1199,7 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, P
       // (cy = 0: the row below may wrap, the row above never does; cy = 1 the other way)
       const int32_t djm = CY ? -(int32_t)c.ch_row : dj_e, djp = CY ? dj_e : (int32_t)c.ch_row;
       const int32_t dkm = CZ ? -(int32_t)c.ch_layer : dk_e, dkp = CZ ? dk_e : (int32_t)c.ch_layer;
-      s16_issue_t<MASK_CT>(a, base, p.t, djm, djp, dkm, dkp, slots);
+      s16_issue_t<MASK_CT | MASK2_CT>(a, base, p.t, djm, djp, dkm, dkp, slots);
     };
     auto wait_neighbours = [&](uint32_t kk) {
       if (!ring || !epoch || kk != kk_edge) return;  // (warp-uniform: a row-step lies in one layer)
@@ -1101,8 +1242,9 @@ __global__ void __launch_bounds__(256, CMX_S16_MINB) k_sweep_pass16(S16Args a, P
           issue(nxt, dj_e, dk_e);
         }
       };
-      s16_rowstep<NOCC, MASK_CT, ACCUM, SLAB>(a, L, base, cur.t, cur.t + c.gid_off, 2 * (int32_t)cur.kk + CZ, sweep_lo,
-                                              ctr_hi, FULL ? true : cur.on, n_acc, e_tot, slots, stage_next);
+      s16_rowstep<NOCC, MASK_CT, ACCUM, SLAB, MASK2_CT>(a, L, base, cur.t, cur.t + c.gid_off, 2 * (int32_t)cur.kk + CZ,
+                                                        sweep_lo, ctr_hi, FULL ? true : cur.on, n_acc, e_tot, slots,
+                                                        stage_next);
     }
     n_acc64 += n_acc;  // (a pass adds at most 16 per row-step to the 32-bit count)
     n_acc = 0;

@@ -284,6 +284,12 @@ int cmx_counters_reset(cmx_state *s);
  * to the lanes); THREAD_GENERIC forces one site per thread (same random bits and
  * decisions; dE differs in the last bits through the summation order). */
 #define CMX_SWEEP_THREAD_GENERIC 16u
+/* Point + pair bases whose active neighbors form TWO symmetry classes (the reference's dense
+ * FCC formation_energy_eci.json: points, 1NN and 2NN pairs -- SURVEY 8d's 19-site
+ * neighbourhood) run the colour-pass kernel with a two-class count table on x4-interleaved
+ * rows (evaluator "pair_lut2"); CMX_SWEEP_PAIR_SUM selects the per-neighbor-table kernel
+ * (k_sweep_pairsum, evaluator "pair_sum") instead: same random bits, same decisions. */
+#define CMX_SWEEP_PAIR_SUM 32u
 int cmx_state_set_sweep_flags(cmx_state *s, uint32_t flags);
 /* Asynchronous forms for pipelines of independent states (each state owns a stream): the
  * upload of one job overlaps the sweeps of another and the download of a third.  Host

@@ -183,7 +183,8 @@ def _sweep_state(dev_tables, systems, case_sys, eci_key, N, T, mu, n_replicas=1,
 
 @pytest.mark.parametrize("case_sys,eci_key,N,expect", [
     ("fcc", "eci_sparse", (16, 16, 16), "pair_lut"),
-    ("fcc", "eci_full", (16, 16, 16), "pair_sum"),    # two neighbor classes: per-neighbor tables
+    ("fcc", "eci_full", (16, 16, 16), "pair_lut2"),   # two neighbor classes: two-class count table
+    ("fcc", "eci_full", (8, 8, 8), "pair_sum"),       # ... on linear rows: per-neighbor tables
     ("fcc", "eci_sparse", (12, 12, 12), "pair_sum"),  # N0 % 16 != 0: outside the pair-LUT path
     ("fcc", "eci_sparse", (64, 6, 10), "pair_lut"),
     ("zro", "eci", (8, 8, 8), "generic"),
@@ -372,6 +373,9 @@ def test_full_size_sweep_variants_agree(dev_tables, systems, N, n_replicas, n_sw
     ("fcc", "eci_sparse", (48, 8, 8), 0),                                  # pair-LUT table (block kernel, linear rows)
     ("fcc", "eci_sparse", (16, 8, 8), _capi.CMX_SWEEP_FORCE_GENERIC),      # folded terms, thread evaluator
     ("fcc", "eci_full", (8, 8, 8), 0),                                     # 1NN + 2NN pairs: pair-sum tables
+    ("fcc", "eci_full", (16, 8, 8), 0),                                    # 1NN + 2NN pairs: two-class count table
+    ("fcc", "eci_full", (32, 6, 4), 0),
+    ("fcc", "eci_full", (16, 8, 8), _capi.CMX_SWEEP_PAIR_SUM),
     ("fcc", "eci_full", (8, 8, 8), _capi.CMX_SWEEP_THREAD_GENERIC),        # the same through the term lists
     ("fcc", "eci_full", (12, 6, 10), 0),                                   # linear rows
     ("fcc", "eci_2", (8, 8, 8), 0),
@@ -497,7 +501,7 @@ def test_pair_sum_kernel_equals_term_list_kernel(dev_tables, systems, case_sys, 
     seam-free fast path and the wrapped path, both row layouts, replicas, several calls."""
     mu = [0.2, -0.1]
     sts = []
-    for flags in (0, _capi.CMX_SWEEP_THREAD_GENERIC):
+    for flags in (_capi.CMX_SWEEP_PAIR_SUM, _capi.CMX_SWEEP_THREAD_GENERIC):
         st, sysd, ex = _sweep_state(dev_tables, systems, case_sys, eci_key, N, 900.0, mu, n_replicas=n_replicas,
                                     seed=5, linear_rows=linear_rows)
         for r in range(n_replicas):
@@ -516,6 +520,60 @@ def test_pair_sum_kernel_equals_term_list_kernel(dev_tables, systems, case_sys, 
             assert ca[r].dE_sum == pytest.approx(cb[r].dE_sum, rel=1e-9, abs=1e-9)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("N,n_replicas", [
+    ((16, 8, 8), 1),       # one chunk per row: 32 rows per row-step, partial row-steps
+    ((64, 6, 4), 3),       # several replicas with different conditions (one table each)
+    ((32, 32, 6), 2),      # whole row-steps only
+    ((128, 4, 2), 1),      # the smallest box in j and k: every row on both seams
+    ((512, 8, 4), 1),      # BASELINE row length: one row per row-step
+    ((64, 2, 2), 1),       # two layers, one row per colour: the diagonal rows coincide
+    ((512, 256, 32), 1),   # every warp of a co-resident grid busy for several rounds
+])
+def test_two_class_table_kernel_equals_pair_sum_and_term_list_kernels(dev_tables, systems, N, n_replicas):
+    """The reference's dense FCC ECI (points + 1NN + 2NN pairs, SURVEY 8d's 19-site neighbourhood)
+    on x4-interleaved rows runs the colour-pass kernel with a two-class count table
+    (evaluator "pair_lut2": k_sweep_pass16 with a second byte-lane sum).  Its table entries are
+    dE values summed in the pair-sum evaluator's order, it draws the same random bits as the
+    pair-sum kernel (CMX_SWEEP_PAIR_SUM) and the term-list kernel (CMX_SWEEP_THREAD_GENERIC),
+    and must leave the SAME occupation and counters as both, call after call; a change of
+    conditions between calls rebuilds its acceptance tables."""
+    mu = [0.2, -0.1]
+    sts = []
+    for flags in (0, _capi.CMX_SWEEP_PAIR_SUM, _capi.CMX_SWEEP_THREAD_GENERIC):
+        st, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_full", N, 900.0, mu, n_replicas=n_replicas, seed=5)
+        for r in range(n_replicas):
+            st.set_conditions(700.0 + 250.0 * r, ex, r)
+        st.set_sweep_flags(flags | _capi.CMX_SWEEP_DE_SUM)
+        sts.append(st)
+    a, b, c = sts
+    assert [x.sweep_info()["evaluator"] for x in sts] == ["pair_lut2", "pair_sum", "generic"]
+    assert a.sweep_info()["one_launch_per_call"]
+    ex2 = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [-0.3, 0.25], sysd["n_species"])
+    for call in range(4):
+        if call == 2:   # new T and mu on every state: the acceptance tables must follow
+            for st in sts:
+                for r in range(n_replicas):
+                    st.set_conditions(1100.0 - 150.0 * r, ex2, r)
+        cnts = [st.sgc_sweep(3, seed=21, first_sweep=3 * call) for st in sts]
+        for r in range(n_replicas):
+            occ_a = a.download_occ(r)
+            for name, st, cn in (("pair_sum", b, cnts[1]), ("generic", c, cnts[2])):
+                diff = int((occ_a != st.download_occ(r)).sum())
+                assert diff == 0, f"call {call}, replica {r}: {diff} sites differ from the {name} kernel"
+                assert (cnts[0][r].n_attempt, cnts[0][r].n_accept) == (cn[r].n_attempt, cn[r].n_accept)
+                assert cnts[0][r].dE_sum == pytest.approx(cn[r].dE_sum, rel=1e-9, abs=1e-9)
+            assert 0 < cnts[0][r].n_accept < cnts[0][r].n_attempt
+    # without the dE sum (the instantiation the benchmark runs) the trajectory is the same
+    a.set_sweep_flags(0)
+    b.set_sweep_flags(_capi.CMX_SWEEP_PAIR_SUM)
+    ca, cb = a.sgc_sweep(2, seed=22), b.sgc_sweep(2, seed=22)
+    for r in range(n_replicas):
+        assert (a.download_occ(r) == b.download_occ(r)).all()
+        assert ca[r].n_accept == cb[r].n_accept and ca[r].dE_sum == 0.0
+    for st in sts:
+        st.close()
 
 
 @pytest.mark.parametrize("T", [500.0, 900.0, 1500.0])

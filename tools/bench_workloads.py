@@ -101,28 +101,36 @@ def c2():
 def c3full():
     """BASELINE configs[2] with ALL nine functions of the FCC basis selected (constant, points,
     1NN and 2NN pairs -- the 19-site neighbourhood SURVEY section 8d quotes; coefficient values
-    of the golden fixture `eci_full`): two neighbour classes, so outside the pair-LUT fast path
-    -- the pair-sum evaluator runs (per-neighbor tables, one site per thread)."""
+    of the golden fixture `eci_full`): two neighbour classes.  Default evaluator: the colour-pass
+    kernel with the two-class count table ("pair_lut2"); beside it the per-neighbor-table kernel
+    it replaced (CMX_SWEEP_PAIR_SUM, one site per thread)."""
     sysd = SYS["fcc"]
     t = tables("fcc_default")
     for N in (256, 512):
-        st = _capi.State(t, (N, N, N), 1)
-        st.set_eci(sysd["eci_full"]["index"], sysd["eci_full"]["value"])
-        st.set_conditions(800.0, semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], (0.0, 0.0), 3))
-        st.randomize(7)
-        st.sgc_sweep(2, seed=1)
-        S = 5
-        ms, cnt = timed(st, lambda: st.sgc_sweep(S, seed=1, first_sweep=2))
-        rate = S * N ** 3 / (ms * 1e-3)
-        info = st.sweep_info()
-        emit(workload=f"c3 all functions: FCC A-B-Va SGC, {N}^3, points + 1NN + 2NN pairs (19-site neighbourhood)",
-             metric="attempted MC steps/s", value=rate, ms=ms, sweeps=S, evaluator=info.get("evaluator"),
-             bytes_per_step_l2=info.get("bytes_per_step"), flops_per_step=info.get("flops_per_step"),
-             roofline={"bound": "issue (L1 gather + FP64 adds)", "achieved": info.get("bytes_per_step") * rate / 1e9,
-                       "unit": "GB/s of neighborhood gather through L1", "hbm_frac_at_2B_per_step": 2.0 * rate / 1e9 / HBM,
-                       "note": "2 B per step at HBM; the pair-sum evaluator is issue bound (20 B per step through L1/L2, ~550 instructions)"},
-             accept_rate=cnt[0].n_accept / cnt[0].n_attempt)
-        st.close()
+        for flags in (0, _capi.CMX_SWEEP_PAIR_SUM):
+            st = _capi.State(t, (N, N, N), 1)
+            st.set_eci(sysd["eci_full"]["index"], sysd["eci_full"]["value"])
+            st.set_conditions(800.0, semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], (0.0, 0.0), 3))
+            st.set_sweep_flags(flags)
+            st.randomize(7)
+            st.sgc_sweep(2, seed=1)
+            S = 5 if flags else 10
+            ms, cnt = timed(st, lambda: st.sgc_sweep(S, seed=1, first_sweep=2))
+            rate = S * N ** 3 / (ms * 1e-3)
+            info = st.sweep_info()
+            two = info.get("evaluator") == "pair_lut2"
+            emit(workload=f"c3 all functions: FCC A-B-Va SGC, {N}^3, points + 1NN + 2NN pairs (19-site neighbourhood)",
+                 metric="attempted MC steps/s", value=rate, ms=ms, sweeps=S, evaluator=info.get("evaluator"),
+                 kernel="k_sweep_pass16<3, fcc 1NN, fcc 2NN>" if two else "k_sweep_pairsum",
+                 launches=1 if two else 8 * S,
+                 bytes_per_step_l2=info.get("bytes_per_step"), flops_per_step=info.get("flops_per_step"),
+                 roofline={"bound": "hbm", "achieved": 2.0 * rate / 1e9, "peak": HBM, "unit": "GB/s",
+                           "frac": 2.0 * rate / 1e9 / HBM,
+                           "note": ("2 B per step at HBM, 20 B per step through L2 / shared memory; issue bound "
+                                    "(about 28 instructions per step: two byte-lane sums, three index-map lookups and one table lookup per site)") if two else
+                                   "2 B per step at HBM; the pair-sum evaluator is issue bound (20 B per step through L1/L2, ~550 instructions)"},
+                 accept_rate=cnt[0].n_accept / cnt[0].n_attempt)
+            st.close()
     t.close()
 
 
