@@ -51,7 +51,8 @@ from casmcode_clexmonte_b200.clocks import ClockSampler  # noqa: E402
 # ---------------------------------------------------------------------------
 # reference CPU path (oracle/_ref), one chain per core
 # ---------------------------------------------------------------------------
-def cpu_reference_rate(seconds_budget: float = 12.0, box: int = 64, threads: int | None = None) -> dict:
+def cpu_reference_rate(seconds_budget: float = 12.0, box: int = 64, threads: int | None = None,
+                       eci_key: str = "eci_sparse") -> dict:
     """Sequential semi-grand Metropolis with the reference's generated kernels
     (methods/occupation_metropolis.hh:92-120 restated in oracle/harness.cpp), one
     independent chain per host core, each on a `box`^3 periodic sample of the
@@ -61,7 +62,7 @@ def cpu_reference_rate(seconds_budget: float = 12.0, box: int = 64, threads: int
     if not O.available("fcc_default"):
         raise RuntimeError("oracle/_ref not built")
     sysd = load_system()
-    eci = sysd["eci_sparse"]
+    eci = sysd[eci_key]
     prim = dict(sublat_to_asym=sysd["sublat_to_asym"], occ_to_species=sysd["occ_to_species"],
                 n_species=3, Rt=np.array(sysd["axes"]["Rt"]))
     cores = threads or len(os.sched_getaffinity(0))
@@ -378,6 +379,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"],
                     help="c3 (default, the headline): 512^3 box, slabs over the GPUs; c2: 64-replica (mu, T) grid of "
                          "128^3 boxes dealt over the GPUs; c5: 4096 KMC trajectories dealt over the GPUs")
+    ap.add_argument("--eci", default="sparse", choices=["sparse", "full"],
+                    help="c3 only: the reference's sparse FCC ECI (points + 1NN pairs: the headline) or all nine functions "
+                         "(points + 1NN + 2NN pairs, SURVEY 8d's 19-site neighbourhood: the two-class count table; one GPU)")
     ap.add_argument("--box", type=int, default=N_BOX)
     ap.add_argument("--layers", type=int, default=0, help="tuning runs: N2 of a (box, box, layers) supercell on one GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -388,8 +392,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = (f"FCC A-B-Va semi-grand canonical, {args.box}^3 primitive supercell, shipped sparse ECI "
-                f"(points+1NN pairs), T={TEMPERATURE:g} K, param_chem_pot={list(MU)}")
+    eci_key = "eci_full" if args.eci == "full" else "eci_sparse"
+    eci_text = ("all nine functions of the FCC basis (points + 1NN + 2NN pairs, 19-site neighbourhood)" if args.eci == "full"
+                else "shipped sparse ECI (points+1NN pairs)")
+    workload = (f"FCC A-B-Va semi-grand canonical, {args.box}^3 primitive supercell, {eci_text}, "
+                f"T={TEMPERATURE:g} K, param_chem_pot={list(MU)}")
     config = {"workload": workload, "sites": args.box ** 3, "sweeps_per_step": SWEEPS_PER_STEP,
               "l2_policy": "inputs larger than L2 (134 MB lattice, streamed once per sweep and direction)",
               "parallelism": f"slab{world}" if world > 1 else "single"}
@@ -397,7 +404,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        res = cpu_reference_rate(seconds_budget=max(5.0, min(60.0, 4.0 * args.steps)))
+        res = cpu_reference_rate(seconds_budget=max(5.0, min(60.0, 4.0 * args.steps)), eci_key=eci_key)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
@@ -418,11 +425,13 @@ def main():
     if args.workload != "c3":
         return bench_replicas(args, torch, _capi, rank, world, local_rank)
     if world > 1:
+        if args.eci != "sparse":
+            raise SystemExit("bench.py: --eci full runs on one GPU (slab states take one neighbor class)")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from casmcode_clexmonte_b200.slab import SlabRunner
     sysd = load_system()
-    eci = sysd["eci_sparse"]
+    eci = sysd[eci_key]
     tables = _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz"), device=local_rank)
     ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], MU, 3)
     N = args.box
@@ -496,7 +505,8 @@ def main():
     # DRAM traffic of one launch and the binding resource from the committed ncu --set full
     # capture of this kernel at this workload (512^3, one GPU, S sweeps per launch); null otherwise
     traffic, binding = None, None
-    prof = ROOT / "profiles" / f"r02_ncu_full_{kernel_name}.csv"
+    prof = ROOT / "profiles" / (f"r02_ncu_full_{kernel_name}_two_class.csv" if info["evaluator"] == "pair_lut2"
+                                else f"r02_ncu_full_{kernel_name}.csv")
     if world == 1 and args.box == N_BOX and not args.layers and prof.exists():
         import csv
         m = {}
@@ -530,7 +540,7 @@ def main():
                                                   "stream_gap_units", "launches_per_sweep")}}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference_rate(seconds_budget=args.cpu_seconds)
+            line["cpu_baseline"] = cpu_reference_rate(seconds_budget=args.cpu_seconds, eci_key=eci_key)
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                     "sample": f"unavailable: {e}"}

@@ -182,8 +182,9 @@ struct SweepPlan {
   };
   std::map<std::pair<int, int>, StreamList> stream_lists;
   uint32_t *d_ticket = nullptr;   // [replica] group tickets of the streaming kernel (dynamic assignment)
-  uint32_t *d_gridbar = nullptr;  // arrivals at the colour-pass kernel's grid barrier (monotonic, wraps)
-  uint32_t gridbar_count = 0;     // arrivals the launches so far have added
+  uint32_t *d_gridbar = nullptr;  // [replica][32] arrivals at the colour-pass kernel's barrier (monotonic, wraps)
+  uint32_t gridbar_count = 0;     // arrivals the launches so far have added (to every counter in use)
+  int gridbar_mode = -1;          // 0: one counter per replica, 1: one for the whole grid (slabs)
   bool l2_window_set = false;     // persisting-L2 window of the lattice decided (colour passes on one GPU)
   int stream_capacity = -1;       // co-resident blocks of the kernel chosen for this state
   int stream_blocks = 0;          // blocks per replica

@@ -2034,13 +2034,19 @@ static int sweep_pass(cmx_state *s, uint64_t seed, int64_t first_sweep, int64_t 
     cmx_set_error("colour-pass sweep: a replica exceeds 2^32 16-byte chunks");
     return CMX_ERR_UNSUPPORTED;
   }
-  if (!P.d_gridbar) {
-    CMX_CUDA(cudaMalloc((void **)&P.d_gridbar, sizeof(uint32_t)));
-    CMX_CUDA(cudaMemsetAsync(P.d_gridbar, 0, sizeof(uint32_t), s->stream));
+  // one barrier counter per replica (independent chains wait for their own blocks only); the
+  // ring protocol of peer-attached slabs publishes an epoch for all replicas: one counter
+  const int bar_mode = a.push ? 1 : 0;
+  const size_t bar_bytes = sizeof(uint32_t) * 32 * (size_t)s->n_replicas;
+  if (!P.d_gridbar) CMX_CUDA(cudaMalloc((void **)&P.d_gridbar, bar_bytes));
+  if (P.gridbar_mode != bar_mode) {
+    CMX_CUDA(cudaMemsetAsync(P.d_gridbar, 0, bar_bytes, s->stream));
     P.gridbar_count = 0;
+    P.gridbar_mode = bar_mode;
   }
   c.bar = P.d_gridbar;
-  c.n_blocks = grid.x * grid.y;
+  c.bar_stride = bar_mode ? 0u : 32u;
+  c.n_blocks = bar_mode ? grid.x * grid.y : grid.x;
   const uint32_t passes_per_sweep = kgroup < 0 ? 4u : 2u;
   // (the barrier counter is compared modulo 2^32: a launch adds less than 2^30 arrivals)
   const int64_t max_sweeps = std::max<int64_t>(1, (int64_t)((1u << 30) / (passes_per_sweep * c.n_blocks)));

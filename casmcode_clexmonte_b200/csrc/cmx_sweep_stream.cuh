@@ -1007,8 +1007,13 @@ struct PassArgs {
   uint32_t gid_off;                    // global chunk id (RNG counter) minus local chunk index
   int32_t kgroup;              // only this k colour (slabs whose halo the host exchanges), -1: both
   unsigned long long *my_sig, *peer_sig_dn, *peer_sig_up;
-  uint32_t *bar;               // grid barrier: arrivals so far (monotonic, modulo 2^32)
-  uint32_t bar_base, n_blocks; // its value when the launch starts; blocks of the grid
+  // barrier between colour passes: arrivals so far (monotonic, modulo 2^32).  Replicas are
+  // independent Markov chains, so on one GPU every replica (grid row) has its OWN counter
+  // (bar + blockIdx.y * bar_stride, one 128-byte line each) and waits for its own blocks only;
+  // the ring protocol of slabs needs all replicas behind one barrier (bar_stride = 0)
+  uint32_t *bar;
+  uint32_t bar_stride;
+  uint32_t bar_base, n_blocks; // the counters' value when the launch starts; arrivals per barrier
 };
 
 // Grid barrier of the colour-pass kernel (cooperative launch: all blocks are co-resident).
@@ -1250,7 +1255,7 @@ __global__ void __launch_bounds__(256, MASK2_CT ? 2 : CMX_S16_MINB) k_sweep_pass
     n_acc = 0;
     // every store of the pass, the ones into the neighbours' ghost layers included
     bar_target += c.n_blocks;
-    s16_grid_barrier(c.bar, bar_target);
+    s16_grid_barrier(c.bar + (size_t)blockIdx.y * c.bar_stride, bar_target);
   };
   using T0 = std::integral_constant<int, 0>;
   using T1 = std::integral_constant<int, 1>;
