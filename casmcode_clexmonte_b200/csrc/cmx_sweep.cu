@@ -1256,7 +1256,8 @@ int cmx_plan_sweep(cmx_state *s) {
     for (auto const &kv : V)
       for (size_t x = 0; x < v0.size(); ++x)
         if (std::fabs(kv.second[x] - v0[x]) > 1e-12 * scale) ok = false;
-    if ((int)V.size() > 14) ok = false;  // byte-lane sums n1 + 18 n2 must stay below 256
+    // byte-lane sums n1 + 18 n2 (+ the column skew of the acceptance table, up to 22) must stay below 256
+    if ((int)V.size() > (t->n_occ[0] == 3 ? 12 : 14)) ok = false;
     for (auto const &kv : V)
       for (int a = 0; a < 3; ++a)
         if (std::abs(t->nbr[4 * kv.first + a]) > 1) ok = false;

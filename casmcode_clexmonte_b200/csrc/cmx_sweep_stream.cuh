@@ -34,13 +34,20 @@
 
 #define CMX_TAB24(NOCC) ((NOCC) == 3 ? 23 * 256 : 512)
 
+// tab24 index of (cnt, sab = code | alt << 2): the column is SKEWED by sab.  Sites with equal
+// neighbor counts and different (occupant, proposal) are common in a warp; unskewed they
+// would read different words of the same shared-memory bank (rows are 256 words apart).
+// cnt + sab <= 18 * 12 + 22 < 256 for ternary models (cmx_plan_sweep: z <= 12).
+__host__ __device__ __forceinline__ uint32_t cmx_tab24_index(uint32_t cnt, uint32_t sab) {
+  return ((cnt + sab) & 255u) | (sab << 8);
+}
 // compact index (k_build_tab16 layout) of a tab24 index
 __host__ __device__ __forceinline__ uint32_t cmx_tab24_to_16(uint32_t idx24) {
   const uint32_t sab = idx24 >> 8;
-  return (idx24 & 255u) | (((sab & 3u) | (((sab >> 2) & 1u) << 2)) << 8);
+  return ((idx24 - sab) & 255u) | (((sab & 3u) | (((sab >> 2) & 1u) << 2)) << 8);
 }
 
-// tab24[idx = cnt | (code | alt << 2) << 8] = thr16 | proposed code << 16, thr16 in [0, 0x8000]
+// tab24[cmx_tab24_index(cnt, code | alt << 2)] = thr16 | proposed code << 16, thr16 in [0, 0x8000]
 __global__ void k_build_tab24(const uint32_t *__restrict__ tab16, int nocc, int n_tab16, int n_tab24,
                               uint32_t *__restrict__ tab24) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,11 +215,13 @@ __device__ __forceinline__ void s16_update_word(uint32_t cnt, uint32_t &C, uint3
     const uint32_t am = prmt_s<0xFDB9u>(R0, R1);
     SA = C | (am & 0x04040404u);
   }
-  // idx = cnt byte b | SA byte b << 8; bytes 2,3 <- sign of an SA byte (codes < 128: zero)
-  idx[0] = prmt_s<0xCC40u>(cnt, SA);
-  idx[1] = prmt_s<0xDD51u>(cnt, SA);
-  idx[2] = prmt_s<0xEE62u>(cnt, SA);
-  idx[3] = prmt_s<0xFF73u>(cnt, SA);
+  // idx = (cnt + SA) byte b | SA byte b << 8 (cmx_tab24_index; no carry between the byte lanes);
+  // bytes 2,3 <- sign of an SA byte (codes < 128: zero)
+  const uint32_t cs = cnt + SA;
+  idx[0] = prmt_s<0xCC40u>(cs, SA);
+  idx[1] = prmt_s<0xDD51u>(cs, SA);
+  idx[2] = prmt_s<0xEE62u>(cs, SA);
+  idx[3] = prmt_s<0xFF73u>(cs, SA);
   const uint32_t e0 = lds_u32(tab + 4u * idx[0]);
   const uint32_t e1 = lds_u32(tab + 4u * idx[1]);
   const uint32_t e2 = lds_u32(tab + 4u * idx[2]);
@@ -246,7 +255,7 @@ __device__ __noinline__ void s16_ties(S16Tie *t, uint32_t tab, const uint32_t *_
       const uint32_t R = t->R[2 * h + (b >> 1)];
       const uint32_t field = (b & 1) ? (R >> 16) : (R & 0xFFFFu);
       const uint32_t sab = ((t->C[h] >> (8 * b)) & 0xFFu) | ((NOCC == 3) ? ((field >> 15) << 2) : 0u);
-      const uint32_t idx = ((t->cnt[h] >> (8 * b)) & 0xFFu) | (sab << 8);
+      const uint32_t idx = cmx_tab24_index((t->cnt[h] >> (8 * b)) & 0xFFu, sab);
       const uint32_t e = lds_u32(tab + 4u * idx);
       if ((field & 0x7FFFu) != (e & 0xFFFFu)) continue;
       const int q = 4 * h + b;  // target site of the chunk's colour, 0..7
