@@ -1125,7 +1125,6 @@ __global__ void __launch_bounds__(256, MASK2_CT ? 2 : CMX_S16_MINB) k_sweep_pass
   uint32_t bar_target = c.bar_base;
   const uint32_t rl = lane >> a.logW, rpw_log = 5u - a.logW;
   const uint32_t slots = (uint32_t)__cvta_generic_to_shared(sh_rows) + wib * (NSLOT * CMX_S16_SLOT) + 16u * lane;
-  const int32_t N2 = a.g.N2;
   const uint32_t halo = (uint32_t)a.g.halo;
   int32_t n_acc = 0;
   long long n_acc64 = 0;
