@@ -3,7 +3,7 @@
 // Replaces the sequential loop of methods/occupation_metropolis.hh:92-120 +
 // the semi-grand proposal (SemiGrandCanonicalCalculator.cc:104-120) + the
 // potential delta (:186-213) by colour-by-colour simultaneous updates of
-// non-interacting site sets.  Two evaluators:
+// non-interacting site sets.  Evaluators:
 //
 //  * "pair_lut": the bound ECI select only point + pair functions on a single
 //    sublattice with <= 3 occupants whose active neighbors all lie in
@@ -15,8 +15,13 @@
 //    per-replica threshold table staged in shared memory.  Sixteen sites per
 //    thread (both x colours of a 16-byte row chunk), neighbor species counted
 //    for all 16 byte lanes at once (kernel k_sweep_pair16).
+//  * "pair_lut2": the same with TWO neighbor classes (FCC 1NN + 2NN: the reference's dense
+//    ECI) on x4-interleaved rows: a second byte-lane sum and a compact two-class table in
+//    the colour-pass kernel (cmx_sweep_stream.cuh).
+//  * "pair_sum": other point + pair bases: per-neighbor tables, one site per thread.
 //  * "generic": any table (multi-sublattice, triplets, quadruplets): ECI-folded
-//    merged term lists, one site per thread, FP64 products, exp().
+//    merged term lists, one site per thread (wide orbit sets: one site per warp), FP64
+//    products, exp().
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -1307,7 +1312,7 @@ int cmx_plan_sweep(cmx_state *s) {
   // summed HERE in the pair-sum evaluator's order (P0, then the neighbors in slot order) on a
   // representative arrangement, so the table holds values k_sweep_pairsum itself produces.
   if (!P.pair_lut && P.pair_sum && !skewed && T.n_sublat == 1 && np == 1 && P.mut_points.size() == 1 &&
-      t->n_occ[0] == 3 && mo == 3 && s->g.coded && s->g.xq_log != 0 && s->g.halo == 0 && s->g.N0 % 16 == 0 &&
+      t->n_occ[0] == 3 && mo == 3 && s->g.coded && s->g.xq_log != 0 && s->g.N0 % 16 == 0 &&
       s->g.N1 % 2 == 0 && s->g.N2 % 2 == 0 && s->g.N2 <= 65534 && ((uint64_t)s->g.rep_stride >> 4) < (1ull << 32) &&
       P.S[0] == 2 && P.S[1] == 2 && P.S[2] == 2 && !ps_act_n.empty() && ps_act_n.size() <= 32) {
     const int n_act = (int)ps_act_n.size(), mo3 = mo * mo * mo;
@@ -1401,7 +1406,9 @@ int cmx_plan_sweep(cmx_state *s) {
         dst[2] = o[2];
       }
       P.n_tab2 = n_tab2;
-      P.pair2 = true;
+      // slabs (ghost layers) keep the pair-sum kernel, but draw the SAME random bits: the
+      // trajectory of a box does not depend on its decomposition
+      P.pair2 = s->g.halo == 0;
       P.rng16 = true;  // the pair-sum and term-list evaluators of this state mirror the kernel's random bits
     }
   }

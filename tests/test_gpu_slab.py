@@ -143,3 +143,35 @@ def test_one_slab_with_fused_halo_equals_periodic_box():
         assert (res[p2p][0] == ref).all(), f"p2p={p2p}"
         assert res[p2p][1] == cnt[0].n_accept
     st.close()
+
+
+def test_one_slab_of_the_dense_eci_equals_periodic_box():
+    """The reference's dense FCC ECI (1NN + 2NN pairs): a box runs the two-class count-table
+    kernel, a slab of it (ghost layers, halo exchanged by the host path) the pair-sum kernel --
+    with the same random bits, so the decomposition does not change the trajectory.  One GPU."""
+    from casmcode_clexmonte_b200 import _capi
+    from casmcode_clexmonte_b200.clexulator_tables import ClexulatorTables
+    from casmcode_clexmonte_b200.potential import semigrand_exchange_table
+    from casmcode_clexmonte_b200.slab import SlabRunner
+    N, n_sweeps = 32, 4
+    sysd = json.loads((GOLDEN / "systems.json").read_text())["fcc"]
+    tables = _capi.Tables(ClexulatorTables.load(GOLDEN / "tables" / "fcc_default.npz"))
+    ex = semigrand_exchange_table(sysd["occ_to_species"], sysd["axes"]["Rt"], [0.1, -0.2], 3)
+    init = np.random.default_rng(4).integers(0, 3, N ** 3).astype(np.int8)
+    run = SlabRunner(tables, N, sysd["eci_full"], 900.0, ex, 0, 1, 0, init_occ=init, p2p=False)
+    assert run.state.sweep_info()["evaluator"] == "pair_sum"
+    run.state.counters_reset()
+    run.sweep(n_sweeps, seed=17)
+    run.synchronize()
+    got, acc = run.download_local(), run.state.counters_read()[0].n_accept
+    run.state.close()
+    st = _capi.State(tables, (N, N, N))
+    st.set_eci(sysd["eci_full"]["index"], sysd["eci_full"]["value"])
+    st.set_conditions(900.0, ex)
+    st.upload_occ(init)
+    assert st.sweep_info()["evaluator"] == "pair_lut2"
+    cnt = st.sgc_sweep(n_sweeps, seed=17)
+    ref = st.download_occ(dtype=np.int8)
+    assert (got == ref).all(), f"{(got != ref).sum()} sites differ"
+    assert acc == cnt[0].n_accept
+    st.close()
