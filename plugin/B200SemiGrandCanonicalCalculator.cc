@@ -38,7 +38,12 @@ void cmx_check(int rc) {
 struct DeviceState {
   cmx_tables *tables = nullptr;
   cmx_state *state = nullptr;
-  Index N[3] = {0, 0, 0};
+  long T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // the transformation matrix the state was created for
+  // the reference's linear site index l -> the library's (empty: the same).  The order of
+  // the unit cells in a supercell is xtal::UnitCellIndexConverter's [EXT]; it is ASKED
+  // (Conversions::l_to_ijk), never assumed.
+  std::vector<int64_t> site_order;
+  int64_t to_library(Index l) const { return site_order.empty() ? (int64_t)l : site_order[(size_t)l]; }
   ~DeviceState() {
     if (state) cmx_state_destroy(state);
     if (tables) cmx_tables_destroy(tables);
@@ -108,7 +113,8 @@ class B200SemiGrandCanonicalPotential : public BaseMontePotential {
   /// dE_clex - mu_x . R^T dN of a proposed event (:186-213), on the device-resident occupation
   double occ_delta_per_supercell(std::vector<Index> const &linear_site_index,
                                  std::vector<int> const &new_occ) override {
-    std::vector<int64_t> l(linear_site_index.begin(), linear_site_index.end());
+    std::vector<int64_t> l(linear_site_index.size());
+    for (size_t q = 0; q < l.size(); ++q) l[q] = dev->to_library(linear_site_index[q]);
     std::vector<int32_t> occ(new_occ.begin(), new_occ.end());
     double dE = 0.0;
     cmx_check(cmx_delta_e(dev->state, 0, 1, (int32_t)l.size(), l.data(), occ.data(), /*potential=*/1, &dE));
@@ -129,14 +135,14 @@ class B200SemiGrandCanonicalCalculator : public BaseMonteCalculator {
                             /*time_sampling_allowed=*/false, /*update_atoms=*/false, /*save_atom_info=*/false,
                             /*is_multistate_method=*/false) {}
 
+  /// any integer transformation matrix of positive volume (diag(N0, N1, N2) boxes run the
+  /// row kernels, skewed ones the general-supercell path of the library)
   Validator validate_configuration(state_type &state) const override {
     Validator v;
     Eigen::Matrix3l const &T = get_transformation_matrix_to_super(state);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j)
-        if (i != j && T(i, j) != 0)
-          v.error.insert("B200SemiGrandCanonicalCalculator: the supercell must be diag(N0, N1, N2) of the prim "
-                         "(general transformation matrices are handled by cmx_state_create_general)");
+    const long det = T(0, 0) * (T(1, 1) * T(2, 2) - T(1, 2) * T(2, 1)) - T(0, 1) * (T(1, 0) * T(2, 2) - T(1, 2) * T(2, 0)) +
+                     T(0, 2) * (T(1, 0) * T(2, 1) - T(1, 1) * T(2, 0));
+    if (det <= 0) v.error.insert("B200SemiGrandCanonicalCalculator: transformation_matrix_to_super must have a positive determinant");
     return v;
   }
   Validator validate_conditions(state_type &state) const override {  // SemiGrandCanonicalCalculator.cc:362-383
@@ -162,12 +168,43 @@ class B200SemiGrandCanonicalCalculator : public BaseMonteCalculator {
     if (!v.valid()) throw std::runtime_error("Error in B200SemiGrandCanonicalCalculator::run: " + *v.error.begin());
     this->state_data = std::make_shared<StateData>(this->system, &state, occ_location);
     Eigen::Matrix3l const &T = this->state_data->transformation_matrix_to_super;
-    if (!m_dev->state || m_dev->N[0] != T(0, 0) || m_dev->N[1] != T(1, 1) || m_dev->N[2] != T(2, 2)) {
+    bool same = m_dev->state != nullptr, diagonal = true;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        same = same && m_dev->T[3 * i + j] == T(i, j);
+        diagonal = diagonal && (i == j || T(i, j) == 0);
+      }
+    if (!same) {
       if (m_dev->state) cmx_state_destroy(m_dev->state);
       m_dev->state = nullptr;
-      cmx_check(cmx_state_create(m_dev->tables, (int32_t)T(0, 0), (int32_t)T(1, 1), (int32_t)T(2, 2), 1, 0,
-                                 &m_dev->state));
-      for (int a = 0; a < 3; ++a) m_dev->N[a] = T(a, a);
+      int32_t T9[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T9[3 * i + j] = (int32_t)(m_dev->T[3 * i + j] = T(i, j));
+      if (diagonal)
+        cmx_check(cmx_state_create(m_dev->tables, T9[0], T9[4], T9[8], 1, 0, &m_dev->state));
+      else
+        cmx_check(cmx_state_create_general(m_dev->tables, T9, 1, 0, &m_dev->state));
+      // the reference's site order: l = b * n_unitcells + unitl, unit cell `unitl` at l_to_ijk(l)
+      {
+        monte::Conversions const &convert = *this->state_data->convert;
+        const Index n_cells = this->state_data->n_unitcells;
+        const Index n_sites = n_cells * (Index)this->system->occ_to_species.size();
+        std::vector<int32_t> ijk(3 * (size_t)n_cells);
+        for (Index u = 0; u < n_cells; ++u) {
+          auto const cell = convert.l_to_ijk(u);
+          for (int a = 0; a < 3; ++a) ijk[3 * (size_t)u + a] = (int32_t)cell[a];
+        }
+        std::vector<int64_t> cell_index((size_t)n_cells);
+        cmx_check(cmx_state_cell_index(m_dev->state, n_cells, ijk.data(), cell_index.data()));
+        m_dev->site_order.resize((size_t)n_sites);
+        bool identity = true;
+        for (Index l = 0; l < n_sites; ++l) {
+          m_dev->site_order[(size_t)l] = (int64_t)convert.l_to_b(l) * n_cells + cell_index[(size_t)(l % n_cells)];
+          identity = identity && m_dev->site_order[(size_t)l] == (int64_t)l;
+        }
+        if (identity) m_dev->site_order.clear();
+        cmx_check(cmx_state_set_site_order(m_dev->state, identity ? nullptr : m_dev->site_order.data()));
+      }
       clexulator::SparseCoefficients const &eci = get_clex_data(*this->system, "formation_energy").coefficients;
       std::vector<uint32_t> index(eci.index.begin(), eci.index.end());
       cmx_check(cmx_state_set_eci(m_dev->state, (int32_t)index.size(), index.data(), eci.value.data()));

@@ -10,6 +10,7 @@
 // With libcasm installed the forwarding headers next to this file are not on the include
 // path and the plugin compiles against the real ones.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -114,14 +115,29 @@ struct SparseCoefficients {
 };
 }  // namespace clexulator
 
+namespace xtal {
+// [EXT] casm/crystallography/UnitCellCoord.hh: xtal::UnitCell, integer prim coordinates of a unit cell
+struct UnitCell {
+  long v[3] = {0, 0, 0};
+  long operator[](int a) const { return v[a]; }
+  long operator()(int a) const { return v[a]; }
+};
+}  // namespace xtal
+
 namespace monte {
 // [EXT] casm/monte/Conversions.hh: the index conversions the potential uses
-// (SemiGrandCanonicalCalculator.cc:202-209)
+// (SemiGrandCanonicalCalculator.cc:202-209).  l = b * n_unitcells + unitl; the ORDER of the
+// unit cells within a supercell is the reference's business (xtal::UnitCellIndexConverter,
+// Smith normal form): this stand-in deliberately uses one of its own (see StateData), so a
+// plugin that guessed the order instead of asking l_to_ijk fails the driver's checks.
 class Conversions {
  public:
   Index m_n_unitcells = 0;
   std::vector<Index> m_b_to_asym;
   std::vector<std::vector<Index>> m_species_index;  // [asym][occ]
+  std::vector<xtal::UnitCell> m_unitl_to_ijk;       // [unitl]
+  xtal::UnitCell l_to_ijk(Index l) const { return m_unitl_to_ijk[(size_t)(l % m_n_unitcells)]; }
+  Index l_to_unitl(Index l) const { return l % m_n_unitcells; }
   Index l_to_b(Index l) const { return l / m_n_unitcells; }
   Index l_to_asym(Index l) const { return m_b_to_asym[(size_t)(l / m_n_unitcells)]; }
   Index species_index(Index asym, Index occ) const { return m_species_index[(size_t)asym][(size_t)occ]; }
@@ -265,6 +281,44 @@ struct StateData {
                   T(0, 2) * (T(1, 0) * T(2, 1) - T(1, 1) * T(2, 0));
     if (n_unitcells < 0) n_unitcells = -n_unitcells;
     owned_convert.m_n_unitcells = n_unitcells;
+    // the unit cells of the supercell: the lattice points whose coordinates in the supercell
+    // lattice, T^-1 ijk = adj(T) ijk / det, lie in [0, 1)^3; numbered k-major in prim coordinates
+    {
+      long A[3][3];  // adjugate of T
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          const int r1 = (c + 1) % 3, r2 = (c + 2) % 3, c1 = (r + 1) % 3, c2 = (r + 2) % 3;
+          A[r][c] = T(r1, c1) * T(r2, c2) - T(r1, c2) * T(r2, c1);
+        }
+      long det = 0;
+      for (int c = 0; c < 3; ++c) det += T(0, c) * A[c][0];
+      long lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // bounding box of the supercell's corners
+      for (int m = 0; m < 8; ++m)
+        for (int r = 0; r < 3; ++r) {
+          long x = 0;
+          for (int c = 0; c < 3; ++c) x += ((m >> c) & 1) ? T(r, c) : 0;
+          lo[r] = std::min(lo[r], x);
+          hi[r] = std::max(hi[r], x);
+        }
+      for (long k = lo[2]; k <= hi[2]; ++k)
+        for (long j = lo[1]; j <= hi[1]; ++j)
+          for (long i = lo[0]; i <= hi[0]; ++i) {
+            bool inside = true;
+            for (int r = 0; r < 3 && inside; ++r) {
+              long f = A[r][0] * i + A[r][1] * j + A[r][2] * k;
+              if (det < 0) f = -f;
+              inside = f >= 0 && f < (det < 0 ? -det : det);
+            }
+            if (!inside) continue;
+            xtal::UnitCell u;
+            u.v[0] = i;
+            u.v[1] = j;
+            u.v[2] = k;
+            owned_convert.m_unitl_to_ijk.push_back(u);
+          }
+      if ((Index)owned_convert.m_unitl_to_ijk.size() != n_unitcells)
+        throw std::runtime_error("casm_shim: unit cell enumeration does not match det(T)");
+    }
     owned_convert.m_b_to_asym = _system->sublat_to_asym;
     owned_convert.m_species_index.assign(_system->occ_to_species.size(), {});
     for (size_t b = 0; b < _system->occ_to_species.size(); ++b)

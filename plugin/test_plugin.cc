@@ -22,6 +22,164 @@ static int fail(const char *what) {
   return 1;
 }
 
+// the caller's unit-cell index of the cell at prim coordinates x (any periodic image): x and
+// the cell's own coordinates differ by a supercell lattice vector T n, i.e. adj(T) (x - y) is
+// a multiple of det(T) in every component
+static Index find_unitl(monte::Conversions const &convert, Eigen::Matrix3l const &T, const long x[3]) {
+  long A[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const int r1 = (c + 1) % 3, r2 = (c + 2) % 3, c1 = (r + 1) % 3, c2 = (r + 2) % 3;
+      A[r][c] = T(r1, c1) * T(r2, c2) - T(r1, c2) * T(r2, c1);
+    }
+  long det = 0;
+  for (int c = 0; c < 3; ++c) det += T(0, c) * A[c][0];
+  for (Index u = 0; u < convert.m_n_unitcells; ++u) {
+    auto const y = convert.l_to_ijk(u);
+    bool same = true;
+    for (int r = 0; r < 3 && same; ++r) {
+      const long f = A[r][0] * (x[0] - y[0]) + A[r][1] * (x[1] - y[1]) + A[r][2] * (x[2] - y[2]);
+      same = f % det == 0;
+    }
+    if (same) return u;
+  }
+  return -1;
+}
+
+// A skewed supercell (general transformation matrix; the caller numbers its unit cells in its
+// own order and at its own periodic images): the plugin must ask Conversions::l_to_ijk.
+//  (1) physics pins the site mapping: a B atom and a vacancy in an otherwise pure-A crystal
+//      interact exactly when they are first neighbours, with the pair energy a diag(N) box gives;
+//  (2) the potential's delta equals the difference of two evaluations;
+//  (3) a run leaves the occupation and the counters of the C ABI driven with the same site order.
+static int general_supercell_case(BaseMonteCalculator &calc, std::shared_ptr<system_type> system, const char *tables_path) {
+  const long Tg[3][3] = {{8, 0, 0}, {2, 8, 0}, {4, 2, 8}};  // columns = supercell lattice vectors; not symmetric
+  state_type state;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) state.configuration.transformation_matrix_to_super(i, j) = Tg[i][j];
+  const Index n_cells = 512;
+  state.configuration.dof_values.occupation = Eigen::VectorXi(n_cells);
+  state.conditions.scalar_values["temperature"] = 900.0;
+  Eigen::VectorXd mu(2);
+  mu[0] = 0.2;
+  mu[1] = -0.1;
+  state.conditions.vector_values["param_chem_pot"] = mu;
+  monte::OccLocation occ_location;
+  occ_location.m_mol_size = n_cells;
+  if (!calc.validate_state(state).valid()) return fail("validate_state rejected a skewed supercell");
+  Eigen::VectorXi &occ = state.configuration.dof_values.occupation;
+
+  // (1) B at unit cell u0, Va at u0 + d
+  for (Index l = 0; l < n_cells; ++l) occ[l] = 0;
+  calc.set_state_and_potential(state, &occ_location);
+  if (calc.state_data->n_unitcells != n_cells) return fail("general supercell: n_unitcells");
+  // (copies: every set_state_and_potential makes a new StateData)
+  const monte::Conversions convert = *calc.state_data->convert;
+  const Eigen::Matrix3l T = calc.state_data->transformation_matrix_to_super;
+  const Index u0 = 137;
+  auto const c0 = convert.l_to_ijk(u0);
+  auto potential_with_vacancy_at = [&](const long d[3], double &out) -> bool {
+    const long x[3] = {c0[0] + d[0], c0[1] + d[1], c0[2] + d[2]};
+    const Index u1 = find_unitl(convert, T, x);
+    if (u1 < 0 || u1 == u0) return false;
+    for (Index l = 0; l < n_cells; ++l) occ[l] = 0;
+    occ[u0] = 1;
+    occ[u1] = 2;
+    calc.set_state_and_potential(state, &occ_location);
+    out = calc.potential->per_supercell();
+    return true;
+  };
+  const long far[3] = {3, 3, 3}, not_nn[3] = {1, 1, 0};
+  const long nn[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, -1}, {1, -1, 0}};  // FCC first neighbours (prim coordinates)
+  double p_far = 0, p_not = 0, p_nn[4];
+  if (!potential_with_vacancy_at(far, p_far) || !potential_with_vacancy_at(not_nn, p_not)) return fail("general supercell: cell lookup");
+  for (int q = 0; q < 4; ++q)
+    if (!potential_with_vacancy_at(nn[q], p_nn[q])) return fail("general supercell: cell lookup");
+  // the same pair in a diag(16) box through the C ABI
+  cmx_tables *t = nullptr;
+  cmx_state *s = nullptr;
+  if (cmx_tables_create_from_file(tables_path, 0, &t)) return fail(cmx_last_error());
+  if (cmx_state_create(t, 16, 16, 16, 1, 0, &s)) return fail(cmx_last_error());
+  ClexData const &clex = system->clex_data.at("formation_energy");
+  std::vector<uint32_t> idx(clex.coefficients.index.begin(), clex.coefficients.index.end());
+  cmx_state_set_eci(s, (int32_t)idx.size(), idx.data(), clex.coefficients.value.data());
+  std::vector<int32_t> box(4096, 0);
+  double e_nn = 0, e_far = 0;
+  box[0] = 1;
+  box[1] = 2;  // cell (1, 0, 0)
+  cmx_state_upload_occ(s, 0, box.data());
+  cmx_energy(s, 0, &e_nn);
+  box[1] = 0;
+  box[3 + 16 * (3 + 16 * 3)] = 2;  // cell (3, 3, 3)
+  cmx_state_upload_occ(s, 0, box.data());
+  cmx_energy(s, 0, &e_far);
+  cmx_state_destroy(s);
+  s = nullptr;
+  const double pair = e_nn - e_far;
+  if (!(std::fabs(pair) > 1e-6)) return fail("general supercell: the probe pair does not interact");
+  if (std::fabs(p_not - p_far) > 1e-9) return fail("general supercell: a non-neighbour pair interacts (site mapping)");
+  for (int q = 0; q < 4; ++q)
+    if (std::fabs((p_nn[q] - p_far) - pair) > 1e-9) return fail("general supercell: first-neighbour pair energy (site mapping)");
+
+  // (2) + (3) on a random configuration
+  std::mt19937_64 init(11);
+  for (Index l = 0; l < n_cells; ++l) occ[l] = (int)(init() % 3);
+  const Eigen::VectorXi occ0 = occ;
+  calc.set_state_and_potential(state, &occ_location);
+  const double p0 = calc.potential->per_supercell();
+  for (Index l : {Index(0), Index(200), Index(511)}) {
+    const int new_occ = (occ0[l] + 1) % 3;
+    const double dE = calc.potential->occ_delta_per_supercell({l}, {new_occ});
+    occ[l] = new_occ;
+    calc.set_state_and_potential(state, &occ_location);
+    const double p1 = calc.potential->per_supercell();
+    occ[l] = occ0[l];
+    if (std::fabs((p1 - p0) - dE) > 1e-9) return fail("general supercell: occ_delta_per_supercell != difference of potentials");
+  }
+  run_manager_type<BaseMonteCalculator::engine_type> run_manager;
+  run_manager.engine = std::make_shared<std::mt19937_64>(99);
+  run_manager.sample_period = 2;
+  run_manager.n_samples_max = 3;  // samples at passes 0, 2, 4
+  run_manager.sampler = [](state_type const &) {};
+  calc.run(state, occ_location, run_manager);
+  if (run_manager.pass != 4) return fail("general supercell: pass count");
+  int32_t T9[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T9[3 * i + j] = (int32_t)Tg[i][j];
+  if (cmx_state_create_general(t, T9, 1, 0, &s)) return fail(cmx_last_error());
+  cmx_state_set_eci(s, (int32_t)idx.size(), idx.data(), clex.coefficients.value.data());
+  std::vector<int32_t> ijk(3 * n_cells);
+  for (Index u = 0; u < n_cells; ++u)
+    for (int a = 0; a < 3; ++a) ijk[3 * u + a] = (int32_t)convert.l_to_ijk(u)[a];
+  std::vector<int64_t> order(n_cells);
+  if (cmx_state_cell_index(s, n_cells, ijk.data(), order.data())) return fail(cmx_last_error());
+  bool identity = true;
+  for (Index u = 0; u < n_cells; ++u) identity = identity && order[u] == u;
+  if (identity) return fail("general supercell: the stand-in's unit-cell order equals the library's (the case tests nothing)");
+  if (cmx_state_set_site_order(s, order.data())) return fail(cmx_last_error());
+  cmx_state_upload_occ(s, 0, occ0.data());
+  std::vector<double> exch(9, 0.0);
+  const double mu_of_species[3] = {0.0, mu[0], mu[1]};
+  for (int oi = 0; oi < 3; ++oi)
+    for (int of = 0; of < 3; ++of) exch[oi * 3 + of] = mu_of_species[of] - mu_of_species[oi];
+  cmx_state_set_conditions(s, 0, 900.0, exch.data());
+  long long acc = 0;
+  for (Index p = 0; p < 4; p += 2) {
+    cmx_counters c;
+    if (cmx_sgc_sweep(s, 2, 12345, p, &c)) return fail(cmx_last_error());
+    acc += c.n_accept;
+  }
+  std::vector<int32_t> ref(n_cells);
+  cmx_state_download_occ(s, 0, ref.data());
+  for (Index l = 0; l < n_cells; ++l)
+    if (ref[l] != occ[l]) return fail("general supercell: occupation after run differs from the C ABI");
+  if (acc != run_manager.n_accept || acc == 0) return fail("general supercell: acceptance count");
+  cmx_state_destroy(s);
+  cmx_tables_destroy(t);
+  std::printf("general supercell ok: pair energy %.6f, accepted %lld of %lld\n", pair, acc, (long long)(4 * n_cells));
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 3) return fail("usage: test_plugin <plugin.so> <tables.flat> [--no-gpu]");
   const bool no_gpu = argc > 3 && !std::strcmp(argv[3], "--no-gpu");
@@ -83,11 +241,11 @@ int main(int argc, char **argv) {
   monte::OccLocation occ_location;
   occ_location.m_mol_size = n_cells;
 
-  // validate_state rejects a non-diagonal supercell
+  // validate_state rejects a supercell of non-positive volume
   {
     state_type bad = state;
-    bad.configuration.transformation_matrix_to_super(0, 1) = 1;
-    if (calc->validate_state(bad).valid()) return fail("validate_state accepted a skewed supercell");
+    bad.configuration.transformation_matrix_to_super(0, 0) = -N;
+    if (calc->validate_state(bad).valid()) return fail("validate_state accepted a left-handed supercell");
   }
 
   // potential: delta of a proposed event == C ABI on the same configuration
@@ -145,6 +303,8 @@ int main(int argc, char **argv) {
   cmx_energy(s, 0, &E);
   cmx_state_destroy(s);
   cmx_tables_destroy(t);
+
+  if (int rc = general_supercell_case(*calc, system, argv[2])) return rc;
 
   // clone: independent device handles, same behaviour
   std::unique_ptr<BaseMonteCalculator> twin = calc->clone();

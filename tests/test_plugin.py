@@ -55,3 +55,6 @@ def test_plugin_run_equals_the_c_abi(built, variant):
     r = subprocess.run([str(PLUGIN / "_build" / "test_plugin"), str(so), str(built)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "plugin ok: 10 passes" in r.stdout
+    # a skewed supercell whose unit cells the caller numbers in its own order: the plugin asks
+    # Conversions::l_to_ijk; a B-Va pair interacts exactly when it is a first-neighbour pair
+    assert "general supercell ok" in r.stdout
