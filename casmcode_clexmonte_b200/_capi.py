@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "cmx_global_corr", "cmx_energy", "cmx_composition",
     "cmx_sgc_sweep", "cmx_sgc_sweep_kgroup", "cmx_sgc_sweep_slab", "cmx_state_set_sweep_flags", "cmx_counters_reset", "cmx_counters_read", "cmx_sweep_info", "cmx_sweep_launches", "cmx_sweep_term_counts", "cmx_sweep_stream_info", "cmx_sweep_debug_delta_e",
     "cmx_metropolis_sequential", "cmx_metropolis_sequential_ties", "cmx_rng_stream_test",
-    "cmx_canonical_set_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
+    "cmx_canonical_set_swaps", "cmx_canonical_default_swaps", "cmx_canonical_sweep", "cmx_canonical_info",
     "cmx_kmc_create", "cmx_kmc_destroy", "cmx_kmc_event_states", "cmx_kmc_all_rates",
     "cmx_kmc_set_impact_table", "cmx_kmc_run_begin", "cmx_kmc_run", "cmx_kmc_current_rates",
     "cmx_sampler_create", "cmx_sampler_destroy", "cmx_sampler_set_param_chem_pot", "cmx_sampler_info",
@@ -175,6 +175,7 @@ def lib():
     L.cmx_metropolis_sequential_ties.argtypes = [vp, C.POINTER(i64), vp, i32]
     L.cmx_rng_stream_test.argtypes = [u64, i64, vp, vp, vp, vp, vp, vp]
     L.cmx_canonical_set_swaps.argtypes = [vp, i32, vp]
+    L.cmx_canonical_default_swaps.argtypes = [vp, i32, i32, i32, vp, C.POINTER(i32)]
     L.cmx_canonical_sweep.argtypes = [vp, i64, u64, i64, vp]
     L.cmx_canonical_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.cmx_kmc_create.argtypes = [vp, i32, C.POINTER(EventType), i32, C.POINTER(PrimEvent), C.POINTER(vp)]
@@ -500,6 +501,15 @@ class State:
             check(lib().cmx_canonical_info(self._h, i, S, C.byref(nc)))
             out.append((tuple(S), nc.value))
         return out
+
+    def canonical_default_swaps(self, n_shell: int = 12, long_range: bool = True) -> list:
+        """The library's default swap table [(b_a, b_b, (t0, t1, t2))] (needs set_occupants);
+        the same list potential.canonical_swap_types builds on the host."""
+        n = C.c_int32()
+        check(lib().cmx_canonical_default_swaps(self._h, int(n_shell), int(bool(long_range)), 0, None, C.byref(n)))
+        arr = np.zeros((max(1, n.value), 5), dtype=np.int32)
+        check(lib().cmx_canonical_default_swaps(self._h, int(n_shell), int(bool(long_range)), n.value, _p(arr), C.byref(n)))
+        return [(int(r[0]), int(r[1]), (int(r[2]), int(r[3]), int(r[4]))) for r in arr[:n.value]]
 
     def canonical_sweep(self, n_sweeps: int, seed: int, first_sweep: int = 0):
         cnt = (Counters * self.n_replicas)()

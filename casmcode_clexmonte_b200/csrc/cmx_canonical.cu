@@ -423,6 +423,74 @@ static bool colouring_ok(const int N[3], const int S[3], const int t[3],
   return true;
 }
 
+// The default swap table: the parallel counterpart of the reference's canonical swaps
+// (make_canonical_swaps [EXT], built at src/casm/clexmonte/system/System.cc:55-58: every pair
+// of candidates that share a species on one asymmetric unit).  For every ordered pair of
+// mutable sublattices on the same asymmetric unit with a common species: the n_shell shortest
+// translations of the prim neighbor list (one of +t / -t when the sublattices are equal: both
+// give the same pairs) and, with long_range, one long translation that moves species across
+// the whole box (t_i = 2 mod 4: a stride-4 colouring along i is conflict free for any
+// short-ranged basis).  The host-language mirror is potential.canonical_swap_types.
+extern "C" int cmx_canonical_default_swaps(const cmx_state *s, int32_t n_shell, int32_t long_range, int32_t cap,
+                                           cmx_swap_type *swaps, int32_t *n) {
+  if (!s || !n || n_shell <= 0 || cap < 0 || (cap && !swaps)) return invalid("cmx_canonical_default_swaps: bad argument");
+  if (s->sublat_to_asym.empty()) {
+    cmx_set_error("cmx_canonical_default_swaps: the occupants are not set (cmx_state_set_occupants)");
+    return CMX_ERR_STATE;
+  }
+  const cmx_tables *t = s->t;
+  const int nb = t->d.n_sublat, mo = t->d.max_occ;
+  std::vector<cmx_swap_type> out;
+  auto shares_species = [&](int ba, int bb) {
+    for (int oa = 0; oa < t->n_occ[ba]; ++oa)
+      for (int ob = 0; ob < t->n_occ[bb]; ++ob)
+        if (s->occ_to_species[(size_t)ba * mo + oa] >= 0 &&
+            s->occ_to_species[(size_t)ba * mo + oa] == s->occ_to_species[(size_t)bb * mo + ob])
+          return true;
+    return false;
+  };
+  for (int ba = 0; ba < nb; ++ba) {
+    if (t->n_occ[ba] <= 1) continue;
+    for (int bb = ba; bb < nb; ++bb) {
+      if (t->n_occ[bb] <= 1 || s->sublat_to_asym[ba] != s->sublat_to_asym[bb] || !shares_species(ba, bb)) continue;
+      const int want = (ba == bb) ? n_shell / 2 : n_shell;
+      const size_t first = out.size();
+      for (int q = 0; q < t->d.nlist_len && (int)(out.size() - first) < want; ++q) {
+        const int32_t *o = &t->nbr[4 * q];
+        if (o[3] != bb || (ba == bb && o[0] == 0 && o[1] == 0 && o[2] == 0)) continue;
+        bool mirrored = false;
+        for (size_t k = first; k < out.size() && ba == bb; ++k)
+          mirrored = mirrored || (out[k].t[0] == -o[0] && out[k].t[1] == -o[1] && out[k].t[2] == -o[2]);
+        if (mirrored) continue;
+        cmx_swap_type w;
+        w.b_a = ba;
+        w.b_b = bb;
+        w.t[0] = o[0];
+        w.t[1] = o[1];
+        w.t[2] = o[2];
+        out.push_back(w);
+      }
+      if (long_range && s->g.N0 >= 8 && s->g.N0 % 4 == 0) {
+        const int half = s->g.N0 / 2;
+        cmx_swap_type w;
+        w.b_a = ba;
+        w.b_b = bb;
+        w.t[0] = (half - (half % 4) + 2) % s->g.N0;
+        w.t[1] = s->g.N1 / 3;
+        w.t[2] = (s->g.N2 > 2) ? s->g.N2 / 2 + 1 : 0;
+        out.push_back(w);
+      }
+    }
+  }
+  *n = (int32_t)out.size();
+  if ((int32_t)out.size() > cap) {
+    if (cap == 0) return CMX_OK;  // size query
+    return invalid("cmx_canonical_default_swaps: more swap types than the caller's buffer holds");
+  }
+  for (size_t q = 0; q < out.size(); ++q) swaps[q] = out[q];
+  return CMX_OK;
+}
+
 extern "C" int cmx_canonical_set_swaps(cmx_state *s, int32_t n, const cmx_swap_type *swaps) {
   if (!s || n <= 0 || !swaps) return invalid("cmx_canonical_set_swaps: bad argument");
   if (!s->plan.valid) {

@@ -344,6 +344,15 @@ typedef struct cmx_swap_type {
  * of the occupants (cmx_state_set_occupants).  Fails with CMX_ERR_INVALID when
  * a type admits no valid colouring of this supercell. */
 int cmx_canonical_set_swaps(cmx_state *s, int32_t n, const cmx_swap_type *swaps);
+/* The default swap table of this state, the parallel counterpart of the reference's
+ * canonical swaps (make_canonical_swaps [EXT], built at system/System.cc:55-58): for every
+ * pair of mutable sublattices on one asymmetric unit that share a species, the `n_shell`
+ * shortest translations of the prim neighbor list (half of them when the sublattices are
+ * equal: +t and -t give the same pairs) and, with `long_range`, one translation across the
+ * box.  Needs cmx_state_set_occupants.  *n receives the number of types; cap = 0 only asks
+ * for it. */
+int cmx_canonical_default_swaps(const cmx_state *s, int32_t n_shell, int32_t long_range, int32_t cap,
+                                cmx_swap_type *swaps, int32_t *n);
 /* One sweep = every swap type, every colour, once: n_swap_types * n_cells pairs
  * visited.  counters[n_replicas]: n_attempt = unlike-species pairs evaluated,
  * n_accept, dE_sum (always accumulated here). */

@@ -20,35 +20,15 @@
 //   "cmx_seed"        seed of the counter-based generator; default: one draw of run_manager.engine
 //   "cmx_reference_order"  != 0: reproduce the reference's proposal order bit for bit
 //                     (cmx_metropolis_sequential) instead of the checkerboard sweeps
-#include "casm/clexmonte/monte_calculator/BaseMonteCalculator.hh"
-#include "casm/clexmonte/monte_calculator/StateData.hh"
-#include "casm/clexmonte/system/System.hh"
-#include "cmx_b200.h"
+#include "b200_common.hh"
 
 namespace CASM {
 namespace clexmonte {
 
 namespace {
 
-void cmx_check(int rc) {
-  if (rc != CMX_OK) throw std::runtime_error(std::string("B200SemiGrandCanonicalCalculator: ") + cmx_last_error());
-}
-
-// device handles of one (system, supercell): never shared between calculator clones
-struct DeviceState {
-  cmx_tables *tables = nullptr;
-  cmx_state *state = nullptr;
-  long T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // the transformation matrix the state was created for
-  // the reference's linear site index l -> the library's (empty: the same).  The order of
-  // the unit cells in a supercell is xtal::UnitCellIndexConverter's [EXT]; it is ASKED
-  // (Conversions::l_to_ijk), never assumed.
-  std::vector<int64_t> site_order;
-  int64_t to_library(Index l) const { return site_order.empty() ? (int64_t)l : site_order[(size_t)l]; }
-  ~DeviceState() {
-    if (state) cmx_state_destroy(state);
-    if (tables) cmx_tables_destroy(tables);
-  }
-};
+using b200::DeviceState;
+void cmx_check(int rc) { b200::cmx_check(rc, "B200SemiGrandCanonicalCalculator"); }
 
 // exch[b][occ_i][occ_f] = mu_x . R^T (e_species(occ_f) - e_species(occ_i)): the exchange term
 // of SemiGrandCanonicalPotential::occ_delta_per_supercell (SemiGrandCanonicalCalculator.cc:186-213)
@@ -140,8 +120,7 @@ class B200SemiGrandCanonicalCalculator : public BaseMonteCalculator {
   Validator validate_configuration(state_type &state) const override {
     Validator v;
     Eigen::Matrix3l const &T = get_transformation_matrix_to_super(state);
-    const long det = T(0, 0) * (T(1, 1) * T(2, 2) - T(1, 2) * T(2, 1)) - T(0, 1) * (T(1, 0) * T(2, 2) - T(1, 2) * T(2, 0)) +
-                     T(0, 2) * (T(1, 0) * T(2, 1) - T(1, 1) * T(2, 0));
+    const long det = b200::determinant(T);
     if (det <= 0) v.error.insert("B200SemiGrandCanonicalCalculator: transformation_matrix_to_super must have a positive determinant");
     return v;
   }
@@ -167,61 +146,7 @@ class B200SemiGrandCanonicalCalculator : public BaseMonteCalculator {
     Validator v = this->validate_state(state);
     if (!v.valid()) throw std::runtime_error("Error in B200SemiGrandCanonicalCalculator::run: " + *v.error.begin());
     this->state_data = std::make_shared<StateData>(this->system, &state, occ_location);
-    Eigen::Matrix3l const &T = this->state_data->transformation_matrix_to_super;
-    bool same = m_dev->state != nullptr, diagonal = true;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        same = same && m_dev->T[3 * i + j] == T(i, j);
-        diagonal = diagonal && (i == j || T(i, j) == 0);
-      }
-    if (!same) {
-      if (m_dev->state) cmx_state_destroy(m_dev->state);
-      m_dev->state = nullptr;
-      int32_t T9[9];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) T9[3 * i + j] = (int32_t)(m_dev->T[3 * i + j] = T(i, j));
-      if (diagonal)
-        cmx_check(cmx_state_create(m_dev->tables, T9[0], T9[4], T9[8], 1, 0, &m_dev->state));
-      else
-        cmx_check(cmx_state_create_general(m_dev->tables, T9, 1, 0, &m_dev->state));
-      // the reference's site order: l = b * n_unitcells + unitl, unit cell `unitl` at l_to_ijk(l)
-      {
-        monte::Conversions const &convert = *this->state_data->convert;
-        const Index n_cells = this->state_data->n_unitcells;
-        const Index n_sites = n_cells * (Index)this->system->occ_to_species.size();
-        std::vector<int32_t> ijk(3 * (size_t)n_cells);
-        for (Index u = 0; u < n_cells; ++u) {
-          auto const cell = convert.l_to_ijk(u);
-          for (int a = 0; a < 3; ++a) ijk[3 * (size_t)u + a] = (int32_t)cell[a];
-        }
-        std::vector<int64_t> cell_index((size_t)n_cells);
-        cmx_check(cmx_state_cell_index(m_dev->state, n_cells, ijk.data(), cell_index.data()));
-        m_dev->site_order.resize((size_t)n_sites);
-        bool identity = true;
-        for (Index l = 0; l < n_sites; ++l) {
-          m_dev->site_order[(size_t)l] = (int64_t)convert.l_to_b(l) * n_cells + cell_index[(size_t)(l % n_cells)];
-          identity = identity && m_dev->site_order[(size_t)l] == (int64_t)l;
-        }
-        if (identity) m_dev->site_order.clear();
-        cmx_check(cmx_state_set_site_order(m_dev->state, identity ? nullptr : m_dev->site_order.data()));
-      }
-      clexulator::SparseCoefficients const &eci = get_clex_data(*this->system, "formation_energy").coefficients;
-      std::vector<uint32_t> index(eci.index.begin(), eci.index.end());
-      cmx_check(cmx_state_set_eci(m_dev->state, (int32_t)index.size(), index.data(), eci.value.data()));
-      // occupant bookkeeping of the reference-order mode (Conversions: asym unit, species)
-      const size_t n_sublat = this->system->occ_to_species.size();
-      std::vector<int32_t> asym(this->system->sublat_to_asym.begin(), this->system->sublat_to_asym.end());
-      std::vector<int32_t> species(n_sublat * m_max_occ, -1);
-      for (size_t b = 0; b < n_sublat; ++b)
-        for (size_t o = 0; o < this->system->occ_to_species[b].size(); ++o)
-          species[b * m_max_occ + o] = (int32_t)this->system->occ_to_species[b][o];
-      cmx_check(cmx_state_set_occupants(m_dev->state, asym.data(), species.data(),
-                                        (int32_t)get_composition_converter(*this->system).components().size()));
-    }
-    Eigen::VectorXi const &occupation = get_occupation(state);
-    if (occupation.size() != this->state_data->n_unitcells * (Index)this->system->occ_to_species.size())
-      throw std::runtime_error("Error in B200SemiGrandCanonicalCalculator: occupation size mismatch");
-    cmx_check(cmx_state_upload_occ(m_dev->state, 0, occupation.data()));
+    b200::bind_state(*m_dev, *this->state_data, *this->system, m_max_occ, "B200SemiGrandCanonicalCalculator");
     std::vector<double> exch =
         exchange_table(*this->system, state.conditions.vector_values.at("param_chem_pot"), m_max_occ);
     cmx_check(cmx_state_set_conditions(m_dev->state, 0, state.conditions.scalar_values.at("temperature"), exch.data()));
@@ -271,13 +196,7 @@ class B200SemiGrandCanonicalCalculator : public BaseMonteCalculator {
       }
       pass += n_passes;
       // RunManager counters (occupation_metropolis.hh:109-116)
-#ifdef CMX_HAVE_RUNMANAGER_BULK
-      run_manager.add_passes(n_passes, n_accept, n_attempt - n_accept);
-#else
-      for (int64_t q = 0; q < n_accept; ++q) run_manager.increment_n_accept();
-      for (int64_t q = n_accept; q < n_attempt; ++q) run_manager.increment_n_reject();
-      for (int64_t q = 0; q < n_attempt; ++q) run_manager.increment_step();
-#endif
+      b200::count_steps(run_manager, n_passes, n_attempt, n_accept);
       // the sampling functions read the host state (sampling_functions.cc): bring it up to date
       cmx_check(cmx_state_download_occ(m_dev->state, 0, occupation.data()));
       run_manager.sample_data_by_count_if_due(state);
@@ -299,10 +218,8 @@ class B200SemiGrandCanonicalCalculator : public BaseMonteCalculator {
   /// after `params` / `system` changed (BaseMonteCalculator.hh:107-113): load the tables
   void _reset() override {
     m_dev = std::make_shared<DeviceState>();
-    const int device = params.contains("cmx_device") ? (int)params.get_number("cmx_device") : 0;
-    cmx_check(cmx_tables_create_from_file(params.get_string("cmx_tables").c_str(), device, &m_dev->tables));
-    m_max_occ = 0;
-    for (auto const &sp : this->system->occ_to_species) m_max_occ = std::max<int>(m_max_occ, (int)sp.size());
+    b200::load_tables(*m_dev, params, "B200SemiGrandCanonicalCalculator");
+    m_max_occ = b200::max_occupants(*this->system);
   }
 
   /// deep copy: the clone gets its own device handles (re-created by reset / set_state_and_potential)

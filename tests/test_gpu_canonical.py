@@ -36,6 +36,8 @@ def _state(dev_tables, systems, case_sys, eci_key, N, T, occ, n_replicas=1):
         st.set_conditions(T, None, r)
         st.upload_occ(occ, r)
     swaps = canonical_swap_types(st.tables.host, sysd["sublat_to_asym"], o2s.tolist(), N)
+    # the library's default swap table (what a C / C++ caller such as the canonical plugin gets)
+    assert st.canonical_default_swaps() == [(a, b, tuple(t)) for a, b, t in swaps]
     return st, sysd, swaps
 
 

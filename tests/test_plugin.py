@@ -1,9 +1,9 @@
-"""The reference-side plugin (plugin/B200SemiGrandCanonicalCalculator.cc): C++ host code against
-the reference's plugin interface, calling the CUDA library through the C ABI only.  It is
-compiled with g++ against the stand-in headers of plugin/shim (libcasm is not in this image)
-and driven by plugin/test_plugin.cc the way MonteCalculator drives a plugin: dlopen,
-make_B200SemiGrandCanonicalCalculator(), reset(params, system), run(state, occ_location,
-run_manager)."""
+"""The reference-side plugins (plugin/B200SemiGrandCanonicalCalculator.cc,
+plugin/B200CanonicalCalculator.cc): C++ host code against the reference's plugin interface,
+calling the CUDA library through the C ABI only.  They are compiled with g++ against the
+stand-in headers of plugin/shim (libcasm is not in this image) and driven by
+plugin/test_plugin*.cc the way MonteCalculator drives a plugin: dlopen, make_<Name>(),
+reset(params, system), run(state, occ_location, run_manager)."""
 import subprocess
 from pathlib import Path
 
@@ -58,3 +58,34 @@ def test_plugin_run_equals_the_c_abi(built, variant):
     # a skewed supercell whose unit cells the caller numbers in its own order: the plugin asks
     # Conversions::l_to_ijk; a B-Va pair interacts exactly when it is a first-neighbour pair
     assert "general supercell ok" in r.stdout
+
+
+def test_canonical_plugin_builds_and_exports_the_factory(built):
+    """CPU: the canonical calculator compiles, exports make_B200CanonicalCalculator and binds
+    the pair-exchange entry points of the C ABI."""
+    so = PLUGIN / "_build" / "libB200CanonicalCalculator.so"
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True).stdout
+    assert " T make_B200CanonicalCalculator" in nm
+    und = subprocess.run(["nm", "-D", "--undefined-only", str(so)], capture_output=True, text=True).stdout
+    cmx = sorted({line.split()[-1] for line in und.splitlines() if " cmx_" in line})
+    for sym in ("cmx_canonical_sweep", "cmx_canonical_default_swaps", "cmx_canonical_set_swaps", "cmx_delta_e",
+                "cmx_state_set_site_order"):
+        assert sym in cmx
+    r = subprocess.run([str(PLUGIN / "_build" / "test_plugin_canonical"), str(so), str(built), "--no-gpu"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "canonical plugin ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_canonical_plugin_run_equals_the_c_abi(built):
+    """GPU: the canonical calculator's potential is the formation energy of the C ABI, a
+    two-site delta equals the difference of two evaluations, validate_state enforces the
+    conditions' composition (CanonicalCalculator.cc:318-360), and one run() conserves the
+    composition and leaves the occupation cmx_canonical_sweep gives for the same seed and the
+    default swap table."""
+    so = PLUGIN / "_build" / "libB200CanonicalCalculator.so"
+    r = subprocess.run([str(PLUGIN / "_build" / "test_plugin_canonical"), str(so), str(built)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "canonical plugin ok: 6 passes" in r.stdout
