@@ -2231,11 +2231,19 @@ static int sweep_prepare(cmx_state *s, const char *who) {
   CMX_CUDA(cudaSetDevice(s->t->device));
   SweepPlan &P = s->plan;
   int blocks;
-  if (use_stream(s) || use_pair2(s)) {
-    if (P.stream_capacity < 0 || P.stream_blocks == 0) {
-      int rc = stream_geometry(s);
-      if (rc) return rc;
+  bool coop = use_stream(s) || use_pair2(s);
+  if (coop && (P.stream_capacity < 0 || P.stream_blocks == 0)) {
+    int rc = stream_geometry(s);
+    if (rc == CMX_ERR_UNSUPPORTED && use_pair2(s)) {
+      // more replicas than co-resident blocks of the two-class kernel (2 per SM): this state
+      // sweeps with the per-neighbor-table kernel -- same random bits, same decisions
+      P.pair2 = false;
+      coop = false;
+    } else if (rc) {
+      return rc;
     }
+  }
+  if (coop) {
     blocks = P.stream_blocks;
   } else {
     uint32_t items;

@@ -576,6 +576,25 @@ def test_two_class_table_kernel_equals_pair_sum_and_term_list_kernels(dev_tables
         st.close()
 
 
+def test_two_class_table_kernel_gives_way_when_the_replicas_do_not_fit(dev_tables, systems):
+    """The two-class kernel is one cooperative launch with a grid row per replica (2 blocks per
+    SM: 296 rows on a B200).  A state with more replicas sweeps with the pair-sum kernel
+    instead of failing -- and leaves the trajectory the two-class kernel leaves on a state
+    that holds only the first replicas."""
+    mu = [0.2, -0.1]
+    N, many, few = (16, 4, 4), 320, 3
+    a, sysd, ex = _sweep_state(dev_tables, systems, "fcc", "eci_full", N, 900.0, mu, n_replicas=many, seed=5)
+    b, _, _ = _sweep_state(dev_tables, systems, "fcc", "eci_full", N, 900.0, mu, n_replicas=few, seed=5)
+    ca = a.sgc_sweep(3, seed=21)
+    cb = b.sgc_sweep(3, seed=21)
+    assert a.sweep_info()["evaluator"] == "pair_sum" and b.sweep_info()["evaluator"] == "pair_lut2"
+    for r in range(few):
+        assert (a.download_occ(r) == b.download_occ(r)).all()
+        assert ca[r].n_accept == cb[r].n_accept
+    a.close()
+    b.close()
+
+
 @pytest.mark.parametrize("T", [500.0, 900.0, 1500.0])
 @pytest.mark.parametrize("mu", [(0.3, -0.4), (0.0, 0.0), (-0.2, 0.2)])
 def test_checkerboard_matches_sequential_thermodynamics(dev_tables, systems, oracle, T, mu):
