@@ -21,6 +21,12 @@
 // sublattice pair, default 12), "cmx_swap_long_range" (default 1).
 #include "b200_common.hh"
 
+extern "C" {
+/// the reference's calculator of this ensemble (libcasm_clexmonte, CanonicalCalculator.cc:472-478):
+/// source of the standard sampling / analysis / state-modifying functions
+CASM::clexmonte::BaseMonteCalculator *make_CanonicalCalculator();
+}
+
 namespace CASM {
 namespace clexmonte {
 
@@ -60,10 +66,10 @@ class B200CanonicalPotential : public BaseMontePotential {
   }
 };
 
-class B200CanonicalCalculator : public BaseMonteCalculator {
+class B200CanonicalCalculator : public b200::DelegatingCalculator {
  public:
   B200CanonicalCalculator()
-      : BaseMonteCalculator(kName,
+      : DelegatingCalculator(&make_CanonicalCalculator, kName,
                             {},                    // required_basis_set
                             {},                    // required_local_basis_set
                             {"formation_energy"},  // required_clex

@@ -22,6 +22,12 @@
 //                     (cmx_metropolis_sequential) instead of the checkerboard sweeps
 #include "b200_common.hh"
 
+extern "C" {
+/// the reference's calculator of this ensemble (libcasm_clexmonte,
+/// SemiGrandCanonicalCalculator.cc:517-523): source of the standard sampling / analysis functions
+CASM::clexmonte::BaseMonteCalculator *make_SemiGrandCanonicalCalculator();
+}
+
 namespace CASM {
 namespace clexmonte {
 
@@ -102,10 +108,10 @@ class B200SemiGrandCanonicalPotential : public BaseMontePotential {
   }
 };
 
-class B200SemiGrandCanonicalCalculator : public BaseMonteCalculator {
+class B200SemiGrandCanonicalCalculator : public b200::DelegatingCalculator {
  public:
   B200SemiGrandCanonicalCalculator()
-      : BaseMonteCalculator("B200SemiGrandCanonicalCalculator",
+      : DelegatingCalculator(&make_SemiGrandCanonicalCalculator, "B200SemiGrandCanonicalCalculator",
                             {},                      // required_basis_set
                             {},                      // required_local_basis_set
                             {"formation_energy"},    // required_clex

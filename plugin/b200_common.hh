@@ -112,6 +112,62 @@ inline bool bind_state(DeviceState &dev, StateData const &state_data, system_typ
   return !same;
 }
 
+/// What a B200 calculator does NOT re-implement: the sampling functions, analysis functions,
+/// state-modifying functions and default sampling fixture of its ensemble are the reference's
+/// own.  They are obtained from the reference's calculator of the same ensemble (the C-linkage
+/// factories libcasm_clexmonte exports, forward-declared the way
+/// python/src/clexmonte_monte_calculator.cpp:34-45 does) and read the state through
+/// `calculation->state_data()` / `calculation->potential()` -- i.e. through THIS calculator's
+/// StateData and device potential.  Sampler names, JSON output and post-processing stay unchanged.
+class DelegatingCalculator : public BaseMonteCalculator {
+ public:
+  typedef BaseMonteCalculator *(*reference_factory)();
+  DelegatingCalculator(reference_factory make_reference, std::string _calculator_name,
+                       std::set<std::string> _required_basis_set, std::set<std::string> _required_local_basis_set,
+                       std::set<std::string> _required_clex, std::set<std::string> _required_multiclex,
+                       std::set<std::string> _required_local_clex, std::set<std::string> _required_local_multiclex,
+                       std::set<std::string> _required_dof_spaces, std::set<std::string> _required_params,
+                       std::set<std::string> _optional_params, bool _time_sampling_allowed, bool _update_atoms,
+                       bool _save_atom_info, bool _is_multistate_method)
+      : BaseMonteCalculator(_calculator_name, _required_basis_set, _required_local_basis_set, _required_clex,
+                            _required_multiclex, _required_local_clex, _required_local_multiclex, _required_dof_spaces,
+                            _required_params, _optional_params, _time_sampling_allowed, _update_atoms, _save_atom_info,
+                            _is_multistate_method),
+        m_reference(make_reference()) {}
+
+  std::map<std::string, state_sampling_function_type> standard_sampling_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const override {
+    return m_reference->standard_sampling_functions(calculation);
+  }
+  std::map<std::string, json_state_sampling_function_type> standard_json_sampling_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const override {
+    return m_reference->standard_json_sampling_functions(calculation);
+  }
+  std::map<std::string, results_analysis_function_type> standard_analysis_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const override {
+    return m_reference->standard_analysis_functions(calculation);
+  }
+  StateModifyingFunctionMap standard_modifying_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const override {
+    return m_reference->standard_modifying_functions(calculation);
+  }
+  std::optional<monte::SelectedEventFunctions> standard_selected_event_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const override {
+    return m_reference->standard_selected_event_functions(calculation);
+  }
+  sampling_fixture_params_type make_default_sampling_fixture_params(
+      std::shared_ptr<MonteCalculator> const &calculation, std::string label, bool write_results,
+      bool write_trajectory, bool write_observations, bool write_status, std::optional<std::string> output_dir,
+      std::optional<std::string> log_file, double log_frequency_in_s) const override {
+    return m_reference->make_default_sampling_fixture_params(calculation, label, write_results, write_trajectory,
+                                                             write_observations, write_status, output_dir, log_file,
+                                                             log_frequency_in_s);
+  }
+
+ private:
+  std::unique_ptr<BaseMonteCalculator> m_reference;
+};
+
 /// RunManager counters of n_attempt steps (occupation_metropolis.hh:109-116)
 template <typename RunManagerType>
 inline void count_steps(RunManagerType &run_manager, Index n_passes, int64_t n_attempt, int64_t n_accept) {

@@ -348,8 +348,35 @@ class BaseMontePotential {
                                          std::vector<int> const &new_occ) = 0;
 };
 
-// monte_calculator/BaseMonteCalculator.hh:47-264 (the sampling-function maps, selected-event
-// and KMC members are [EXT]-typed and not used by a Metropolis plugin: left out here)
+// [EXT]-typed values of the sampling / analysis / fixture interface (libcasm-monte:
+// StateSamplingFunction, jsonStateSamplingFunction, ResultsAnalysisFunction,
+// StateModifyingFunction, SelectedEventFunctions, SamplingFixtureParams; typedefs in
+// include/casm/clexmonte/definitions.hh).  Opaque here: a plugin only passes them through.
+struct state_sampling_function_type {
+  std::string name;
+};
+struct json_state_sampling_function_type {
+  std::string name;
+};
+struct results_analysis_function_type {
+  std::string name;
+};
+struct StateModifyingFunction {
+  std::string name;
+};
+typedef std::map<std::string, StateModifyingFunction> StateModifyingFunctionMap;
+struct sampling_fixture_params_type {
+  std::string label;
+  std::vector<std::string> sampler_names;
+};
+}  // namespace clexmonte
+namespace monte {
+struct SelectedEventFunctions {};
+}  // namespace monte
+namespace clexmonte {
+
+// monte_calculator/BaseMonteCalculator.hh:47-264 (the selected-event and KMC data members are
+// [EXT]-typed and not used by a Metropolis plugin: left out here)
 class BaseMonteCalculator {
  public:
   typedef default_engine_type engine_type;
@@ -383,6 +410,21 @@ class BaseMonteCalculator {
       if (!params.contains(key)) throw std::runtime_error("Error: missing required parameter '" + key + "'");
     this->_reset();
   }
+  // :121-151 -- the sampling / analysis / fixture maps every calculator provides
+  virtual std::map<std::string, state_sampling_function_type> standard_sampling_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const = 0;
+  virtual std::map<std::string, json_state_sampling_function_type> standard_json_sampling_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const = 0;
+  virtual std::map<std::string, results_analysis_function_type> standard_analysis_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const = 0;
+  virtual StateModifyingFunctionMap standard_modifying_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const = 0;
+  virtual std::optional<monte::SelectedEventFunctions> standard_selected_event_functions(
+      std::shared_ptr<MonteCalculator> const &calculation) const = 0;
+  virtual sampling_fixture_params_type make_default_sampling_fixture_params(
+      std::shared_ptr<MonteCalculator> const &calculation, std::string label, bool write_results,
+      bool write_trajectory, bool write_observations, bool write_status, std::optional<std::string> output_dir,
+      std::optional<std::string> log_file, double log_frequency_in_s) const = 0;
   virtual Validator validate_configuration(state_type &state) const = 0;
   virtual Validator validate_conditions(state_type &state) const = 0;
   virtual Validator validate_state(state_type &state) const = 0;

@@ -193,6 +193,21 @@ int main(int argc, char **argv) {
   if (!calc->required_clex.count("formation_energy") || !calc->required_params.count("cmx_tables"))
     return fail("required clex / params");
 
+  // the sampling / analysis / fixture maps are the reference's own (SemiGrandCanonicalCalculator.cc:238-330),
+  // handed through from its calculator of the same ensemble
+  {
+    auto sf = calc->standard_sampling_functions(nullptr);
+    auto af = calc->standard_analysis_functions(nullptr);
+    if (!sf.count("potential_energy") || !sf.count("clex.formation_energy") || !sf.count("param_chem_pot"))
+      return fail("standard_sampling_functions are not the reference's");
+    if (!af.count("heat_capacity") || !af.count("param_susc")) return fail("standard_analysis_functions are not the reference's");
+    if (!calc->standard_modifying_functions(nullptr).empty()) return fail("standard_modifying_functions");
+    if (calc->standard_selected_event_functions(nullptr).has_value()) return fail("standard_selected_event_functions");
+    auto fx = calc->make_default_sampling_fixture_params(nullptr, "thermo", true, false, false, true, std::nullopt,
+                                                         std::nullopt, 600.0);
+    if (fx.label != "thermo" || fx.sampler_names.size() != 4) return fail("make_default_sampling_fixture_params");
+  }
+
   // the FCC A-B-Va test system (tests/unit/clexmonte/data/FCC_binary_vacancy): one sublattice,
   // occupants A, B, Va; composition axes origin A, end members B and Va; shipped sparse ECI
   auto system = std::make_shared<system_type>();

@@ -36,6 +36,16 @@ int main(int argc, char **argv) {
   if (!calc->required_clex.count("formation_energy") || !calc->required_params.count("cmx_tables"))
     return fail("required clex / params");
 
+  // the sampling / analysis / state-modifying maps are the reference's own (CanonicalCalculator.cc:171-280)
+  {
+    auto sf = calc->standard_sampling_functions(nullptr);
+    if (!sf.count("potential_energy") || !sf.count("mol_composition") || sf.count("param_chem_pot"))
+      return fail("standard_sampling_functions are not the reference's");
+    if (!calc->standard_analysis_functions(nullptr).count("heat_capacity")) return fail("standard_analysis_functions");
+    if (!calc->standard_modifying_functions(nullptr).count("enforce.composition")) return fail("standard_modifying_functions");
+    if (!calc->standard_json_sampling_functions(nullptr).count("config")) return fail("standard_json_sampling_functions");
+  }
+
   // the FCC A-B-Va test system (tests/unit/clexmonte/data/FCC_binary_vacancy), shipped sparse ECI
   auto system = std::make_shared<system_type>();
   system->sublat_to_asym = {0};

@@ -38,6 +38,9 @@ def test_plugin_builds_and_exports_the_factory(built):
     und = subprocess.run(["nm", "-D", "--undefined-only", str(so)], capture_output=True, text=True).stdout
     cmx = sorted({line.split()[-1] for line in und.splitlines() if " cmx_" in line})
     assert "cmx_sgc_sweep" in cmx and "cmx_delta_e" in cmx and "cmx_tables_create_from_file" in cmx
+    # ... and the reference's own calculator of the ensemble (libcasm_clexmonte; a stand-in here),
+    # from which the standard sampling / analysis functions are handed through
+    assert " U make_SemiGrandCanonicalCalculator" in und
     r = subprocess.run([str(PLUGIN / "_build" / "test_plugin"), str(so), str(built), "--no-gpu"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
