@@ -22,6 +22,21 @@ def test_header_symbols_exported():
         assert hasattr(L, name), name
 
 
+def test_header_constants_match_the_binding():
+    """Every status code, sweep flag and state option of include/cmx_b200.h has the same value
+    in the ctypes binding (the plugin and the Python host must mean the same bits)."""
+    header = (ROOT / "include" / "cmx_b200.h").read_text()
+    defines = {m.group(1): int(m.group(2)) for m in
+               re.finditer(r"^#define\s+(CMX_[A-Z0-9_]+)\s+(\d+)u?\b", header, flags=re.M)}
+    names = [n for n in defines if n.startswith(("CMX_SWEEP_", "CMX_ERR_", "CMX_STATE_")) or n == "CMX_OK"]
+    assert {"CMX_SWEEP_DE_SUM", "CMX_SWEEP_FORCE_GENERIC", "CMX_SWEEP_STREAM", "CMX_SWEEP_THREAD_GENERIC",
+            "CMX_SWEEP_PAIR_SUM", "CMX_STATE_LINEAR_ROWS", "CMX_OK", "CMX_ERR_CUDA"} <= set(names)
+    for n in names:
+        assert getattr(_capi, n) == defines[n], n
+    flags = [defines[n] for n in names if n.startswith("CMX_SWEEP_")]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags)   # distinct single bits
+
+
 def test_version_and_device_count():
     assert _capi.lib().cmx_version() >= 100
     assert _capi.device_count() >= 0
