@@ -108,9 +108,18 @@ class B200CanonicalCalculator : public b200::DelegatingCalculator {
     const size_t n_sublat = this->system->occ_to_species.size();
     const Index n_cells = occupation.size() / (Index)n_sublat;
     std::vector<double> mol((size_t)want.size(), 0.0);
+    if (n_cells == 0 || occupation.size() != n_cells * (Index)n_sublat) {
+      v.error.insert("Error: the occupation does not fit the system's sublattices");
+      return v;
+    }
     for (Index l = 0; l < occupation.size(); ++l) {
-      const Index species = this->system->occ_to_species[(size_t)(l / n_cells)][(size_t)occupation[l]];
-      if (species < (Index)mol.size()) mol[(size_t)species] += 1.0 / (double)n_cells;
+      auto const &allowed = this->system->occ_to_species[(size_t)(l / n_cells)];
+      if (occupation[l] < 0 || (size_t)occupation[l] >= allowed.size()) {
+        v.error.insert("Error: occupant index out of range");
+        return v;
+      }
+      const Index species = allowed[(size_t)occupation[l]];
+      if (species >= 0 && species < (Index)mol.size()) mol[(size_t)species] += 1.0 / (double)n_cells;
     }
     for (long q = 0; q < want.size(); ++q)
       if (std::fabs(mol[(size_t)q] - want[q]) > this->mol_composition_tol)
