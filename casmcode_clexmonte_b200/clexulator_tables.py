@@ -718,6 +718,87 @@ def read_eci(data, corr_size: Optional[int] = None) -> Tuple[np.ndarray, np.ndar
     return np.array(idx, dtype=np.uint32), np.array(val, dtype=np.float64)
 
 
+# ---------------------------------------------------------------------------
+# basis.json reader: the reference's own description of the basis set, used to cross-check
+# an exported table
+# ---------------------------------------------------------------------------
+def read_basis_json(data) -> Dict:
+    """The parts of a CASM ``basis.json`` (written next to the generated Clexulator,
+    e.g. tests/unit/clexmonte/data/FCC_binary_vacancy/basis_sets/bset.default/basis.json)
+    that describe what the generated source computes:
+
+    * ``phi[b][f][occ]``: occupation site basis functions per sublattice, occupants in the
+      order of ``prim.basis[b].occupants`` (``site_functions[*].occ.basis``);
+    * ``orbits``: ``linear_orbit_index``, multiplicity, prototype cluster sites ``(b, i, j, k)``
+      and the ``linear_function_index`` of every cluster function of the orbit.
+    """
+    if isinstance(data, (str, Path)):
+        import json
+        data = json.loads(Path(data).read_text())
+    occupants = [list(site["occupants"]) for site in data["prim"]["basis"]]
+    phi: Dict[int, List[List[float]]] = {}
+    for sf in data.get("site_functions", []):
+        b = int(sf["sublat"])
+        basis = (sf.get("occ") or {}).get("basis") or {}
+
+        def f_index(key: str) -> int:       # "\\phi_{b,f}"
+            m = re.search(r"\{\s*\d+\s*,\s*(\d+)\s*\}", key)
+            if not m:
+                raise ValueError(f"basis.json: unrecognised site function name {key!r}")
+            return int(m.group(1))
+        rows = sorted(((f_index(k), v) for k, v in basis.items()), key=lambda kv: kv[0])
+        phi[b] = [[float(v[name]) for name in occupants[b]] for _, v in rows]
+    orbits = []
+    for orb in data["orbits"]:
+        orbits.append(dict(
+            index=int(orb["linear_orbit_index"]), mult=int(orb["mult"]),
+            sites=[tuple(int(x) for x in site) for site in orb["prototype"]["sites"]],
+            functions=[int(cf["linear_function_index"]) for cf in orb.get("cluster_functions", [])]))
+    return dict(occupants=occupants, phi=phi, orbits=orbits)
+
+
+def check_tables_against_basis(t: "ClexulatorTables", basis) -> None:
+    """Cross-check exported tables against the project's ``basis.json``: number of functions,
+    occupants per sublattice, the site basis functions (to the 6 digits the generated source
+    prints), the orbit of every correlation, and per global function the cluster size (factors
+    per term), the multiplicity (the divisor, and a whole number of terms per equivalent
+    cluster).  Raises ValueError listing every mismatch."""
+    if not isinstance(basis, dict) or "orbits" not in basis or "phi" not in basis:
+        basis = read_basis_json(basis)
+    bad: List[str] = []
+    n_functions = sum(len(o["functions"]) for o in basis["orbits"])
+    if n_functions != t.corr_size:
+        bad.append(f"basis.json lists {n_functions} cluster functions, the source declares corr_size {t.corr_size}")
+    for b, occ in enumerate(basis["occupants"]):
+        if b < t.n_sublat and len(occ) != int(t.n_occ[b]):
+            bad.append(f"sublattice {b}: {len(occ)} occupants in basis.json, {int(t.n_occ[b])} in the tables")
+    for b, rows in basis["phi"].items():
+        for f, row in enumerate(rows):
+            got = t.phi[b, f, :len(row)] if b < t.n_sublat and f < t.n_func else None
+            if got is None or not np.allclose(got, row, rtol=0.0, atol=5e-7):
+                bad.append(f"site function phi_{{{b},{f}}}: basis.json {row}, tables {None if got is None else got.tolist()}")
+    for orb in basis["orbits"]:
+        for c in orb["functions"]:
+            if c >= t.corr_size:
+                continue
+            if len(t.corr_orbit) and int(t.corr_orbit[c]) != orb["index"]:
+                bad.append(f"function {c}: orbit {int(t.corr_orbit[c])} in the source, {orb['index']} in basis.json")
+            n_terms = 0
+            for g in range(int(t.global_gbeg[c]), int(t.global_gbeg[c + 1])):
+                if orb["sites"] and t.group_div[g] not in (0.0, float(orb["mult"])):
+                    bad.append(f"function {c}: divisor {t.group_div[g]} in the source, multiplicity {orb['mult']} in basis.json")
+                for e in range(int(t.group_ebeg[g]), int(t.group_ebeg[g + 1])):
+                    for tm in range(int(t.elem_tbeg[e]), int(t.elem_tbeg[e + 1])):
+                        n_terms += 1
+                        nf = int(t.term_fbeg[tm + 1] - t.term_fbeg[tm])
+                        if nf != len(orb["sites"]):
+                            bad.append(f"function {c}: a term with {nf} factors, the orbit's clusters have {len(orb['sites'])} sites")
+            if orb["sites"] and (n_terms == 0 or n_terms % orb["mult"]):
+                bad.append(f"function {c}: {n_terms} terms is not a multiple of the multiplicity {orb['mult']}")
+    if bad:
+        raise ValueError("tables do not match basis.json:\n  " + "\n  ".join(bad))
+
+
 def _main(argv=None) -> int:
     """python -m casmcode_clexmonte_b200.clexulator_tables <Clexulator.cc> <out.npz> [eci.json] [--flat out.cmxt]
 

@@ -39,7 +39,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import kmc as K
-from .clexulator_tables import ClexulatorTables, parse_clexulator_source, read_eci
+from .clexulator_tables import ClexulatorTables, check_tables_against_basis, parse_clexulator_source, read_eci
 
 
 class SystemError_(ValueError):
@@ -163,6 +163,13 @@ def load_system(source, search_path: Sequence = ()) -> System:
             if b in set(int(x) for x in t.nlist_sublat) and int(t.n_occ[b]) != len(r):
                 raise SystemError_(f"basis_sets/{name}: sublattice {b} has {int(t.n_occ[b])} occupants in the "
                                    f"clexulator and {len(r)} in the prim")
+        # "basis": the project's basis.json (System_json_io.cc: basis_sets/<name>/{source, basis});
+        # when it is there the exported tables must agree with it
+        if bs.get("basis"):
+            try:
+                check_tables_against_basis(t, _resolve(bs["basis"], roots, f"basis_sets/{name}/basis"))
+            except ValueError as e:
+                raise SystemError_(f"basis_sets/{name}: {e}") from None
         sysd.basis_sets[name] = t
 
     def basis(name, entry, what):

@@ -64,3 +64,44 @@ def test_reference_systems_load_to_the_committed_facts(load_tables):
         assert [[list(x) for x in ev["sites"]] for ev in e["events"]] == [ev["sites"] for ev in ge["events"]]
         assert e["kra"][1].tolist() == ge["kra"]["value"] and e["freq"][1].tolist() == ge["freq"]["value"]
         assert len(k.local_basis_sets[e["local_basis_set"]]["tables"]) == 6
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="the reference's fixtures are not on this machine")
+def test_exported_tables_match_the_projects_basis_json(load_tables):
+    """the project's basis.json (the reference's own description of the basis set)
+    agrees with the tables exported from the generated source -- number of functions, occupants,
+    site basis functions, orbit, cluster size and multiplicity of every function -- and the
+    checker names what differs when a table is tampered with."""
+    import copy
+
+    from casmcode_clexmonte_b200.clexulator_tables import check_tables_against_basis, read_basis_json
+    path = REFERENCE / "tests/unit/clexmonte/data/FCC_binary_vacancy/basis_sets/bset.default/basis.json"
+    basis = read_basis_json(path)
+    assert basis["occupants"] == [["A", "B", "Va"]]
+    assert [(o["index"], o["mult"], len(o["sites"]), o["functions"]) for o in basis["orbits"]] == \
+        [(0, 1, 0, [0]), (1, 1, 1, [1, 2]), (2, 6, 2, [3, 4, 5]), (3, 3, 2, [6, 7, 8])]
+    t = load_tables("fcc_default")
+    check_tables_against_basis(t, basis)
+    check_tables_against_basis(t, path)
+    bad = copy.copy(t)
+    bad.phi = t.phi.copy()
+    bad.phi[0, 1, 2] = 0.5
+    bad.group_div = t.group_div.copy()
+    bad.group_div[int(t.global_gbeg[3])] = 4.0
+    with pytest.raises(ValueError) as e:
+        check_tables_against_basis(bad, basis)
+    assert "phi_{0,1}" in str(e.value) and "multiplicity 6" in str(e.value)
+    # the synthetic basis of configs[0] has no basis.json: a wrong one is refused
+    with pytest.raises(ValueError):
+        check_tables_against_basis(load_tables("fcc_synthetic"), basis)
+    # load_system runs the same check when a basis set names its basis.json
+    # (System_json_io.cc: basis_sets/<name>/{source, basis})
+    root = REFERENCE / "python/tests/data/FCC_binary_vacancy"
+    data = json.loads((root / "system.json").read_text())
+    data["basis_sets"]["default"]["basis"] = str(path)
+    s = load_system(data, search_path=[root])
+    assert s.basis_sets["default"].corr_size == 9
+    data["basis_sets"]["default"]["basis"] = "basis_sets/bset.A_Va_1NN/basis.json"   # another basis set's description
+    with pytest.raises(SystemError_) as e:
+        load_system(data, search_path=[root])
+    assert "basis_sets/default" in str(e.value) and "basis.json" in str(e.value)
