@@ -753,12 +753,14 @@ def read_basis_json(data) -> Dict:
         orbits.append(dict(
             index=int(orb["linear_orbit_index"]), mult=int(orb["mult"]),
             sites=[tuple(int(x) for x in site) for site in orb["prototype"]["sites"]],
-            functions=[int(cf["linear_function_index"]) for cf in orb.get("cluster_functions", [])]))
+            functions=([int(cf["linear_function_index"]) for cf in orb["cluster_functions"]]
+                       if "cluster_functions" in orb else None)))     # None: a clust.json (orbits only)
     return dict(occupants=occupants, phi=phi, orbits=orbits)
 
 
 def check_tables_against_basis(t: "ClexulatorTables", basis) -> None:
-    """Cross-check exported tables against the project's ``basis.json``: number of functions,
+    """Cross-check exported tables against the project's ``basis.json`` (or ``clust.json``: the
+    same orbits without the functions): number of functions,
     occupants per sublattice, the site basis functions (to the 6 digits the generated source
     prints), the orbit of every correlation, and per global function the cluster size (factors
     per term), the multiplicity (the divisor, and a whole number of terms per equivalent
@@ -766,6 +768,15 @@ def check_tables_against_basis(t: "ClexulatorTables", basis) -> None:
     if not isinstance(basis, dict) or "orbits" not in basis or "phi" not in basis:
         basis = read_basis_json(basis)
     bad: List[str] = []
+    if any(o["functions"] is None for o in basis["orbits"]):
+        # a clust.json: orbits and prototype clusters only -- the functions of an orbit are the
+        # ones the generated source assigns to it
+        if not len(t.corr_orbit):
+            raise ValueError("tables without corr_orbit cannot be checked against a clust.json")
+        for o in basis["orbits"]:
+            o["functions"] = [c for c in range(t.corr_size) if int(t.corr_orbit[c]) == o["index"]]
+        if sorted(set(int(x) for x in t.corr_orbit)) != sorted(o["index"] for o in basis["orbits"] if o["functions"]):
+            bad.append("the orbits of the source's functions are not the orbits of clust.json")
     n_functions = sum(len(o["functions"]) for o in basis["orbits"])
     if n_functions != t.corr_size:
         bad.append(f"basis.json lists {n_functions} cluster functions, the source declares corr_size {t.corr_size}")
@@ -795,6 +806,14 @@ def check_tables_against_basis(t: "ClexulatorTables", basis) -> None:
                             bad.append(f"function {c}: a term with {nf} factors, the orbit's clusters have {len(orb['sites'])} sites")
             if orb["sites"] and (n_terms == 0 or n_terms % orb["mult"]):
                 bad.append(f"function {c}: {n_terms} terms is not a multiple of the multiplicity {orb['mult']}")
+            # the prototype cluster lies in the function's site neighborhood (m_orbit_site_neighborhood)
+            if len(t.orbit_nbhd_beg) == t.corr_size + 1 and len(orb["sites"]) > 1:
+                nb = {tuple(int(x) for x in r) for r in t.orbit_nbhd[int(t.orbit_nbhd_beg[c]):int(t.orbit_nbhd_beg[c + 1])]}
+                o0 = orb["sites"][0]
+                for site in orb["sites"]:
+                    rel = (site[0], site[1] - o0[1], site[2] - o0[2], site[3] - o0[3])   # about the first site's cell
+                    if rel not in nb:
+                        bad.append(f"function {c}: prototype site {site} is not in the function's site neighborhood")
     if bad:
         raise ValueError("tables do not match basis.json:\n  " + "\n  ".join(bad))
 

@@ -91,6 +91,15 @@ def test_exported_tables_match_the_projects_basis_json(load_tables):
     with pytest.raises(ValueError) as e:
         check_tables_against_basis(bad, basis)
     assert "phi_{0,1}" in str(e.value) and "multiplicity 6" in str(e.value)
+    # clust.json (the orbits without the functions) checks the same tables through the source's
+    # own function -> orbit assignment and the prototype clusters
+    check_tables_against_basis(t, path.with_name("clust.json"))
+    bad2 = copy.copy(t)
+    bad2.orbit_nbhd = t.orbit_nbhd.copy()
+    bad2.orbit_nbhd[int(t.orbit_nbhd_beg[6]):int(t.orbit_nbhd_beg[7]), 1:] += 5
+    with pytest.raises(ValueError) as e:
+        check_tables_against_basis(bad2, path.with_name("clust.json"))
+    assert "site neighborhood" in str(e.value)
     # the synthetic basis of configs[0] has no basis.json: a wrong one is refused
     with pytest.raises(ValueError):
         check_tables_against_basis(load_tables("fcc_synthetic"), basis)
