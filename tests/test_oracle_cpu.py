@@ -269,3 +269,61 @@ def test_semigrand_exchange_table(systems):
     assert ex[0, 1, 0] == pytest.approx(-0.3) and ex[0, 1, 2] == pytest.approx(-0.5)
     with pytest.raises(ValueError):
         semigrand_exchange_table(systems["fcc"]["occ_to_species"], Rt, [0.3], 3)
+
+
+def test_point_pair_delta_e_depends_on_shell_counts_only(oracle, systems, load_tables):
+    """The premise of the count-table sweep kernels, checked on the reference's own generated
+    kernels: with the dense FCC ECI (points + 1NN + 2NN pairs) the delta E of a site flip is a
+    function of (occupant, proposal, species counts of the first shell, species counts of the
+    second shell) -- two arrangements with the same counts give the same delta E (to rounding),
+    whatever the rest of the box holds -- and with the sparse ECI (points + 1NN pairs) of the
+    first-shell counts alone."""
+    if oracle is None:
+        pytest.skip("oracle/_ref not built")
+    N = 8
+    sc = oracle.RefClexulator("fcc_default").supercell(N)
+    nbr = np.asarray(load_tables("fcc_default").nbr).reshape(-1, 4)
+    shell1, shell2 = nbr[1:13, :3], nbr[13:19, :3]
+    assert len(shell1) == 12 and len(shell2) == 6
+
+    def site(c):
+        return int((c[0] % N) + N * ((c[1] % N) + N * (c[2] % N)))
+
+    c0 = np.array([4, 3, 5])
+    l0 = site(c0)
+    l1 = [site(c0 + d) for d in shell1]
+    l2 = [site(c0 + d) for d in shell2]
+    near = set(l1) | set(l2) | {l0}
+    rng = np.random.default_rng(17)
+
+    def arrangement(nB1, nV1, nB2, nV2, oi):
+        occ = rng.integers(0, 3, sc.n_sites).astype(np.int32)      # the rest of the box: anything
+        for ls, nB, nV in ((l1, nB1, nV1), (l2, nB2, nV2)):
+            vals = np.array([1] * nB + [2] * nV + [0] * (len(ls) - nB - nV), dtype=np.int32)
+            occ[ls] = rng.permutation(vals)
+        occ[l0] = oi
+        return occ
+
+    for eci_key, second_shell_matters in (("eci_full", True), ("eci_sparse", False)):
+        eci = systems["fcc"][eci_key]
+        scale = float(np.abs(eci["value"]).sum())
+        seen_second = False
+        for _ in range(60):
+            nV1 = int(rng.integers(0, 13))
+            nB1 = int(rng.integers(0, 13 - nV1))
+            nV2 = int(rng.integers(0, 7))
+            nB2 = int(rng.integers(0, 7 - nV2))
+            oi = int(rng.integers(0, 3))
+            of = (oi + 1 + int(rng.integers(0, 2))) % 3
+            dE = [sc.occ_delta_value(arrangement(nB1, nV1, nB2, nV2, oi), [l0], [of], eci["index"], eci["value"])
+                  for _ in range(3)]
+            assert max(dE) - min(dE) <= 1e-12 * scale, (eci_key, nB1, nV1, nB2, nV2, oi, of, dE)
+            # a different second-shell count changes dE exactly when 2NN pairs carry coefficients
+            if nB2 + nV2 < 6:
+                other = sc.occ_delta_value(arrangement(nB1, nV1, nB2 + 1, nV2, oi), [l0], [of], eci["index"], eci["value"])
+                if abs(other - dE[0]) > 1e-9 * scale:
+                    seen_second = True
+                if not second_shell_matters:
+                    assert abs(other - dE[0]) <= 1e-12 * scale
+        assert seen_second == second_shell_matters
+    assert len(near) == 19       # SURVEY 8d's 19-site neighbourhood
