@@ -231,6 +231,22 @@ int main(int argc, char **argv) {
     return fail("reset() accepted params without cmx_tables");
   } catch (std::runtime_error const &) {
   }
+  // the stand-in Conversions of a skewed supercell: det(T) unit cells, pairwise inequivalent
+  // modulo the supercell lattice, in an order that is not the library's box order
+  {
+    state_type skew;
+    const long Tg[3][3] = {{8, 0, 0}, {2, 8, 0}, {4, 2, 8}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) skew.configuration.transformation_matrix_to_super(i, j) = Tg[i][j];
+    monte::OccLocation none;
+    StateData sd(system, &skew, &none);
+    if (sd.n_unitcells != 512 || sd.convert->m_unitl_to_ijk.size() != 512) return fail("stand-in unit cell enumeration");
+    for (Index u = 0; u < 512; u += 37) {
+      auto const c = sd.convert->l_to_ijk(u);
+      const long x[3] = {c[0] + 8, c[1] + 2 + 8, c[2] + 4 + 2 - 8};  // + (column 0) + (column 1) - (column 2)
+      if (find_unitl(*sd.convert, sd.transformation_matrix_to_super, x) != u) return fail("stand-in unit cells are not a transversal of the supercell lattice");
+    }
+  }
   if (no_gpu) {
     std::printf("plugin ok (interface only: no GPU)\n");
     return 0;
