@@ -1,6 +1,10 @@
 """Host logic of the run series (casmcode_clexmonte_b200/run_series.py)."""
+import json
+
 import numpy as np
 import pytest
+
+from conftest import REFERENCE
 
 from casmcode_clexmonte_b200.run_series import conditions_path, make_incremented_values
 
@@ -131,3 +135,123 @@ def test_completed_runs_save_rules_and_restart(tmp_path):
     (tmp_path / "b" / "completed_runs.json").write_text('[{"conditions": {}}]')
     with pytest.raises(ValueError):
         CompletedRuns(p).read()
+
+
+_AXES = dict(components=["Zr", "Va", "O"], Rt=[[0.0, -0.5, 0.5]], origin=[2.0, 2.0, 0.0], end_members=[[2.0, 0.0, 2.0]])
+
+
+def _run_params(**over):
+    fixture = {"sampling": {"sample_by": "pass", "spacing": "linear", "begin": 0, "period": 5,
+                            "quantities": ["potential_energy", "param_composition"], "sample_trajectory": False},
+               "completion_check": {"cutoff": {"count": {"min": None, "max": 100}},
+                                    "convergence": [{"quantity": "potential_energy", "precision": 0.001}]},
+               "results_io": {"method": "json", "kwargs": {"output_dir": "out/thermo"}}}
+    p = {"state_generation": {"method": "incremental", "kwargs": {
+            "initial_configuration": {"method": "fixed", "kwargs": {
+                "transformation_matrix_to_supercell": [[8, 0, 0], [0, 8, 0], [0, 0, 4]], "_dof": None}},
+            "initial_conditions": {"temperature": 1000.0, "param_chem_pot": {"a": -4.0}},
+            "conditions_increment": {"temperature": 0.0, "param_chem_pot": [0.4]},
+            "n_states": 11, "dependent_runs": False, "modifiers": []}},
+         "sampling_fixtures": {"thermo": fixture}}
+    p.update(over)
+    return p
+
+
+def test_run_params_reader():
+    """run_params.json of the reference's command-line programs -> the arguments of a run
+    series (RunParams_json_io_impl.hh:38-130, StateGenerator_json_io.cc, parse_conditions.cc:45-66);
+    what the device path does not do is refused by key, never dropped."""
+    import copy
+
+    from casmcode_clexmonte_b200.run_params import RunParamsError, read_run_params
+    p = read_run_params(_run_params(), _AXES)
+    assert p["N"] == (8, 8, 4) and p["occupation"] is None and p["n_states"] == 11 and not p["dependent_runs"]
+    assert p["initial_conditions"] == {"temperature": 1000.0, "param_chem_pot": [-4.0]}
+    assert p["conditions_increment"] == {"temperature": 0.0, "param_chem_pot": [0.4]}
+    fx = p["fixtures"]["thermo"]
+    assert (fx["sample_period"], fx["n_samples"], fx["max_count"], fx["output_dir"]) == (5, 20, 100, "out/thermo")
+    assert fx["not_applied"] == ["convergence of 'potential_energy' to 0.001"] and not fx["with_corr"]
+    # a skewed supercell is read (and left to the caller: run series on the device need a diagonal one)
+    q = _run_params()
+    q["state_generation"]["kwargs"]["initial_configuration"]["kwargs"]["transformation_matrix_to_supercell"] = \
+        [[-4, 4, 4], [4, -4, 4], [4, 4, -4]]
+    assert read_run_params(q, _AXES)["N"] is None
+    # an explicit occupation
+    q = _run_params()
+    q["state_generation"]["kwargs"]["initial_configuration"]["kwargs"]["dof"] = {"occ": [0, 1] * 8}
+    assert read_run_params(q, _AXES)["occupation"].tolist() == [0, 1] * 8
+
+    def refused(mutate, key):
+        q = copy.deepcopy(_run_params())
+        mutate(q)
+        with pytest.raises(RunParamsError) as e:
+            read_run_params(q, _AXES)
+        assert key in str(e.value), str(e.value)
+
+    refused(lambda q: q["state_generation"].update(method="enumeration"), "state_generation/method")
+    refused(lambda q: q["state_generation"]["kwargs"]["initial_configuration"].update(method="random"), "initial_configuration/method")
+    refused(lambda q: q["state_generation"]["kwargs"].update(modifiers=["match.mol_composition"]), "modifiers")
+    refused(lambda q: q["state_generation"]["kwargs"]["initial_conditions"].update(param_chem_pot={"b": 1.0}), "param_chem_pot")
+    refused(lambda q: q["state_generation"]["kwargs"]["initial_conditions"].update(order_parameter_pot=[1.0]), "order_parameter_pot")
+    refused(lambda q: q["state_generation"]["kwargs"]["conditions_increment"].update(mol_composition=[0, 0, 0]), "conditions_increment/mol_composition")
+    refused(lambda q: q["sampling_fixtures"]["thermo"]["sampling"].update(sample_by="time"), "sample_by")
+    refused(lambda q: q["sampling_fixtures"]["thermo"]["sampling"].update(spacing="log"), "spacing")
+    refused(lambda q: q["sampling_fixtures"]["thermo"]["completion_check"]["cutoff"]["count"].update(max=None), "count/max")
+    refused(lambda q: q["sampling_fixtures"]["thermo"]["completion_check"]["cutoff"].update(clocktime={"max": 60}), "clocktime")
+    refused(lambda q: q["sampling_fixtures"]["thermo"]["results_io"].update(method="hdf5"), "results_io/method")
+    refused(lambda q: q.update(before_first_run={"x": {}}), "before_first_run")
+    refused(lambda q: q.update(sampling_fixtures={"thermo": "missing_file.json"}), "missing_file.json")
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="the reference's fixtures are not on this machine")
+def test_run_params_reader_on_the_reference_input_decks():
+    """The ZrO input decks of the reference's own tests (tests/unit/clexmonte/data/Clex_ZrO_Occ)."""
+    from casmcode_clexmonte_b200.run_params import read_run_params
+    from casmcode_clexmonte_b200.system import composition_axes
+    root = REFERENCE / "tests/unit/clexmonte/data/Clex_ZrO_Occ"
+    axes = composition_axes(json.loads((root / "system.json").read_text())["composition_axes"])
+    p = read_run_params(root / "run_params_sgc_complete.json", axes)
+    assert p["N"] == (6, 6, 6) and p["n_states"] == 11 and not p["dependent_runs"]
+    assert p["initial_conditions"]["param_chem_pot"] == [-4.0] and p["conditions_increment"]["param_chem_pot"] == [0.4]
+    fx = p["fixtures"]["thermo"]
+    assert fx["n_samples"] == 100 and fx["sample_period"] == 1 and fx["with_corr"]
+    # fixtures named by file (the tests of the reference fill the "TODO" placeholders in)
+    d = json.loads((root / "run_params_sgc_by_file.json").read_text())
+    d["sampling_fixtures"] = {"thermo_period1": "thermo_sampling.period1.json", "thermo_period10": "thermo_sampling.period10.json"}
+    q = read_run_params(d, axes, search_path=[root])
+    assert {k: (v["sample_period"], v["n_samples"]) for k, v in q["fixtures"].items()} == \
+        {"thermo_period1": (1, 1000), "thermo_period10": (10, 100)}
+    c = read_run_params(root / "run_params_complete.json", axes)     # the canonical deck: mol_composition path
+    assert c["initial_conditions"]["mol_composition"] == [2.0, 1.9, 0.1] and c["conditions_increment"]["temperature"] == 10.0
+
+
+def test_run_series_from_params_maps_the_deck_onto_run_series(monkeypatch):
+    """The arguments run_series receives from an input deck (the device run itself is covered
+    by test_run_series_batches_the_conditions_path)."""
+    from types import SimpleNamespace
+
+    import casmcode_clexmonte_b200.run_series as RS
+    from casmcode_clexmonte_b200.run_params import RunParamsError, read_run_params, run_series_from_params
+    seen = {}
+
+    def fake(tables, N, system, eci_index, eci_value, initial, increment, n_states, occupation, **kw):
+        seen.update(N=N, eci=(eci_index, eci_value), initial=initial, increment=increment, n_states=n_states,
+                    n_sites=occupation.size, **kw)
+        return []
+
+    monkeypatch.setattr(RS, "run_series", fake)
+    system = SimpleNamespace(occ_to_species=[[0], [0], [1, 2], [1, 2]], clex={"formation_energy": {"index": [0, 1], "value": [0.5, 1.0]}},
+                             as_dict=lambda: {"n_species": 3})
+    params = read_run_params(_run_params(), _AXES)
+    run_series_from_params(None, system, params, seed=7, n_equilibration_passes=3)
+    assert seen["N"] == (8, 8, 4) and seen["n_sites"] == 8 * 8 * 4 * 4 and seen["n_states"] == 11
+    assert seen["eci"] == ([0, 1], [0.5, 1.0]) and seen["initial"]["param_chem_pot"] == [-4.0]
+    assert (seen["n_equilibration_passes"], seen["n_samples"], seen["sample_period"], seen["seed"]) == (3, 20, 5, 7)
+    assert seen["dependent_runs"] is False and seen["with_corr"] is False
+    assert seen["output_params"].output_dir == "out/thermo"
+    two = _run_params()
+    two["sampling_fixtures"]["second"] = two["sampling_fixtures"]["thermo"]
+    with pytest.raises(RunParamsError):
+        run_series_from_params(None, system, read_run_params(two, _AXES))
+    run_series_from_params(None, system, read_run_params(two, _AXES), fixture="second", output_dir="elsewhere")
+    assert seen["output_params"].output_dir == "elsewhere"
