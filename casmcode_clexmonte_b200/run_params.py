@@ -184,14 +184,19 @@ def read_run_params(source, axes: Dict, search_path: Sequence = ()) -> Dict:
 
 
 def run_series_from_params(tables, system, params: Dict, fixture: Optional[str] = None, clex: str = "formation_energy",
-                           seed: int = 0, n_equilibration_passes: int = 0, output_dir=None) -> List[Dict]:
-    """A semi-grand canonical run series from read_run_params(...) output.  `system`: a
-    system.System (load_system); `tables`: _capi.Tables of the clex's basis set.  One sampling
-    fixture drives a device run: `fixture` names it when the parameters hold several."""
+                           seed: int = 0, n_equilibration_passes: int = 0, output_dir=None,
+                           ensemble: Optional[str] = None) -> List[Dict]:
+    """A run series from read_run_params(...) output.  `system`: a system.System (load_system);
+    `tables`: _capi.Tables of the clex's basis set.  The ensemble follows the conditions, as the
+    choice of program does for the reference: "param_chem_pot" -> semi-grand canonical
+    (ccasm_clexmonte_semigrand_canonical), a composition -> canonical (ccasm_clexmonte_canonical).
+    One sampling fixture drives a device run: `fixture` names it when the parameters hold several."""
     from .run_series import run_series
     if params["N"] is None:
         raise RunParamsError("run series on the device need a diagonal transformation_matrix_to_supercell")
-    if "param_chem_pot" not in params["initial_conditions"]:
+    if ensemble is None:
+        ensemble = "semigrand_canonical" if "param_chem_pot" in params["initial_conditions"] else "canonical"
+    if ensemble == "semigrand_canonical" and "param_chem_pot" not in params["initial_conditions"]:
         raise RunParamsError("initial_conditions/param_chem_pot: required by the semi-grand canonical run series")
     names = sorted(params["fixtures"])
     if fixture is None:
@@ -210,4 +215,4 @@ def run_series_from_params(tables, system, params: Dict, fixture: Optional[str] 
                       n_equilibration_passes=n_equilibration_passes + fx["begin"], n_samples=fx["n_samples"],
                       sample_period=fx["sample_period"], seed=seed, dependent_runs=params["dependent_runs"],
                       with_corr=fx["with_corr"],
-                      output_params=RunDataOutputParams(output_dir=out_dir) if out_dir else None)
+                      output_params=RunDataOutputParams(output_dir=out_dir) if out_dir else None, ensemble=ensemble)

@@ -53,19 +53,64 @@ def conditions_path(initial: Dict, increment: Dict, n_states: int) -> List[Dict]
     return [make_incremented_values(initial, increment, k) for k in range(int(n_states))]
 
 
+def mol_composition(system: Dict, occupation, n_cells: int) -> np.ndarray:
+    """species per unit cell of an occupation in the reference's site order l = b n_cells + cell"""
+    occ = np.asarray(occupation)
+    out = np.zeros(int(system["n_species"]))
+    for b, species in enumerate(system["occ_to_species"]):
+        counts = np.bincount(occ[b * n_cells:(b + 1) * n_cells], minlength=len(species))
+        if len(counts) > len(species):
+            raise ValueError(f"occupation: occupant index {len(counts) - 1} on sublattice {b} with {len(species)} occupants")
+        for o, sp in enumerate(species):
+            out[sp] += counts[o] / n_cells
+    return out
+
+
+def check_canonical_conditions(system: Dict, initial: Dict, increment: Dict, occupation, N, tol: float = 1e-4) -> None:
+    """validate_state of the canonical calculator (CanonicalCalculator.cc:318-360): the
+    configuration's composition is the conditions'; and the path keeps it."""
+    for key in ("mol_composition", "param_composition"):
+        if key in increment and np.any(np.asarray(increment[key], dtype=float) != 0.0):
+            raise ValueError(f"run_series (canonical): conditions_increment/{key} must be zero "
+                             "(the path cannot change the composition of a configuration)")
+    if "param_chem_pot" in initial:
+        raise ValueError("run_series (canonical): param_chem_pot is a semi-grand canonical condition")
+    n_cells = int(np.prod(N if not np.isscalar(N) else (N, N, N)))
+    mol = mol_composition(system, occupation, n_cells)
+    axes = system["axes"]
+    if "mol_composition" in initial and np.abs(mol - np.asarray(initial["mol_composition"], dtype=float)).max() > tol:
+        raise ValueError(f"run_series (canonical): the initial occupation has mol_composition {mol.tolist()}, "
+                         f"the conditions {list(initial['mol_composition'])}")
+    if "param_composition" in initial:
+        param = np.asarray(axes["Rt"], dtype=float) @ (mol - np.asarray(axes["origin"], dtype=float))
+        if np.abs(param - np.asarray(initial["param_composition"], dtype=float)).max() > tol:
+            raise ValueError(f"run_series (canonical): the initial occupation has param_composition {param.tolist()}, "
+                             f"the conditions {list(initial['param_composition'])}")
+
+
 def run_series(tables: "_capi.Tables", N: Sequence[int], system: Dict, eci_index, eci_value,
                initial_conditions: Dict, conditions_increment: Dict, n_states: int, occupation: np.ndarray,
                n_equilibration_passes: int, n_samples: int, sample_period: int = 1, seed: int = 0,
                dependent_runs: bool = False, with_corr: bool = False,
-               output_params: Optional[RunDataOutputParams] = None, summary_dir=None) -> List[Dict]:
-    """Semi-grand canonical run series.  `system`: occ_to_species, sublat_to_asym, n_species,
-    axes {origin, Rt}.  Conditions: {"temperature": T, "param_chem_pot": [...]}.
+               output_params: Optional[RunDataOutputParams] = None, summary_dir=None,
+               ensemble: str = "semigrand_canonical") -> List[Dict]:
+    """Run series in the semi-grand canonical (default) or the canonical ensemble.  `system`:
+    occ_to_species, sublat_to_asym, n_species, axes {origin, Rt}.  Conditions: {"temperature": T,
+    "param_chem_pot": [...]}; canonical: {"temperature": T} plus optionally "mol_composition" /
+    "param_composition", which the initial occupation must have (CanonicalCalculator.cc:318-360)
+    and which the path may not change (parallel pair exchanges over the library's default swap
+    table conserve the composition).
     Returns one dict per state RUN BY THIS CALL: conditions, means of the sampled quantities,
     the analysis functions, acceptance rate, final occupation.  output_params.output_dir:
     completed_runs.json (read first: completed states are not run again); summary_dir
     (default: the same directory): summary.json."""
+    if ensemble not in ("semigrand_canonical", "canonical"):
+        raise ValueError(f"run_series: unknown ensemble {ensemble!r}")
+    canonical = ensemble == "canonical"
     path = conditions_path(initial_conditions, conditions_increment, n_states)
     axes = system["axes"]
+    if canonical:
+        check_canonical_conditions(system, initial_conditions, conditions_increment, occupation, N)
     completed = CompletedRuns(output_params or RunDataOutputParams())
     n_done = min(completed.read(), len(path))
     if summary_dir is None:
@@ -98,11 +143,22 @@ def run_series(tables: "_capi.Tables", N: Sequence[int], system: Dict, eci_index
         st.set_occupants(system["sublat_to_asym"], o2s, system["n_species"])
         sm = _capi.Sampler(st, n_samples, axes["origin"], axes["Rt"], with_corr=with_corr)
         for r, c in enumerate(conds):
+            if canonical:       # the potential is the formation energy: no exchange term, no mu . x
+                st.set_conditions(float(c["temperature"]), None, r)
+                continue
             mu = np.atleast_1d(c["param_chem_pot"])
             st.set_conditions(float(c["temperature"]),
                               semigrand_exchange_table(system["occ_to_species"], axes["Rt"], mu, system["n_species"]), r)
             sm.set_param_chem_pot(mu, r)
         return st, sm
+
+    def equilibrate(st, n_passes, run_seed) -> None:
+        if canonical:
+            st.canonical_set_swaps(st.canonical_default_swaps())
+            if n_passes > 0:
+                st.canonical_sweep(int(n_passes), seed=run_seed)
+        else:
+            st.sgc_sweep(int(n_passes), seed=run_seed, counters=False)
 
     def collect(st, sm, r, cond, counters, occ_initial=None, seconds=0.0) -> Dict:
         ser = sm.series(r)
@@ -128,8 +184,9 @@ def run_series(tables: "_capi.Tables", N: Sequence[int], system: Dict, eci_index
         st, sm = make_state(todo)
         for r in range(len(todo)):
             st.upload_occ(occupation, r)
-        st.sgc_sweep(int(n_equilibration_passes), seed=seed, counters=False)
-        cnt = sm.run(int(n_samples), int(sample_period), seed=seed, first_sweep=int(n_equilibration_passes))
+        equilibrate(st, n_equilibration_passes, seed)
+        cnt = sm.run(int(n_samples), int(sample_period), seed=seed, first_sweep=int(n_equilibration_passes),
+                     ensemble=ensemble)
         st.synchronize()
         dt = (time.perf_counter() - t0) / len(todo)
         results = [collect(st, sm, r, todo[r], cnt, seconds=dt) for r in range(len(todo))]
@@ -146,8 +203,9 @@ def run_series(tables: "_capi.Tables", N: Sequence[int], system: Dict, eci_index
         t0 = time.perf_counter()
         st, sm = make_state([cond])
         st.upload_occ(occ)
-        st.sgc_sweep(int(n_equilibration_passes), seed=seed + k, counters=False)
-        cnt = sm.run(int(n_samples), int(sample_period), seed=seed + k, first_sweep=int(n_equilibration_passes))
+        equilibrate(st, n_equilibration_passes, seed + k)
+        cnt = sm.run(int(n_samples), int(sample_period), seed=seed + k, first_sweep=int(n_equilibration_passes),
+                     ensemble=ensemble)
         st.synchronize()
         res = collect(st, sm, 0, cond, cnt, occ_initial=occ, seconds=time.perf_counter() - t0)
         occ = res["final_occupation"]

@@ -255,3 +255,119 @@ def test_run_series_from_params_maps_the_deck_onto_run_series(monkeypatch):
         run_series_from_params(None, system, read_run_params(two, _AXES))
     run_series_from_params(None, system, read_run_params(two, _AXES), fixture="second", output_dir="elsewhere")
     assert seen["output_params"].output_dir == "elsewhere"
+
+
+class _FakeState:
+    """Records the calls run_series makes (the device calls themselves: tests/test_gpu_sampler.py,
+    tests/test_gpu_canonical.py)."""
+    log = []
+
+    def __init__(self, tables, N, n_replicas=1):
+        self.N, self.n_replicas = N, n_replicas
+        self.occ = {}
+        _FakeState.log.append(("state", tuple(N), n_replicas))
+
+    def set_eci(self, i, v):
+        pass
+
+    def set_occupants(self, *a):
+        pass
+
+    def set_conditions(self, T, exch, r=0):
+        _FakeState.log.append(("conditions", r, float(T), exch is None))
+
+    def upload_occ(self, occ, r=0):
+        self.occ[r] = np.asarray(occ).copy()
+
+    def download_occ(self, r=0, dtype=np.int32):
+        return self.occ[r].astype(dtype)
+
+    def canonical_default_swaps(self):
+        return [(0, 0, (1, 0, 0))]
+
+    def canonical_set_swaps(self, swaps):
+        _FakeState.log.append(("swaps", len(swaps)))
+
+    def canonical_sweep(self, n, seed, first_sweep=0):
+        _FakeState.log.append(("canonical_sweep", n, seed))
+
+    def sgc_sweep(self, n, seed, counters=True):
+        _FakeState.log.append(("sgc_sweep", n, seed))
+
+    def synchronize(self):
+        pass
+
+    def close(self):
+        pass
+
+
+class _FakeSampler:
+    def __init__(self, st, n_samples, origin, Rt, with_corr=False):
+        self.st, self.n = st, n_samples
+
+    def set_param_chem_pot(self, mu, r):
+        _FakeState.log.append(("mu", r))
+
+    def run(self, n_samples, period, seed, first_sweep=0, ensemble="semigrand_canonical"):
+        from types import SimpleNamespace
+        _FakeState.log.append(("run", n_samples, period, seed, first_sweep, ensemble))
+        return [SimpleNamespace(n_attempt=100, n_accept=40) for _ in range(self.st.n_replicas)]
+
+    def series(self, r):
+        return {"potential_energy": np.linspace(-1.0, -1.1, self.n)}
+
+    def analysis(self, r):
+        return {"heat_capacity": 0.5}
+
+    def close(self):
+        pass
+
+
+def test_run_series_canonical_branch(monkeypatch, tmp_path):
+    """The canonical run series (BASELINE configs[0]: a temperature path at fixed composition):
+    conditions without an exchange term, the library's default swap table, pair-exchange
+    sweeps, the sampled run in the canonical ensemble; the composition conditions are checked
+    against the configuration and may not be incremented."""
+    import casmcode_clexmonte_b200.run_series as RS
+    monkeypatch.setattr(RS._capi, "State", _FakeState)
+    monkeypatch.setattr(RS._capi, "Sampler", _FakeSampler)
+    from types import SimpleNamespace
+    tables = SimpleNamespace(host=SimpleNamespace(max_occ=2))
+    system = dict(occ_to_species=[[0, 1]], sublat_to_asym=[0], n_species=2, species=["A", "B"],
+                  axes=dict(origin=[1.0, 0.0], Rt=[[0.0, 1.0]]))
+    N = (4, 4, 2)
+    occ = np.array([0, 1] * 16, dtype=np.int32)
+    init = {"temperature": 900.0, "mol_composition": [0.5, 0.5]}
+    inc = {"temperature": -300.0, "mol_composition": [0.0, 0.0]}
+    _FakeState.log = []
+    res = RS.run_series(tables, N, system, [0], [1.0], init, inc, 3, occ, n_equilibration_passes=5, n_samples=4,
+                        sample_period=2, seed=11, dependent_runs=True, ensemble="canonical",
+                        output_params=RS.RunDataOutputParams(output_dir=str(tmp_path)))
+    assert [r["conditions"]["temperature"] for r in res] == [900.0, 600.0, 300.0]
+    log = _FakeState.log
+    assert [e for e in log if e[0] == "conditions"] == [("conditions", 0, T, True) for T in (900.0, 600.0, 300.0)]
+    assert not [e for e in log if e[0] in ("mu", "sgc_sweep")]
+    assert [e for e in log if e[0] == "canonical_sweep"] == [("canonical_sweep", 5, 11 + k) for k in range(3)]
+    assert [e for e in log if e[0] == "run"] == [("run", 4, 2, 11 + k, 5, "canonical") for k in range(3)]
+    assert log.count(("swaps", 1)) == 3
+    assert (tmp_path / "summary.json").exists() and (tmp_path / "completed_runs.json").exists()
+    # independent runs: one state with a replica per temperature
+    _FakeState.log = []
+    RS.run_series(tables, N, system, [0], [1.0], init, inc, 3, occ, 5, 4, ensemble="canonical")
+    assert ("state", N, 3) in _FakeState.log and _FakeState.log.count(("swaps", 1)) == 1
+    # composition conditions
+    with pytest.raises(ValueError):
+        RS.run_series(tables, N, system, [0], [1.0], {"temperature": 900.0, "mol_composition": [0.75, 0.25]}, {}, 1, occ, 1, 1,
+                      ensemble="canonical")
+    with pytest.raises(ValueError):
+        RS.run_series(tables, N, system, [0], [1.0], init, {"mol_composition": [0.1, -0.1]}, 2, occ, 1, 1, ensemble="canonical")
+    with pytest.raises(ValueError):
+        RS.run_series(tables, N, system, [0], [1.0], {"temperature": 900.0, "param_chem_pot": [0.0]}, {}, 1, occ, 1, 1,
+                      ensemble="canonical")
+    RS.run_series(tables, N, system, [0], [1.0], {"temperature": 900.0, "param_composition": [0.5]}, {}, 1, occ, 1, 1,
+                  ensemble="canonical")
+    # the semi-grand branch is what it was
+    _FakeState.log = []
+    RS.run_series(tables, N, system, [0], [1.0], {"temperature": 900.0, "param_chem_pot": [0.1]}, {}, 1, occ, 5, 4)
+    assert ("sgc_sweep", 5, 0) in _FakeState.log and ("mu", 0) in _FakeState.log
+    assert ("run", 4, 1, 0, 5, "semigrand_canonical") in _FakeState.log
